@@ -1,0 +1,161 @@
+/*
+ * orbx.h -- C ABI of the B200-native ORB feature front end.
+ *
+ * This is the drop-in boundary for ONE path of yxqc/ORBSLAM2_with_quadrics:
+ * ORB_SLAM2::ORBextractor (reference include/ORBextractor.h:45-111,
+ * src/ORBextractor.cc:410-470 and :1043-1132).  Everything behind these entry
+ * points runs as hand-written sm_100a CUDA kernels; there is no CPU fallback.
+ * The OpenCV-typed C++ class that ORB-SLAM2 links against
+ * (orbslam2_with_quadrics_b200/cpp/ORBextractor.{h,cc}) and the Python mirror
+ * (orbslam2_with_quadrics_b200/extractor.py) are thin adapters over this header.
+ * INTEGRATION.md shows the reference-side change (CMakeLists.txt:57,76-82).
+ *
+ * Conventions: plain C, POD only, no exceptions cross the boundary.  Every
+ * function returns 0 (ORBX_OK) or a negative orbx_status.  A handle owns one
+ * CUDA stream plus its device and pinned-host buffers and, like the reference
+ * object (src/Frame.cc:78-81), is NOT re-entrant: use one handle per host
+ * thread; distinct handles run concurrently (stereo = two handles, two streams).
+ */
+#ifndef ORBX_H
+#define ORBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define ORBX_API __attribute__((visibility("default")))
+#else
+#define ORBX_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBX_MAX_LEVELS 16
+#define ORBX_EDGE_THRESHOLD 19 /* src/ORBextractor.cc:74 */
+
+typedef enum orbx_status {
+    ORBX_OK = 0,
+    ORBX_ERR_BAD_ARGS = -1,           /* null pointer, n > max_batch, non-positive sizes ...            */
+    ORBX_ERR_BAD_GEOMETRY = -2,       /* a level narrower than 62 px, aspect ratio with 0 root nodes,   */
+                                      /* or an image larger than 4096 px     */
+    ORBX_ERR_CUDA = -3,               /* a CUDA runtime call failed; see orbx_last_cuda_error()         */
+    ORBX_ERR_CANDIDATE_OVERFLOW = -4, /* more FAST corners than the candidate buffer holds              */
+    ORBX_ERR_NO_DEVICE = -5,          /* no CUDA device / device ordinal out of range                   */
+    ORBX_ERR_OUT_OF_MEMORY = -6,
+    ORBX_ERR_EMPTY_IMAGE = -7         /* orbx_extract*: w*h == 0; outputs untouched (:1046-1047)        */
+} orbx_status;
+
+/* The five constructor arguments of ORBextractor (src/ORBextractor.cc:410-414) + placement. */
+typedef struct orbx_config {
+    int nfeatures;
+    float scale_factor;
+    int nlevels;
+    int ini_th_fast;
+    int min_th_fast;
+    int device;           /* CUDA device ordinal                                                        */
+    int max_batch;        /* frames processed per launch sequence (>= 1)                                */
+    int download_pyramid; /* 1: copy the padded pyramid to pinned host memory on every extract, as the  */
+                          /*    public mvImagePyramid contract requires (read by src/Frame.cc:563-580); */
+                          /* 0: leave it in HBM (monocular / RGB-D callers never read it)               */
+    int candidate_divisor;/* per-level candidate capacity = level_pixels / divisor + 1024 (0 -> 8)      */
+    int reserved[7];
+} orbx_config;
+
+/* Same field order and size (28 bytes) as cv::KeyPoint. */
+typedef struct orbx_keypoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} orbx_keypoint;
+
+/* Result of one frame; pointers are library-owned pinned host memory, valid until the
+ * next extract call on the same handle.  desc is n x 32 bytes, row i <-> kps[i]
+ * (read by consumers as int32[8], src/ORBmatcher.cc:1649-1650). */
+typedef struct orbx_result {
+    int n;
+    int status; /* per-frame orbx_status */
+    const orbx_keypoint* kps;
+    const uint8_t* desc;
+} orbx_result;
+
+typedef struct orbx_handle orbx_handle;
+
+/* ORBextractor::ORBextractor (src/ORBextractor.cc:410-470). */
+ORBX_API int orbx_create(const orbx_config* cfg, orbx_handle** out);
+/* ~ORBextractor (include/ORBextractor.h:54). */
+ORBX_API int orbx_destroy(orbx_handle* h);
+
+/* ORBextractor::operator() (src/ORBextractor.cc:1043-1105) on one host image (CV_8UC1, any
+ * stride).  Blocks until the outputs are in host memory. */
+ORBX_API int orbx_extract(orbx_handle* h, const uint8_t* img, int width, int height, size_t stride, orbx_result* result);
+
+/* The same for n <= max_batch frames of identical size in one launch sequence. */
+ORBX_API int orbx_extract_batch(orbx_handle* h, int n, const uint8_t* const* imgs, int width, int height,
+                       const size_t* strides, orbx_result* results);
+
+/* Device-resident variant for roofline timing: n images already in HBM at
+ * d_imgs + i*frame_stride, row pitch `pitch`.  Only enqueues work on the handle's stream. */
+ORBX_API int orbx_extract_device(orbx_handle* h, int n, const uint8_t* d_imgs, int width, int height, size_t pitch,
+                        size_t frame_stride);
+/* Copies the results of the last orbx_extract_device to host and waits for them. */
+ORBX_API int orbx_fetch_results(orbx_handle* h, int n, orbx_result* results);
+
+/* Pinned host buffers callers may fill with frames so that H2D copies are asynchronous DMA. */
+ORBX_API int orbx_alloc_host(size_t bytes, void** out);
+ORBX_API int orbx_free_host(void* p);
+
+/* mvImagePyramid (include/ORBextractor.h:85): level `level` of frame `frame` of the last extract
+ * as a host-readable plane.  *image points at pixel (0,0) of the w x h level; the 19-pixel
+ * BORDER_REFLECT_101 frame around it is valid (src/ORBextractor.cc:1113-1128).  Needs
+ * download_pyramid = 1. */
+ORBX_API int orbx_pyramid_level(orbx_handle* h, int frame, int level, const uint8_t** image, int* width, int* height,
+                       size_t* step);
+
+/* GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+ * (include/ORBextractor.h:66-83): nlevels floats each, owned by the handle. */
+ORBX_API int orbx_scale_tables(orbx_handle* h, const float** scale, const float** inv_scale, const float** sigma2,
+                      const float** inv_sigma2);
+ORBX_API int orbx_get_levels(orbx_handle* h);                 /* GetLevels (:63)        */
+ORBX_API float orbx_get_scale_factor(orbx_handle* h);         /* GetScaleFactor (:66)   */
+/* mnFeaturesPerLevel (src/ORBextractor.cc:435-446) and umax (:454-469). */
+ORBX_API int orbx_level_quotas(orbx_handle* h, int* quotas /* nlevels */, int* umax16 /* 16 */);
+/* Level sizes for an input of width x height (src/ORBextractor.cc:1111-1112). */
+ORBX_API int orbx_level_sizes(orbx_handle* h, int width, int height, int* widths, int* heights);
+
+/* Intermediate results of the last extract, for stage-level parity tests. */
+typedef enum orbx_stage {
+    ORBX_STAGE_PYRAMID = 0,    /* padded plane, (h+38) x (w+38) bytes, step w+38                        */
+    ORBX_STAGE_CANDIDATES = 1, /* int32 (x, y, response) triples in the reference's push order, box     */
+                               /* coordinates (src/ORBextractor.cc:818-826)                             */
+    ORBX_STAGE_KEPT = 2,       /* int32 (x, y, response) triples after DistributeOctTree, level coords  */
+    ORBX_STAGE_ANGLES = 3,     /* float32 per kept keypoint (IC_Angle, :77-104)                          */
+    ORBX_STAGE_BLURRED = 4     /* blurred level, h x w bytes, step w (:1085-1086)                        */
+} orbx_stage;
+/* Writes up to cap bytes to out; *bytes receives the full size of the stage output. */
+ORBX_API int orbx_stage_dump(orbx_handle* h, int frame, int level, int stage, void* out, size_t cap, size_t* bytes);
+
+/* The handle's cudaStream_t (for event timing from the caller's side) and a blocking wait on it. */
+ORBX_API void* orbx_stream(orbx_handle* h);
+ORBX_API int orbx_synchronize(orbx_handle* h);
+
+/* Per-stage device time of the extract calls since the last reset (CUDA events on the handle's
+ * stream; enabling it adds event records between kernels).  names/ms arrays hold up to cap entries;
+ * returns the number of stages. */
+ORBX_API int orbx_stage_timing_enable(orbx_handle* h, int enable);
+ORBX_API int orbx_stage_timing_read(orbx_handle* h, int cap, const char** names, float* ms, int* launches);
+
+/* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+ORBX_API long long orbx_launch_count(orbx_handle* h);
+
+/* Algorithmic bytes per image of the whole path. */
+ORBX_API long long orbx_algorithmic_bytes(orbx_handle* h, int width, int height);
+
+ORBX_API const char* orbx_strerror(int status);
+ORBX_API const char* orbx_last_cuda_error(orbx_handle* h);
+ORBX_API const char* orbx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBX_H */

@@ -1,0 +1,102 @@
+"""ctypes binding of liborbx.so (include/orbx.h).  Fails loudly when the CUDA library is
+missing or cannot be loaded: there is no CPU fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "liborbx.so")
+
+ORBX_OK = 0
+ERR_BAD_ARGS, ERR_BAD_GEOMETRY, ERR_CUDA, ERR_CANDIDATE_OVERFLOW, ERR_NO_DEVICE, ERR_OOM, ERR_EMPTY_IMAGE = \
+    -1, -2, -3, -4, -5, -6, -7
+STAGE_PYRAMID, STAGE_CANDIDATES, STAGE_KEPT, STAGE_ANGLES, STAGE_BLURRED = range(5)
+
+# every symbol include/orbx.h declares (tests check the library exports exactly these)
+SYMBOLS = [
+    "orbx_create", "orbx_destroy", "orbx_extract", "orbx_extract_batch", "orbx_extract_device",
+    "orbx_fetch_results", "orbx_alloc_host", "orbx_free_host", "orbx_pyramid_level", "orbx_scale_tables",
+    "orbx_get_levels", "orbx_get_scale_factor", "orbx_level_quotas", "orbx_level_sizes", "orbx_stage_dump",
+    "orbx_stream", "orbx_synchronize", "orbx_stage_timing_enable", "orbx_stage_timing_read",
+    "orbx_launch_count", "orbx_algorithmic_bytes", "orbx_strerror", "orbx_last_cuda_error", "orbx_version",
+]
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+
+
+class OrbxConfig(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int),
+                ("ini_th_fast", C.c_int), ("min_th_fast", C.c_int), ("device", C.c_int),
+                ("max_batch", C.c_int), ("download_pyramid", C.c_int), ("candidate_divisor", C.c_int),
+                ("reserved", C.c_int * 7)]
+
+
+class OrbxResult(C.Structure):
+    _fields_ = [("n", C.c_int), ("status", C.c_int), ("kps", C.c_void_p), ("desc", C.c_void_p)]
+
+
+class OrbxError(RuntimeError):
+    def __init__(self, status: int, detail: str = ""):
+        self.status = status
+        msg = lib().orbx_strerror(status).decode() if _lib is not None else str(status)
+        super().__init__("orbx status %d: %s%s" % (status, msg, (" -- " + detail) if detail else ""))
+
+
+_lib = None
+
+
+def lib():
+    """Loads liborbx.so; raises (never falls back) if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "liborbx.so is not built (%s). Run `python -m orbslam2_with_quadrics_b200.build`; "
+            "this package has no CPU path." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i, sz = C.c_void_p, C.c_int, C.c_size_t
+    L.orbx_create.argtypes = [C.POINTER(OrbxConfig), C.POINTER(vp)]
+    L.orbx_destroy.argtypes = [vp]
+    L.orbx_extract.argtypes = [vp, vp, i, i, sz, C.POINTER(OrbxResult)]
+    L.orbx_extract_batch.argtypes = [vp, i, C.POINTER(vp), i, i, C.POINTER(sz), C.POINTER(OrbxResult)]
+    L.orbx_extract_device.argtypes = [vp, i, vp, i, i, sz, sz]
+    L.orbx_fetch_results.argtypes = [vp, i, C.POINTER(OrbxResult)]
+    L.orbx_alloc_host.argtypes = [sz, C.POINTER(vp)]
+    L.orbx_free_host.argtypes = [vp]
+    L.orbx_pyramid_level.argtypes = [vp, i, i, C.POINTER(vp), C.POINTER(i), C.POINTER(i), C.POINTER(sz)]
+    L.orbx_scale_tables.argtypes = [vp] + [C.POINTER(C.POINTER(C.c_float))] * 4
+    L.orbx_get_levels.argtypes = [vp]
+    L.orbx_get_scale_factor.argtypes = [vp]
+    L.orbx_get_scale_factor.restype = C.c_float
+    L.orbx_level_quotas.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
+    L.orbx_level_sizes.argtypes = [vp, i, i, C.POINTER(i), C.POINTER(i)]
+    L.orbx_stage_dump.argtypes = [vp, i, i, i, vp, sz, C.POINTER(sz)]
+    L.orbx_stream.argtypes = [vp]
+    L.orbx_stream.restype = vp
+    L.orbx_synchronize.argtypes = [vp]
+    L.orbx_stage_timing_enable.argtypes = [vp, i]
+    L.orbx_stage_timing_read.argtypes = [vp, i, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(i)]
+    L.orbx_launch_count.argtypes = [vp]
+    L.orbx_launch_count.restype = C.c_longlong
+    L.orbx_algorithmic_bytes.argtypes = [vp, i, i]
+    L.orbx_algorithmic_bytes.restype = C.c_longlong
+    L.orbx_strerror.argtypes = [i]
+    L.orbx_strerror.restype = C.c_char_p
+    L.orbx_last_cuda_error.argtypes = [vp]
+    L.orbx_last_cuda_error.restype = C.c_char_p
+    L.orbx_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def check(status: int, handle=None):
+    if status != ORBX_OK:
+        detail = ""
+        if handle is not None and status == ERR_CUDA:
+            detail = lib().orbx_last_cuda_error(handle).decode()
+        raise OrbxError(status, detail)

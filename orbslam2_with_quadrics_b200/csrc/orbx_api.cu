@@ -1,0 +1,664 @@
+// C-ABI layer of the B200 ORB front end (include/orbx.h): handle, plan, HBM/pinned buffers,
+// and the launch sequence that replaces ORB_SLAM2::ORBextractor::operator()
+// (reference src/ORBextractor.cc:1043-1105).  Host code only prepares tables and enqueues
+// kernels; every pixel, keypoint and descriptor is produced on the GPU (orbx_kernels.cu).
+#include <cuda_runtime.h>
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/orbx.h"
+#include "orbx_kernels.h"
+
+namespace {
+
+enum { ST_PYRAMID = 0, ST_FAST, ST_OCTREE, ST_ORIENT, ST_BLUR, ST_DESC, ST_COUNT };
+const char* kStageNames[ST_COUNT] = {"pyramid", "fast_cells", "octree", "orient", "blur", "descriptor"};
+const int kTimingRing = 64;
+
+template <typename T> T round_up(T v, T a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct orbx_handle {
+    orbx_config cfg;
+    int num_sms;
+    cudaStream_t stream;
+    std::string last_error;
+    long long launches;
+
+    // ctor tables (src/ORBextractor.cc:415-469)
+    float sf[ORBX_MAXL], inv_sf[ORBX_MAXL], sigma2[ORBX_MAXL], inv_sigma2[ORBX_MAXL];
+    int quotas[ORBX_MAXL];
+    int umax[16];
+
+    // geometry-dependent state
+    bool have_plan;
+    OrbxPlan plan;
+    std::vector<OrbxTap> taps;
+    OrbxPlan* d_plan;
+    OrbxTap* d_taps;
+    int in_pitch;
+    uint8_t *d_input, *d_pyr, *d_blur;
+    uint32_t *d_cand, *d_cand_sorted, *d_kept;
+    uint16_t* d_key_node;
+    uint2* d_cell_rec;
+    int* d_counters;             // [level_counts B*L][sorted_counts B*L][kept_counts B*L][status B]
+    float* d_angles;
+    float* d_out_kp;
+    uint8_t* d_out_desc;
+    // pinned host mirrors
+    int* h_counters;
+    float* h_out_kp;
+    uint8_t* h_out_desc;
+    uint8_t* h_pyr;
+    uint8_t* h_input;
+    int last_n;
+    bool pyramid_valid;
+
+    // stage timing
+    bool timing;
+    cudaEvent_t ev[kTimingRing][ST_COUNT + 1];
+    bool ev_created;
+    int ev_head, ev_pending;
+    double stage_ms[ST_COUNT];
+    int stage_launches[ST_COUNT];
+
+    int counters_count() const { return cfg.max_batch * (3 * plan.nlevels + 1); }
+    int* d_level_counts() const { return d_counters; }
+    int* d_sorted_counts() const { return d_counters + cfg.max_batch * plan.nlevels; }
+    int* d_kept_counts() const { return d_counters + 2 * cfg.max_batch * plan.nlevels; }
+    int* d_status() const { return d_counters + 3 * cfg.max_batch * plan.nlevels; }
+    const int* h_sorted_counts() const { return h_counters + cfg.max_batch * plan.nlevels; }
+    const int* h_kept_counts() const { return h_counters + 2 * cfg.max_batch * plan.nlevels; }
+    const int* h_status() const { return h_counters + 3 * cfg.max_batch * plan.nlevels; }
+};
+
+namespace {
+
+int cuda_fail(orbx_handle* h, cudaError_t e, const char* what) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    if (h) h->last_error = buf;
+    return e == cudaErrorMemoryAllocation ? ORBX_ERR_OUT_OF_MEMORY : ORBX_ERR_CUDA;
+}
+#define CK(h, call)                                                  \
+    do {                                                             \
+        cudaError_t e__ = (call);                                    \
+        if (e__ != cudaSuccess) return cuda_fail((h), e__, #call);   \
+    } while (0)
+
+// ORBextractor::ORBextractor (src/ORBextractor.cc:410-470), float/double semantics kept as written there.
+void build_ctor_tables(orbx_handle* h) {
+    const int n = h->cfg.nlevels;
+    const double scaleFactor = (double)h->cfg.scale_factor;          // member is double, argument float (.h:98)
+    h->sf[0] = 1.0f;
+    h->sigma2[0] = 1.0f;
+    for (int i = 1; i < n; ++i) {
+        h->sf[i] = (float)(h->sf[i - 1] * scaleFactor);
+        h->sigma2[i] = h->sf[i] * h->sf[i];
+    }
+    for (int i = 0; i < n; ++i) {
+        h->inv_sf[i] = 1.0f / h->sf[i];
+        h->inv_sigma2[i] = 1.0f / h->sigma2[i];
+    }
+    const float factor = (float)(1.0f / scaleFactor);
+    const float one_minus = 1 - factor;
+    const float denom = 1 - (float)pow((double)factor, (double)n);
+    float nDesired = (float)h->cfg.nfeatures * one_minus / denom;
+    int sum = 0;
+    for (int l = 0; l < n - 1; ++l) {
+        h->quotas[l] = (int)lrintf(nDesired);
+        sum += h->quotas[l];
+        nDesired *= factor;
+    }
+    h->quotas[n - 1] = h->cfg.nfeatures - sum > 0 ? h->cfg.nfeatures - sum : 0;
+    // umax (:454-469)
+    const int HP = 15;
+    const float half_diag = HP * sqrtf(2.f) / 2;
+    const int vmax = (int)floor((double)(half_diag + 1));
+    const int vmin = (int)ceil((double)half_diag);
+    const double hp2 = HP * HP;
+    for (int v = 0; v < 16; ++v) h->umax[v] = 0;
+    for (int v = 0; v <= vmax; ++v) h->umax[v] = (int)lrint(sqrt(hp2 - v * v));
+    for (int v = HP, v0 = 0; v >= vmin; --v) {
+        while (h->umax[v0] == h->umax[v0 + 1]) ++v0;
+        h->umax[v] = v0;
+        ++v0;
+    }
+}
+
+// cv::resize INTER_LINEAR 8U tap table for one axis
+void build_taps(std::vector<OrbxTap>& out, int ssize, int dsize) {
+    const double scale = (double)ssize / dsize;
+    for (int d = 0; d < dsize; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= s;
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+        long c1 = lrintf(f * 2048.f), c0 = lrintf((1.f - f) * 2048.f);
+        OrbxTap t;
+        t.ofs = s;
+        t.c0 = (short)(c0 > 32767 ? 32767 : c0);
+        t.c1 = (short)(c1 > 32767 ? 32767 : c1);
+        out.push_back(t);
+    }
+}
+
+void level_size(const orbx_handle* h, int w, int hgt, int l, int* lw, int* lh) {
+    const float scale = h->inv_sf[l];                                  // (:1111-1112)
+    *lw = (int)lrintf((float)w * scale);
+    *lh = (int)lrintf((float)hgt * scale);
+}
+
+int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>* taps) {
+    memset(P, 0, sizeof *P);
+    if (w <= 0 || hgt <= 0) return ORBX_ERR_BAD_ARGS;
+    if (w > 4096 || hgt > 4096) return ORBX_ERR_BAD_GEOMETRY;
+    const int n = h->cfg.nlevels;
+    P->nlevels = n;
+    P->width = w;
+    P->height = hgt;
+    P->ini_th = h->cfg.ini_th_fast;
+    P->min_th = h->cfg.min_th_fast;
+    const int div = h->cfg.candidate_divisor > 0 ? h->cfg.candidate_divisor : 8;
+    long long off = 0;
+    int cells = 0, cand = 0, kept = 0, tiles = 0;
+    taps->clear();
+    for (int l = 0; l < n; ++l) {
+        OrbxLevel& L = P->lv[l];
+        level_size(h, w, hgt, l, &L.w, &L.h);
+        if (L.w < 62 || L.h < 62) return ORBX_ERR_BAD_GEOMETRY;     // nCols/nRows would be 0 (App. B-7b)
+        L.pitch = round_up(ORBX_XO + L.w + ORBX_EDGE, 64);
+        L.rows = L.h + 2 * ORBX_EDGE;
+        L.plane_off = off;
+        off += round_up((long long)L.pitch * L.rows, 256LL);
+        // cell grid (:771-787)
+        L.maxBX = L.w - ORBX_EDGE + 3;
+        L.maxBY = L.h - ORBX_EDGE + 3;
+        const float width = (float)(L.maxBX - ORBX_BOX), height = (float)(L.maxBY - ORBX_BOX);
+        const float W = 30;
+        const int nCols = (int)(width / W), nRows = (int)(height / W);
+        L.wCell = (int)ceilf(width / nCols);
+        L.hCell = (int)ceilf(height / nRows);
+        L.nColsV = 0;
+        for (int j = 0; j < nCols; ++j)
+            if (ORBX_BOX + j * L.wCell < L.maxBX - 6) ++L.nColsV;     // (:803)
+        L.nRowsV = 0;
+        for (int i = 0; i < nRows; ++i)
+            if (ORBX_BOX + i * L.hCell < L.maxBY - 3) ++L.nRowsV;     // (:794)
+        L.cell_base = cells;
+        cells += L.nColsV * L.nRowsV;
+        const int cw = (L.wCell + 6 < (int)width) ? L.wCell + 6 : (int)width;
+        const int ch = (L.hCell + 6 < (int)height) ? L.hCell + 6 : (int)height;
+        if (cw > P->max_cell_w) P->max_cell_w = cw;
+        if (ch > P->max_cell_h) P->max_cell_h = ch;
+        L.cand_off = cand;
+        L.cand_cap = (int)((long long)L.w * L.h / div) + 1024;
+        if (L.cand_cap > (1 << 24) - 1) L.cand_cap = (1 << 24) - 1;
+        cand += round_up(L.cand_cap, 64);
+        L.quota = h->quotas[l];
+        // DistributeOctTree roots (:543-545)
+        const float ratio = (float)(L.maxBX - ORBX_BOX) / (L.maxBY - ORBX_BOX);
+        L.nIni = (int)roundf(ratio);
+        if (L.nIni < 1 || L.nIni > ORBX_MAX_ROOTS) return ORBX_ERR_BAD_GEOMETRY;   // division by zero in the reference (App. B-7)
+        L.hX = (float)(L.maxBX - ORBX_BOX) / L.nIni;
+        L.kept_off = kept;
+        L.kept_cap = L.quota + 4 * L.nIni + 8;
+        kept += L.kept_cap;
+        if (L.kept_cap > P->node_cap) P->node_cap = L.kept_cap;
+        L.scale = h->sf[l];
+        L.kp_size = (float)(int)(31 * h->sf[l]);                         // (:837)
+        if (l > 0) {
+            L.xtab_off = (int)taps->size();
+            build_taps(*taps, P->lv[l - 1].w, L.w);
+            L.ytab_off = (int)taps->size();
+            build_taps(*taps, P->lv[l - 1].h, L.h);
+        }
+        L.blur_tile_base = tiles;
+        L.blur_tiles_x = (L.w + 127) / 128;
+        tiles += L.blur_tiles_x * ((L.h + 15) / 16);
+    }
+    if (P->node_cap < 64) P->node_cap = 64;
+    if (P->node_cap > 60000) return ORBX_ERR_BAD_ARGS;
+    P->node_cap = round_up(P->node_cap, 32);
+    if (P->max_cell_w < 7) P->max_cell_w = 7;
+    if (P->max_cell_h < 7) P->max_cell_h = 7;
+    P->cells_per_frame = cells;
+    P->cand_per_frame = cand;
+    P->kept_per_frame = kept;
+    P->blur_tiles_per_frame = tiles;
+    P->slab_bytes = off;
+    // cv::fastAtan2 coefficients as OpenCV forms them: float products (App. A-4)
+    const float scale = (float)(180.0 / 3.1415926535897932384626433832795);
+    P->atan_p1 = 0.9997878412794807f * scale;
+    P->atan_p3 = -0.3258083974640975f * scale;
+    P->atan_p5 = 0.1555786518463281f * scale;
+    P->atan_p7 = -0.04432655554792128f * scale;
+    P->factor_pi = (float)(3.1415926535897932384626433832795 / 180.f);  // (:107)
+    for (int i = 0; i < 16; ++i) P->umax[i] = h->umax[i];
+    if (orbx::fast_smem_bytes(*P) > 200 * 1024 || orbx::octree_smem_bytes(*P) > 200 * 1024) return ORBX_ERR_BAD_GEOMETRY;
+    return ORBX_OK;
+}
+
+void free_geometry(orbx_handle* h) {
+    cudaFree(h->d_plan); cudaFree(h->d_taps); cudaFree(h->d_input); cudaFree(h->d_pyr); cudaFree(h->d_blur);
+    cudaFree(h->d_cand); cudaFree(h->d_cand_sorted); cudaFree(h->d_kept); cudaFree(h->d_key_node);
+    cudaFree(h->d_cell_rec); cudaFree(h->d_counters); cudaFree(h->d_angles); cudaFree(h->d_out_kp);
+    cudaFree(h->d_out_desc);
+    cudaFreeHost(h->h_counters); cudaFreeHost(h->h_out_kp); cudaFreeHost(h->h_out_desc); cudaFreeHost(h->h_pyr);
+    cudaFreeHost(h->h_input);
+    h->d_plan = 0; h->d_taps = 0; h->d_input = h->d_pyr = h->d_blur = 0;
+    h->d_cand = h->d_cand_sorted = h->d_kept = 0; h->d_key_node = 0; h->d_cell_rec = 0; h->d_counters = 0;
+    h->d_angles = 0; h->d_out_kp = 0; h->d_out_desc = 0;
+    h->h_counters = 0; h->h_out_kp = 0; h->h_out_desc = 0; h->h_pyr = 0; h->h_input = 0;
+    h->have_plan = false;
+    h->pyramid_valid = false;
+    h->last_n = 0;
+}
+
+int ensure_geometry(orbx_handle* h, int w, int hgt) {
+    if (h->have_plan && h->plan.width == w && h->plan.height == hgt) return ORBX_OK;
+    OrbxPlan P;
+    std::vector<OrbxTap> taps;
+    int rc = build_plan(h, w, hgt, &P, &taps);
+    if (rc != ORBX_OK) return rc;
+    CK(h, cudaStreamSynchronize(h->stream));
+    free_geometry(h);
+    h->plan = P;
+    h->taps.swap(taps);
+    const size_t B = (size_t)h->cfg.max_batch;
+    h->in_pitch = round_up(w, 16);
+    CK(h, cudaMalloc(&h->d_plan, sizeof(OrbxPlan)));
+    CK(h, cudaMalloc(&h->d_taps, sizeof(OrbxTap) * (h->taps.size() + 1)));
+    CK(h, cudaMalloc(&h->d_input, B * hgt * h->in_pitch));
+    CK(h, cudaMalloc(&h->d_pyr, B * P.slab_bytes));
+    CK(h, cudaMalloc(&h->d_blur, B * P.slab_bytes));
+    CK(h, cudaMalloc(&h->d_cand, B * P.cand_per_frame * 4));
+    CK(h, cudaMalloc(&h->d_cand_sorted, B * P.cand_per_frame * 4));
+    CK(h, cudaMalloc(&h->d_key_node, B * P.cand_per_frame * 2));
+    CK(h, cudaMalloc(&h->d_cell_rec, B * P.cells_per_frame * sizeof(uint2)));
+    CK(h, cudaMalloc(&h->d_counters, sizeof(int) * h->counters_count()));
+    CK(h, cudaMalloc(&h->d_kept, B * P.kept_per_frame * 4));
+    CK(h, cudaMalloc(&h->d_angles, B * P.kept_per_frame * 4));
+    CK(h, cudaMalloc(&h->d_out_kp, B * P.kept_per_frame * sizeof(orbx_keypoint)));
+    CK(h, cudaMalloc(&h->d_out_desc, B * P.kept_per_frame * 32));
+    CK(h, cudaMallocHost(&h->h_counters, sizeof(int) * h->counters_count()));
+    CK(h, cudaMallocHost(&h->h_out_kp, B * P.kept_per_frame * sizeof(orbx_keypoint)));
+    CK(h, cudaMallocHost(&h->h_out_desc, B * P.kept_per_frame * 32));
+    CK(h, cudaMallocHost(&h->h_input, B * hgt * h->in_pitch));
+    if (h->cfg.download_pyramid) CK(h, cudaMallocHost(&h->h_pyr, B * P.slab_bytes));
+    CK(h, cudaMemcpyAsync(h->d_plan, &h->plan, sizeof(OrbxPlan), cudaMemcpyHostToDevice, h->stream));
+    if (!h->taps.empty())
+        CK(h, cudaMemcpyAsync(h->d_taps, h->taps.data(), sizeof(OrbxTap) * h->taps.size(), cudaMemcpyHostToDevice, h->stream));
+    // border bytes of the blurred planes are never written by blur_kernel; keep them defined
+    CK(h, cudaMemsetAsync(h->d_blur, 0, B * P.slab_bytes, h->stream));
+    CK(h, cudaMemsetAsync(h->d_pyr, 0, B * P.slab_bytes, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->have_plan = true;
+    return ORBX_OK;
+}
+
+void timing_collect(orbx_handle* h, int upto_pending) {
+    // accumulate the oldest `upto_pending` recorded event sets (their work has to be complete)
+    while (upto_pending-- > 0 && h->ev_pending > 0) {
+        const int idx = (h->ev_head - h->ev_pending + kTimingRing * 2) % kTimingRing;
+        cudaEventSynchronize(h->ev[idx][ST_COUNT]);
+        for (int s = 0; s < ST_COUNT; ++s) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, h->ev[idx][s], h->ev[idx][s + 1]) == cudaSuccess) h->stage_ms[s] += ms;
+        }
+        --h->ev_pending;
+    }
+}
+
+int enqueue_pipeline(orbx_handle* h, int n, const uint8_t* d_imgs, size_t pitch, size_t frame_stride) {
+    const OrbxPlan& P = h->plan;
+    cudaStream_t st = h->stream;
+    cudaEvent_t* ev = 0;
+    if (h->timing) {
+        if (h->ev_pending == kTimingRing) timing_collect(h, 1);
+        ev = h->ev[h->ev_head];
+    }
+    CK(h, cudaMemsetAsync(h->d_counters, 0, sizeof(int) * h->counters_count(), st));
+    if (ev) CK(h, cudaEventRecord(ev[ST_PYRAMID], st));
+    for (int l = 0; l < P.nlevels; ++l)
+        orbx::launch_pyr_level(h->d_plan, P, l, n, d_imgs, pitch, frame_stride, h->d_pyr, h->d_taps, st);
+    if (ev) CK(h, cudaEventRecord(ev[ST_FAST], st));
+    CK(h, orbx::launch_fast(h->d_plan, P, n, h->num_sms, h->d_pyr, h->d_cand, h->d_cell_rec, h->d_level_counts(), h->d_status(), st));
+    if (ev) CK(h, cudaEventRecord(ev[ST_OCTREE], st));
+    CK(h, orbx::launch_octree(h->d_plan, P, n, h->d_cand, h->d_cell_rec, h->d_cand_sorted, h->d_key_node,
+                              h->d_sorted_counts(), h->d_kept, h->d_kept_counts(), h->d_status(), st));
+    if (ev) CK(h, cudaEventRecord(ev[ST_ORIENT], st));
+    orbx::launch_orient(h->d_plan, P, n, h->num_sms, h->d_pyr, h->d_kept, h->d_kept_counts(), h->d_angles, st);
+    if (ev) CK(h, cudaEventRecord(ev[ST_BLUR], st));
+    orbx::launch_blur(h->d_plan, P, n, h->num_sms, h->d_pyr, h->d_blur, st);
+    if (ev) CK(h, cudaEventRecord(ev[ST_DESC], st));
+    orbx::launch_desc(h->d_plan, P, n, h->num_sms, h->d_blur, h->d_kept, h->d_kept_counts(), h->d_angles, h->d_out_kp, h->d_out_desc, st);
+    if (ev) {
+        CK(h, cudaEventRecord(ev[ST_COUNT], st));
+        h->ev_head = (h->ev_head + 1) % kTimingRing;
+        ++h->ev_pending;
+        h->stage_launches[ST_PYRAMID] += P.nlevels;
+        for (int s = ST_FAST; s < ST_COUNT; ++s) h->stage_launches[s] += 1;
+    }
+    h->launches += P.nlevels + 5;
+    CK(h, cudaGetLastError());
+    h->last_n = n;
+    h->pyramid_valid = false;
+    return ORBX_OK;
+}
+
+int fetch(orbx_handle* h, int n, orbx_result* results) {
+    const OrbxPlan& P = h->plan;
+    cudaStream_t st = h->stream;
+    const size_t kpf = (size_t)P.kept_per_frame;
+    CK(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int) * h->counters_count(), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h->h_out_kp, h->d_out_kp, n * kpf * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h->h_out_desc, h->d_out_desc, n * kpf * 32, cudaMemcpyDeviceToHost, st));
+    if (h->cfg.download_pyramid)
+        CK(h, cudaMemcpyAsync(h->h_pyr, h->d_pyr, (size_t)n * P.slab_bytes, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    h->pyramid_valid = h->cfg.download_pyramid != 0;
+    int rc = ORBX_OK;
+    for (int f = 0; f < n; ++f) {
+        int total = 0;
+        for (int l = 0; l < P.nlevels; ++l) total += h->h_kept_counts()[f * P.nlevels + l];
+        const int dev = h->h_status()[f];
+        int fs = ORBX_OK;
+        if (dev & ORBX_DEV_CAND_OVERFLOW) fs = ORBX_ERR_CANDIDATE_OVERFLOW;
+        else if (dev & ORBX_DEV_NODE_OVERFLOW) fs = ORBX_ERR_CUDA;
+        if (fs != ORBX_OK) { rc = fs; total = 0; }
+        if (results) {
+            results[f].n = total;
+            results[f].status = fs;
+            results[f].kps = reinterpret_cast<const orbx_keypoint*>(h->h_out_kp) + f * kpf;
+            results[f].desc = h->h_out_desc + f * kpf * 32;
+        }
+    }
+    if (rc == ORBX_ERR_CUDA) h->last_error = "octree node capacity exceeded (internal invariant broken)";
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* orbx_version(void) { return "orbx-b200 0.1 (sm_100a)"; }
+
+const char* orbx_strerror(int s) {
+    switch (s) {
+        case ORBX_OK: return "ok";
+        case ORBX_ERR_BAD_ARGS: return "bad arguments";
+        case ORBX_ERR_BAD_GEOMETRY: return "unsupported image geometry (level < 62 px, > 4096 px, or degenerate aspect ratio)";
+        case ORBX_ERR_CUDA: return "CUDA error";
+        case ORBX_ERR_CANDIDATE_OVERFLOW: return "FAST candidate buffer overflow (lower candidate_divisor)";
+        case ORBX_ERR_NO_DEVICE: return "no usable CUDA device";
+        case ORBX_ERR_OUT_OF_MEMORY: return "out of device or pinned memory";
+        case ORBX_ERR_EMPTY_IMAGE: return "empty image: outputs untouched";
+        default: return "unknown status";
+    }
+}
+
+const char* orbx_last_cuda_error(orbx_handle* h) { return h ? h->last_error.c_str() : ""; }
+
+int orbx_create(const orbx_config* cfg, orbx_handle** out) {
+    if (!cfg || !out) return ORBX_ERR_BAD_ARGS;
+    *out = 0;
+    if (cfg->nlevels < 1 || cfg->nlevels > ORBX_MAXL || cfg->nfeatures < 1 || !(cfg->scale_factor > 1.0f) ||
+        cfg->ini_th_fast < 1 || cfg->min_th_fast < 1 || cfg->ini_th_fast > 254 || cfg->min_th_fast > 254 ||
+        cfg->max_batch < 1)
+        return ORBX_ERR_BAD_ARGS;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev) {
+        cudaGetLastError();
+        return ORBX_ERR_NO_DEVICE;
+    }
+    orbx_handle* h = new orbx_handle();
+    h->cfg = *cfg;
+    h->launches = 0;
+    h->have_plan = false;
+    h->d_plan = 0; h->d_taps = 0; h->d_input = h->d_pyr = h->d_blur = 0;
+    h->d_cand = h->d_cand_sorted = h->d_kept = 0; h->d_key_node = 0; h->d_cell_rec = 0; h->d_counters = 0;
+    h->d_angles = 0; h->d_out_kp = 0; h->d_out_desc = 0;
+    h->h_counters = 0; h->h_out_kp = 0; h->h_out_desc = 0; h->h_pyr = 0; h->h_input = 0;
+    h->last_n = 0; h->pyramid_valid = false;
+    h->timing = false; h->ev_created = false; h->ev_head = 0; h->ev_pending = 0;
+    memset(h->stage_ms, 0, sizeof h->stage_ms);
+    memset(h->stage_launches, 0, sizeof h->stage_launches);
+    h->stream = 0;
+    cudaError_t e = cudaSetDevice(cfg->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    if (e != cudaSuccess) {
+        delete h;
+        return ORBX_ERR_CUDA;
+    }
+    build_ctor_tables(h);
+    *out = h;
+    return ORBX_OK;
+}
+
+int orbx_destroy(orbx_handle* h) {
+    if (!h) return ORBX_ERR_BAD_ARGS;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    free_geometry(h);
+    if (h->ev_created)
+        for (int i = 0; i < kTimingRing; ++i)
+            for (int s = 0; s <= ST_COUNT; ++s) cudaEventDestroy(h->ev[i][s]);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return ORBX_OK;
+}
+
+int orbx_extract_device(orbx_handle* h, int n, const uint8_t* d_imgs, int width, int height, size_t pitch,
+                        size_t frame_stride) {
+    if (!h || !d_imgs || n < 1 || n > h->cfg.max_batch || pitch < (size_t)width) return ORBX_ERR_BAD_ARGS;
+    CK(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_geometry(h, width, height);
+    if (rc != ORBX_OK) return rc;
+    return enqueue_pipeline(h, n, d_imgs, pitch, frame_stride);
+}
+
+int orbx_fetch_results(orbx_handle* h, int n, orbx_result* results) {
+    if (!h || !h->have_plan || n < 1 || n > h->last_n) return ORBX_ERR_BAD_ARGS;
+    CK(h, cudaSetDevice(h->cfg.device));
+    return fetch(h, n, results);
+}
+
+int orbx_extract_batch(orbx_handle* h, int n, const uint8_t* const* imgs, int width, int height,
+                       const size_t* strides, orbx_result* results) {
+    if (!h || !imgs || !results || n < 1 || n > h->cfg.max_batch) return ORBX_ERR_BAD_ARGS;
+    if (width == 0 || height == 0) return ORBX_ERR_EMPTY_IMAGE;       // (:1046-1047)
+    if (width < 0 || height < 0) return ORBX_ERR_BAD_ARGS;
+    for (int i = 0; i < n; ++i)
+        if (!imgs[i] || (strides && strides[i] < (size_t)width)) return ORBX_ERR_BAD_ARGS;
+    CK(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_geometry(h, width, height);
+    if (rc != ORBX_OK) return rc;
+    const size_t fbytes = (size_t)height * h->in_pitch;
+    for (int i = 0; i < n; ++i) {
+        const size_t stride = strides ? strides[i] : (size_t)width;
+        cudaPointerAttributes attr;
+        bool pinned = cudaPointerGetAttributes(&attr, imgs[i]) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (!pinned) cudaGetLastError();
+        const uint8_t* src = imgs[i];
+        size_t spitch = stride;
+        if (!pinned) {     // pageable caller memory: stage through the handle's pinned buffer
+            uint8_t* stg = h->h_input + i * fbytes;
+            for (int y = 0; y < height; ++y) memcpy(stg + (size_t)y * h->in_pitch, imgs[i] + (size_t)y * stride, (size_t)width);
+            src = stg;
+            spitch = (size_t)h->in_pitch;
+        }
+        CK(h, cudaMemcpy2DAsync(h->d_input + i * fbytes, (size_t)h->in_pitch, src, spitch, (size_t)width, (size_t)height,
+                                cudaMemcpyHostToDevice, h->stream));
+    }
+    rc = enqueue_pipeline(h, n, h->d_input, (size_t)h->in_pitch, fbytes);
+    if (rc != ORBX_OK) return rc;
+    return fetch(h, n, results);
+}
+
+int orbx_extract(orbx_handle* h, const uint8_t* img, int width, int height, size_t stride, orbx_result* result) {
+    const uint8_t* imgs[1] = {img};
+    const size_t strides[1] = {stride};
+    return orbx_extract_batch(h, 1, imgs, width, height, strides, result);
+}
+
+int orbx_alloc_host(size_t bytes, void** out) {
+    if (!out) return ORBX_ERR_BAD_ARGS;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) { cudaGetLastError(); *out = 0; return ORBX_ERR_OUT_OF_MEMORY; }
+    return ORBX_OK;
+}
+
+int orbx_free_host(void* p) {
+    if (cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return ORBX_ERR_CUDA; }
+    return ORBX_OK;
+}
+
+int orbx_pyramid_level(orbx_handle* h, int frame, int level, const uint8_t** image, int* width, int* height, size_t* step) {
+    if (!h || !h->have_plan || !h->pyramid_valid || frame < 0 || frame >= h->last_n || level < 0 || level >= h->plan.nlevels)
+        return ORBX_ERR_BAD_ARGS;
+    const OrbxLevel& L = h->plan.lv[level];
+    if (image) *image = h->h_pyr + (size_t)frame * h->plan.slab_bytes + L.plane_off + (size_t)ORBX_EDGE * L.pitch + ORBX_XO;
+    if (width) *width = L.w;
+    if (height) *height = L.h;
+    if (step) *step = (size_t)L.pitch;
+    return ORBX_OK;
+}
+
+int orbx_scale_tables(orbx_handle* h, const float** scale, const float** inv_scale, const float** sigma2, const float** inv_sigma2) {
+    if (!h) return ORBX_ERR_BAD_ARGS;
+    if (scale) *scale = h->sf;
+    if (inv_scale) *inv_scale = h->inv_sf;
+    if (sigma2) *sigma2 = h->sigma2;
+    if (inv_sigma2) *inv_sigma2 = h->inv_sigma2;
+    return ORBX_OK;
+}
+
+int orbx_get_levels(orbx_handle* h) { return h ? h->cfg.nlevels : ORBX_ERR_BAD_ARGS; }
+float orbx_get_scale_factor(orbx_handle* h) { return h ? (float)(double)h->cfg.scale_factor : 0.f; }
+
+int orbx_level_quotas(orbx_handle* h, int* quotas, int* umax16) {
+    if (!h) return ORBX_ERR_BAD_ARGS;
+    if (quotas) for (int i = 0; i < h->cfg.nlevels; ++i) quotas[i] = h->quotas[i];
+    if (umax16) for (int i = 0; i < 16; ++i) umax16[i] = h->umax[i];
+    return ORBX_OK;
+}
+
+int orbx_level_sizes(orbx_handle* h, int width, int height, int* widths, int* heights) {
+    if (!h || !widths || !heights) return ORBX_ERR_BAD_ARGS;
+    for (int l = 0; l < h->cfg.nlevels; ++l) level_size(h, width, height, l, &widths[l], &heights[l]);
+    return ORBX_OK;
+}
+
+int orbx_stage_dump(orbx_handle* h, int frame, int level, int stage, void* out, size_t cap, size_t* bytes) {
+    if (!h || !h->have_plan || frame < 0 || frame >= h->last_n || level < 0 || level >= h->plan.nlevels || !bytes)
+        return ORBX_ERR_BAD_ARGS;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    const OrbxPlan& P = h->plan;
+    const OrbxLevel& L = P.lv[level];
+    const int nl = P.nlevels;
+    int counts[2];
+    CK(h, cudaMemcpy(&counts[0], h->d_sorted_counts() + frame * nl + level, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(&counts[1], h->d_kept_counts() + frame * nl + level, sizeof(int), cudaMemcpyDeviceToHost));
+    switch (stage) {
+        case ORBX_STAGE_PYRAMID: {
+            const size_t wp = (size_t)L.w + 2 * ORBX_EDGE;
+            *bytes = wp * L.rows;
+            if (out && cap >= *bytes)
+                CK(h, cudaMemcpy2D(out, wp, h->d_pyr + (size_t)frame * P.slab_bytes + L.plane_off + (ORBX_XO - ORBX_EDGE), L.pitch, wp, L.rows, cudaMemcpyDeviceToHost));
+            return ORBX_OK;
+        }
+        case ORBX_STAGE_BLURRED: {
+            *bytes = (size_t)L.w * L.h;
+            if (out && cap >= *bytes)
+                CK(h, cudaMemcpy2D(out, L.w, h->d_blur + (size_t)frame * P.slab_bytes + L.plane_off + (size_t)ORBX_EDGE * L.pitch + ORBX_XO, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+            return ORBX_OK;
+        }
+        case ORBX_STAGE_CANDIDATES:
+        case ORBX_STAGE_KEPT: {
+            const bool isc = stage == ORBX_STAGE_CANDIDATES;
+            const int n = isc ? counts[0] : counts[1];
+            *bytes = (size_t)n * 12;
+            if (out && cap >= *bytes && n > 0) {
+                std::vector<uint32_t> tmp((size_t)n);
+                const uint32_t* src = isc ? h->d_cand_sorted + (size_t)frame * P.cand_per_frame + L.cand_off
+                                          : h->d_kept + (size_t)frame * P.kept_per_frame + L.kept_off;
+                CK(h, cudaMemcpy(tmp.data(), src, (size_t)n * 4, cudaMemcpyDeviceToHost));
+                int32_t* o = (int32_t*)out;
+                for (int i = 0; i < n; ++i) { o[3 * i] = ORBX_PX(tmp[i]); o[3 * i + 1] = ORBX_PY(tmp[i]); o[3 * i + 2] = ORBX_PR(tmp[i]); }
+            }
+            return ORBX_OK;
+        }
+        case ORBX_STAGE_ANGLES: {
+            const int n = counts[1];
+            *bytes = (size_t)n * 4;
+            if (out && cap >= *bytes && n > 0)
+                CK(h, cudaMemcpy(out, h->d_angles + (size_t)frame * P.kept_per_frame + L.kept_off, (size_t)n * 4, cudaMemcpyDeviceToHost));
+            return ORBX_OK;
+        }
+        default: return ORBX_ERR_BAD_ARGS;
+    }
+}
+
+void* orbx_stream(orbx_handle* h) { return h ? (void*)h->stream : 0; }
+
+int orbx_synchronize(orbx_handle* h) {
+    if (!h) return ORBX_ERR_BAD_ARGS;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+int orbx_stage_timing_enable(orbx_handle* h, int enable) {
+    if (!h) return ORBX_ERR_BAD_ARGS;
+    CK(h, cudaSetDevice(h->cfg.device));
+    if (enable && !h->ev_created) {
+        for (int i = 0; i < kTimingRing; ++i)
+            for (int s = 0; s <= ST_COUNT; ++s) CK(h, cudaEventCreate(&h->ev[i][s]));
+        h->ev_created = true;
+    }
+    if (h->ev_pending) timing_collect(h, h->ev_pending);
+    h->timing = enable != 0;
+    memset(h->stage_ms, 0, sizeof h->stage_ms);
+    memset(h->stage_launches, 0, sizeof h->stage_launches);
+    return ORBX_OK;
+}
+
+int orbx_stage_timing_read(orbx_handle* h, int cap, const char** names, float* ms, int* launches) {
+    if (!h) return ORBX_ERR_BAD_ARGS;
+    if (h->ev_pending) timing_collect(h, h->ev_pending);
+    for (int s = 0; s < ST_COUNT && s < cap; ++s) {
+        if (names) names[s] = kStageNames[s];
+        if (ms) ms[s] = (float)h->stage_ms[s];
+        if (launches) launches[s] = h->stage_launches[s];
+    }
+    return ST_COUNT;
+}
+
+long long orbx_launch_count(orbx_handle* h) { return h ? h->launches : 0; }
+
+// B_alg = sum_l [A_max(l-1,0) + P_l] + 3 * sum_l A_l + nfeatures * 1321   
+long long orbx_algorithmic_bytes(orbx_handle* h, int width, int height) {
+    if (!h) return ORBX_ERR_BAD_ARGS;
+    long long total = 0, prevA = 0;
+    for (int l = 0; l < h->cfg.nlevels; ++l) {
+        int lw, lh;
+        level_size(h, width, height, l, &lw, &lh);
+        const long long A = (long long)lw * lh, Pl = (long long)(lw + 38) * (lh + 38);
+        total += (l == 0 ? A : prevA) + Pl + 3 * A;
+        prevA = A;
+    }
+    return total + (long long)h->cfg.nfeatures * (749 + 512 + 32 + 28);
+}
+
+}  // extern "C"

@@ -1,0 +1,892 @@
+// Hand-written sm_100a kernels for ORB_SLAM2::ORBextractor::operator().
+//
+// One kernel per stage of the reference path (src/ORBextractor.cc), every launch covers
+// ALL frames of a batch with a persistent / grid-stride loop:
+//   pyr_level_kernel      ComputePyramid           (:1107-1132)  resize + REFLECT_101 border
+//   fast_cells_kernel     ComputeKeyPointsOctTree  (:765-829)    per-cell FAST-9 + NMS + retry
+//   octree_kernel         DistributeOctTree        (:539-763)    quadtree split, exact order
+//   orient_kernel         IC_Angle                 (:77-104)     intensity centroid + fastAtan2
+//   blur_kernel           GaussianBlur 7x7 s=2     (:1086)       separable fixed point
+//   desc_kernel           computeOrbDescriptor     (:108-147)    rotated BRIEF, packed stores
+// No stage is a dense contraction: everything is integer/byte work bounded by HBM/L2 and
+// instruction issue, so there is no tensor-core code here by design.
+//
+// Exactness rules: integer stages are bit-exact restatements of the
+// OpenCV 4.x fixed-point arithmetic; float stages use __f*_rn intrinsics so nothing is
+// contracted into FMAs.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "orbx_kernels.h"
+
+namespace orbx {
+
+static __constant__ signed char c_pattern[1024] = {
+#include "orb_pattern_31.inc"
+};
+
+__device__ __forceinline__ int reflect_clamp(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return max(0, min(i, n - 1));
+}
+
+__device__ __forceinline__ const uint8_t* level_px(const uint8_t* slab, const OrbxLevel& L, int x, int y) {
+    return slab + L.plane_off + (size_t)(y + ORBX_EDGE) * L.pitch + ORBX_XO + x;
+}
+
+// =====================================================================================
+// ComputePyramid: every padded pixel is produced directly as f(reflect(x), reflect(y)), so
+// the border needs no second pass (copyMakeBorder of the just-resized level, :1122).
+// Level 0 copies the input (:1127); level l > 0 is the 11-bit fixed-point bilinear
+// resize of level l-1 (cv::resize INTER_LINEAR 8U).  4 pixels / thread,
+// one aligned 32-bit store.
+// =====================================================================================
+template <bool L0>
+__global__ void __launch_bounds__(256) pyr_level_kernel(const OrbxPlan* __restrict__ plan, int l,
+                                                        const uint8_t* __restrict__ imgs, size_t img_pitch,
+                                                        size_t img_frame_stride, uint8_t* __restrict__ pyr,
+                                                        const OrbxTap* __restrict__ taps) {
+    const OrbxLevel& L = plan->lv[l];
+    const int w = L.w, h = L.h;
+    const int frame = blockIdx.z;
+    const int c = 12 + (blockIdx.x * 32 + threadIdx.x) * 4;        // plane column, multiple of 4
+    const int row = blockIdx.y * 8 + threadIdx.y;                  // plane row
+    if (row >= L.rows || c >= ORBX_XO + w + ORBX_EDGE) return;
+    uint8_t* slab = pyr + (size_t)frame * plan->slab_bytes;
+    const int dy = reflect_clamp(row - ORBX_EDGE, h);
+    uint32_t out = 0;
+    if (L0) {
+        const uint8_t* src = imgs + (size_t)frame * img_frame_stride + (size_t)dy * img_pitch;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int dx = reflect_clamp(c + i - ORBX_XO, w);
+            out |= (uint32_t)__ldg(src + dx) << (8 * i);
+        }
+    } else {
+        const OrbxLevel& S = plan->lv[l - 1];
+        const OrbxTap ty = taps[L.ytab_off + dy];
+        const int sy1 = min(ty.ofs + 1, S.h - 1);
+        const uint8_t* r0 = level_px(slab, S, 0, ty.ofs);
+        const uint8_t* r1 = level_px(slab, S, 0, sy1);
+        const int b0 = ty.c0, b1 = ty.c1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int dx = reflect_clamp(c + i - ORBX_XO, w);
+            const OrbxTap tx = taps[L.xtab_off + dx];
+            const int sx1 = min(tx.ofs + 1, S.w - 1);
+            const int a0 = tx.c0, a1 = tx.c1;
+            const int H0 = (int)r0[tx.ofs] * a0 + (int)r0[sx1] * a1;
+            const int H1 = (int)r1[tx.ofs] * a0 + (int)r1[sx1] * a1;
+            int v = (((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2;
+            v = min(max(v, 0), 255);
+            out |= (uint32_t)v << (8 * i);
+        }
+    }
+    *reinterpret_cast<uint32_t*>(slab + L.plane_off + (size_t)row * L.pitch + c) = out;
+}
+
+// =====================================================================================
+// FAST-9/16 per 30-px cell (cv::FAST(window, t, true)), one warp per cell.
+//   phase 1  every pixel of the window interior: opposite-pair pre-test, survivors queued
+//   phase 2  queued pixels: 16-bit bright/dark ring masks, circular run-of-9 test, exact
+//            score A-1 (A = max over the 16 arcs of the min signed difference)
+//   phase 3  3x3 non-max suppression inside the window (frame scores 0), ordered compaction
+// The iniThFAST pass is repeated with minThFAST iff it produced no keypoint (:812).  All
+// compaction is by ballot/popc in row-major order, so a cell's list is already in cv::FAST's
+// output order; cells are put in reference order by the octree kernel's prologue.
+// =====================================================================================
+__device__ __forceinline__ bool run9(uint32_t m) {
+    uint32_t x = m | (m << 16);
+    uint32_t y = x & (x >> 1);
+    y &= y >> 2;
+    y &= y >> 4;
+    y &= x >> 8;
+    return (y & 0xffffu) != 0;
+}
+
+__device__ __forceinline__ int fast_score(const uint8_t* __restrict__ p, int pitch, int t) {
+    const int v = p[0];
+    int q[16];
+    q[0] = p[3 * pitch];       q[1] = p[3 * pitch + 1];   q[2] = p[2 * pitch + 2];   q[3] = p[pitch + 3];
+    q[4] = p[3];               q[5] = p[-pitch + 3];      q[6] = p[-2 * pitch + 2];  q[7] = p[-3 * pitch + 1];
+    q[8] = p[-3 * pitch];      q[9] = p[-3 * pitch - 1];  q[10] = p[-2 * pitch - 2]; q[11] = p[-pitch - 3];
+    q[12] = p[-3];             q[13] = p[pitch - 3];      q[14] = p[2 * pitch - 2];  q[15] = p[3 * pitch - 1];
+    uint32_t bright = 0, dark = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        bright |= (uint32_t)(q[k] > v + t) << k;
+        dark |= (uint32_t)(q[k] < v - t) << k;
+    }
+    if (!run9(bright) && !run9(dark)) return 0;
+    // z_k = (q_k - v, v - q_k) as s16x2; arc score = min over 9 consecutive, both signs at once
+    uint32_t z[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int e = q[k] - v;
+        z[k] = __byte_perm((uint32_t)e, (uint32_t)(-e), 0x5410);
+    }
+    uint32_t m3[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m3[k] = __vimin3_s16x2(z[k], z[(k + 1) & 15], z[(k + 2) & 15]);
+    uint32_t best = 0x80008000u;                       // (-32768, -32768)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t m9 = __vimin3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+        best = __vmaxs2(best, m9);
+    }
+    const int A = max((int)(short)(best & 0xffffu), (int)(short)(best >> 16));
+    return A - 1;                                      // A > t >= 1 for a corner
+}
+
+__global__ void __launch_bounds__(ORBX_FAST_WARPS * 32)
+fast_cells_kernel(const OrbxPlan* __restrict__ plan, const uint8_t* __restrict__ pyr, int nframes,
+                  uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec, int* __restrict__ level_counts,
+                  int* __restrict__ status) {
+    extern __shared__ uint32_t fast_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int SP = (plan->max_cell_w + 3) & ~3;                       // score-map pitch (bytes)
+    const int score_words = SP * plan->max_cell_h / 4;
+    const int queue_words = (plan->max_cell_w - 6) * (plan->max_cell_h - 6);
+    uint32_t* wbase = fast_smem + (size_t)warp * (score_words + queue_words);
+    uint8_t* sc = reinterpret_cast<uint8_t*>(wbase);
+    uint32_t* queue = wbase + score_words;
+    const int nlevels = plan->nlevels;
+    const int cpf = plan->cells_per_frame;
+    const long long total = (long long)nframes * cpf;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    for (long long item = (long long)blockIdx.x * ORBX_FAST_WARPS + warp; item < total;
+         item += (long long)gridDim.x * ORBX_FAST_WARPS) {
+        const int frame = (int)(item / cpf);
+        const int c = (int)(item - (long long)frame * cpf);
+        int l = 0;
+        while (l + 1 < nlevels && c >= plan->lv[l + 1].cell_base) ++l;
+        const OrbxLevel& L = plan->lv[l];
+        const int ci = (c - L.cell_base) / L.nColsV;
+        const int cj = (c - L.cell_base) - ci * L.nColsV;
+        const int iniX = ORBX_BOX + cj * L.wCell, iniY = ORBX_BOX + ci * L.hCell;
+        const int ww = min(iniX + L.wCell + 6, L.maxBX) - iniX;
+        const int wh = min(iniY + L.hCell + 6, L.maxBY) - iniY;
+        const int pitch = L.pitch;
+        const uint8_t* win = level_px(pyr + (size_t)frame * plan->slab_bytes, L, iniX, iniY);
+        int count = 0;
+        if (ww >= 7 && wh >= 7) {
+            for (int pass = 0; pass < 2 && count == 0; ++pass) {
+                const int t = pass == 0 ? plan->ini_th : plan->min_th;
+                for (int i = lane; i < score_words; i += 32) wbase[i] = 0;
+                // ---- phase 1: pre-test, queue survivors in row-major order
+                int qn = 0;
+                for (int y = 3; y < wh - 3; ++y) {
+                    const uint8_t* row = win + (size_t)y * pitch;
+                    for (int x0 = 3; x0 < ww - 3; x0 += 32) {
+                        const int x = x0 + lane;
+                        bool pass1 = false;
+                        if (x < ww - 3) {
+                            const uint8_t* p = row + x;
+                            const int v = p[0];
+                            // every 9-arc holds one pixel of each opposite pair (k, k+8)
+                            const bool in0 = abs((int)p[3 * pitch] - v) <= t && abs((int)p[-3 * pitch] - v) <= t;
+                            const bool in4 = abs((int)p[3] - v) <= t && abs((int)p[-3] - v) <= t;
+                            pass1 = !(in0 || in4);
+                        }
+                        const uint32_t b = __ballot_sync(0xffffffffu, pass1);
+                        if (pass1) queue[qn + __popc(b & lt_mask)] = (uint32_t)x | ((uint32_t)y << 12);
+                        qn += __popc(b);
+                    }
+                }
+                __syncwarp();
+                // ---- phase 2: exact corner test + score; corners compacted in place, scores to the map
+                int cn = 0;
+                for (int i0 = 0; i0 < qn; i0 += 32) {
+                    const int i = i0 + lane;
+                    int s = 0;
+                    uint32_t e = 0;
+                    if (i < qn) {
+                        e = queue[i];
+                        s = fast_score(win + (size_t)(e >> 12) * pitch + (e & 0xfffu), pitch, t);
+                    }
+                    const uint32_t b = __ballot_sync(0xffffffffu, s > 0);
+                    if (s > 0) {
+                        sc[(e >> 12) * SP + (e & 0xfffu)] = (uint8_t)s;
+                        queue[cn + __popc(b & lt_mask)] = e | ((uint32_t)s << 24);
+                    }
+                    cn += __popc(b);
+                }
+                __syncwarp();
+                // ---- phase 3: strict 3x3 NMS against the score map (window frame is 0)
+                for (int i0 = 0; i0 < cn; i0 += 32) {
+                    const int i = i0 + lane;
+                    bool keep = false;
+                    uint32_t e = 0;
+                    if (i < cn) {
+                        e = queue[i];
+                        const int s = (int)(e >> 24);
+                        const uint8_t* m = sc + ((e >> 12) & 0xfffu) * SP + (e & 0xfffu);
+                        keep = s > m[-1] && s > m[1] && s > m[-SP - 1] && s > m[-SP] && s > m[-SP + 1] &&
+                               s > m[SP - 1] && s > m[SP] && s > m[SP + 1];
+                    }
+                    const uint32_t b = __ballot_sync(0xffffffffu, keep);
+                    if (keep) queue[count + __popc(b & lt_mask)] = e;
+                    count += __popc(b);
+                }
+                __syncwarp();
+            }
+        }
+        // ---- emit: claim a contiguous block of the level's candidate region
+        int base = 0;
+        if (count > 0) {
+            if (lane == 0) base = atomicAdd(&level_counts[frame * nlevels + l], count);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + count > L.cand_cap) {
+                if (lane == 0) atomicOr(&status[frame], ORBX_DEV_CAND_OVERFLOW);
+                count = 0;
+            }
+        }
+        uint32_t* dst = cand + (size_t)frame * plan->cand_per_frame + L.cand_off + base;
+        const int ox = cj * L.wCell, oy = ci * L.hCell;                    // (:822-823)
+        for (int i = lane; i < count; i += 32) {
+            const uint32_t e = queue[i];
+            dst[i] = ORBX_PACK((e & 0xfffu) + ox, ((e >> 12) & 0xfffu) + oy, e >> 24);
+        }
+        if (lane == 0) cell_rec[item] = make_uint2((uint32_t)base, (uint32_t)count);
+        __syncwarp();
+    }
+}
+
+// =====================================================================================
+// DistributeOctTree (:539-763) + DivideNode (:481-537), one CTA per (frame, level).
+//
+// The reference keeps a std::list of nodes; every new child is push_front'ed, so the list
+// is always in descending creation order and the final output order is the list order.
+// Each pass expands a set of nodes in a processing order:
+//   phase A (:606-665)  every multi-key node, in list order;
+//   phase B (:676-737)  multi-key nodes sorted by (key count, creation sequence)
+//                       descending (canonical rule B-1), stopping right after the
+//                       expansion that brings the list to >= N nodes (:730).
+// With the list stored as an array in list order, "creation sequence descending" is
+// "array index ascending", the children of the r-th processed node land in front of
+// those of the (r-1)-th, and survivors keep their relative order behind all children:
+// every pass is counting (smem atomics per key), one sort (phase B), prefix sums and a
+// scatter.  Keys stay in HBM/L2 as packed (x, y, response) plus a 16-bit node id.
+// =====================================================================================
+__device__ __forceinline__ int block_excl_scan(int v, int* total, int* s_warp) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const int w = lane < (ORBX_OT_THREADS / 32) ? s_warp[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    const int res = inc - v + s_warp[wid];
+    *total = s_warp[32];
+    __syncthreads();
+    return res;
+}
+
+struct Rect4 {
+    short ulx, urx, uly, bry;
+};
+
+__global__ void __launch_bounds__(ORBX_OT_THREADS, 2)
+octree_kernel(const OrbxPlan* __restrict__ plan, int nframes, const uint32_t* __restrict__ cand,
+              const uint2* __restrict__ cell_rec, uint32_t* __restrict__ cand_sorted,
+              uint16_t* __restrict__ key_node, int* __restrict__ sorted_counts, uint32_t* __restrict__ kept,
+              int* __restrict__ kept_counts, int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char ot_smem[];
+    __shared__ int s_warp[33];
+    __shared__ int s_misc[4];
+    const int tid = threadIdx.x;
+    const int T = ORBX_OT_THREADS;
+    const int l = blockIdx.x / nframes, frame = blockIdx.x - l * nframes;     // big levels first
+    const OrbxLevel& L = plan->lv[l];
+    const int CAP = plan->node_cap;
+    int SORTN = 1;
+    while (SORTN < CAP) SORTN <<= 1;
+    // ---- shared-memory carve-up
+    unsigned char* sp = ot_smem;
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(sp); sp += (size_t)SORTN * 8;
+    Rect4* rect0 = reinterpret_cast<Rect4*>(sp); sp += (size_t)CAP * 8;
+    Rect4* rect1 = reinterpret_cast<Rect4*>(sp); sp += (size_t)CAP * 8;
+    int* cnt0 = reinterpret_cast<int*>(sp); sp += (size_t)CAP * 4;
+    int* cnt1 = reinterpret_cast<int*>(sp); sp += (size_t)CAP * 4;
+    int* cc = reinterpret_cast<int*>(sp); sp += (size_t)CAP * 16;          // child key counts [node][4]
+    int* cp = reinterpret_cast<int*>(sp); sp += (size_t)CAP * 16;          // child positions  [node][4]
+    int* procrank = reinterpret_cast<int*>(sp); sp += (size_t)CAP * 4;     // node -> processing rank or -1
+    int* proc = reinterpret_cast<int*>(sp); sp += (size_t)CAP * 4;         // rank -> node
+    int* ne_incl = reinterpret_cast<int*>(sp); sp += (size_t)CAP * 4;      // inclusive sum of non-empty children by rank
+    int* surv_pos = reinterpret_cast<int*>(sp); sp += (size_t)CAP * 4;     // node -> new index if it survives
+
+    const size_t cbase = (size_t)frame * plan->cand_per_frame + L.cand_off;
+    const uint32_t* in = cand + cbase;
+    uint32_t* keys = cand_sorted + cbase;
+    uint16_t* knode = key_node + cbase;
+
+    // ---- prologue: put the per-cell blocks into the reference's cell order (:789-826)
+    const int ncell = L.nRowsV * L.nColsV;
+    const uint2* rec = cell_rec + (size_t)frame * plan->cells_per_frame + L.cell_base;
+    int M = 0;
+    for (int b0 = 0; b0 < ncell; b0 += T) {
+        const int c = b0 + tid;
+        const uint2 r = c < ncell ? rec[c] : make_uint2(0, 0);
+        int tot;
+        const int e = block_excl_scan((int)r.y, &tot, s_warp);
+        for (uint32_t i = 0; i < r.y; ++i) keys[M + e + i] = in[r.x + i];
+        M += tot;
+    }
+    if (tid == 0) sorted_counts[frame * plan->nlevels + l] = M;
+    __syncthreads();
+
+    // ---- roots (:543-585)
+    const int N = L.quota;
+    const int nIni = L.nIni;
+    const float hX = L.hX;
+    const int boxH = L.maxBY - ORBX_BOX;
+    int* root_map = cp;
+    for (int i = tid; i < nIni; i += T) {
+        Rect4 r;
+        r.ulx = (short)(int)__fmul_rn(hX, (float)i);
+        r.urx = (short)(int)__fmul_rn(hX, (float)(i + 1));
+        r.uly = 0;
+        r.bry = (short)boxH;
+        rect0[i] = r;
+        cnt0[i] = 0;
+    }
+    __syncthreads();
+    for (int k = tid; k < M; k += T) {
+        int r = (int)__fdiv_rn((float)ORBX_PX(keys[k]), hX);                 // (:569) truncation
+        r = min(r, nIni - 1);
+        knode[k] = (uint16_t)r;
+        atomicAdd(&cnt0[r], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int n = 0;
+        for (int i = 0; i < nIni; ++i) {
+            if (cnt0[i] > 0) {
+                root_map[i] = n;
+                rect1[n] = rect0[i];
+                cnt1[n] = cnt0[i];
+                ++n;
+            } else {
+                root_map[i] = -1;
+            }
+        }
+        s_misc[0] = n;
+    }
+    __syncthreads();
+    int n_nodes = s_misc[0];
+    for (int k = tid; k < M; k += T) knode[k] = (uint16_t)root_map[knode[k]];
+    __syncthreads();
+
+    Rect4* rc = rect1; Rect4* rn = rect0;
+    int* cntc = cnt1; int* cntn = cnt0;
+    bool phaseB = false;
+    bool failed = false;
+
+    while (true) {
+        const int S0 = n_nodes;
+        for (int i = tid; i < S0 * 4; i += T) cc[i] = 0;
+        if (tid == 0) { s_misc[1] = 0; s_misc[2] = 0x7fffffff; }
+        __syncthreads();
+        // ---- count keys per child quadrant (DivideNode :510-526)
+        for (int k = tid; k < M; k += T) {
+            const int nd = knode[k];
+            if (cntc[nd] > 1) {
+                const Rect4 r = rc[nd];
+                const int mx = r.ulx + ((r.urx - r.ulx + 1) >> 1);       // ceil(float(d)/2) (:483-484)
+                const int my = r.uly + ((r.bry - r.uly + 1) >> 1);
+                const uint32_t p = keys[k];
+                const int q = (ORBX_PX(p) < mx ? 0 : 1) + (ORBX_PY(p) < my ? 0 : 2);
+                atomicAdd(&cc[nd * 4 + q], 1);
+            }
+        }
+        __syncthreads();
+        // ---- processing order
+        int E = 0;
+        if (!phaseB) {
+            for (int b0 = 0; b0 < S0; b0 += T) {
+                const int i = b0 + tid;
+                const int f = (i < S0 && cntc[i] > 1) ? 1 : 0;
+                int tot;
+                const int e = block_excl_scan(f, &tot, s_warp);
+                if (i < S0) procrank[i] = f ? E + e : -1;
+                if (f) proc[E + e] = i;
+                E += tot;
+            }
+        } else {
+            for (int i = tid; i < SORTN; i += T) {
+                unsigned long long key = 0;
+                if (i < S0 && cntc[i] > 1) key = ((unsigned long long)(uint32_t)cntc[i] << 32) | (uint32_t)(0xffffffffu - (uint32_t)i);
+                skey[i] = key;
+                if (i < S0) procrank[i] = -1;
+            }
+            __syncthreads();
+            for (int k2 = 2; k2 <= SORTN; k2 <<= 1) {                     // bitonic sort, descending
+                for (int j = k2 >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < SORTN; i += T) {
+                        const int ixj = i ^ j;
+                        if (ixj > i) {
+                            const unsigned long long a = skey[i], b = skey[ixj];
+                            const bool desc = (i & k2) == 0;
+                            if (desc ? (a < b) : (a > b)) { skey[i] = b; skey[ixj] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            int e_local = 0;
+            for (int r = tid; r < S0; r += T) {
+                const unsigned long long key = skey[r];
+                if (key != 0) {
+                    const int i = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffu));
+                    proc[r] = i;
+                    procrank[i] = r;
+                    ++e_local;
+                }
+            }
+            atomicAdd(&s_misc[1], e_local);
+            __syncthreads();
+            E = s_misc[1];
+            __syncthreads();
+            if (tid == 0) s_misc[1] = 0;
+        }
+        __syncthreads();
+        // ---- list size after each expansion; phase B stops at the first size >= N (:730)
+        {
+            int carry = 0;
+            for (int b0 = 0; b0 < E; b0 += T) {
+                const int r = b0 + tid;
+                int ne = 0;
+                if (r < E) {
+                    const int i = proc[r];
+                    ne = (cc[i * 4] > 0) + (cc[i * 4 + 1] > 0) + (cc[i * 4 + 2] > 0) + (cc[i * 4 + 3] > 0);
+                }
+                int tot;
+                const int e = block_excl_scan(ne, &tot, s_warp);
+                if (r < E) {
+                    const int incl = carry + e + ne;
+                    ne_incl[r] = incl;
+                    if (phaseB && S0 + incl - (r + 1) >= N) atomicMin(&s_misc[2], r + 1);
+                }
+                carry += tot;
+            }
+        }
+        __syncthreads();
+        const int P = min(E, s_misc[2]);
+        const int C = P > 0 ? ne_incl[P - 1] : 0;
+        // ---- survivors keep their order behind all new children
+        int S1 = C;
+        for (int b0 = 0; b0 < S0; b0 += T) {
+            const int i = b0 + tid;
+            int f = 0;
+            if (i < S0) {
+                const int pr = procrank[i];
+                f = (pr >= 0 && pr < P) ? 0 : 1;
+            }
+            int tot;
+            const int e = block_excl_scan(f, &tot, s_warp);
+            if (i < S0) surv_pos[i] = f ? S1 + e : -1;
+            S1 += tot;
+        }
+        if (S1 > CAP) { failed = true; break; }
+        // ---- children: the r-th processed node's block sits in front of the (r-1)-th's; inside a
+        //      block the order is n4, n3, n2, n1 (push_front of n1..n4, :621-660)
+        int nexp = 0;
+        for (int r = tid; r < P; r += T) {
+            const int i = proc[r];
+            const Rect4 pr = rc[i];
+            const int mx = pr.ulx + ((pr.urx - pr.ulx + 1) >> 1);
+            const int my = pr.uly + ((pr.bry - pr.uly + 1) >> 1);
+            int pos = C - ne_incl[r];
+#pragma unroll
+            for (int q = 3; q >= 0; --q) {
+                const int kc = cc[i * 4 + q];
+                if (kc > 0) {
+                    Rect4 ch;
+                    ch.ulx = (short)((q & 1) ? mx : pr.ulx);
+                    ch.urx = (short)((q & 1) ? pr.urx : mx);
+                    ch.uly = (short)((q & 2) ? my : pr.uly);
+                    ch.bry = (short)((q & 2) ? pr.bry : my);
+                    rn[pos] = ch;
+                    cntn[pos] = kc;
+                    cp[i * 4 + q] = pos;
+                    nexp += kc > 1;
+                    ++pos;
+                } else {
+                    cp[i * 4 + q] = -1;
+                }
+            }
+        }
+        if (nexp) atomicAdd(&s_misc[1], nexp);
+        for (int i = tid; i < S0; i += T) {
+            const int sp2 = surv_pos[i];
+            if (sp2 >= 0) { rn[sp2] = rc[i]; cntn[sp2] = cntc[i]; }
+        }
+        __syncthreads();
+        // ---- move keys to their new nodes
+        for (int k = tid; k < M; k += T) {
+            const int nd = knode[k];
+            const int pr = procrank[nd];
+            if (pr >= 0 && pr < P) {
+                const Rect4 r = rc[nd];
+                const int mx = r.ulx + ((r.urx - r.ulx + 1) >> 1);
+                const int my = r.uly + ((r.bry - r.uly + 1) >> 1);
+                const uint32_t p = keys[k];
+                const int q = (ORBX_PX(p) < mx ? 0 : 1) + (ORBX_PY(p) < my ? 0 : 2);
+                knode[k] = (uint16_t)cp[nd * 4 + q];
+            } else {
+                knode[k] = (uint16_t)surv_pos[nd];
+            }
+        }
+        const int nToExpand = s_misc[1];
+        __syncthreads();
+        { Rect4* t = rc; rc = rn; rn = t; }
+        { int* t = cntc; cntc = cntn; cntn = t; }
+        n_nodes = S1;
+        if (S1 >= N || S1 == S0) break;                                   // (:669, :734)
+        if (!phaseB && S1 + 3 * nToExpand > N) phaseB = true;             // (:673)
+    }
+
+    // ---- best key per node: max response, first in list order wins (:741-760)
+    int* best = cc;
+    if (failed) {
+        if (tid == 0) { atomicOr(&status[frame], ORBX_DEV_NODE_OVERFLOW); kept_counts[frame * plan->nlevels + l] = 0; }
+        return;
+    }
+    for (int i = tid; i < n_nodes; i += T) best[i] = 0;
+    __syncthreads();
+    for (int k = tid; k < M; k += T)
+        atomicMax(reinterpret_cast<unsigned int*>(&best[knode[k]]),
+                  ((uint32_t)ORBX_PR(keys[k]) << 24) | (0xffffffu - (uint32_t)k));
+    __syncthreads();
+    const int out_n = min(n_nodes, L.kept_cap);
+    uint32_t* out = kept + (size_t)frame * plan->kept_per_frame + L.kept_off;
+    for (int i = tid; i < out_n; i += T) {
+        const uint32_t k = 0xffffffu - ((uint32_t)best[i] & 0xffffffu);
+        const uint32_t p = keys[k];
+        out[i] = ORBX_PACK(ORBX_PX(p) + ORBX_BOX, ORBX_PY(p) + ORBX_BOX, ORBX_PR(p));      // (:843-844)
+    }
+    if (tid == 0) {
+        kept_counts[frame * plan->nlevels + l] = out_n;
+        if (n_nodes > L.kept_cap) atomicOr(&status[frame], ORBX_DEV_NODE_OVERFLOW);
+    }
+}
+
+// =====================================================================================
+// IC_Angle (:77-104): intensity centroid over the umax disc of the UN-blurred level, one warp
+// per keypoint (lane = column u), then cv::fastAtan2's polynomial without FMA (App. A-4).
+// =====================================================================================
+__device__ __forceinline__ float fast_atan2_deg(float y, float x, const OrbxPlan* plan) {
+    const float eps = 2.2204460492503131e-16f;                    // (float)DBL_EPSILON
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a;
+    if (ax >= ay) {
+        const float c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        const float c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(plan->atan_p7, c2), plan->atan_p5), c2), plan->atan_p3), c2), plan->atan_p1), c);
+    } else {
+        const float c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        const float c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(plan->atan_p7, c2), plan->atan_p5), c2), plan->atan_p3), c2), plan->atan_p1), c));
+    }
+    if (x < 0.f) a = __fsub_rn(180.f, a);
+    if (y < 0.f) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__device__ __forceinline__ int level_of_slot(const OrbxPlan* plan, int s) {
+    int l = 0;
+    while (l + 1 < plan->nlevels && s >= plan->lv[l + 1].kept_off) ++l;
+    return l;
+}
+
+__global__ void __launch_bounds__(256) orient_kernel(const OrbxPlan* __restrict__ plan, int nframes,
+                                                     const uint8_t* __restrict__ pyr,
+                                                     const uint32_t* __restrict__ kept,
+                                                     const int* __restrict__ kept_counts,
+                                                     float* __restrict__ angles) {
+    const int lane = threadIdx.x & 31;
+    const int kpf = plan->kept_per_frame;
+    const long long total = (long long)nframes * kpf;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long it = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < total; it += nwarps) {
+        const int frame = (int)(it / kpf);
+        const int s = (int)(it - (long long)frame * kpf);
+        const int l = level_of_slot(plan, s);
+        const OrbxLevel& L = plan->lv[l];
+        if (s - L.kept_off >= kept_counts[frame * plan->nlevels + l]) continue;
+        const uint32_t p = kept[it];
+        const uint8_t* center = level_px(pyr + (size_t)frame * plan->slab_bytes, L, ORBX_PX(p), ORBX_PY(p));
+        const int u = lane - 15;
+        int m10 = 0, m01 = 0;
+        if (lane < 31) {
+            const int au = abs(u);
+            for (int v = -15; v <= 15; ++v) {
+                if (au <= plan->umax[abs(v)]) {
+                    const int val = center[v * L.pitch + u];
+                    m10 += u * val;
+                    m01 += v * val;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        }
+        if (lane == 0) angles[it] = fast_atan2_deg((float)m01, (float)m10, plan);
+    }
+}
+
+// =====================================================================================
+// GaussianBlur 7x7 sigma 2 (:1086): separable 8.8 fixed point [18,34,48,56,48,34,18]/256
+// (SURVEY App. A-2).  The padded plane's REFLECT_101 border is exactly the blur's own border
+// mode on the border-less clone, so taps simply read the plane.  128x16 output tile per
+// CTA: source tile and 16-bit row sums staged in shared memory, 4 pixels per 32-bit store.
+// =====================================================================================
+#define BL_TW 128
+#define BL_TH 16
+__global__ void __launch_bounds__(256) blur_kernel(const OrbxPlan* __restrict__ plan, int nframes,
+                                                   const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
+    __shared__ __align__(16) uint8_t s_src[(BL_TH + 6) * (BL_TW + 8)];
+    __shared__ __align__(16) uint16_t s_row[(BL_TH + 6) * BL_TW];
+    const int tpf = plan->blur_tiles_per_frame;
+    const long long total = (long long)nframes * tpf;
+    for (long long it = blockIdx.x; it < total; it += gridDim.x) {
+        const int frame = (int)(it / tpf);
+        const int t = (int)(it - (long long)frame * tpf);
+        int l = 0;
+        while (l + 1 < plan->nlevels && t >= plan->lv[l + 1].blur_tile_base) ++l;
+        const OrbxLevel& L = plan->lv[l];
+        const int tl = t - L.blur_tile_base;
+        const int ty = tl / L.blur_tiles_x, tx = tl - ty * L.blur_tiles_x;
+        const int x0 = tx * BL_TW, y0 = ty * BL_TH;
+        const uint8_t* src = pyr + (size_t)frame * plan->slab_bytes;
+        // stage rows y0-3 .. y0+TH+2, cols x0-3 .. x0+TW+2 (clamped into the padded plane)
+        for (int i = threadIdx.x; i < (BL_TH + 6) * (BL_TW + 6); i += 256) {
+            const int r = i / (BL_TW + 6), c = i - r * (BL_TW + 6);
+            const int yy = min(y0 + r - 3, L.h + ORBX_EDGE - 1);
+            const int xx = min(x0 + c - 3, L.w + ORBX_EDGE - 1);
+            s_src[r * (BL_TW + 8) + c] = *level_px(src, L, xx, yy);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < (BL_TH + 6) * BL_TW; i += 256) {
+            const int r = i / BL_TW, c = i - r * BL_TW;
+            const uint8_t* p = s_src + r * (BL_TW + 8) + c;
+            s_row[i] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+        }
+        __syncthreads();
+        uint8_t* dstp = blur + (size_t)frame * plan->slab_bytes;
+        const int cx = (threadIdx.x & 31) * 4;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int ry = (threadIdx.x >> 5) + 8 * k;
+            if (y0 + ry < L.h && x0 + cx < L.w) {
+                uint32_t out = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint16_t* q = s_row + ry * BL_TW + cx + j;
+                    const uint32_t csum = 18u * (q[0] + q[6 * BL_TW]) + 34u * (q[BL_TW] + q[5 * BL_TW]) +
+                                          48u * (q[2 * BL_TW] + q[4 * BL_TW]) + 56u * q[3 * BL_TW];
+                    out |= ((csum + 32768u) >> 16) << (8 * j);
+                }
+                *reinterpret_cast<uint32_t*>(dstp + L.plane_off + (size_t)(y0 + ry + ORBX_EDGE) * L.pitch + ORBX_XO + x0 + cx) = out;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// =====================================================================================
+// computeOrbDescriptor (:108-147), one warp per keypoint: lane i produces descriptor byte i
+// from its 16 pattern points (held in registers), bytes are merged with shuffles and the
+// 256 bits leave as two 128-bit stores.  The warp also writes the final cv::KeyPoint record
+// (pt scaled by mvScaleFactor[level] AFTER sampling, :1095-1101).  Canonical rule B-2:
+// a, b = float(cos/sin in double); products and sums individually rounded; round-half-even.
+// =====================================================================================
+__global__ void __launch_bounds__(256) desc_kernel(const OrbxPlan* __restrict__ plan, int nframes,
+                                                   const uint8_t* __restrict__ blur,
+                                                   const uint32_t* __restrict__ kept,
+                                                   const int* __restrict__ kept_counts,
+                                                   const float* __restrict__ angles,
+                                                   float* __restrict__ out_kp, uint8_t* __restrict__ out_desc) {
+    const int lane = threadIdx.x & 31;
+    float px[16], py[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        px[j] = (float)c_pattern[lane * 32 + 2 * j];
+        py[j] = (float)c_pattern[lane * 32 + 2 * j + 1];
+    }
+    const int kpf = plan->kept_per_frame;
+    const int nl = plan->nlevels;
+    const long long total = (long long)nframes * kpf;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long it = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < total; it += nwarps) {
+        const int frame = (int)(it / kpf);
+        const int s = (int)(it - (long long)frame * kpf);
+        const int l = level_of_slot(plan, s);
+        const OrbxLevel& L = plan->lv[l];
+        const int* kc = kept_counts + frame * nl;
+        const int sl = s - L.kept_off;
+        if (sl >= kc[l]) continue;
+        int oidx = sl;
+        for (int q = 0; q < l; ++q) oidx += kc[q];                          // levels concatenated (:1076-1104)
+        const uint32_t p = kept[it];
+        const int kx = ORBX_PX(p), ky = ORBX_PY(p);
+        const float angle = angles[it];
+        const float rad = __fmul_rn(angle, plan->factor_pi);               // (:111)
+        const float a = (float)cos((double)rad), b = (float)sin((double)rad);
+        const uint8_t* center = level_px(blur + (size_t)frame * plan->slab_bytes, L, kx, ky);
+        const int pitch = L.pitch;
+        uint32_t byte = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float x = px[2 * j + e], y = py[2 * j + e];
+                const int rr = __float2int_rn(__fadd_rn(__fmul_rn(x, b), __fmul_rn(y, a)));    // (:119)
+                const int cc2 = __float2int_rn(__fsub_rn(__fmul_rn(x, a), __fmul_rn(y, b)));   // (:120)
+                v[e] = center[rr * pitch + cc2];
+            }
+            byte |= (uint32_t)(v[0] < v[1]) << j;
+        }
+        uint32_t word = byte << (8 * (lane & 3));
+        word |= __shfl_xor_sync(0xffffffffu, word, 1);
+        word |= __shfl_xor_sync(0xffffffffu, word, 2);                     // lanes 4k..4k+3 hold word k
+        const int half = lane >> 4;
+        uint4 v4;
+        v4.x = __shfl_sync(0xffffffffu, word, 16 * half + 0);
+        v4.y = __shfl_sync(0xffffffffu, word, 16 * half + 4);
+        v4.z = __shfl_sync(0xffffffffu, word, 16 * half + 8);
+        v4.w = __shfl_sync(0xffffffffu, word, 16 * half + 12);
+        const size_t orow = (size_t)frame * kpf + oidx;
+        if ((lane & 15) == 0) *reinterpret_cast<uint4*>(out_desc + orow * 32 + 16 * half) = v4;
+        if (lane < 7) {
+            float f;
+            if (lane == 0) f = l ? __fmul_rn((float)kx, L.scale) : (float)kx;
+            else if (lane == 1) f = l ? __fmul_rn((float)ky, L.scale) : (float)ky;
+            else if (lane == 2) f = L.kp_size;
+            else if (lane == 3) f = angle;
+            else if (lane == 4) f = (float)ORBX_PR(p);
+            else if (lane == 5) f = __int_as_float(l);
+            else f = __int_as_float(-1);
+            out_kp[orow * 7 + lane] = f;
+        }
+    }
+}
+
+// =====================================================================================
+// launch wrappers (called from orbx_api.cu)
+// =====================================================================================
+void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nframes, const uint8_t* imgs,
+                      size_t img_pitch, size_t img_frame_stride, uint8_t* pyr, const OrbxTap* taps,
+                      cudaStream_t st) {
+    const OrbxLevel& L = hp.lv[l];
+    const int cols4 = (ORBX_XO + L.w + ORBX_EDGE - 12 + 3) / 4;
+    dim3 block(32, 8), grid((cols4 + 31) / 32, (L.rows + 7) / 8, nframes);
+    if (l == 0)
+        pyr_level_kernel<true><<<grid, block, 0, st>>>(d_plan, l, imgs, img_pitch, img_frame_stride, pyr, taps);
+    else
+        pyr_level_kernel<false><<<grid, block, 0, st>>>(d_plan, l, imgs, img_pitch, img_frame_stride, pyr, taps);
+}
+
+size_t fast_smem_bytes(const OrbxPlan& hp) {
+    const int SP = (hp.max_cell_w + 3) & ~3;
+    const size_t words = (size_t)SP * hp.max_cell_h / 4 + (size_t)(hp.max_cell_w - 6) * (hp.max_cell_h - 6);
+    return words * 4 * ORBX_FAST_WARPS;
+}
+
+cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* pyr,
+                        uint32_t* cand, uint2* cell_rec, int* level_counts, int* status, cudaStream_t st) {
+    const size_t smem = fast_smem_bytes(hp);
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev & 63] = smem;
+    }
+    const long long total = (long long)nframes * hp.cells_per_frame;
+    long long blocks = (total + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_cells_kernel, ORBX_FAST_WARPS * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    const long long cap = (long long)num_sms * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    fast_cells_kernel<<<(int)blocks, ORBX_FAST_WARPS * 32, smem, st>>>(d_plan, pyr, nframes, cand, cell_rec,
+                                                                      level_counts, status);
+    return cudaSuccess;
+}
+
+size_t octree_smem_bytes(const OrbxPlan& hp) {
+    int sortn = 1;
+    while (sortn < hp.node_cap) sortn <<= 1;
+    return (size_t)sortn * 8 + (size_t)hp.node_cap * (8 + 8 + 4 + 4 + 16 + 16 + 4 + 4 + 4 + 4);
+}
+
+cudaError_t launch_octree(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, const uint32_t* cand,
+                          const uint2* cell_rec, uint32_t* cand_sorted, uint16_t* key_node, int* sorted_counts,
+                          uint32_t* kept, int* kept_counts, int* status, cudaStream_t st) {
+    const size_t smem = octree_smem_bytes(hp);
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev & 63] = smem;
+    }
+    octree_kernel<<<nframes * hp.nlevels, ORBX_OT_THREADS, smem, st>>>(d_plan, nframes, cand, cell_rec, cand_sorted,
+                                                                      key_node, sorted_counts, kept, kept_counts,
+                                                                      status);
+    return cudaSuccess;
+}
+
+static int warp_grid(long long items, int num_sms) {
+    long long blocks = (items + 7) / 8;
+    const long long cap = (long long)num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+void launch_orient(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* pyr,
+                   const uint32_t* kept, const int* kept_counts, float* angles, cudaStream_t st) {
+    orient_kernel<<<warp_grid((long long)nframes * hp.kept_per_frame, num_sms), 256, 0, st>>>(d_plan, nframes, pyr, kept,
+                                                                                              kept_counts, angles);
+}
+
+void launch_blur(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* pyr,
+                 uint8_t* blur, cudaStream_t st) {
+    long long blocks = (long long)nframes * hp.blur_tiles_per_frame;
+    const long long cap = (long long)num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    blur_kernel<<<(int)blocks, 256, 0, st>>>(d_plan, nframes, pyr, blur);
+}
+
+void launch_desc(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* blur,
+                 const uint32_t* kept, const int* kept_counts, const float* angles, float* out_kp,
+                 uint8_t* out_desc, cudaStream_t st) {
+    desc_kernel<<<warp_grid((long long)nframes * hp.kept_per_frame, num_sms), 256, 0, st>>>(
+        d_plan, nframes, blur, kept, kept_counts, angles, out_kp, out_desc);
+}
+
+}  // namespace orbx

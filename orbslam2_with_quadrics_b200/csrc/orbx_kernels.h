@@ -1,0 +1,35 @@
+// Launch wrappers of the stage kernels (orbx_kernels.cu), used by the C-ABI layer (orbx_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "orbx_plan.h"
+
+#define ORBX_FAST_WARPS 8
+#define ORBX_OT_THREADS 512
+
+// per-frame device status bits
+#define ORBX_DEV_CAND_OVERFLOW 1
+#define ORBX_DEV_NODE_OVERFLOW 2
+
+namespace orbx {
+
+void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nframes, const uint8_t* imgs,
+                      size_t img_pitch, size_t img_frame_stride, uint8_t* pyr, const OrbxTap* taps, cudaStream_t st);
+size_t fast_smem_bytes(const OrbxPlan& hp);
+cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* pyr,
+                        uint32_t* cand, uint2* cell_rec, int* level_counts, int* status, cudaStream_t st);
+size_t octree_smem_bytes(const OrbxPlan& hp);
+cudaError_t launch_octree(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, const uint32_t* cand,
+                          const uint2* cell_rec, uint32_t* cand_sorted, uint16_t* key_node, int* sorted_counts,
+                          uint32_t* kept, int* kept_counts, int* status, cudaStream_t st);
+void launch_orient(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* pyr,
+                   const uint32_t* kept, const int* kept_counts, float* angles, cudaStream_t st);
+void launch_blur(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* pyr,
+                 uint8_t* blur, cudaStream_t st);
+void launch_desc(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* blur,
+                 const uint32_t* kept, const int* kept_counts, const float* angles, float* out_kp, uint8_t* out_desc,
+                 cudaStream_t st);
+
+}  // namespace orbx

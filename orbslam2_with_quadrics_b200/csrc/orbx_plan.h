@@ -1,0 +1,63 @@
+// Device-visible plan of one extractor geometry: per-level sizes, HBM layout, cell grid,
+// quotas.  Built on the host (orbx_api.cu) from the five ORBextractor constructor
+// arguments and the image size, following src/ORBextractor.cc:410-470 (tables),
+// :1107-1115 (level sizes) and :771-787 (cell grid) of the reference.
+#pragma once
+#include <stdint.h>
+
+#define ORBX_XO 32          // plane column of level pixel x = 0 (19 used by the border; 32 keeps rows 32-byte aligned)
+#define ORBX_EDGE 19        // EDGE_THRESHOLD, src/ORBextractor.cc:74
+#define ORBX_BOX 16         // minBorderX/Y = EDGE_THRESHOLD - 3, :773-774
+#define ORBX_MAXL 16
+#define ORBX_MAX_ROOTS 256
+
+// Candidate / keypoint record: x | y << 12 | response << 24 (x, y < 4096; response = FAST score <= 254)
+#define ORBX_PACK(x, y, r) ((uint32_t)(x) | ((uint32_t)(y) << 12) | ((uint32_t)(r) << 24))
+#define ORBX_PX(p) ((int)((p) & 0xfffu))
+#define ORBX_PY(p) ((int)(((p) >> 12) & 0xfffu))
+#define ORBX_PR(p) ((int)((p) >> 24))
+
+struct OrbxLevel {
+    int w, h;                 // level size
+    int pitch;                // plane row pitch in bytes (multiple of 64)
+    int rows;                 // h + 38
+    long long plane_off;      // byte offset of the padded plane inside one frame's pyramid slab
+    int maxBX, maxBY;         // w - 16, h - 16 (box [16, maxB) is where FAST runs)
+    int nColsV, nRowsV;       // cells that survive the skip rules (:794, :803)
+    int wCell, hCell;
+    int cell_base;            // first FAST work item of this level inside a frame
+    int cand_off, cand_cap;   // this level's region in a frame's candidate buffers (entries)
+    int quota;                // mnFeaturesPerLevel[l]
+    int nIni;                 // root nodes of DistributeOctTree (:543)
+    float hX;                 // (:545)
+    int kept_off, kept_cap;   // this level's slots in a frame's kept-keypoint arrays
+    float scale;              // mvScaleFactor[l]
+    float kp_size;            // (float)(int)(31 * scale) (:837)
+    int xtab_off, ytab_off;   // resize tap tables of this level (entries)
+    int blur_tile_base;       // first blur tile of this level inside a frame
+    int blur_tiles_x;
+    int pad_;
+};
+
+struct OrbxPlan {
+    int nlevels;
+    int width, height;
+    int cells_per_frame;
+    int cand_per_frame;       // entries
+    int kept_per_frame;       // slots (= capacity of a frame's output arrays)
+    int blur_tiles_per_frame;
+    int node_cap;             // octree node capacity (max over levels)
+    int max_cell_w, max_cell_h;   // largest FAST window (incl. the 6-px overlap)
+    int ini_th, min_th;
+    long long slab_bytes;     // one frame's pyramid slab
+    float atan_p1, atan_p3, atan_p5, atan_p7;   // cv::fastAtan2 coefficients (float products)
+    float factor_pi;          // (float)(CV_PI/180.f) (:107)
+    int umax[16];             // (:454-469)
+    OrbxLevel lv[ORBX_MAXL];
+};
+
+// One bilinear tap pair of cv::resize INTER_LINEAR 8U
+struct OrbxTap {
+    int ofs;                  // first source index; second is min(ofs + 1, ssize - 1)
+    short c0, c1;             // 11-bit fixed-point weights
+};

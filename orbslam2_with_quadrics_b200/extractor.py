@@ -1,0 +1,194 @@
+"""Python mirror of ORB_SLAM2::ORBextractor (reference include/ORBextractor.h:45-111) on top of
+the C ABI (include/orbx.h).  Same constructor arguments, same getters, `mvImagePyramid`, and a
+call operator that returns (keypoints, descriptors) instead of filling output arguments.
+
+All compute happens in liborbx.so's CUDA kernels; if the library is missing, importing this
+module works but constructing an extractor raises."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
+from ._capi import KP_DTYPE, OrbxConfig, OrbxError, OrbxResult, check, lib
+
+
+class ORBextractor:
+    HARRIS_SCORE = 0     # include/ORBextractor.h:49 (unused by the reference as well)
+    FAST_SCORE = 1
+
+    def __init__(self, nfeatures: int, scaleFactor: float, nlevels: int, iniThFAST: int, minThFAST: int,
+                 device: int = 0, max_batch: int = 1, download_pyramid: bool = True, candidate_divisor: int = 0):
+        self._L = lib()
+        self._h = C.c_void_p()
+        cfg = OrbxConfig(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device, max_batch,
+                         1 if download_pyramid else 0, candidate_divisor)
+        check(self._L.orbx_create(C.byref(cfg), C.byref(self._h)))
+        self.nfeatures, self.nlevels, self.max_batch = nfeatures, nlevels, max_batch
+        self.download_pyramid = bool(download_pyramid)
+        self.mvImagePyramid: List[np.ndarray] = [np.zeros((0, 0), np.uint8) for _ in range(nlevels)]
+        self._pyramids: List[List[np.ndarray]] = []
+        self._last_n = 0
+        self._last_shape: Optional[Tuple[int, int]] = None
+
+    # ---------------------------------------------------------------- lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.orbx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------- getters (ORBextractor.h:63-83)
+    def GetLevels(self) -> int:
+        return self._L.orbx_get_levels(self._h)
+
+    def GetScaleFactor(self) -> float:
+        return float(self._L.orbx_get_scale_factor(self._h))
+
+    def _tables(self):
+        p = [C.POINTER(C.c_float)() for _ in range(4)]
+        check(self._L.orbx_scale_tables(self._h, *[C.byref(x) for x in p]))
+        return [np.ctypeslib.as_array(x, shape=(self.nlevels,)).copy() for x in p]
+
+    def GetScaleFactors(self): return self._tables()[0]
+    def GetInverseScaleFactors(self): return self._tables()[1]
+    def GetScaleSigmaSquares(self): return self._tables()[2]
+    def GetInverseScaleSigmaSquares(self): return self._tables()[3]
+
+    def level_quotas(self):
+        q = (C.c_int * self.nlevels)()
+        u = (C.c_int * 16)()
+        check(self._L.orbx_level_quotas(self._h, q, u))
+        return list(q), list(u)
+
+    def level_sizes(self, width: int, height: int):
+        w = (C.c_int * self.nlevels)()
+        h = (C.c_int * self.nlevels)()
+        check(self._L.orbx_level_sizes(self._h, width, height, w, h))
+        return list(zip(w, h))
+
+    def algorithmic_bytes(self, width: int, height: int) -> int:
+        return int(self._L.orbx_algorithmic_bytes(self._h, width, height))
+
+    # ---------------------------------------------------------------- operator()
+    def __call__(self, image: np.ndarray, mask=None):
+        """ORBextractor::operator() (src/ORBextractor.cc:1043).  mask is ignored, as in the reference.
+        Returns None for an empty image (the reference returns without touching its outputs)."""
+        if image is None or image.size == 0:
+            return None
+        return self.extract_batch([image])[0]
+
+    def extract_batch(self, images: Sequence[np.ndarray]):
+        n = len(images)
+        if n == 0:
+            return []
+        h, w = images[0].shape
+        ptrs = (C.c_void_p * n)()
+        strides = (C.c_size_t * n)()
+        keep = []
+        for i, im in enumerate(images):
+            if im.dtype != np.uint8 or im.ndim != 2 or im.shape != (h, w):
+                raise ValueError("images must be 2-D uint8 arrays of identical shape (CV_8UC1)")
+            if im.strides[1] != 1:
+                im = np.ascontiguousarray(im)
+            keep.append(im)
+            ptrs[i] = im.ctypes.data
+            strides[i] = im.strides[0]
+        res = (OrbxResult * n)()
+        check(self._L.orbx_extract_batch(self._h, n, ptrs, w, h, strides, res), self._h)
+        self._last_n, self._last_shape = n, (h, w)
+        out = [self._copy_result(res[i]) for i in range(n)]
+        self._refresh_pyramids(n)
+        return out
+
+    @staticmethod
+    def _copy_result(r: OrbxResult):
+        n = r.n
+        if n == 0:     # descriptors released (src/ORBextractor.cc:1064-1065)
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        kps = np.ctypeslib.as_array(C.cast(r.kps, C.POINTER(C.c_uint8)), shape=(n * 28,)).view(KP_DTYPE).copy()
+        desc = np.ctypeslib.as_array(C.cast(r.desc, C.POINTER(C.c_uint8)), shape=(n, 32)).copy()
+        return kps, desc
+
+    def _refresh_pyramids(self, n: int):
+        self._pyramids = []
+        if not self.download_pyramid:
+            return
+        for f in range(n):
+            self._pyramids.append([self._pyramid_view(f, l) for l in range(self.nlevels)])
+        self.mvImagePyramid = self._pyramids[0]
+
+    def _pyramid_view(self, frame: int, level: int, padded: bool = False) -> np.ndarray:
+        p = C.c_void_p()
+        w, h, step = C.c_int(), C.c_int(), C.c_size_t()
+        check(self._L.orbx_pyramid_level(self._h, frame, level, C.byref(p), C.byref(w), C.byref(h), C.byref(step)))
+        E = 19
+        base = p.value - E * step.value - E
+        rows, cols = h.value + 2 * E, w.value + 2 * E
+        buf = (C.c_uint8 * (rows * step.value)).from_address(base)
+        plane = np.ctypeslib.as_array(buf).reshape(rows, step.value)[:, :cols]
+        return plane if padded else plane[E:-E, E:-E]
+
+    def pyramid(self, frame: int = 0, padded: bool = True):
+        """Host views (valid until the next call) of the padded planes of `frame`."""
+        return [self._pyramid_view(frame, l, padded) for l in range(self.nlevels)]
+
+    # ---------------------------------------------------------------- device-resident path
+    def extract_device(self, d_ptr: int, n: int, width: int, height: int, pitch: int, frame_stride: int):
+        """Enqueue the path on n images already in HBM (roofline timing); no host sync."""
+        check(self._L.orbx_extract_device(self._h, n, C.c_void_p(d_ptr), width, height, pitch, frame_stride), self._h)
+        self._last_n, self._last_shape = n, (height, width)
+
+    def fetch_results(self, n: int):
+        res = (OrbxResult * n)()
+        check(self._L.orbx_fetch_results(self._h, n, res), self._h)
+        out = [self._copy_result(res[i]) for i in range(n)]
+        self._refresh_pyramids(n)
+        return out
+
+    def synchronize(self):
+        check(self._L.orbx_synchronize(self._h), self._h)
+
+    @property
+    def stream(self) -> int:
+        return int(self._L.orbx_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.orbx_launch_count(self._h))
+
+    def stage_timing(self, enable: bool):
+        check(self._L.orbx_stage_timing_enable(self._h, 1 if enable else 0), self._h)
+
+    def stage_times(self):
+        names = (C.c_char_p * 16)()
+        ms = (C.c_float * 16)()
+        ln = (C.c_int * 16)()
+        k = self._L.orbx_stage_timing_read(self._h, 16, names, ms, ln)
+        return [(names[i].decode(), float(ms[i]), int(ln[i])) for i in range(k)]
+
+    # ---------------------------------------------------------------- stage dumps (parity tests)
+    def stage_dump(self, frame: int, level: int, stage: int):
+        nbytes = C.c_size_t()
+        check(self._L.orbx_stage_dump(self._h, frame, level, stage, None, 0, C.byref(nbytes)), self._h)
+        buf = np.zeros(max(nbytes.value, 1), np.uint8)
+        check(self._L.orbx_stage_dump(self._h, frame, level, stage, buf.ctypes.data, buf.size, C.byref(nbytes)), self._h)
+        buf = buf[:nbytes.value]
+        h, w = self._last_shape
+        lw, lh = self.level_sizes(w, h)[level]
+        if stage == _capi.STAGE_PYRAMID:
+            return buf.reshape(lh + 38, lw + 38)
+        if stage == _capi.STAGE_BLURRED:
+            return buf.reshape(lh, lw)
+        if stage in (_capi.STAGE_CANDIDATES, _capi.STAGE_KEPT):
+            return buf.view(np.int32).reshape(-1, 3)
+        if stage == _capi.STAGE_ANGLES:
+            return buf.view(np.float32)
+        raise ValueError(stage)
