@@ -1,0 +1,329 @@
+#!/usr/bin/env python3
+"""Benchmark of the ORB feature front end (BASELINE.json metric: ORB extraction frames/s + latency).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl orbx|reference] [--config NAME] [--batch B]
+
+A step = one pass of ORBextractor::operator() over one batch of synthetic frames per GPU.
+`value`   : frames/s with the batch already resident in HBM (CUDA events on the library's stream).
+`e2e`     : frames/s through the C ABI with pinned HOST buffers, H2D + D2H inside the timed region.
+`roofline`: algorithmic bytes / device time against the measured HBM peak.
+`--impl reference`: the reference's own unmodified ORBextractor TU (oracle/_ref) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from orbslam2_with_quadrics_b200 import frames as fr          # noqa: E402
+from orbslam2_with_quadrics_b200 import geometry as geo       # noqa: E402
+
+METRIC = "orb_extraction_frames_per_sec"
+UNIT = "frames/s"
+DISTINCT_FRAMES = 8
+
+
+def workload_desc(name):
+    w, h, nf, sf, nl, it, mt, nimg = fr.CONFIGS[name]
+    return "%s: %dx%d 8-bit gray%s, nFeatures=%d, %d levels, scale %.1f, FAST %d/%d" % (
+        name, w, h, " x2 (stereo pair = 1 frame)" if nimg == 2 else "", nf, nl, sf, it, mt)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def make_frames(name, stream, count):
+    w, h, *_rest, nimg = fr.CONFIGS[name]
+    base = [fr.cluttered_scene(w, h, fr.stream_seed(stream, i)) for i in range(min(count, DISTINCT_FRAMES))]
+    return [base[i % len(base)] for i in range(count)]
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def run_reference_cpu(name, frames_per_step, steps, warmup, cores):
+    """Times the reference's own code (unmodified TU on the OpenCV shim), one thread per frame."""
+    from oracle import ref_lib                 # the one place bench.py executes oracle/: the CPU arm
+    if not ref_lib.available():
+        ref_lib.build()
+    w, h, nf, sf, nl, it, mt, nimg = fr.CONFIGS[name]
+    imgs = make_frames(name, 0, DISTINCT_FRAMES)
+    nthreads = max(1, min(cores, frames_per_step))
+    exs = [ref_lib.RefORBextractor(nf, sf, nl, it, mt) for _ in range(nthreads)]
+    lat = []
+
+    def work(tid, nsteps, record):
+        for s in range(nsteps):
+            for f in range(tid, frames_per_step, nthreads):
+                for k in range(nimg):
+                    t0 = time.perf_counter()
+                    exs[tid](imgs[(f + k) % len(imgs)])
+                    if record:
+                        lat.append(time.perf_counter() - t0)
+
+    def run(nsteps, record):
+        th = [threading.Thread(target=work, args=(t, nsteps, record)) for t in range(nthreads)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        return time.perf_counter() - t0
+
+    run(warmup, False)
+    el = run(steps, True)
+    fps = frames_per_step * steps / el
+    lat_ms = np.asarray(lat) * 1e3
+    return {"value": fps, "unit": UNIT, "cores": nthreads, "kind": "reference",
+            "sample": "%d frames/step x %d steps of %s, one thread per frame on %d host threads; "
+                      "unmodified reference ORBextractor.cc on the scalar OpenCV shim (oracle/_ref)" % (
+                          frames_per_step, steps, name, nthreads),
+            "image_latency_ms_p50": float(np.percentile(lat_ms, 50)), "image_latency_ms_p99": float(np.percentile(lat_ms, 99)),
+            "elapsed_s": el}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = host_cores()
+    fps_step = max(8, 2 * cores) if args.config in ("rgbd_1080p", "mono_4k") else max(16, 4 * cores)
+    r = run_reference_cpu(args.config, fps_step, args.steps, args.warmup, cores)
+    line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["elapsed_s"] / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_desc(args.config), "frames_per_step": fps_step, "host_threads": r["cores"]},
+            "cpu_baseline": r,
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.rows = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------- own arm
+def own_arm(args):
+    import torch
+    from orbslam2_with_quadrics_b200 import ORBextractor, sharding
+
+    rank, world, local = sharding.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    name = args.config
+    w, h, nf, sf, nl, it, mt, nimg = fr.CONFIGS[name]
+    B = args.batch                       # frames per step per GPU
+    nimgs = B * nimg                     # images per step per GPU
+    K, W = args.steps, args.warmup
+    balg = geo.algorithmic_bytes(w, h, nf, sf, nl) * nimg           # per frame
+    stage_bytes = geo.stage_algorithmic_bytes(w, h, nf, sf, nl)
+
+    # ---- synthetic input: this rank serves camera stream `rank` (no cross-rank data dependency)
+    if nimg == 1:
+        imgs = make_frames(name, rank, nimgs)
+    else:              # stereo: left/right streams interleaved, pairs kept on this GPU
+        left = make_frames(name, rank * 2, B)
+        right = make_frames(name, rank * 2 + 1, B)
+        imgs = [x for pair in zip(left, right) for x in pair]
+    pitch = (w + 15) // 16 * 16
+    host = torch.zeros((nimgs, h, pitch), dtype=torch.uint8).pin_memory()
+    hnp = host.numpy()
+    for i, im in enumerate(imgs):
+        hnp[i, :, :w] = im
+    dev = host.cuda(non_blocking=False)
+
+    need_pyr = nimg == 2                 # only ComputeStereoMatches reads mvImagePyramid (src/Frame.cc:563-580)
+    ex = ORBextractor(nf, sf, nl, it, mt, device=local, max_batch=nimgs, download_pyramid=False)
+    stream = torch.cuda.ExternalStream(ex.stream, device=torch.device("cuda", local))
+
+    def step_device():
+        ex.extract_device(dev.data_ptr(), nimgs, w, h, pitch, h * pitch)
+
+    for _ in range(W):
+        step_device()
+    ex.synchronize()
+    res = ex.fetch_results(nimgs)
+    kp_counts = [len(k) for k, _ in res]
+    if min(kp_counts) == 0:
+        raise SystemExit("bench: a frame produced no keypoints; refusing to time a degenerate run")
+
+    sampler = ClockSampler(local if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local])
+    if rank == 0:
+        sampler.start()
+    ex.stage_timing(True)
+    l0 = ex.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sharding.barrier(); torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(K):
+        step_device()
+    e1.record(stream)
+    ex.synchronize(); torch.cuda.synchronize(); sharding.barrier()
+    dev_ms = e0.elapsed_time(e1)
+    launches = ex.launch_count - l0
+    stages = ex.stage_times()
+    ex.stage_timing(False)
+    dev_ms_max = sharding.max_over_ranks(dev_ms)
+    value = world * B * K / (dev_ms_max / 1e3)
+
+    # ---- e2e through the C ABI: pinned host frames in, keypoints + descriptors (+ pyramid for stereo) out
+    ex2 = ORBextractor(nf, sf, nl, it, mt, device=local, max_batch=nimgs, download_pyramid=need_pyr)
+    views = [hnp[i, :, :w] for i in range(nimgs)]
+    for _ in range(max(1, W // 2)):
+        ex2.extract_batch(views)
+    stream2 = torch.cuda.ExternalStream(ex2.stream, device=torch.device("cuda", local))
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    Ke = max(3, min(K, 10))
+    sharding.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    f0.record(stream2)
+    for _ in range(Ke):
+        out = ex2.extract_batch(views)
+    f1.record(stream2)
+    ex2.synchronize(); torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    sharding.barrier()
+    e2e_ms = max(f0.elapsed_time(f1), wall * 1e3)        # the blocking host call is what a user waits for
+    e2e_ms_max = sharding.max_over_ranks(e2e_ms)
+    e2e_value = world * B * Ke / (e2e_ms_max / 1e3)
+    n_out = int(np.mean([len(k) for k, _ in out]))
+    slab = sum(((32 + lw + 19 + 63) // 64 * 64) * (lh + 38) for lw, lh in geo.level_sizes(w, h, sf, nl))
+    d2h = nimgs * (n_out * 60) + (nimgs * slab if need_pyr else 0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-frame latency through the C ABI, batch = 1 frame (rank 0 reports)
+    lat = None
+    if rank == 0 and args.latency_frames > 0:
+        ex1 = ORBextractor(nf, sf, nl, it, mt, device=local, max_batch=nimg, download_pyramid=need_pyr)
+        for i in range(5):
+            ex1.extract_batch(views[:nimg])
+        ts = []
+        for i in range(args.latency_frames):
+            v = views[(i * nimg) % nimgs:(i * nimg) % nimgs + nimg]
+            t0 = time.perf_counter()
+            ex1.extract_batch(v)
+            ts.append(time.perf_counter() - t0)
+        ts = np.asarray(ts) * 1e3
+        lat = {"p50": float(np.percentile(ts, 50)), "p99": float(np.percentile(ts, 99)), "frames": len(ts),
+               "batch": 1, "path": "C ABI, pinned host in, keypoints+descriptors out" + (", pyramid D2H" if need_pyr else "")}
+        ex1.close()
+
+    if rank != 0:
+        return 0
+    # ---- roofline of the whole step and of each stage kernel
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_file):
+        peak, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = balg * B * K / (dev_ms / 1e3) / 1e9
+    stage_rows = []
+    for nm, ms, ln in stages:
+        sb = stage_bytes.get(nm, 0) * nimgs * K
+        stage_rows.append({"kernel": nm, "ms_per_step": ms / K, "launches_per_step": ln / K,
+                           "share": ms / max(sum(m for _, m, _ in stages), 1e-9),
+                           "alg_gbs": (sb / (ms / 1e3) / 1e9) if ms > 0 else None})
+    dom = max(stage_rows, key=lambda r: r["ms_per_step"])
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(tf):
+        try:
+            traffic = json.load(open(tf)).get(name)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "scope": "whole step (all stage kernels of the batch); algorithmic bytes %d per frame x %d frames per launch sequence" % (balg, B),
+                "dominant_kernel": dom["kernel"], "stages": stage_rows}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        per = max(8, cores)
+        cpu = run_reference_cpu(name, per, 2, 1, cores)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_desc(name), "batch_per_gpu": B, "frames_per_step": world * B,
+                       "distinct_frames": DISTINCT_FRAMES, "parallelism": "one camera stream per GPU, no collective",
+                       "l2_policy": "per-step working set (inputs %.0f MB + pyramids %.0f MB per GPU) exceeds the 126 MB L2" % (
+                           nimgs * h * pitch / 1e6, nimgs * slab / 1e6),
+                       "keypoints_per_image": n_out},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nimgs * w * h, "d2h_bytes_per_step": d2h,
+                    "steps": Ke, "pyramid_d2h": need_pyr},
+            "latency_ms": lat, "gpu_launches": int(launches), "clocks": clocks}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
+    ap.add_argument("--config", default="rgbd_1080p", choices=list(fr.CONFIGS))
+    ap.add_argument("--batch", type=int, default=32, help="frames per step per GPU")
+    ap.add_argument("--latency-frames", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return reference_arm(args)
+    return own_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
