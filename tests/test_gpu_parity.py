@@ -91,7 +91,7 @@ def test_adversarial_frames(kind):
 
 @pytest.mark.parametrize("shape,args", [((333, 517), (500, 1.2, 6, 20, 7)), ((480, 640), (1500, 1.5, 4, 12, 5)),
                                          ((200, 900), (700, 1.1, 10, 20, 7)), ((131, 257), (200, 1.2, 3, 20, 7)),
-                                         ((600, 300), (400, 1.3, 5, 30, 10))])
+                                         ((600, 400), (400, 1.3, 5, 30, 10))])
 def test_odd_shapes_strides_and_parameters(shape, args):
     h, w = shape
     big = fr.cluttered_scene(w + 64, h + 32, 900 + h)
@@ -175,6 +175,9 @@ def test_api_conformance():
     assert e.value.status == _capi.ERR_BAD_GEOMETRY
     with pytest.raises(OrbxError) as e:
         gx(np.zeros((100, 5000), np.uint8))
+    assert e.value.status == _capi.ERR_BAD_GEOMETRY
+    with pytest.raises(OrbxError) as e:
+        gx(np.zeros((600, 300), np.uint8))      # width/height < 0.5: nIni = 0, the reference divides by zero (App. B-7)
     assert e.value.status == _capi.ERR_BAD_GEOMETRY
     img = fr.cluttered_scene(640, 480, 5)
     k1, d1 = gx(img)
