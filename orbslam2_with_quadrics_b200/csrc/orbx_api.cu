@@ -48,7 +48,8 @@ struct orbx_handle {
     uint32_t *d_cand, *d_cand_sorted, *d_kept;
     uint16_t* d_key_node;
     uint2* d_cell_rec;
-    int* d_counters;             // [level_counts B*L][sorted_counts B*L][kept_counts B*L][status B]
+    int* d_counters;             // [level_counts B*L][sorted_counts B*L][kept_counts B*L][status B][work counter]
+    std::vector<unsigned char> fast_maps;   // per-level TMA descriptors of the pyramid slabs
     float* d_angles;
     float* d_out_kp;
     uint8_t* d_out_desc;
@@ -69,11 +70,12 @@ struct orbx_handle {
     double stage_ms[ST_COUNT];
     int stage_launches[ST_COUNT];
 
-    int counters_count() const { return cfg.max_batch * (3 * plan.nlevels + 1); }
+    int counters_count() const { return cfg.max_batch * (3 * plan.nlevels + 1) + 1; }
     int* d_level_counts() const { return d_counters; }
     int* d_sorted_counts() const { return d_counters + cfg.max_batch * plan.nlevels; }
     int* d_kept_counts() const { return d_counters + 2 * cfg.max_batch * plan.nlevels; }
     int* d_status() const { return d_counters + 3 * cfg.max_batch * plan.nlevels; }
+    int* d_work_counter() const { return d_counters + cfg.max_batch * (3 * plan.nlevels + 1); }
     const int* h_sorted_counts() const { return h_counters + cfg.max_batch * plan.nlevels; }
     const int* h_kept_counts() const { return h_counters + 2 * cfg.max_batch * plan.nlevels; }
     const int* h_status() const { return h_counters + 3 * cfg.max_batch * plan.nlevels; }
@@ -230,6 +232,9 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
     P->node_cap = round_up(P->node_cap, 32);
     if (P->max_cell_w < 7) P->max_cell_w = 7;
     if (P->max_cell_h < 7) P->max_cell_h = 7;
+    P->fast_bw = round_up(P->max_cell_w + 24, 16);     // 16-aligned TMA start (delta <= 15), 1-byte shift, 2 words of read-ahead
+    P->fast_bh = P->max_cell_h;
+    if (P->fast_bw > 256 || P->fast_bh > 127 || P->max_cell_w > 250) return ORBX_ERR_BAD_GEOMETRY;
     P->cells_per_frame = cells;
     P->cand_per_frame = cand;
     P->kept_per_frame = kept;
@@ -294,6 +299,11 @@ int ensure_geometry(orbx_handle* h, int w, int hgt) {
     CK(h, cudaMallocHost(&h->h_out_desc, B * P.kept_per_frame * 32));
     CK(h, cudaMallocHost(&h->h_input, B * hgt * h->in_pitch));
     if (h->cfg.download_pyramid) CK(h, cudaMallocHost(&h->h_pyr, B * P.slab_bytes));
+    h->fast_maps.resize(orbx::fast_maps_bytes());
+    if (orbx::build_fast_maps(h->plan, h->d_pyr, h->cfg.max_batch, h->fast_maps.data()) != 0) {
+        h->last_error = "cuTensorMapEncodeTiled failed";
+        return ORBX_ERR_CUDA;
+    }
     CK(h, cudaMemcpyAsync(h->d_plan, &h->plan, sizeof(OrbxPlan), cudaMemcpyHostToDevice, h->stream));
     if (!h->taps.empty())
         CK(h, cudaMemcpyAsync(h->d_taps, h->taps.data(), sizeof(OrbxTap) * h->taps.size(), cudaMemcpyHostToDevice, h->stream));
@@ -331,7 +341,8 @@ int enqueue_pipeline(orbx_handle* h, int n, const uint8_t* d_imgs, size_t pitch,
     for (int l = 0; l < P.nlevels; ++l)
         orbx::launch_pyr_level(h->d_plan, P, l, n, d_imgs, pitch, frame_stride, h->d_pyr, h->d_taps, st);
     if (ev) CK(h, cudaEventRecord(ev[ST_FAST], st));
-    CK(h, orbx::launch_fast(h->d_plan, P, n, h->num_sms, h->d_pyr, h->d_cand, h->d_cell_rec, h->d_level_counts(), h->d_status(), st));
+    CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), n, h->num_sms, h->d_cand, h->d_cell_rec, h->d_level_counts(),
+                            h->d_work_counter(), h->d_status(), st));
     if (ev) CK(h, cudaEventRecord(ev[ST_OCTREE], st));
     CK(h, orbx::launch_octree(h->d_plan, P, n, h->d_cand, h->d_cell_rec, h->d_cand_sorted, h->d_key_node,
                               h->d_sorted_counts(), h->d_kept, h->d_kept_counts(), h->d_status(), st));

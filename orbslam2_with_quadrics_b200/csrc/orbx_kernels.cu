@@ -14,8 +14,11 @@
 // Exactness rules: integer stages are bit-exact restatements of the
 // OpenCV 4.x fixed-point arithmetic; float stages use __f*_rn intrinsics so nothing is
 // contracted into FMAs.
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "orbx_kernels.h"
 
@@ -87,170 +90,300 @@ __global__ void __launch_bounds__(256) pyr_level_kernel(const OrbxPlan* __restri
 }
 
 // =====================================================================================
-// FAST-9/16 per 30-px cell (cv::FAST(window, t, true)), one warp per cell.
-//   phase 1  every pixel of the window interior: opposite-pair pre-test, survivors queued
-//   phase 2  queued pixels: 16-bit bright/dark ring masks, circular run-of-9 test, exact
-//            score A-1 (A = max over the 16 arcs of the min signed difference)
-//   phase 3  3x3 non-max suppression inside the window (frame scores 0), ordered compaction
-// The iniThFAST pass is repeated with minThFAST iff it produced no keypoint (:812).  All
-// compaction is by ballot/popc in row-major order, so a cell's list is already in cv::FAST's
-// output order; cells are put in reference order by the octree kernel's prologue.
+// FAST-9/16 per 30-px cell (cv::FAST(window, t, true)), one warp per cell,
+// persistent warps with a dynamic work counter.
+//
+// Staging: each cell window is fetched by ONE elected lane with a TMA tile load
+// (cp.async.bulk.tensor.3d over a per-level {pitch, rows, frame} tensor map) into a
+// double-buffered shared-memory tile; the next cell's tile is in flight while the current one
+// is processed.  TMA needs the inner coordinate on a 16-byte boundary, so the BW x BH box starts
+// at the 16-aligned column at or before (window x0 - 1) and the window sits `delta` (0..15) bytes
+// into the tile: tile column = window x + 1 + delta.  Words are re-aligned with funnel shifts.
+//   phase 1  4 pixels per lane, SIMD-in-word: |ring - centre| for the compass points 0/8 and
+//            4/12 with VABSDIFF4; a 9-arc needs one pixel of every opposite pair beyond the
+//            threshold, so pixels failing either pair are dropped.  Survivors are compacted in
+//            row-major order with a warp scan.
+//   phase 2  per survivor: exact score A = max over the 16 arcs of min(+-(ring - centre)) with
+//            packed 16-bit VIMNMX3 (two arcs per instruction); corner iff A > t, score = A - 1.
+//   phase 3  strict 3x3 NMS on a zero-framed score map, count, then ordered emission.
+// The iniThFAST pass is repeated with minThFAST iff it produced no keypoint (:812).
 // =====================================================================================
-__device__ __forceinline__ bool run9(uint32_t m) {
-    uint32_t x = m | (m << 16);
-    uint32_t y = x & (x >> 1);
-    y &= y >> 2;
-    y &= y >> 4;
-    y &= x >> 8;
-    return (y & 0xffffu) != 0;
+struct FastMaps {
+    CUtensorMap m[ORBX_MAXL];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
-__device__ __forceinline__ int fast_score(const uint8_t* __restrict__ p, int pitch, int t) {
-    const int v = p[0];
-    int q[16];
-    q[0] = p[3 * pitch];       q[1] = p[3 * pitch + 1];   q[2] = p[2 * pitch + 2];   q[3] = p[pitch + 3];
-    q[4] = p[3];               q[5] = p[-pitch + 3];      q[6] = p[-2 * pitch + 2];  q[7] = p[-3 * pitch + 1];
-    q[8] = p[-3 * pitch];      q[9] = p[-3 * pitch - 1];  q[10] = p[-2 * pitch - 2]; q[11] = p[-pitch - 3];
-    q[12] = p[-3];             q[13] = p[pitch - 3];      q[14] = p[2 * pitch - 2];  q[15] = p[3 * pitch - 1];
-    uint32_t bright = 0, dark = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        bright |= (uint32_t)(q[k] > v + t) << k;
-        dark |= (uint32_t)(q[k] < v - t) << k;
-    }
-    if (!run9(bright) && !run9(dark)) return 0;
-    // z_k = (q_k - v, v - q_k) as s16x2; arc score = min over 9 consecutive, both signs at once
-    uint32_t z[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int e = q[k] - v;
-        z[k] = __byte_perm((uint32_t)e, (uint32_t)(-e), 0x5410);
-    }
-    uint32_t m3[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) m3[k] = __vimin3_s16x2(z[k], z[(k + 1) & 15], z[(k + 2) & 15]);
-    uint32_t best = 0x80008000u;                       // (-32768, -32768)
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const uint32_t m9 = __vimin3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
-        best = __vmaxs2(best, m9);
-    }
-    const int A = max((int)(short)(best & 0xffffu), (int)(short)(best >> 16));
-    return A - 1;                                      // A > t >= 1 for a corner
-}
+struct FastCell {
+    int frame, l, ci, cj;
+};
 
-__global__ void __launch_bounds__(ORBX_FAST_WARPS * 32)
-fast_cells_kernel(const OrbxPlan* __restrict__ plan, const uint8_t* __restrict__ pyr, int nframes,
-                  uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec, int* __restrict__ level_counts,
-                  int* __restrict__ status) {
-    extern __shared__ uint32_t fast_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int SP = (plan->max_cell_w + 3) & ~3;                       // score-map pitch (bytes)
-    const int score_words = SP * plan->max_cell_h / 4;
-    const int queue_words = (plan->max_cell_w - 6) * (plan->max_cell_h - 6);
-    uint32_t* wbase = fast_smem + (size_t)warp * (score_words + queue_words);
-    uint8_t* sc = reinterpret_cast<uint8_t*>(wbase);
-    uint32_t* queue = wbase + score_words;
-    const int nlevels = plan->nlevels;
+__device__ __forceinline__ FastCell fast_decode(const OrbxPlan* __restrict__ plan, long long item) {
+    FastCell c;
     const int cpf = plan->cells_per_frame;
-    const long long total = (long long)nframes * cpf;
-    const uint32_t lt_mask = (1u << lane) - 1u;
+    c.frame = (int)(item / cpf);
+    const int r = (int)(item - (long long)c.frame * cpf);
+    int l = 0;
+    while (l + 1 < plan->nlevels && r >= plan->lv[l + 1].cell_base) ++l;
+    c.l = l;
+    const OrbxLevel& L = plan->lv[l];
+    c.ci = (r - L.cell_base) / L.nColsV;
+    c.cj = (r - L.cell_base) - c.ci * L.nColsV;
+    return c;
+}
 
-    for (long long item = (long long)blockIdx.x * ORBX_FAST_WARPS + warp; item < total;
-         item += (long long)gridDim.x * ORBX_FAST_WARPS) {
-        const int frame = (int)(item / cpf);
-        const int c = (int)(item - (long long)frame * cpf);
-        int l = 0;
-        while (l + 1 < nlevels && c >= plan->lv[l + 1].cell_base) ++l;
-        const OrbxLevel& L = plan->lv[l];
-        const int ci = (c - L.cell_base) / L.nColsV;
-        const int cj = (c - L.cell_base) - ci * L.nColsV;
-        const int iniX = ORBX_BOX + cj * L.wCell, iniY = ORBX_BOX + ci * L.hCell;
+// exact FAST score of the pixel at tile byte p (pitch BW): A - 1 if A > t else 0
+__device__ __forceinline__ int fast_score_packed(const uint8_t* __restrict__ p, int BW, int t) {
+    const int v = p[0];
+    uint32_t q[16];
+    q[0] = p[3 * BW];        q[1] = p[3 * BW + 1];    q[2] = p[2 * BW + 2];    q[3] = p[BW + 3];
+    q[4] = p[3];             q[5] = p[-BW + 3];       q[6] = p[-2 * BW + 2];   q[7] = p[-3 * BW + 1];
+    q[8] = p[-3 * BW];       q[9] = p[-3 * BW - 1];   q[10] = p[-2 * BW - 2];  q[11] = p[-BW - 3];
+    q[12] = p[-3];           q[13] = p[BW - 3];       q[14] = p[2 * BW - 2];   q[15] = p[3 * BW - 1];
+    // Z[k] = (e_k + 256, e_{k+8} + 256) as s16x2 with e = ring - centre; Z[k+8] = halves swapped
+    const uint32_t bias = (uint32_t)(256 - v) * 0x00010001u;
+    uint32_t Z[16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        Z[k] = (q[k] | (q[k + 8] << 16)) + bias;
+        Z[k + 8] = __byte_perm(Z[k], 0, 0x1032);
+    }
+    uint32_t n3[14], x3[14];
+#pragma unroll
+    for (int k = 0; k < 14; ++k) {
+        n3[k] = __vimin3_s16x2(Z[k], Z[k + 1], Z[k + 2]);
+        x3[k] = __vimax3_s16x2(Z[k], Z[k + 1], Z[k + 2]);
+    }
+    uint32_t n9[8], x9[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        n9[k] = __vimin3_s16x2(n3[k], n3[k + 3], n3[k + 6]);      // min over ring k .. k+8 (lo) and k+8 .. k+16 (hi)
+        x9[k] = __vimax3_s16x2(x3[k], x3[k + 3], x3[k + 6]);
+    }
+    uint32_t bm = __vimax3_s16x2(n9[0], n9[1], n9[2]);
+    bm = __vimax3_s16x2(bm, n9[3], n9[4]);
+    bm = __vimax3_s16x2(bm, n9[5], n9[6]);
+    bm = __vmaxs2(bm, n9[7]);
+    uint32_t dm = __vimin3_s16x2(x9[0], x9[1], x9[2]);
+    dm = __vimin3_s16x2(dm, x9[3], x9[4]);
+    dm = __vimin3_s16x2(dm, x9[5], x9[6]);
+    dm = __vmins2(dm, x9[7]);
+    const int Ab = max((int)(bm & 0xffffu), (int)(bm >> 16)) - 256;      // brighter arc: min(ring - centre)
+    const int Ad = 256 - min((int)(dm & 0xffffu), (int)(dm >> 16));      // darker arc: min(centre - ring)
+    const int A = max(Ab, Ad);
+    return A > t ? A - 1 : 0;
+}
+
+__global__ void __launch_bounds__(ORBX_FAST_WARPS * 32, 3)
+fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, int nframes,
+                  uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec, int* __restrict__ level_counts,
+                  int* __restrict__ work_counter, int* __restrict__ status) {
+    extern __shared__ uint8_t fast_smem_raw[];
+    __shared__ uint64_t s_bar[ORBX_FAST_WARPS][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int BW = plan->fast_bw, BH = plan->fast_bh;
+    const int TB = (BW * BH + 127) & ~127;                               // tile bytes
+    const int QN = (plan->max_cell_w - 6) * (plan->max_cell_h - 6);      // queue entries (u16)
+    const int SP = (plan->max_cell_w + 2 + 3) & ~3;                      // score-map pitch; column = window x + 1
+    const int SB = (SP * BH + 127) & ~127;
+    const int per_warp = 2 * TB + SB + ((QN * 2 + 127) & ~127);
+    uint8_t* base = fast_smem_raw + ((128 - (smem_u32(fast_smem_raw) & 127)) & 127) + (size_t)warp * per_warp;
+    uint8_t* sc = base + 2 * TB;                                         // zero-framed score map
+    uint16_t* queue = reinterpret_cast<uint16_t*>(base + 2 * TB + SB);   // entries (y << 8) | x, window coordinates
+    const int nlevels = plan->nlevels;
+    const long long total = (long long)nframes * plan->cells_per_frame;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int BW4 = BW >> 2;
+
+    for (int i = lane; i < SB / 4; i += 32) reinterpret_cast<uint32_t*>(sc)[i] = 0;
+    if (lane == 0) {
+        mbar_init(&s_bar[warp][0], 1);
+        mbar_init(&s_bar[warp][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
+    auto fetch = [&]() -> long long {
+        int v = 0;
+        if (lane == 0) v = atomicAdd(work_counter, 1);
+        return (long long)__shfl_sync(0xffffffffu, v, 0);
+    };
+    auto issue = [&](const FastCell& c, int b) {
+        if (lane == 0) {
+            const OrbxLevel& L = plan->lv[c.l];
+            mbar_expect_tx(&s_bar[warp][b], (uint32_t)(BW * BH));
+            tma_load_3d(base + b * TB, &maps.m[c.l], &s_bar[warp][b], (ORBX_XO + ORBX_BOX + c.cj * L.wCell - 1) & ~15,
+                        ORBX_EDGE + ORBX_BOX + c.ci * L.hCell, c.frame);
+        }
+    };
+
+    long long cur = fetch();
+    FastCell cc, nc;
+    if (cur < total) { cc = fast_decode(plan, cur); issue(cc, 0); }
+    uint32_t phase[2] = {0, 0};
+    int b = 0;
+    while (cur < total) {
+        const long long nxt = fetch();
+        if (nxt < total) { nc = fast_decode(plan, nxt); issue(nc, b ^ 1); }
+        mbar_wait(&s_bar[warp][b], phase[b]);
+        phase[b] ^= 1;
+
+        const OrbxLevel& L = plan->lv[cc.l];
+        const int iniX = ORBX_BOX + cc.cj * L.wCell, iniY = ORBX_BOX + cc.ci * L.hCell;
         const int ww = min(iniX + L.wCell + 6, L.maxBX) - iniX;
         const int wh = min(iniY + L.hCell + 6, L.maxBY) - iniY;
-        const int pitch = L.pitch;
-        const uint8_t* win = level_px(pyr + (size_t)frame * plan->slab_bytes, L, iniX, iniY);
-        int count = 0;
+        const int delta = (ORBX_XO + iniX - 1) & 15;
+        const uint8_t* tile = base + b * TB + delta + 1;                 // byte of window pixel (0, 0)
+        const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(base + b * TB) + (delta >> 2);
+        const int sh = (delta & 3) * 8;
+        int count = 0, cn = 0;
         if (ww >= 7 && wh >= 7) {
+            const int ew = ww - 6;                                       // emission width
+            const int G = (ew + 3) >> 2;                                 // 4-pixel groups per row
+            const int RPI = 32 / G;                                      // rows per warp iteration
+            const int ry = lane / G, g = lane - ry * G;
+            const int nvalid = min(max(ew - 4 * g, 0), 4);
+            const uint32_t vmask = (ry < RPI && nvalid > 0) ? (0x80808080u >> (8 * (4 - nvalid))) : 0u;
             for (int pass = 0; pass < 2 && count == 0; ++pass) {
                 const int t = pass == 0 ? plan->ini_th : plan->min_th;
-                for (int i = lane; i < score_words; i += 32) wbase[i] = 0;
-                // ---- phase 1: pre-test, queue survivors in row-major order
+                const uint32_t C = (uint32_t)(0x7f - min(t, 0x7f)) * 0x01010101u;
+                // ---- phase 1
                 int qn = 0;
-                for (int y = 3; y < wh - 3; ++y) {
-                    const uint8_t* row = win + (size_t)y * pitch;
-                    for (int x0 = 3; x0 < ww - 3; x0 += 32) {
-                        const int x = x0 + lane;
-                        bool pass1 = false;
-                        if (x < ww - 3) {
-                            const uint8_t* p = row + x;
-                            const int v = p[0];
-                            // every 9-arc holds one pixel of each opposite pair (k, k+8)
-                            const bool in0 = abs((int)p[3 * pitch] - v) <= t && abs((int)p[-3 * pitch] - v) <= t;
-                            const bool in4 = abs((int)p[3] - v) <= t && abs((int)p[-3] - v) <= t;
-                            pass1 = !(in0 || in4);
-                        }
-                        const uint32_t b = __ballot_sync(0xffffffffu, pass1);
-                        if (pass1) queue[qn + __popc(b & lt_mask)] = (uint32_t)x | ((uint32_t)y << 12);
-                        qn += __popc(b);
+                for (int yb = 3; yb < wh - 3; yb += RPI) {
+                    const int y = yb + ry;
+                    uint32_t m = 0;
+                    if (vmask && y < wh - 3) {
+                        const uint32_t* r = tile32 + y * BW4 + g;             // raw word holding tile column 4g + (delta & ~3)
+                        const uint32_t c1 = __funnelshift_r(r[1], r[2], sh);      // pixels x .. x+3, x = 3 + 4g
+                        const uint32_t c0 = __funnelshift_r(r[0], r[1], sh);
+                        const uint32_t c2 = __funnelshift_r(r[2], r[3], sh);
+                        const uint32_t up = __funnelshift_r(r[1 - 3 * BW4], r[2 - 3 * BW4], sh);
+                        const uint32_t dn = __funnelshift_r(r[1 + 3 * BW4], r[2 + 3 * BW4], sh);
+                        const uint32_t r4 = __funnelshift_r(c1, c2, 24);        // pixels x+3 .. x+6
+                        const uint32_t r12 = __funnelshift_r(c0, c1, 8);        // pixels x-3 .. x
+                        const uint32_t a0 = __vabsdiffu4(dn, c1), a8 = __vabsdiffu4(up, c1);
+                        const uint32_t a4 = __vabsdiffu4(r4, c1), a12 = __vabsdiffu4(r12, c1);
+                        // bit 7 of a byte of ((a & 0x7f) + C) | a  <=>  a > t
+                        const uint32_t s0 = (a0 & 0x7f7f7f7fu) + C, s8 = (a8 & 0x7f7f7f7fu) + C;
+                        const uint32_t s4 = (a4 & 0x7f7f7f7fu) + C, s12 = (a12 & 0x7f7f7f7fu) + C;
+                        m = ((s0 | a0) | (s8 | a8)) & ((s4 | a4) | (s12 | a12)) & vmask;
                     }
+                    const int cnt = __popc(m);
+                    int pre = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int tt = __shfl_up_sync(0xffffffffu, pre, o);
+                        if (lane >= o) pre += tt;
+                    }
+                    const int tot = __shfl_sync(0xffffffffu, pre, 31);
+                    if (m) {
+                        int w = qn + pre - cnt;
+                        const int e = (y << 8) | (3 + 4 * g);
+                        if (m & 0x80u) queue[w++] = (uint16_t)e;
+                        if (m & 0x8000u) queue[w++] = (uint16_t)(e + 1);
+                        if (m & 0x800000u) queue[w++] = (uint16_t)(e + 2);
+                        if (m & 0x80000000u) queue[w++] = (uint16_t)(e + 3);
+                    }
+                    qn += tot;
                 }
                 __syncwarp();
-                // ---- phase 2: exact corner test + score; corners compacted in place, scores to the map
-                int cn = 0;
+                // ---- phase 2: exact score; corners compacted in place (order kept), scores to the map
+                cn = 0;
                 for (int i0 = 0; i0 < qn; i0 += 32) {
                     const int i = i0 + lane;
-                    int s = 0;
-                    uint32_t e = 0;
+                    int s = 0, e = 0;
                     if (i < qn) {
                         e = queue[i];
-                        s = fast_score(win + (size_t)(e >> 12) * pitch + (e & 0xfffu), pitch, t);
+                        s = fast_score_packed(tile + (e >> 8) * BW + (e & 0xff), BW, t);
                     }
-                    const uint32_t b = __ballot_sync(0xffffffffu, s > 0);
+                    const uint32_t bal = __ballot_sync(0xffffffffu, s > 0);
                     if (s > 0) {
-                        sc[(e >> 12) * SP + (e & 0xfffu)] = (uint8_t)s;
-                        queue[cn + __popc(b & lt_mask)] = e | ((uint32_t)s << 24);
+                        sc[(e >> 8) * SP + (e & 0xff) + 1] = (uint8_t)s;
+                        queue[cn + __popc(bal & lt_mask)] = (uint16_t)e;
                     }
-                    cn += __popc(b);
+                    cn += __popc(bal);
                 }
                 __syncwarp();
-                // ---- phase 3: strict 3x3 NMS against the score map (window frame is 0)
+                // ---- phase 3a: strict 3x3 NMS (the window frame and non-corners score 0); mark + count
                 for (int i0 = 0; i0 < cn; i0 += 32) {
                     const int i = i0 + lane;
                     bool keep = false;
-                    uint32_t e = 0;
                     if (i < cn) {
-                        e = queue[i];
-                        const int s = (int)(e >> 24);
-                        const uint8_t* m = sc + ((e >> 12) & 0xfffu) * SP + (e & 0xfffu);
-                        keep = s > m[-1] && s > m[1] && s > m[-SP - 1] && s > m[-SP] && s > m[-SP + 1] &&
-                               s > m[SP - 1] && s > m[SP] && s > m[SP + 1];
+                        const int e = queue[i];
+                        const uint8_t* mp = sc + (e >> 8) * SP + (e & 0xff) + 1;
+                        const int s = mp[0];
+                        keep = s > mp[-1] && s > mp[1] && s > mp[-SP - 1] && s > mp[-SP] && s > mp[-SP + 1] &&
+                               s > mp[SP - 1] && s > mp[SP] && s > mp[SP + 1];
+                        if (keep) queue[i] = (uint16_t)(e | 0x8000);
                     }
-                    const uint32_t b = __ballot_sync(0xffffffffu, keep);
-                    if (keep) queue[count + __popc(b & lt_mask)] = e;
-                    count += __popc(b);
+                    count += __popc(__ballot_sync(0xffffffffu, keep));
                 }
                 __syncwarp();
+                if (count == 0) {                                                // clear the map before the retry
+                    for (int i = lane; i < cn; i += 32) sc[(queue[i] >> 8) * SP + (queue[i] & 0xff) + 1] = 0;
+                    __syncwarp();
+                    cn = 0;
+                }
             }
         }
-        // ---- emit: claim a contiguous block of the level's candidate region
-        int base = 0;
+        // ---- emit: claim a contiguous block of the level's candidate region, write in row-major order
+        int gbase = 0;
+        bool overflow = false;
         if (count > 0) {
-            if (lane == 0) base = atomicAdd(&level_counts[frame * nlevels + l], count);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + count > L.cand_cap) {
-                if (lane == 0) atomicOr(&status[frame], ORBX_DEV_CAND_OVERFLOW);
-                count = 0;
+            if (lane == 0) gbase = atomicAdd(&level_counts[cc.frame * nlevels + cc.l], count);
+            gbase = __shfl_sync(0xffffffffu, gbase, 0);
+            if (gbase + count > L.cand_cap) {
+                if (lane == 0) atomicOr(&status[cc.frame], ORBX_DEV_CAND_OVERFLOW);
+                overflow = true;
             }
         }
-        uint32_t* dst = cand + (size_t)frame * plan->cand_per_frame + L.cand_off + base;
-        const int ox = cj * L.wCell, oy = ci * L.hCell;                    // (:822-823)
-        for (int i = lane; i < count; i += 32) {
-            const uint32_t e = queue[i];
-            dst[i] = ORBX_PACK((e & 0xfffu) + ox, ((e >> 12) & 0xfffu) + oy, e >> 24);
+        uint32_t* dst = cand + (size_t)cc.frame * plan->cand_per_frame + L.cand_off + gbase;
+        const int ox = cc.cj * L.wCell, oy = cc.ci * L.hCell;                  // (:822-823)
+        int w = 0;
+        for (int i0 = 0; i0 < cn; i0 += 32) {
+            const int i = i0 + lane;
+            bool keep = false;
+            int x = 0, y = 0, s = 0;
+            if (i < cn) {
+                const int e = queue[i];
+                keep = (e & 0x8000) != 0;
+                y = (e >> 8) & 0x7f;
+                x = e & 0xff;
+                s = sc[y * SP + x + 1];
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            if (keep && !overflow) dst[w + __popc(bal & lt_mask)] = ORBX_PACK(x + ox, y + oy, s);
+            w += __popc(bal);
         }
-        if (lane == 0) cell_rec[item] = make_uint2((uint32_t)base, (uint32_t)count);
         __syncwarp();
+        for (int i = lane; i < cn; i += 32) sc[((queue[i] >> 8) & 0x7f) * SP + (queue[i] & 0xff) + 1] = 0;   // leave the map all-zero
+        if (lane == 0) cell_rec[cur] = make_uint2((uint32_t)gbase, overflow ? 0u : (uint32_t)count);
+        __syncwarp();
+        cur = nxt;
+        cc = nc;
+        b ^= 1;
     }
 }
 
@@ -807,32 +940,66 @@ void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nfr
 }
 
 size_t fast_smem_bytes(const OrbxPlan& hp) {
-    const int SP = (hp.max_cell_w + 3) & ~3;
-    const size_t words = (size_t)SP * hp.max_cell_h / 4 + (size_t)(hp.max_cell_w - 6) * (hp.max_cell_h - 6);
-    return words * 4 * ORBX_FAST_WARPS;
+    const size_t TB = ((size_t)hp.fast_bw * hp.fast_bh + 127) & ~(size_t)127;
+    const size_t SP = (size_t)((hp.max_cell_w + 2 + 3) & ~3);
+    const size_t SB = (SP * hp.fast_bh + 127) & ~(size_t)127;
+    const size_t QB = ((size_t)(hp.max_cell_w - 6) * (hp.max_cell_h - 6) * 2 + 127) & ~(size_t)127;
+    return (2 * TB + SB + QB) * ORBX_FAST_WARPS + 128;
 }
 
-cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* pyr,
-                        uint32_t* cand, uint2* cell_rec, int* level_counts, int* status, cudaStream_t st) {
+// One {pitch, rows, frames} u8 tensor map per level over the pyramid slabs; box = one FAST window.
+int build_fast_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* out_maps) {
+    static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess || !fn)
+            return -1;
+        encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }
+    FastMaps* fm = reinterpret_cast<FastMaps*>(out_maps);
+    memset(fm, 0, sizeof(FastMaps));
+    for (int l = 0; l < hp.nlevels; ++l) {
+        const OrbxLevel& L = hp.lv[l];
+        cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.rows, (cuuint64_t)max_frames};
+        cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)hp.slab_bytes};
+        cuuint32_t box[3] = {(cuuint32_t)hp.fast_bw, (cuuint32_t)hp.fast_bh, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&fm->m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_pyr + L.plane_off, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return -(int)r - 100;
+    }
+    return 0;
+}
+
+size_t fast_maps_bytes() { return sizeof(FastMaps); }
+
+cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, int nframes, int num_sms,
+                        uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counter, int* status,
+                        cudaStream_t st) {
     const size_t smem = fast_smem_bytes(hp);
     static size_t configured[64] = {0};
+    static int per_sm_cache[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (smem > configured[dev & 63]) {
+    if (smem != configured[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = smem;
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_cells_kernel, ORBX_FAST_WARPS * 32, smem);
+        per_sm_cache[dev & 63] = per_sm < 1 ? 1 : per_sm;
     }
     const long long total = (long long)nframes * hp.cells_per_frame;
     long long blocks = (total + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS;
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_cells_kernel, ORBX_FAST_WARPS * 32, smem);
-    if (per_sm < 1) per_sm = 1;
-    const long long cap = (long long)num_sms * per_sm;
+    const long long cap = (long long)num_sms * per_sm_cache[dev & 63];
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    fast_cells_kernel<<<(int)blocks, ORBX_FAST_WARPS * 32, smem, st>>>(d_plan, pyr, nframes, cand, cell_rec,
-                                                                      level_counts, status);
+    fast_cells_kernel<<<(int)blocks, ORBX_FAST_WARPS * 32, smem, st>>>(*reinterpret_cast<const FastMaps*>(maps), d_plan,
+                                                                      nframes, cand, cell_rec, level_counts,
+                                                                      work_counter, status);
     return cudaSuccess;
 }
 

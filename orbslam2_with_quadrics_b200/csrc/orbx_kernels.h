@@ -18,8 +18,11 @@ namespace orbx {
 void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nframes, const uint8_t* imgs,
                       size_t img_pitch, size_t img_frame_stride, uint8_t* pyr, const OrbxTap* taps, cudaStream_t st);
 size_t fast_smem_bytes(const OrbxPlan& hp);
-cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* pyr,
-                        uint32_t* cand, uint2* cell_rec, int* level_counts, int* status, cudaStream_t st);
+int build_fast_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* out_maps);
+size_t fast_maps_bytes();
+cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, int nframes, int num_sms,
+                        uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counter, int* status,
+                        cudaStream_t st);
 size_t octree_smem_bytes(const OrbxPlan& hp);
 cudaError_t launch_octree(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, const uint32_t* cand,
                           const uint2* cell_rec, uint32_t* cand_sorted, uint16_t* key_node, int* sorted_counts,

@@ -48,6 +48,7 @@ struct OrbxPlan {
     int blur_tiles_per_frame;
     int node_cap;             // octree node capacity (max over levels)
     int max_cell_w, max_cell_h;   // largest FAST window (incl. the 6-px overlap)
+    int fast_bw, fast_bh;         // TMA box of a FAST window tile (bw multiple of 16)
     int ini_th, min_th;
     long long slab_bytes;     // one frame's pyramid slab
     float atan_p1, atan_p3, atan_p5, atan_p7;   // cv::fastAtan2 coefficients (float products)
