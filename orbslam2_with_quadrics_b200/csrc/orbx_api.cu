@@ -225,7 +225,7 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
         }
         L.blur_tile_base = tiles;
         L.blur_tiles_x = (L.w + 127) / 128;
-        tiles += L.blur_tiles_x * ((L.h + 15) / 16);
+        tiles += L.blur_tiles_x * ((L.h + 31) / 32);
     }
     if (P->node_cap < 64) P->node_cap = 64;
     if (P->node_cap > 60000) return ORBX_ERR_BAD_ARGS;

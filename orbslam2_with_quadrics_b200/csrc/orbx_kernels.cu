@@ -789,18 +789,30 @@ __global__ void __launch_bounds__(256) orient_kernel(const OrbxPlan* __restrict_
 // =====================================================================================
 // GaussianBlur 7x7 sigma 2 (:1086): separable 8.8 fixed point [18,34,48,56,48,34,18]/256
 // (SURVEY App. A-2).  The padded plane's REFLECT_101 border is exactly the blur's own border
-// mode on the border-less clone, so taps simply read the plane.  128x16 output tile per
-// CTA: source tile and 16-bit row sums staged in shared memory, 4 pixels per 32-bit store.
+// mode on the border-less clone, so taps simply read the plane.
+// One warp owns a 128 x 32 output tile, one lane a 4-pixel-wide column strip, and walks down
+// the rows with everything in registers (no shared memory, no barriers):
+//   row pass     3 aligned 32-bit loads give pixels x-4 .. x+7; each of the 4 row sums is two
+//                IDP.4A (byte dot products) on funnel-shifted words;
+//   column pass  the 16-bit row sums of two consecutive rows are packed into one register,
+//                so each output is four IDP.2A over a ring of 4 row pairs;
+//   store        (sum + 32768) >> 16, four pixels per 32-bit store.
 // =====================================================================================
 #define BL_TW 128
-#define BL_TH 16
-__global__ void __launch_bounds__(256) blur_kernel(const OrbxPlan* __restrict__ plan, int nframes,
+#define BL_TH 32
+__global__ void __launch_bounds__(128) blur_kernel(const OrbxPlan* __restrict__ plan, int nframes,
                                                    const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
-    __shared__ __align__(16) uint8_t s_src[(BL_TH + 6) * (BL_TW + 8)];
-    __shared__ __align__(16) uint16_t s_row[(BL_TH + 6) * BL_TW];
+    const int lane = threadIdx.x & 31;
     const int tpf = plan->blur_tiles_per_frame;
     const long long total = (long long)nframes * tpf;
-    for (long long it = blockIdx.x; it < total; it += gridDim.x) {
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const uint32_t K0123 = 18u | (34u << 8) | (48u << 16) | (56u << 24);
+    const uint32_t K456 = 48u | (34u << 8) | (18u << 16);
+    const uint32_t KA = 18u | (34u << 8) | (48u << 16) | (56u << 24);     // even output: pairs m-3 (lo), m-2 (hi)
+    const uint32_t KB = 48u | (34u << 8) | (18u << 16);                   //              pairs m-1 (lo), m (hi)
+    const uint32_t KC = (18u << 8) | (34u << 16) | (48u << 24);           // odd output:  pairs m-3 (lo), m-2 (hi)
+    const uint32_t KD = 56u | (48u << 8) | (34u << 16) | (18u << 24);     //              pairs m-1 (lo), m (hi)
+    for (long long it = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < total; it += nwarps) {
         const int frame = (int)(it / tpf);
         const int t = (int)(it - (long long)frame * tpf);
         int l = 0;
@@ -808,40 +820,45 @@ __global__ void __launch_bounds__(256) blur_kernel(const OrbxPlan* __restrict__ 
         const OrbxLevel& L = plan->lv[l];
         const int tl = t - L.blur_tile_base;
         const int ty = tl / L.blur_tiles_x, tx = tl - ty * L.blur_tiles_x;
-        const int x0 = tx * BL_TW, y0 = ty * BL_TH;
-        const uint8_t* src = pyr + (size_t)frame * plan->slab_bytes;
-        // stage rows y0-3 .. y0+TH+2, cols x0-3 .. x0+TW+2 (clamped into the padded plane)
-        for (int i = threadIdx.x; i < (BL_TH + 6) * (BL_TW + 6); i += 256) {
-            const int r = i / (BL_TW + 6), c = i - r * (BL_TW + 6);
-            const int yy = min(y0 + r - 3, L.h + ORBX_EDGE - 1);
-            const int xx = min(x0 + c - 3, L.w + ORBX_EDGE - 1);
-            s_src[r * (BL_TW + 8) + c] = *level_px(src, L, xx, yy);
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < (BL_TH + 6) * BL_TW; i += 256) {
-            const int r = i / BL_TW, c = i - r * BL_TW;
-            const uint8_t* p = s_src + r * (BL_TW + 8) + c;
-            s_row[i] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-        }
-        __syncthreads();
-        uint8_t* dstp = blur + (size_t)frame * plan->slab_bytes;
-        const int cx = (threadIdx.x & 31) * 4;
+        const int x = tx * BL_TW + 4 * lane, y0 = ty * BL_TH;
+        if (x >= L.w) continue;
+        const int pitch = L.pitch;
+        const int last_row = L.h + ORBX_EDGE - 1;                         // last valid plane row (level coordinates)
+        const uint8_t* src = pyr + (size_t)frame * plan->slab_bytes + L.plane_off + (size_t)ORBX_EDGE * pitch + ORBX_XO + x - 4;
+        uint8_t* dst = blur + (size_t)frame * plan->slab_bytes + L.plane_off + (size_t)ORBX_EDGE * pitch + ORBX_XO + x;
+        uint32_t P[4][4];                                                 // ring of row pairs x 4 columns
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int ry = (threadIdx.x >> 5) + 8 * k;
-            if (y0 + ry < L.h && x0 + cx < L.w) {
-                uint32_t out = 0;
+        for (int m = 0; m < (BL_TH + 6) / 2; ++m) {
+            uint32_t hs[2][4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint16_t* q = s_row + ry * BL_TW + cx + j;
-                    const uint32_t csum = 18u * (q[0] + q[6 * BL_TW]) + 34u * (q[BL_TW] + q[5 * BL_TW]) +
-                                          48u * (q[2 * BL_TW] + q[4 * BL_TW]) + 56u * q[3 * BL_TW];
-                    out |= ((csum + 32768u) >> 16) << (8 * j);
+            for (int e = 0; e < 2; ++e) {
+                const int yy = min(y0 - 3 + 2 * m + e, last_row);
+                const uint32_t* rp = reinterpret_cast<const uint32_t*>(src + (long long)yy * pitch);
+                const uint32_t w0 = __ldg(rp), w1 = __ldg(rp + 1), w2 = __ldg(rp + 2);
+                hs[e][0] = __dp4a(__funnelshift_r(w0, w1, 8), K0123, __dp4a(__funnelshift_r(w1, w2, 8), K456, 0u));
+                hs[e][1] = __dp4a(__funnelshift_r(w0, w1, 16), K0123, __dp4a(__funnelshift_r(w1, w2, 16), K456, 0u));
+                hs[e][2] = __dp4a(__funnelshift_r(w0, w1, 24), K0123, __dp4a(__funnelshift_r(w1, w2, 24), K456, 0u));
+                hs[e][3] = __dp4a(w1, K0123, __dp4a(w2, K456, 0u));
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) P[m & 3][c] = __byte_perm(hs[0][c], hs[1][c], 0x5410);
+            if (m >= 3) {
+                const int oe = y0 + 2 * m - 6;                            // even output row (level coordinates)
+                uint32_t ve[4], vo[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t p0 = P[(m - 3) & 3][c], p1 = P[(m - 2) & 3][c], p2 = P[(m - 1) & 3][c], p3 = P[m & 3][c];
+                    ve[c] = __dp2a_lo(p0, KA, __dp2a_hi(p1, KA, __dp2a_lo(p2, KB, __dp2a_hi(p3, KB, 32768u))));
+                    vo[c] = __dp2a_lo(p0, KC, __dp2a_hi(p1, KC, __dp2a_lo(p2, KD, __dp2a_hi(p3, KD, 32768u))));
                 }
-                *reinterpret_cast<uint32_t*>(dstp + L.plane_off + (size_t)(y0 + ry + ORBX_EDGE) * L.pitch + ORBX_XO + x0 + cx) = out;
+                if (oe < L.h)
+                    *reinterpret_cast<uint32_t*>(dst + (long long)oe * pitch) =
+                        __byte_perm(__byte_perm(ve[0], ve[1], 0x0062), __byte_perm(ve[2], ve[3], 0x0062), 0x5410);
+                if (oe + 1 < L.h)
+                    *reinterpret_cast<uint32_t*>(dst + (long long)(oe + 1) * pitch) =
+                        __byte_perm(__byte_perm(vo[0], vo[1], 0x0062), __byte_perm(vo[2], vo[3], 0x0062), 0x5410);
             }
         }
-        __syncthreads();
     }
 }
 
@@ -1043,10 +1060,11 @@ void launch_orient(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int 
 
 void launch_blur(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* pyr,
                  uint8_t* blur, cudaStream_t st) {
-    long long blocks = (long long)nframes * hp.blur_tiles_per_frame;
-    const long long cap = (long long)num_sms * 8;
+    long long blocks = ((long long)nframes * hp.blur_tiles_per_frame + 3) / 4;      // one warp per 128 x 32 tile
+    const long long cap = (long long)num_sms * 12;
     if (blocks > cap) blocks = cap;
-    blur_kernel<<<(int)blocks, 256, 0, st>>>(d_plan, nframes, pyr, blur);
+    if (blocks < 1) blocks = 1;
+    blur_kernel<<<(int)blocks, 128, 0, st>>>(d_plan, nframes, pyr, blur);
 }
 
 void launch_desc(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* blur,
