@@ -222,6 +222,21 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
             build_taps(*taps, P->lv[l - 1].w, L.w);
             L.ytab_off = (int)taps->size();
             build_taps(*taps, P->lv[l - 1].h, L.h);
+            // does any lane's group of 4 plane columns need more than 8 consecutive source bytes?
+            L.resize_wide = 0;
+            for (int c = 12; c < ORBX_XO + L.w + ORBX_EDGE; c += 4) {
+                int lo = 1 << 30, hi = 0;
+                for (int j = 0; j < 4; ++j) {
+                    int dx = c + j - ORBX_XO;
+                    if (dx < 0) dx = -dx;
+                    if (dx >= L.w) dx = 2 * (L.w - 1) - dx;
+                    dx = dx < 0 ? 0 : (dx > L.w - 1 ? L.w - 1 : dx);
+                    const int s = (*taps)[L.xtab_off + dx].ofs;
+                    lo = s < lo ? s : lo;
+                    hi = s > hi ? s : hi;
+                }
+                if (hi - (lo & ~3) > 7) L.resize_wide = 1;
+            }
         }
         L.blur_tile_base = tiles;
         L.blur_tiles_x = (L.w + 127) / 128;

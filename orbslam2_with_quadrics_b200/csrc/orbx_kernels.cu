@@ -39,54 +39,124 @@ __device__ __forceinline__ const uint8_t* level_px(const uint8_t* slab, const Or
 }
 
 // =====================================================================================
-// ComputePyramid: every padded pixel is produced directly as f(reflect(x), reflect(y)), so
-// the border needs no second pass (copyMakeBorder of the just-resized level, :1122).
-// Level 0 copies the input (:1127); level l > 0 is the 11-bit fixed-point bilinear
-// resize of level l-1 (cv::resize INTER_LINEAR 8U).  4 pixels / thread,
-// one aligned 32-bit store.
+// ComputePyramid (:1107-1132).  Every padded pixel is produced directly as
+// f(reflect(x), reflect(y)), so the REFLECT_101 border (copyMakeBorder of the just-resized
+// level, :1122) needs no second pass.
+//
+// pyr_level0_kernel: level 0 = the input image plus border (:1127); aligned 32-bit copies in
+// the interior, byte gathers only where the reflection applies.
+//
+// pyr_resize_kernel: level l from level l-1, cv::resize INTER_LINEAR 8U (11-bit fixed point,
+// SURVEY App. A-1).  One lane owns 4 adjacent plane columns (one 32-bit store) and walks down
+// 16 plane rows.  Its column taps live in registers: per pixel the packed weights (a0, a1) for
+// one IDP.2A and the byte offset of its source pair inside three aligned words of the source
+// row.  H[sy][dx] >> 4 is cached for the two most recent source rows, so going down one output
+// row costs ~1.2 row passes; the column pass is two IMAD.HI per pixel.
 // =====================================================================================
-template <bool L0>
-__global__ void __launch_bounds__(256) pyr_level_kernel(const OrbxPlan* __restrict__ plan, int l,
-                                                        const uint8_t* __restrict__ imgs, size_t img_pitch,
-                                                        size_t img_frame_stride, uint8_t* __restrict__ pyr,
-                                                        const OrbxTap* __restrict__ taps) {
-    const OrbxLevel& L = plan->lv[l];
+__global__ void __launch_bounds__(256) pyr_level0_kernel(const OrbxPlan* __restrict__ plan,
+                                                         const uint8_t* __restrict__ imgs, size_t img_pitch,
+                                                         size_t img_frame_stride, int aligned4,
+                                                         uint8_t* __restrict__ pyr) {
+    const OrbxLevel& L = plan->lv[0];
     const int w = L.w, h = L.h;
     const int frame = blockIdx.z;
     const int c = 12 + (blockIdx.x * 32 + threadIdx.x) * 4;        // plane column, multiple of 4
     const int row = blockIdx.y * 8 + threadIdx.y;                  // plane row
     if (row >= L.rows || c >= ORBX_XO + w + ORBX_EDGE) return;
-    uint8_t* slab = pyr + (size_t)frame * plan->slab_bytes;
     const int dy = reflect_clamp(row - ORBX_EDGE, h);
-    uint32_t out = 0;
-    if (L0) {
-        const uint8_t* src = imgs + (size_t)frame * img_frame_stride + (size_t)dy * img_pitch;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int dx = reflect_clamp(c + i - ORBX_XO, w);
-            out |= (uint32_t)__ldg(src + dx) << (8 * i);
-        }
+    const uint8_t* src = imgs + (size_t)frame * img_frame_stride + (size_t)dy * img_pitch;
+    const int dx0 = c - ORBX_XO;
+    uint32_t out;
+    if (aligned4 && dx0 >= 0 && dx0 + 3 < w) {
+        out = __ldg(reinterpret_cast<const uint32_t*>(src + dx0));
     } else {
-        const OrbxLevel& S = plan->lv[l - 1];
-        const OrbxTap ty = taps[L.ytab_off + dy];
-        const int sy1 = min(ty.ofs + 1, S.h - 1);
-        const uint8_t* r0 = level_px(slab, S, 0, ty.ofs);
-        const uint8_t* r1 = level_px(slab, S, 0, sy1);
-        const int b0 = ty.c0, b1 = ty.c1;
+        out = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int dx = reflect_clamp(c + i - ORBX_XO, w);
-            const OrbxTap tx = taps[L.xtab_off + dx];
-            const int sx1 = min(tx.ofs + 1, S.w - 1);
-            const int a0 = tx.c0, a1 = tx.c1;
-            const int H0 = (int)r0[tx.ofs] * a0 + (int)r0[sx1] * a1;
-            const int H1 = (int)r1[tx.ofs] * a0 + (int)r1[sx1] * a1;
-            int v = (((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2;
-            v = min(max(v, 0), 255);
-            out |= (uint32_t)v << (8 * i);
-        }
+        for (int i = 0; i < 4; ++i) out |= (uint32_t)__ldg(src + reflect_clamp(dx0 + i, w)) << (8 * i);
     }
-    *reinterpret_cast<uint32_t*>(slab + L.plane_off + (size_t)row * L.pitch + c) = out;
+    *reinterpret_cast<uint32_t*>(pyr + (size_t)frame * plan->slab_bytes + L.plane_off + (size_t)row * L.pitch + c) = out;
+}
+
+#define PYR_RY 16
+template <bool WIDE>
+__global__ void __launch_bounds__(128) pyr_resize_kernel(const OrbxPlan* __restrict__ plan, int l,
+                                                         uint8_t* __restrict__ pyr,
+                                                         const OrbxTap* __restrict__ taps) {
+    const OrbxLevel& L = plan->lv[l];
+    const OrbxLevel& S = plan->lv[l - 1];
+    const int w = L.w, h = L.h;
+    const int frame = blockIdx.z;
+    const int c = 12 + (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;             // plane column, multiple of 4
+    const int row0 = (blockIdx.y * 4 + (threadIdx.x >> 5)) * PYR_RY;          // first plane row of this warp
+    if (row0 >= L.rows || c >= ORBX_XO + w + ORBX_EDGE) return;
+    uint8_t* slab = pyr + (size_t)frame * plan->slab_bytes;
+    // ---- column taps of the 4 pixels
+    int sx[4];
+    uint32_t coef[4];
+    int minsx = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const OrbxTap t = taps[L.xtab_off + reflect_clamp(c + j - ORBX_XO, w)];
+        sx[j] = t.ofs;
+        coef[j] = (uint32_t)(uint16_t)t.c0 | ((uint32_t)(uint16_t)t.c1 << 16);
+        minsx = min(minsx, t.ofs);
+    }
+    const int wb = minsx & ~3;                                                // first source column of word 0
+    int sh[4], wofs[4];
+    bool hiw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int o = sx[j] - wb;                                             // <= 7 unless WIDE (scale factors > ~1.3)
+        hiw[j] = o >= 4;
+        sh[j] = 8 * (o & 3);
+        wofs[j] = o >> 2;
+    }
+    const uint8_t* sbase = slab + S.plane_off + (size_t)ORBX_EDGE * S.pitch + ORBX_XO + wb;   // row 0 of the source level
+    const int spitch = S.pitch;
+    uint32_t HA[4], HB[4];
+    int rowA = -1, rowB = -1;
+    auto row_pass = [&](int sy, uint32_t* H) {
+        const uint32_t* rp = reinterpret_cast<const uint32_t*>(sbase + (size_t)sy * spitch);
+        if (WIDE) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t pair = __funnelshift_r(rp[wofs[j]], rp[wofs[j] + 1], sh[j]);
+                H[j] = __dp2a_lo(coef[j], pair, 0u) >> 4;
+            }
+        } else {
+            const uint32_t w0 = rp[0], w1 = rp[1], w2 = rp[2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t pair = __funnelshift_r(hiw[j] ? w1 : w0, hiw[j] ? w2 : w1, sh[j]);
+                H[j] = __dp2a_lo(coef[j], pair, 0u) >> 4;                     // (S[sx]*a0 + S[sx+1]*a1) >> 4
+            }
+        }
+    };
+    const int row_end = min(row0 + PYR_RY, L.rows);
+    uint8_t* dst = slab + L.plane_off + (size_t)row0 * L.pitch + c;
+    for (int row = row0; row < row_end; ++row, dst += L.pitch) {
+        const int dy = reflect_clamp(row - ORBX_EDGE, h);
+        const OrbxTap ty = taps[L.ytab_off + dy];
+        const int r0 = ty.ofs, r1 = min(r0 + 1, S.h - 1);
+        if (r0 == rowB) {                                                     // the usual step: one new source row
+#pragma unroll
+            for (int j = 0; j < 4; ++j) HA[j] = HB[j];
+            rowA = rowB;
+            if (r1 != r0) { row_pass(r1, HB); rowB = r1; }
+        } else if (!(r0 == rowA && (r1 == rowB || r1 == r0))) {
+            row_pass(r0, HA);
+            rowA = r0;
+            if (r1 != r0) { row_pass(r1, HB); rowB = r1; } else { rowB = -1; }
+        }
+        const uint32_t b0 = (uint32_t)ty.c0 << 16, b1 = (r1 != r0) ? ((uint32_t)ty.c1 << 16) : 0u;
+        uint32_t out = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t v = (__umulhi(b0, HA[j]) + __umulhi(b1, (r1 != r0) ? HB[j] : 0u) + 2u) >> 2;
+            out |= min(v, 255u) << (8 * j);
+        }
+        *reinterpret_cast<uint32_t*>(dst) = out;
+    }
 }
 
 // =====================================================================================
@@ -949,11 +1019,15 @@ void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nfr
                       cudaStream_t st) {
     const OrbxLevel& L = hp.lv[l];
     const int cols4 = (ORBX_XO + L.w + ORBX_EDGE - 12 + 3) / 4;
-    dim3 block(32, 8), grid((cols4 + 31) / 32, (L.rows + 7) / 8, nframes);
-    if (l == 0)
-        pyr_level_kernel<true><<<grid, block, 0, st>>>(d_plan, l, imgs, img_pitch, img_frame_stride, pyr, taps);
-    else
-        pyr_level_kernel<false><<<grid, block, 0, st>>>(d_plan, l, imgs, img_pitch, img_frame_stride, pyr, taps);
+    if (l == 0) {
+        const int aligned4 = ((reinterpret_cast<uintptr_t>(imgs) | img_pitch | img_frame_stride) & 3) == 0;
+        dim3 block(32, 8), grid((cols4 + 31) / 32, (L.rows + 7) / 8, nframes);
+        pyr_level0_kernel<<<grid, block, 0, st>>>(d_plan, imgs, img_pitch, img_frame_stride, aligned4, pyr);
+    } else {
+        dim3 grid((cols4 + 31) / 32, (L.rows + 4 * PYR_RY - 1) / (4 * PYR_RY), nframes);
+        if (L.resize_wide) pyr_resize_kernel<true><<<grid, 128, 0, st>>>(d_plan, l, pyr, taps);
+        else pyr_resize_kernel<false><<<grid, 128, 0, st>>>(d_plan, l, pyr, taps);
+    }
 }
 
 size_t fast_smem_bytes(const OrbxPlan& hp) {

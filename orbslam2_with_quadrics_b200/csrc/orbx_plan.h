@@ -36,7 +36,7 @@ struct OrbxLevel {
     int xtab_off, ytab_off;   // resize tap tables of this level (entries)
     int blur_tile_base;       // first blur tile of this level inside a frame
     int blur_tiles_x;
-    int pad_;
+    int resize_wide;          // 1: the 4 pixels of a lane span more than two source words (large scale factors)
 };
 
 struct OrbxPlan {
