@@ -51,6 +51,7 @@ struct orbx_handle {
     int* d_counters;             // [level_counts B*L][sorted_counts B*L][kept_counts B*L][status B][work counter]
     std::vector<unsigned char> fast_maps;   // per-level TMA descriptors of the pyramid slabs
     float* d_angles;
+    float2* d_rot;               // (cos, sin) of each kept keypoint's angle
     float* d_out_kp;
     uint8_t* d_out_desc;
     // pinned host mirrors
@@ -262,7 +263,11 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
     P->atan_p5 = 0.1555786518463281f * scale;
     P->atan_p7 = -0.04432655554792128f * scale;
     P->factor_pi = (float)(3.1415926535897932384626433832795 / 180.f);  // (:107)
-    for (int i = 0; i < 16; ++i) P->umax[i] = h->umax[i];
+    static const int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};   // orient_kernel's table
+    for (int i = 0; i < 16; ++i) {
+        P->umax[i] = h->umax[i];
+        if (h->umax[i] != kUmax[i]) return ORBX_ERR_BAD_ARGS;
+    }
     if (orbx::fast_smem_bytes(*P) > 200 * 1024 || orbx::octree_smem_bytes(*P) > 200 * 1024) return ORBX_ERR_BAD_GEOMETRY;
     return ORBX_OK;
 }
@@ -270,13 +275,13 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
 void free_geometry(orbx_handle* h) {
     cudaFree(h->d_plan); cudaFree(h->d_taps); cudaFree(h->d_input); cudaFree(h->d_pyr); cudaFree(h->d_blur);
     cudaFree(h->d_cand); cudaFree(h->d_cand_sorted); cudaFree(h->d_kept); cudaFree(h->d_key_node);
-    cudaFree(h->d_cell_rec); cudaFree(h->d_counters); cudaFree(h->d_angles); cudaFree(h->d_out_kp);
+    cudaFree(h->d_cell_rec); cudaFree(h->d_counters); cudaFree(h->d_angles); cudaFree(h->d_rot); cudaFree(h->d_out_kp);
     cudaFree(h->d_out_desc);
     cudaFreeHost(h->h_counters); cudaFreeHost(h->h_out_kp); cudaFreeHost(h->h_out_desc); cudaFreeHost(h->h_pyr);
     cudaFreeHost(h->h_input);
     h->d_plan = 0; h->d_taps = 0; h->d_input = h->d_pyr = h->d_blur = 0;
     h->d_cand = h->d_cand_sorted = h->d_kept = 0; h->d_key_node = 0; h->d_cell_rec = 0; h->d_counters = 0;
-    h->d_angles = 0; h->d_out_kp = 0; h->d_out_desc = 0;
+    h->d_angles = 0; h->d_rot = 0; h->d_out_kp = 0; h->d_out_desc = 0;
     h->h_counters = 0; h->h_out_kp = 0; h->h_out_desc = 0; h->h_pyr = 0; h->h_input = 0;
     h->have_plan = false;
     h->pyramid_valid = false;
@@ -307,6 +312,7 @@ int ensure_geometry(orbx_handle* h, int w, int hgt) {
     CK(h, cudaMalloc(&h->d_counters, sizeof(int) * h->counters_count()));
     CK(h, cudaMalloc(&h->d_kept, B * P.kept_per_frame * 4));
     CK(h, cudaMalloc(&h->d_angles, B * P.kept_per_frame * 4));
+    CK(h, cudaMalloc(&h->d_rot, B * P.kept_per_frame * sizeof(float2)));
     CK(h, cudaMalloc(&h->d_out_kp, B * P.kept_per_frame * sizeof(orbx_keypoint)));
     CK(h, cudaMalloc(&h->d_out_desc, B * P.kept_per_frame * 32));
     CK(h, cudaMallocHost(&h->h_counters, sizeof(int) * h->counters_count()));
@@ -354,7 +360,7 @@ int enqueue_pipeline(orbx_handle* h, int n, const uint8_t* d_imgs, size_t pitch,
     CK(h, cudaMemsetAsync(h->d_counters, 0, sizeof(int) * h->counters_count(), st));
     if (ev) CK(h, cudaEventRecord(ev[ST_PYRAMID], st));
     for (int l = 0; l < P.nlevels; ++l)
-        orbx::launch_pyr_level(h->d_plan, P, l, n, d_imgs, pitch, frame_stride, h->d_pyr, h->d_taps, st);
+        orbx::launch_pyr_level(h->d_plan, P, l, n, h->num_sms, d_imgs, pitch, frame_stride, h->d_pyr, h->d_taps, st);
     if (ev) CK(h, cudaEventRecord(ev[ST_FAST], st));
     CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), n, h->num_sms, h->d_cand, h->d_cell_rec, h->d_level_counts(),
                             h->d_work_counter(), h->d_status(), st));
@@ -362,11 +368,11 @@ int enqueue_pipeline(orbx_handle* h, int n, const uint8_t* d_imgs, size_t pitch,
     CK(h, orbx::launch_octree(h->d_plan, P, n, h->d_cand, h->d_cell_rec, h->d_cand_sorted, h->d_key_node,
                               h->d_sorted_counts(), h->d_kept, h->d_kept_counts(), h->d_status(), st));
     if (ev) CK(h, cudaEventRecord(ev[ST_ORIENT], st));
-    orbx::launch_orient(h->d_plan, P, n, h->num_sms, h->d_pyr, h->d_kept, h->d_kept_counts(), h->d_angles, st);
+    orbx::launch_orient(h->d_plan, P, n, h->num_sms, h->d_pyr, h->d_kept, h->d_kept_counts(), h->d_angles, h->d_rot, st);
     if (ev) CK(h, cudaEventRecord(ev[ST_BLUR], st));
     orbx::launch_blur(h->d_plan, P, n, h->num_sms, h->d_pyr, h->d_blur, st);
     if (ev) CK(h, cudaEventRecord(ev[ST_DESC], st));
-    orbx::launch_desc(h->d_plan, P, n, h->num_sms, h->d_blur, h->d_kept, h->d_kept_counts(), h->d_angles, h->d_out_kp, h->d_out_desc, st);
+    orbx::launch_desc(h->d_plan, P, n, h->num_sms, h->d_blur, h->d_kept, h->d_kept_counts(), h->d_angles, h->d_rot, h->d_out_kp, h->d_out_desc, st);
     if (ev) {
         CK(h, cudaEventRecord(ev[ST_COUNT], st));
         h->ev_head = (h->ev_head + 1) % kTimingRing;
@@ -452,7 +458,7 @@ int orbx_create(const orbx_config* cfg, orbx_handle** out) {
     h->have_plan = false;
     h->d_plan = 0; h->d_taps = 0; h->d_input = h->d_pyr = h->d_blur = 0;
     h->d_cand = h->d_cand_sorted = h->d_kept = 0; h->d_key_node = 0; h->d_cell_rec = 0; h->d_counters = 0;
-    h->d_angles = 0; h->d_out_kp = 0; h->d_out_desc = 0;
+    h->d_angles = 0; h->d_rot = 0; h->d_out_kp = 0; h->d_out_desc = 0;
     h->h_counters = 0; h->h_out_kp = 0; h->h_out_desc = 0; h->h_pyr = 0; h->h_input = 0;
     h->last_n = 0; h->pyramid_valid = false;
     h->timing = false; h->ev_created = false; h->ev_head = 0; h->ev_pending = 0;

@@ -24,7 +24,9 @@
 
 namespace orbx {
 
-static __constant__ signed char c_pattern[1024] = {
+// In global (not __constant__) memory on purpose: lane i reads ITS 32 bytes, i.e. 32 different
+// addresses per warp, which the constant cache would serialise.
+static __device__ __align__(16) signed char g_pattern[1024] = {
 #include "orb_pattern_31.inc"
 };
 
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(256) pyr_level0_kernel(const OrbxPlan* __restr
 
 #define PYR_RY 16
 template <bool WIDE>
-__global__ void __launch_bounds__(128) pyr_resize_kernel(const OrbxPlan* __restrict__ plan, int l,
+__global__ void __launch_bounds__(128) pyr_resize_kernel(const OrbxPlan* __restrict__ plan, int l, int RY,
                                                          uint8_t* __restrict__ pyr,
                                                          const OrbxTap* __restrict__ taps) {
     const OrbxLevel& L = plan->lv[l];
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const OrbxPlan* __restr
     const int w = L.w, h = L.h;
     const int frame = blockIdx.z;
     const int c = 12 + (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;             // plane column, multiple of 4
-    const int row0 = (blockIdx.y * 4 + (threadIdx.x >> 5)) * PYR_RY;          // first plane row of this warp
+    const int row0 = (blockIdx.y * 4 + (threadIdx.x >> 5)) * RY;              // first plane row of this warp
     if (row0 >= L.rows || c >= ORBX_XO + w + ORBX_EDGE) return;
     uint8_t* slab = pyr + (size_t)frame * plan->slab_bytes;
     // ---- column taps of the 4 pixels
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const OrbxPlan* __restr
             }
         }
     };
-    const int row_end = min(row0 + PYR_RY, L.rows);
+    const int row_end = min(row0 + RY, L.rows);
     uint8_t* dst = slab + L.plane_off + (size_t)row0 * L.pitch + c;
     for (int row = row0; row < row_end; ++row, dst += L.pitch) {
         const int dy = reflect_clamp(row - ORBX_EDGE, h);
@@ -152,8 +154,9 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const OrbxPlan* __restr
         uint32_t out = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+            // <= 255: the weights sum to 2048 and H >> 4 <= 255 * 128
             const uint32_t v = (__umulhi(b0, HA[j]) + __umulhi(b1, (r1 != r0) ? HB[j] : 0u) + 2u) >> 2;
-            out |= min(v, 255u) << (8 * j);
+            out |= v << (8 * j);
         }
         *reinterpret_cast<uint32_t*>(dst) = out;
     }
@@ -209,16 +212,16 @@ struct FastCell {
     int frame, l, ci, cj;
 };
 
-__device__ __forceinline__ FastCell fast_decode(const OrbxPlan* __restrict__ plan, long long item) {
+__device__ __forceinline__ FastCell fast_decode(const OrbxPlan* __restrict__ plan, unsigned item) {
     FastCell c;
-    const int cpf = plan->cells_per_frame;
+    const unsigned cpf = (unsigned)plan->cells_per_frame;
     c.frame = (int)(item / cpf);
-    const int r = (int)(item - (long long)c.frame * cpf);
+    const int r = (int)(item - (unsigned)c.frame * cpf);
     int l = 0;
     while (l + 1 < plan->nlevels && r >= plan->lv[l + 1].cell_base) ++l;
     c.l = l;
     const OrbxLevel& L = plan->lv[l];
-    c.ci = (r - L.cell_base) / L.nColsV;
+    c.ci = (int)((unsigned)(r - L.cell_base) / (unsigned)L.nColsV);
     c.cj = (r - L.cell_base) - c.ci * L.nColsV;
     return c;
 }
@@ -282,7 +285,7 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
     uint8_t* sc = base + 2 * TB;                                         // zero-framed score map
     uint16_t* queue = reinterpret_cast<uint16_t*>(base + 2 * TB + SB);   // entries (y << 8) | x, window coordinates
     const int nlevels = plan->nlevels;
-    const long long total = (long long)nframes * plan->cells_per_frame;
+    const unsigned total = (unsigned)nframes * (unsigned)plan->cells_per_frame;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int BW4 = BW >> 2;
 
@@ -295,10 +298,10 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
     }
     __syncwarp();
 
-    auto fetch = [&]() -> long long {
+    auto fetch = [&]() -> unsigned {
         int v = 0;
         if (lane == 0) v = atomicAdd(work_counter, 1);
-        return (long long)__shfl_sync(0xffffffffu, v, 0);
+        return (unsigned)__shfl_sync(0xffffffffu, v, 0);
     };
     auto issue = [&](const FastCell& c, int b) {
         if (lane == 0) {
@@ -309,13 +312,13 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
         }
     };
 
-    long long cur = fetch();
+    unsigned cur = fetch();
     FastCell cc, nc;
     if (cur < total) { cc = fast_decode(plan, cur); issue(cc, 0); }
     uint32_t phase[2] = {0, 0};
     int b = 0;
     while (cur < total) {
-        const long long nxt = fetch();
+        const unsigned nxt = fetch();
         if (nxt < total) { nc = fast_decode(plan, nxt); issue(nc, b ^ 1); }
         mbar_wait(&s_bar[warp][b], phase[b]);
         phase[b] ^= 1;
@@ -332,8 +335,9 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
         if (ww >= 7 && wh >= 7) {
             const int ew = ww - 6;                                       // emission width
             const int G = (ew + 3) >> 2;                                 // 4-pixel groups per row
-            const int RPI = 32 / G;                                      // rows per warp iteration
-            const int ry = lane / G, g = lane - ry * G;
+            const int mg = (int)((65536u + (unsigned)G - 1u) / (unsigned)G);   // (n * mg) >> 16 == n / G for n <= 32
+            const int RPI = (32 * mg) >> 16;                             // rows per warp iteration
+            const int ry = (lane * mg) >> 16, g = lane - ry * G;
             const int nvalid = min(max(ew - 4 * g, 0), 4);
             const uint32_t vmask = (ry < RPI && nvalid > 0) ? (0x80808080u >> (8 * (4 - nvalid))) : 0u;
             for (int pass = 0; pass < 2 && count == 0; ++pass) {
@@ -822,37 +826,51 @@ __global__ void __launch_bounds__(256) orient_kernel(const OrbxPlan* __restrict_
                                                      const uint8_t* __restrict__ pyr,
                                                      const uint32_t* __restrict__ kept,
                                                      const int* __restrict__ kept_counts,
-                                                     float* __restrict__ angles) {
+                                                     float* __restrict__ angles, float2* __restrict__ rot) {
+    // umax (:454-469) is a function of HALF_PATCH_SIZE only; the host-computed copy in the plan is
+    // checked against this table when the plan is built.
+    constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
     const int lane = threadIdx.x & 31;
     const int kpf = plan->kept_per_frame;
-    const long long total = (long long)nframes * kpf;
-    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long it = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < total; it += nwarps) {
-        const int frame = (int)(it / kpf);
-        const int s = (int)(it - (long long)frame * kpf);
+    const unsigned total = (unsigned)nframes * (unsigned)kpf;
+    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+    const int u = lane - 15, au = abs(u);
+    for (unsigned it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < total; it += nwarps) {
+        const int frame = (int)(it / (unsigned)kpf);
+        const int s = (int)(it - (unsigned)frame * (unsigned)kpf);
         const int l = level_of_slot(plan, s);
         const OrbxLevel& L = plan->lv[l];
         if (s - L.kept_off >= kept_counts[frame * plan->nlevels + l]) continue;
         const uint32_t p = kept[it];
-        const uint8_t* center = level_px(pyr + (size_t)frame * plan->slab_bytes, L, ORBX_PX(p), ORBX_PY(p));
-        const int u = lane - 15;
+        const uint8_t* center = level_px(pyr + (size_t)frame * plan->slab_bytes, L, ORBX_PX(p), ORBX_PY(p)) + u;
+        const int pitch = L.pitch;
         int m10 = 0, m01 = 0;
         if (lane < 31) {
-            const int au = abs(u);
+            int vals[31];
+#pragma unroll
+            for (int v = -15; v <= 15; ++v) vals[v + 15] = (au <= UMAX[v < 0 ? -v : v]) ? (int)center[v * pitch] : 0;
+            int colsum = 0;
+#pragma unroll
             for (int v = -15; v <= 15; ++v) {
-                if (au <= plan->umax[abs(v)]) {
-                    const int val = center[v * L.pitch + u];
-                    m10 += u * val;
-                    m01 += v * val;
-                }
+                colsum += vals[v + 15];
+                m01 += v * vals[v + 15];
             }
+            m10 = u * colsum;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             m10 += __shfl_xor_sync(0xffffffffu, m10, o);
             m01 += __shfl_xor_sync(0xffffffffu, m01, o);
         }
-        if (lane == 0) angles[it] = fast_atan2_deg((float)m01, (float)m10, plan);
+        if (lane == 0) {
+            const float angle = fast_atan2_deg((float)m01, (float)m10, plan);
+            angles[it] = angle;
+            // rotation of computeOrbDescriptor (:111-113) under canonical rule B-2: float(cos/sin in double)
+            const float rad = __fmul_rn(angle, plan->factor_pi);
+            double sn, cs;
+            sincos((double)rad, &sn, &cs);
+            rot[it] = make_float2((float)cs, (float)sn);
+        }
     }
 }
 
@@ -940,25 +958,31 @@ __global__ void __launch_bounds__(128) blur_kernel(const OrbxPlan* __restrict__ 
 // a, b = float(cos/sin in double); products and sums individually rounded; round-half-even.
 // =====================================================================================
 __global__ void __launch_bounds__(256) desc_kernel(const OrbxPlan* __restrict__ plan, int nframes,
-                                                   const uint8_t* __restrict__ blur,
-                                                   const uint32_t* __restrict__ kept,
-                                                   const int* __restrict__ kept_counts,
-                                                   const float* __restrict__ angles,
-                                                   float* __restrict__ out_kp, uint8_t* __restrict__ out_desc) {
+                                                      const uint8_t* __restrict__ blur,
+                                                      const uint32_t* __restrict__ kept,
+                                                      const int* __restrict__ kept_counts,
+                                                      const float* __restrict__ angles,
+                                                      const float2* __restrict__ rot,
+                                                      float* __restrict__ out_kp, uint8_t* __restrict__ out_desc) {
     const int lane = threadIdx.x & 31;
     float px[16], py[16];
+    {
+        const uint4 lo = reinterpret_cast<const uint4*>(g_pattern)[lane * 2], hi = reinterpret_cast<const uint4*>(g_pattern)[lane * 2 + 1];
+        const uint32_t wds[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        px[j] = (float)c_pattern[lane * 32 + 2 * j];
-        py[j] = (float)c_pattern[lane * 32 + 2 * j + 1];
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t wd = wds[j >> 1] >> (16 * (j & 1));
+            px[j] = (float)(int)(signed char)(wd & 0xff);
+            py[j] = (float)(int)(signed char)((wd >> 8) & 0xff);
+        }
     }
     const int kpf = plan->kept_per_frame;
     const int nl = plan->nlevels;
-    const long long total = (long long)nframes * kpf;
-    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long it = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < total; it += nwarps) {
-        const int frame = (int)(it / kpf);
-        const int s = (int)(it - (long long)frame * kpf);
+    const unsigned total = (unsigned)nframes * (unsigned)kpf;
+    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+    for (unsigned it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < total; it += nwarps) {
+        const int frame = (int)(it / (unsigned)kpf);
+        const int s = (int)(it - (unsigned)frame * (unsigned)kpf);
         const int l = level_of_slot(plan, s);
         const OrbxLevel& L = plan->lv[l];
         const int* kc = kept_counts + frame * nl;
@@ -969,8 +993,8 @@ __global__ void __launch_bounds__(256) desc_kernel(const OrbxPlan* __restrict__ 
         const uint32_t p = kept[it];
         const int kx = ORBX_PX(p), ky = ORBX_PY(p);
         const float angle = angles[it];
-        const float rad = __fmul_rn(angle, plan->factor_pi);               // (:111)
-        const float a = (float)cos((double)rad), b = (float)sin((double)rad);
+        const float2 ab = rot[it];                                         // (cos, sin) from orient_kernel (:111-113)
+        const float a = ab.x, b = ab.y;
         const uint8_t* center = level_px(blur + (size_t)frame * plan->slab_bytes, L, kx, ky);
         const int pitch = L.pitch;
         uint32_t byte = 0;
@@ -1014,7 +1038,7 @@ __global__ void __launch_bounds__(256) desc_kernel(const OrbxPlan* __restrict__ 
 // =====================================================================================
 // launch wrappers (called from orbx_api.cu)
 // =====================================================================================
-void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nframes, const uint8_t* imgs,
+void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nframes, int num_sms, const uint8_t* imgs,
                       size_t img_pitch, size_t img_frame_stride, uint8_t* pyr, const OrbxTap* taps,
                       cudaStream_t st) {
     const OrbxLevel& L = hp.lv[l];
@@ -1024,9 +1048,12 @@ void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nfr
         dim3 block(32, 8), grid((cols4 + 31) / 32, (L.rows + 7) / 8, nframes);
         pyr_level0_kernel<<<grid, block, 0, st>>>(d_plan, imgs, img_pitch, img_frame_stride, aligned4, pyr);
     } else {
-        dim3 grid((cols4 + 31) / 32, (L.rows + 4 * PYR_RY - 1) / (4 * PYR_RY), nframes);
-        if (L.resize_wide) pyr_resize_kernel<true><<<grid, 128, 0, st>>>(d_plan, l, pyr, taps);
-        else pyr_resize_kernel<false><<<grid, 128, 0, st>>>(d_plan, l, pyr, taps);
+        // rows per warp: long strips reuse row passes (1 + 1/RY... per row) but small levels need warps
+        int RY = PYR_RY;
+        while (RY > 4 && (long long)((cols4 + 31) / 32) * ((L.rows + RY - 1) / RY) * nframes < (long long)num_sms * 32) RY >>= 1;
+        dim3 grid((cols4 + 31) / 32, (L.rows + 4 * RY - 1) / (4 * RY), nframes);
+        if (L.resize_wide) pyr_resize_kernel<true><<<grid, 128, 0, st>>>(d_plan, l, RY, pyr, taps);
+        else pyr_resize_kernel<false><<<grid, 128, 0, st>>>(d_plan, l, RY, pyr, taps);
     }
 }
 
@@ -1127,9 +1154,9 @@ static int warp_grid(long long items, int num_sms) {
 }
 
 void launch_orient(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* pyr,
-                   const uint32_t* kept, const int* kept_counts, float* angles, cudaStream_t st) {
+                   const uint32_t* kept, const int* kept_counts, float* angles, float2* rot, cudaStream_t st) {
     orient_kernel<<<warp_grid((long long)nframes * hp.kept_per_frame, num_sms), 256, 0, st>>>(d_plan, nframes, pyr, kept,
-                                                                                              kept_counts, angles);
+                                                                                              kept_counts, angles, rot);
 }
 
 void launch_blur(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* pyr,
@@ -1142,10 +1169,10 @@ void launch_blur(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int nu
 }
 
 void launch_desc(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* blur,
-                 const uint32_t* kept, const int* kept_counts, const float* angles, float* out_kp,
-                 uint8_t* out_desc, cudaStream_t st) {
+                 const uint32_t* kept, const int* kept_counts, const float* angles, const float2* rot,
+                 float* out_kp, uint8_t* out_desc, cudaStream_t st) {
     desc_kernel<<<warp_grid((long long)nframes * hp.kept_per_frame, num_sms), 256, 0, st>>>(
-        d_plan, nframes, blur, kept, kept_counts, angles, out_kp, out_desc);
+        d_plan, nframes, blur, kept, kept_counts, angles, rot, out_kp, out_desc);
 }
 
 }  // namespace orbx

@@ -15,7 +15,7 @@
 
 namespace orbx {
 
-void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nframes, const uint8_t* imgs,
+void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nframes, int num_sms, const uint8_t* imgs,
                       size_t img_pitch, size_t img_frame_stride, uint8_t* pyr, const OrbxTap* taps, cudaStream_t st);
 size_t fast_smem_bytes(const OrbxPlan& hp);
 int build_fast_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* out_maps);
@@ -28,11 +28,11 @@ cudaError_t launch_octree(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframe
                           const uint2* cell_rec, uint32_t* cand_sorted, uint16_t* key_node, int* sorted_counts,
                           uint32_t* kept, int* kept_counts, int* status, cudaStream_t st);
 void launch_orient(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* pyr,
-                   const uint32_t* kept, const int* kept_counts, float* angles, cudaStream_t st);
+                   const uint32_t* kept, const int* kept_counts, float* angles, float2* rot, cudaStream_t st);
 void launch_blur(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* pyr,
                  uint8_t* blur, cudaStream_t st);
 void launch_desc(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* blur,
-                 const uint32_t* kept, const int* kept_counts, const float* angles, float* out_kp, uint8_t* out_desc,
-                 cudaStream_t st);
+                 const uint32_t* kept, const int* kept_counts, const float* angles, const float2* rot, float* out_kp,
+                 uint8_t* out_desc, cudaStream_t st);
 
 }  // namespace orbx
