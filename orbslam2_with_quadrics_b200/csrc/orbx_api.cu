@@ -20,6 +20,7 @@ namespace {
 enum { ST_PYRAMID = 0, ST_FAST, ST_OCTREE, ST_ORIENT, ST_BLUR, ST_DESC, ST_COUNT };
 const char* kStageNames[ST_COUNT] = {"pyramid", "fast_cells", "octree", "orient", "blur", "descriptor"};
 const int kTimingRing = 64;
+const int kMaxChunks = 8;         // sub-batches of one extract_batch call that overlap H2D, kernels and D2H
 
 template <typename T> T round_up(T v, T a) { return (v + a - 1) / a * a; }
 
@@ -28,7 +29,10 @@ template <typename T> T round_up(T v, T a) { return (v + a - 1) / a * a; }
 struct orbx_handle {
     orbx_config cfg;
     int num_sms;
-    cudaStream_t stream;
+    cudaStream_t stream;          // kernels
+    cudaStream_t stream2;         // second kernel stream: alternate sub-batches so their latency-bound tails overlap
+    cudaStream_t h2d_stream, d2h_stream;
+    cudaEvent_t ev_h2d[8], ev_done[8], ev_clear;
     std::string last_error;
     long long launches;
 
@@ -71,7 +75,7 @@ struct orbx_handle {
     double stage_ms[ST_COUNT];
     int stage_launches[ST_COUNT];
 
-    int counters_count() const { return cfg.max_batch * (3 * plan.nlevels + 1) + 1; }
+    int counters_count() const { return cfg.max_batch * (3 * plan.nlevels + 1) + kMaxChunks; }
     int* d_level_counts() const { return d_counters; }
     int* d_sorted_counts() const { return d_counters + cfg.max_batch * plan.nlevels; }
     int* d_kept_counts() const { return d_counters + 2 * cfg.max_batch * plan.nlevels; }
@@ -349,43 +353,69 @@ void timing_collect(orbx_handle* h, int upto_pending) {
     }
 }
 
-int enqueue_pipeline(orbx_handle* h, int n, const uint8_t* d_imgs, size_t pitch, size_t frame_stride) {
+// Enqueues the whole path for frames [f0, f0 + n) on stream st.  All per-frame arrays are frame-major, so a chunk is
+// addressed by offsetting the base pointers; only the TMA tile fetch needs the absolute frame index (frame0).
+int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t pitch, size_t frame_stride, int chunk,
+                   cudaStream_t st) {
     const OrbxPlan& P = h->plan;
-    cudaStream_t st = h->stream;
+    const int L = P.nlevels;
     cudaEvent_t* ev = 0;
     if (h->timing) {
         if (h->ev_pending == kTimingRing) timing_collect(h, 1);
         ev = h->ev[h->ev_head];
     }
-    CK(h, cudaMemsetAsync(h->d_counters, 0, sizeof(int) * h->counters_count(), st));
+    uint8_t* pyr = h->d_pyr + (size_t)f0 * P.slab_bytes;
+    uint8_t* blur = h->d_blur + (size_t)f0 * P.slab_bytes;
+    uint32_t* cand = h->d_cand + (size_t)f0 * P.cand_per_frame;
+    uint32_t* cand_sorted = h->d_cand_sorted + (size_t)f0 * P.cand_per_frame;
+    uint16_t* key_node = h->d_key_node + (size_t)f0 * P.cand_per_frame;
+    uint2* cell_rec = h->d_cell_rec + (size_t)f0 * P.cells_per_frame;
+    uint32_t* kept = h->d_kept + (size_t)f0 * P.kept_per_frame;
+    float* angles = h->d_angles + (size_t)f0 * P.kept_per_frame;
+    float2* rot = h->d_rot + (size_t)f0 * P.kept_per_frame;
+    float* out_kp = h->d_out_kp + (size_t)f0 * P.kept_per_frame * 7;
+    uint8_t* out_desc = h->d_out_desc + (size_t)f0 * P.kept_per_frame * 32;
+    int* level_counts = h->d_level_counts() + f0 * L;
+    int* sorted_counts = h->d_sorted_counts() + f0 * L;
+    int* kept_counts = h->d_kept_counts() + f0 * L;
+    int* status = h->d_status() + f0;
     if (ev) CK(h, cudaEventRecord(ev[ST_PYRAMID], st));
-    for (int l = 0; l < P.nlevels; ++l)
-        orbx::launch_pyr_level(h->d_plan, P, l, n, h->num_sms, d_imgs, pitch, frame_stride, h->d_pyr, h->d_taps, st);
+    for (int l = 0; l < L; ++l)
+        orbx::launch_pyr_level(h->d_plan, P, l, n, h->num_sms, d_imgs, pitch, frame_stride, pyr, h->d_taps, st);
     if (ev) CK(h, cudaEventRecord(ev[ST_FAST], st));
-    CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), n, h->num_sms, h->d_cand, h->d_cell_rec, h->d_level_counts(),
-                            h->d_work_counter(), h->d_status(), st));
+    CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), f0, n, h->num_sms, cand, cell_rec, level_counts,
+                            h->d_work_counter() + chunk, status, st));
     if (ev) CK(h, cudaEventRecord(ev[ST_OCTREE], st));
-    CK(h, orbx::launch_octree(h->d_plan, P, n, h->d_cand, h->d_cell_rec, h->d_cand_sorted, h->d_key_node,
-                              h->d_sorted_counts(), h->d_kept, h->d_kept_counts(), h->d_status(), st));
+    CK(h, orbx::launch_octree(h->d_plan, P, n, cand, cell_rec, cand_sorted, key_node, sorted_counts, kept, kept_counts,
+                              status, st));
     if (ev) CK(h, cudaEventRecord(ev[ST_ORIENT], st));
-    orbx::launch_orient(h->d_plan, P, n, h->num_sms, h->d_pyr, h->d_kept, h->d_kept_counts(), h->d_angles, h->d_rot, st);
+    orbx::launch_orient(h->d_plan, P, n, h->num_sms, pyr, kept, kept_counts, angles, rot, st);
     if (ev) CK(h, cudaEventRecord(ev[ST_BLUR], st));
-    orbx::launch_blur(h->d_plan, P, n, h->num_sms, h->d_pyr, h->d_blur, st);
+    orbx::launch_blur(h->d_plan, P, n, h->num_sms, pyr, blur, st);
     if (ev) CK(h, cudaEventRecord(ev[ST_DESC], st));
-    orbx::launch_desc(h->d_plan, P, n, h->num_sms, h->d_blur, h->d_kept, h->d_kept_counts(), h->d_angles, h->d_rot, h->d_out_kp, h->d_out_desc, st);
+    orbx::launch_desc(h->d_plan, P, n, h->num_sms, blur, kept, kept_counts, angles, rot, out_kp, out_desc, st);
     if (ev) {
         CK(h, cudaEventRecord(ev[ST_COUNT], st));
         h->ev_head = (h->ev_head + 1) % kTimingRing;
         ++h->ev_pending;
-        h->stage_launches[ST_PYRAMID] += P.nlevels;
+        h->stage_launches[ST_PYRAMID] += L;
         for (int s = ST_FAST; s < ST_COUNT; ++s) h->stage_launches[s] += 1;
     }
-    h->launches += P.nlevels + 5;
+    h->launches += L + 5;
     CK(h, cudaGetLastError());
+    return ORBX_OK;
+}
+
+int enqueue_pipeline(orbx_handle* h, int n, const uint8_t* d_imgs, size_t pitch, size_t frame_stride) {
+    CK(h, cudaMemsetAsync(h->d_counters, 0, sizeof(int) * h->counters_count(), h->stream));
+    int rc = enqueue_frames(h, 0, n, d_imgs, pitch, frame_stride, 0, h->stream);
+    if (rc != ORBX_OK) return rc;
     h->last_n = n;
     h->pyramid_valid = false;
     return ORBX_OK;
 }
+
+int finish_results(orbx_handle* h, int n, orbx_result* results);
 
 int fetch(orbx_handle* h, int n, orbx_result* results) {
     const OrbxPlan& P = h->plan;
@@ -397,6 +427,12 @@ int fetch(orbx_handle* h, int n, orbx_result* results) {
     if (h->cfg.download_pyramid)
         CK(h, cudaMemcpyAsync(h->h_pyr, h->d_pyr, (size_t)n * P.slab_bytes, cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
+    return finish_results(h, n, results);
+}
+
+int finish_results(orbx_handle* h, int n, orbx_result* results) {
+    const OrbxPlan& P = h->plan;
+    const size_t kpf = (size_t)P.kept_per_frame;
     h->pyramid_valid = h->cfg.download_pyramid != 0;
     int rc = ORBX_OK;
     for (int f = 0; f < n; ++f) {
@@ -467,6 +503,15 @@ int orbx_create(const orbx_config* cfg, orbx_handle** out) {
     h->stream = 0;
     cudaError_t e = cudaSetDevice(cfg->device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    h->h2d_stream = h->d2h_stream = h->stream2 = 0;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_clear, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < kMaxChunks && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
     if (e != cudaSuccess) {
         delete h;
@@ -481,10 +526,18 @@ int orbx_destroy(orbx_handle* h) {
     if (!h) return ORBX_ERR_BAD_ARGS;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->stream2);
+    cudaStreamSynchronize(h->h2d_stream);
+    cudaStreamSynchronize(h->d2h_stream);
     free_geometry(h);
     if (h->ev_created)
         for (int i = 0; i < kTimingRing; ++i)
             for (int s = 0; s <= ST_COUNT; ++s) cudaEventDestroy(h->ev[i][s]);
+    for (int i = 0; i < kMaxChunks; ++i) { cudaEventDestroy(h->ev_h2d[i]); cudaEventDestroy(h->ev_done[i]); }
+    cudaEventDestroy(h->ev_clear);
+    cudaStreamDestroy(h->stream2);
+    cudaStreamDestroy(h->h2d_stream);
+    cudaStreamDestroy(h->d2h_stream);
     cudaStreamDestroy(h->stream);
     delete h;
     return ORBX_OK;
@@ -515,26 +568,54 @@ int orbx_extract_batch(orbx_handle* h, int n, const uint8_t* const* imgs, int wi
     CK(h, cudaSetDevice(h->cfg.device));
     int rc = ensure_geometry(h, width, height);
     if (rc != ORBX_OK) return rc;
+    const OrbxPlan& P = h->plan;
     const size_t fbytes = (size_t)height * h->in_pitch;
-    for (int i = 0; i < n; ++i) {
-        const size_t stride = strides ? strides[i] : (size_t)width;
-        cudaPointerAttributes attr;
-        bool pinned = cudaPointerGetAttributes(&attr, imgs[i]) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-        if (!pinned) cudaGetLastError();
-        const uint8_t* src = imgs[i];
-        size_t spitch = stride;
-        if (!pinned) {     // pageable caller memory: stage through the handle's pinned buffer
-            uint8_t* stg = h->h_input + i * fbytes;
-            for (int y = 0; y < height; ++y) memcpy(stg + (size_t)y * h->in_pitch, imgs[i] + (size_t)y * stride, (size_t)width);
-            src = stg;
-            spitch = (size_t)h->in_pitch;
+    const size_t kpf = (size_t)P.kept_per_frame;
+    // Sub-batches pipeline the three engines: H2D of chunk k+1, kernels of chunk k and D2H of chunk k-1 overlap.
+    int nchunks = n >= 16 ? 4 : (n >= 4 ? 2 : 1);
+    if (nchunks > kMaxChunks) nchunks = kMaxChunks;
+    CK(h, cudaMemsetAsync(h->d_counters, 0, sizeof(int) * h->counters_count(), h->stream));
+    CK(h, cudaEventRecord(h->ev_clear, h->stream));
+    CK(h, cudaStreamWaitEvent(h->stream2, h->ev_clear, 0));
+    for (int k = 0; k < nchunks; ++k) {
+        cudaStream_t cs = (k & 1) ? h->stream2 : h->stream;
+        const int f0 = (int)((long long)n * k / nchunks), f1 = (int)((long long)n * (k + 1) / nchunks);
+        for (int i = f0; i < f1; ++i) {
+            const size_t stride = strides ? strides[i] : (size_t)width;
+            cudaPointerAttributes attr;
+            bool pinned = cudaPointerGetAttributes(&attr, imgs[i]) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+            if (!pinned) cudaGetLastError();
+            const uint8_t* src = imgs[i];
+            size_t spitch = stride;
+            if (!pinned) {     // pageable caller memory: stage through the handle's pinned buffer
+                uint8_t* stg = h->h_input + i * fbytes;
+                for (int y = 0; y < height; ++y) memcpy(stg + (size_t)y * h->in_pitch, imgs[i] + (size_t)y * stride, (size_t)width);
+                src = stg;
+                spitch = (size_t)h->in_pitch;
+            }
+            CK(h, cudaMemcpy2DAsync(h->d_input + i * fbytes, (size_t)h->in_pitch, src, spitch, (size_t)width, (size_t)height,
+                                    cudaMemcpyHostToDevice, h->h2d_stream));
         }
-        CK(h, cudaMemcpy2DAsync(h->d_input + i * fbytes, (size_t)h->in_pitch, src, spitch, (size_t)width, (size_t)height,
-                                cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaEventRecord(h->ev_h2d[k], h->h2d_stream));
+        CK(h, cudaStreamWaitEvent(cs, h->ev_h2d[k], 0));
+        rc = enqueue_frames(h, f0, f1 - f0, h->d_input + f0 * fbytes, (size_t)h->in_pitch, fbytes, k, cs);
+        if (rc != ORBX_OK) return rc;
+        CK(h, cudaEventRecord(h->ev_done[k], cs));
+        CK(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_done[k], 0));
+        CK(h, cudaMemcpyAsync(h->h_out_kp + f0 * kpf * 7, h->d_out_kp + f0 * kpf * 7, (f1 - f0) * kpf * sizeof(orbx_keypoint),
+                              cudaMemcpyDeviceToHost, h->d2h_stream));
+        CK(h, cudaMemcpyAsync(h->h_out_desc + f0 * kpf * 32, h->d_out_desc + f0 * kpf * 32, (f1 - f0) * kpf * 32,
+                              cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (h->cfg.download_pyramid)
+            CK(h, cudaMemcpyAsync(h->h_pyr + (size_t)f0 * P.slab_bytes, h->d_pyr + (size_t)f0 * P.slab_bytes,
+                                  (size_t)(f1 - f0) * P.slab_bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
     }
-    rc = enqueue_pipeline(h, n, h->d_input, (size_t)h->in_pitch, fbytes);
-    if (rc != ORBX_OK) return rc;
-    return fetch(h, n, results);
+    CK(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int) * h->counters_count(), cudaMemcpyDeviceToHost, h->d2h_stream));
+    CK(h, cudaStreamSynchronize(h->d2h_stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaStreamSynchronize(h->stream2));
+    h->last_n = n;
+    return finish_results(h, n, results);
 }
 
 int orbx_extract(orbx_handle* h, const uint8_t* img, int width, int height, size_t stride, orbx_result* result) {

@@ -269,7 +269,7 @@ __device__ __forceinline__ int fast_score_packed(const uint8_t* __restrict__ p, 
 }
 
 __global__ void __launch_bounds__(ORBX_FAST_WARPS * 32, 3)
-fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, int nframes,
+fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, int frame0, int nframes,
                   uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec, int* __restrict__ level_counts,
                   int* __restrict__ work_counter, int* __restrict__ status) {
     extern __shared__ uint8_t fast_smem_raw[];
@@ -308,7 +308,7 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
             const OrbxLevel& L = plan->lv[c.l];
             mbar_expect_tx(&s_bar[warp][b], (uint32_t)(BW * BH));
             tma_load_3d(base + b * TB, &maps.m[c.l], &s_bar[warp][b], (ORBX_XO + ORBX_BOX + c.cj * L.wCell - 1) & ~15,
-                        ORBX_EDGE + ORBX_BOX + c.ci * L.hCell, c.frame);
+                        ORBX_EDGE + ORBX_BOX + c.ci * L.hCell, frame0 + c.frame);
         }
     };
 
@@ -1094,7 +1094,7 @@ int build_fast_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* ou
 
 size_t fast_maps_bytes() { return sizeof(FastMaps); }
 
-cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, int nframes, int num_sms,
+cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, int frame0, int nframes, int num_sms,
                         uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counter, int* status,
                         cudaStream_t st) {
     const size_t smem = fast_smem_bytes(hp);
@@ -1116,7 +1116,7 @@ cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* 
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     fast_cells_kernel<<<(int)blocks, ORBX_FAST_WARPS * 32, smem, st>>>(*reinterpret_cast<const FastMaps*>(maps), d_plan,
-                                                                      nframes, cand, cell_rec, level_counts,
+                                                                      frame0, nframes, cand, cell_rec, level_counts,
                                                                       work_counter, status);
     return cudaSuccess;
 }

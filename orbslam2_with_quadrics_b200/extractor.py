@@ -85,7 +85,9 @@ class ORBextractor:
             return None
         return self.extract_batch([image])[0]
 
-    def extract_batch(self, images: Sequence[np.ndarray]):
+    def extract_batch(self, images: Sequence[np.ndarray], copy: bool = True):
+        """n frames of identical shape in one launch sequence.  With copy=False the returned arrays are
+        views of the library's pinned result buffers, valid until the next call (the C ABI's contract)."""
         n = len(images)
         if n == 0:
             return []
@@ -99,31 +101,35 @@ class ORBextractor:
             if im.strides[1] != 1:
                 im = np.ascontiguousarray(im)
             keep.append(im)
-            ptrs[i] = im.ctypes.data
+            ptrs[i] = im.__array_interface__["data"][0]
             strides[i] = im.strides[0]
         res = (OrbxResult * n)()
         check(self._L.orbx_extract_batch(self._h, n, ptrs, w, h, strides, res), self._h)
         self._last_n, self._last_shape = n, (h, w)
-        out = [self._copy_result(res[i]) for i in range(n)]
+        out = self._copy_results(res, n, copy)
         self._refresh_pyramids(n)
         return out
 
     @staticmethod
-    def _copy_result(r: OrbxResult):
-        n = r.n
-        if n == 0:     # descriptors released (src/ORBextractor.cc:1064-1065)
-            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
-        kps = np.ctypeslib.as_array(C.cast(r.kps, C.POINTER(C.c_uint8)), shape=(n * 28,)).view(KP_DTYPE).copy()
-        desc = np.ctypeslib.as_array(C.cast(r.desc, C.POINTER(C.c_uint8)), shape=(n, 32)).copy()
-        return kps, desc
+    def _copy_results(res, n: int, copy: bool = True):
+        """Copies the per-frame results out of the library's pinned buffers (two numpy views over the
+        whole batch, then one slice copy per frame)."""
+        if n == 0:
+            return []
+        stride_kp = (res[1].kps - res[0].kps) if n > 1 else max(res[0].n, 1) * 28       # bytes between frames
+        cap = stride_kp // 28
+        kp_all = np.ctypeslib.as_array(C.cast(res[0].kps, C.POINTER(C.c_uint8)), shape=(n * cap * 28,)).view(KP_DTYPE).reshape(n, cap)
+        ds_all = np.ctypeslib.as_array(C.cast(res[0].desc, C.POINTER(C.c_uint8)), shape=(n, cap, 32))
+        out = []
+        for f in range(n):
+            k = res[f].n          # 0: descriptors released (src/ORBextractor.cc:1064-1065)
+            out.append((kp_all[f, :k].copy(), ds_all[f, :k].copy()) if copy else (kp_all[f, :k], ds_all[f, :k]))
+        return out
 
     def _refresh_pyramids(self, n: int):
-        self._pyramids = []
         if not self.download_pyramid:
             return
-        for f in range(n):
-            self._pyramids.append([self._pyramid_view(f, l) for l in range(self.nlevels)])
-        self.mvImagePyramid = self._pyramids[0]
+        self.mvImagePyramid = [self._pyramid_view(0, l) for l in range(self.nlevels)]
 
     def _pyramid_view(self, frame: int, level: int, padded: bool = False) -> np.ndarray:
         p = C.c_void_p()
@@ -149,7 +155,7 @@ class ORBextractor:
     def fetch_results(self, n: int):
         res = (OrbxResult * n)()
         check(self._L.orbx_fetch_results(self._h, n, res), self._h)
-        out = [self._copy_result(res[i]) for i in range(n)]
+        out = self._copy_results(res, n)
         self._refresh_pyramids(n)
         return out
 
