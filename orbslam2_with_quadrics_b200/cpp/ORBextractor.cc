@@ -1,0 +1,131 @@
+// ORB_SLAM2::ORBextractor on top of the B200 C ABI (include/orbx.h).  Replaces the reference's
+// src/ORBextractor.cc in libORB_SLAM2.so (reference CMakeLists.txt:57); see INTEGRATION.md.
+#include "ORBextractor.h"
+
+#include <cassert>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "orbx.h"
+
+namespace ORB_SLAM2
+{
+
+static int g_orbx_device = 0;
+
+void ORBextractor::SetDevice(int device) { g_orbx_device = device; }
+
+static void orbx_throw(orbx_handle* h, int rc, const char* where)
+{
+    std::string msg = std::string("ORBextractor (orbx): ") + where + ": " + orbx_strerror(rc);
+    if (h && rc == ORBX_ERR_CUDA) msg += std::string(" -- ") + orbx_last_cuda_error(h);
+    throw std::runtime_error(msg);
+}
+
+void ORBextractor::Create()
+{
+    orbx_config cfg;
+    std::memset(&cfg, 0, sizeof cfg);
+    cfg.nfeatures = nfeatures_;
+    cfg.scale_factor = scaleFactor_;
+    cfg.nlevels = nlevels_;
+    cfg.ini_th_fast = iniThFAST_;
+    cfg.min_th_fast = minThFAST_;
+    cfg.device = g_orbx_device;
+    cfg.max_batch = 1;
+    cfg.download_pyramid = downloadPyramid_ ? 1 : 0;
+    int rc = orbx_create(&cfg, &handle_);
+    if (rc != ORBX_OK) { handle_ = 0; orbx_throw(0, rc, "orbx_create"); }
+}
+
+ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels,
+                           int _iniThFAST, int _minThFAST):
+    handle_(0), nfeatures_(_nfeatures), nlevels_(_nlevels), iniThFAST_(_iniThFAST), minThFAST_(_minThFAST),
+    scaleFactor_(_scaleFactor), downloadPyramid_(true)
+{
+    Create();
+    mvImagePyramid.resize(nlevels_);       // reference src/ORBextractor.cc:433
+}
+
+ORBextractor::~ORBextractor()
+{
+    if (handle_) orbx_destroy(handle_);
+}
+
+void ORBextractor::SetPyramidDownload(bool enable)
+{
+    if (enable == downloadPyramid_) return;
+    downloadPyramid_ = enable;
+    if (handle_) orbx_destroy(handle_);
+    handle_ = 0;
+    for (size_t l = 0; l < mvImagePyramid.size(); ++l) mvImagePyramid[l] = cv::Mat();
+    Create();
+}
+
+int ORBextractor::GetLevels() { return nlevels_; }
+
+float ORBextractor::GetScaleFactor() { return orbx_get_scale_factor(handle_); }
+
+static std::vector<float> table(orbx_handle* h, int which, int n)
+{
+    const float* t[4] = {0, 0, 0, 0};
+    orbx_scale_tables(h, &t[0], &t[1], &t[2], &t[3]);
+    return std::vector<float>(t[which], t[which] + n);
+}
+
+std::vector<float> ORBextractor::GetScaleFactors() { return table(handle_, 0, nlevels_); }
+std::vector<float> ORBextractor::GetInverseScaleFactors() { return table(handle_, 1, nlevels_); }
+std::vector<float> ORBextractor::GetScaleSigmaSquares() { return table(handle_, 2, nlevels_); }
+std::vector<float> ORBextractor::GetInverseScaleSigmaSquares() { return table(handle_, 3, nlevels_); }
+
+void ORBextractor::operator()( cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint>& _keypoints,
+                      cv::OutputArray _descriptors)
+{
+    (void)_mask;                                   // ignored by the reference too (.h:58)
+    if(_image.empty())
+        return;                                    // outputs untouched (reference :1046-1047)
+
+    cv::Mat image = _image.getMat();
+    assert(image.type() == CV_8UC1 );
+
+    orbx_result r;
+    int rc = orbx_extract(handle_, image.data, image.cols, image.rows, (size_t)image.step, &r);
+    if (rc != ORBX_OK) orbx_throw(handle_, rc, "orbx_extract");
+
+    if( r.n == 0 )
+        _descriptors.release();                    // (:1064-1065)
+    else
+    {
+        _descriptors.create(r.n, 32, CV_8U);       // (:1068)
+        cv::Mat descriptors = _descriptors.getMat();
+        for (int i = 0; i < r.n; ++i)
+            std::memcpy(descriptors.ptr(i), r.desc + 32 * (size_t)i, 32);
+    }
+
+    _keypoints.clear();
+    _keypoints.reserve(r.n);
+    for (int i = 0; i < r.n; ++i)
+    {
+        const orbx_keypoint& k = r.kps[i];
+        cv::KeyPoint kp;
+        kp.pt.x = k.x; kp.pt.y = k.y;
+        kp.size = k.size; kp.angle = k.angle; kp.response = k.response;
+        kp.octave = k.octave; kp.class_id = k.class_id;
+        _keypoints.push_back(kp);
+    }
+
+    if (downloadPyramid_)
+    {
+        for (int level = 0; level < nlevels_; ++level)
+        {
+            const unsigned char* px = 0; int w = 0, h = 0; size_t step = 0;
+            rc = orbx_pyramid_level(handle_, 0, level, &px, &w, &h, &step);
+            if (rc != ORBX_OK) orbx_throw(handle_, rc, "orbx_pyramid_level");
+            // non-owning header at offset (19,19) of the padded plane, like temp(Rect(...)) (:1115)
+            mvImagePyramid[level] = cv::Mat(h, w, CV_8UC1, const_cast<unsigned char*>(px), step);
+        }
+    }
+}
+
+} //namespace ORB_SLAM

@@ -1,0 +1,74 @@
+// Drop-in replacement for the reference's include/ORBextractor.h (yxqc/ORBSLAM2_with_quadrics).
+//
+// Same namespace, class name, constructor, operator(), getters and public mvImagePyramid as
+// reference include/ORBextractor.h:45-85, so Frame, Tracking, KeyFrame and the quadric_slam
+// modules compile against it unchanged (they only need source compatibility: the extractor is
+// one TU of libORB_SLAM2.so, reference CMakeLists.txt:57).  All work happens on the GPU behind
+// the C ABI in include/orbx.h; this class only moves cv:: types in and out.
+//
+// Differences a maintainer should know about:
+//  * ExtractorNode (reference .h:32-43) is gone: nothing outside the old TU used it.
+//  * The destructor is out of line (it releases the GPU handle).
+//  * mvImagePyramid[l] are non-owning cv::Mat headers over the library's pinned host buffer; as in
+//    the reference they are valid until the next operator() on the same object.
+//  * Errors (CUDA failure, unsupported geometry, candidate overflow) throw std::runtime_error;
+//    there is no silent CPU fallback.
+#ifndef ORBEXTRACTOR_H
+#define ORBEXTRACTOR_H
+
+#include <vector>
+#include <opencv2/core/core.hpp>
+
+struct orbx_handle;
+
+namespace ORB_SLAM2
+{
+
+class ORBextractor
+{
+public:
+
+    enum {HARRIS_SCORE=0, FAST_SCORE=1 };
+
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels,
+                 int iniThFAST, int minThFAST);
+
+    ~ORBextractor();
+
+    // Compute the ORB features and descriptors on an image.
+    // Mask is ignored, as in the reference implementation.
+    void operator()( cv::InputArray image, cv::InputArray mask,
+      std::vector<cv::KeyPoint>& keypoints,
+      cv::OutputArray descriptors);
+
+    int GetLevels();
+    float GetScaleFactor();
+    std::vector<float> GetScaleFactors();
+    std::vector<float> GetInverseScaleFactors();
+    std::vector<float> GetScaleSigmaSquares();
+    std::vector<float> GetInverseScaleSigmaSquares();
+
+    std::vector<cv::Mat> mvImagePyramid;
+
+    // --- additions (not in the reference) ---
+    // Monocular / RGB-D pipelines never read mvImagePyramid (only Frame::ComputeStereoMatches does,
+    // reference src/Frame.cc:563-580); switching the download off keeps the pyramid in HBM and removes
+    // the largest device->host copy.  Default: on (exact drop-in behaviour).
+    void SetPyramidDownload(bool enable);
+    // CUDA device used by extractors created afterwards in this thread's process (default 0).
+    static void SetDevice(int device);
+
+private:
+    ORBextractor(const ORBextractor&);
+    ORBextractor& operator=(const ORBextractor&);
+    void Create();
+
+    orbx_handle* handle_;
+    int nfeatures_, nlevels_, iniThFAST_, minThFAST_;
+    float scaleFactor_;
+    bool downloadPyramid_;
+};
+
+} //namespace ORB_SLAM
+
+#endif

@@ -1,0 +1,45 @@
+// Test driver for the C++ adapter (orbslam2_with_quadrics_b200/cpp/ORBextractor.{h,cc}) compiled against
+// the OpenCV shim.  Mirrors Frame::ExtractORB (reference src/Frame.cc:247-253): calls operator() with a
+// cv::Mat image and an empty mask, then dumps keypoints, descriptors and the pyramid for the pytest side.
+//   adapter_main <w> <h> <nfeatures> <scale> <nlevels> <ini> <min> <in.raw> <out.bin>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "ORBextractor.h"
+
+int main(int argc, char** argv)
+{
+    if (argc < 10) return 2;
+    const int w = atoi(argv[1]), h = atoi(argv[2]);
+    ORB_SLAM2::ORBextractor ex(atoi(argv[3]), (float)atof(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]));
+    std::vector<unsigned char> buf((size_t)w * h);
+    FILE* f = fopen(argv[8], "rb");
+    if (!f || fread(buf.data(), 1, buf.size(), f) != buf.size()) return 3;
+    fclose(f);
+    cv::Mat im(h, w, CV_8UC1, buf.data(), (size_t)w);
+    std::vector<cv::KeyPoint> keys(3);                 // must be cleared by the call
+    cv::Mat desc;
+    ex(cv::Mat(), cv::Mat(), keys, desc);              // empty image: outputs untouched
+    if (keys.size() != 3) return 4;
+    for (int rep = 0; rep < 2; ++rep) ex(im, cv::Mat(), keys, desc);
+    FILE* o = fopen(argv[9], "wb");
+    int n = (int)keys.size(), nl = ex.GetLevels();
+    fwrite(&n, 4, 1, o);
+    fwrite(&nl, 4, 1, o);
+    for (int i = 0; i < n; ++i) {
+        float v[5] = {keys[i].pt.x, keys[i].pt.y, keys[i].size, keys[i].angle, keys[i].response};
+        int q[2] = {keys[i].octave, keys[i].class_id};
+        fwrite(v, 4, 5, o); fwrite(q, 4, 2, o);
+    }
+    for (int i = 0; i < n; ++i) fwrite(desc.ptr(i), 1, 32, o);
+    std::vector<float> sf = ex.GetScaleFactors(), isf = ex.GetInverseScaleSigmaSquares();
+    fwrite(sf.data(), 4, nl, o); fwrite(isf.data(), 4, nl, o);
+    for (int l = 0; l < nl; ++l) {                     // padded planes through the public mvImagePyramid views
+        const cv::Mat& m = ex.mvImagePyramid[l];
+        int dims[2] = {m.cols, m.rows};
+        fwrite(dims, 4, 2, o);
+        for (int y = -19; y < m.rows + 19; ++y) fwrite(m.data + (long)y * (long)m.step - 19, 1, (size_t)m.cols + 38, o);
+    }
+    fclose(o);
+    return 0;
+}
