@@ -57,26 +57,27 @@ __device__ __forceinline__ const uint8_t* level_px(const uint8_t* slab, const Or
 // =====================================================================================
 __global__ void __launch_bounds__(256) pyr_level0_kernel(const OrbxPlan* __restrict__ plan,
                                                          const uint8_t* __restrict__ imgs, size_t img_pitch,
-                                                         size_t img_frame_stride, int aligned4,
+                                                         size_t img_frame_stride, int aligned16,
                                                          uint8_t* __restrict__ pyr) {
     const OrbxLevel& L = plan->lv[0];
     const int w = L.w, h = L.h;
     const int frame = blockIdx.z;
-    const int c = 12 + (blockIdx.x * 32 + threadIdx.x) * 4;        // plane column, multiple of 4
+    const int c = (blockIdx.x * 32 + threadIdx.x) * 16;            // plane column, multiple of 16 (XO is too)
     const int row = blockIdx.y * 8 + threadIdx.y;                  // plane row
     if (row >= L.rows || c >= ORBX_XO + w + ORBX_EDGE) return;
     const int dy = reflect_clamp(row - ORBX_EDGE, h);
     const uint8_t* src = imgs + (size_t)frame * img_frame_stride + (size_t)dy * img_pitch;
     const int dx0 = c - ORBX_XO;
-    uint32_t out;
-    if (aligned4 && dx0 >= 0 && dx0 + 3 < w) {
-        out = __ldg(reinterpret_cast<const uint32_t*>(src + dx0));
+    uint4 out;
+    if (aligned16 && dx0 >= 0 && dx0 + 15 < w) {
+        out = __ldg(reinterpret_cast<const uint4*>(src + dx0));
     } else {
-        out = 0;
+        uint32_t o[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) out |= (uint32_t)__ldg(src + reflect_clamp(dx0 + i, w)) << (8 * i);
+        for (int i = 0; i < 16; ++i) o[i >> 2] |= (uint32_t)__ldg(src + reflect_clamp(dx0 + i, w)) << (8 * (i & 3));
+        out = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    *reinterpret_cast<uint32_t*>(pyr + (size_t)frame * plan->slab_bytes + L.plane_off + (size_t)row * L.pitch + c) = out;
+    *reinterpret_cast<uint4*>(pyr + (size_t)frame * plan->slab_bytes + L.plane_off + (size_t)row * L.pitch + c) = out;
 }
 
 #define PYR_RY 16
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const OrbxPlan* __restr
     }
     const uint8_t* sbase = slab + S.plane_off + (size_t)ORBX_EDGE * S.pitch + ORBX_XO + wb;   // row 0 of the source level
     const int spitch = S.pitch;
-    uint32_t HA[4], HB[4];
+    uint32_t HA[4] = {0, 0, 0, 0}, HB[4] = {0, 0, 0, 0};
     int rowA = -1, rowB = -1;
     auto row_pass = [&](int sy, uint32_t* H) {
         const uint32_t* rp = reinterpret_cast<const uint32_t*>(sbase + (size_t)sy * spitch);
@@ -150,12 +151,13 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const OrbxPlan* __restr
             rowA = r0;
             if (r1 != r0) { row_pass(r1, HB); rowB = r1; } else { rowB = -1; }
         }
-        const uint32_t b0 = (uint32_t)ty.c0 << 16, b1 = (r1 != r0) ? ((uint32_t)ty.c1 << 16) : 0u;
+        // when the source row is clamped (r1 == r0) the table's second weight is 0, so a stale HB is harmless
+        const uint32_t b0 = (uint32_t)ty.c0 << 16, b1 = (uint32_t)ty.c1 << 16;
         uint32_t out = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             // <= 255: the weights sum to 2048 and H >> 4 <= 255 * 128
-            const uint32_t v = (__umulhi(b0, HA[j]) + __umulhi(b1, (r1 != r0) ? HB[j] : 0u) + 2u) >> 2;
+            const uint32_t v = (__umulhi(b0, HA[j]) + __umulhi(b1, HB[j]) + 2u) >> 2;
             out |= v << (8 * j);
         }
         *reinterpret_cast<uint32_t*>(dst) = out;
@@ -1044,9 +1046,10 @@ void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nfr
     const OrbxLevel& L = hp.lv[l];
     const int cols4 = (ORBX_XO + L.w + ORBX_EDGE - 12 + 3) / 4;
     if (l == 0) {
-        const int aligned4 = ((reinterpret_cast<uintptr_t>(imgs) | img_pitch | img_frame_stride) & 3) == 0;
-        dim3 block(32, 8), grid((cols4 + 31) / 32, (L.rows + 7) / 8, nframes);
-        pyr_level0_kernel<<<grid, block, 0, st>>>(d_plan, imgs, img_pitch, img_frame_stride, aligned4, pyr);
+        const int aligned16 = ((reinterpret_cast<uintptr_t>(imgs) | img_pitch | img_frame_stride) & 15) == 0;
+        const int cols16 = (ORBX_XO + L.w + ORBX_EDGE + 15) / 16;          // 16-byte chunks from plane column 0
+        dim3 block(32, 8), grid((cols16 + 31) / 32, (L.rows + 7) / 8, nframes);
+        pyr_level0_kernel<<<grid, block, 0, st>>>(d_plan, imgs, img_pitch, img_frame_stride, aligned16, pyr);
     } else {
         // rows per warp: long strips reuse row passes (1 + 1/RY... per row) but small levels need warps
         int RY = PYR_RY;
