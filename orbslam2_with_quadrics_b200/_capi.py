@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "liborbx.so")
+LIB_PATH = os.environ.get("ORBX_LIB") or os.path.join(PKG, "liborbx.so")     # ORBX_LIB: A/B builds of the same library
 
 ORBX_OK = 0
 ERR_BAD_ARGS, ERR_BAD_GEOMETRY, ERR_CUDA, ERR_CANDIDATE_OVERFLOW, ERR_NO_DEVICE, ERR_OOM, ERR_EMPTY_IMAGE = \

@@ -314,14 +314,17 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
         }
     };
 
+    // The work counter is read one cell further ahead than the tile prefetch, so the atomic's round trip
+    // overlaps the processing of a whole cell.
     unsigned cur = fetch();
+    unsigned nxt = fetch();
     FastCell cc, nc;
     if (cur < total) { cc = fast_decode(plan, cur); issue(cc, 0); }
     uint32_t phase[2] = {0, 0};
     int b = 0;
     while (cur < total) {
-        const unsigned nxt = fetch();
         if (nxt < total) { nc = fast_decode(plan, nxt); issue(nc, b ^ 1); }
+        const unsigned nxt2 = nxt < total ? fetch() : nxt;
         mbar_wait(&s_bar[warp][b], phase[b]);
         phase[b] ^= 1;
 
@@ -345,44 +348,59 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
             for (int pass = 0; pass < 2 && count == 0; ++pass) {
                 const int t = pass == 0 ? plan->ini_th : plan->min_th;
                 const uint32_t C = (uint32_t)(0x7f - min(t, 0x7f)) * 0x01010101u;
-                // ---- phase 1
+                // ---- phase 1, in chunks of 8 warp iterations (RPI rows each): first all pre-tests (independent
+                //      loads and SIMD math, nothing serialises), then ONE pair of packed warp scans for the chunk
+                //      (four 8-bit counts per register), then the ordered queue writes.
                 int qn = 0;
-                for (int yb = 3; yb < wh - 3; yb += RPI) {
-                    const int y = yb + ry;
-                    uint32_t m = 0;
-                    if (vmask && y < wh - 3) {
-                        const uint32_t* r = tile32 + y * BW4 + g;             // raw word holding tile column 4g + (delta & ~3)
-                        const uint32_t c1 = __funnelshift_r(r[1], r[2], sh);      // pixels x .. x+3, x = 3 + 4g
-                        const uint32_t c0 = __funnelshift_r(r[0], r[1], sh);
-                        const uint32_t c2 = __funnelshift_r(r[2], r[3], sh);
-                        const uint32_t up = __funnelshift_r(r[1 - 3 * BW4], r[2 - 3 * BW4], sh);
-                        const uint32_t dn = __funnelshift_r(r[1 + 3 * BW4], r[2 + 3 * BW4], sh);
-                        const uint32_t r4 = __funnelshift_r(c1, c2, 24);        // pixels x+3 .. x+6
-                        const uint32_t r12 = __funnelshift_r(c0, c1, 8);        // pixels x-3 .. x
-                        const uint32_t a0 = __vabsdiffu4(dn, c1), a8 = __vabsdiffu4(up, c1);
-                        const uint32_t a4 = __vabsdiffu4(r4, c1), a12 = __vabsdiffu4(r12, c1);
-                        // bit 7 of a byte of ((a & 0x7f) + C) | a  <=>  a > t
-                        const uint32_t s0 = (a0 & 0x7f7f7f7fu) + C, s8 = (a8 & 0x7f7f7f7fu) + C;
-                        const uint32_t s4 = (a4 & 0x7f7f7f7fu) + C, s12 = (a12 & 0x7f7f7f7fu) + C;
-                        m = ((s0 | a0) | (s8 | a8)) & ((s4 | a4) | (s12 | a12)) & vmask;
+                for (int yc = 3; yc < wh - 3; yc += 8 * RPI) {
+                    uint32_t m[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int y = yc + k * RPI + ry;
+                        m[k] = 0;
+                        if (vmask && y < wh - 3) {
+                            const uint32_t* r = tile32 + y * BW4 + g;         // raw word holding tile column 4g + (delta & ~3)
+                            const uint32_t c1 = __funnelshift_r(r[1], r[2], sh);      // pixels x .. x+3, x = 3 + 4g
+                            const uint32_t c0 = __funnelshift_r(r[0], r[1], sh);
+                            const uint32_t c2 = __funnelshift_r(r[2], r[3], sh);
+                            const uint32_t up = __funnelshift_r(r[1 - 3 * BW4], r[2 - 3 * BW4], sh);
+                            const uint32_t dn = __funnelshift_r(r[1 + 3 * BW4], r[2 + 3 * BW4], sh);
+                            const uint32_t r4 = __funnelshift_r(c1, c2, 24);        // pixels x+3 .. x+6
+                            const uint32_t r12 = __funnelshift_r(c0, c1, 8);        // pixels x-3 .. x
+                            const uint32_t a0 = __vabsdiffu4(dn, c1), a8 = __vabsdiffu4(up, c1);
+                            const uint32_t a4 = __vabsdiffu4(r4, c1), a12 = __vabsdiffu4(r12, c1);
+                            // bit 7 of a byte of ((a & 0x7f) + C) | a  <=>  a > t
+                            const uint32_t s0 = (a0 & 0x7f7f7f7fu) + C, s8 = (a8 & 0x7f7f7f7fu) + C;
+                            const uint32_t s4 = (a4 & 0x7f7f7f7fu) + C, s12 = (a12 & 0x7f7f7f7fu) + C;
+                            m[k] = ((s0 | a0) | (s8 | a8)) & ((s4 | a4) | (s12 | a12)) & vmask;
+                        }
                     }
-                    const int cnt = __popc(m);
-                    int pre = cnt;
+                    // per-lane counts are <= 4 and a warp total is <= 128, so four counts fit one register
+                    uint32_t pa = (uint32_t)__popc(m[0]) | ((uint32_t)__popc(m[1]) << 8) | ((uint32_t)__popc(m[2]) << 16) | ((uint32_t)__popc(m[3]) << 24);
+                    uint32_t pb = (uint32_t)__popc(m[4]) | ((uint32_t)__popc(m[5]) << 8) | ((uint32_t)__popc(m[6]) << 16) | ((uint32_t)__popc(m[7]) << 24);
+                    const uint32_t ca = pa, cb = pb;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
-                        const int tt = __shfl_up_sync(0xffffffffu, pre, o);
-                        if (lane >= o) pre += tt;
+                        const uint32_t ta = __shfl_up_sync(0xffffffffu, pa, o), tb = __shfl_up_sync(0xffffffffu, pb, o);
+                        if (lane >= o) { pa += ta; pb += tb; }
                     }
-                    const int tot = __shfl_sync(0xffffffffu, pre, 31);
-                    if (m) {
-                        int w = qn + pre - cnt;
-                        const int e = (y << 8) | (3 + 4 * g);
-                        if (m & 0x80u) queue[w++] = (uint16_t)e;
-                        if (m & 0x8000u) queue[w++] = (uint16_t)(e + 1);
-                        if (m & 0x800000u) queue[w++] = (uint16_t)(e + 2);
-                        if (m & 0x80000000u) queue[w++] = (uint16_t)(e + 3);
+                    const uint32_t tota = __shfl_sync(0xffffffffu, pa, 31), totb = __shfl_sync(0xffffffffu, pb, 31);
+                    pa -= ca;                                                    // exclusive prefixes
+                    pb -= cb;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t pk = ((k < 4 ? pa : pb) >> (8 * (k & 3))) & 0xffu;
+                        const uint32_t tk = ((k < 4 ? tota : totb) >> (8 * (k & 3))) & 0xffu;
+                        if (m[k]) {
+                            uint16_t* wq = queue + qn + pk;
+                            const int e = ((yc + k * RPI + ry) << 8) | (3 + 4 * g);
+                            if (m[k] & 0x80u) *wq++ = (uint16_t)e;
+                            if (m[k] & 0x8000u) *wq++ = (uint16_t)(e + 1);
+                            if (m[k] & 0x800000u) *wq++ = (uint16_t)(e + 2);
+                            if (m[k] & 0x80000000u) *wq++ = (uint16_t)(e + 3);
+                        }
+                        qn += (int)tk;
                     }
-                    qn += tot;
                 }
                 __syncwarp();
                 // ---- phase 2: exact score; corners compacted in place (order kept), scores to the map
@@ -458,6 +476,7 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
         if (lane == 0) cell_rec[cur] = make_uint2((uint32_t)gbase, overflow ? 0u : (uint32_t)count);
         __syncwarp();
         cur = nxt;
+        nxt = nxt2;
         cc = nc;
         b ^= 1;
     }
