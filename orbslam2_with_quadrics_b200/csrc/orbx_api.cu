@@ -252,7 +252,24 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
     P->node_cap = round_up(P->node_cap, 32);
     if (P->max_cell_w < 7) P->max_cell_w = 7;
     if (P->max_cell_h < 7) P->max_cell_h = 7;
-    P->fast_bw = round_up(P->max_cell_w + 24, 16);     // 16-aligned TMA start (delta <= 15), 1-byte shift, 2 words of read-ahead
+    // FAST tiling: NC cells per TMA tile, NB tile buffers per warp, W warps per CTA (env overrides are for tuning runs)
+    const char* e_nc = getenv("ORBX_FAST_NC"); const char* e_nb = getenv("ORBX_FAST_NB"); const char* e_w = getenv("ORBX_FAST_WARPS");
+    P->fast_nc = e_nc ? atoi(e_nc) : 2;       // measured best on B200 at 1080p: 2 cells per tile, single buffer, 8 warps
+    P->fast_nb = e_nb ? atoi(e_nb) : 1;
+    P->fast_warps = e_w ? atoi(e_w) : 8;
+    if (P->fast_nc < 1 || P->fast_nc > 8 || P->fast_nb < 1 || P->fast_nb > 2 || P->fast_warps < 1 || P->fast_warps > ORBX_FAST_WARPS)
+        return ORBX_ERR_BAD_ARGS;
+    int max_wcell = 0, strips = 0;
+    for (int l = 0; l < n; ++l) {
+        OrbxLevel& L = P->lv[l];
+        if (L.wCell > max_wcell) max_wcell = L.wCell;
+        L.strip_base = strips;
+        L.strips_x = (L.nColsV + P->fast_nc - 1) / P->fast_nc;
+        strips += L.strips_x * L.nRowsV;
+    }
+    P->strips_per_frame = strips;
+    // 16-aligned TMA start (delta <= 15), 1-byte shift, NC cell steps + the 6-px overlap, 2 words of read-ahead
+    P->fast_bw = round_up((P->fast_nc - 1) * max_wcell + P->max_cell_w + 24, 16);
     P->fast_bh = P->max_cell_h;
     if (P->fast_bw > 256 || P->fast_bh > 127 || P->max_cell_w > 250) return ORBX_ERR_BAD_GEOMETRY;
     P->cells_per_frame = cells;

@@ -210,21 +210,21 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
-struct FastCell {
-    int frame, l, ci, cj;
+struct FastStrip {
+    int frame, l, ci, cj0;     // NC horizontally adjacent cells starting at column cj0 of cell row ci
 };
 
-__device__ __forceinline__ FastCell fast_decode(const OrbxPlan* __restrict__ plan, unsigned item) {
-    FastCell c;
-    const unsigned cpf = (unsigned)plan->cells_per_frame;
-    c.frame = (int)(item / cpf);
-    const int r = (int)(item - (unsigned)c.frame * cpf);
+__device__ __forceinline__ FastStrip fast_decode(const OrbxPlan* __restrict__ plan, unsigned item) {
+    FastStrip c;
+    const unsigned spf = (unsigned)plan->strips_per_frame;
+    c.frame = (int)(item / spf);
+    const int r = (int)(item - (unsigned)c.frame * spf);
     int l = 0;
-    while (l + 1 < plan->nlevels && r >= plan->lv[l + 1].cell_base) ++l;
+    while (l + 1 < plan->nlevels && r >= plan->lv[l + 1].strip_base) ++l;
     c.l = l;
     const OrbxLevel& L = plan->lv[l];
-    c.ci = (int)((unsigned)(r - L.cell_base) / (unsigned)L.nColsV);
-    c.cj = (r - L.cell_base) - c.ci * L.nColsV;
+    c.ci = (int)((unsigned)(r - L.strip_base) / (unsigned)L.strips_x);
+    c.cj0 = ((r - L.strip_base) - c.ci * L.strips_x) * plan->fast_nc;
     return c;
 }
 
@@ -270,7 +270,10 @@ __device__ __forceinline__ int fast_score_packed(const uint8_t* __restrict__ p, 
     return A > t ? A - 1 : 0;
 }
 
-__global__ void __launch_bounds__(ORBX_FAST_WARPS * 32, 3)
+#ifndef ORBX_FAST_MINB
+#define ORBX_FAST_MINB 3
+#endif
+__global__ void __launch_bounds__(ORBX_FAST_WARPS * 32, ORBX_FAST_MINB)
 fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, int frame0, int nframes,
                   uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec, int* __restrict__ level_counts,
                   int* __restrict__ work_counter, int* __restrict__ status) {
@@ -278,16 +281,17 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
     __shared__ uint64_t s_bar[ORBX_FAST_WARPS][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int BW = plan->fast_bw, BH = plan->fast_bh;
+    const int NC = plan->fast_nc, NB = plan->fast_nb;                    // cells per tile, tile buffers per warp
     const int TB = (BW * BH + 127) & ~127;                               // tile bytes
     const int QN = (plan->max_cell_w - 6) * (plan->max_cell_h - 6);      // queue entries (u16)
     const int SP = (plan->max_cell_w + 2 + 3) & ~3;                      // score-map pitch; column = window x + 1
     const int SB = (SP * BH + 127) & ~127;
-    const int per_warp = 2 * TB + SB + ((QN * 2 + 127) & ~127);
+    const int per_warp = NB * TB + SB + ((QN * 2 + 127) & ~127);
     uint8_t* base = fast_smem_raw + ((128 - (smem_u32(fast_smem_raw) & 127)) & 127) + (size_t)warp * per_warp;
-    uint8_t* sc = base + 2 * TB;                                         // zero-framed score map
-    uint16_t* queue = reinterpret_cast<uint16_t*>(base + 2 * TB + SB);   // entries (y << 8) | x, window coordinates
+    uint8_t* sc = base + NB * TB;                                        // zero-framed score map
+    uint16_t* queue = reinterpret_cast<uint16_t*>(base + NB * TB + SB);  // entries (y << 8) | x, window coordinates
     const int nlevels = plan->nlevels;
-    const unsigned total = (unsigned)nframes * (unsigned)plan->cells_per_frame;
+    const unsigned total = (unsigned)nframes * (unsigned)plan->strips_per_frame;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int BW4 = BW >> 2;
 
@@ -305,39 +309,48 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
         if (lane == 0) v = atomicAdd(work_counter, 1);
         return (unsigned)__shfl_sync(0xffffffffu, v, 0);
     };
-    auto issue = [&](const FastCell& c, int b) {
+    auto issue = [&](const FastStrip& c, int b) {
         if (lane == 0) {
             const OrbxLevel& L = plan->lv[c.l];
             mbar_expect_tx(&s_bar[warp][b], (uint32_t)(BW * BH));
-            tma_load_3d(base + b * TB, &maps.m[c.l], &s_bar[warp][b], (ORBX_XO + ORBX_BOX + c.cj * L.wCell - 1) & ~15,
+            tma_load_3d(base + b * TB, &maps.m[c.l], &s_bar[warp][b], (ORBX_XO + ORBX_BOX + c.cj0 * L.wCell - 1) & ~15,
                         ORBX_EDGE + ORBX_BOX + c.ci * L.hCell, frame0 + c.frame);
         }
     };
 
-    // The work counter is read one cell further ahead than the tile prefetch, so the atomic's round trip
-    // overlaps the processing of a whole cell.
+    // A work item is a strip of NC cells fetched as ONE tile (fewer, wider TMA rows).  The work counter is read
+    // one item further ahead than the tile prefetch, so the atomic's round trip overlaps a whole strip.
     unsigned cur = fetch();
     unsigned nxt = fetch();
-    FastCell cc, nc;
+    FastStrip cc, nc;
     if (cur < total) { cc = fast_decode(plan, cur); issue(cc, 0); }
     uint32_t phase[2] = {0, 0};
     int b = 0;
     while (cur < total) {
-        if (nxt < total) { nc = fast_decode(plan, nxt); issue(nc, b ^ 1); }
+        if (NB == 2 && nxt < total) { nc = fast_decode(plan, nxt); issue(nc, b ^ 1); }
         const unsigned nxt2 = nxt < total ? fetch() : nxt;
         mbar_wait(&s_bar[warp][b], phase[b]);
         phase[b] ^= 1;
 
         const OrbxLevel& L = plan->lv[cc.l];
-        const int iniX = ORBX_BOX + cc.cj * L.wCell, iniY = ORBX_BOX + cc.ci * L.hCell;
-        const int ww = min(iniX + L.wCell + 6, L.maxBX) - iniX;
+        const int delta0 = (ORBX_XO + ORBX_BOX + cc.cj0 * L.wCell - 1) & 15;
+        const int iniY = ORBX_BOX + cc.ci * L.hCell;
         const int wh = min(iniY + L.hCell + 6, L.maxBY) - iniY;
-        const int delta = (ORBX_XO + iniX - 1) & 15;
+        const int ncell = min(NC, L.nColsV - cc.cj0);
+        for (int cix = 0; cix < ncell; ++cix) {
+        const int cj = cc.cj0 + cix;
+        const int iniX = ORBX_BOX + cj * L.wCell;
+        const int ww = min(iniX + L.wCell + 6, L.maxBX) - iniX;
+        const int delta = delta0 + cix * L.wCell;                        // byte offset of (window x0 - 1) inside the tile
         const uint8_t* tile = base + b * TB + delta + 1;                 // byte of window pixel (0, 0)
         const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(base + b * TB) + (delta >> 2);
         const int sh = (delta & 3) * 8;
         int count = 0, cn = 0;
+#ifdef ORBX_EXP_SKIP_ALL
+        if (ww >= 7 && wh >= 70000) {
+#else
         if (ww >= 7 && wh >= 7) {
+#endif
             const int ew = ww - 6;                                       // emission width
             const int G = (ew + 3) >> 2;                                 // 4-pixel groups per row
             const int mg = (int)((65536u + (unsigned)G - 1u) / (unsigned)G);   // (n * mg) >> 16 == n / G for n <= 32
@@ -410,7 +423,11 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
                     int s = 0, e = 0;
                     if (i < qn) {
                         e = queue[i];
+#ifdef ORBX_EXP_SKIP_P2
+                        s = 0;
+#else
                         s = fast_score_packed(tile + (e >> 8) * BW + (e & 0xff), BW, t);
+#endif
                     }
                     const uint32_t bal = __ballot_sync(0xffffffffu, s > 0);
                     if (s > 0) {
@@ -454,7 +471,7 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
             }
         }
         uint32_t* dst = cand + (size_t)cc.frame * plan->cand_per_frame + L.cand_off + gbase;
-        const int ox = cc.cj * L.wCell, oy = cc.ci * L.hCell;                  // (:822-823)
+        const int ox = cj * L.wCell, oy = cc.ci * L.hCell;                     // (:822-823)
         int w = 0;
         for (int i0 = 0; i0 < cn; i0 += 32) {
             const int i = i0 + lane;
@@ -473,12 +490,16 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
         }
         __syncwarp();
         for (int i = lane; i < cn; i += 32) sc[((queue[i] >> 8) & 0x7f) * SP + (queue[i] & 0xff) + 1] = 0;   // leave the map all-zero
-        if (lane == 0) cell_rec[cur] = make_uint2((uint32_t)gbase, overflow ? 0u : (uint32_t)count);
+        if (lane == 0)
+            cell_rec[(size_t)cc.frame * plan->cells_per_frame + L.cell_base + cc.ci * L.nColsV + cj] =
+                make_uint2((uint32_t)gbase, overflow ? 0u : (uint32_t)count);
         __syncwarp();
+        }   // cells of the strip
+        if (NB == 1 && nxt < total) { nc = fast_decode(plan, nxt); issue(nc, 0); }
         cur = nxt;
         nxt = nxt2;
         cc = nc;
-        b ^= 1;
+        if (NB == 2) b ^= 1;
     }
 }
 
@@ -1084,7 +1105,7 @@ size_t fast_smem_bytes(const OrbxPlan& hp) {
     const size_t SP = (size_t)((hp.max_cell_w + 2 + 3) & ~3);
     const size_t SB = (SP * hp.fast_bh + 127) & ~(size_t)127;
     const size_t QB = ((size_t)(hp.max_cell_w - 6) * (hp.max_cell_h - 6) * 2 + 127) & ~(size_t)127;
-    return (2 * TB + SB + QB) * ORBX_FAST_WARPS + 128;
+    return ((size_t)hp.fast_nb * TB + SB + QB) * hp.fast_warps + 128;
 }
 
 // One {pitch, rows, frames} u8 tensor map per level over the pyramid slabs; box = one FAST window.
@@ -1129,17 +1150,17 @@ cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* 
         if (e != cudaSuccess) return e;
         configured[dev & 63] = smem;
         int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_cells_kernel, ORBX_FAST_WARPS * 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_cells_kernel, hp.fast_warps * 32, smem);
         per_sm_cache[dev & 63] = per_sm < 1 ? 1 : per_sm;
     }
-    const long long total = (long long)nframes * hp.cells_per_frame;
-    long long blocks = (total + ORBX_FAST_WARPS - 1) / ORBX_FAST_WARPS;
+    const int W = hp.fast_warps;
+    const long long total = (long long)nframes * hp.strips_per_frame;
+    long long blocks = (total + W - 1) / W;
     const long long cap = (long long)num_sms * per_sm_cache[dev & 63];
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    fast_cells_kernel<<<(int)blocks, ORBX_FAST_WARPS * 32, smem, st>>>(*reinterpret_cast<const FastMaps*>(maps), d_plan,
-                                                                      frame0, nframes, cand, cell_rec, level_counts,
-                                                                      work_counter, status);
+    fast_cells_kernel<<<(int)blocks, W * 32, smem, st>>>(*reinterpret_cast<const FastMaps*>(maps), d_plan, frame0, nframes,
+                                                        cand, cell_rec, level_counts, work_counter, status);
     return cudaSuccess;
 }
 
