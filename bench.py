@@ -156,6 +156,8 @@ def own_arm(args):
     import torch
     from orbslam2_with_quadrics_b200 import ORBextractor, sharding
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     rank, world, local = sharding.init_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
@@ -277,6 +279,9 @@ def own_arm(args):
                "batch": 1, "path": "C ABI, pinned host in, keypoints+descriptors out" + (", pyramid D2H" if need_pyr else "")}
         ex1.close()
 
+    if world > 1:
+        sharding.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return 0
     # ---- roofline of the whole step and of each stage kernel
