@@ -228,6 +228,27 @@ __device__ __forceinline__ FastStrip fast_decode(const OrbxPlan* __restrict__ pl
     return c;
 }
 
+// VIMNMX3.S16x2 issues on the quarter-rate XU pipe on sm_100 (measured: XU 85 % busy with the score network
+// written entirely in 3-input min/max), two VIMNMX.S16x2 on the full-rate ALU pipe.  ORBX_MNMX3_MODE picks which
+// chains use which: 0 = all 3-input, 1 = all 2-input pairs, 2 = min chain 3-input / max chain pairs.
+#ifndef ORBX_MNMX3_MODE
+#define ORBX_MNMX3_MODE 2
+#endif
+__device__ __forceinline__ uint32_t min3_s16x2(uint32_t a, uint32_t b, uint32_t c) {
+#if ORBX_MNMX3_MODE == 1
+    return __vmins2(__vmins2(a, b), c);
+#else
+    return __vimin3_s16x2(a, b, c);
+#endif
+}
+__device__ __forceinline__ uint32_t max3_s16x2(uint32_t a, uint32_t b, uint32_t c) {
+#if ORBX_MNMX3_MODE == 0
+    return __vimax3_s16x2(a, b, c);
+#else
+    return __vmaxs2(__vmaxs2(a, b), c);
+#endif
+}
+
 // exact FAST score of the pixel at tile byte p (pitch BW): A - 1 if A > t else 0
 __device__ __forceinline__ int fast_score_packed(const uint8_t* __restrict__ p, int BW, int t) {
     const int v = p[0];
@@ -247,22 +268,22 @@ __device__ __forceinline__ int fast_score_packed(const uint8_t* __restrict__ p, 
     uint32_t n3[14], x3[14];
 #pragma unroll
     for (int k = 0; k < 14; ++k) {
-        n3[k] = __vimin3_s16x2(Z[k], Z[k + 1], Z[k + 2]);
-        x3[k] = __vimax3_s16x2(Z[k], Z[k + 1], Z[k + 2]);
+        n3[k] = min3_s16x2(Z[k], Z[k + 1], Z[k + 2]);
+        x3[k] = max3_s16x2(Z[k], Z[k + 1], Z[k + 2]);
     }
     uint32_t n9[8], x9[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        n9[k] = __vimin3_s16x2(n3[k], n3[k + 3], n3[k + 6]);      // min over ring k .. k+8 (lo) and k+8 .. k+16 (hi)
-        x9[k] = __vimax3_s16x2(x3[k], x3[k + 3], x3[k + 6]);
+        n9[k] = min3_s16x2(n3[k], n3[k + 3], n3[k + 6]);      // min over ring k .. k+8 (lo) and k+8 .. k+16 (hi)
+        x9[k] = max3_s16x2(x3[k], x3[k + 3], x3[k + 6]);
     }
-    uint32_t bm = __vimax3_s16x2(n9[0], n9[1], n9[2]);
-    bm = __vimax3_s16x2(bm, n9[3], n9[4]);
-    bm = __vimax3_s16x2(bm, n9[5], n9[6]);
+    uint32_t bm = max3_s16x2(n9[0], n9[1], n9[2]);
+    bm = max3_s16x2(bm, n9[3], n9[4]);
+    bm = max3_s16x2(bm, n9[5], n9[6]);
     bm = __vmaxs2(bm, n9[7]);
-    uint32_t dm = __vimin3_s16x2(x9[0], x9[1], x9[2]);
-    dm = __vimin3_s16x2(dm, x9[3], x9[4]);
-    dm = __vimin3_s16x2(dm, x9[5], x9[6]);
+    uint32_t dm = min3_s16x2(x9[0], x9[1], x9[2]);
+    dm = min3_s16x2(dm, x9[3], x9[4]);
+    dm = min3_s16x2(dm, x9[5], x9[6]);
     dm = __vmins2(dm, x9[7]);
     const int Ab = max((int)(bm & 0xffffu), (int)(bm >> 16)) - 256;      // brighter arc: min(ring - centre)
     const int Ad = 256 - min((int)(dm & 0xffffu), (int)(dm >> 16));      // darker arc: min(centre - ring)
@@ -273,6 +294,8 @@ __device__ __forceinline__ int fast_score_packed(const uint8_t* __restrict__ p, 
 #ifndef ORBX_FAST_MINB
 #define ORBX_FAST_MINB 3
 #endif
+// BW_T: tile pitch known at compile time (ring offsets become immediates); 0 = read it from the plan.
+template <int BW_T>
 __global__ void __launch_bounds__(ORBX_FAST_WARPS * 32, ORBX_FAST_MINB)
 fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, int frame0, int nframes,
                   uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec, int* __restrict__ level_counts,
@@ -280,7 +303,7 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
     extern __shared__ uint8_t fast_smem_raw[];
     __shared__ uint64_t s_bar[ORBX_FAST_WARPS][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int BW = plan->fast_bw, BH = plan->fast_bh;
+    const int BW = BW_T ? BW_T : plan->fast_bw, BH = plan->fast_bh;
     const int NC = plan->fast_nc, NB = plan->fast_nb;                    // cells per tile, tile buffers per warp
     const int TB = (BW * BH + 127) & ~127;                               // tile bytes
     const int QN = (plan->max_cell_w - 6) * (plan->max_cell_h - 6);      // queue entries (u16)
@@ -370,9 +393,8 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int y = yc + k * RPI + ry;
-                        m[k] = 0;
-                        if (vmask && y < wh - 3) {
-                            const uint32_t* r = tile32 + y * BW4 + g;         // raw word holding tile column 4g + (delta & ~3)
+                        {   // rows past the window are clamped (always inside the tile) and masked out: no divergence
+                            const uint32_t* r = tile32 + min(y, wh - 4) * BW4 + g;    // raw word holding tile column 4g + (delta & ~3)
                             const uint32_t c1 = __funnelshift_r(r[1], r[2], sh);      // pixels x .. x+3, x = 3 + 4g
                             const uint32_t c0 = __funnelshift_r(r[0], r[1], sh);
                             const uint32_t c2 = __funnelshift_r(r[2], r[3], sh);
@@ -385,7 +407,7 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
                             // bit 7 of a byte of ((a & 0x7f) + C) | a  <=>  a > t
                             const uint32_t s0 = (a0 & 0x7f7f7f7fu) + C, s8 = (a8 & 0x7f7f7f7fu) + C;
                             const uint32_t s4 = (a4 & 0x7f7f7f7fu) + C, s12 = (a12 & 0x7f7f7f7fu) + C;
-                            m[k] = ((s0 | a0) | (s8 | a8)) & ((s4 | a4) | (s12 | a12)) & vmask;
+                            m[k] = ((s0 | a0) | (s8 | a8)) & ((s4 | a4) | (s12 | a12)) & (y < wh - 3 ? vmask : 0u);
                         }
                     }
                     // per-lane counts are <= 4 and a warp total is <= 128, so four counts fit one register
@@ -420,15 +442,9 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
                 cn = 0;
                 for (int i0 = 0; i0 < qn; i0 += 32) {
                     const int i = i0 + lane;
-                    int s = 0, e = 0;
-                    if (i < qn) {
-                        e = queue[i];
-#ifdef ORBX_EXP_SKIP_P2
-                        s = 0;
-#else
-                        s = fast_score_packed(tile + (e >> 8) * BW + (e & 0xff), BW, t);
-#endif
-                    }
+                    const int e = queue[min(i, qn - 1)];                         // clamped: every lane scores a real pixel
+                    int s = fast_score_packed(tile + (e >> 8) * BW + (e & 0xff), BW, t);
+                    if (i >= qn) s = 0;
                     const uint32_t bal = __ballot_sync(0xffffffffu, s > 0);
                     if (s > 0) {
                         sc[(e >> 8) * SP + (e & 0xff) + 1] = (uint8_t)s;
@@ -1145,12 +1161,18 @@ cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* 
     static int per_sm_cache[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
+    typedef void (*fast_fn)(const FastMaps, const OrbxPlan*, int, int, uint32_t*, uint2*, int*, int*, int*);
+    fast_fn fn = hp.fast_bw == 64 ? fast_cells_kernel<64> : hp.fast_bw == 96 ? fast_cells_kernel<96> :
+                 hp.fast_bw == 128 ? fast_cells_kernel<128> : fast_cells_kernel<0>;
     if (smem != configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+        fast_fn all[4] = {fast_cells_kernel<64>, fast_cells_kernel<96>, fast_cells_kernel<128>, fast_cells_kernel<0>};
+        for (int i = 0; i < 4; ++i) {
+            cudaError_t e = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
         configured[dev & 63] = smem;
         int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_cells_kernel, hp.fast_warps * 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, hp.fast_warps * 32, smem);
         per_sm_cache[dev & 63] = per_sm < 1 ? 1 : per_sm;
     }
     const int W = hp.fast_warps;
@@ -1159,8 +1181,8 @@ cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* 
     const long long cap = (long long)num_sms * per_sm_cache[dev & 63];
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    fast_cells_kernel<<<(int)blocks, W * 32, smem, st>>>(*reinterpret_cast<const FastMaps*>(maps), d_plan, frame0, nframes,
-                                                        cand, cell_rec, level_counts, work_counter, status);
+    fn<<<(int)blocks, W * 32, smem, st>>>(*reinterpret_cast<const FastMaps*>(maps), d_plan, frame0, nframes, cand, cell_rec,
+                                          level_counts, work_counter, status);
     return cudaSuccess;
 }
 
