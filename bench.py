@@ -203,7 +203,6 @@ def own_arm(args):
     if min(kp_counts) == 0:
         raise SystemExit("bench: a frame produced no keypoints; refusing to time a degenerate run")
 
-    ex.stage_timing(True)
     l0 = ex.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sharding.barrier(); torch.cuda.synchronize()
@@ -214,6 +213,12 @@ def own_arm(args):
     ex.synchronize(); torch.cuda.synchronize(); sharding.barrier()
     dev_ms = e0.elapsed_time(e1)
     launches = ex.launch_count - l0
+    # second pass of K steps with per-stage CUDA events (each kernel then runs alone on the stream, i.e. without the
+    # blur/FAST overlap of the timed pass): the per-kernel durations behind the roofline table
+    ex.stage_timing(True)
+    for _ in range(K):
+        step_device()
+    ex.synchronize()
     stages = ex.stage_times()
     ex.stage_timing(False)
     dev_ms_max = sharding.max_over_ranks(dev_ms)

@@ -31,6 +31,8 @@ struct orbx_handle {
     int num_sms;
     cudaStream_t stream;          // kernels
     cudaStream_t stream2;         // second kernel stream: alternate sub-batches so their latency-bound tails overlap
+    cudaStream_t aux[2];          // side streams of stream / stream2: the blur only needs the pyramid, so it runs beside FAST/octree
+    cudaEvent_t ev_pyr[2], ev_blur[2];
     cudaStream_t h2d_stream, d2h_stream;
     cudaEvent_t ev_h2d[8], ev_done[8], ev_clear;
     std::string last_error;
@@ -399,6 +401,16 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
     if (ev) CK(h, cudaEventRecord(ev[ST_PYRAMID], st));
     for (int l = 0; l < L; ++l)
         orbx::launch_pyr_level(h->d_plan, P, l, n, h->num_sms, d_imgs, pitch, frame_stride, pyr, h->d_taps, st);
+    // Without per-stage timing the blur (which depends on the pyramid only) runs on a side stream beside
+    // FAST -> octree -> orientation; with timing on, every kernel runs alone so its duration is its own.
+    const int si = st == h->stream2 ? 1 : 0;
+    const bool overlap_blur = ev == 0;
+    if (overlap_blur) {
+        CK(h, cudaEventRecord(h->ev_pyr[si], st));
+        CK(h, cudaStreamWaitEvent(h->aux[si], h->ev_pyr[si], 0));
+        orbx::launch_blur(h->d_plan, P, n, h->num_sms, pyr, blur, h->aux[si]);
+        CK(h, cudaEventRecord(h->ev_blur[si], h->aux[si]));
+    }
     if (ev) CK(h, cudaEventRecord(ev[ST_FAST], st));
     CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), f0, n, h->num_sms, cand, cell_rec, level_counts,
                             h->d_work_counter() + chunk, status, st));
@@ -408,7 +420,8 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
     if (ev) CK(h, cudaEventRecord(ev[ST_ORIENT], st));
     orbx::launch_orient(h->d_plan, P, n, h->num_sms, pyr, kept, kept_counts, angles, rot, st);
     if (ev) CK(h, cudaEventRecord(ev[ST_BLUR], st));
-    orbx::launch_blur(h->d_plan, P, n, h->num_sms, pyr, blur, st);
+    if (overlap_blur) CK(h, cudaStreamWaitEvent(st, h->ev_blur[si], 0));
+    else orbx::launch_blur(h->d_plan, P, n, h->num_sms, pyr, blur, st);
     if (ev) CK(h, cudaEventRecord(ev[ST_DESC], st));
     orbx::launch_desc(h->d_plan, P, n, h->num_sms, blur, kept, kept_counts, angles, rot, out_kp, out_desc, st);
     if (ev) {
@@ -522,6 +535,12 @@ int orbx_create(const orbx_config* cfg, orbx_handle** out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     h->h2d_stream = h->d2h_stream = h->stream2 = 0;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+    for (int i = 0; i < 2; ++i) {
+        h->aux[i] = 0;
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pyr[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_blur[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_clear, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking);
@@ -544,6 +563,8 @@ int orbx_destroy(orbx_handle* h) {
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->stream2);
+    cudaStreamSynchronize(h->aux[0]);
+    cudaStreamSynchronize(h->aux[1]);
     cudaStreamSynchronize(h->h2d_stream);
     cudaStreamSynchronize(h->d2h_stream);
     free_geometry(h);
@@ -552,6 +573,7 @@ int orbx_destroy(orbx_handle* h) {
             for (int s = 0; s <= ST_COUNT; ++s) cudaEventDestroy(h->ev[i][s]);
     for (int i = 0; i < kMaxChunks; ++i) { cudaEventDestroy(h->ev_h2d[i]); cudaEventDestroy(h->ev_done[i]); }
     cudaEventDestroy(h->ev_clear);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_pyr[i]); cudaEventDestroy(h->ev_blur[i]); cudaStreamDestroy(h->aux[i]); }
     cudaStreamDestroy(h->stream2);
     cudaStreamDestroy(h->h2d_stream);
     cudaStreamDestroy(h->d2h_stream);

@@ -327,11 +327,20 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
     }
     __syncwarp();
 
+#ifdef ORBX_EXP_STATIC
+    unsigned static_next = blockIdx.x * (blockDim.x >> 5) + warp;
+    auto fetch = [&]() -> unsigned {
+        const unsigned v = static_next;
+        static_next += gridDim.x * (blockDim.x >> 5);
+        return v;
+    };
+#else
     auto fetch = [&]() -> unsigned {
         int v = 0;
         if (lane == 0) v = atomicAdd(work_counter, 1);
         return (unsigned)__shfl_sync(0xffffffffu, v, 0);
     };
+#endif
     auto issue = [&](const FastStrip& c, int b) {
         if (lane == 0) {
             const OrbxLevel& L = plan->lv[c.l];
