@@ -32,7 +32,7 @@ struct orbx_handle {
     cudaStream_t stream;          // kernels
     cudaStream_t stream2;         // second kernel stream: alternate sub-batches so their latency-bound tails overlap
     cudaStream_t aux[2];          // side streams of stream / stream2: the blur only needs the pyramid, so it runs beside FAST/octree
-    cudaEvent_t ev_pyr[2], ev_blur[2];
+    cudaEvent_t ev_pyr[2], ev_blur[2], ev_low[2], ev_fast_low[2];
     cudaStream_t h2d_stream, d2h_stream;
     cudaEvent_t ev_h2d[8], ev_done[8], ev_clear;
     std::string last_error;
@@ -77,7 +77,7 @@ struct orbx_handle {
     double stage_ms[ST_COUNT];
     int stage_launches[ST_COUNT];
 
-    int counters_count() const { return cfg.max_batch * (3 * plan.nlevels + 1) + kMaxChunks; }
+    int counters_count() const { return cfg.max_batch * (3 * plan.nlevels + 1) + 2 * kMaxChunks; }
     int* d_level_counts() const { return d_counters; }
     int* d_sorted_counts() const { return d_counters + cfg.max_batch * plan.nlevels; }
     int* d_kept_counts() const { return d_counters + 2 * cfg.max_batch * plan.nlevels; }
@@ -398,29 +398,43 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
     int* sorted_counts = h->d_sorted_counts() + f0 * L;
     int* kept_counts = h->d_kept_counts() + f0 * L;
     int* status = h->d_status() + f0;
-    if (ev) CK(h, cudaEventRecord(ev[ST_PYRAMID], st));
-    for (int l = 0; l < L; ++l)
-        orbx::launch_pyr_level(h->d_plan, P, l, n, h->num_sms, d_imgs, pitch, frame_stride, pyr, h->d_taps, st);
-    // Without per-stage timing the blur (which depends on the pyramid only) runs on a side stream beside
-    // FAST -> octree -> orientation; with timing on, every kernel runs alone so its duration is its own.
+    // Two schedules.  With per-stage timing on, every kernel runs alone on `st`, so its duration is its own.
+    // Otherwise the dependency graph is exploited with a side stream:
+    //   st : pyramid L0..1 | pyramid L2..  (small, latency-bound levels)  | FAST L2.. | octree | orient | descriptors
+    //   aux:               | FAST L0..1 (needs only those levels)         | blur (needs the pyramid only)
     const int si = st == h->stream2 ? 1 : 0;
-    const bool overlap_blur = ev == 0;
-    if (overlap_blur) {
+    const bool overlap = ev == 0;
+    const int ls = (overlap && L > 2) ? 2 : 0;                       // levels [0, ls) get their own FAST launch
+    cudaStream_t ax = h->aux[si];
+    int* wc = h->d_work_counter() + 2 * chunk;
+    if (ev) CK(h, cudaEventRecord(ev[ST_PYRAMID], st));
+    for (int l = 0; l < L; ++l) {
+        orbx::launch_pyr_level(h->d_plan, P, l, n, h->num_sms, d_imgs, pitch, frame_stride, pyr, h->d_taps, st);
+        if (ls && l == ls - 1) {
+            CK(h, cudaEventRecord(h->ev_low[si], st));
+            CK(h, cudaStreamWaitEvent(ax, h->ev_low[si], 0));
+            CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), f0, n, 0, ls, h->num_sms, cand, cell_rec, level_counts,
+                                    wc, status, ax));
+            CK(h, cudaEventRecord(h->ev_fast_low[si], ax));
+        }
+    }
+    if (overlap) {
         CK(h, cudaEventRecord(h->ev_pyr[si], st));
-        CK(h, cudaStreamWaitEvent(h->aux[si], h->ev_pyr[si], 0));
-        orbx::launch_blur(h->d_plan, P, n, h->num_sms, pyr, blur, h->aux[si]);
-        CK(h, cudaEventRecord(h->ev_blur[si], h->aux[si]));
+        CK(h, cudaStreamWaitEvent(ax, h->ev_pyr[si], 0));
+        orbx::launch_blur(h->d_plan, P, n, h->num_sms, pyr, blur, ax);
+        CK(h, cudaEventRecord(h->ev_blur[si], ax));
     }
     if (ev) CK(h, cudaEventRecord(ev[ST_FAST], st));
-    CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), f0, n, h->num_sms, cand, cell_rec, level_counts,
-                            h->d_work_counter() + chunk, status, st));
+    if (ls) CK(h, cudaStreamWaitEvent(st, h->ev_fast_low[si], 0));
+    CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), f0, n, ls, L, h->num_sms, cand, cell_rec, level_counts,
+                            wc + 1, status, st));
     if (ev) CK(h, cudaEventRecord(ev[ST_OCTREE], st));
     CK(h, orbx::launch_octree(h->d_plan, P, n, cand, cell_rec, cand_sorted, key_node, sorted_counts, kept, kept_counts,
                               status, st));
     if (ev) CK(h, cudaEventRecord(ev[ST_ORIENT], st));
     orbx::launch_orient(h->d_plan, P, n, h->num_sms, pyr, kept, kept_counts, angles, rot, st);
     if (ev) CK(h, cudaEventRecord(ev[ST_BLUR], st));
-    if (overlap_blur) CK(h, cudaStreamWaitEvent(st, h->ev_blur[si], 0));
+    if (overlap) CK(h, cudaStreamWaitEvent(st, h->ev_blur[si], 0));
     else orbx::launch_blur(h->d_plan, P, n, h->num_sms, pyr, blur, st);
     if (ev) CK(h, cudaEventRecord(ev[ST_DESC], st));
     orbx::launch_desc(h->d_plan, P, n, h->num_sms, blur, kept, kept_counts, angles, rot, out_kp, out_desc, st);
@@ -431,7 +445,7 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
         h->stage_launches[ST_PYRAMID] += L;
         for (int s = ST_FAST; s < ST_COUNT; ++s) h->stage_launches[s] += 1;
     }
-    h->launches += L + 5;
+    h->launches += L + 5 + (ls ? 1 : 0);
     CK(h, cudaGetLastError());
     return ORBX_OK;
 }
@@ -540,6 +554,8 @@ int orbx_create(const orbx_config* cfg, orbx_handle** out) {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pyr[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_blur[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_low[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fast_low[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_clear, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking);
@@ -573,7 +589,7 @@ int orbx_destroy(orbx_handle* h) {
             for (int s = 0; s <= ST_COUNT; ++s) cudaEventDestroy(h->ev[i][s]);
     for (int i = 0; i < kMaxChunks; ++i) { cudaEventDestroy(h->ev_h2d[i]); cudaEventDestroy(h->ev_done[i]); }
     cudaEventDestroy(h->ev_clear);
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_pyr[i]); cudaEventDestroy(h->ev_blur[i]); cudaStreamDestroy(h->aux[i]); }
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_pyr[i]); cudaEventDestroy(h->ev_blur[i]); cudaEventDestroy(h->ev_low[i]); cudaEventDestroy(h->ev_fast_low[i]); cudaStreamDestroy(h->aux[i]); }
     cudaStreamDestroy(h->stream2);
     cudaStreamDestroy(h->h2d_stream);
     cudaStreamDestroy(h->d2h_stream);

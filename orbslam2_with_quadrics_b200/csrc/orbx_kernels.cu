@@ -214,13 +214,14 @@ struct FastStrip {
     int frame, l, ci, cj0;     // NC horizontally adjacent cells starting at column cj0 of cell row ci
 };
 
-__device__ __forceinline__ FastStrip fast_decode(const OrbxPlan* __restrict__ plan, unsigned item) {
+// Items of one launch: the strips of levels [l0, l1) of every frame, frame-major.
+__device__ __forceinline__ FastStrip fast_decode(const OrbxPlan* __restrict__ plan, unsigned item, int l0, int l1,
+                                                 unsigned spf, int first_strip) {
     FastStrip c;
-    const unsigned spf = (unsigned)plan->strips_per_frame;
     c.frame = (int)(item / spf);
-    const int r = (int)(item - (unsigned)c.frame * spf);
-    int l = 0;
-    while (l + 1 < plan->nlevels && r >= plan->lv[l + 1].strip_base) ++l;
+    const int r = (int)(item - (unsigned)c.frame * spf) + first_strip;
+    int l = l0;
+    while (l + 1 < l1 && r >= plan->lv[l + 1].strip_base) ++l;
     c.l = l;
     const OrbxLevel& L = plan->lv[l];
     c.ci = (int)((unsigned)(r - L.strip_base) / (unsigned)L.strips_x);
@@ -298,7 +299,7 @@ __device__ __forceinline__ int fast_score_packed(const uint8_t* __restrict__ p, 
 template <int BW_T>
 __global__ void __launch_bounds__(ORBX_FAST_WARPS * 32, ORBX_FAST_MINB)
 fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, int frame0, int nframes,
-                  uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec, int* __restrict__ level_counts,
+                  int l0, int l1, uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec, int* __restrict__ level_counts,
                   int* __restrict__ work_counter, int* __restrict__ status) {
     extern __shared__ uint8_t fast_smem_raw[];
     __shared__ uint64_t s_bar[ORBX_FAST_WARPS][2];
@@ -314,7 +315,9 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
     uint8_t* sc = base + NB * TB;                                        // zero-framed score map
     uint16_t* queue = reinterpret_cast<uint16_t*>(base + NB * TB + SB);  // entries (y << 8) | x, window coordinates
     const int nlevels = plan->nlevels;
-    const unsigned total = (unsigned)nframes * (unsigned)plan->strips_per_frame;
+    const int first_strip = plan->lv[l0].strip_base;
+    const unsigned spf = (unsigned)((l1 < nlevels ? plan->lv[l1].strip_base : plan->strips_per_frame) - first_strip);
+    const unsigned total = (unsigned)nframes * spf;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int BW4 = BW >> 2;
 
@@ -355,11 +358,11 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
     unsigned cur = fetch();
     unsigned nxt = fetch();
     FastStrip cc, nc;
-    if (cur < total) { cc = fast_decode(plan, cur); issue(cc, 0); }
+    if (cur < total) { cc = fast_decode(plan, cur, l0, l1, spf, first_strip); issue(cc, 0); }
     uint32_t phase[2] = {0, 0};
     int b = 0;
     while (cur < total) {
-        if (NB == 2 && nxt < total) { nc = fast_decode(plan, nxt); issue(nc, b ^ 1); }
+        if (NB == 2 && nxt < total) { nc = fast_decode(plan, nxt, l0, l1, spf, first_strip); issue(nc, b ^ 1); }
         const unsigned nxt2 = nxt < total ? fetch() : nxt;
         mbar_wait(&s_bar[warp][b], phase[b]);
         phase[b] ^= 1;
@@ -520,7 +523,7 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
                 make_uint2((uint32_t)gbase, overflow ? 0u : (uint32_t)count);
         __syncwarp();
         }   // cells of the strip
-        if (NB == 1 && nxt < total) { nc = fast_decode(plan, nxt); issue(nc, 0); }
+        if (NB == 1 && nxt < total) { nc = fast_decode(plan, nxt, l0, l1, spf, first_strip); issue(nc, 0); }
         cur = nxt;
         nxt = nxt2;
         cc = nc;
@@ -1162,15 +1165,15 @@ int build_fast_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* ou
 
 size_t fast_maps_bytes() { return sizeof(FastMaps); }
 
-cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, int frame0, int nframes, int num_sms,
-                        uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counter, int* status,
+cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, int frame0, int nframes, int l0,
+                        int l1, int num_sms, uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counter, int* status,
                         cudaStream_t st) {
     const size_t smem = fast_smem_bytes(hp);
     static size_t configured[64] = {0};
     static int per_sm_cache[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
-    typedef void (*fast_fn)(const FastMaps, const OrbxPlan*, int, int, uint32_t*, uint2*, int*, int*, int*);
+    typedef void (*fast_fn)(const FastMaps, const OrbxPlan*, int, int, int, int, uint32_t*, uint2*, int*, int*, int*);
     fast_fn fn = hp.fast_bw == 64 ? fast_cells_kernel<64> : hp.fast_bw == 96 ? fast_cells_kernel<96> :
                  hp.fast_bw == 128 ? fast_cells_kernel<128> : fast_cells_kernel<0>;
     if (smem != configured[dev & 63]) {
@@ -1185,13 +1188,14 @@ cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* 
         per_sm_cache[dev & 63] = per_sm < 1 ? 1 : per_sm;
     }
     const int W = hp.fast_warps;
-    const long long total = (long long)nframes * hp.strips_per_frame;
+    const int strips = (l1 < hp.nlevels ? hp.lv[l1].strip_base : hp.strips_per_frame) - hp.lv[l0].strip_base;
+    const long long total = (long long)nframes * strips;
     long long blocks = (total + W - 1) / W;
     const long long cap = (long long)num_sms * per_sm_cache[dev & 63];
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    fn<<<(int)blocks, W * 32, smem, st>>>(*reinterpret_cast<const FastMaps*>(maps), d_plan, frame0, nframes, cand, cell_rec,
-                                          level_counts, work_counter, status);
+    fn<<<(int)blocks, W * 32, smem, st>>>(*reinterpret_cast<const FastMaps*>(maps), d_plan, frame0, nframes, l0, l1, cand,
+                                          cell_rec, level_counts, work_counter, status);
     return cudaSuccess;
 }
 

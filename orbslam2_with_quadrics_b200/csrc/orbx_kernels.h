@@ -20,7 +20,7 @@ void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nfr
 size_t fast_smem_bytes(const OrbxPlan& hp);
 int build_fast_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* out_maps);
 size_t fast_maps_bytes();
-cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, int frame0, int nframes, int num_sms,
+cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, int frame0, int nframes, int l0, int l1, int num_sms,
                         uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counter, int* status,
                         cudaStream_t st);
 size_t octree_smem_bytes(const OrbxPlan& hp);
