@@ -452,8 +452,24 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
 
 int enqueue_pipeline(orbx_handle* h, int n, const uint8_t* d_imgs, size_t pitch, size_t frame_stride) {
     CK(h, cudaMemsetAsync(h->d_counters, 0, sizeof(int) * h->counters_count(), h->stream));
-    int rc = enqueue_frames(h, 0, n, d_imgs, pitch, frame_stride, 0, h->stream);
-    if (rc != ORBX_OK) return rc;
+    // Two half-batches on the two kernel streams: the latency-bound tail of one half (octree, orientation,
+    // descriptors) overlaps the issue-bound head (pyramid, FAST) of the other.  With per-stage timing on, one
+    // stream runs everything so each kernel's duration is its own.
+    const int nchunks = (!h->timing && n >= 8) ? 2 : 1;
+    if (nchunks > 1) {
+        CK(h, cudaEventRecord(h->ev_clear, h->stream));
+        CK(h, cudaStreamWaitEvent(h->stream2, h->ev_clear, 0));
+    }
+    for (int k = 0; k < nchunks; ++k) {
+        const int f0 = (int)((long long)n * k / nchunks), f1 = (int)((long long)n * (k + 1) / nchunks);
+        cudaStream_t cs = (k & 1) ? h->stream2 : h->stream;
+        int rc = enqueue_frames(h, f0, f1 - f0, d_imgs + (size_t)f0 * frame_stride, pitch, frame_stride, k, cs);
+        if (rc != ORBX_OK) return rc;
+    }
+    if (nchunks > 1) {      // join: everything recorded on the handle's stream after this call covers both halves
+        CK(h, cudaEventRecord(h->ev_done[0], h->stream2));
+        CK(h, cudaStreamWaitEvent(h->stream, h->ev_done[0], 0));
+    }
     h->last_n = n;
     h->pyramid_valid = false;
     return ORBX_OK;
