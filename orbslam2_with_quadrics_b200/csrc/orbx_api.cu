@@ -455,7 +455,11 @@ int enqueue_pipeline(orbx_handle* h, int n, const uint8_t* d_imgs, size_t pitch,
     // Two half-batches on the two kernel streams: the latency-bound tail of one half (octree, orientation,
     // descriptors) overlaps the issue-bound head (pyramid, FAST) of the other.  With per-stage timing on, one
     // stream runs everything so each kernel's duration is its own.
-    const int nchunks = (!h->timing && n >= 8) ? 2 : 1;
+    const char* e_ch = getenv("ORBX_DEVICE_CHUNKS");          // tuning override
+    int nchunks = (!h->timing && n >= 8) ? (e_ch ? atoi(e_ch) : 2) : 1;
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > kMaxChunks) nchunks = kMaxChunks;
+    if (nchunks > n) nchunks = n;
     if (nchunks > 1) {
         CK(h, cudaEventRecord(h->ev_clear, h->stream));
         CK(h, cudaStreamWaitEvent(h->stream2, h->ev_clear, 0));
