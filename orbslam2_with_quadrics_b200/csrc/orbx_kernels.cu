@@ -981,18 +981,20 @@ __global__ void __launch_bounds__(128) blur_kernel(const OrbxPlan* __restrict__ 
         const int x = tx * BL_TW + 4 * lane, y0 = ty * BL_TH;
         if (x >= L.w) continue;
         const int pitch = L.pitch;
-        const int last_row = L.h + ORBX_EDGE - 1;                         // last valid plane row (level coordinates)
-        const uint8_t* src = pyr + (size_t)frame * plan->slab_bytes + L.plane_off + (size_t)ORBX_EDGE * pitch + ORBX_XO + x - 4;
-        uint8_t* dst = blur + (size_t)frame * plan->slab_bytes + L.plane_off + (size_t)ORBX_EDGE * pitch + ORBX_XO + x;
+        // Row pointers advance by one pitch per row (one 64-bit add instead of a multiply per access); the last valid
+        // plane row is level row h+18, rows past it (partial bottom tiles) re-read it and their outputs are not stored.
+        const int rows_ok = L.h + ORBX_EDGE - (y0 - 3);                    // readable rows from the first tap row on
+        const uint8_t* srow = pyr + (size_t)frame * plan->slab_bytes + L.plane_off + (size_t)(ORBX_EDGE + y0 - 3) * pitch + ORBX_XO + x - 4;
+        uint8_t* drow = blur + (size_t)frame * plan->slab_bytes + L.plane_off + (size_t)(ORBX_EDGE + y0) * pitch + ORBX_XO + x;
         uint32_t P[4][4];                                                 // ring of row pairs x 4 columns
 #pragma unroll
         for (int m = 0; m < (BL_TH + 6) / 2; ++m) {
             uint32_t hs[2][4];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int yy = min(y0 - 3 + 2 * m + e, last_row);
-                const uint32_t* rp = reinterpret_cast<const uint32_t*>(src + (long long)yy * pitch);
+                const uint32_t* rp = reinterpret_cast<const uint32_t*>(srow);
                 const uint32_t w0 = __ldg(rp), w1 = __ldg(rp + 1), w2 = __ldg(rp + 2);
+                if (2 * m + e + 1 < rows_ok) srow += pitch;
                 hs[e][0] = __dp4a(__funnelshift_r(w0, w1, 8), K0123, __dp4a(__funnelshift_r(w1, w2, 8), K456, 0u));
                 hs[e][1] = __dp4a(__funnelshift_r(w0, w1, 16), K0123, __dp4a(__funnelshift_r(w1, w2, 16), K456, 0u));
                 hs[e][2] = __dp4a(__funnelshift_r(w0, w1, 24), K0123, __dp4a(__funnelshift_r(w1, w2, 24), K456, 0u));
@@ -1010,11 +1012,12 @@ __global__ void __launch_bounds__(128) blur_kernel(const OrbxPlan* __restrict__ 
                     vo[c] = __dp2a_lo(p0, KC, __dp2a_hi(p1, KC, __dp2a_lo(p2, KD, __dp2a_hi(p3, KD, 32768u))));
                 }
                 if (oe < L.h)
-                    *reinterpret_cast<uint32_t*>(dst + (long long)oe * pitch) =
+                    *reinterpret_cast<uint32_t*>(drow) =
                         __byte_perm(__byte_perm(ve[0], ve[1], 0x0062), __byte_perm(ve[2], ve[3], 0x0062), 0x5410);
                 if (oe + 1 < L.h)
-                    *reinterpret_cast<uint32_t*>(dst + (long long)(oe + 1) * pitch) =
+                    *reinterpret_cast<uint32_t*>(drow + pitch) =
                         __byte_perm(__byte_perm(vo[0], vo[1], 0x0062), __byte_perm(vo[2], vo[3], 0x0062), 0x5410);
+                drow += 2 * pitch;
             }
         }
     }
