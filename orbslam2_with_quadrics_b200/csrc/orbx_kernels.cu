@@ -118,38 +118,64 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const OrbxPlan* __restr
     const int spitch = S.pitch;
     uint32_t HA[4] = {0, 0, 0, 0}, HB[4] = {0, 0, 0, 0};
     int rowA = -1, rowB = -1;
+    // the three source words of a row (non-WIDE); loaded one output row ahead so the DRAM/L2 latency of the
+    // next row pass overlaps the arithmetic of the current one
+    struct Words { uint32_t w0, w1, w2; };
+    auto load_row = [&](int sy) -> Words {
+        const uint32_t* rp = reinterpret_cast<const uint32_t*>(sbase + (unsigned)(sy * spitch));
+        Words q;
+        q.w0 = rp[0]; q.w1 = rp[1]; q.w2 = rp[2];
+        return q;
+    };
+    auto row_pass_words = [&](const Words& q, uint32_t* H) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t pair = __funnelshift_r(hiw[j] ? q.w1 : q.w0, hiw[j] ? q.w2 : q.w1, sh[j]);
+            H[j] = __dp2a_lo(coef[j], pair, 0u) >> 4;                         // (S[sx]*a0 + S[sx+1]*a1) >> 4
+        }
+    };
     auto row_pass = [&](int sy, uint32_t* H) {
-        const uint32_t* rp = reinterpret_cast<const uint32_t*>(sbase + (size_t)sy * spitch);
         if (WIDE) {
+            const uint32_t* rp = reinterpret_cast<const uint32_t*>(sbase + (unsigned)(sy * spitch));
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t pair = __funnelshift_r(rp[wofs[j]], rp[wofs[j] + 1], sh[j]);
                 H[j] = __dp2a_lo(coef[j], pair, 0u) >> 4;
             }
         } else {
-            const uint32_t w0 = rp[0], w1 = rp[1], w2 = rp[2];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t pair = __funnelshift_r(hiw[j] ? w1 : w0, hiw[j] ? w2 : w1, sh[j]);
-                H[j] = __dp2a_lo(coef[j], pair, 0u) >> 4;                     // (S[sx]*a0 + S[sx+1]*a1) >> 4
-            }
+            row_pass_words(load_row(sy), H);
         }
     };
     const int row_end = min(row0 + RY, L.rows);
+    const int hs1 = S.h - 1;
     uint8_t* dst = slab + L.plane_off + (size_t)row0 * L.pitch + c;
+    const OrbxTap* ytab = taps + L.ytab_off;
+    OrbxTap ty = ytab[reflect_clamp(row0 - ORBX_EDGE, h)];
+    Words pre = {0, 0, 0};
+    if (!WIDE) pre = load_row(min(ty.ofs + 1, hs1));                          // row r1 of the first output row
     for (int row = row0; row < row_end; ++row, dst += L.pitch) {
-        const int dy = reflect_clamp(row - ORBX_EDGE, h);
-        const OrbxTap ty = taps[L.ytab_off + dy];
-        const int r0 = ty.ofs, r1 = min(r0 + 1, S.h - 1);
+        // prefetch for the next output row: its tap entry and (speculatively) its second source row
+        const OrbxTap tyn = ytab[reflect_clamp(min(row + 1, L.rows - 1) - ORBX_EDGE, h)];
+        Words pren = {0, 0, 0};
+        if (!WIDE) pren = load_row(min(tyn.ofs + 1, hs1));
+        const int r0 = ty.ofs, r1 = min(r0 + 1, hs1);
         if (r0 == rowB) {                                                     // the usual step: one new source row
 #pragma unroll
             for (int j = 0; j < 4; ++j) HA[j] = HB[j];
             rowA = rowB;
-            if (r1 != r0) { row_pass(r1, HB); rowB = r1; }
+            if (r1 != r0) {
+                if (WIDE) row_pass(r1, HB); else row_pass_words(pre, HB);
+                rowB = r1;
+            }
         } else if (!(r0 == rowA && (r1 == rowB || r1 == r0))) {
             row_pass(r0, HA);
             rowA = r0;
-            if (r1 != r0) { row_pass(r1, HB); rowB = r1; } else { rowB = -1; }
+            if (r1 != r0) {
+                if (WIDE) row_pass(r1, HB); else row_pass_words(pre, HB);
+                rowB = r1;
+            } else {
+                rowB = -1;
+            }
         }
         // when the source row is clamped (r1 == r0) the table's second weight is 0, so a stale HB is harmless
         const uint32_t b0 = (uint32_t)ty.c0 << 16, b1 = (uint32_t)ty.c1 << 16;
@@ -161,6 +187,8 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const OrbxPlan* __restr
             out |= v << (8 * j);
         }
         *reinterpret_cast<uint32_t*>(dst) = out;
+        ty = tyn;
+        pre = pren;
     }
 }
 
