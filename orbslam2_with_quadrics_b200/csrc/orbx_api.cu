@@ -49,7 +49,7 @@ struct orbx_handle {
     std::vector<OrbxTap> taps;
     OrbxPlan* d_plan;
     OrbxTap* d_taps;
-    int in_pitch;
+    int in_pitch;                // capacity of a staged input row (bytes)
     uint8_t *d_input, *d_pyr, *d_blur;
     uint32_t *d_cand, *d_cand_sorted, *d_kept;
     uint16_t* d_key_node;
@@ -322,7 +322,7 @@ int ensure_geometry(orbx_handle* h, int w, int hgt) {
     h->plan = P;
     h->taps.swap(taps);
     const size_t B = (size_t)h->cfg.max_batch;
-    h->in_pitch = round_up(w, 16);
+    h->in_pitch = round_up(w, 64) + 64;      // room to adopt the caller's own row stride (1-D H2D copies)
     CK(h, cudaMalloc(&h->d_plan, sizeof(OrbxPlan)));
     CK(h, cudaMalloc(&h->d_taps, sizeof(OrbxTap) * (h->taps.size() + 1)));
     CK(h, cudaMalloc(&h->d_input, B * hgt * h->in_pitch));
@@ -644,7 +644,16 @@ int orbx_extract_batch(orbx_handle* h, int n, const uint8_t* const* imgs, int wi
     int rc = ensure_geometry(h, width, height);
     if (rc != ORBX_OK) return rc;
     const OrbxPlan& P = h->plan;
-    const size_t fbytes = (size_t)height * h->in_pitch;
+    // The staging buffer adopts the caller's row stride when all frames share one that fits: frames then go up as plain
+    // 1-D copies (a strided 2-D cudaMemcpy of a 752x480 frame measured ~10x slower than the 1-D copy of the same bytes).
+    size_t pitch = (size_t)round_up(width, 16);
+    {
+        const size_t s0 = strides ? strides[0] : (size_t)width;
+        bool same = s0 <= (size_t)h->in_pitch;
+        for (int i = 1; i < n && same; ++i) same = (strides ? strides[i] : (size_t)width) == s0;
+        if (same) pitch = s0;
+    }
+    const size_t fbytes = (size_t)height * pitch;
     const size_t kpf = (size_t)P.kept_per_frame;
     // Sub-batches pipeline the three engines: H2D of chunk k+1, kernels of chunk k and D2H of chunk k-1 overlap.
     int nchunks = n >= 16 ? 4 : (n >= 4 ? 2 : 1);
@@ -655,25 +664,35 @@ int orbx_extract_batch(orbx_handle* h, int n, const uint8_t* const* imgs, int wi
     for (int k = 0; k < nchunks; ++k) {
         cudaStream_t cs = (k & 1) ? h->stream2 : h->stream;
         const int f0 = (int)((long long)n * k / nchunks), f1 = (int)((long long)n * (k + 1) / nchunks);
-        for (int i = f0; i < f1; ++i) {
+        for (int i = f0; i < f1;) {
             const size_t stride = strides ? strides[i] : (size_t)width;
             cudaPointerAttributes attr;
             bool pinned = cudaPointerGetAttributes(&attr, imgs[i]) == cudaSuccess && attr.type == cudaMemoryTypeHost;
             if (!pinned) cudaGetLastError();
+            if (pinned && stride == pitch) {
+                // same pitch on both sides: plain 1-D copies, and frames that are contiguous in the caller's
+                // pinned buffer (a ring of camera frames) go as ONE copy
+                int j = i + 1;
+                while (j < f1 && imgs[j] == imgs[j - 1] + fbytes && (strides ? strides[j] : (size_t)width) == stride) ++j;
+                CK(h, cudaMemcpyAsync(h->d_input + i * fbytes, imgs[i], (size_t)(j - i) * fbytes, cudaMemcpyHostToDevice, h->h2d_stream));
+                i = j;
+                continue;
+            }
             const uint8_t* src = imgs[i];
             size_t spitch = stride;
             if (!pinned) {     // pageable caller memory: stage through the handle's pinned buffer
                 uint8_t* stg = h->h_input + i * fbytes;
-                for (int y = 0; y < height; ++y) memcpy(stg + (size_t)y * h->in_pitch, imgs[i] + (size_t)y * stride, (size_t)width);
-                src = stg;
-                spitch = (size_t)h->in_pitch;
+                for (int y = 0; y < height; ++y) memcpy(stg + (size_t)y * pitch, imgs[i] + (size_t)y * stride, (size_t)width);
+                CK(h, cudaMemcpyAsync(h->d_input + i * fbytes, stg, fbytes, cudaMemcpyHostToDevice, h->h2d_stream));
+            } else {
+                CK(h, cudaMemcpy2DAsync(h->d_input + i * fbytes, pitch, src, spitch, (size_t)width, (size_t)height,
+                                        cudaMemcpyHostToDevice, h->h2d_stream));
             }
-            CK(h, cudaMemcpy2DAsync(h->d_input + i * fbytes, (size_t)h->in_pitch, src, spitch, (size_t)width, (size_t)height,
-                                    cudaMemcpyHostToDevice, h->h2d_stream));
+            ++i;
         }
         CK(h, cudaEventRecord(h->ev_h2d[k], h->h2d_stream));
         CK(h, cudaStreamWaitEvent(cs, h->ev_h2d[k], 0));
-        rc = enqueue_frames(h, f0, f1 - f0, h->d_input + f0 * fbytes, (size_t)h->in_pitch, fbytes, k, cs);
+        rc = enqueue_frames(h, f0, f1 - f0, h->d_input + f0 * fbytes, pitch, fbytes, k, cs);
         if (rc != ORBX_OK) return rc;
         CK(h, cudaEventRecord(h->ev_done[k], cs));
         CK(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_done[k], 0));

@@ -71,6 +71,15 @@ __global__ void __launch_bounds__(256) pyr_level0_kernel(const OrbxPlan* __restr
     uint4 out;
     if (aligned16 && dx0 >= 0 && dx0 + 15 < w) {
         out = __ldg(reinterpret_cast<const uint4*>(src + dx0));
+    } else if (dx0 >= 16 && dx0 + 20 <= w) {
+        // source rows of arbitrary alignment (e.g. a 1241-byte stride): five aligned words, re-aligned with funnel
+        // shifts; the reads stay inside this image row
+        const uint8_t* ps = src + dx0;
+        const int a = (int)(reinterpret_cast<uintptr_t>(ps) & 3);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(ps - a);
+        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
+        out = make_uint4(__funnelshift_r(w0, w1, 8 * a), __funnelshift_r(w1, w2, 8 * a), __funnelshift_r(w2, w3, 8 * a),
+                         __funnelshift_r(w3, w4, 8 * a));
     } else {
         uint32_t o[4] = {0, 0, 0, 0};
 #pragma unroll
