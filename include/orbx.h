@@ -50,7 +50,7 @@ typedef enum orbx_status {
 /* The five constructor arguments of ORBextractor (src/ORBextractor.cc:410-414) + placement. */
 typedef struct orbx_config {
     int nfeatures;
-    float scale_factor;
+    float scale_factor;   /* 1 < scale_factor <= 2 */
     int nlevels;
     int ini_th_fast;
     int min_th_fast;

@@ -543,7 +543,8 @@ const char* orbx_last_cuda_error(orbx_handle* h) { return h ? h->last_error.c_st
 int orbx_create(const orbx_config* cfg, orbx_handle** out) {
     if (!cfg || !out) return ORBX_ERR_BAD_ARGS;
     *out = 0;
-    if (cfg->nlevels < 1 || cfg->nlevels > ORBX_MAXL || cfg->nfeatures < 1 || !(cfg->scale_factor > 1.0f) ||
+    // scale factors above 2 would make a lane's 4 output pixels read past the 19-px border of the source row
+    if (cfg->nlevels < 1 || cfg->nlevels > ORBX_MAXL || cfg->nfeatures < 1 || !(cfg->scale_factor > 1.0f) || cfg->scale_factor > 2.0f ||
         cfg->ini_th_fast < 1 || cfg->min_th_fast < 1 || cfg->ini_th_fast > 254 || cfg->min_th_fast > 254 ||
         cfg->max_batch < 1)
         return ORBX_ERR_BAD_ARGS;

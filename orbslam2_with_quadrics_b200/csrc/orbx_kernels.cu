@@ -224,6 +224,11 @@ struct FastMaps {
     CUtensorMap m[ORBX_MAXL];
 };
 
+// ceil(65536 / G): (n * c_recip16[G]) >> 16 == n / G for n <= 32, G <= 32
+static __constant__ int c_recip16[33] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042,
+                                         4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428,
+                                         2341, 2260, 2185, 2115, 2048};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -425,7 +430,7 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
 #endif
             const int ew = ww - 6;                                       // emission width
             const int G = (ew + 3) >> 2;                                 // 4-pixel groups per row
-            const int mg = (int)((65536u + (unsigned)G - 1u) / (unsigned)G);   // (n * mg) >> 16 == n / G for n <= 32
+            const int mg = c_recip16[min(G, 32)];                       // (n * mg) >> 16 == n / G for n <= 32
             const int RPI = (32 * mg) >> 16;                             // rows per warp iteration
             const int ry = (lane * mg) >> 16, g = lane - ry * G;
             const int nvalid = min(max(ew - 4 * g, 0), 4);
@@ -551,10 +556,9 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, keep);
             if (keep && !overflow) dst[w + __popc(bal & lt_mask)] = ORBX_PACK(x + ox, y + oy, s);
+            if (i < cn) sc[y * SP + x + 1] = 0;                               // leave the score map all-zero (NMS is done)
             w += __popc(bal);
         }
-        __syncwarp();
-        for (int i = lane; i < cn; i += 32) sc[((queue[i] >> 8) & 0x7f) * SP + (queue[i] & 0xff) + 1] = 0;   // leave the map all-zero
         if (lane == 0)
             cell_rec[(size_t)cc.frame * plan->cells_per_frame + L.cell_base + cc.ci * L.nColsV + cj] =
                 make_uint2((uint32_t)gbase, overflow ? 0u : (uint32_t)count);

@@ -42,7 +42,7 @@ def test_strerror_and_version(lib):
 
 def test_bad_config_is_rejected_before_touching_cuda(lib):
     h = C.c_void_p()
-    for bad in [dict(nlevels=0), dict(nlevels=17), dict(nfeatures=0), dict(scale_factor=1.0), dict(ini_th_fast=0), dict(max_batch=0)]:
+    for bad in [dict(nlevels=0), dict(nlevels=17), dict(nfeatures=0), dict(scale_factor=1.0), dict(scale_factor=2.5), dict(ini_th_fast=0), dict(max_batch=0)]:
         kw = dict(nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th_fast=20, min_th_fast=7, device=0, max_batch=1,
                   download_pyramid=1, candidate_divisor=0)
         kw.update(bad)
