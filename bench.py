@@ -321,7 +321,8 @@ def own_arm(args):
     tf = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(tf):
         try:
-            traffic = json.load(open(tf)).get(name)
+            t = json.load(open(tf)).get(name)
+            traffic = t["bytes_per_frame"] * B if t else None      # per launch sequence, like `achieved`
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
