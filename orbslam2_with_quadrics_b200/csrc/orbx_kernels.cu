@@ -205,18 +205,21 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const OrbxPlan* __restr
 // FAST-9/16 per 30-px cell (cv::FAST(window, t, true)), one warp per cell,
 // persistent warps with a dynamic work counter.
 //
-// Staging: each cell window is fetched by ONE elected lane with a TMA tile load
-// (cp.async.bulk.tensor.3d over a per-level {pitch, rows, frame} tensor map) into a
-// double-buffered shared-memory tile; the next cell's tile is in flight while the current one
-// is processed.  TMA needs the inner coordinate on a 16-byte boundary, so the BW x BH box starts
-// at the 16-aligned column at or before (window x0 - 1) and the window sits `delta` (0..15) bytes
-// into the tile: tile column = window x + 1 + delta.  Words are re-aligned with funnel shifts.
+// Staging: a work item is a strip of NC horizontally adjacent cell windows (default 2), fetched by
+// ONE elected lane with a TMA tile load (cp.async.bulk.tensor.3d over a per-level
+// {pitch, rows, frame} tensor map, mbarrier complete_tx) into shared memory (NB = 1 or 2 tile
+// buffers per warp; with 2 the next strip is in flight while the current one is processed --
+// measured equal, so the default is 1 and more resident warps).  TMA needs the inner coordinate
+// on a 16-byte boundary, so the BW x BH box starts at the 16-aligned column at or before
+// (window x0 - 1) and a window sits `delta` bytes into the tile: tile column = window x + 1 +
+// delta.  Words are re-aligned with funnel shifts.
 //   phase 1  4 pixels per lane, SIMD-in-word: |ring - centre| for the compass points 0/8 and
 //            4/12 with VABSDIFF4; a 9-arc needs one pixel of every opposite pair beyond the
-//            threshold, so pixels failing either pair are dropped.  Survivors are compacted in
-//            row-major order with a warp scan.
+//            threshold, so pixels failing either pair are dropped.  8 warp iterations of tests
+//            are issued back to back, their survivor counts scanned together (packed 8-bit
+//            counts), survivors queued in row-major order.
 //   phase 2  per survivor: exact score A = max over the 16 arcs of min(+-(ring - centre)) with
-//            packed 16-bit VIMNMX3 (two arcs per instruction); corner iff A > t, score = A - 1.
+//            packed 16-bit min/max (two arcs per instruction); corner iff A > t, score = A - 1.
 //   phase 3  strict 3x3 NMS on a zero-framed score map, count, then ordered emission.
 // The iniThFAST pass is repeated with minThFAST iff it produced no keypoint (:812).
 // =====================================================================================
