@@ -500,7 +500,11 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
                 for (int i0 = 0; i0 < qn; i0 += 32) {
                     const int i = i0 + lane;
                     const int e = queue[min(i, qn - 1)];                         // clamped: every lane scores a real pixel
+#ifdef ORBX_EXP_SKIP_P2
+                    int s = 0;
+#else
                     int s = fast_score_packed(tile + (e >> 8) * BW + (e & 0xff), BW, t);
+#endif
                     if (i >= qn) s = 0;
                     const uint32_t bal = __ballot_sync(0xffffffffu, s > 0);
                     if (s > 0) {
