@@ -7,7 +7,7 @@
 #include "orbx_plan.h"
 
 #define ORBX_FAST_WARPS 8
-#define ORBX_OT_THREADS 512
+#define ORBX_OT_THREADS 1024
 
 // per-frame device status bits
 #define ORBX_DEV_CAND_OVERFLOW 1
