@@ -660,8 +660,13 @@ int orbx_extract_batch(orbx_handle* h, int n, const uint8_t* const* imgs, int wi
     int nchunks = n >= 16 ? 4 : (n >= 4 ? 2 : 1);
     if (nchunks > kMaxChunks) nchunks = kMaxChunks;
     CK(h, cudaMemsetAsync(h->d_counters, 0, sizeof(int) * h->counters_count(), h->stream));
-    CK(h, cudaEventRecord(h->ev_clear, h->stream));
-    CK(h, cudaStreamWaitEvent(h->stream2, h->ev_clear, 0));
+    // a single sub-batch (latency mode) stays on one stream: no cross-stream events on the critical path
+    const bool one = nchunks == 1;
+    cudaStream_t h2d = one ? h->stream : h->h2d_stream, d2h = one ? h->stream : h->d2h_stream;
+    if (!one) {
+        CK(h, cudaEventRecord(h->ev_clear, h->stream));
+        CK(h, cudaStreamWaitEvent(h->stream2, h->ev_clear, 0));
+    }
     for (int k = 0; k < nchunks; ++k) {
         cudaStream_t cs = (k & 1) ? h->stream2 : h->stream;
         const int f0 = (int)((long long)n * k / nchunks), f1 = (int)((long long)n * (k + 1) / nchunks);
@@ -675,7 +680,7 @@ int orbx_extract_batch(orbx_handle* h, int n, const uint8_t* const* imgs, int wi
                 // pinned buffer (a ring of camera frames) go as ONE copy
                 int j = i + 1;
                 while (j < f1 && imgs[j] == imgs[j - 1] + fbytes && (strides ? strides[j] : (size_t)width) == stride) ++j;
-                CK(h, cudaMemcpyAsync(h->d_input + i * fbytes, imgs[i], (size_t)(j - i) * fbytes, cudaMemcpyHostToDevice, h->h2d_stream));
+                CK(h, cudaMemcpyAsync(h->d_input + i * fbytes, imgs[i], (size_t)(j - i) * fbytes, cudaMemcpyHostToDevice, h2d));
                 i = j;
                 continue;
             }
@@ -684,31 +689,37 @@ int orbx_extract_batch(orbx_handle* h, int n, const uint8_t* const* imgs, int wi
             if (!pinned) {     // pageable caller memory: stage through the handle's pinned buffer
                 uint8_t* stg = h->h_input + i * fbytes;
                 for (int y = 0; y < height; ++y) memcpy(stg + (size_t)y * pitch, imgs[i] + (size_t)y * stride, (size_t)width);
-                CK(h, cudaMemcpyAsync(h->d_input + i * fbytes, stg, fbytes, cudaMemcpyHostToDevice, h->h2d_stream));
+                CK(h, cudaMemcpyAsync(h->d_input + i * fbytes, stg, fbytes, cudaMemcpyHostToDevice, h2d));
             } else {
                 CK(h, cudaMemcpy2DAsync(h->d_input + i * fbytes, pitch, src, spitch, (size_t)width, (size_t)height,
-                                        cudaMemcpyHostToDevice, h->h2d_stream));
+                                        cudaMemcpyHostToDevice, h2d));
             }
             ++i;
         }
-        CK(h, cudaEventRecord(h->ev_h2d[k], h->h2d_stream));
-        CK(h, cudaStreamWaitEvent(cs, h->ev_h2d[k], 0));
+        if (!one) {
+            CK(h, cudaEventRecord(h->ev_h2d[k], h2d));
+            CK(h, cudaStreamWaitEvent(cs, h->ev_h2d[k], 0));
+        }
         rc = enqueue_frames(h, f0, f1 - f0, h->d_input + f0 * fbytes, pitch, fbytes, k, cs);
         if (rc != ORBX_OK) return rc;
-        CK(h, cudaEventRecord(h->ev_done[k], cs));
-        CK(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_done[k], 0));
+        if (!one) {
+            CK(h, cudaEventRecord(h->ev_done[k], cs));
+            CK(h, cudaStreamWaitEvent(d2h, h->ev_done[k], 0));
+        }
         CK(h, cudaMemcpyAsync(h->h_out_kp + f0 * kpf * 7, h->d_out_kp + f0 * kpf * 7, (f1 - f0) * kpf * sizeof(orbx_keypoint),
-                              cudaMemcpyDeviceToHost, h->d2h_stream));
+                              cudaMemcpyDeviceToHost, d2h));
         CK(h, cudaMemcpyAsync(h->h_out_desc + f0 * kpf * 32, h->d_out_desc + f0 * kpf * 32, (f1 - f0) * kpf * 32,
-                              cudaMemcpyDeviceToHost, h->d2h_stream));
+                              cudaMemcpyDeviceToHost, d2h));
         if (h->cfg.download_pyramid)
             CK(h, cudaMemcpyAsync(h->h_pyr + (size_t)f0 * P.slab_bytes, h->d_pyr + (size_t)f0 * P.slab_bytes,
-                                  (size_t)(f1 - f0) * P.slab_bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
+                                  (size_t)(f1 - f0) * P.slab_bytes, cudaMemcpyDeviceToHost, d2h));
     }
-    CK(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int) * h->counters_count(), cudaMemcpyDeviceToHost, h->d2h_stream));
-    CK(h, cudaStreamSynchronize(h->d2h_stream));
-    CK(h, cudaStreamSynchronize(h->stream));
-    CK(h, cudaStreamSynchronize(h->stream2));
+    CK(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int) * h->counters_count(), cudaMemcpyDeviceToHost, d2h));
+    CK(h, cudaStreamSynchronize(d2h));
+    if (!one) {
+        CK(h, cudaStreamSynchronize(h->stream));
+        CK(h, cudaStreamSynchronize(h->stream2));
+    }
     h->last_n = n;
     return finish_results(h, n, results);
 }
