@@ -222,3 +222,45 @@ def test_full_size_properties():
         assert np.all((k1["angle"] >= 0) & (k1["angle"] < 360)) and np.all(k1["response"] >= 6)
         assert len(np.unique(np.stack([k1["x"], k1["y"], k1["octave"].astype(np.float32)], 1), axis=0)) == len(k1)
         gx.close()
+
+
+@pytest.mark.parametrize("w,h,pad", [(1241, 376, 0), (1241, 376, 7), (752, 480, 0), (640, 480, 32)])
+def test_pinned_inputs_all_copy_paths(w, h, pad):
+    """Host frames in pinned memory take the direct 1-D H2D path (one merged copy when contiguous), with the
+    caller's own row stride -- including strides that are not a multiple of 16 (unaligned level-0 copy)."""
+    import torch
+    n, stride = 5, w + pad
+    host = torch.zeros((n, h, stride), dtype=torch.uint8).pin_memory()
+    imgs = [fr.cluttered_scene(w, h, 300 + i) for i in range(n)]
+    hnp = host.numpy()
+    hnp[:] = 255                                     # padding bytes must never leak into the result
+    for i, im in enumerate(imgs):
+        hnp[i, :, :w] = im
+    gx = ORBextractor(800, 1.2, 8, 20, 7, max_batch=n)
+    out = gx.extract_batch([hnp[i, :, :w] for i in range(n)])                 # contiguous frames: merged copy
+    out_rev = gx.extract_batch([hnp[i, :, :w] for i in reversed(range(n))])   # non-contiguous order: one copy per frame
+    for i, im in enumerate(imgs):
+        ro = orb_oracle.ORBextractor(800, 1.2, 8, 20, 7)(im)
+        assert_same(out[i][0], out[i][1], ro)
+        assert_same(out_rev[n - 1 - i][0], out_rev[n - 1 - i][1], ro)
+    assert np.array_equal(gx.pyramid(0)[0], orb_oracle.ORBextractor(800, 1.2, 8, 20, 7)(imgs[n - 1]).pyramid[0])
+    gx.close()
+
+
+def test_large_batch_through_both_paths_matches_single():
+    """32 frames: orbx_extract_batch (4 sub-batches, 2 kernel streams) and orbx_extract_device (2 half-batches)
+    give exactly what 32 single-frame calls give."""
+    import torch
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["mono_tum"]
+    imgs = [fr.cluttered_scene(w, h, 500 + i) for i in range(32)]
+    g1 = ORBextractor(nf, sf, nl, it, mt)
+    single = [g1(im) for im in imgs]
+    gb = ORBextractor(nf, sf, nl, it, mt, max_batch=32, download_pyramid=False)
+    batch = gb.extract_batch(imgs)
+    dev = torch.from_numpy(np.stack(imgs)).cuda()
+    gb.extract_device(dev.data_ptr(), 32, w, h, w, w * h)
+    devres = gb.fetch_results(32)
+    for i in range(32):
+        for k, d in (batch[i], devres[i]):
+            assert np.array_equal(k.view(np.uint8), single[i][0].view(np.uint8)) and np.array_equal(d, single[i][1])
+    g1.close(); gb.close()
