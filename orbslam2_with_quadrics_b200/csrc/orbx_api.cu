@@ -30,9 +30,10 @@ struct orbx_handle {
     orbx_config cfg;
     int num_sms;
     cudaStream_t stream;          // kernels
-    cudaStream_t stream2;         // second kernel stream: alternate sub-batches so their latency-bound tails overlap
-    cudaStream_t aux[2];          // side streams of stream / stream2: the blur only needs the pyramid, so it runs beside FAST/octree
-    cudaEvent_t ev_pyr[2], ev_blur[2], ev_low[2], ev_fast_low[2];
+    cudaStream_t ks[4];           // kernel streams (ks[0] == stream): sub-batches alternate so latency-bound tails overlap
+    cudaStream_t aux[4];          // side stream of each kernel stream: the blur only needs the pyramid, so it runs beside FAST/octree
+    cudaEvent_t ev_pyr[4], ev_blur[4], ev_low[4], ev_fast_low[4], ev_join[4];
+    int nks;                      // kernel streams in use (ORBX_KERNEL_STREAMS, default 2)
     cudaStream_t h2d_stream, d2h_stream;
     cudaEvent_t ev_h2d[8], ev_done[8], ev_clear;
     std::string last_error;
@@ -402,7 +403,8 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
     // Otherwise the dependency graph is exploited with a side stream:
     //   st : pyramid L0..1 | pyramid L2..  (small, latency-bound levels)  | FAST L2.. | octree | orient | descriptors
     //   aux:               | FAST L0..1 (needs only those levels)         | blur (needs the pyramid only)
-    const int si = st == h->stream2 ? 1 : 0;
+    int si = 0;
+    for (int i = 1; i < 4; ++i) if (st == h->ks[i]) si = i;
     const bool overlap = ev == 0;
     const int ls = (overlap && L > 2) ? 2 : 0;                       // levels [0, ls) get their own FAST launch
     cudaStream_t ax = h->aux[si];
@@ -460,19 +462,19 @@ int enqueue_pipeline(orbx_handle* h, int n, const uint8_t* d_imgs, size_t pitch,
     if (nchunks < 1) nchunks = 1;
     if (nchunks > kMaxChunks) nchunks = kMaxChunks;
     if (nchunks > n) nchunks = n;
-    if (nchunks > 1) {
+    const int ns = nchunks < h->nks ? nchunks : h->nks;
+    if (ns > 1) {
         CK(h, cudaEventRecord(h->ev_clear, h->stream));
-        CK(h, cudaStreamWaitEvent(h->stream2, h->ev_clear, 0));
+        for (int i = 1; i < ns; ++i) CK(h, cudaStreamWaitEvent(h->ks[i], h->ev_clear, 0));
     }
     for (int k = 0; k < nchunks; ++k) {
         const int f0 = (int)((long long)n * k / nchunks), f1 = (int)((long long)n * (k + 1) / nchunks);
-        cudaStream_t cs = (k & 1) ? h->stream2 : h->stream;
-        int rc = enqueue_frames(h, f0, f1 - f0, d_imgs + (size_t)f0 * frame_stride, pitch, frame_stride, k, cs);
+        int rc = enqueue_frames(h, f0, f1 - f0, d_imgs + (size_t)f0 * frame_stride, pitch, frame_stride, k, h->ks[k % ns]);
         if (rc != ORBX_OK) return rc;
     }
-    if (nchunks > 1) {      // join: everything recorded on the handle's stream after this call covers both halves
-        CK(h, cudaEventRecord(h->ev_done[0], h->stream2));
-        CK(h, cudaStreamWaitEvent(h->stream, h->ev_done[0], 0));
+    for (int i = 1; i < ns; ++i) {      // join: everything recorded on the handle's stream after this call covers all sub-batches
+        CK(h, cudaEventRecord(h->ev_join[i], h->ks[i]));
+        CK(h, cudaStreamWaitEvent(h->stream, h->ev_join[i], 0));
     }
     h->last_n = n;
     h->pyramid_valid = false;
@@ -568,10 +570,21 @@ int orbx_create(const orbx_config* cfg, orbx_handle** out) {
     h->stream = 0;
     cudaError_t e = cudaSetDevice(cfg->device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    h->h2d_stream = h->d2h_stream = h->stream2 = 0;
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
-    for (int i = 0; i < 2; ++i) {
+    h->h2d_stream = h->d2h_stream = 0;
+    h->ks[0] = h->stream;
+    for (int i = 1; i < 4; ++i) {
+        h->ks[i] = 0;
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->ks[i], cudaStreamNonBlocking);
+    }
+    {
+        const char* e_ns = getenv("ORBX_KERNEL_STREAMS");
+        h->nks = e_ns ? atoi(e_ns) : 2;
+        if (h->nks < 1) h->nks = 1;
+        if (h->nks > 4) h->nks = 4;
+    }
+    for (int i = 0; i < 4; ++i) {
         h->aux[i] = 0;
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pyr[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_blur[i], cudaEventDisableTiming);
@@ -599,9 +612,8 @@ int orbx_destroy(orbx_handle* h) {
     if (!h) return ORBX_ERR_BAD_ARGS;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
-    cudaStreamSynchronize(h->stream2);
-    cudaStreamSynchronize(h->aux[0]);
-    cudaStreamSynchronize(h->aux[1]);
+    for (int i = 1; i < 4; ++i) cudaStreamSynchronize(h->ks[i]);
+    for (int i = 0; i < 4; ++i) cudaStreamSynchronize(h->aux[i]);
     cudaStreamSynchronize(h->h2d_stream);
     cudaStreamSynchronize(h->d2h_stream);
     free_geometry(h);
@@ -610,8 +622,11 @@ int orbx_destroy(orbx_handle* h) {
             for (int s = 0; s <= ST_COUNT; ++s) cudaEventDestroy(h->ev[i][s]);
     for (int i = 0; i < kMaxChunks; ++i) { cudaEventDestroy(h->ev_h2d[i]); cudaEventDestroy(h->ev_done[i]); }
     cudaEventDestroy(h->ev_clear);
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_pyr[i]); cudaEventDestroy(h->ev_blur[i]); cudaEventDestroy(h->ev_low[i]); cudaEventDestroy(h->ev_fast_low[i]); cudaStreamDestroy(h->aux[i]); }
-    cudaStreamDestroy(h->stream2);
+    for (int i = 0; i < 4; ++i) {
+        cudaEventDestroy(h->ev_pyr[i]); cudaEventDestroy(h->ev_blur[i]); cudaEventDestroy(h->ev_low[i]);
+        cudaEventDestroy(h->ev_fast_low[i]); cudaEventDestroy(h->ev_join[i]); cudaStreamDestroy(h->aux[i]);
+    }
+    for (int i = 1; i < 4; ++i) cudaStreamDestroy(h->ks[i]);
     cudaStreamDestroy(h->h2d_stream);
     cudaStreamDestroy(h->d2h_stream);
     cudaStreamDestroy(h->stream);
@@ -663,12 +678,13 @@ int orbx_extract_batch(orbx_handle* h, int n, const uint8_t* const* imgs, int wi
     // a single sub-batch (latency mode) stays on one stream: no cross-stream events on the critical path
     const bool one = nchunks == 1;
     cudaStream_t h2d = one ? h->stream : h->h2d_stream, d2h = one ? h->stream : h->d2h_stream;
+    const int ns = nchunks < h->nks ? nchunks : h->nks;
     if (!one) {
         CK(h, cudaEventRecord(h->ev_clear, h->stream));
-        CK(h, cudaStreamWaitEvent(h->stream2, h->ev_clear, 0));
+        for (int i = 1; i < ns; ++i) CK(h, cudaStreamWaitEvent(h->ks[i], h->ev_clear, 0));
     }
     for (int k = 0; k < nchunks; ++k) {
-        cudaStream_t cs = (k & 1) ? h->stream2 : h->stream;
+        cudaStream_t cs = h->ks[k % ns];
         const int f0 = (int)((long long)n * k / nchunks), f1 = (int)((long long)n * (k + 1) / nchunks);
         for (int i = f0; i < f1;) {
             const size_t stride = strides ? strides[i] : (size_t)width;
@@ -716,10 +732,8 @@ int orbx_extract_batch(orbx_handle* h, int n, const uint8_t* const* imgs, int wi
     }
     CK(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int) * h->counters_count(), cudaMemcpyDeviceToHost, d2h));
     CK(h, cudaStreamSynchronize(d2h));
-    if (!one) {
-        CK(h, cudaStreamSynchronize(h->stream));
-        CK(h, cudaStreamSynchronize(h->stream2));
-    }
+    if (!one)
+        for (int i = 0; i < ns; ++i) CK(h, cudaStreamSynchronize(h->ks[i]));
     h->last_n = n;
     return finish_results(h, n, results);
 }
