@@ -684,6 +684,8 @@ octree_kernel(const OrbxPlan* __restrict__ plan, int nframes, const uint32_t* __
     int* proc = reinterpret_cast<int*>(sp); sp += (size_t)CAP * 4;         // rank -> node
     int* ne_incl = reinterpret_cast<int*>(sp); sp += (size_t)CAP * 4;      // inclusive sum of non-empty children by rank
     int* surv_pos = reinterpret_cast<int*>(sp); sp += (size_t)CAP * 4;     // node -> new index if it survives
+    uint32_t* keysS = reinterpret_cast<uint32_t*>(sp); sp += (size_t)ORBX_OT_KEYCAP * 4;
+    uint16_t* knodeS = reinterpret_cast<uint16_t*>(sp); sp += (size_t)ORBX_OT_KEYCAP * 2;
 
     const size_t cbase = (size_t)frame * plan->cand_per_frame + L.cand_off;
     const uint32_t* in = cand + cbase;
@@ -699,12 +701,19 @@ octree_kernel(const OrbxPlan* __restrict__ plan, int nframes, const uint32_t* __
         const uint2 r = c < ncell ? rec[c] : make_uint2(0, 0);
         int tot;
         const int e = block_excl_scan((int)r.y, &tot, s_warp);
-        for (uint32_t i = 0; i < r.y; ++i) keys[M + e + i] = in[r.x + i];
+        for (uint32_t i = 0; i < r.y; ++i) {
+            const uint32_t v = in[r.x + i];
+            keys[M + e + i] = v;                                               // reference push order (stage dump, final pick)
+            if (M + e + (int)i < ORBX_OT_KEYCAP) keysS[M + e + i] = v;
+        }
         M += tot;
     }
     if (tid == 0) sorted_counts[frame * plan->nlevels + l] = M;
     __syncthreads();
 
+    // Keys (packed x, y, response) and their node ids are swept twice per pass.  When a level's candidates fit
+    // (<= ORBX_OT_KEYCAP) they live in shared memory for the whole kernel; otherwise the sweeps go to HBM/L2.
+    auto run = [&](const uint32_t* K, uint16_t* KN) {
     // ---- roots (:543-585)
     const int N = L.quota;
     const int nIni = L.nIni;
@@ -722,9 +731,9 @@ octree_kernel(const OrbxPlan* __restrict__ plan, int nframes, const uint32_t* __
     }
     __syncthreads();
     for (int k = tid; k < M; k += T) {
-        int r = (int)__fdiv_rn((float)ORBX_PX(keys[k]), hX);                 // (:569) truncation
+        int r = (int)__fdiv_rn((float)ORBX_PX(K[k]), hX);                 // (:569) truncation
         r = min(r, nIni - 1);
-        knode[k] = (uint16_t)r;
+        KN[k] = (uint16_t)r;
         atomicAdd(&cnt0[r], 1);
     }
     __syncthreads();
@@ -744,7 +753,7 @@ octree_kernel(const OrbxPlan* __restrict__ plan, int nframes, const uint32_t* __
     }
     __syncthreads();
     int n_nodes = s_misc[0];
-    for (int k = tid; k < M; k += T) knode[k] = (uint16_t)root_map[knode[k]];
+    for (int k = tid; k < M; k += T) KN[k] = (uint16_t)root_map[KN[k]];
     __syncthreads();
 
     Rect4* rc = rect1; Rect4* rn = rect0;
@@ -759,12 +768,12 @@ octree_kernel(const OrbxPlan* __restrict__ plan, int nframes, const uint32_t* __
         __syncthreads();
         // ---- count keys per child quadrant (DivideNode :510-526)
         for (int k = tid; k < M; k += T) {
-            const int nd = knode[k];
+            const int nd = KN[k];
             if (cntc[nd] > 1) {
                 const Rect4 r = rc[nd];
                 const int mx = r.ulx + ((r.urx - r.ulx + 1) >> 1);       // ceil(float(d)/2) (:483-484)
                 const int my = r.uly + ((r.bry - r.uly + 1) >> 1);
-                const uint32_t p = keys[k];
+                const uint32_t p = K[k];
                 const int q = (ORBX_PX(p) < mx ? 0 : 1) + (ORBX_PY(p) < my ? 0 : 2);
                 atomicAdd(&cc[nd * 4 + q], 1);
             }
@@ -783,31 +792,22 @@ octree_kernel(const OrbxPlan* __restrict__ plan, int nframes, const uint32_t* __
                 E += tot;
             }
         } else {
-            for (int i = tid; i < SORTN; i += T) {
+            // order by (key count, creation sequence) descending = (count desc, list index asc): rule B-1.  Keys are
+            // distinct, so a node's processing rank is the number of larger keys -- an all-pairs count over <= node_cap
+            // shared-memory keys (broadcast reads, two barriers) instead of a 45-barrier bitonic sort.
+            for (int i = tid; i < S0; i += T) {
                 unsigned long long key = 0;
-                if (i < S0 && cntc[i] > 1) key = ((unsigned long long)(uint32_t)cntc[i] << 32) | (uint32_t)(0xffffffffu - (uint32_t)i);
+                if (cntc[i] > 1) key = ((unsigned long long)(uint32_t)cntc[i] << 32) | (uint32_t)(0xffffffffu - (uint32_t)i);
                 skey[i] = key;
-                if (i < S0) procrank[i] = -1;
+                procrank[i] = -1;
             }
             __syncthreads();
-            for (int k2 = 2; k2 <= SORTN; k2 <<= 1) {                     // bitonic sort, descending
-                for (int j = k2 >> 1; j > 0; j >>= 1) {
-                    for (int i = tid; i < SORTN; i += T) {
-                        const int ixj = i ^ j;
-                        if (ixj > i) {
-                            const unsigned long long a = skey[i], b = skey[ixj];
-                            const bool desc = (i & k2) == 0;
-                            if (desc ? (a < b) : (a > b)) { skey[i] = b; skey[ixj] = a; }
-                        }
-                    }
-                    __syncthreads();
-                }
-            }
             int e_local = 0;
-            for (int r = tid; r < S0; r += T) {
-                const unsigned long long key = skey[r];
+            for (int i = tid; i < S0; i += T) {
+                const unsigned long long key = skey[i];
                 if (key != 0) {
-                    const int i = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffu));
+                    int r = 0;
+                    for (int j = 0; j < S0; ++j) r += skey[j] > key;
                     proc[r] = i;
                     procrank[i] = r;
                     ++e_local;
@@ -894,17 +894,17 @@ octree_kernel(const OrbxPlan* __restrict__ plan, int nframes, const uint32_t* __
         __syncthreads();
         // ---- move keys to their new nodes
         for (int k = tid; k < M; k += T) {
-            const int nd = knode[k];
+            const int nd = KN[k];
             const int pr = procrank[nd];
             if (pr >= 0 && pr < P) {
                 const Rect4 r = rc[nd];
                 const int mx = r.ulx + ((r.urx - r.ulx + 1) >> 1);
                 const int my = r.uly + ((r.bry - r.uly + 1) >> 1);
-                const uint32_t p = keys[k];
+                const uint32_t p = K[k];
                 const int q = (ORBX_PX(p) < mx ? 0 : 1) + (ORBX_PY(p) < my ? 0 : 2);
-                knode[k] = (uint16_t)cp[nd * 4 + q];
+                KN[k] = (uint16_t)cp[nd * 4 + q];
             } else {
-                knode[k] = (uint16_t)surv_pos[nd];
+                KN[k] = (uint16_t)surv_pos[nd];
             }
         }
         const int nToExpand = s_misc[1];
@@ -925,20 +925,23 @@ octree_kernel(const OrbxPlan* __restrict__ plan, int nframes, const uint32_t* __
     for (int i = tid; i < n_nodes; i += T) best[i] = 0;
     __syncthreads();
     for (int k = tid; k < M; k += T)
-        atomicMax(reinterpret_cast<unsigned int*>(&best[knode[k]]),
-                  ((uint32_t)ORBX_PR(keys[k]) << 24) | (0xffffffu - (uint32_t)k));
+        atomicMax(reinterpret_cast<unsigned int*>(&best[KN[k]]),
+                  ((uint32_t)ORBX_PR(K[k]) << 24) | (0xffffffu - (uint32_t)k));
     __syncthreads();
     const int out_n = min(n_nodes, L.kept_cap);
     uint32_t* out = kept + (size_t)frame * plan->kept_per_frame + L.kept_off;
     for (int i = tid; i < out_n; i += T) {
         const uint32_t k = 0xffffffu - ((uint32_t)best[i] & 0xffffffu);
-        const uint32_t p = keys[k];
+        const uint32_t p = K[k];
         out[i] = ORBX_PACK(ORBX_PX(p) + ORBX_BOX, ORBX_PY(p) + ORBX_BOX, ORBX_PR(p));      // (:843-844)
     }
     if (tid == 0) {
         kept_counts[frame * plan->nlevels + l] = out_n;
         if (n_nodes > L.kept_cap) atomicOr(&status[frame], ORBX_DEV_NODE_OVERFLOW);
     }
+    };
+    if (M <= ORBX_OT_KEYCAP) run(keysS, knodeS);
+    else run(keys, knode);
 }
 
 // =====================================================================================
@@ -1288,7 +1291,7 @@ cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* 
 size_t octree_smem_bytes(const OrbxPlan& hp) {
     int sortn = 1;
     while (sortn < hp.node_cap) sortn <<= 1;
-    return (size_t)sortn * 8 + (size_t)hp.node_cap * (8 + 8 + 4 + 4 + 16 + 16 + 4 + 4 + 4 + 4);
+    return (size_t)sortn * 8 + (size_t)hp.node_cap * (8 + 8 + 4 + 4 + 16 + 16 + 4 + 4 + 4 + 4) + (size_t)ORBX_OT_KEYCAP * 6;
 }
 
 cudaError_t launch_octree(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, const uint32_t* cand,
