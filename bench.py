@@ -93,6 +93,41 @@ def run_reference_cpu(name, frames_per_step, steps, warmup, cores):
             "elapsed_s": el}
 
 
+def opencv_primitive_times(name, reps=3):
+    """Cross-check for the CPU baseline: single-thread time of the real OpenCV (cv2, SIMD) primitives
+    the reference calls -- pyramid, FAST on whole levels (a lower bound on the per-cell calls) and the blur -- on
+    one frame of the workload.  The reference's own code (cell loop, quadtree, orientation, descriptors) comes on top."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    cv2.setNumThreads(1)
+    w, h, nf, sf, nl, it, mt, nimg = fr.CONFIGS[name]
+    img = fr.cluttered_scene(w, h, fr.stream_seed(0, 0))
+    sizes = geo.level_sizes(w, h, sf, nl)
+    det = cv2.FastFeatureDetector_create(threshold=it, nonmaxSuppression=True, type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    best = {"pyramid": 1e9, "fast_whole_levels": 1e9, "blur": 1e9}
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        lv = [cv2.copyMakeBorder(img, 19, 19, 19, 19, cv2.BORDER_REFLECT_101)]
+        for lw, lh in sizes[1:]:
+            r = cv2.resize(lv[-1][19:-19, 19:-19], (lw, lh), interpolation=cv2.INTER_LINEAR)
+            lv.append(cv2.copyMakeBorder(r, 19, 19, 19, 19, cv2.BORDER_REFLECT_101))
+        t1 = time.perf_counter()
+        for p in lv:
+            det.detect(np.ascontiguousarray(p[19:-19, 19:-19]), None)
+        t2 = time.perf_counter()
+        for p in lv:
+            cv2.GaussianBlur(np.ascontiguousarray(p[19:-19, 19:-19]), (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+        t3 = time.perf_counter()
+        best["pyramid"] = min(best["pyramid"], (t1 - t0) * 1e3)
+        best["fast_whole_levels"] = min(best["fast_whole_levels"], (t2 - t1) * 1e3)
+        best["blur"] = min(best["blur"], (t3 - t2) * 1e3)
+    best["sum"] = best["pyramid"] + best["fast_whole_levels"] + best["blur"]
+    best["note"] = "cv2 %s, 1 thread, ms per image, best of %d" % (cv2.__version__, reps)
+    return best
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -334,6 +369,7 @@ def own_arm(args):
         cores = host_cores()
         per = max(8, cores)
         cpu = run_reference_cpu(name, per, 2, 1, cores)
+        cpu["opencv_primitives_ms"] = opencv_primitive_times(name)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
