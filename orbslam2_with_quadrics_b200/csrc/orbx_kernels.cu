@@ -972,7 +972,7 @@ __device__ __forceinline__ int level_of_slot(const OrbxPlan* plan, int s) {
     return l;
 }
 
-__global__ void __launch_bounds__(256) orient_kernel(const OrbxPlan* __restrict__ plan, int nframes,
+__global__ void __launch_bounds__(256, 8) orient_kernel(const OrbxPlan* __restrict__ plan, int nframes,
                                                      const uint8_t* __restrict__ pyr,
                                                      const uint32_t* __restrict__ kept,
                                                      const int* __restrict__ kept_counts,
@@ -997,14 +997,21 @@ __global__ void __launch_bounds__(256) orient_kernel(const OrbxPlan* __restrict_
         const int pitch = L.pitch;
         int m10 = 0, m01 = 0;
         if (lane < 31) {
-            int vals[31];
-#pragma unroll
-            for (int v = -15; v <= 15; ++v) vals[v + 15] = (au <= UMAX[v < 0 ? -v : v]) ? (int)center[v * pitch] : 0;
+            // 31 rows in four groups of 8 independent loads (enough memory-level parallelism, few live registers)
             int colsum = 0;
 #pragma unroll
-            for (int v = -15; v <= 15; ++v) {
-                colsum += vals[v + 15];
-                m01 += v * vals[v + 15];
+            for (int v0 = -15; v0 <= 15; v0 += 8) {
+                int vals[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int v = v0 + j;
+                    vals[j] = (v <= 15 && au <= UMAX[v < 0 ? -v : v]) ? (int)center[v * pitch] : 0;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    colsum += vals[j];
+                    m01 += (v0 + j) * vals[j];
+                }
             }
             m10 = u * colsum;
         }
