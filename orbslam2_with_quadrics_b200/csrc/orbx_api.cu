@@ -17,8 +17,8 @@
 
 namespace {
 
-enum { ST_PYRAMID = 0, ST_FAST, ST_OCTREE, ST_ORIENT, ST_BLUR, ST_DESC, ST_COUNT };
-const char* kStageNames[ST_COUNT] = {"pyramid", "fast_cells", "octree", "orient", "blur", "descriptor"};
+enum { ST_PYRAMID = 0, ST_FAST, ST_OCTREE, ST_DESCRIBE, ST_COUNT };
+const char* kStageNames[ST_COUNT] = {"pyramid", "fast_cells", "octree", "describe"};
 const int kTimingRing = 64;
 const int kMaxChunks = 8;         // sub-batches of one extract_batch call that overlap H2D, kernels and D2H
 
@@ -31,8 +31,8 @@ struct orbx_handle {
     int num_sms;
     cudaStream_t stream;          // kernels
     cudaStream_t ks[4];           // kernel streams (ks[0] == stream): sub-batches alternate so latency-bound tails overlap
-    cudaStream_t aux[4];          // side stream of each kernel stream: the blur only needs the pyramid, so it runs beside FAST/octree
-    cudaEvent_t ev_pyr[4], ev_blur[4], ev_low[4], ev_fast_low[4], ev_join[4];
+    cudaStream_t aux[4];          // side stream of each kernel stream: FAST of levels 0-1 runs beside the pyramid tail
+    cudaEvent_t ev_low[4], ev_fast_low[4], ev_join[4];
     int nks;                      // kernel streams in use (ORBX_KERNEL_STREAMS, default 2)
     cudaStream_t h2d_stream, d2h_stream;
     cudaEvent_t ev_h2d[8], ev_done[8], ev_clear;
@@ -51,14 +51,15 @@ struct orbx_handle {
     OrbxPlan* d_plan;
     OrbxTap* d_taps;
     int in_pitch;                // capacity of a staged input row (bytes)
-    uint8_t *d_input, *d_pyr, *d_blur;
+    uint8_t *d_input, *d_pyr;
+    uint8_t* d_blur;             // ONE frame's blurred slab, allocated on the first ORBX_STAGE_BLURRED dump (diagnostics only)
     uint32_t *d_cand, *d_cand_sorted, *d_kept;
     uint16_t* d_key_node;
     uint2* d_cell_rec;
     int* d_counters;             // [level_counts B*L][sorted_counts B*L][kept_counts B*L][status B][work counter]
-    std::vector<unsigned char> fast_maps;   // per-level TMA descriptors of the pyramid slabs
+    std::vector<unsigned char> fast_maps;   // per-level TMA descriptors of the pyramid slabs (box = strip of FAST windows)
+    std::vector<unsigned char> desc_maps;   // the same planes with box = one keypoint's raw window
     float* d_angles;
-    float2* d_rot;               // (cos, sin) of each kept keypoint's angle
     float* d_out_kp;
     uint8_t* d_out_desc;
     // pinned host mirrors
@@ -299,13 +300,13 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
 void free_geometry(orbx_handle* h) {
     cudaFree(h->d_plan); cudaFree(h->d_taps); cudaFree(h->d_input); cudaFree(h->d_pyr); cudaFree(h->d_blur);
     cudaFree(h->d_cand); cudaFree(h->d_cand_sorted); cudaFree(h->d_kept); cudaFree(h->d_key_node);
-    cudaFree(h->d_cell_rec); cudaFree(h->d_counters); cudaFree(h->d_angles); cudaFree(h->d_rot); cudaFree(h->d_out_kp);
+    cudaFree(h->d_cell_rec); cudaFree(h->d_counters); cudaFree(h->d_angles); cudaFree(h->d_out_kp);
     cudaFree(h->d_out_desc);
     cudaFreeHost(h->h_counters); cudaFreeHost(h->h_out_kp); cudaFreeHost(h->h_out_desc); cudaFreeHost(h->h_pyr);
     cudaFreeHost(h->h_input);
     h->d_plan = 0; h->d_taps = 0; h->d_input = h->d_pyr = h->d_blur = 0;
     h->d_cand = h->d_cand_sorted = h->d_kept = 0; h->d_key_node = 0; h->d_cell_rec = 0; h->d_counters = 0;
-    h->d_angles = 0; h->d_rot = 0; h->d_out_kp = 0; h->d_out_desc = 0;
+    h->d_angles = 0; h->d_out_kp = 0; h->d_out_desc = 0;
     h->h_counters = 0; h->h_out_kp = 0; h->h_out_desc = 0; h->h_pyr = 0; h->h_input = 0;
     h->have_plan = false;
     h->pyramid_valid = false;
@@ -328,7 +329,6 @@ int ensure_geometry(orbx_handle* h, int w, int hgt) {
     CK(h, cudaMalloc(&h->d_taps, sizeof(OrbxTap) * (h->taps.size() + 1)));
     CK(h, cudaMalloc(&h->d_input, B * hgt * h->in_pitch));
     CK(h, cudaMalloc(&h->d_pyr, B * P.slab_bytes));
-    CK(h, cudaMalloc(&h->d_blur, B * P.slab_bytes));
     CK(h, cudaMalloc(&h->d_cand, B * P.cand_per_frame * 4));
     CK(h, cudaMalloc(&h->d_cand_sorted, B * P.cand_per_frame * 4));
     CK(h, cudaMalloc(&h->d_key_node, B * P.cand_per_frame * 2));
@@ -336,7 +336,6 @@ int ensure_geometry(orbx_handle* h, int w, int hgt) {
     CK(h, cudaMalloc(&h->d_counters, sizeof(int) * h->counters_count()));
     CK(h, cudaMalloc(&h->d_kept, B * P.kept_per_frame * 4));
     CK(h, cudaMalloc(&h->d_angles, B * P.kept_per_frame * 4));
-    CK(h, cudaMalloc(&h->d_rot, B * P.kept_per_frame * sizeof(float2)));
     CK(h, cudaMalloc(&h->d_out_kp, B * P.kept_per_frame * sizeof(orbx_keypoint)));
     CK(h, cudaMalloc(&h->d_out_desc, B * P.kept_per_frame * 32));
     CK(h, cudaMallocHost(&h->h_counters, sizeof(int) * h->counters_count()));
@@ -345,15 +344,15 @@ int ensure_geometry(orbx_handle* h, int w, int hgt) {
     CK(h, cudaMallocHost(&h->h_input, B * hgt * h->in_pitch));
     if (h->cfg.download_pyramid) CK(h, cudaMallocHost(&h->h_pyr, B * P.slab_bytes));
     h->fast_maps.resize(orbx::fast_maps_bytes());
-    if (orbx::build_fast_maps(h->plan, h->d_pyr, h->cfg.max_batch, h->fast_maps.data()) != 0) {
+    h->desc_maps.resize(orbx::fast_maps_bytes());
+    if (orbx::build_fast_maps(h->plan, h->d_pyr, h->cfg.max_batch, h->fast_maps.data()) != 0 ||
+        orbx::build_describe_maps(h->plan, h->d_pyr, h->cfg.max_batch, h->desc_maps.data()) != 0) {
         h->last_error = "cuTensorMapEncodeTiled failed";
         return ORBX_ERR_CUDA;
     }
     CK(h, cudaMemcpyAsync(h->d_plan, &h->plan, sizeof(OrbxPlan), cudaMemcpyHostToDevice, h->stream));
     if (!h->taps.empty())
         CK(h, cudaMemcpyAsync(h->d_taps, h->taps.data(), sizeof(OrbxTap) * h->taps.size(), cudaMemcpyHostToDevice, h->stream));
-    // border bytes of the blurred planes are never written by blur_kernel; keep them defined
-    CK(h, cudaMemsetAsync(h->d_blur, 0, B * P.slab_bytes, h->stream));
     CK(h, cudaMemsetAsync(h->d_pyr, 0, B * P.slab_bytes, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     h->have_plan = true;
@@ -385,14 +384,12 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
         ev = h->ev[h->ev_head];
     }
     uint8_t* pyr = h->d_pyr + (size_t)f0 * P.slab_bytes;
-    uint8_t* blur = h->d_blur + (size_t)f0 * P.slab_bytes;
     uint32_t* cand = h->d_cand + (size_t)f0 * P.cand_per_frame;
     uint32_t* cand_sorted = h->d_cand_sorted + (size_t)f0 * P.cand_per_frame;
     uint16_t* key_node = h->d_key_node + (size_t)f0 * P.cand_per_frame;
     uint2* cell_rec = h->d_cell_rec + (size_t)f0 * P.cells_per_frame;
     uint32_t* kept = h->d_kept + (size_t)f0 * P.kept_per_frame;
     float* angles = h->d_angles + (size_t)f0 * P.kept_per_frame;
-    float2* rot = h->d_rot + (size_t)f0 * P.kept_per_frame;
     float* out_kp = h->d_out_kp + (size_t)f0 * P.kept_per_frame * 7;
     uint8_t* out_desc = h->d_out_desc + (size_t)f0 * P.kept_per_frame * 32;
     int* level_counts = h->d_level_counts() + f0 * L;
@@ -401,8 +398,8 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
     int* status = h->d_status() + f0;
     // Two schedules.  With per-stage timing on, every kernel runs alone on `st`, so its duration is its own.
     // Otherwise the dependency graph is exploited with a side stream:
-    //   st : pyramid L0..1 | pyramid L2..  (small, latency-bound levels)  | FAST L2.. | octree | orient | descriptors
-    //   aux:               | FAST L0..1 (needs only those levels)         | blur (needs the pyramid only)
+    //   st : pyramid L0..1 | pyramid L2..  (small, latency-bound levels)  | FAST L2.. | octree | describe
+    //   aux:               | FAST L0..1 (needs only those levels)         |
     int si = 0;
     for (int i = 1; i < 4; ++i) if (st == h->ks[i]) si = i;
     const bool overlap = ev == 0;
@@ -420,12 +417,6 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
             CK(h, cudaEventRecord(h->ev_fast_low[si], ax));
         }
     }
-    if (overlap) {
-        CK(h, cudaEventRecord(h->ev_pyr[si], st));
-        CK(h, cudaStreamWaitEvent(ax, h->ev_pyr[si], 0));
-        orbx::launch_blur(h->d_plan, P, n, h->num_sms, pyr, blur, ax);
-        CK(h, cudaEventRecord(h->ev_blur[si], ax));
-    }
     if (ev) CK(h, cudaEventRecord(ev[ST_FAST], st));
     if (ls) CK(h, cudaStreamWaitEvent(st, h->ev_fast_low[si], 0));
     CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), f0, n, ls, L, h->num_sms, cand, cell_rec, level_counts,
@@ -433,13 +424,9 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
     if (ev) CK(h, cudaEventRecord(ev[ST_OCTREE], st));
     CK(h, orbx::launch_octree(h->d_plan, P, n, cand, cell_rec, cand_sorted, key_node, sorted_counts, kept, kept_counts,
                               status, st));
-    if (ev) CK(h, cudaEventRecord(ev[ST_ORIENT], st));
-    orbx::launch_orient(h->d_plan, P, n, h->num_sms, pyr, kept, kept_counts, angles, rot, st);
-    if (ev) CK(h, cudaEventRecord(ev[ST_BLUR], st));
-    if (overlap) CK(h, cudaStreamWaitEvent(st, h->ev_blur[si], 0));
-    else orbx::launch_blur(h->d_plan, P, n, h->num_sms, pyr, blur, st);
-    if (ev) CK(h, cudaEventRecord(ev[ST_DESC], st));
-    orbx::launch_desc(h->d_plan, P, n, h->num_sms, blur, kept, kept_counts, angles, rot, out_kp, out_desc, st);
+    if (ev) CK(h, cudaEventRecord(ev[ST_DESCRIBE], st));
+    CK(h, orbx::launch_describe(h->d_plan, P, h->desc_maps.data(), f0, n, h->num_sms, kept, kept_counts, angles, out_kp, out_desc,
+                                st));
     if (ev) {
         CK(h, cudaEventRecord(ev[ST_COUNT], st));
         h->ev_head = (h->ev_head + 1) % kTimingRing;
@@ -447,7 +434,7 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
         h->stage_launches[ST_PYRAMID] += L;
         for (int s = ST_FAST; s < ST_COUNT; ++s) h->stage_launches[s] += 1;
     }
-    h->launches += L + 5 + (ls ? 1 : 0);
+    h->launches += L + 3 + (ls ? 1 : 0);
     CK(h, cudaGetLastError());
     return ORBX_OK;
 }
@@ -561,7 +548,7 @@ int orbx_create(const orbx_config* cfg, orbx_handle** out) {
     h->have_plan = false;
     h->d_plan = 0; h->d_taps = 0; h->d_input = h->d_pyr = h->d_blur = 0;
     h->d_cand = h->d_cand_sorted = h->d_kept = 0; h->d_key_node = 0; h->d_cell_rec = 0; h->d_counters = 0;
-    h->d_angles = 0; h->d_rot = 0; h->d_out_kp = 0; h->d_out_desc = 0;
+    h->d_angles = 0; h->d_out_kp = 0; h->d_out_desc = 0;
     h->h_counters = 0; h->h_out_kp = 0; h->h_out_desc = 0; h->h_pyr = 0; h->h_input = 0;
     h->last_n = 0; h->pyramid_valid = false;
     h->timing = false; h->ev_created = false; h->ev_head = 0; h->ev_pending = 0;
@@ -586,8 +573,6 @@ int orbx_create(const orbx_config* cfg, orbx_handle** out) {
         h->aux[i] = 0;
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pyr[i], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_blur[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_low[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fast_low[i], cudaEventDisableTiming);
     }
@@ -623,7 +608,7 @@ int orbx_destroy(orbx_handle* h) {
     for (int i = 0; i < kMaxChunks; ++i) { cudaEventDestroy(h->ev_h2d[i]); cudaEventDestroy(h->ev_done[i]); }
     cudaEventDestroy(h->ev_clear);
     for (int i = 0; i < 4; ++i) {
-        cudaEventDestroy(h->ev_pyr[i]); cudaEventDestroy(h->ev_blur[i]); cudaEventDestroy(h->ev_low[i]);
+        cudaEventDestroy(h->ev_low[i]);
         cudaEventDestroy(h->ev_fast_low[i]); cudaEventDestroy(h->ev_join[i]); cudaStreamDestroy(h->aux[i]);
     }
     for (int i = 1; i < 4; ++i) cudaStreamDestroy(h->ks[i]);
@@ -813,8 +798,17 @@ int orbx_stage_dump(orbx_handle* h, int frame, int level, int stage, void* out, 
         }
         case ORBX_STAGE_BLURRED: {
             *bytes = (size_t)L.w * L.h;
-            if (out && cap >= *bytes)
-                CK(h, cudaMemcpy2D(out, L.w, h->d_blur + (size_t)frame * P.slab_bytes + L.plane_off + (size_t)ORBX_EDGE * L.pitch + ORBX_XO, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+            if (out && cap >= *bytes) {
+                // Diagnostics only: the product path blurs just the keypoint patches (describe_kernel); the whole-level
+                // blur of the reference (:1085-1086) is produced here on demand with the same arithmetic.
+                if (!h->d_blur) {
+                    CK(h, cudaMalloc(&h->d_blur, P.slab_bytes));
+                    CK(h, cudaMemsetAsync(h->d_blur, 0, P.slab_bytes, h->stream));
+                }
+                orbx::launch_blur(h->d_plan, P, 1, h->num_sms, h->d_pyr + (size_t)frame * P.slab_bytes, h->d_blur, h->stream);
+                CK(h, cudaStreamSynchronize(h->stream));
+                CK(h, cudaMemcpy2D(out, L.w, h->d_blur + L.plane_off + (size_t)ORBX_EDGE * L.pitch + ORBX_XO, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+            }
             return ORBX_OK;
         }
         case ORBX_STAGE_CANDIDATES:

@@ -945,8 +945,7 @@ octree_kernel(const OrbxPlan* __restrict__ plan, int nframes, const uint32_t* __
 }
 
 // =====================================================================================
-// IC_Angle (:77-104): intensity centroid over the umax disc of the UN-blurred level, one warp
-// per keypoint (lane = column u), then cv::fastAtan2's polynomial without FMA (App. A-4).
+// cv::fastAtan2's polynomial without FMA (App. A-4), used by describe_kernel for IC_Angle (:103).
 // =====================================================================================
 __device__ __forceinline__ float fast_atan2_deg(float y, float x, const OrbxPlan* plan) {
     const float eps = 2.2204460492503131e-16f;                    // (float)DBL_EPSILON
@@ -972,46 +971,138 @@ __device__ __forceinline__ int level_of_slot(const OrbxPlan* plan, int s) {
     return l;
 }
 
-__global__ void __launch_bounds__(256, 8) orient_kernel(const OrbxPlan* __restrict__ plan, int nframes,
-                                                     const uint8_t* __restrict__ pyr,
-                                                     const uint32_t* __restrict__ kept,
-                                                     const int* __restrict__ kept_counts,
-                                                     float* __restrict__ angles, float2* __restrict__ rot) {
+// =====================================================================================
+// describe_kernel: everything the reference does per kept keypoint, one warp per keypoint:
+//   IC_Angle (:77-104) on the UN-blurred level, GaussianBlur 7x7 sigma 2 (:1086) of the
+//   37 x 37 patch the rotated pattern can reach (|coordinate| <= 18) instead of
+//   the whole level, computeOrbDescriptor (:108-147) on that blurred patch, and the final
+//   cv::KeyPoint record (pt scaled by mvScaleFactor[level] AFTER sampling, :1095-1101).
+// A blurred pixel is a pure function of its 7 x 7 neighbourhood, so blurring only the
+// patches gives the same bytes as blurring the level; the plane's REFLECT_101 border is the
+// blur's own border mode on the border-less clone (App. B-9).
+//
+// Staging: one elected lane fetches the 64 x 43 raw window (16-byte aligned start, rows
+// ky-21 .. ky+21) with ONE TMA tile load; the next keypoint's window is requested as soon as
+// the row pass has consumed the current one, so the load overlaps column pass + sampling.
+//   phase 1  intensity centroid: lane = column u, 31 conflict-free byte reads, warp reduction,
+//            cv::fastAtan2's polynomial and float(cos/sin in double) (canonical rule B-2);
+//   phase 2  blur row pass: item = (row pair, 8 columns); byte windows by funnel shift, two
+//            IDP.4A per pixel; the 16-bit sums of two consecutive rows are packed in one word;
+//   phase 3  blur column pass: item = (column, 8 rows), four IDP.2A per pixel over the row
+//            pairs, (sum + 32768) >> 16, stored transposed (4 rows per 32-bit store);
+//   phase 4  512 rotated pattern samples (16 per lane) from the blurred patch, packed stores.
+// =====================================================================================
+#define KP_RAW_W 64
+#define KP_RAW_H 43
+#define KP_RAW_BYTES 2816                      // 64 * 43 = 2752, rounded up to 128
+#define KP_HP_COLS 40
+#define KP_HP_BYTES (24 * KP_HP_COLS * 4)     // 24 row pairs (22 written; the column pass of rows 37..39 reads 2 more)
+#define KP_BL_PITCH 40
+#define KP_BL_BYTES (KP_HP_COLS * KP_BL_PITCH)
+#define KP_WARP_BYTES (KP_RAW_BYTES + KP_HP_BYTES + KP_BL_BYTES + 64)      // 8320 = 65 * 128
+#define KP_WARPS 8
+
+struct KpItem {
+    unsigned it;               // slot index (frame * kept_per_frame + slot); >= total: none
+    int frame, l, sl;
+    uint32_t p;                // packed x | y << 12 | response << 24, level coordinates
+};
+
+__global__ void __launch_bounds__(KP_WARPS * 32, 3)
+describe_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, int frame0, int nframes,
+                const uint32_t* __restrict__ kept, const int* __restrict__ kept_counts, float* __restrict__ angles,
+                float* __restrict__ out_kp, uint8_t* __restrict__ out_desc) {
     ORBX_PDL_WAIT();
+    extern __shared__ uint8_t kp_smem_raw[];
+    __shared__ uint64_t s_bar[KP_WARPS];
     // umax (:454-469) is a function of HALF_PATCH_SIZE only; the host-computed copy in the plan is
     // checked against this table when the plan is built.
     constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* base = kp_smem_raw + ((128 - (smem_u32(kp_smem_raw) & 127)) & 127) + (size_t)warp * KP_WARP_BYTES;
+    const uint8_t* raw = base;
+    uint32_t* Hp = reinterpret_cast<uint32_t*>(base + KP_RAW_BYTES);
+    uint8_t* blT = base + KP_RAW_BYTES + KP_HP_BYTES;
+    uint64_t* bar = &s_bar[warp];
+
+    // this lane's 16 pattern points (descriptor byte `lane`, :123-144)
+    float px[16], py[16];
+    {
+        const uint4 lo = reinterpret_cast<const uint4*>(g_pattern)[lane * 2], hi = reinterpret_cast<const uint4*>(g_pattern)[lane * 2 + 1];
+        const uint32_t wds[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t wd = wds[j >> 1] >> (16 * (j & 1));
+            px[j] = (float)(int)(signed char)(wd & 0xff);
+            py[j] = (float)(int)(signed char)((wd >> 8) & 0xff);
+        }
+    }
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
     const int kpf = plan->kept_per_frame;
+    const int nl = plan->nlevels;
     const unsigned total = (unsigned)nframes * (unsigned)kpf;
-    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
-    const int u = lane - 15, au = abs(u);
-    for (unsigned it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < total; it += nwarps) {
-        const int frame = (int)(it / (unsigned)kpf);
-        const int s = (int)(it - (unsigned)frame * (unsigned)kpf);
-        const int l = level_of_slot(plan, s);
-        const OrbxLevel& L = plan->lv[l];
-        if (s - L.kept_off >= kept_counts[frame * plan->nlevels + l]) continue;
-        const uint32_t p = kept[it];
-        const uint8_t* center = level_px(pyr + (size_t)frame * plan->slab_bytes, L, ORBX_PX(p), ORBX_PY(p)) + u;
-        const int pitch = L.pitch;
+    const unsigned nwarps = gridDim.x * KP_WARPS;
+    const uint32_t K0123 = 18u | (34u << 8) | (48u << 16) | (56u << 24);
+    const uint32_t K456 = 48u | (34u << 8) | (18u << 16);
+    const uint32_t KA = K0123;                                            // even row: pairs m (lo), m+1 (hi)
+    const uint32_t KB = K456;                                             //           pairs m+2 (lo), m+3 (hi)
+    const uint32_t KC = (18u << 8) | (34u << 16) | (48u << 24);           // odd row:  pairs m (lo), m+1 (hi)
+    const uint32_t KD = 56u | (48u << 8) | (34u << 16) | (18u << 24);     //           pairs m+2 (lo), m+3 (hi)
+
+    // next occupied slot at or after `it` (slots past a level's kept count are empty)
+    auto next_item = [&](unsigned it) -> KpItem {
+        KpItem k;
+        k.frame = k.l = k.sl = 0;
+        k.p = 0;
+        for (; it < total; it += nwarps) {
+            k.frame = (int)(it / (unsigned)kpf);
+            const int s = (int)(it - (unsigned)k.frame * (unsigned)kpf);
+            k.l = level_of_slot(plan, s);
+            k.sl = s - plan->lv[k.l].kept_off;
+            if (k.sl < kept_counts[k.frame * nl + k.l]) {
+                k.p = kept[it];
+                break;
+            }
+        }
+        k.it = it;
+        return k;
+    };
+    auto issue = [&](const KpItem& k) {
+        if (lane == 0) {
+            mbar_expect_tx(bar, KP_RAW_W * KP_RAW_H);
+            tma_load_3d(base, &maps.m[k.l], bar, (ORBX_XO + ORBX_PX(k.p) - 21) & ~15, ORBX_EDGE + ORBX_PY(k.p) - 21,
+                        frame0 + k.frame);
+        }
+    };
+
+    KpItem cur = next_item(blockIdx.x * KP_WARPS + warp);
+    if (cur.it < total) issue(cur);
+    uint32_t phase = 0;
+    while (cur.it < total) {
+        const KpItem nxt = next_item(cur.it + nwarps);
+        const OrbxLevel& L = plan->lv[cur.l];
+        const int kx = ORBX_PX(cur.p), ky = ORBX_PY(cur.p);
+        const int a16 = (ORBX_XO + kx - 21) & 15;                         // byte column of patch column -21 inside the window
+        mbar_wait(bar, phase);
+        phase ^= 1;
+
+        // ---- phase 1: IC_Angle.  lane = column u = lane - 15; row v reads +-umax[|v|] (:86-101)
         int m10 = 0, m01 = 0;
         if (lane < 31) {
-            // 31 rows in four groups of 8 independent loads (enough memory-level parallelism, few live registers)
+            const int u = lane - 15, au = abs(u);
+            const uint8_t* c = raw + 21 * KP_RAW_W + a16 + 21 + u;
             int colsum = 0;
 #pragma unroll
-            for (int v0 = -15; v0 <= 15; v0 += 8) {
-                int vals[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int v = v0 + j;
-                    vals[j] = (v <= 15 && au <= UMAX[v < 0 ? -v : v]) ? (int)center[v * pitch] : 0;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    colsum += vals[j];
-                    m01 += (v0 + j) * vals[j];
-                }
+            for (int v = -15; v <= 15; ++v) {
+                const int val = au <= UMAX[v < 0 ? -v : v] ? (int)c[v * KP_RAW_W] : 0;
+                colsum += val;
+                m01 += v * val;
             }
             m10 = u * colsum;
         }
@@ -1020,15 +1111,122 @@ __global__ void __launch_bounds__(256, 8) orient_kernel(const OrbxPlan* __restri
             m10 += __shfl_xor_sync(0xffffffffu, m10, o);
             m01 += __shfl_xor_sync(0xffffffffu, m01, o);
         }
-        if (lane == 0) {
-            const float angle = fast_atan2_deg((float)m01, (float)m10, plan);
-            angles[it] = angle;
-            // rotation of computeOrbDescriptor (:111-113) under canonical rule B-2: float(cos/sin in double)
+        // every lane evaluates the same scalars (no broadcast needed)
+        const float angle = fast_atan2_deg((float)m01, (float)m10, plan);
+        float a, b;                                                       // (:111-113) under canonical rule B-2
+        {
             const float rad = __fmul_rn(angle, plan->factor_pi);
             double sn, cs;
             sincos((double)rad, &sn, &cs);
-            rot[it] = make_float2((float)cs, (float)sn);
+            a = (float)cs;
+            b = (float)sn;
         }
+
+        // ---- phase 2: blur row pass.  Column index B = first-tap byte column - 4 * wbase; blurred patch column
+        //      i = B - (a16 & 3), i in [0, 37).  Row pair rp = window rows 2rp, 2rp+1.
+        const int wbase = a16 >> 2;
+#pragma unroll 1
+        for (int q = lane; q < 22 * 5; q += 32) {
+            const int rp = (q * 13108) >> 16;                             // q / 5
+            const int g = q - rp * 5;
+            const uint32_t* r0 = reinterpret_cast<const uint32_t*>(raw + 2 * rp * KP_RAW_W) + wbase + 2 * g;
+            const uint32_t* r1 = r0 + (rp < 21 ? KP_RAW_W / 4 : 0);       // window row 43 does not exist (and is never used)
+            uint32_t hs[2][8];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const uint32_t* r = e ? r1 : r0;
+                const uint32_t w0 = r[0], w1 = r[1], w2 = r[2], w3 = r[3];
+                uint32_t W[12];
+                W[0] = w0; W[4] = w1; W[8] = w2;
+#pragma unroll
+                for (int j = 1; j < 4; ++j) {
+                    W[j] = __funnelshift_r(w0, w1, 8 * j);
+                    W[4 + j] = __funnelshift_r(w1, w2, 8 * j);
+                    W[8 + j] = __funnelshift_r(w2, w3, 8 * j);
+                }
+#pragma unroll
+                for (int x = 0; x < 8; ++x) hs[e][x] = __dp4a(W[x], K0123, __dp4a(W[x + 4], K456, 0u));
+            }
+            uint4 o0, o1;
+            o0.x = __byte_perm(hs[0][0], hs[1][0], 0x5410); o0.y = __byte_perm(hs[0][1], hs[1][1], 0x5410);
+            o0.z = __byte_perm(hs[0][2], hs[1][2], 0x5410); o0.w = __byte_perm(hs[0][3], hs[1][3], 0x5410);
+            o1.x = __byte_perm(hs[0][4], hs[1][4], 0x5410); o1.y = __byte_perm(hs[0][5], hs[1][5], 0x5410);
+            o1.z = __byte_perm(hs[0][6], hs[1][6], 0x5410); o1.w = __byte_perm(hs[0][7], hs[1][7], 0x5410);
+            uint4* dst = reinterpret_cast<uint4*>(Hp + rp * KP_HP_COLS + 8 * g);
+            dst[0] = o0;
+            dst[1] = o1;
+        }
+        __syncwarp();
+        // the raw window is consumed: fetch the next keypoint's while this one is blurred and sampled
+        if (nxt.it < total) issue(nxt);
+
+        // ---- phase 3: blur column pass.  item = (patch column ci, chunk of 8 rows); transposed store blT[B][y]
+        const int a4 = a16 & 3;
+#pragma unroll 1
+        for (int q = lane; q < 37 * 5; q += 32) {
+            const int ch = (q * 1772) >> 16;                              // q / 37 (exact for q < 185)
+            const int B = a4 + q - ch * 37;
+            const uint32_t* hp = Hp + 4 * ch * KP_HP_COLS + B;
+            uint32_t pr[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) pr[k] = hp[k * KP_HP_COLS];
+            uint32_t ve[4], vo[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                ve[m] = __dp2a_lo(pr[m], KA, __dp2a_hi(pr[m + 1], KA, __dp2a_lo(pr[m + 2], KB, __dp2a_hi(pr[m + 3], KB, 32768u))));
+                vo[m] = __dp2a_lo(pr[m], KC, __dp2a_hi(pr[m + 1], KC, __dp2a_lo(pr[m + 2], KD, __dp2a_hi(pr[m + 3], KD, 32768u))));
+            }
+            uint2 o;
+            o.x = __byte_perm(__byte_perm(ve[0], vo[0], 0x0062), __byte_perm(ve[1], vo[1], 0x0062), 0x5410);
+            o.y = __byte_perm(__byte_perm(ve[2], vo[2], 0x0062), __byte_perm(ve[3], vo[3], 0x0062), 0x5410);
+            *reinterpret_cast<uint2*>(blT + B * KP_BL_PITCH + 8 * ch) = o;
+        }
+        __syncwarp();
+
+        // ---- phase 4: descriptor byte `lane` (:115-144) from the blurred patch; sample (row rr, column cc)
+        //      relative to the keypoint sits at blT[a4 + cc + 18][rr + 18]
+        const uint8_t* bc = blT + (a4 + 18) * KP_BL_PITCH + 18;
+        uint32_t byte = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float x = px[2 * j + e], y = py[2 * j + e];
+                const int rr = __float2int_rn(__fadd_rn(__fmul_rn(x, b), __fmul_rn(y, a)));    // (:119)
+                const int cc = __float2int_rn(__fsub_rn(__fmul_rn(x, a), __fmul_rn(y, b)));    // (:120)
+                v[e] = bc[cc * KP_BL_PITCH + rr];
+            }
+            byte |= (uint32_t)(v[0] < v[1]) << j;
+        }
+        uint32_t word = byte << (8 * (lane & 3));
+        word |= __shfl_xor_sync(0xffffffffu, word, 1);
+        word |= __shfl_xor_sync(0xffffffffu, word, 2);                     // lanes 4k..4k+3 hold word k
+        const int half = lane >> 4;
+        uint4 v4;
+        v4.x = __shfl_sync(0xffffffffu, word, 16 * half + 0);
+        v4.y = __shfl_sync(0xffffffffu, word, 16 * half + 4);
+        v4.z = __shfl_sync(0xffffffffu, word, 16 * half + 8);
+        v4.w = __shfl_sync(0xffffffffu, word, 16 * half + 12);
+        const int* kc = kept_counts + cur.frame * nl;
+        int oidx = cur.sl;
+        for (int q = 0; q < cur.l; ++q) oidx += kc[q];                    // levels concatenated (:1076-1104)
+        const size_t orow = (size_t)cur.frame * kpf + oidx;
+        if ((lane & 15) == 0) *reinterpret_cast<uint4*>(out_desc + orow * 32 + 16 * half) = v4;
+        if (lane < 7) {
+            float f;
+            if (lane == 0) f = cur.l ? __fmul_rn((float)kx, L.scale) : (float)kx;
+            else if (lane == 1) f = cur.l ? __fmul_rn((float)ky, L.scale) : (float)ky;
+            else if (lane == 2) f = L.kp_size;
+            else if (lane == 3) f = angle;
+            else if (lane == 4) f = (float)ORBX_PR(cur.p);
+            else if (lane == 5) f = __int_as_float(cur.l);
+            else f = __int_as_float(-1);
+            out_kp[orow * 7 + lane] = f;
+        }
+        if (lane == 7) angles[cur.it] = angle;
+        __syncwarp();
+        cur = nxt;
     }
 }
 
@@ -1113,92 +1311,6 @@ __global__ void __launch_bounds__(128) blur_kernel(const OrbxPlan* __restrict__ 
 }
 
 // =====================================================================================
-// computeOrbDescriptor (:108-147), one warp per keypoint: lane i produces descriptor byte i
-// from its 16 pattern points (held in registers), bytes are merged with shuffles and the
-// 256 bits leave as two 128-bit stores.  The warp also writes the final cv::KeyPoint record
-// (pt scaled by mvScaleFactor[level] AFTER sampling, :1095-1101).  Canonical rule B-2:
-// a, b = float(cos/sin in double); products and sums individually rounded; round-half-even.
-// =====================================================================================
-__global__ void __launch_bounds__(256) desc_kernel(const OrbxPlan* __restrict__ plan, int nframes,
-                                                      const uint8_t* __restrict__ blur,
-                                                      const uint32_t* __restrict__ kept,
-                                                      const int* __restrict__ kept_counts,
-                                                      const float* __restrict__ angles,
-                                                      const float2* __restrict__ rot,
-                                                      float* __restrict__ out_kp, uint8_t* __restrict__ out_desc) {
-    ORBX_PDL_WAIT();
-    const int lane = threadIdx.x & 31;
-    float px[16], py[16];
-    {
-        const uint4 lo = reinterpret_cast<const uint4*>(g_pattern)[lane * 2], hi = reinterpret_cast<const uint4*>(g_pattern)[lane * 2 + 1];
-        const uint32_t wds[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const uint32_t wd = wds[j >> 1] >> (16 * (j & 1));
-            px[j] = (float)(int)(signed char)(wd & 0xff);
-            py[j] = (float)(int)(signed char)((wd >> 8) & 0xff);
-        }
-    }
-    const int kpf = plan->kept_per_frame;
-    const int nl = plan->nlevels;
-    const unsigned total = (unsigned)nframes * (unsigned)kpf;
-    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
-    for (unsigned it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < total; it += nwarps) {
-        const int frame = (int)(it / (unsigned)kpf);
-        const int s = (int)(it - (unsigned)frame * (unsigned)kpf);
-        const int l = level_of_slot(plan, s);
-        const OrbxLevel& L = plan->lv[l];
-        const int* kc = kept_counts + frame * nl;
-        const int sl = s - L.kept_off;
-        if (sl >= kc[l]) continue;
-        int oidx = sl;
-        for (int q = 0; q < l; ++q) oidx += kc[q];                          // levels concatenated (:1076-1104)
-        const uint32_t p = kept[it];
-        const int kx = ORBX_PX(p), ky = ORBX_PY(p);
-        const float angle = angles[it];
-        const float2 ab = rot[it];                                         // (cos, sin) from orient_kernel (:111-113)
-        const float a = ab.x, b = ab.y;
-        const uint8_t* center = level_px(blur + (size_t)frame * plan->slab_bytes, L, kx, ky);
-        const int pitch = L.pitch;
-        uint32_t byte = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            int v[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const float x = px[2 * j + e], y = py[2 * j + e];
-                const int rr = __float2int_rn(__fadd_rn(__fmul_rn(x, b), __fmul_rn(y, a)));    // (:119)
-                const int cc2 = __float2int_rn(__fsub_rn(__fmul_rn(x, a), __fmul_rn(y, b)));   // (:120)
-                v[e] = center[rr * pitch + cc2];
-            }
-            byte |= (uint32_t)(v[0] < v[1]) << j;
-        }
-        uint32_t word = byte << (8 * (lane & 3));
-        word |= __shfl_xor_sync(0xffffffffu, word, 1);
-        word |= __shfl_xor_sync(0xffffffffu, word, 2);                     // lanes 4k..4k+3 hold word k
-        const int half = lane >> 4;
-        uint4 v4;
-        v4.x = __shfl_sync(0xffffffffu, word, 16 * half + 0);
-        v4.y = __shfl_sync(0xffffffffu, word, 16 * half + 4);
-        v4.z = __shfl_sync(0xffffffffu, word, 16 * half + 8);
-        v4.w = __shfl_sync(0xffffffffu, word, 16 * half + 12);
-        const size_t orow = (size_t)frame * kpf + oidx;
-        if ((lane & 15) == 0) *reinterpret_cast<uint4*>(out_desc + orow * 32 + 16 * half) = v4;
-        if (lane < 7) {
-            float f;
-            if (lane == 0) f = l ? __fmul_rn((float)kx, L.scale) : (float)kx;
-            else if (lane == 1) f = l ? __fmul_rn((float)ky, L.scale) : (float)ky;
-            else if (lane == 2) f = L.kp_size;
-            else if (lane == 3) f = angle;
-            else if (lane == 4) f = (float)ORBX_PR(p);
-            else if (lane == 5) f = __int_as_float(l);
-            else f = __int_as_float(-1);
-            out_kp[orow * 7 + lane] = f;
-        }
-    }
-}
-
-// =====================================================================================
 // launch wrappers (called from orbx_api.cu)
 // =====================================================================================
 void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nframes, int num_sms, const uint8_t* imgs,
@@ -1229,8 +1341,8 @@ size_t fast_smem_bytes(const OrbxPlan& hp) {
     return ((size_t)hp.fast_nb * TB + SB + QB) * hp.fast_warps + 128;
 }
 
-// One {pitch, rows, frames} u8 tensor map per level over the pyramid slabs; box = one FAST window.
-int build_fast_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* out_maps) {
+// One {pitch, rows, frames} u8 tensor map per level over the pyramid slabs; box = bw x bh bytes of one frame.
+static int build_tile_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, int bw, int bh, void* out_maps) {
     static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -1246,7 +1358,7 @@ int build_fast_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* ou
         const OrbxLevel& L = hp.lv[l];
         cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.rows, (cuuint64_t)max_frames};
         cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)hp.slab_bytes};
-        cuuint32_t box[3] = {(cuuint32_t)hp.fast_bw, (cuuint32_t)hp.fast_bh, 1};
+        cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = encode(&fm->m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_pyr + L.plane_off, dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -1254,6 +1366,16 @@ int build_fast_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* ou
         if (r != CUDA_SUCCESS) return -(int)r - 100;
     }
     return 0;
+}
+
+// box = one strip of FAST cell windows
+int build_fast_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* out_maps) {
+    return build_tile_maps(hp, d_pyr, max_frames, hp.fast_bw, hp.fast_bh, out_maps);
+}
+
+// box = the raw window of one keypoint (describe_kernel)
+int build_describe_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* out_maps) {
+    return build_tile_maps(hp, d_pyr, max_frames, KP_RAW_W, KP_RAW_H, out_maps);
 }
 
 size_t fast_maps_bytes() { return sizeof(FastMaps); }
@@ -1321,20 +1443,6 @@ cudaError_t launch_octree(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframe
     return cudaSuccess;
 }
 
-static int warp_grid(long long items, int num_sms) {
-    long long blocks = (items + 7) / 8;
-    const long long cap = (long long)num_sms * 8;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    return (int)blocks;
-}
-
-void launch_orient(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* pyr,
-                   const uint32_t* kept, const int* kept_counts, float* angles, float2* rot, cudaStream_t st) {
-    launch_k(orient_kernel, dim3(warp_grid((long long)nframes * hp.kept_per_frame, num_sms)), dim3(256), 0, st, d_plan, nframes,
-             pyr, kept, kept_counts, angles, rot);
-}
-
 void launch_blur(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* pyr,
                  uint8_t* blur, cudaStream_t st) {
     long long blocks = ((long long)nframes * hp.blur_tiles_per_frame + 3) / 4;      // one warp per 128 x 32 tile
@@ -1344,11 +1452,30 @@ void launch_blur(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int nu
     launch_k(blur_kernel, dim3((unsigned)blocks), dim3(128), 0, st, d_plan, nframes, pyr, blur);
 }
 
-void launch_desc(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* blur,
-                 const uint32_t* kept, const int* kept_counts, const float* angles, const float2* rot,
-                 float* out_kp, uint8_t* out_desc, cudaStream_t st) {
-    launch_k(desc_kernel, dim3(warp_grid((long long)nframes * hp.kept_per_frame, num_sms)), dim3(256), 0, st, d_plan, nframes, blur,
-             kept, kept_counts, angles, rot, out_kp, out_desc);
+cudaError_t launch_describe(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, int frame0, int nframes, int num_sms,
+                            const uint32_t* kept, const int* kept_counts, float* angles, float* out_kp, uint8_t* out_desc,
+                            cudaStream_t st) {
+    const size_t smem = (size_t)KP_WARPS * KP_WARP_BYTES + 128;
+    static bool configured[64] = {false};
+    static int per_sm_cache[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, describe_kernel, KP_WARPS * 32, smem);
+        per_sm_cache[dev & 63] = per_sm < 1 ? 1 : per_sm;
+        configured[dev & 63] = true;
+    }
+    long long blocks = ((long long)nframes * hp.kept_per_frame + KP_WARPS - 1) / KP_WARPS;
+    const long long cap = (long long)num_sms * per_sm_cache[dev & 63];
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    FastMaps fm;
+    memcpy(&fm, maps, sizeof fm);
+    return launch_k(describe_kernel, dim3((unsigned)blocks), dim3(KP_WARPS * 32), smem, st, fm, d_plan, frame0, nframes, kept,
+                    kept_counts, angles, out_kp, out_desc);
 }
 
 }  // namespace orbx

@@ -28,12 +28,11 @@ size_t octree_smem_bytes(const OrbxPlan& hp);
 cudaError_t launch_octree(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, const uint32_t* cand,
                           const uint2* cell_rec, uint32_t* cand_sorted, uint16_t* key_node, int* sorted_counts,
                           uint32_t* kept, int* kept_counts, int* status, cudaStream_t st);
-void launch_orient(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* pyr,
-                   const uint32_t* kept, const int* kept_counts, float* angles, float2* rot, cudaStream_t st);
 void launch_blur(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* pyr,
                  uint8_t* blur, cudaStream_t st);
-void launch_desc(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, int num_sms, const uint8_t* blur,
-                 const uint32_t* kept, const int* kept_counts, const float* angles, const float2* rot, float* out_kp,
-                 uint8_t* out_desc, cudaStream_t st);
+int build_describe_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* out_maps);
+cudaError_t launch_describe(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, int frame0, int nframes, int num_sms,
+                            const uint32_t* kept, const int* kept_counts, float* angles, float* out_kp, uint8_t* out_desc,
+                            cudaStream_t st);
 
 }  // namespace orbx

@@ -54,5 +54,7 @@ def stage_algorithmic_bytes(width: int, height: int, nfeatures: int, scale_facto
     sizes = level_sizes(width, height, scale_factor, nlevels)
     areas = [w * h for w, h in sizes]
     pyr = sum((areas[0] if l == 0 else areas[l - 1]) + (w + 38) * (h + 38) for l, (w, h) in enumerate(sizes))
-    return {"pyramid": pyr, "fast_cells": sum(areas), "octree": 0, "orient": nfeatures * 749,
-            "blur": 2 * sum(areas), "descriptor": nfeatures * (512 + 32 + 28)}
+    # "describe" = IC_Angle + GaussianBlur + computeOrbDescriptor, fused per keypoint; its algorithmic bytes stay the
+    # stage sum of what the reference does (whole-level blur included), SURVEY.md §8(d): no fusion credit.
+    return {"pyramid": pyr, "fast_cells": sum(areas), "octree": 0,
+            "describe": nfeatures * 749 + 2 * sum(areas) + nfeatures * (512 + 32 + 28)}
