@@ -9,7 +9,9 @@ so = os.path.join(ROOT, "orbslam2_with_quadrics_b200", "liborbx.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 cub = [f for f in os.listdir(tmp) if f.startswith("orbx_kernels.") and f.endswith(".cubin")][0]
-sass = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
+# with inlining, each instruction is preceded by a chain of "//## File ..., line N inlined at ..." comments; the LAST
+# one of the chain is the line in the kernel's own body (outermost call site)
+sass = subprocess.run(["nvdisasm", "--print-line-info-inline", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kre], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 kname = rows[0][1]
