@@ -256,23 +256,26 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
     P->node_cap = round_up(P->node_cap, 32);
     if (P->max_cell_w < 7) P->max_cell_w = 7;
     if (P->max_cell_h < 7) P->max_cell_h = 7;
-    // FAST work units: segments of a cell row that fit one 256-byte-wide TMA tile (16-aligned start: up to 15 bytes of
-    // slack, plus the 6-px window overlap)
-    int units = 0;
+    // FAST tiling: NC cells per TMA tile, NB tile buffers per warp, W warps per CTA (env overrides are for tuning runs)
+    const char* e_nc = getenv("ORBX_FAST_NC"); const char* e_nb = getenv("ORBX_FAST_NB"); const char* e_w = getenv("ORBX_FAST_WARPS");
+    P->fast_nc = e_nc ? atoi(e_nc) : 2;       // measured best on B200 at 1080p: 2 cells per tile, single buffer, 8 warps
+    P->fast_nb = e_nb ? atoi(e_nb) : 1;
+    P->fast_warps = e_w ? atoi(e_w) : 8;
+    if (P->fast_nc < 1 || P->fast_nc > 8 || P->fast_nb < 1 || P->fast_nb > 2 || P->fast_warps < 1 || P->fast_warps > ORBX_FAST_WARPS)
+        return ORBX_ERR_BAD_ARGS;
+    int max_wcell = 0, strips = 0;
     for (int l = 0; l < n; ++l) {
         OrbxLevel& L = P->lv[l];
-        L.seg_cells = (256 - 15 - 6) / L.wCell;
-        if (L.seg_cells > 7) L.seg_cells = 7;
-        if (L.seg_cells < 1) return ORBX_ERR_BAD_GEOMETRY;
-        L.segs_x = (L.nColsV + L.seg_cells - 1) / L.seg_cells;
-        L.unit_base = units;
-        units += L.segs_x * L.nRowsV;
-        L.recip_wcell = (65536 + L.wCell - 1) / L.wCell;
-        L.recip_wcell1 = (65536 + L.wCell) / (L.wCell + 1);
+        if (L.wCell > max_wcell) max_wcell = L.wCell;
+        L.strip_base = strips;
+        L.strips_x = (L.nColsV + P->fast_nc - 1) / P->fast_nc;
+        strips += L.strips_x * L.nRowsV;
     }
-    P->units_per_frame = units;
+    P->strips_per_frame = strips;
+    // 16-aligned TMA start (delta <= 15), 1-byte shift, NC cell steps + the 6-px overlap, 2 words of read-ahead
+    P->fast_bw = round_up((P->fast_nc - 1) * max_wcell + P->max_cell_w + 24, 16);
     P->fast_bh = P->max_cell_h;
-    if (P->fast_bh > 127 || P->max_cell_w > 250) return ORBX_ERR_BAD_GEOMETRY;
+    if (P->fast_bw > 256 || P->fast_bh > 127 || P->max_cell_w > 250) return ORBX_ERR_BAD_GEOMETRY;
     P->cells_per_frame = cells;
     P->cand_per_frame = cand;
     P->kept_per_frame = kept;

@@ -229,35 +229,26 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const OrbxPlan* __restr
 }
 
 // =====================================================================================
-// FAST-9/16 per 30-px cell (cv::FAST(window, t, true)).
+// FAST-9/16 per 30-px cell (cv::FAST(window, t, true)), one warp per cell,
+// persistent warps with a dynamic work counter.
 //
-// Work unit = one SEGMENT of a cell row: up to seg_cells horizontally adjacent cell windows of
-// one level of one frame, processed by a whole CTA.  The cells' detection regions tile the
-// segment without gaps (cell j detects in window columns [j*wCell + 3, (j+1)*wCell + 3)), so
-// the threshold pre-test, the exact score and the non-maximum suppression run over the
-// segment as one data-parallel pass; only what the reference decides per cell is kept per
-// cell: the NMS frame (no score crosses a window edge), the iniThFAST -> minThFAST retry
-// (:812, taken iff the post-NMS result is empty) and the ordered output block.
-//
-// Staging: ONE TMA tile load (cp.async.bulk.tensor.3d, box 256 x fast_bh bytes over the
-// per-level {pitch, rows, frame} tensor map, mbarrier complete_tx) per unit; TMA needs the
-// inner coordinate on a 16-byte boundary, so window column 0 sits `delta` bytes into the tile.
-//   phase A  pre-test on ALIGNED words, 4 pixels per lane (SIMD in a word): |ring - centre| of
-//            the compass points 0/8 and 4/12 with VABSDIFF4; a 9-arc contains one pixel of
-//            every opposite pair, so pixels failing either pair are dropped.  Four runs of 128
-//            pixels share one packed warp scan; survivors go to an UNORDERED queue (one
-//            shared-memory atomic per warp and four runs).
-//   phase B  exact score of every survivor: A = max over the 16 arcs of min(+-(ring - centre))
-//            with packed 16-bit min/max; corner iff A > t, score A - 1 written to a score map
-//            in which neighbouring cells are separated by a zero column; corners are
-//            compacted in place (the queue region already consumed).
-//   phase C  strict 3x3 NMS on the score map; survivors set a bit in a per-row bitmap and
-//            count into their cell.
-//   emit     one global atomic per unit claims the cells' blocks; one warp per cell walks its
-//            rows of the bitmap (lane = row, warp scan of the popcounts) and writes the
-//            keypoints in the reference's order (row-major inside the window, :818-826).
-// Cells whose iniThFAST pass kept nothing are redone with minThFAST (same phases, run
-// families restricted to those cells).
+// Staging: a work item is a strip of NC horizontally adjacent cell windows (default 2), fetched by
+// ONE elected lane with a TMA tile load (cp.async.bulk.tensor.3d over a per-level
+// {pitch, rows, frame} tensor map, mbarrier complete_tx) into shared memory (NB = 1 or 2 tile
+// buffers per warp; with 2 the next strip is in flight while the current one is processed --
+// measured equal, so the default is 1 and more resident warps).  TMA needs the inner coordinate
+// on a 16-byte boundary, so the BW x BH box starts at the 16-aligned column at or before
+// (window x0 - 1) and a window sits `delta` bytes into the tile: tile column = window x + 1 +
+// delta.  Words are re-aligned with funnel shifts.
+//   phase 1  4 pixels per lane, SIMD-in-word: |ring - centre| for the compass points 0/8 and
+//            4/12 with VABSDIFF4; a 9-arc needs one pixel of every opposite pair beyond the
+//            threshold, so pixels failing either pair are dropped.  8 warp iterations of tests
+//            are issued back to back, their survivor counts scanned together (packed 8-bit
+//            counts), survivors queued in row-major order.
+//   phase 2  per survivor: exact score A = max over the 16 arcs of min(+-(ring - centre)) with
+//            packed 16-bit min/max (two arcs per instruction); corner iff A > t, score = A - 1.
+//   phase 3  strict 3x3 NMS on a zero-framed score map, count, then ordered emission.
+// The iniThFAST pass is repeated with minThFAST iff it produced no keypoint (:812).
 // =====================================================================================
 struct FastMaps {
     CUtensorMap m[ORBX_MAXL];
@@ -289,6 +280,25 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+struct FastStrip {
+    int frame, l, ci, cj0;     // NC horizontally adjacent cells starting at column cj0 of cell row ci
+};
+
+// Items of one launch: the strips of levels [l0, l1) of every frame, frame-major.
+__device__ __forceinline__ FastStrip fast_decode(const OrbxPlan* __restrict__ plan, unsigned item, int l0, int l1,
+                                                 unsigned spf, int first_strip) {
+    FastStrip c;
+    c.frame = (int)(item / spf);
+    const int r = (int)(item - (unsigned)c.frame * spf) + first_strip;
+    int l = l0;
+    while (l + 1 < l1 && r >= plan->lv[l + 1].strip_base) ++l;
+    c.l = l;
+    const OrbxLevel& L = plan->lv[l];
+    c.ci = (int)((unsigned)(r - L.strip_base) / (unsigned)L.strips_x);
+    c.cj0 = ((r - L.strip_base) - c.ci * L.strips_x) * plan->fast_nc;
+    return c;
 }
 
 // VIMNMX3.S16x2 issues on the quarter-rate XU pipe on sm_100 (measured: XU 85 % busy with the score network
@@ -354,327 +364,246 @@ __device__ __forceinline__ int fast_score_packed(const uint8_t* __restrict__ p, 
     return A > t ? A - 1 : 0;
 }
 
-#define FB_THREADS 256
-#define FB_WARPS 8
-#define FB_TW 256                 // tile pitch = TMA box width (bytes)
-#define FB_TW4 (FB_TW / 4)
-#define FB_SP 272                 // score-map pitch; cell jj of a segment owns map columns [jj * (wCell + 1) + 1, ... + wCell)
-#define FB_BMW 10                 // bitmap words per tile row (272 bits + read-ahead of the emission funnel shifts)
-#define FB_MAXCELLS 7             // cells per segment: seg_cells * wCell + 6 + 15 <= 256 and wCell >= 30
-
-// A family of pre-test runs: a run covers RPI consecutive rows x G consecutive tile words (RPI * G <= 32 lanes);
-// runs are issued in groups of 4 (one packed warp scan per group).
-struct FastFam {
-    int wl, G, RPI, mg;           // first tile word, words per row, rows per run, c_recip16[G]
-    int ca, cb;                   // detection columns of the family: tile bytes [ca, cb)
-    int first, ngroups;           // group index range [first, first + ngroups)
-};
-
-__global__ void __launch_bounds__(FB_THREADS, 4)
-fast_band_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, int frame0, int nframes,
-                 int l0, int l1, uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec, int* __restrict__ level_counts,
-                 int* __restrict__ work_counter, int* __restrict__ status) {
+#ifndef ORBX_FAST_MINB
+#define ORBX_FAST_MINB 3
+#endif
+// BW_T: tile pitch known at compile time (ring offsets become immediates); 0 = read it from the plan.
+template <int BW_T>
+__global__ void __launch_bounds__(ORBX_FAST_WARPS * 32, ORBX_FAST_MINB)
+fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, int frame0, int nframes,
+                  int l0, int l1, uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec, int* __restrict__ level_counts,
+                  int* __restrict__ work_counter, int* __restrict__ status) {
     ORBX_PDL_WAIT();
     extern __shared__ uint8_t fast_smem_raw[];
-    __shared__ uint64_t s_bar;
-    __shared__ int s_next, s_qn, s_cn, s_ovf, s_emit, s_ngroups;
-    __shared__ int s_cnt[8], s_cbase[8];
-    __shared__ FastFam s_fam[8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int BH = plan->fast_bh;
-    uint8_t* tile = fast_smem_raw + ((128 - (smem_u32(fast_smem_raw) & 127)) & 127);
-    const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
-    uint8_t* sc = tile + FB_TW * BH;                                      // zero except at corners of the current pass
-    uint32_t* bm = reinterpret_cast<uint32_t*>(sc + FB_SP * BH);         // kept-corner bits, map columns
-    uint16_t* queue = reinterpret_cast<uint16_t*>(bm + BH * FB_BMW);     // survivors (r << 8 | c), then corners (r << 9 | mc)
+    __shared__ uint64_t s_bar[ORBX_FAST_WARPS][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int BW = BW_T ? BW_T : plan->fast_bw, BH = plan->fast_bh;
+    const int NC = plan->fast_nc, NB = plan->fast_nb;                    // cells per tile, tile buffers per warp
+    const int TB = (BW * BH + 127) & ~127;                               // tile bytes
+    const int QN = (plan->max_cell_w - 6) * (plan->max_cell_h - 6);      // queue entries (u16)
+    const int SP = (plan->max_cell_w + 2 + 3) & ~3;                      // score-map pitch; column = window x + 1
+    const int SB = (SP * BH + 127) & ~127;
+    const int per_warp = NB * TB + SB + ((QN * 2 + 127) & ~127);
+    uint8_t* base = fast_smem_raw + ((128 - (smem_u32(fast_smem_raw) & 127)) & 127) + (size_t)warp * per_warp;
+    uint8_t* sc = base + NB * TB;                                        // zero-framed score map
+    uint16_t* queue = reinterpret_cast<uint16_t*>(base + NB * TB + SB);  // entries (y << 8) | x, window coordinates
     const int nlevels = plan->nlevels;
-    const int first_unit = plan->lv[l0].unit_base;
-    const unsigned upf = (unsigned)((l1 < nlevels ? plan->lv[l1].unit_base : plan->units_per_frame) - first_unit);
-    const unsigned total = (unsigned)nframes * upf;
+    const int first_strip = plan->lv[l0].strip_base;
+    const unsigned spf = (unsigned)((l1 < nlevels ? plan->lv[l1].strip_base : plan->strips_per_frame) - first_strip);
+    const unsigned total = (unsigned)nframes * spf;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const int BW4 = BW >> 2;
 
-    for (int i = tid; i < (FB_SP * BH + BH * FB_BMW * 4) / 4; i += FB_THREADS) reinterpret_cast<uint32_t*>(sc)[i] = 0;
-    if (tid == 0) {
-        mbar_init(&s_bar, 1);
+    for (int i = lane; i < SB / 4; i += 32) reinterpret_cast<uint32_t*>(sc)[i] = 0;
+    if (lane == 0) {
+        mbar_init(&s_bar[warp][0], 1);
+        mbar_init(&s_bar[warp][1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        s_next = atomicAdd(work_counter, 1);
-        s_qn = 0;
-        s_cn = 0;
     }
-    if (tid < 8) s_cnt[tid] = 0;
-    __syncthreads();
-    unsigned cur = (unsigned)s_next;
-    uint32_t phase = 0;
+    __syncwarp();
 
-    while (cur < total) {
-        // ---- decode the unit (uniform)
-        const int frame = (int)(cur / upf);
-        const int ru = (int)(cur - (unsigned)frame * upf) + first_unit;
-        int l = l0;
-        while (l + 1 < l1 && ru >= plan->lv[l + 1].unit_base) ++l;
-        const OrbxLevel& L = plan->lv[l];
-        const int ci = (int)((unsigned)(ru - L.unit_base) / (unsigned)L.segs_x);
-        const int cj0 = ((ru - L.unit_base) - ci * L.segs_x) * L.seg_cells;
-        const int nseg = min(L.seg_cells, L.nColsV - cj0);
-        const int wCell = L.wCell;
-        const int x0 = cj0 * wCell, y0 = ci * L.hCell;                    // box coordinates of the segment window
-        const int ww = min(x0 + nseg * wCell + 6, L.maxBX - ORBX_BOX) - x0;
-        const int wh = min(y0 + L.hCell + 6, L.maxBY - ORBX_BOX) - y0;
-        const int px0 = ORBX_XO + ORBX_BOX + x0;                          // plane column of window column 0
-        const int delta = px0 & 15;
-        const bool detect = ww >= 7 && wh >= 7;                           // cv::FAST returns nothing below 7 x 7
-        const int cE0 = delta + 3, cE1 = delta + ww - 3;                  // detection columns (tile bytes)
-        const int rE1 = wh - 3;                                           // detection rows [3, rE1)
-        const int recipW = plan->lv[l].recip_wcell;                       // ceil(65536 / wCell)
-        const int recipW1 = plan->lv[l].recip_wcell1;                     // ceil(65536 / (wCell + 1))
-        if (tid == 0) {
-            mbar_expect_tx(&s_bar, (uint32_t)(FB_TW * BH));
-            tma_load_3d(tile, &maps.m[l], &s_bar, px0 & ~15, ORBX_EDGE + ORBX_BOX + y0, frame0 + frame);
-            s_next = atomicAdd(work_counter, 1);                          // next unit, fetched a whole unit ahead
-            // run families of the iniThFAST pass: the whole detection area, 32 words per row at a time
-            int nf = 0, ng = 0;
-            if (detect) {
-                const int wlo = cE0 >> 2, NW = ((cE1 - 1) >> 2) - wlo + 1, nrows = rE1 - 3;
-                for (int hf = 0; hf * 32 < NW; ++hf) {
-                    FastFam F;
-                    F.wl = wlo + 32 * hf;
-                    F.G = min(NW - 32 * hf, 32);
-                    F.RPI = 32 / F.G;
-                    F.mg = c_recip16[F.G];
-                    F.ca = cE0;
-                    F.cb = cE1;
-                    F.first = ng;
-                    F.ngroups = ((nrows + F.RPI - 1) / F.RPI + 3) >> 2;
-                    ng += F.ngroups;
-                    s_fam[nf++] = F;
-                }
-            }
-            s_ngroups = ng;
+#ifdef ORBX_EXP_STATIC
+    unsigned static_next = blockIdx.x * (blockDim.x >> 5) + warp;
+    auto fetch = [&]() -> unsigned {
+        const unsigned v = static_next;
+        static_next += gridDim.x * (blockDim.x >> 5);
+        return v;
+    };
+#else
+    auto fetch = [&]() -> unsigned {
+        int v = 0;
+        if (lane == 0) v = atomicAdd(work_counter, 1);
+        return (unsigned)__shfl_sync(0xffffffffu, v, 0);
+    };
+#endif
+    auto issue = [&](const FastStrip& c, int b) {
+        if (lane == 0) {
+            const OrbxLevel& L = plan->lv[c.l];
+            mbar_expect_tx(&s_bar[warp][b], (uint32_t)(BW * BH));
+            tma_load_3d(base + b * TB, &maps.m[c.l], &s_bar[warp][b], (ORBX_XO + ORBX_BOX + c.cj0 * L.wCell - 1) & ~15,
+                        ORBX_EDGE + ORBX_BOX + c.ci * L.hCell, frame0 + c.frame);
         }
-        __syncthreads();
-        const unsigned nxt = (unsigned)s_next;
-        mbar_wait(&s_bar, phase);
-        phase ^= 1;
+    };
 
-        int emit_mask = 0;                                                // cells whose result is final after this pass
-        uint32_t done_mask = 0;
-        for (int pass = 0; pass < 2; ++pass) {
-            const int t = pass == 0 ? plan->ini_th : plan->min_th;
-            const uint32_t C = (uint32_t)(0x7f - min(t, 0x7f)) * 0x01010101u;
-            // ---- phase A: pre-test + unordered compaction
-            const int ngroups = s_ngroups;
-            {
-                int f = 0;
-                for (int gq = warp; gq < ngroups; gq += FB_WARPS) {
-                    while (gq >= s_fam[f].first + s_fam[f].ngroups) ++f;
-                    const FastFam F = s_fam[f];
-                    const int ry = (lane * F.mg) >> 16, g = lane - ry * F.G;
-                    const int w = F.wl + g;
-                    uint32_t vm = 0;
-                    if (ry < F.RPI) {
-                        const int lo = max(F.ca - 4 * w, 0), hi = min(F.cb - 4 * w, 4);
-                        if (hi > lo) vm = (0x80808080u << (8 * lo)) & (0x80808080u >> (8 * (4 - hi)));
-                    }
-                    const int rbase = 3 + (gq - F.first) * 4 * F.RPI + ry;
-                    uint32_t m[4];
+    // A work item is a strip of NC cells fetched as ONE tile (fewer, wider TMA rows).  The work counter is read
+    // one item further ahead than the tile prefetch, so the atomic's round trip overlaps a whole strip.
+    unsigned cur = fetch();
+    unsigned nxt = fetch();
+    FastStrip cc, nc;
+    if (cur < total) { cc = fast_decode(plan, cur, l0, l1, spf, first_strip); issue(cc, 0); }
+    uint32_t phase[2] = {0, 0};
+    int b = 0;
+    while (cur < total) {
+        if (NB == 2 && nxt < total) { nc = fast_decode(plan, nxt, l0, l1, spf, first_strip); issue(nc, b ^ 1); }
+        const unsigned nxt2 = nxt < total ? fetch() : nxt;
+        mbar_wait(&s_bar[warp][b], phase[b]);
+        phase[b] ^= 1;
+
+        const OrbxLevel& L = plan->lv[cc.l];
+        const int delta0 = (ORBX_XO + ORBX_BOX + cc.cj0 * L.wCell - 1) & 15;
+        const int iniY = ORBX_BOX + cc.ci * L.hCell;
+        const int wh = min(iniY + L.hCell + 6, L.maxBY) - iniY;
+        const int ncell = min(NC, L.nColsV - cc.cj0);
+        for (int cix = 0; cix < ncell; ++cix) {
+        const int cj = cc.cj0 + cix;
+        const int iniX = ORBX_BOX + cj * L.wCell;
+        const int ww = min(iniX + L.wCell + 6, L.maxBX) - iniX;
+        const int delta = delta0 + cix * L.wCell;                        // byte offset of (window x0 - 1) inside the tile
+        const uint8_t* tile = base + b * TB + delta + 1;                 // byte of window pixel (0, 0)
+        const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(base + b * TB) + (delta >> 2);
+        const int sh = (delta & 3) * 8;
+        int count = 0, cn = 0;
+#ifdef ORBX_EXP_SKIP_ALL
+        if (ww >= 7 && wh >= 70000) {
+#else
+        if (ww >= 7 && wh >= 7) {
+#endif
+            const int ew = ww - 6;                                       // emission width
+            const int G = (ew + 3) >> 2;                                 // 4-pixel groups per row
+            const int mg = c_recip16[min(G, 32)];                       // (n * mg) >> 16 == n / G for n <= 32
+            const int RPI = (32 * mg) >> 16;                             // rows per warp iteration
+            const int ry = (lane * mg) >> 16, g = lane - ry * G;
+            const int nvalid = min(max(ew - 4 * g, 0), 4);
+            const uint32_t vmask = (ry < RPI && nvalid > 0) ? (0x80808080u >> (8 * (4 - nvalid))) : 0u;
+            for (int pass = 0; pass < 2 && count == 0; ++pass) {
+                const int t = pass == 0 ? plan->ini_th : plan->min_th;
+                const uint32_t C = (uint32_t)(0x7f - min(t, 0x7f)) * 0x01010101u;
+                // ---- phase 1, in chunks of 8 warp iterations (RPI rows each): first all pre-tests (independent
+                //      loads and SIMD math, nothing serialises), then ONE pair of packed warp scans for the chunk
+                //      (four 8-bit counts per register), then the ordered queue writes.
+                int qn = 0;
+                for (int yc = 3; yc < wh - 3; yc += 8 * RPI) {
+                    uint32_t m[8];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int r = rbase + k * F.RPI;
-                        // rows past the detection area are clamped (always inside the tile) and masked out: no divergence
-                        const uint32_t* rp = tile32 + min(r, rE1 - 1) * FB_TW4 + w;
-                        const uint32_t c1 = rp[0], c0 = rp[-1], c2 = rp[1];
-                        const uint32_t up = rp[-3 * FB_TW4], dn = rp[3 * FB_TW4];
-                        const uint32_t r4 = __funnelshift_r(c1, c2, 24);        // pixels x+3 .. x+6
-                        const uint32_t r12 = __funnelshift_r(c0, c1, 8);        // pixels x-3 .. x
-                        const uint32_t a0 = __vabsdiffu4(dn, c1), a8 = __vabsdiffu4(up, c1);
-                        const uint32_t a4 = __vabsdiffu4(r4, c1), a12 = __vabsdiffu4(r12, c1);
-                        // bit 7 of a byte of ((a & 0x7f) + C) | a  <=>  a > t
-                        const uint32_t s0 = (a0 & 0x7f7f7f7fu) + C, s8 = (a8 & 0x7f7f7f7fu) + C;
-                        const uint32_t s4 = (a4 & 0x7f7f7f7fu) + C, s12 = (a12 & 0x7f7f7f7fu) + C;
-                        m[k] = ((s0 | a0) | (s8 | a8)) & ((s4 | a4) | (s12 | a12)) & (r < rE1 ? vm : 0u);
+                    for (int k = 0; k < 8; ++k) {
+                        const int y = yc + k * RPI + ry;
+                        {   // rows past the window are clamped (always inside the tile) and masked out: no divergence
+                            const uint32_t* r = tile32 + min(y, wh - 4) * BW4 + g;    // raw word holding tile column 4g + (delta & ~3)
+                            const uint32_t c1 = __funnelshift_r(r[1], r[2], sh);      // pixels x .. x+3, x = 3 + 4g
+                            const uint32_t c0 = __funnelshift_r(r[0], r[1], sh);
+                            const uint32_t c2 = __funnelshift_r(r[2], r[3], sh);
+                            const uint32_t up = __funnelshift_r(r[1 - 3 * BW4], r[2 - 3 * BW4], sh);
+                            const uint32_t dn = __funnelshift_r(r[1 + 3 * BW4], r[2 + 3 * BW4], sh);
+                            const uint32_t r4 = __funnelshift_r(c1, c2, 24);        // pixels x+3 .. x+6
+                            const uint32_t r12 = __funnelshift_r(c0, c1, 8);        // pixels x-3 .. x
+                            const uint32_t a0 = __vabsdiffu4(dn, c1), a8 = __vabsdiffu4(up, c1);
+                            const uint32_t a4 = __vabsdiffu4(r4, c1), a12 = __vabsdiffu4(r12, c1);
+                            // bit 7 of a byte of ((a & 0x7f) + C) | a  <=>  a > t
+                            const uint32_t s0 = (a0 & 0x7f7f7f7fu) + C, s8 = (a8 & 0x7f7f7f7fu) + C;
+                            const uint32_t s4 = (a4 & 0x7f7f7f7fu) + C, s12 = (a12 & 0x7f7f7f7fu) + C;
+                            m[k] = ((s0 | a0) | (s8 | a8)) & ((s4 | a4) | (s12 | a12)) & (y < wh - 3 ? vmask : 0u);
+                        }
                     }
-                    // per-lane counts are <= 4 and a run total is <= 128, so the four runs' counts share one register
+                    // per-lane counts are <= 4 and a warp total is <= 128, so four counts fit one register
                     uint32_t pa = (uint32_t)__popc(m[0]) | ((uint32_t)__popc(m[1]) << 8) | ((uint32_t)__popc(m[2]) << 16) | ((uint32_t)__popc(m[3]) << 24);
-                    const uint32_t ca = pa;
+                    uint32_t pb = (uint32_t)__popc(m[4]) | ((uint32_t)__popc(m[5]) << 8) | ((uint32_t)__popc(m[6]) << 16) | ((uint32_t)__popc(m[7]) << 24);
+                    const uint32_t ca = pa, cb = pb;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t ta = __shfl_up_sync(0xffffffffu, pa, o);
-                        if (lane >= o) pa += ta;
+                        const uint32_t ta = __shfl_up_sync(0xffffffffu, pa, o), tb = __shfl_up_sync(0xffffffffu, pb, o);
+                        if (lane >= o) { pa += ta; pb += tb; }
                     }
-                    const uint32_t tot = __shfl_sync(0xffffffffu, pa, 31);
-                    const int t0 = tot & 0xff, t1 = (tot >> 8) & 0xff, t2 = (tot >> 16) & 0xff, t3 = tot >> 24;
-                    int qb = 0;
-                    if (lane == 31 && tot) qb = atomicAdd(&s_qn, t0 + t1 + t2 + t3);
-                    qb = __shfl_sync(0xffffffffu, qb, 31);
+                    const uint32_t tota = __shfl_sync(0xffffffffu, pa, 31), totb = __shfl_sync(0xffffffffu, pb, 31);
                     pa -= ca;                                                    // exclusive prefixes
+                    pb -= cb;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t pk = ((k < 4 ? pa : pb) >> (8 * (k & 3))) & 0xffu;
+                        const uint32_t tk = ((k < 4 ? tota : totb) >> (8 * (k & 3))) & 0xffu;
                         if (m[k]) {
-                            uint16_t* wq = queue + qb + ((pa >> (8 * k)) & 0xffu);
-                            const int e = ((rbase + k * F.RPI) << 8) | (4 * w);
+                            uint16_t* wq = queue + qn + pk;
+                            const int e = ((yc + k * RPI + ry) << 8) | (3 + 4 * g);
                             if (m[k] & 0x80u) *wq++ = (uint16_t)e;
                             if (m[k] & 0x8000u) *wq++ = (uint16_t)(e + 1);
                             if (m[k] & 0x800000u) *wq++ = (uint16_t)(e + 2);
                             if (m[k] & 0x80000000u) *wq++ = (uint16_t)(e + 3);
                         }
-                        qb += k == 0 ? t0 : k == 1 ? t1 : t2;
+                        qn += (int)tk;
                     }
                 }
-            }
-            __syncthreads();
-            // ---- phase B: exact score of the survivors; corners compacted in place, scores to the map
-            const int qn = s_qn;
-            for (int i0 = 0; i0 < qn; i0 += FB_THREADS) {
-                const int i = i0 + tid;
-                const int e = queue[min(i, qn - 1)];                             // clamped: every thread scores a real pixel
-                const int r = e >> 8, c = e & 0xff;
-                int s = fast_score_packed(tile + r * FB_TW + c, FB_TW, t);
-                if (i >= qn) s = 0;
-                __syncthreads();                                                 // this round's queue reads are done
-                const uint32_t bal = __ballot_sync(0xffffffffu, s > 0);
-                if (bal) {
-                    int pos = 0;
-                    if (lane == 0) pos = atomicAdd(&s_cn, __popc(bal));
-                    pos = __shfl_sync(0xffffffffu, pos, 0);
+                __syncwarp();
+                // ---- phase 2: exact score; corners compacted in place (order kept), scores to the map
+                cn = 0;
+                for (int i0 = 0; i0 < qn; i0 += 32) {
+                    const int i = i0 + lane;
+                    const int e = queue[min(i, qn - 1)];                         // clamped: every lane scores a real pixel
+#ifdef ORBX_EXP_SKIP_P2
+                    int s = 0;
+#else
+                    int s = fast_score_packed(tile + (e >> 8) * BW + (e & 0xff), BW, t);
+#endif
+                    if (i >= qn) s = 0;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, s > 0);
                     if (s > 0) {
-                        const int jj = ((c - cE0) * recipW) >> 16;               // cell of the segment
-                        const int mc = c - cE0 + jj + 1;                         // map column: one zero column between cells
-                        sc[r * FB_SP + mc] = (uint8_t)s;
-                        queue[pos + __popc(bal & lt_mask)] = (uint16_t)((r << 9) | mc);   // pos + rank < (round + 1) * 256
+                        sc[(e >> 8) * SP + (e & 0xff) + 1] = (uint8_t)s;
+                        queue[cn + __popc(bal & lt_mask)] = (uint16_t)e;
                     }
+                    cn += __popc(bal);
+                }
+                __syncwarp();
+                // ---- phase 3a: strict 3x3 NMS (the window frame and non-corners score 0); mark + count
+                for (int i0 = 0; i0 < cn; i0 += 32) {
+                    const int i = i0 + lane;
+                    bool keep = false;
+                    if (i < cn) {
+                        const int e = queue[i];
+                        const uint8_t* mp = sc + (e >> 8) * SP + (e & 0xff) + 1;
+                        const int s = mp[0];
+                        keep = s > mp[-1] && s > mp[1] && s > mp[-SP - 1] && s > mp[-SP] && s > mp[-SP + 1] &&
+                               s > mp[SP - 1] && s > mp[SP] && s > mp[SP + 1];
+                        if (keep) queue[i] = (uint16_t)(e | 0x8000);
+                    }
+                    count += __popc(__ballot_sync(0xffffffffu, keep));
+                }
+                __syncwarp();
+                if (count == 0) {                                                // clear the map before the retry
+                    for (int i = lane; i < cn; i += 32) sc[(queue[i] >> 8) * SP + (queue[i] & 0xff) + 1] = 0;
+                    __syncwarp();
+                    cn = 0;
                 }
             }
-            __syncthreads();
-            // ---- phase C: strict 3x3 NMS (the frame of every cell and non-corners score 0)
-            const int cn = s_cn;
-            for (int i = tid; i < cn; i += FB_THREADS) {
-                const int e = queue[i];
-                const int r = e >> 9, mc = e & 511;
-                const uint8_t* mp = sc + r * FB_SP + mc;
-                const int s = mp[0];
-                const bool keep = s > mp[-1] && s > mp[1] && s > mp[-FB_SP - 1] && s > mp[-FB_SP] && s > mp[-FB_SP + 1] &&
-                                  s > mp[FB_SP - 1] && s > mp[FB_SP] && s > mp[FB_SP + 1];
-                if (keep) {
-                    atomicOr(&bm[r * FB_BMW + (mc >> 5)], 1u << (mc & 31));
-                    atomicAdd(&s_cnt[((mc - 1) * recipW1) >> 16], 1);
-                }
-            }
-            __syncthreads();
-            // ---- claim the output blocks: cells with keypoints, and (last pass) everything still open
-            if (tid == 0) {
-                int tot = 0, em = 0;
-                for (int jj = 0; jj < nseg; ++jj)
-                    if (!((done_mask >> jj) & 1u) && (s_cnt[jj] > 0 || pass == 1 || !detect)) {
-                        em |= 1 << jj;
-                        tot += s_cnt[jj];
-                    }
-                int gbase = 0, ovf = 0;
-                if (tot > 0) {
-                    gbase = atomicAdd(&level_counts[frame * nlevels + l], tot);
-                    if (gbase + tot > L.cand_cap) {
-                        atomicOr(&status[frame], ORBX_DEV_CAND_OVERFLOW);
-                        ovf = 1;
-                    }
-                }
-                for (int jj = 0; jj < nseg; ++jj)
-                    if ((em >> jj) & 1) {
-                        s_cbase[jj] = gbase;
-                        gbase += s_cnt[jj];
-                    }
-                s_ovf = ovf;
-                s_emit = em;
-            }
-            __syncthreads();
-            emit_mask = s_emit;
-            const int ovf = s_ovf;
-            // ---- emit: warp jj writes cell jj in row-major order
-            if (warp < nseg && ((emit_mask >> warp) & 1)) {
-                const int jj = warp;
-                const int cnt = s_cnt[jj];
-                const int cbase = s_cbase[jj];
-                if (cnt > 0 && !ovf) {
-                    const int mc0 = jj * (wCell + 1) + 1;
-                    const int ew = min(wCell, cE1 - cE0 - jj * wCell);           // clipped detection width of the cell (> 0 here)
-                    const uint32_t mlo = ew >= 32 ? 0xffffffffu : (1u << ew) - 1u;
-                    const uint32_t mhi = ew > 32 ? (ew >= 64 ? 0xffffffffu : (1u << (ew - 32)) - 1u) : 0u;
-                    uint32_t* dst = cand + (size_t)frame * plan->cand_per_frame + L.cand_off;
-                    const int xb = x0 + 3 + jj * wCell;                          // box x of map column mc0 (:822)
-                    int outpos = cbase;
-                    for (int rb = 3; rb < rE1; rb += 32) {
-                        const int r = rb + lane;
-                        uint32_t lo = 0, hi = 0;
-                        if (r < rE1) {
-                            const uint32_t* bw = bm + r * FB_BMW + (mc0 >> 5);
-                            const int sh = mc0 & 31;
-                            lo = __funnelshift_r(bw[0], bw[1], sh) & mlo;
-                            hi = __funnelshift_r(bw[1], bw[2], sh) & mhi;
-                        }
-                        const int c = __popc(lo) + __popc(hi);
-                        int inc = c;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const int tv = __shfl_up_sync(0xffffffffu, inc, o);
-                            if (lane >= o) inc += tv;
-                        }
-                        int pos = outpos + inc - c;
-                        outpos += __shfl_sync(0xffffffffu, inc, 31);
-                        const uint8_t* srow = sc + r * FB_SP + mc0;
-                        while (lo) {
-                            const int b = __ffs(lo) - 1;
-                            lo &= lo - 1;
-                            dst[pos++] = ORBX_PACK(xb + b, y0 + r, srow[b]);
-                        }
-                        while (hi) {
-                            const int b = __ffs(hi) + 31;
-                            hi &= hi - 1;
-                            dst[pos++] = ORBX_PACK(xb + b, y0 + r, srow[b]);
-                        }
-                    }
-                }
-                if (lane == 0)
-                    cell_rec[(size_t)frame * plan->cells_per_frame + L.cell_base + ci * L.nColsV + cj0 + jj] =
-                        make_uint2((uint32_t)(cnt > 0 ? cbase : 0), ovf ? 0u : (uint32_t)cnt);
-            }
-            done_mask |= (uint32_t)emit_mask;
-            const bool more = pass == 0 && done_mask != (1u << nseg) - 1u;      // uniform
-            __syncthreads();
-            // ---- leave the score map and the bitmap all-zero; prepare the retry
-            for (int i = tid; i < cn; i += FB_THREADS) {
-                const int e = queue[i];
-                sc[(e >> 9) * FB_SP + (e & 511)] = 0;
-            }
-            for (int i = tid; i < BH * FB_BMW; i += FB_THREADS) bm[i] = 0;
-            if (tid < 8) s_cnt[tid] = 0;
-            if (tid == 0) {
-                s_qn = 0;
-                s_cn = 0;
-                int nf = 0, ng = 0;
-                if (more) {
-                    // run families of the minThFAST pass: one per cell that kept nothing (:812-816)
-                    const int nrows = rE1 - 3;
-                    for (int jj = 0; jj < nseg; ++jj) {
-                        if ((done_mask >> jj) & 1u) continue;
-                        FastFam F;
-                        F.ca = cE0 + jj * wCell;
-                        F.cb = min(F.ca + wCell, cE1);
-                        if (F.cb <= F.ca) continue;
-                        F.wl = F.ca >> 2;
-                        F.G = ((F.cb - 1) >> 2) - F.wl + 1;
-                        F.RPI = 32 / F.G;
-                        F.mg = c_recip16[F.G];
-                        F.first = ng;
-                        F.ngroups = ((nrows + F.RPI - 1) / F.RPI + 3) >> 2;
-                        ng += F.ngroups;
-                        s_fam[nf++] = F;
-                    }
-                }
-                s_ngroups = ng;
-            }
-            __syncthreads();
-            if (!more) break;
         }
+        // ---- emit: claim a contiguous block of the level's candidate region, write in row-major order
+        int gbase = 0;
+        bool overflow = false;
+        if (count > 0) {
+            if (lane == 0) gbase = atomicAdd(&level_counts[cc.frame * nlevels + cc.l], count);
+            gbase = __shfl_sync(0xffffffffu, gbase, 0);
+            if (gbase + count > L.cand_cap) {
+                if (lane == 0) atomicOr(&status[cc.frame], ORBX_DEV_CAND_OVERFLOW);
+                overflow = true;
+            }
+        }
+        uint32_t* dst = cand + (size_t)cc.frame * plan->cand_per_frame + L.cand_off + gbase;
+        const int ox = cj * L.wCell, oy = cc.ci * L.hCell;                     // (:822-823)
+        int w = 0;
+        for (int i0 = 0; i0 < cn; i0 += 32) {
+            const int i = i0 + lane;
+            bool keep = false;
+            int x = 0, y = 0, s = 0;
+            if (i < cn) {
+                const int e = queue[i];
+                keep = (e & 0x8000) != 0;
+                y = (e >> 8) & 0x7f;
+                x = e & 0xff;
+                s = sc[y * SP + x + 1];
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            if (keep && !overflow) dst[w + __popc(bal & lt_mask)] = ORBX_PACK(x + ox, y + oy, s);
+            if (i < cn) sc[y * SP + x + 1] = 0;                               // leave the score map all-zero (NMS is done)
+            w += __popc(bal);
+        }
+        if (lane == 0)
+            cell_rec[(size_t)cc.frame * plan->cells_per_frame + L.cell_base + cc.ci * L.nColsV + cj] =
+                make_uint2((uint32_t)gbase, overflow ? 0u : (uint32_t)count);
+        __syncwarp();
+        }   // cells of the strip
+        if (NB == 1 && nxt < total) { nc = fast_decode(plan, nxt, l0, l1, spf, first_strip); issue(nc, 0); }
         cur = nxt;
+        nxt = nxt2;
+        cc = nc;
+        if (NB == 2) b ^= 1;
     }
 }
 
@@ -1405,9 +1334,11 @@ void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nfr
 }
 
 size_t fast_smem_bytes(const OrbxPlan& hp) {
-    const size_t BH = (size_t)hp.fast_bh;
-    // tile + score map + kept bitmap + queue (worst case: every pixel of the detection area survives the pre-test)
-    return FB_TW * BH + FB_SP * BH + FB_BMW * 4 * BH + (BH - 6) * 236 * 2 + 256;
+    const size_t TB = ((size_t)hp.fast_bw * hp.fast_bh + 127) & ~(size_t)127;
+    const size_t SP = (size_t)((hp.max_cell_w + 2 + 3) & ~3);
+    const size_t SB = (SP * hp.fast_bh + 127) & ~(size_t)127;
+    const size_t QB = ((size_t)(hp.max_cell_w - 6) * (hp.max_cell_h - 6) * 2 + 127) & ~(size_t)127;
+    return ((size_t)hp.fast_nb * TB + SB + QB) * hp.fast_warps + 128;
 }
 
 // One {pitch, rows, frames} u8 tensor map per level over the pyramid slabs; box = bw x bh bytes of one frame.
@@ -1439,7 +1370,7 @@ static int build_tile_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, i
 
 // box = one strip of FAST cell windows
 int build_fast_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* out_maps) {
-    return build_tile_maps(hp, d_pyr, max_frames, FB_TW, hp.fast_bh, out_maps);
+    return build_tile_maps(hp, d_pyr, max_frames, hp.fast_bw, hp.fast_bh, out_maps);
 }
 
 // box = the raw window of one keypoint (describe_kernel)
@@ -1457,23 +1388,33 @@ cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* 
     static int per_sm_cache[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
+    typedef void (*fast_fn)(const FastMaps, const OrbxPlan*, int, int, int, int, uint32_t*, uint2*, int*, int*, int*);
+    fast_fn fn = hp.fast_bw == 64 ? fast_cells_kernel<64> : hp.fast_bw == 96 ? fast_cells_kernel<96> :
+                 hp.fast_bw == 128 ? fast_cells_kernel<128> : fast_cells_kernel<0>;
     if (smem != configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(fast_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+        fast_fn all[4] = {fast_cells_kernel<64>, fast_cells_kernel<96>, fast_cells_kernel<128>, fast_cells_kernel<0>};
+        for (int i = 0; i < 4; ++i) {
+            cudaError_t e = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
         configured[dev & 63] = smem;
         int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_band_kernel, FB_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, hp.fast_warps * 32, smem);
         per_sm_cache[dev & 63] = per_sm < 1 ? 1 : per_sm;
     }
-    const int units = (l1 < hp.nlevels ? hp.lv[l1].unit_base : hp.units_per_frame) - hp.lv[l0].unit_base;
-    long long blocks = (long long)nframes * units;
+    const int W = hp.fast_warps;
+    const int strips = (l1 < hp.nlevels ? hp.lv[l1].strip_base : hp.strips_per_frame) - hp.lv[l0].strip_base;
+    const long long total = (long long)nframes * strips;
+    long long blocks = (total + W - 1) / W;
     const long long cap = (long long)num_sms * per_sm_cache[dev & 63];
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     FastMaps fm;
     memcpy(&fm, maps, sizeof fm);
-    return launch_k(fast_band_kernel, dim3((unsigned)blocks), dim3(FB_THREADS), smem, st, fm, d_plan, frame0, nframes, l0, l1, cand,
-                    cell_rec, level_counts, work_counter, status);
+    const cudaError_t le = launch_k(fn, dim3((unsigned)blocks), dim3(W * 32), smem, st, fm, d_plan, frame0, nframes, l0, l1, cand,
+                                    cell_rec, level_counts, work_counter, status);
+    if (le != cudaSuccess) return le;
+    return cudaSuccess;
 }
 
 size_t octree_smem_bytes(const OrbxPlan& hp) {

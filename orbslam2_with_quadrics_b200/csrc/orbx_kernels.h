@@ -6,6 +6,7 @@
 
 #include "orbx_plan.h"
 
+#define ORBX_FAST_WARPS 8
 #define ORBX_OT_THREADS 1024
 #define ORBX_OT_KEYCAP 8192     // candidates of one level kept in shared memory by the octree kernel (6 bytes each)
 

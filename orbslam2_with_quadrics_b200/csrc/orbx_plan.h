@@ -26,9 +26,7 @@ struct OrbxLevel {
     int nColsV, nRowsV;       // cells that survive the skip rules (:794, :803)
     int wCell, hCell;
     int cell_base;            // first cell of this level inside a frame (cell_rec index)
-    int seg_cells, segs_x;    // FAST work units: segments of seg_cells cells of one cell row; units per cell row
-    int unit_base;            // first unit of this level inside a frame
-    int recip_wcell, recip_wcell1;   // ceil(65536 / wCell), ceil(65536 / (wCell + 1)): exact division of tile columns
+    int strip_base, strips_x; // FAST work items: strips of fast_nc cells; first item of the level, items per cell row
     int cand_off, cand_cap;   // this level's region in a frame's candidate buffers (entries)
     int quota;                // mnFeaturesPerLevel[l]
     int nIni;                 // root nodes of DistributeOctTree (:543)
@@ -51,8 +49,9 @@ struct OrbxPlan {
     int blur_tiles_per_frame;
     int node_cap;             // octree node capacity (max over levels)
     int max_cell_w, max_cell_h;   // largest FAST window (incl. the 6-px overlap)
-    int fast_bh;                  // rows of a FAST tile (TMA box 256 x fast_bh)
-    int units_per_frame;
+    int fast_bw, fast_bh;         // TMA box of a FAST tile (bw multiple of 16)
+    int fast_nc, fast_nb, fast_warps;   // cells per tile, tile buffers per warp (1 or 2), warps per CTA
+    int strips_per_frame;
     int ini_th, min_th;
     long long slab_bytes;     // one frame's pyramid slab
     float atan_p1, atan_p3, atan_p5, atan_p7;   // cv::fastAtan2 coefficients (float products)
