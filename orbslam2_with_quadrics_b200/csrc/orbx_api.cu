@@ -162,6 +162,51 @@ void build_taps(std::vector<OrbxTap>& out, int ssize, int dsize) {
     }
 }
 
+int reflect_clamp_host(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+}
+
+// Tables of pyr_resize8_kernel for level L (source level S): one OrbxCol8 per group of 8 plane columns and one row-tap
+// entry per PLANE row (the REFLECT_101 border of copyMakeBorder, :1122, folded into the index), both appended to the
+// tap buffer (8-byte units).  Needs L.xtab_off / L.ytab_off.
+void build_resize8_tables(std::vector<OrbxTap>& taps, const OrbxLevel& S, OrbxLevel& L) {
+    static_assert(sizeof(OrbxCol8) == 8 * sizeof(OrbxTap), "OrbxCol8 is 8 tap units");
+    while (taps.size() % 8) taps.push_back(OrbxTap{0, 0, 0});               // 64-byte alignment of the records
+    L.ngroups8 = (ORBX_XO + L.w + ORBX_EDGE - 8 + 7) / 8;
+    L.resize8_ok = 1;
+    std::vector<OrbxCol8> cols((size_t)L.ngroups8);
+    for (int g = 0; g < L.ngroups8; ++g) {
+        OrbxCol8& C = cols[g];
+        memset(&C, 0, sizeof C);
+        int ofs[8];
+        for (int j = 0; j < 8; ++j) {
+            const OrbxTap& t = taps[L.xtab_off + reflect_clamp_host(8 + 8 * g + j - ORBX_XO, L.w)];
+            ofs[j] = t.ofs;
+            C.coef[j] = (uint32_t)(uint16_t)t.c0 | ((uint32_t)(uint16_t)t.c1 << 16);
+        }
+        for (int hf = 0; hf < 2; ++hf) {
+            int mn = ofs[4 * hf];
+            for (int j = 1; j < 4; ++j) mn = ofs[4 * hf + j] < mn ? ofs[4 * hf + j] : mn;
+            C.base[hf] = mn & ~3;
+            C.sh |= (uint32_t)(8 * (mn & 3)) << (8 * hf);
+            for (int pr = 0; pr < 2; ++pr) {
+                const int o0 = ofs[4 * hf + 2 * pr] - mn, o1 = ofs[4 * hf + 2 * pr + 1] - mn;
+                if (o0 + 1 > 7 || o1 + 1 > 7) L.resize8_ok = 0;
+                C.sel[2 * hf + pr] = (uint32_t)(o0 & 7) | ((uint32_t)((o0 + 1) & 7) << 4) | ((uint32_t)(o1 & 7) << 8) |
+                                     ((uint32_t)((o1 + 1) & 7) << 12);
+            }
+        }
+    }
+    (void)S;
+    L.col8_off = (int)taps.size();
+    const OrbxTap* raw = reinterpret_cast<const OrbxTap*>(cols.data());
+    taps.insert(taps.end(), raw, raw + (size_t)L.ngroups8 * 8);
+    L.yrow_off = (int)taps.size();
+    for (int r = 0; r < L.rows; ++r) taps.push_back(taps[L.ytab_off + reflect_clamp_host(r - ORBX_EDGE, L.h)]);
+}
+
 void level_size(const orbx_handle* h, int w, int hgt, int l, int* lw, int* lh) {
     const float scale = h->inv_sf[l];                                  // (:1111-1112)
     *lw = (int)lrintf((float)w * scale);
@@ -246,6 +291,7 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
                 }
                 if (hi - (lo & ~3) > 7) L.resize_wide = 1;
             }
+            build_resize8_tables(*taps, P->lv[l - 1], L);
         }
         L.blur_tile_base = tiles;
         L.blur_tiles_x = (L.w + 127) / 128;

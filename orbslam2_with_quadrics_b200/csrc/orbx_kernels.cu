@@ -228,6 +228,97 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const OrbxPlan* __restr
     }
 }
 
+// pyr_resize8_kernel: the same arithmetic with 8 adjacent plane columns per lane (one 64-bit store per row) and every
+// column decision moved into a host-built OrbxCol8 record.  A half (4 pixels) reads 3 aligned source words; one funnel
+// shift pair leaves the 8 bytes from the half's smallest tap offset on in (U, V), a pixel PAIR's two source byte
+// pairs are one PRMT with a constant selector, a pixel's row sum one IDP.2A.  The two cached rows H0/H1 never move:
+// which of them is the upper row is tracked by their source row ids and only the two row weights swap.  The row-tap
+// table is indexed by PLANE row (border reflection folded in).  ~11 thread instructions per output pixel against 26.
+struct Row6 { uint32_t a0, a1, a2, b0, b1, b2; };
+
+__global__ void __launch_bounds__(128) pyr_resize8_kernel(const OrbxPlan* __restrict__ plan, int l, int RY,
+                                                          uint8_t* __restrict__ pyr, const OrbxTap* __restrict__ taps) {
+    ORBX_PDL_WAIT();
+    const OrbxLevel& L = plan->lv[l];
+    const OrbxLevel& S = plan->lv[l - 1];
+    const int g = blockIdx.x * 32 + (threadIdx.x & 31);                        // group of 8 plane columns from column 8 on
+    const int row0 = (blockIdx.y * 4 + (threadIdx.x >> 5)) * RY;              // first plane row of this warp
+    if (row0 >= L.rows || g >= L.ngroups8) return;
+    uint8_t* slab = pyr + (size_t)blockIdx.z * plan->slab_bytes;
+    const uint4* cgp = reinterpret_cast<const uint4*>(taps + L.col8_off) + 4 * g;
+    const uint4 c0 = __ldg(cgp), c1 = __ldg(cgp + 1), c2 = __ldg(cgp + 2), c3 = __ldg(cgp + 3);
+    const uint8_t* sbase = slab + S.plane_off + (size_t)ORBX_EDGE * S.pitch + ORBX_XO;     // source pixel (0, 0)
+    const uint8_t* plo = sbase + (int)c0.x;
+    const uint8_t* phi = sbase + (int)c0.y;
+    const uint32_t shl = c0.z & 31u, shh = (c0.z >> 8) & 31u;
+    const uint32_t sel0 = c1.x, sel1 = c1.y, sel2 = c1.z, sel3 = c1.w;
+    const uint32_t k0 = c2.x, k1 = c2.y, k2 = c2.z, k3 = c2.w, k4 = c3.x, k5 = c3.y, k6 = c3.z, k7 = c3.w;
+    const int spitch = S.pitch;
+    auto load_row = [&](int sy) -> Row6 {
+        const unsigned o = (unsigned)(sy * spitch);
+        const uint32_t* pa = reinterpret_cast<const uint32_t*>(plo + o);
+        const uint32_t* pb = reinterpret_cast<const uint32_t*>(phi + o);
+        Row6 q;
+        q.a0 = pa[0]; q.a1 = pa[1]; q.a2 = pa[2];
+        q.b0 = pb[0]; q.b1 = pb[1]; q.b2 = pb[2];
+        return q;
+    };
+    auto pass = [&](const Row6& q, uint32_t* H) {                              // H[j] = (S[sx]*a0 + S[sx+1]*a1) >> 4
+        const uint32_t U = __funnelshift_r(q.a0, q.a1, shl), V = __funnelshift_r(q.a1, q.a2, shl);
+        const uint32_t X = __funnelshift_r(q.b0, q.b1, shh), Y = __funnelshift_r(q.b1, q.b2, shh);
+        const uint32_t p0 = __byte_perm(U, V, sel0), p1 = __byte_perm(U, V, sel1);
+        const uint32_t p2 = __byte_perm(X, Y, sel2), p3 = __byte_perm(X, Y, sel3);
+        H[0] = __dp2a_lo(k0, p0, 0u) >> 4; H[1] = __dp2a_hi(k1, p0, 0u) >> 4;
+        H[2] = __dp2a_lo(k2, p1, 0u) >> 4; H[3] = __dp2a_hi(k3, p1, 0u) >> 4;
+        H[4] = __dp2a_lo(k4, p2, 0u) >> 4; H[5] = __dp2a_hi(k5, p2, 0u) >> 4;
+        H[6] = __dp2a_lo(k6, p3, 0u) >> 4; H[7] = __dp2a_hi(k7, p3, 0u) >> 4;
+    };
+    const int nrow = min(RY, L.rows - row0);
+    const int hs1 = S.h - 1;
+    const uint2* yt = reinterpret_cast<const uint2*>(taps + L.yrow_off + row0);     // (source row, c0 | c1 << 16)
+    uint8_t* dst = slab + L.plane_off + (size_t)row0 * L.pitch + 8 + 8 * g;
+    uint32_t H0[8], H1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) H0[j] = H1[j] = 0;
+    int id0 = -1, id1 = -1;
+    uint2 ty = __ldg(yt);
+    int pre_id = min((int)ty.x + 1, hs1);                                     // speculative: the lower row of the first output row
+    Row6 pre = load_row(pre_id);
+    for (int i = 0; i < nrow; ++i, dst += L.pitch) {
+        // one output row ahead: its tap entry and (speculatively) its lower source row
+        const uint2 tyn = __ldg(yt + min(i + 1, nrow - 1));
+        const int pren_id = min((int)tyn.x + 1, hs1);
+        const Row6 pren = load_row(pren_id);
+        const int r0 = (int)ty.x, r1 = min(r0 + 1, hs1);
+        uint32_t b0, b1;                                                      // row weights of H0, H1, << 16
+        if (r0 == id1) {                                                      // the usual step: last row's lower row is the upper one
+            if (r1 != r0 && id0 != r1) {
+                if (pre_id == r1) pass(pre, H0); else pass(load_row(r1), H0);
+                id0 = r1;
+            }
+            b0 = ty.y & 0xffff0000u; b1 = ty.y << 16;
+        } else {
+            if (r0 != id0) { pass(load_row(r0), H0); id0 = r0; }
+            if (r1 != r0 && id1 != r1) {
+                if (pre_id == r1) pass(pre, H1); else pass(load_row(r1), H1);
+                id1 = r1;
+            }
+            b0 = ty.y << 16; b1 = ty.y & 0xffff0000u;
+        }
+        // when the source row is clamped (r1 == r0) the second weight is 0, so a stale lower row is harmless
+        uint32_t s[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = __umulhi(b0, H0[j]) + __umulhi(b1, H1[j]);     // <= 1020: weights sum to 2048
+        // (s + 2) >> 2 for two pixels at a time (10-bit fields), then one PRMT per four pixels
+        const uint32_t t01 = (s[0] + (s[1] << 16) + 0x00020002u) >> 2, t23 = (s[2] + (s[3] << 16) + 0x00020002u) >> 2;
+        const uint32_t t45 = (s[4] + (s[5] << 16) + 0x00020002u) >> 2, t67 = (s[6] + (s[7] << 16) + 0x00020002u) >> 2;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(__byte_perm(t01, t23, 0x6420), __byte_perm(t45, t67, 0x6420));
+        ty = tyn;
+        pre = pren;
+        pre_id = pren_id;
+    }
+}
+
 // =====================================================================================
 // FAST-9/16 per 30-px cell (cv::FAST(window, t, true)), one warp per cell,
 // persistent warps with a dynamic work counter.
@@ -1313,6 +1404,11 @@ __global__ void __launch_bounds__(128) blur_kernel(const OrbxPlan* __restrict__ 
 // =====================================================================================
 // launch wrappers (called from orbx_api.cu)
 // =====================================================================================
+static bool force_resize4() {          // ORBX_RESIZE4=1: A/B switch back to the 4-pixel-per-lane resize kernel
+    static const bool v = getenv("ORBX_RESIZE4") != nullptr;
+    return v;
+}
+
 void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nframes, int num_sms, const uint8_t* imgs,
                       size_t img_pitch, size_t img_frame_stride, uint8_t* pyr, const OrbxTap* taps,
                       cudaStream_t st) {
@@ -1323,6 +1419,12 @@ void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nfr
         const int cols16 = (ORBX_XO + L.w + ORBX_EDGE + 15) / 16;          // 16-byte chunks from plane column 0
         dim3 block(32, 8), grid((cols16 + 31) / 32, (L.rows + 7) / 8, nframes);
         launch_k(pyr_level0_kernel, grid, block, 0, st, d_plan, imgs, img_pitch, img_frame_stride, aligned16, pyr);
+    } else if (L.resize8_ok && !force_resize4()) {
+        const int gx = (L.ngroups8 + 31) / 32;
+        int RY = PYR_RY;
+        while (RY > 4 && (long long)gx * ((L.rows + RY - 1) / RY) * nframes < (long long)num_sms * 32) RY >>= 1;
+        dim3 grid(gx, (L.rows + 4 * RY - 1) / (4 * RY), nframes);
+        launch_k(pyr_resize8_kernel, grid, dim3(128), 0, st, d_plan, l, RY, pyr, taps);
     } else {
         // rows per warp: long strips reuse row passes (1 + 1/RY... per row) but small levels need warps
         int RY = PYR_RY;

@@ -38,6 +38,9 @@ struct OrbxLevel {
     int blur_tile_base;       // first blur tile of this level inside a frame
     int blur_tiles_x;
     int resize_wide;          // 1: the 4 pixels of a lane span more than two source words (large scale factors)
+    int col8_off, ngroups8;   // pyr_resize8_kernel: this level's OrbxCol8 records (offset in OrbxTap units), groups of 8 plane columns
+    int yrow_off;             // per PLANE row row-tap entries (border reflection already applied), OrbxTap units
+    int resize8_ok;           // 0: a half-group's source window exceeds 8 bytes (scale factor > 2): 4-pixel kernel instead
 };
 
 struct OrbxPlan {
@@ -58,6 +61,18 @@ struct OrbxPlan {
     float factor_pi;          // (float)(CV_PI/180.f) (:107)
     int umax[16];             // (:454-469)
     OrbxLevel lv[ORBX_MAXL];
+};
+
+// Column plan of one lane of pyr_resize8_kernel: 8 adjacent plane columns (from plane column 8 + 8 * group), as two
+// halves of 4.  Each half reads 3 aligned source words starting `base` bytes after source pixel x = 0; shifting by `sh`
+// bits leaves the 8 source bytes from the half's smallest tap offset on in two registers (U, V); a pixel pair's two
+// source byte pairs are then ONE PRMT (sel) and each pixel's row sum ONE IDP.2A with its packed weights (coef).
+struct OrbxCol8 {
+    int base[2];              // byte offsets (multiples of 4) of the halves' first source word
+    uint32_t sh;              // bit shift of half 0 | half 1 << 8 (0, 8, 16 or 24)
+    uint32_t pad;
+    uint32_t sel[4];          // PRMT selectors of pixel pairs (0,1) (2,3) | (4,5) (6,7)
+    uint32_t coef[8];         // c0 | c1 << 16 (11-bit fixed point weights, App. A-1)
 };
 
 // One bilinear tap pair of cv::resize INTER_LINEAR 8U
