@@ -208,10 +208,9 @@ def own_arm(args):
     # ---- synthetic input: this rank serves camera stream `rank` (no cross-rank data dependency)
     if nimg == 1:
         imgs = make_frames(name, rank, nimgs)
-    else:              # stereo: left/right streams interleaved, pairs kept on this GPU
-        left = make_frames(name, rank * 2, B)
-        right = make_frames(name, rank * 2 + 1, B)
-        imgs = [x for pair in zip(left, right) for x in pair]
+    else:              # stereo: rectified synthetic pairs (right = left shifted by band-wise disparities), pairs kept on this GPU
+        base = [fr.stereo_pair(w, h, fr.stream_seed(rank, i)) for i in range(min(B, DISTINCT_FRAMES))]
+        imgs = [x for i in range(B) for x in base[i % len(base)]]
     pitch = (w + 15) // 16 * 16
     host = torch.zeros((nimgs, h, pitch), dtype=torch.uint8).pin_memory()
     hnp = host.numpy()
@@ -219,7 +218,11 @@ def own_arm(args):
         hnp[i, :, :w] = im
     dev = host.cuda(non_blocking=False)
 
-    need_pyr = nimg == 2                 # only ComputeStereoMatches reads mvImagePyramid (src/Frame.cc:563-580)
+    # only ComputeStereoMatches reads mvImagePyramid (src/Frame.cc:563-580): with the matcher on the device
+    # (orbx_stereo_match, the default) the pyramids stay in HBM; --stereo-match host ships them to the CPU consumer
+    stereo_dev = nimg == 2 and args.stereo_match == "device"
+    need_pyr = nimg == 2 and not stereo_dev
+    mbf, mb = (386.1448, 0.5371657) if name == "stereo_kitti" else (47.90639384423901, 0.11007784)   # KITTI00-02.yaml / EuRoC.yaml
     ex = ORBextractor(nf, sf, nl, it, mt, device=local, max_batch=nimgs, download_pyramid=False)
     stream = torch.cuda.ExternalStream(ex.stream, device=torch.device("cuda", local))
 
@@ -275,11 +278,19 @@ def own_arm(args):
         strides_t = (C.c_size_t * n_t)(*[pitch] * n_t)
         call.append((exs2[t]._h, n_t, ptrs_t, strides_t, (_capi.OrbxResult * n_t)()))
     ptrs, strides = call[0][2], call[0][3]
+    st_args = []
+    for t in range(T):
+        np_t = call[t][1] // 2
+        st_args.append(((C.c_int * max(np_t, 1))(*range(0, 2 * np_t, 2)), (C.c_int * max(np_t, 1))(*range(1, 2 * np_t, 2)),
+                        (_capi.OrbxStereoResult * max(np_t, 1))(), np_t))
 
     def worker(t, steps):
         hd, n_t, p_t, s_t, r_t = call[t]
+        lf, rf, sres, np_t = st_args[t]
         for _ in range(steps):
             _capi.check(capi.orbx_extract_batch(hd, n_t, p_t, w, h, s_t, r_t), hd)
+            if stereo_dev:       # Frame::ComputeStereoMatches on the device-resident results; mvuRight / mvDepth come back
+                _capi.check(capi.orbx_stereo_match(hd, hd, np_t, lf, rf, mbf, mb, sres), hd)
 
     def run_threads(steps):
         if T == 1:
@@ -310,6 +321,8 @@ def own_arm(args):
     kept_cap = sum(q + 4 * int(np.floor(float(np.float32(lw - 32) / np.float32(lh - 32)) + 0.5)) + 8
                    for q, (lw, lh) in zip(geo.level_quotas(nf, sf, nl), geo.level_sizes(w, h, sf, nl)))
     d2h = nimgs * kept_cap * 60 + 4 * (nimgs * (3 * nl + 1) + 8) + (nimgs * slab if need_pyr else 0)   # what the library copies
+    if stereo_dev:
+        d2h += nimgs * kept_cap * 8 + 4 * (nimgs * (3 * nl + 1) + 8)     # mvuRight + mvDepth of the batch, counters again
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-frame latency through the C ABI, batch = 1 frame (rank 0 reports)
@@ -321,16 +334,20 @@ def own_arm(args):
         for i in range(5):
             _capi.check(capi.orbx_extract_batch(ex1._h, nimg, ptrs, w, h, strides, r1), ex1._h)
         ts = []
+        lf1, rf1, sres1 = (C.c_int * 1)(0), (C.c_int * 1)(1), (_capi.OrbxStereoResult * 1)()
         for i in range(args.latency_frames):
             k0 = (i * nimg) % call[0][1]
             pp = C.cast(C.byref(ptrs, k0 * psz), C.POINTER(C.c_void_p))
             t0 = time.perf_counter()
             rc = capi.orbx_extract_batch(ex1._h, nimg, pp, w, h, strides, r1)
+            if stereo_dev and rc == 0:
+                rc = capi.orbx_stereo_match(ex1._h, ex1._h, 1, lf1, rf1, mbf, mb, sres1)
             ts.append(time.perf_counter() - t0)
             _capi.check(rc, ex1._h)
         ts = np.asarray(ts) * 1e3
         lat = {"p50": float(np.percentile(ts, 50)), "p99": float(np.percentile(ts, 99)), "frames": len(ts),
-               "batch": 1, "path": "C ABI, pinned host in, keypoints+descriptors out" + (", pyramid D2H" if need_pyr else "")}
+               "batch": 1, "path": "C ABI, pinned host in, keypoints+descriptors out" + (", pyramid D2H" if need_pyr else "") +
+                       (", stereo match on device, mvuRight+mvDepth out" if stereo_dev else "")}
         ex1.close()
 
     if world > 1:
@@ -381,6 +398,7 @@ def own_arm(args):
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nimgs * w * h, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "pyramid_d2h": need_pyr, "host_threads": T,
+                    "stereo_match": ("device (orbx_stereo_match inside the timed region)" if stereo_dev else "host consumer (pyramid D2H)") if nimg == 2 else None,
                     "call": "orbx_extract_batch (C ABI), %d frames per call per thread, pinned host frames" % (B // T)},
             "latency_ms": lat, "gpu_launches": int(launches), "clocks": clocks}
     print(json.dumps(line))
@@ -398,6 +416,9 @@ def main():
     ap.add_argument("--latency-frames", type=int, default=200)
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads (one handle each) in the e2e measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stereo-match", default="device", choices=["device", "host"],
+                    help="stereo configs: run Frame::ComputeStereoMatches on the GPU (pyramids stay in HBM) or leave it to a "
+                         "host consumer (pyramid D2H inside the timed region)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

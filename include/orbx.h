@@ -101,6 +101,27 @@ ORBX_API int orbx_extract_device(orbx_handle* h, int n, const uint8_t* d_imgs, i
 /* Copies the results of the last orbx_extract_device to host and waits for them. */
 ORBX_API int orbx_fetch_results(orbx_handle* h, int n, orbx_result* results);
 
+/* ---- Frame::ComputeStereoMatches (reference src/Frame.cc:466-640) on the device-resident results of a left and a
+ * right extraction: the immediate consumer of the path in the stereo configurations.  Running it here means the
+ * pyramids never have to leave HBM (download_pyramid = 0).  Pair i matches frame left_frames[i] of the last extract on
+ * `left` against frame right_frames[i] of the last extract on `right` (NULL index arrays mean i); `left` and `right`
+ * may be the same handle (a batch that holds both eyes).  Both handles must share constructor arguments, image size
+ * and device.  mbf = baseline * fx, mb = baseline (Frame::mbf, Frame::mb, src/Frame.cc:97-98).  Thresholds are the
+ * reference's ORBmatcher::TH_HIGH / TH_LOW (src/ORBmatcher.cc:37-38).
+ * Result: mvuRight / mvDepth, one float per LEFT keypoint in keypoint order, -1 where there is no match; pinned host
+ * memory owned by `left`, valid until its next stereo call. */
+typedef struct orbx_stereo_result {
+    int n;                 /* left keypoints */
+    const float* u_right;  /* mvuRight */
+    const float* depth;    /* mvDepth  */
+} orbx_stereo_result;
+ORBX_API int orbx_stereo_match(orbx_handle* left, orbx_handle* right, int npairs, const int* left_frames,
+                               const int* right_frames, float mbf, float mb, orbx_stereo_result* results);
+/* The same split in two for device-side timing: enqueue only / copy back and wait. */
+ORBX_API int orbx_stereo_match_device(orbx_handle* left, orbx_handle* right, int npairs, const int* left_frames,
+                                      const int* right_frames, float mbf, float mb);
+ORBX_API int orbx_stereo_fetch(orbx_handle* left, int npairs, const int* left_frames, orbx_stereo_result* results);
+
 /* Pinned host buffers callers may fill with frames so that H2D copies are asynchronous DMA. */
 ORBX_API int orbx_alloc_host(size_t bytes, void** out);
 ORBX_API int orbx_free_host(void* p);

@@ -1,0 +1,29 @@
+#!/bin/sh
+# Builds oracle/_ref/libstereoref.so: the reference's OWN lines of Frame::ComputeStereoMatches and
+# ORBmatcher::DescriptorDistance, taken at build time from where they lie under $REF (never copied into this
+# repo: the generated translation unit lives in a temporary directory and only the .so is kept), compiled against
+# oracle/shim_stereo/stereo_shim.h.  TEST INFRASTRUCTURE only.
+set -e
+REF=${REF:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+OUT=$HERE/_ref
+F=$REF/src/Frame.cc
+M=$REF/src/ORBmatcher.cc
+# the line ranges are pinned to the reference revision surveyed in SURVEY.md; refuse to build from anything else
+sed -n '466p' "$F" | grep -q 'void Frame::ComputeStereoMatches()' || { echo "Frame.cc:466 is not ComputeStereoMatches"; exit 1; }
+sed -n '640p' "$F" | grep -q '^}' || { echo "Frame.cc:640 is not the end of ComputeStereoMatches"; exit 1; }
+sed -n '1647p' "$M" | grep -q 'int ORBmatcher::DescriptorDistance' || { echo "ORBmatcher.cc:1647 is not DescriptorDistance"; exit 1; }
+TMP=$(mktemp -d)
+trap 'rm -rf "$TMP"' EXIT
+{
+  echo '#include "stereo_shim.h"'
+  echo 'namespace ORB_SLAM2 {'
+  sed -n '37,39p' "$M"
+  sed -n '1647,1663p' "$M"
+  sed -n '466,640p' "$F"
+  echo '}'
+} > "$TMP/stereo_ref_gen.cpp"
+mkdir -p "$OUT"
+${CXX:-g++} -std=c++11 -O2 -march=x86-64-v2 -ffp-contract=off -fPIC -shared -w -I"$HERE/shim_stereo" \
+    "$TMP/stereo_ref_gen.cpp" "$HERE/stereo_ref_driver.cpp" -o "$OUT/libstereoref.so"
+echo "$OUT/libstereoref.so"

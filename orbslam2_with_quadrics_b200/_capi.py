@@ -22,6 +22,7 @@ SYMBOLS = [
     "orbx_get_levels", "orbx_get_scale_factor", "orbx_level_quotas", "orbx_level_sizes", "orbx_stage_dump",
     "orbx_stream", "orbx_synchronize", "orbx_stage_timing_enable", "orbx_stage_timing_read",
     "orbx_launch_count", "orbx_algorithmic_bytes", "orbx_strerror", "orbx_last_cuda_error", "orbx_version",
+    "orbx_stereo_match", "orbx_stereo_match_device", "orbx_stereo_fetch",
 ]
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
@@ -37,6 +38,10 @@ class OrbxConfig(C.Structure):
 
 class OrbxResult(C.Structure):
     _fields_ = [("n", C.c_int), ("status", C.c_int), ("kps", C.c_void_p), ("desc", C.c_void_p)]
+
+
+class OrbxStereoResult(C.Structure):
+    _fields_ = [("n", C.c_int), ("u_right", C.c_void_p), ("depth", C.c_void_p)]
 
 
 class OrbxError(RuntimeError):
@@ -90,6 +95,9 @@ def lib():
     L.orbx_last_cuda_error.argtypes = [vp]
     L.orbx_last_cuda_error.restype = C.c_char_p
     L.orbx_version.restype = C.c_char_p
+    L.orbx_stereo_match.argtypes = [vp, vp, i, C.POINTER(i), C.POINTER(i), C.c_float, C.c_float, C.POINTER(OrbxStereoResult)]
+    L.orbx_stereo_match_device.argtypes = [vp, vp, i, C.POINTER(i), C.POINTER(i), C.c_float, C.c_float]
+    L.orbx_stereo_fetch.argtypes = [vp, i, C.POINTER(i), C.POINTER(OrbxStereoResult)]
     _lib = L
     return L
 

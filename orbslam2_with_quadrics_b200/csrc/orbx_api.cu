@@ -68,6 +68,12 @@ struct orbx_handle {
     uint8_t* h_out_desc;
     uint8_t* h_pyr;
     uint8_t* h_input;
+    // stereo matcher (orbx_stereo_match; allocated on first use, owned by the LEFT handle)
+    float *d_st_u, *d_st_depth, *h_st;        // h_st: [u_right B*kpf][depth B*kpf]
+    int *d_st_sad, *d_st_pairs, *h_st_pairs;
+    int st_right_cap, st_pairs_n;
+    uint32_t* d_st_bands;     // row bands of the RIGHT handle's keypoints, indexed like its keypoint records
+    cudaEvent_t ev_stereo;
     int last_n;
     bool pyramid_valid;
 
@@ -350,6 +356,9 @@ void free_geometry(orbx_handle* h) {
     cudaFree(h->d_out_desc);
     cudaFreeHost(h->h_counters); cudaFreeHost(h->h_out_kp); cudaFreeHost(h->h_out_desc); cudaFreeHost(h->h_pyr);
     cudaFreeHost(h->h_input);
+    cudaFree(h->d_st_u); cudaFree(h->d_st_depth); cudaFree(h->d_st_sad); cudaFree(h->d_st_pairs); cudaFree(h->d_st_bands); h->d_st_bands = 0;
+    cudaFreeHost(h->h_st); cudaFreeHost(h->h_st_pairs);
+    h->d_st_u = h->d_st_depth = h->h_st = 0; h->d_st_sad = h->d_st_pairs = h->h_st_pairs = 0;
     h->d_plan = 0; h->d_taps = 0; h->d_input = h->d_pyr = h->d_blur = 0;
     h->d_cand = h->d_cand_sorted = h->d_kept = 0; h->d_key_node = 0; h->d_cell_rec = 0; h->d_counters = 0;
     h->d_angles = 0; h->d_out_kp = 0; h->d_out_desc = 0;
@@ -596,6 +605,7 @@ int orbx_create(const orbx_config* cfg, orbx_handle** out) {
     h->d_cand = h->d_cand_sorted = h->d_kept = 0; h->d_key_node = 0; h->d_cell_rec = 0; h->d_counters = 0;
     h->d_angles = 0; h->d_out_kp = 0; h->d_out_desc = 0;
     h->h_counters = 0; h->h_out_kp = 0; h->h_out_desc = 0; h->h_pyr = 0; h->h_input = 0;
+    h->d_st_u = h->d_st_depth = h->h_st = 0; h->d_st_sad = h->d_st_pairs = h->h_st_pairs = 0; h->d_st_bands = 0;
     h->last_n = 0; h->pyramid_valid = false;
     h->timing = false; h->ev_created = false; h->ev_head = 0; h->ev_pending = 0;
     memset(h->stage_ms, 0, sizeof h->stage_ms);
@@ -623,6 +633,7 @@ int orbx_create(const orbx_config* cfg, orbx_handle** out) {
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fast_low[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_clear, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_stereo, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking);
     for (int i = 0; i < kMaxChunks && e == cudaSuccess; ++i) {
@@ -653,6 +664,7 @@ int orbx_destroy(orbx_handle* h) {
             for (int s = 0; s <= ST_COUNT; ++s) cudaEventDestroy(h->ev[i][s]);
     for (int i = 0; i < kMaxChunks; ++i) { cudaEventDestroy(h->ev_h2d[i]); cudaEventDestroy(h->ev_done[i]); }
     cudaEventDestroy(h->ev_clear);
+    cudaEventDestroy(h->ev_stereo);
     for (int i = 0; i < 4; ++i) {
         cudaEventDestroy(h->ev_low[i]);
         cudaEventDestroy(h->ev_fast_low[i]); cudaEventDestroy(h->ev_join[i]); cudaStreamDestroy(h->aux[i]);
@@ -773,6 +785,101 @@ int orbx_extract(orbx_handle* h, const uint8_t* img, int width, int height, size
     const uint8_t* imgs[1] = {img};
     const size_t strides[1] = {stride};
     return orbx_extract_batch(h, 1, imgs, width, height, strides, result);
+}
+
+
+namespace {
+int stereo_enqueue(orbx_handle* L, orbx_handle* R, int npairs, const int* left_frames, const int* right_frames, float mbf,
+                   float mb) {
+    if (!L || !R || npairs < 1 || npairs > L->cfg.max_batch || !L->have_plan || !R->have_plan) return ORBX_ERR_BAD_ARGS;
+    if (!(mb > 0.f) || !(mbf > 0.f)) return ORBX_ERR_BAD_ARGS;
+    const OrbxPlan& P = L->plan;
+    // both eyes must have been extracted with the same constructor arguments and image size on the same device
+    if (L->cfg.device != R->cfg.device || R->plan.width != P.width || R->plan.height != P.height ||
+        R->plan.nlevels != P.nlevels || R->plan.kept_per_frame != P.kept_per_frame || R->plan.slab_bytes != P.slab_bytes ||
+        R->cfg.scale_factor != L->cfg.scale_factor)
+        return ORBX_ERR_BAD_ARGS;
+    if (L->d_st_u && R->cfg.max_batch > L->st_right_cap) return ORBX_ERR_BAD_ARGS;   // bands buffer was sized for a smaller right handle
+    for (int i = 0; i < npairs; ++i) {
+        const int fl = left_frames ? left_frames[i] : i, fr = right_frames ? right_frames[i] : i;
+        if (fl < 0 || fl >= L->last_n || fr < 0 || fr >= R->last_n) return ORBX_ERR_BAD_ARGS;
+        for (int k = 0; k < i; ++k)            // results are stored per left frame: one pair per left frame and call
+            if ((left_frames ? left_frames[k] : k) == fl) return ORBX_ERR_BAD_ARGS;
+    }
+    CK(L, cudaSetDevice(L->cfg.device));
+    const size_t B = (size_t)L->cfg.max_batch, kpf = (size_t)P.kept_per_frame;
+    if (!L->d_st_u) {
+        CK(L, cudaMalloc(&L->d_st_u, B * kpf * 4));
+        CK(L, cudaMalloc(&L->d_st_depth, B * kpf * 4));
+        CK(L, cudaMalloc(&L->d_st_sad, B * kpf * 4));
+        CK(L, cudaMalloc(&L->d_st_pairs, B * 2 * sizeof(int)));
+        CK(L, cudaMalloc(&L->d_st_bands, (size_t)R->cfg.max_batch * kpf * 4));
+        L->st_right_cap = R->cfg.max_batch;
+        L->st_pairs_n = 0;
+        CK(L, cudaMallocHost(&L->h_st, 2 * B * kpf * 4));
+        CK(L, cudaMallocHost(&L->h_st_pairs, B * 2 * sizeof(int)));
+    }
+    cudaStream_t st = L->stream;
+    // the pair list rarely changes between calls (same batch layout every time): upload it only when it does
+    bool same = L->st_pairs_n == npairs;
+    for (int i = 0; i < npairs && same; ++i)
+        same = L->h_st_pairs[2 * i] == (left_frames ? left_frames[i] : i) && L->h_st_pairs[2 * i + 1] == (right_frames ? right_frames[i] : i);
+    if (!same) {
+        CK(L, cudaStreamSynchronize(st));                                  // a previous upload from h_st_pairs is complete
+        for (int i = 0; i < npairs; ++i) {
+            L->h_st_pairs[2 * i] = left_frames ? left_frames[i] : i;
+            L->h_st_pairs[2 * i + 1] = right_frames ? right_frames[i] : i;
+        }
+        L->st_pairs_n = npairs;
+        CK(L, cudaMemcpyAsync(L->d_st_pairs, L->h_st_pairs, (size_t)npairs * 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    if (R != L) {                                                          // the right eye's extraction may still be in flight
+        CK(L, cudaEventRecord(L->ev_stereo, R->stream));
+        CK(L, cudaStreamWaitEvent(st, L->ev_stereo, 0));
+    }
+    CK(L, orbx::launch_stereo(L->d_plan, P, L->num_sms, L->d_pyr, L->d_out_kp, L->d_out_desc, L->d_kept_counts(), R->d_pyr,
+                              R->d_out_kp, R->d_out_desc, R->d_kept_counts(), L->d_st_pairs, npairs, mbf, mb, L->d_st_u,
+                              L->d_st_depth, L->d_st_sad, L->d_st_bands, st));
+    L->launches += 3;
+    return ORBX_OK;
+}
+}  // namespace
+
+int orbx_stereo_match_device(orbx_handle* left, orbx_handle* right, int npairs, const int* left_frames, const int* right_frames,
+                             float mbf, float mb) {
+    return stereo_enqueue(left, right, npairs, left_frames, right_frames, mbf, mb);
+}
+
+int orbx_stereo_fetch(orbx_handle* left, int npairs, const int* left_frames, orbx_stereo_result* results) {
+    if (!left || !results || npairs < 1 || !left->d_st_u || npairs > left->cfg.max_batch) return ORBX_ERR_BAD_ARGS;
+    orbx_handle* h = left;
+    CK(h, cudaSetDevice(h->cfg.device));
+    const OrbxPlan& P = h->plan;
+    const size_t B = (size_t)h->cfg.max_batch, kpf = (size_t)P.kept_per_frame;
+    const size_t n = (size_t)h->last_n;
+    cudaStream_t st = h->stream;
+    CK(h, cudaMemcpyAsync(h->h_st, h->d_st_u, n * kpf * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h->h_st + B * kpf, h->d_st_depth, n * kpf * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int) * h->counters_count(), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    for (int i = 0; i < npairs; ++i) {
+        const int f = left_frames ? left_frames[i] : i;
+        if (f < 0 || f >= h->last_n) return ORBX_ERR_BAD_ARGS;
+        int total = 0;
+        for (int l = 0; l < P.nlevels; ++l) total += h->h_kept_counts()[f * P.nlevels + l];
+        results[i].n = total;
+        results[i].u_right = h->h_st + (size_t)f * kpf;
+        results[i].depth = h->h_st + B * kpf + (size_t)f * kpf;
+    }
+    return ORBX_OK;
+}
+
+int orbx_stereo_match(orbx_handle* left, orbx_handle* right, int npairs, const int* left_frames, const int* right_frames,
+                      float mbf, float mb, orbx_stereo_result* results) {
+    if (!results) return ORBX_ERR_BAD_ARGS;
+    const int rc = stereo_enqueue(left, right, npairs, left_frames, right_frames, mbf, mb);
+    if (rc != ORBX_OK) return rc;
+    return orbx_stereo_fetch(left, npairs, left_frames, results);
 }
 
 int orbx_alloc_host(size_t bytes, void** out) {

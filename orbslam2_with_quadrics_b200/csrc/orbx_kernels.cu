@@ -1402,6 +1402,202 @@ __global__ void __launch_bounds__(128) blur_kernel(const OrbxPlan* __restrict__ 
 }
 
 // =====================================================================================
+// Frame::ComputeStereoMatches (reference src/Frame.cc:466-640) on the device-resident
+// outputs of a left and a right extraction (the immediate consumer
+// of the path in the stereo configurations; doing it here removes the pyramid D2H).
+//
+// stereo_match_kernel, one warp per left keypoint:
+//   1. best right keypoint (:506-546): every right keypoint whose row band floor(y - r) ..
+//      ceil(y + r), r = 2 * scale[octave] (:486-492) holds row (size_t)vL, with octave within
+//      +-1 and uR in [uL - maxD, uL] is compared by Hamming distance (ORBmatcher.cc:1647-1663);
+//      lanes stride over the right keypoints, the warp minimum of (dist << 16 | iR) is the
+//      reference's "first strictly smaller wins" in iR order;
+//   2. 11x11 SAD over incR = -5..5 on the keypoint's pyramid level (:552-596), each window
+//      minus its own centre -- integers, so the reference's float L1 norm is exact;
+//   3. parabola, re-scaling, disparity test (:598-626) in float32 without contraction.
+// stereo_filter_kernel, one CTA per pair: the (size/2)-th smallest accepted SAD by rank
+// counting, thDist = 1.5f * 1.4f * median, matches with SAD >= thDist dropped (:629-640).
+// =====================================================================================
+struct StereoSide {
+    const uint8_t* pyr;        // frame 0 of the handle's pyramid slabs
+    const float* kp;           // frame 0 of the 7-float keypoint records
+    const uint8_t* desc;
+    const int* kept_counts;    // [frame][level]
+};
+
+// Row band of every right keypoint (:486-492) as minr | maxr << 16, so the candidate scan rejects on one word.
+__global__ void __launch_bounds__(256)
+stereo_bands_kernel(const OrbxPlan* __restrict__ plan, StereoSide SR, const int* __restrict__ pairs, int npairs,
+                    uint32_t* __restrict__ bands) {
+    const int kpf = plan->kept_per_frame, nl = plan->nlevels;
+    const unsigned total = (unsigned)npairs * (unsigned)kpf;
+    for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
+        const int p = (int)(it / (unsigned)kpf), j = (int)(it - (unsigned)p * (unsigned)kpf);
+        const int fR = pairs[2 * p + 1];
+        int Nr = 0;
+        for (int l = 0; l < nl; ++l) Nr += SR.kept_counts[fR * nl + l];
+        if (j >= Nr) continue;
+        const float* kr = SR.kp + ((size_t)fR * kpf + j) * 7;
+        const float yr = kr[1];
+        const float r = __fmul_rn(2.0f, plan->lv[__float_as_int(kr[5])].scale);
+        const int maxr = (int)ceilf(__fadd_rn(yr, r)), minr = max((int)floorf(__fsub_rn(yr, r)), 0);
+        bands[(size_t)fR * kpf + j] = (uint32_t)minr | ((uint32_t)min(maxr, 0xffff) << 16);
+    }
+}
+
+#define ST_WARPS 8
+__global__ void __launch_bounds__(ST_WARPS * 32)
+stereo_match_kernel(const OrbxPlan* __restrict__ plan, StereoSide SL, StereoSide SR, const int* __restrict__ pairs, int npairs,
+                    const uint32_t* __restrict__ bands, float mbf, float mb, float* __restrict__ u_right,
+                    float* __restrict__ depth, int* __restrict__ sad_out) {
+    __shared__ int s_sad[ST_WARPS][12];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kpf = plan->kept_per_frame, nl = plan->nlevels;
+    const unsigned total = (unsigned)npairs * (unsigned)kpf;
+    const float maxD = __fdiv_rn(mbf, mb);                                 // (:499-501)
+    for (unsigned it = blockIdx.x * ST_WARPS + warp; it < total; it += gridDim.x * ST_WARPS) {
+        const int p = (int)(it / (unsigned)kpf), iL = (int)(it - (unsigned)p * (unsigned)kpf);
+        const int fL = pairs[2 * p], fR = pairs[2 * p + 1];
+        int N = 0, Nr = 0;
+        for (int l = 0; l < nl; ++l) { N += SL.kept_counts[fL * nl + l]; Nr += SR.kept_counts[fR * nl + l]; }
+        if (iL >= N) continue;
+        const size_t oL = (size_t)fL * kpf + iL;
+        const float* kl = SL.kp + oL * 7;
+        const float uL = kl[0], vL = kl[1];
+        const int levelL = __float_as_int(kl[5]);
+        float res_u = -1.f, res_d = -1.f;
+        int res_sad = -1;
+        const int row = (int)vL;                                           // vRowIndices[vL] (:512)
+        const float minU = __fsub_rn(uL, maxD), maxU = uL;                 // minD = 0 (:517-518)
+        uint32_t best = ((uint32_t)100 << 16) | 0xffffu;                   // TH_HIGH (:523)
+        if (!(maxU < 0.f)) {
+            const uint4* dl = reinterpret_cast<const uint4*>(SL.desc + oL * 32);
+            const uint4 a0 = __ldg(dl), a1 = __ldg(dl + 1);
+            const float* kr0 = SR.kp + (size_t)fR * kpf * 7;
+            const uint8_t* dr0 = SR.desc + (size_t)fR * kpf * 32;
+            const uint32_t* bd0 = bands + (size_t)fR * kpf;
+            for (int j = lane; j < Nr; j += 32) {
+                const uint32_t band = __ldg(bd0 + j);
+                const int minr = (int)(band & 0xffffu), maxr = (int)(band >> 16);
+                if (row < minr || row > maxr) continue;                    // row >= 0, so clamping minr at 0 changes nothing
+                const float* kr = kr0 + (size_t)j * 7;
+                const float xr = kr[0];
+                const int oc = __float_as_int(kr[5]);
+                if (oc >= levelL - 1 && oc <= levelL + 1 && xr >= minU && xr <= maxU) {
+                    const uint4* dr = reinterpret_cast<const uint4*>(dr0 + (size_t)j * 32);
+                    const uint4 b0 = __ldg(dr), b1 = __ldg(dr + 1);
+                    const uint32_t d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                                       __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+                    best = min(best, (d << 16) | (uint32_t)j);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        }
+        const int bestDist = (int)(best >> 16);
+        if (bestDist < (100 + 50) / 2) {                                   // thOrbDist (:471, :549)
+            const int bestR = (int)(best & 0xffffu);
+            const float uR0 = SR.kp[((size_t)fR * kpf + bestR) * 7];
+            const OrbxLevel& Lv = plan->lv[levelL];
+            const float inv = __fdiv_rn(1.0f, Lv.scale);                   // mvInvScaleFactors (src/ORBextractor.cc:425-431)
+            const int su = (int)roundf(__fmul_rn(uL, inv)), sv = (int)roundf(__fmul_rn(vL, inv));
+            const int sr = (int)roundf(__fmul_rn(uR0, inv));
+            // (:575-578) iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1.  The windows themselves reach 10 columns
+            // left of scaleduR0: OpenCV throws on a negative colRange; here such a keypoint simply gets no match, and any
+            // window leaving the padded plane is refused so no read can go out of bounds.
+            const bool ok = !(sr < 0 || sr + 11 >= Lv.w) && sr - 10 >= -ORBX_EDGE && sr + 10 < Lv.w + ORBX_EDGE &&
+                            su - 5 >= -ORBX_EDGE && su + 5 < Lv.w + ORBX_EDGE && sv - 5 >= -ORBX_EDGE && sv + 5 < Lv.h + ORBX_EDGE;
+            if (ok) {
+                if (lane < 12) s_sad[warp][lane] = 0;
+                __syncwarp();
+                const uint8_t* PL = SL.pyr + (size_t)fL * plan->slab_bytes + Lv.plane_off + (size_t)(sv - 5 + ORBX_EDGE) * Lv.pitch + ORBX_XO + su - 5;
+                const uint8_t* PR = SR.pyr + (size_t)fR * plan->slab_bytes + Lv.plane_off + (size_t)(sv - 5 + ORBX_EDGE) * Lv.pitch + ORBX_XO + sr - 10;
+                const int cL = PL[5 * Lv.pitch + 5];
+                for (int t = lane; t < 121; t += 32) {
+                    const int i = (t * 5958) >> 16, rw = t - i * 11;      // incR = i - 5, window row rw
+                    const int cR = PR[5 * Lv.pitch + 5 + i];
+                    const uint8_t* a = PL + (size_t)rw * Lv.pitch;
+                    const uint8_t* b = PR + (size_t)rw * Lv.pitch + i;
+                    int acc = 0;
+#pragma unroll
+                    for (int c = 0; c < 11; ++c) acc += abs(((int)a[c] - cL) - ((int)b[c] - cR));
+                    atomicAdd(&s_sad[warp][i], acc);
+                }
+                __syncwarp();
+                int bd = 0x7fffffff, bi = 0;
+#pragma unroll
+                for (int i = 0; i < 11; ++i) {
+                    const int d = s_sad[warp][i];
+                    if (d < bd) { bd = d; bi = i; }
+                }
+                __syncwarp();
+                if (bi != 0 && bi != 10) {                                 // (:598-599)
+                    const float d1 = (float)s_sad[warp][bi - 1], d2 = (float)bd, d3 = (float)s_sad[warp][bi + 1];
+                    const float deltaR = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
+                    if (!(deltaR < -1.f || deltaR > 1.f)) {                // a NaN passes, as in the reference (:608)
+                        float bestuR = __fmul_rn(Lv.scale, __fadd_rn(__fadd_rn((float)sr, (float)(bi - 5)), deltaR));
+                        float disparity = __fsub_rn(uL, bestuR);
+                        if (disparity >= 0.f && disparity < maxD) {
+                            if (disparity <= 0.f) {
+                                disparity = 0.01f;
+                                bestuR = (float)((double)uL - 0.01);       // (:620) evaluated in double
+                            }
+                            res_d = __fdiv_rn(mbf, disparity);
+                            res_u = bestuR;
+                            res_sad = bd;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0) {
+            u_right[oL] = res_u;
+            depth[oL] = res_d;
+            sad_out[oL] = res_sad;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+stereo_filter_kernel(const OrbxPlan* __restrict__ plan, const int* __restrict__ left_counts, const int* __restrict__ pairs,
+                     float* __restrict__ u_right, float* __restrict__ depth, const int* __restrict__ sad) {
+    extern __shared__ int sf_d[];                                          // accepted SADs, compacted
+    __shared__ int s_n, s_median;
+    const int kpf = plan->kept_per_frame, nl = plan->nlevels;
+    const int fL = pairs[2 * blockIdx.x];
+    int N = 0;
+    for (int l = 0; l < nl; ++l) N += left_counts[fL * nl + l];
+    const size_t o = (size_t)fL * kpf;
+    if (threadIdx.x == 0) { s_n = 0; s_median = 0; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const int d = sad[o + i];
+        if (d >= 0) sf_d[atomicAdd(&s_n, 1)] = d;                         // order is irrelevant for a rank
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n == 0) return;                                                    // vDistIdx[0] of an empty vector in the reference
+    const int k = n / 2;                                                   // (:630)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int d = sf_d[i];
+        int lt = 0, le = 0;
+        for (int j = 0; j < n; ++j) {
+            const int e = sf_d[j];
+            lt += e < d;
+            le += e <= d;
+        }
+        if (lt <= k && k < le) s_median = d;                               // every writer writes the same value
+    }
+    __syncthreads();
+    const float thDist = __fmul_rn(__fmul_rn(1.5f, 1.4f), (float)s_median);   // (:631)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const int d = sad[o + i];
+        if (d >= 0 && !((float)d < thDist)) { u_right[o + i] = -1.f; depth[o + i] = -1.f; }
+    }
+}
+
+// =====================================================================================
 // launch wrappers (called from orbx_api.cu)
 // =====================================================================================
 static bool force_resize4() {          // ORBX_RESIZE4=1: A/B switch back to the 4-pixel-per-lane resize kernel
@@ -1578,6 +1774,37 @@ cudaError_t launch_describe(const OrbxPlan* d_plan, const OrbxPlan& hp, const vo
     memcpy(&fm, maps, sizeof fm);
     return launch_k(describe_kernel, dim3((unsigned)blocks), dim3(KP_WARPS * 32), smem, st, fm, d_plan, frame0, nframes, kept,
                     kept_counts, angles, out_kp, out_desc);
+}
+
+cudaError_t launch_stereo(const OrbxPlan* d_plan, const OrbxPlan& hp, int num_sms, const uint8_t* pyrL, const float* kpL,
+                          const uint8_t* descL, const int* countsL, const uint8_t* pyrR, const float* kpR, const uint8_t* descR,
+                          const int* countsR, const int* d_pairs, int npairs, float mbf, float mb, float* u_right, float* depth,
+                          int* sad, uint32_t* bands, cudaStream_t st) {
+    StereoSide SL = {pyrL, kpL, descL, countsL}, SR = {pyrR, kpR, descR, countsR};
+    {
+        long long nb = ((long long)npairs * hp.kept_per_frame + 255) / 256;
+        if (nb > (long long)num_sms * 8) nb = (long long)num_sms * 8;
+        cudaError_t e0 = launch_k(stereo_bands_kernel, dim3((unsigned)(nb < 1 ? 1 : nb)), dim3(256), 0, st, d_plan, SR, d_pairs, npairs, bands);
+        if (e0 != cudaSuccess) return e0;
+    }
+    long long blocks = ((long long)npairs * hp.kept_per_frame + ST_WARPS - 1) / ST_WARPS;
+    const long long cap = (long long)num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    cudaError_t e = launch_k(stereo_match_kernel, dim3((unsigned)blocks), dim3(ST_WARPS * 32), 0, st, d_plan, SL, SR, d_pairs, npairs,
+                             (const uint32_t*)bands, mbf, mb, u_right, depth, sad);
+    if (e != cudaSuccess) return e;
+    const size_t smem = (size_t)hp.kept_per_frame * sizeof(int);
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && smem > configured[dev & 63]) {
+        e = cudaFuncSetAttribute(stereo_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev & 63] = smem;
+    }
+    return launch_k(stereo_filter_kernel, dim3((unsigned)npairs), dim3(1024), smem, st, d_plan, countsL, d_pairs, u_right, depth,
+                    (const int*)sad);
 }
 
 }  // namespace orbx

@@ -35,4 +35,10 @@ cudaError_t launch_describe(const OrbxPlan* d_plan, const OrbxPlan& hp, const vo
                             const uint32_t* kept, const int* kept_counts, float* angles, float* out_kp, uint8_t* out_desc,
                             cudaStream_t st);
 
+// Frame::ComputeStereoMatches (src/Frame.cc:466-640) on the device-resident outputs of two extractions
+cudaError_t launch_stereo(const OrbxPlan* d_plan, const OrbxPlan& hp, int num_sms, const uint8_t* pyrL, const float* kpL,
+                          const uint8_t* descL, const int* countsL, const uint8_t* pyrR, const float* kpR, const uint8_t* descR,
+                          const int* countsR, const int* d_pairs, int npairs, float mbf, float mb, float* u_right, float* depth,
+                          int* sad, uint32_t* bands, cudaStream_t st);
+
 }  // namespace orbx

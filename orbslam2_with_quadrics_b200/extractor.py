@@ -180,6 +180,32 @@ class ORBextractor:
         k = self._L.orbx_stage_timing_read(self._h, 16, names, ms, ln)
         return [(names[i].decode(), float(ms[i]), int(ln[i])) for i in range(k)]
 
+    # ---------------------------------------------------------------- Frame::ComputeStereoMatches (src/Frame.cc:466-640)
+    def stereo_match(self, right: "ORBextractor", mbf: float, mb: float, left_frames=None, right_frames=None,
+                     npairs: Optional[int] = None):
+        """Matches frames of the last extract on `self` (left eye) against frames of the last extract on `right`
+        (which may be `self` when one batch holds both eyes).  Returns [(mvuRight, mvDepth)] per pair, one float per
+        left keypoint, -1 where the reference leaves -1."""
+        if npairs is None:
+            npairs = len(left_frames) if left_frames is not None else min(self._last_n, right._last_n)
+        lf = (C.c_int * npairs)(*left_frames) if left_frames is not None else None
+        rf = (C.c_int * npairs)(*right_frames) if right_frames is not None else None
+        res = (_capi.OrbxStereoResult * npairs)()
+        check(self._L.orbx_stereo_match(self._h, right._h, npairs, lf, rf, mbf, mb, res), self._h)
+        out = []
+        for i in range(npairs):
+            n = res[i].n
+            u = np.ctypeslib.as_array(C.cast(res[i].u_right, C.POINTER(C.c_float)), shape=(max(n, 1),))[:n].copy()
+            d = np.ctypeslib.as_array(C.cast(res[i].depth, C.POINTER(C.c_float)), shape=(max(n, 1),))[:n].copy()
+            out.append((u, d))
+        return out
+
+    def stereo_match_device(self, right: "ORBextractor", mbf: float, mb: float, left_frames, right_frames):
+        """Enqueue only (device-side timing)."""
+        n = len(left_frames)
+        check(self._L.orbx_stereo_match_device(self._h, right._h, n, (C.c_int * n)(*left_frames), (C.c_int * n)(*right_frames),
+                                               mbf, mb), self._h)
+
     # ---------------------------------------------------------------- stage dumps (parity tests)
     def stage_dump(self, frame: int, level: int, stage: int):
         nbytes = C.c_size_t()

@@ -92,6 +92,25 @@ def checker_frame(width: int, height: int, seed: int, cell: int = 9) -> np.ndarr
     return np.ascontiguousarray(np.kron(grid, np.ones((cell, cell), np.uint8))[:height, :width])
 
 
+def stereo_pair(width: int, height: int, seed: int, bands: int = 6, max_disparity: int = 40):
+    """Rectified synthetic stereo pair for the ComputeStereoMatches row (src/Frame.cc:466-640): the right image is
+    the left scene shifted by an integer disparity that is constant inside each of `bands` horizontal bands
+    (right(x) = left(x + d), so a feature at uL appears at uR = uL - d), plus its own +-2 sensor noise."""
+    rng = np.random.default_rng(seed + 777)
+    margin = max_disparity + 8
+    scene = cluttered_scene(width + margin, height, seed)
+    left = np.ascontiguousarray(scene[:, :width])
+    right = np.empty_like(left)
+    edges = np.linspace(0, height, bands + 1).astype(int)
+    disp = rng.integers(2, max_disparity + 1, bands)
+    for b in range(bands):
+        d = int(disp[b])
+        right[edges[b]:edges[b + 1]] = scene[edges[b]:edges[b + 1], d:d + width]
+    noise = rng.integers(-2, 3, right.shape)
+    right = np.clip(right.astype(np.int32) + noise, 0, 255).astype(np.uint8)
+    return left, right
+
+
 def config_frames(name: str, stream: int = 0, frame: int = 0):
     """Images of one frame of a BASELINE config (2 for stereo: right uses stream+1)."""
     w, h, *_rest, nimg = CONFIGS[name]
