@@ -128,4 +128,14 @@ void ORBextractor::operator()( cv::InputArray _image, cv::InputArray _mask, std:
     }
 }
 
+void ORBextractor::ComputeStereoMatches(ORBextractor& left, ORBextractor& right, float mbf, float mb,
+                                        std::vector<float>& mvuRight, std::vector<float>& mvDepth)
+{
+    orbx_stereo_result r;
+    int rc = orbx_stereo_match(left.handle_, right.handle_, 1, 0, 0, mbf, mb, &r);
+    if (rc != ORBX_OK) orbx_throw(left.handle_, rc, "orbx_stereo_match");
+    mvuRight.assign(r.u_right, r.u_right + r.n);       // (:468-469) N floats each, -1 where unmatched
+    mvDepth.assign(r.depth, r.depth + r.n);
+}
+
 } //namespace ORB_SLAM

@@ -57,6 +57,12 @@ public:
     void SetPyramidDownload(bool enable);
     // CUDA device used by extractors created afterwards in this thread's process (default 0).
     static void SetDevice(int device);
+    // Frame::ComputeStereoMatches (reference src/Frame.cc:466-640) on the GPU, over the results both extractors still
+    // hold in HBM from their last operator(): fills mvuRight / mvDepth exactly as the reference does (-1 = no match).
+    // Call it from Frame::ComputeStereoMatches after the two ExtractORB threads have joined (src/Frame.cc:78-81); with
+    // it the stereo pipeline can run with SetPyramidDownload(false).  mbf, mb: Frame::mbf, Frame::mb.
+    static void ComputeStereoMatches(ORBextractor& left, ORBextractor& right, float mbf, float mb,
+                                     std::vector<float>& mvuRight, std::vector<float>& mvDepth);
 
 private:
     ORBextractor(const ORBextractor&);

@@ -72,7 +72,8 @@ struct orbx_handle {
     float *d_st_u, *d_st_depth, *h_st;        // h_st: [u_right B*kpf][depth B*kpf]
     int *d_st_sad, *d_st_pairs, *h_st_pairs;
     int st_right_cap, st_pairs_n;
-    uint32_t* d_st_bands;     // row bands of the RIGHT handle's keypoints, indexed like its keypoint records
+    int* d_st_rows;           // row table of the RIGHT handle's frames (vRowIndices): row_start, (height + 1) per frame
+    uint16_t* d_st_bucket;    // ... and the keypoint indices listed per row
     cudaEvent_t ev_stereo;
     int last_n;
     bool pyramid_valid;
@@ -356,7 +357,7 @@ void free_geometry(orbx_handle* h) {
     cudaFree(h->d_out_desc);
     cudaFreeHost(h->h_counters); cudaFreeHost(h->h_out_kp); cudaFreeHost(h->h_out_desc); cudaFreeHost(h->h_pyr);
     cudaFreeHost(h->h_input);
-    cudaFree(h->d_st_u); cudaFree(h->d_st_depth); cudaFree(h->d_st_sad); cudaFree(h->d_st_pairs); cudaFree(h->d_st_bands); h->d_st_bands = 0;
+    cudaFree(h->d_st_u); cudaFree(h->d_st_depth); cudaFree(h->d_st_sad); cudaFree(h->d_st_pairs); cudaFree(h->d_st_rows); cudaFree(h->d_st_bucket); h->d_st_rows = 0; h->d_st_bucket = 0;
     cudaFreeHost(h->h_st); cudaFreeHost(h->h_st_pairs);
     h->d_st_u = h->d_st_depth = h->h_st = 0; h->d_st_sad = h->d_st_pairs = h->h_st_pairs = 0;
     h->d_plan = 0; h->d_taps = 0; h->d_input = h->d_pyr = h->d_blur = 0;
@@ -605,7 +606,7 @@ int orbx_create(const orbx_config* cfg, orbx_handle** out) {
     h->d_cand = h->d_cand_sorted = h->d_kept = 0; h->d_key_node = 0; h->d_cell_rec = 0; h->d_counters = 0;
     h->d_angles = 0; h->d_out_kp = 0; h->d_out_desc = 0;
     h->h_counters = 0; h->h_out_kp = 0; h->h_out_desc = 0; h->h_pyr = 0; h->h_input = 0;
-    h->d_st_u = h->d_st_depth = h->h_st = 0; h->d_st_sad = h->d_st_pairs = h->h_st_pairs = 0; h->d_st_bands = 0;
+    h->d_st_u = h->d_st_depth = h->h_st = 0; h->d_st_sad = h->d_st_pairs = h->h_st_pairs = 0; h->d_st_rows = 0; h->d_st_bucket = 0;
     h->last_n = 0; h->pyramid_valid = false;
     h->timing = false; h->ev_created = false; h->ev_head = 0; h->ev_pending = 0;
     memset(h->stage_ms, 0, sizeof h->stage_ms);
@@ -793,6 +794,8 @@ int stereo_enqueue(orbx_handle* L, orbx_handle* R, int npairs, const int* left_f
                    float mb) {
     if (!L || !R || npairs < 1 || npairs > L->cfg.max_batch || !L->have_plan || !R->have_plan) return ORBX_ERR_BAD_ARGS;
     if (!(mb > 0.f) || !(mbf > 0.f)) return ORBX_ERR_BAD_ARGS;
+    // row bands of at most 24 rows (2 * ceil(2 * scale) + 2) and at most 15 keypoints per thread of the filter kernel
+    if (L->sf[L->cfg.nlevels - 1] > 5.4f || L->plan.kept_per_frame > 15 * 1024 || L->plan.kept_per_frame > 65535) return ORBX_ERR_BAD_GEOMETRY;
     const OrbxPlan& P = L->plan;
     // both eyes must have been extracted with the same constructor arguments and image size on the same device
     if (L->cfg.device != R->cfg.device || R->plan.width != P.width || R->plan.height != P.height ||
@@ -803,8 +806,9 @@ int stereo_enqueue(orbx_handle* L, orbx_handle* R, int npairs, const int* left_f
     for (int i = 0; i < npairs; ++i) {
         const int fl = left_frames ? left_frames[i] : i, fr = right_frames ? right_frames[i] : i;
         if (fl < 0 || fl >= L->last_n || fr < 0 || fr >= R->last_n) return ORBX_ERR_BAD_ARGS;
-        for (int k = 0; k < i; ++k)            // results are stored per left frame: one pair per left frame and call
-            if ((left_frames ? left_frames[k] : k) == fl) return ORBX_ERR_BAD_ARGS;
+        for (int k = 0; k < i; ++k)            // results are stored per left frame and row tables per right frame: each
+            if ((left_frames ? left_frames[k] : k) == fl || (right_frames ? right_frames[k] : k) == fr)   // may appear once per call
+                return ORBX_ERR_BAD_ARGS;
     }
     CK(L, cudaSetDevice(L->cfg.device));
     const size_t B = (size_t)L->cfg.max_batch, kpf = (size_t)P.kept_per_frame;
@@ -813,7 +817,8 @@ int stereo_enqueue(orbx_handle* L, orbx_handle* R, int npairs, const int* left_f
         CK(L, cudaMalloc(&L->d_st_depth, B * kpf * 4));
         CK(L, cudaMalloc(&L->d_st_sad, B * kpf * 4));
         CK(L, cudaMalloc(&L->d_st_pairs, B * 2 * sizeof(int)));
-        CK(L, cudaMalloc(&L->d_st_bands, (size_t)R->cfg.max_batch * kpf * 4));
+        CK(L, cudaMalloc(&L->d_st_rows, (size_t)R->cfg.max_batch * (P.height + 1) * sizeof(int)));
+        CK(L, cudaMalloc(&L->d_st_bucket, (size_t)R->cfg.max_batch * orbx::stereo_bucket_entries(P) * sizeof(uint16_t)));
         L->st_right_cap = R->cfg.max_batch;
         L->st_pairs_n = 0;
         CK(L, cudaMallocHost(&L->h_st, 2 * B * kpf * 4));
@@ -839,7 +844,7 @@ int stereo_enqueue(orbx_handle* L, orbx_handle* R, int npairs, const int* left_f
     }
     CK(L, orbx::launch_stereo(L->d_plan, P, L->num_sms, L->d_pyr, L->d_out_kp, L->d_out_desc, L->d_kept_counts(), R->d_pyr,
                               R->d_out_kp, R->d_out_desc, R->d_kept_counts(), L->d_st_pairs, npairs, mbf, mb, L->d_st_u,
-                              L->d_st_depth, L->d_st_sad, L->d_st_bands, st));
+                              L->d_st_depth, L->d_st_sad, L->d_st_rows, L->d_st_bucket, st));
     L->launches += 3;
     return ORBX_OK;
 }

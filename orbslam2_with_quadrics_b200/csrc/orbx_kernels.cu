@@ -1425,31 +1425,65 @@ struct StereoSide {
     const int* kept_counts;    // [frame][level]
 };
 
-// Row band of every right keypoint (:486-492) as minr | maxr << 16, so the candidate scan rejects on one word.
+// Row table of the right image (vRowIndices, :476-496), one CTA per pair: right keypoint j is listed in every row
+// of its band floor(y - r) .. ceil(y + r), r = 2 * scale[octave].  Counting sort by row: per-row counts in shared
+// memory, an exclusive scan gives row_start (height + 1 entries per right frame), then the keypoint indices are
+// scattered into their rows' lists.  The order inside a row is arbitrary: the matcher takes the minimum of
+// (distance << 16 | index), which is the reference's "first strictly smaller wins" whatever the visiting order.
+#define ST_MAX_SPAN 24          // rows per keypoint: 2 * ceil(2 * 5.16) + 2 at the 10th level of a 1.2 pyramid; checked at launch
 __global__ void __launch_bounds__(256)
-stereo_bands_kernel(const OrbxPlan* __restrict__ plan, StereoSide SR, const int* __restrict__ pairs, int npairs,
-                    uint32_t* __restrict__ bands) {
-    const int kpf = plan->kept_per_frame, nl = plan->nlevels;
-    const unsigned total = (unsigned)npairs * (unsigned)kpf;
-    for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
-        const int p = (int)(it / (unsigned)kpf), j = (int)(it - (unsigned)p * (unsigned)kpf);
-        const int fR = pairs[2 * p + 1];
-        int Nr = 0;
-        for (int l = 0; l < nl; ++l) Nr += SR.kept_counts[fR * nl + l];
-        if (j >= Nr) continue;
-        const float* kr = SR.kp + ((size_t)fR * kpf + j) * 7;
-        const float yr = kr[1];
-        const float r = __fmul_rn(2.0f, plan->lv[__float_as_int(kr[5])].scale);
-        const int maxr = (int)ceilf(__fadd_rn(yr, r)), minr = max((int)floorf(__fsub_rn(yr, r)), 0);
-        bands[(size_t)fR * kpf + j] = (uint32_t)minr | ((uint32_t)min(maxr, 0xffff) << 16);
+stereo_rows_kernel(const OrbxPlan* __restrict__ plan, StereoSide SR, const int* __restrict__ pairs, int* __restrict__ row_start,
+                   uint16_t* __restrict__ bucket) {
+    extern __shared__ int sr_cnt[];                                        // height + 1 counters, then cursors
+    __shared__ int s_warp[33];
+    const int kpf = plan->kept_per_frame, nl = plan->nlevels, H = plan->height;
+    const int fR = pairs[2 * blockIdx.x + 1];
+    int Nr = 0;
+    for (int l = 0; l < nl; ++l) Nr += SR.kept_counts[fR * nl + l];
+    for (int y = threadIdx.x; y <= H; y += blockDim.x) sr_cnt[y] = 0;
+    __syncthreads();
+    const float* kr0 = SR.kp + (size_t)fR * kpf * 7;
+    auto band = [&](int j, int& minr, int& maxr) {
+        const float yr = kr0[(size_t)j * 7 + 1];
+        const float r = __fmul_rn(2.0f, plan->lv[__float_as_int(kr0[(size_t)j * 7 + 5])].scale);
+        maxr = min((int)ceilf(__fadd_rn(yr, r)), H - 1);                   // rows outside the image are never looked up
+        minr = max((int)floorf(__fsub_rn(yr, r)), 0);
+        maxr = min(maxr, minr + ST_MAX_SPAN - 1);
+    };
+    for (int j = threadIdx.x; j < Nr; j += blockDim.x) {
+        int minr, maxr;
+        band(j, minr, maxr);
+        for (int y = minr; y <= maxr; ++y) atomicAdd(&sr_cnt[y], 1);
+    }
+    __syncthreads();
+    // exclusive scan over the rows: thread t owns rows [t * per, (t + 1) * per)
+    const int per = (H + 1 + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int y0 = threadIdx.x * per, y1 = min(y0 + per, H + 1);
+    int local = 0;
+    for (int y = y0; y < y1; ++y) local += sr_cnt[y];
+    int total;
+    int run = block_excl_scan(local, &total, s_warp);
+    int* rs = row_start + (size_t)fR * (H + 1);
+    for (int y = y0; y < y1; ++y) {
+        const int c = sr_cnt[y];
+        sr_cnt[y] = run;                                                   // cursor
+        rs[y] = run;
+        run += c;
+    }
+    __syncthreads();
+    uint16_t* bk = bucket + (size_t)fR * kpf * ST_MAX_SPAN;
+    for (int j = threadIdx.x; j < Nr; j += blockDim.x) {
+        int minr, maxr;
+        band(j, minr, maxr);
+        for (int y = minr; y <= maxr; ++y) bk[atomicAdd(&sr_cnt[y], 1)] = (uint16_t)j;
     }
 }
 
 #define ST_WARPS 8
 __global__ void __launch_bounds__(ST_WARPS * 32)
 stereo_match_kernel(const OrbxPlan* __restrict__ plan, StereoSide SL, StereoSide SR, const int* __restrict__ pairs, int npairs,
-                    const uint32_t* __restrict__ bands, float mbf, float mb, float* __restrict__ u_right,
-                    float* __restrict__ depth, int* __restrict__ sad_out) {
+                    const int* __restrict__ row_start, const uint16_t* __restrict__ bucket, float mbf, float mb,
+                    float* __restrict__ u_right, float* __restrict__ depth, int* __restrict__ sad_out) {
     __shared__ int s_sad[ST_WARPS][12];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int kpf = plan->kept_per_frame, nl = plan->nlevels;
@@ -1458,8 +1492,8 @@ stereo_match_kernel(const OrbxPlan* __restrict__ plan, StereoSide SL, StereoSide
     for (unsigned it = blockIdx.x * ST_WARPS + warp; it < total; it += gridDim.x * ST_WARPS) {
         const int p = (int)(it / (unsigned)kpf), iL = (int)(it - (unsigned)p * (unsigned)kpf);
         const int fL = pairs[2 * p], fR = pairs[2 * p + 1];
-        int N = 0, Nr = 0;
-        for (int l = 0; l < nl; ++l) { N += SL.kept_counts[fL * nl + l]; Nr += SR.kept_counts[fR * nl + l]; }
+        int N = 0;
+        for (int l = 0; l < nl; ++l) N += SL.kept_counts[fL * nl + l];
         if (iL >= N) continue;
         const size_t oL = (size_t)fL * kpf + iL;
         const float* kl = SL.kp + oL * 7;
@@ -1475,11 +1509,11 @@ stereo_match_kernel(const OrbxPlan* __restrict__ plan, StereoSide SL, StereoSide
             const uint4 a0 = __ldg(dl), a1 = __ldg(dl + 1);
             const float* kr0 = SR.kp + (size_t)fR * kpf * 7;
             const uint8_t* dr0 = SR.desc + (size_t)fR * kpf * 32;
-            const uint32_t* bd0 = bands + (size_t)fR * kpf;
-            for (int j = lane; j < Nr; j += 32) {
-                const uint32_t band = __ldg(bd0 + j);
-                const int minr = (int)(band & 0xffffu), maxr = (int)(band >> 16);
-                if (row < minr || row > maxr) continue;                    // row >= 0, so clamping minr at 0 changes nothing
+            const int* rs = row_start + (size_t)fR * (plan->height + 1);
+            const int cbeg = row < plan->height ? rs[row] : 0, cend = row < plan->height ? rs[row + 1] : 0;
+            const uint16_t* bk = bucket + (size_t)fR * kpf * ST_MAX_SPAN;
+            for (int c = cbeg + lane; c < cend; c += 32) {                 // vRowIndices[vL] (:512)
+                const int j = bk[c];
                 const float* kr = kr0 + (size_t)j * 7;
                 const float xr = kr[0];
                 const int oc = __float_as_int(kr[5]);
@@ -1579,16 +1613,18 @@ stereo_filter_kernel(const OrbxPlan* __restrict__ plan, const int* __restrict__ 
     const int n = s_n;
     if (n == 0) return;                                                    // vDistIdx[0] of an empty vector in the reference
     const int k = n / 2;                                                   // (:630)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int d = sf_d[i];
-        int lt = 0, le = 0;
-        for (int j = 0; j < n; ++j) {
-            const int e = sf_d[j];
-            lt += e < d;
-            le += e <= d;
-        }
-        if (lt <= k && k < le) s_median = d;                               // every writer writes the same value
+    // sorted[k] = the smallest v with #(d <= v) > k: bisection on the value (SADs are < 2^17), one block-wide
+    // population count per step
+    int lo = 0, hi = (1 << 17) - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        int c = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) c += sf_d[i] <= mid;
+        const int tot = __syncthreads_count(c & 1) + 2 * __syncthreads_count(c & 2) + 4 * __syncthreads_count(c & 4) +
+                        8 * __syncthreads_count(c & 8);                    // c <= 15: at most 15 elements per thread (checked at launch)
+        if (tot > k) hi = mid; else lo = mid + 1;
     }
+    if (threadIdx.x == 0) s_median = lo;
     __syncthreads();
     const float thDist = __fmul_rn(__fmul_rn(1.5f, 1.4f), (float)s_median);   // (:631)
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
@@ -1776,15 +1812,16 @@ cudaError_t launch_describe(const OrbxPlan* d_plan, const OrbxPlan& hp, const vo
                     kept_counts, angles, out_kp, out_desc);
 }
 
+size_t stereo_bucket_entries(const OrbxPlan& hp) { return (size_t)hp.kept_per_frame * ST_MAX_SPAN; }
+
 cudaError_t launch_stereo(const OrbxPlan* d_plan, const OrbxPlan& hp, int num_sms, const uint8_t* pyrL, const float* kpL,
                           const uint8_t* descL, const int* countsL, const uint8_t* pyrR, const float* kpR, const uint8_t* descR,
                           const int* countsR, const int* d_pairs, int npairs, float mbf, float mb, float* u_right, float* depth,
-                          int* sad, uint32_t* bands, cudaStream_t st) {
+                          int* sad, int* row_start, uint16_t* bucket, cudaStream_t st) {
     StereoSide SL = {pyrL, kpL, descL, countsL}, SR = {pyrR, kpR, descR, countsR};
     {
-        long long nb = ((long long)npairs * hp.kept_per_frame + 255) / 256;
-        if (nb > (long long)num_sms * 8) nb = (long long)num_sms * 8;
-        cudaError_t e0 = launch_k(stereo_bands_kernel, dim3((unsigned)(nb < 1 ? 1 : nb)), dim3(256), 0, st, d_plan, SR, d_pairs, npairs, bands);
+        const size_t smem_rows = (size_t)(hp.height + 1) * sizeof(int);
+        cudaError_t e0 = launch_k(stereo_rows_kernel, dim3((unsigned)npairs), dim3(256), smem_rows, st, d_plan, SR, d_pairs, row_start, bucket);
         if (e0 != cudaSuccess) return e0;
     }
     long long blocks = ((long long)npairs * hp.kept_per_frame + ST_WARPS - 1) / ST_WARPS;
@@ -1792,7 +1829,7 @@ cudaError_t launch_stereo(const OrbxPlan* d_plan, const OrbxPlan& hp, int num_sm
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     cudaError_t e = launch_k(stereo_match_kernel, dim3((unsigned)blocks), dim3(ST_WARPS * 32), 0, st, d_plan, SL, SR, d_pairs, npairs,
-                             (const uint32_t*)bands, mbf, mb, u_right, depth, sad);
+                             (const int*)row_start, (const uint16_t*)bucket, mbf, mb, u_right, depth, sad);
     if (e != cudaSuccess) return e;
     const size_t smem = (size_t)hp.kept_per_frame * sizeof(int);
     static size_t configured[64] = {0};

@@ -39,6 +39,7 @@ cudaError_t launch_describe(const OrbxPlan* d_plan, const OrbxPlan& hp, const vo
 cudaError_t launch_stereo(const OrbxPlan* d_plan, const OrbxPlan& hp, int num_sms, const uint8_t* pyrL, const float* kpL,
                           const uint8_t* descL, const int* countsL, const uint8_t* pyrR, const float* kpR, const uint8_t* descR,
                           const int* countsR, const int* d_pairs, int npairs, float mbf, float mb, float* u_right, float* depth,
-                          int* sad, uint32_t* bands, cudaStream_t st);
+                          int* sad, int* row_start, uint16_t* bucket, cudaStream_t st);
+size_t stereo_bucket_entries(const OrbxPlan& hp);     // uint16 entries of one right frame's row table
 
 }  // namespace orbx

@@ -41,5 +41,26 @@ int main(int argc, char** argv)
         for (int y = -19; y < m.rows + 19; ++y) fwrite(m.data + (long)y * (long)m.step - 19, 1, (size_t)m.cols + 38, o);
     }
     fclose(o);
+    // optional stereo leg: <right.raw> <stereo_out.bin> <mbf> <mb> -- two extractors as in src/Frame.cc:78-81, then the
+    // GPU ComputeStereoMatches; dumps N, mvuRight, mvDepth
+    if (argc >= 14) {
+        ORB_SLAM2::ORBextractor exr(atoi(argv[3]), (float)atof(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]));
+        std::vector<unsigned char> rb((size_t)w * h);
+        FILE* fr = fopen(argv[10], "rb");
+        if (!fr || fread(rb.data(), 1, rb.size(), fr) != rb.size()) return 5;
+        fclose(fr);
+        cv::Mat imr(h, w, CV_8UC1, rb.data(), (size_t)w);
+        std::vector<cv::KeyPoint> keysr;
+        cv::Mat descr;
+        exr(imr, cv::Mat(), keysr, descr);
+        std::vector<float> uR, dep;
+        ORB_SLAM2::ORBextractor::ComputeStereoMatches(ex, exr, (float)atof(argv[12]), (float)atof(argv[13]), uR, dep);
+        FILE* so = fopen(argv[11], "wb");
+        int ns = (int)uR.size();
+        fwrite(&ns, 4, 1, so);
+        fwrite(uR.data(), 4, uR.size(), so);
+        fwrite(dep.data(), 4, dep.size(), so);
+        fclose(so);
+    }
     return 0;
 }

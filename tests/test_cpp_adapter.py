@@ -66,3 +66,28 @@ def test_adapter_matches_oracle(tmp_path):
         lw, lh = np.frombuffer(b, np.int32, 2, off); off += 8
         plane = np.frombuffer(b, np.uint8, (lw + 38) * (lh + 38), off).reshape(lh + 38, lw + 38); off += plane.size
         assert np.array_equal(plane, ro.pyramid[l]), l
+
+
+@pytest.mark.gpu
+def test_adapter_stereo_matches_oracle(tmp_path):
+    """Two adapter objects (one per eye, src/Frame.cc:78-81) + the GPU ComputeStereoMatches vs the stereo oracle."""
+    from oracle import orb_oracle, stereo_oracle
+    exe = build_adapter()
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["stereo_euroc"]
+    left, right = fr.stereo_pair(w, h, 4242)
+    mbf = 47.90639384423901
+    mb = float(np.float32(mbf) / np.float32(435.2046959714599))
+    rawl, rawr, outp, sout = tmp_path / "l.raw", tmp_path / "r.raw", tmp_path / "out.bin", tmp_path / "stereo.bin"
+    left.tofile(rawl); right.tofile(rawr)
+    subprocess.run([exe, str(w), str(h), str(nf), str(sf), str(nl), str(it), str(mt), str(rawl), str(outp), str(rawr), str(sout),
+                    repr(mbf), repr(mb)], check=True)
+    ex = orb_oracle.ORBextractor(nf, sf, nl, it, mt)
+    rl, rr = ex(left), ex(right)
+    u, d, _ = stereo_oracle.compute_stereo_matches(rl.keypoints, rl.descriptors, rl.pyramid, rr.keypoints, rr.descriptors, rr.pyramid,
+                                                   ex.GetScaleFactors(), ex.GetInverseScaleFactors(), mbf, mb)
+    b = sout.read_bytes()
+    n = int(np.frombuffer(b, np.int32, 1)[0])
+    assert n == rl.n
+    ug, dg = np.frombuffer(b, np.float32, n, 4), np.frombuffer(b, np.float32, n, 4 + 4 * n)
+    assert (ug >= 0).sum() > 100
+    assert np.array_equal(ug.view(np.uint32), u.view(np.uint32)) and np.array_equal(dg.view(np.uint32), d.view(np.uint32))
