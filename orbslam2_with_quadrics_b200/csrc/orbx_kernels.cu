@@ -236,7 +236,10 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const OrbxPlan* __restr
 // table is indexed by PLANE row (border reflection folded in).  ~11 thread instructions per output pixel against 26.
 struct Row6 { uint32_t a0, a1, a2, b0, b1, b2; };
 
-__global__ void __launch_bounds__(128) pyr_resize8_kernel(const OrbxPlan* __restrict__ plan, int l, int RY,
+#ifndef ORBX_R8_MINB
+#define ORBX_R8_MINB 1
+#endif
+__global__ void __launch_bounds__(128, ORBX_R8_MINB) pyr_resize8_kernel(const OrbxPlan* __restrict__ plan, int l, int RY,
                                                           uint8_t* __restrict__ pyr, const OrbxTap* __restrict__ taps) {
     ORBX_PDL_WAIT();
     const OrbxLevel& L = plan->lv[l];

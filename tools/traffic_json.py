@@ -1,0 +1,24 @@
+#!/usr/bin/env python3
+"""profiles/dominant_kernel_traffic.json from an `ncu --set full` capture of ONE half-batch launch sequence:
+dram__bytes_read.sum + dram__bytes_write.sum of every stage kernel, per frame (feeds bench.py's roofline.traffic).
+usage: traffic_json.py <file.ncu-rep> <frames in the captured launch sequence> [config name]"""
+import csv, json, subprocess, sys, collections
+rep, frames = sys.argv[1], int(sys.argv[2])
+name = sys.argv[3] if len(sys.argv) > 3 else "rgbd_1080p"
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+h, units, data = rows[0], rows[1], rows[2:]
+ki, ir, iw = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+def to_bytes(v, u):
+    f = float(v.replace(",", ""))
+    return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+per = collections.OrderedDict()
+for r in data:
+    k = r[ki].split("(")[0].replace("void ", "").replace("orbx::", "")
+    per[k] = per.get(k, 0.0) + to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw])
+total = sum(per.values())
+doc = {name: {"bytes_per_frame": total / frames,
+              "per_kernel_MB_per_%d_frames" % frames: {k: v / 1e6 for k, v in per.items()},
+              "source": "%s: dram__bytes_read.sum + dram__bytes_write.sum of the %d launches of one %d-frame half-batch (ncu --set full)" % (
+                  rep.split("/")[-1], len(data), frames)}}
+print(json.dumps(doc, indent=1))
