@@ -32,6 +32,26 @@ UNIT = "frames/s"
 DISTINCT_FRAMES = 8
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Rank 0 prints exactly ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner
+    on the first collective whatever NCCL_DEBUG says), so file descriptor 1 is pointed at stderr for the rest of the
+    process and the JSON line goes to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def workload_desc(name):
     w, h, nf, sf, nl, it, mt, nimg = fr.CONFIGS[name]
     return "%s: %dx%d 8-bit gray%s, nFeatures=%d, %d levels, scale %.1f, FAST %d/%d" % (
@@ -141,7 +161,7 @@ def reference_arm(args):
             "config": {"workload": workload_desc(args.config), "frames_per_step": fps_step, "host_threads": r["cores"]},
             "cpu_baseline": r,
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -401,7 +421,7 @@ def own_arm(args):
                     "stereo_match": ("device (orbx_stereo_match inside the timed region)" if stereo_dev else "host consumer (pyramid D2H)") if nimg == 2 else None,
                     "call": "orbx_extract_batch (C ABI), %d frames per call per thread, pinned host frames" % (B // T)},
             "latency_ms": lat, "gpu_launches": int(launches), "clocks": clocks}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -422,6 +442,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    claim_stdout()
     if args.impl == "reference":
         return reference_arm(args)
     return own_arm(args)
