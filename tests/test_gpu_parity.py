@@ -91,7 +91,8 @@ def test_adversarial_frames(kind):
 
 @pytest.mark.parametrize("shape,args", [((333, 517), (500, 1.2, 6, 20, 7)), ((480, 640), (1500, 1.5, 4, 12, 5)),
                                          ((200, 900), (700, 1.1, 10, 20, 7)), ((131, 257), (200, 1.2, 3, 20, 7)),
-                                         ((600, 400), (400, 1.3, 5, 30, 10))])
+                                         ((600, 400), (400, 1.3, 5, 30, 10)), ((480, 640), (500, 2.0, 3, 20, 7)),
+                                         ((480, 752), (800, 1.8, 4, 20, 7))])
 def test_odd_shapes_strides_and_parameters(shape, args):
     h, w = shape
     big = fr.cluttered_scene(w + 64, h + 32, 900 + h)
