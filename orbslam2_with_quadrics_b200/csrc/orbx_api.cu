@@ -68,6 +68,17 @@ struct orbx_handle {
     uint8_t* h_out_desc;
     uint8_t* h_pyr;
     uint8_t* h_input;
+    // CUDA graphs of the per-sub-batch launch sequence (see enqueue_frames_graphed)
+    struct GraphEntry {
+        int f0, n, chunk, si;
+        size_t pitch, frame_stride;
+        const uint8_t* d_imgs;
+        cudaGraphExec_t exec;     // 0 until the sequence has been seen twice
+        int launches;
+    };
+    std::vector<GraphEntry> graphs;
+    bool use_graphs;
+
     // stereo matcher (orbx_stereo_match; allocated on first use, owned by the LEFT handle)
     float *d_st_u, *d_st_depth, *h_st;        // h_st: [u_right B*kpf][depth B*kpf]
     int *d_st_sad, *d_st_pairs, *h_st_pairs;
@@ -351,6 +362,9 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
 }
 
 void free_geometry(orbx_handle* h) {
+    for (size_t i = 0; i < h->graphs.size(); ++i)
+        if (h->graphs[i].exec) cudaGraphExecDestroy(h->graphs[i].exec);
+    h->graphs.clear();
     cudaFree(h->d_plan); cudaFree(h->d_taps); cudaFree(h->d_input); cudaFree(h->d_pyr); cudaFree(h->d_blur);
     cudaFree(h->d_cand); cudaFree(h->d_cand_sorted); cudaFree(h->d_kept); cudaFree(h->d_key_node);
     cudaFree(h->d_cell_rec); cudaFree(h->d_counters); cudaFree(h->d_angles); cudaFree(h->d_out_kp);
@@ -495,6 +509,58 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
     return ORBX_OK;
 }
 
+// The launch sequence of a sub-batch (nlevels + 4 kernels, two streams, three events) is identical from call to call
+// for a given (first frame, frame count, input pointer, pitch, stream): the second time a sequence is seen it is
+// stream-captured into a CUDA graph and from then on replayed with ONE launch.  For small images the path is bound by
+// host launch overhead (640x480: 56 launches per 32-frame call), so this is where end-to-end throughput and single-frame
+// latency come from.  Off while per-stage timing is on (events between kernels) and with ORBX_NO_GRAPHS=1.
+int enqueue_frames_graphed(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t pitch, size_t frame_stride, int chunk,
+                           cudaStream_t st) {
+    if (!h->use_graphs || h->timing) return enqueue_frames(h, f0, n, d_imgs, pitch, frame_stride, chunk, st);
+    int si = 0;
+    for (int i = 1; i < 4; ++i) if (st == h->ks[i]) si = i;
+    orbx_handle::GraphEntry* e = 0;
+    for (size_t i = 0; i < h->graphs.size(); ++i) {
+        orbx_handle::GraphEntry& g = h->graphs[i];
+        if (g.f0 == f0 && g.n == n && g.chunk == chunk && g.si == si && g.pitch == pitch && g.frame_stride == frame_stride &&
+            g.d_imgs == d_imgs) { e = &g; break; }
+    }
+    if (!e) {                                  // first sight: run eagerly (also performs the one-time kernel attribute set-up)
+        if (h->graphs.size() < 64) {
+            orbx_handle::GraphEntry g = {f0, n, chunk, si, pitch, frame_stride, d_imgs, 0, 0};
+            h->graphs.push_back(g);
+        }
+        return enqueue_frames(h, f0, n, d_imgs, pitch, frame_stride, chunk, st);
+    }
+    if (!e->exec) {                            // second sight: capture
+        const long long before = h->launches;
+        cudaGraph_t graph = 0;
+        CK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_frames(h, f0, n, d_imgs, pitch, frame_stride, chunk, st);
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc != ORBX_OK || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            h->use_graphs = false;             // capture is not possible here: stay on the eager path for good
+            h->launches = before;
+            return enqueue_frames(h, f0, n, d_imgs, pitch, frame_stride, chunk, st);
+        }
+        e->launches = (int)(h->launches - before);
+        h->launches = before;
+        const cudaError_t ie = cudaGraphInstantiate(&e->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {
+            e->exec = 0;
+            cudaGetLastError();
+            h->use_graphs = false;
+            return enqueue_frames(h, f0, n, d_imgs, pitch, frame_stride, chunk, st);
+        }
+    }
+    CK(h, cudaGraphLaunch(e->exec, st));
+    h->launches += e->launches;                // kernels the replay launches
+    return ORBX_OK;
+}
+
 int enqueue_pipeline(orbx_handle* h, int n, const uint8_t* d_imgs, size_t pitch, size_t frame_stride) {
     CK(h, cudaMemsetAsync(h->d_counters, 0, sizeof(int) * h->counters_count(), h->stream));
     // Two half-batches on the two kernel streams: the latency-bound tail of one half (octree, orientation,
@@ -512,7 +578,7 @@ int enqueue_pipeline(orbx_handle* h, int n, const uint8_t* d_imgs, size_t pitch,
     }
     for (int k = 0; k < nchunks; ++k) {
         const int f0 = (int)((long long)n * k / nchunks), f1 = (int)((long long)n * (k + 1) / nchunks);
-        int rc = enqueue_frames(h, f0, f1 - f0, d_imgs + (size_t)f0 * frame_stride, pitch, frame_stride, k, h->ks[k % ns]);
+        int rc = enqueue_frames_graphed(h, f0, f1 - f0, d_imgs + (size_t)f0 * frame_stride, pitch, frame_stride, k, h->ks[k % ns]);
         if (rc != ORBX_OK) return rc;
     }
     for (int i = 1; i < ns; ++i) {      // join: everything recorded on the handle's stream after this call covers all sub-batches
@@ -608,6 +674,7 @@ int orbx_create(const orbx_config* cfg, orbx_handle** out) {
     h->h_counters = 0; h->h_out_kp = 0; h->h_out_desc = 0; h->h_pyr = 0; h->h_input = 0;
     h->d_st_u = h->d_st_depth = h->h_st = 0; h->d_st_sad = h->d_st_pairs = h->h_st_pairs = 0; h->d_st_rows = 0; h->d_st_bucket = 0;
     h->last_n = 0; h->pyramid_valid = false;
+    h->use_graphs = getenv("ORBX_NO_GRAPHS") == nullptr;
     h->timing = false; h->ev_created = false; h->ev_head = 0; h->ev_pending = 0;
     memset(h->stage_ms, 0, sizeof h->stage_ms);
     memset(h->stage_launches, 0, sizeof h->stage_launches);
@@ -760,7 +827,7 @@ int orbx_extract_batch(orbx_handle* h, int n, const uint8_t* const* imgs, int wi
             CK(h, cudaEventRecord(h->ev_h2d[k], h2d));
             CK(h, cudaStreamWaitEvent(cs, h->ev_h2d[k], 0));
         }
-        rc = enqueue_frames(h, f0, f1 - f0, h->d_input + f0 * fbytes, pitch, fbytes, k, cs);
+        rc = enqueue_frames_graphed(h, f0, f1 - f0, h->d_input + f0 * fbytes, pitch, fbytes, k, cs);
         if (rc != ORBX_OK) return rc;
         if (!one) {
             CK(h, cudaEventRecord(h->ev_done[k], cs));
