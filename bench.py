@@ -434,7 +434,7 @@ def main():
     ap.add_argument("--config", default="rgbd_1080p", choices=list(fr.CONFIGS))
     ap.add_argument("--batch", type=int, default=32, help="frames per step per GPU")
     ap.add_argument("--latency-frames", type=int, default=200)
-    ap.add_argument("--e2e-threads", type=int, default=2, help="host threads (one handle each) in the e2e measurement")
+    ap.add_argument("--e2e-threads", type=int, default=4, help="host threads (one handle each) in the e2e measurement; 4 measured best (640x480: 2 threads 76.8k, 3-4 threads 99.9k frames/s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stereo-match", default="device", choices=["device", "host"],
                     help="stereo configs: run Frame::ComputeStereoMatches on the GPU (pyramids stay in HBM) or leave it to a "
