@@ -122,6 +122,22 @@ ORBX_API int orbx_stereo_match_device(orbx_handle* left, orbx_handle* right, int
                                       const int* right_frames, float mbf, float mb);
 ORBX_API int orbx_stereo_fetch(orbx_handle* left, int npairs, const int* left_frames, orbx_stereo_result* results);
 
+/* ---- cvtColor in front of the path (reference src/Tracking.cc:172-197, :212-225, :242-255: every GrabImage* converts
+ * RGB/BGR(A) to gray on the CPU before the Frame is built).  These variants take the colour frame and convert it on the
+ * device with OpenCV 4.x's 8U arithmetic, gray = (B*3735 + G*19235 + R*9798 + 16384) >> 15, bit-identical to cv::cvtColor.
+ * strides / pitch are in BYTES of the colour rows. */
+typedef enum orbx_pixel_format {
+    ORBX_GRAY8 = 0,
+    ORBX_BGR8 = 1,  /* CV_BGR2GRAY  */
+    ORBX_RGB8 = 2,  /* CV_RGB2GRAY  */
+    ORBX_BGRA8 = 3, /* CV_BGRA2GRAY */
+    ORBX_RGBA8 = 4  /* CV_RGBA2GRAY */
+} orbx_pixel_format;
+ORBX_API int orbx_extract_batch_color(orbx_handle* h, int n, const uint8_t* const* imgs, int width, int height,
+                                      const size_t* strides, int format, orbx_result* results);
+ORBX_API int orbx_extract_device_color(orbx_handle* h, int n, const uint8_t* d_imgs, int width, int height, size_t pitch,
+                                       size_t frame_stride, int format);
+
 /* Pinned host buffers callers may fill with frames so that H2D copies are asynchronous DMA. */
 ORBX_API int orbx_alloc_host(size_t bytes, void** out);
 ORBX_API int orbx_free_host(void* p);

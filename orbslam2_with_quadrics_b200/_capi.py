@@ -23,7 +23,9 @@ SYMBOLS = [
     "orbx_stream", "orbx_synchronize", "orbx_stage_timing_enable", "orbx_stage_timing_read",
     "orbx_launch_count", "orbx_algorithmic_bytes", "orbx_strerror", "orbx_last_cuda_error", "orbx_version",
     "orbx_stereo_match", "orbx_stereo_match_device", "orbx_stereo_fetch",
+    "orbx_extract_batch_color", "orbx_extract_device_color",
 ]
+GRAY8, BGR8, RGB8, BGRA8, RGBA8 = range(5)
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
                      ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
@@ -98,6 +100,8 @@ def lib():
     L.orbx_stereo_match.argtypes = [vp, vp, i, C.POINTER(i), C.POINTER(i), C.c_float, C.c_float, C.POINTER(OrbxStereoResult)]
     L.orbx_stereo_match_device.argtypes = [vp, vp, i, C.POINTER(i), C.POINTER(i), C.c_float, C.c_float]
     L.orbx_stereo_fetch.argtypes = [vp, i, C.POINTER(i), C.POINTER(OrbxStereoResult)]
+    L.orbx_extract_batch_color.argtypes = [vp, i, C.POINTER(vp), i, i, C.POINTER(sz), i, C.POINTER(OrbxResult)]
+    L.orbx_extract_device_color.argtypes = [vp, i, vp, i, i, sz, sz, i]
     _lib = L
     return L
 

@@ -42,7 +42,7 @@ void ORBextractor::Create()
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels,
                            int _iniThFAST, int _minThFAST):
     handle_(0), nfeatures_(_nfeatures), nlevels_(_nlevels), iniThFAST_(_iniThFAST), minThFAST_(_minThFAST),
-    scaleFactor_(_scaleFactor), downloadPyramid_(true)
+    scaleFactor_(_scaleFactor), downloadPyramid_(true), rgb_(false)
 {
     Create();
     mvImagePyramid.resize(nlevels_);       // reference src/ORBextractor.cc:433
@@ -62,6 +62,8 @@ void ORBextractor::SetPyramidDownload(bool enable)
     for (size_t l = 0; l < mvImagePyramid.size(); ++l) mvImagePyramid[l] = cv::Mat();
     Create();
 }
+
+void ORBextractor::SetColorOrder(bool rgb) { rgb_ = rgb; }
 
 int ORBextractor::GetLevels() { return nlevels_; }
 
@@ -87,10 +89,21 @@ void ORBextractor::operator()( cv::InputArray _image, cv::InputArray _mask, std:
         return;                                    // outputs untouched (reference :1046-1047)
 
     cv::Mat image = _image.getMat();
-    assert(image.type() == CV_8UC1 );
+    const int type = image.type();                 // CV_8UC1 = 0, CV_8UC3 = 16, CV_8UC4 = 24
+    assert(type == CV_8UC1 || type == 16 || type == 24);
 
     orbx_result r;
-    int rc = orbx_extract(handle_, image.data, image.cols, image.rows, (size_t)image.step, &r);
+    int rc;
+    if (type == CV_8UC1)
+        rc = orbx_extract(handle_, image.data, image.cols, image.rows, (size_t)image.step, &r);
+    else
+    {
+        // colour frame: cvtColor on the device (reference src/Tracking.cc:172-255 does it on the CPU first)
+        const unsigned char* p = image.data;
+        const size_t step = (size_t)image.step;
+        const int fmt = type == 16 ? (rgb_ ? ORBX_RGB8 : ORBX_BGR8) : (rgb_ ? ORBX_RGBA8 : ORBX_BGRA8);
+        rc = orbx_extract_batch_color(handle_, 1, &p, image.cols, image.rows, &step, fmt, &r);
+    }
     if (rc != ORBX_OK) orbx_throw(handle_, rc, "orbx_extract");
 
     if( r.n == 0 )

@@ -57,6 +57,10 @@ public:
     void SetPyramidDownload(bool enable);
     // CUDA device used by extractors created afterwards in this thread's process (default 0).
     static void SetDevice(int device);
+    // Colour input: with this set, operator() also accepts CV_8UC3 / CV_8UC4 images -- the frames Tracking::GrabImage*
+    // receives (reference src/Tracking.cc:172-255) -- and does the cvtColor(RGB/BGR(A) -> GRAY) on the GPU, bit-identical
+    // to cv::cvtColor.  rgb = Tracking::mbRGB.  The cvtColor calls in GrabImage* can then be dropped.
+    void SetColorOrder(bool rgb);
     // Frame::ComputeStereoMatches (reference src/Frame.cc:466-640) on the GPU, over the results both extractors still
     // hold in HBM from their last operator(): fills mvuRight / mvDepth exactly as the reference does (-1 = no match).
     // Call it from Frame::ComputeStereoMatches after the two ExtractORB threads have joined (src/Frame.cc:78-81); with
@@ -73,6 +77,7 @@ private:
     int nfeatures_, nlevels_, iniThFAST_, minThFAST_;
     float scaleFactor_;
     bool downloadPyramid_;
+    bool rgb_;
 };
 
 } //namespace ORB_SLAM

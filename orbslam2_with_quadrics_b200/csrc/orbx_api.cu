@@ -52,6 +52,8 @@ struct orbx_handle {
     OrbxTap* d_taps;
     int in_pitch;                // capacity of a staged input row (bytes)
     uint8_t *d_input, *d_pyr;
+    uint8_t *d_color, *h_color;  // colour staging of orbx_extract_batch_color (allocated on first use)
+    size_t color_bytes;
     uint8_t* d_blur;             // ONE frame's blurred slab, allocated on the first ORBX_STAGE_BLURRED dump (diagnostics only)
     uint32_t *d_cand, *d_cand_sorted, *d_kept;
     uint16_t* d_key_node;
@@ -371,6 +373,7 @@ void free_geometry(orbx_handle* h) {
     cudaFree(h->d_out_desc);
     cudaFreeHost(h->h_counters); cudaFreeHost(h->h_out_kp); cudaFreeHost(h->h_out_desc); cudaFreeHost(h->h_pyr);
     cudaFreeHost(h->h_input);
+    cudaFree(h->d_color); cudaFreeHost(h->h_color); h->d_color = h->h_color = 0; h->color_bytes = 0;
     cudaFree(h->d_st_u); cudaFree(h->d_st_depth); cudaFree(h->d_st_sad); cudaFree(h->d_st_pairs); cudaFree(h->d_st_rows); cudaFree(h->d_st_bucket); h->d_st_rows = 0; h->d_st_bucket = 0;
     cudaFreeHost(h->h_st); cudaFreeHost(h->h_st_pairs);
     h->d_st_u = h->d_st_depth = h->h_st = 0; h->d_st_sad = h->d_st_pairs = h->h_st_pairs = 0;
@@ -675,6 +678,7 @@ int orbx_create(const orbx_config* cfg, orbx_handle** out) {
     h->d_st_u = h->d_st_depth = h->h_st = 0; h->d_st_sad = h->d_st_pairs = h->h_st_pairs = 0; h->d_st_rows = 0; h->d_st_bucket = 0;
     h->last_n = 0; h->pyramid_valid = false;
     h->use_graphs = getenv("ORBX_NO_GRAPHS") == nullptr;
+    h->d_color = h->h_color = 0; h->color_bytes = 0;
     h->timing = false; h->ev_created = false; h->ev_head = 0; h->ev_pending = 0;
     memset(h->stage_ms, 0, sizeof h->stage_ms);
     memset(h->stage_launches, 0, sizeof h->stage_launches);
@@ -952,6 +956,67 @@ int orbx_stereo_match(orbx_handle* left, orbx_handle* right, int npairs, const i
     const int rc = stereo_enqueue(left, right, npairs, left_frames, right_frames, mbf, mb);
     if (rc != ORBX_OK) return rc;
     return orbx_stereo_fetch(left, npairs, left_frames, results);
+}
+
+// ---- cvtColor in front of the path: colour frames are converted to gray on the device into the
+// handle's gray staging buffer, then the normal launch sequence runs on it.
+namespace {
+int color_channels(int format) { return (format == ORBX_BGR8 || format == ORBX_RGB8) ? 3 : (format == ORBX_BGRA8 || format == ORBX_RGBA8) ? 4 : 0; }
+}
+
+int orbx_extract_device_color(orbx_handle* h, int n, const uint8_t* d_imgs, int width, int height, size_t pitch, size_t frame_stride,
+                              int format) {
+    const int ch = h ? color_channels(format) : 0;
+    if (!h || !d_imgs || ch == 0 || n < 1 || n > h->cfg.max_batch || pitch < (size_t)width * ch) return ORBX_ERR_BAD_ARGS;
+    CK(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_geometry(h, width, height);
+    if (rc != ORBX_OK) return rc;
+    const size_t gp = (size_t)round_up(width, 16);
+    CK(h, orbx::launch_cvt_gray(d_imgs, pitch, frame_stride, width, height, n, format, h->d_input, gp, gp * height, h->stream));
+    h->launches += 1;
+    return enqueue_pipeline(h, n, h->d_input, gp, gp * height);
+}
+
+int orbx_extract_batch_color(orbx_handle* h, int n, const uint8_t* const* imgs, int width, int height, const size_t* strides,
+                             int format, orbx_result* results) {
+    const int ch = h ? color_channels(format) : 0;
+    if (!h || !imgs || !results || ch == 0 || n < 1 || n > h->cfg.max_batch) return ORBX_ERR_BAD_ARGS;
+    if (width == 0 || height == 0) return ORBX_ERR_EMPTY_IMAGE;
+    if (width < 0 || height < 0) return ORBX_ERR_BAD_ARGS;
+    const size_t rowb = (size_t)width * ch;
+    for (int i = 0; i < n; ++i)
+        if (!imgs[i] || (strides && strides[i] < rowb)) return ORBX_ERR_BAD_ARGS;
+    CK(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_geometry(h, width, height);
+    if (rc != ORBX_OK) return rc;
+    const size_t cp = (size_t)round_up((int)rowb, 16), cf = cp * height;
+    if (h->color_bytes < cf * h->cfg.max_batch) {
+        CK(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_color); cudaFreeHost(h->h_color);
+        h->d_color = h->h_color = 0;
+        h->color_bytes = cf * h->cfg.max_batch;
+        CK(h, cudaMalloc(&h->d_color, h->color_bytes));
+        CK(h, cudaMallocHost(&h->h_color, h->color_bytes));
+    }
+    cudaStream_t st = h->stream;
+    for (int i = 0; i < n; ++i) {
+        const size_t stride = strides ? strides[i] : rowb;
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, imgs[i]) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (!pinned) cudaGetLastError();
+        if (pinned && stride == cp) {
+            CK(h, cudaMemcpyAsync(h->d_color + i * cf, imgs[i], cf, cudaMemcpyHostToDevice, st));
+        } else if (pinned) {
+            CK(h, cudaMemcpy2DAsync(h->d_color + i * cf, cp, imgs[i], stride, rowb, (size_t)height, cudaMemcpyHostToDevice, st));
+        } else {                                                           // pageable: through the pinned colour staging
+            uint8_t* stg = h->h_color + i * cf;
+            for (int y = 0; y < height; ++y) memcpy(stg + (size_t)y * cp, imgs[i] + (size_t)y * stride, rowb);
+            CK(h, cudaMemcpyAsync(h->d_color + i * cf, stg, cf, cudaMemcpyHostToDevice, st));
+        }
+    }
+    rc = orbx_extract_device_color(h, n, h->d_color, width, height, cp, cf, format);
+    if (rc != ORBX_OK) return rc;
+    return fetch(h, n, results);
 }
 
 int orbx_alloc_host(size_t bytes, void** out) {

@@ -110,6 +110,31 @@ class ORBextractor:
         self._refresh_pyramids(n)
         return out
 
+    def extract_batch_color(self, images: Sequence[np.ndarray], fmt: int):
+        """Colour frames (H x W x 3 or 4, uint8; fmt = _capi.BGR8 / RGB8 / BGRA8 / RGBA8): cvtColor -> GRAY on the device
+        (reference src/Tracking.cc:172-255), then the normal path."""
+        n = len(images)
+        if n == 0:
+            return []
+        h, w, ch = images[0].shape
+        ptrs = (C.c_void_p * n)()
+        strides = (C.c_size_t * n)()
+        keep = []
+        for i, im in enumerate(images):
+            if im.dtype != np.uint8 or im.ndim != 3 or im.shape != (h, w, ch):
+                raise ValueError("images must be H x W x C uint8 arrays of identical shape")
+            if im.strides[2] != 1 or im.strides[1] != ch:
+                im = np.ascontiguousarray(im)
+            keep.append(im)
+            ptrs[i] = im.__array_interface__["data"][0]
+            strides[i] = im.strides[0]
+        res = (OrbxResult * n)()
+        check(self._L.orbx_extract_batch_color(self._h, n, ptrs, w, h, strides, fmt, res), self._h)
+        self._last_n, self._last_shape = n, (h, w)
+        out = self._copy_results(res, n, True)
+        self._refresh_pyramids(n)
+        return out
+
     @staticmethod
     def _copy_results(res, n: int, copy: bool = True):
         """Copies the per-frame results out of the library's pinned buffers (two numpy views over the

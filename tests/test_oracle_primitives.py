@@ -113,3 +113,17 @@ def test_fast_atan2_matches_cv2(ref_available):
         a = np.float32(L.cvshim_fast_atan2(float(y), float(x)))
         b = np.float32(cv2.fastAtan2(float(y), float(x)))
         assert a.view(np.uint32) == b.view(np.uint32), (y, x, a, b)
+
+
+def test_cvtcolor_gray_closed_form_matches_cv2():
+    """SURVEY.md §8(f) row 2 (reference src/Tracking.cc:172-255): the arithmetic the CUDA conversion kernel restates,
+    gray = (B*3735 + G*19235 + R*9798 + 16384) >> 15, against the real cv2.cvtColor for all four colour orders."""
+    import cv2
+    rng = np.random.default_rng(5)
+    for ch, codes in ((3, (cv2.COLOR_BGR2GRAY, cv2.COLOR_RGB2GRAY)), (4, (cv2.COLOR_BGRA2GRAY, cv2.COLOR_RGBA2GRAY))):
+        img = rng.integers(0, 256, (301, 517, ch), dtype=np.uint8)
+        c = [img[..., i].astype(np.int64) for i in range(3)]
+        for code, (b, g, r) in zip(codes, ((c[0], c[1], c[2]), (c[2], c[1], c[0]))):
+            want = cv2.cvtColor(img, code)
+            got = ((b * 3735 + g * 19235 + r * 9798 + 16384) >> 15).astype(np.uint8)
+            assert np.array_equal(want, got)
