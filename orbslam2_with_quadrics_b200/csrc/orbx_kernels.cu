@@ -1801,7 +1801,12 @@ cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* 
     const int strips = (l1 < hp.nlevels ? hp.lv[l1].strip_base : hp.strips_per_frame) - hp.lv[l0].strip_base;
     const long long total = (long long)nframes * strips;
     long long blocks = (total + W - 1) / W;
-    const long long cap = (long long)num_sms * per_sm_cache[dev & 63];
+    // ORBX_FAST_CTAS_PER_SM (tuning): fewer resident FAST CTAs leave registers / shared memory for the kernels of the
+    // other half-batch's stream to co-run
+    static const int env_cap = getenv("ORBX_FAST_CTAS_PER_SM") ? atoi(getenv("ORBX_FAST_CTAS_PER_SM")) : 0;
+    int per_sm_eff = per_sm_cache[dev & 63];
+    if (env_cap > 0 && env_cap < per_sm_eff) per_sm_eff = env_cap;
+    const long long cap = (long long)num_sms * per_sm_eff;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     FastMaps fm;

@@ -265,3 +265,26 @@ def test_large_batch_through_both_paths_matches_single():
         for k, d in (batch[i], devres[i]):
             assert np.array_equal(k.view(np.uint8), single[i][0].view(np.uint8)) and np.array_equal(d, single[i][1])
     g1.close(); gb.close()
+
+
+def test_graph_replay_is_identical_and_survives_geometry_changes():
+    """The launch sequence is captured into a CUDA graph the second time it is seen and replayed afterwards: calls 1
+    (eager), 2 (capture) and 3+ (replay) must return the same bytes, for a batch and for single frames, and a change of
+    image size in between must drop the graphs of the old geometry."""
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["mono_tum"]
+    imgs = [fr.cluttered_scene(w, h, 70 + i) for i in range(8)]
+    small = [fr.cluttered_scene(333, 257, 90 + i) for i in range(8)]
+    ref = [orb_oracle.ORBextractor(nf, sf, nl, it, mt)(im) for im in imgs]
+    gx = ORBextractor(nf, sf, nl, it, mt, max_batch=8)
+    for rep in range(4):
+        for (kps, desc), ro in zip(gx.extract_batch(imgs), ref):
+            assert_same(kps, desc, ro)
+    first_small = gx.extract_batch(small)
+    for rep in range(3):
+        for (k0, d0), (k1, d1) in zip(first_small, gx.extract_batch(small)):
+            assert np.array_equal(k0, k1) and np.array_equal(d0, d1)
+    for rep in range(3):                                      # back to the first geometry, single frames this time
+        for im, ro in zip(imgs[:3], ref[:3]):
+            kps, desc = gx(im)
+            assert_same(kps, desc, ro)
+    gx.close()
