@@ -21,9 +21,15 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "orbx_kernels.h"
 
 namespace orbx {
+
+// One-time per-device kernel configuration (dynamic shared memory limits, occupancy queries) in the launch wrappers is
+// guarded by this mutex: handles are driven from several host threads (one handle per thread).
+static std::mutex g_config_mutex;
 
 // In global (not __constant__) memory on purpose: lane i reads ITS 32 bytes, i.e. 32 different
 // addresses per warp, which the constant cache would serialise.
@@ -1783,6 +1789,7 @@ cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* 
     static int per_sm_cache[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> config_lock(g_config_mutex);
     typedef void (*fast_fn)(const FastMaps, const OrbxPlan*, int, int, int, int, uint32_t*, uint2*, int*, int*, int*);
     fast_fn fn = hp.fast_bw == 64 ? fast_cells_kernel<64> : hp.fast_bw == 96 ? fast_cells_kernel<96> :
                  hp.fast_bw == 128 ? fast_cells_kernel<128> : fast_cells_kernel<0>;
@@ -1830,6 +1837,7 @@ cudaError_t launch_octree(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframe
     static size_t configured[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> config_lock(g_config_mutex);
     if (smem > configured[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1860,6 +1868,7 @@ cudaError_t launch_describe(const OrbxPlan* d_plan, const OrbxPlan& hp, const vo
     static int per_sm_cache[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> config_lock(g_config_mutex);
     if (!configured[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1901,6 +1910,7 @@ cudaError_t launch_stereo(const OrbxPlan* d_plan, const OrbxPlan& hp, int num_sm
     static size_t configured[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> config_lock(g_config_mutex);
     if (smem > 48 * 1024 && smem > configured[dev & 63]) {
         e = cudaFuncSetAttribute(stereo_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
