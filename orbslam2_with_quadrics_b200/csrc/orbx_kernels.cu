@@ -1720,8 +1720,9 @@ void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nfr
         launch_k(pyr_level0_kernel, grid, block, 0, st, d_plan, imgs, img_pitch, img_frame_stride, aligned16, pyr);
     } else if (L.resize8_ok && !force_resize4()) {
         const int gx = (L.ngroups8 + 31) / 32;
+        static const int min_ry = getenv("ORBX_PYR_MINRY") ? atoi(getenv("ORBX_PYR_MINRY")) : 2;      // 2: single 640x480 frame 50 -> 38 us
         int RY = PYR_RY;
-        while (RY > 4 && (long long)gx * ((L.rows + RY - 1) / RY) * nframes < (long long)num_sms * 32) RY >>= 1;
+        while (RY > min_ry && (long long)gx * ((L.rows + RY - 1) / RY) * nframes < (long long)num_sms * 32) RY >>= 1;
         dim3 grid(gx, (L.rows + 4 * RY - 1) / (4 * RY), nframes);
         launch_k(pyr_resize8_kernel, grid, dim3(128), 0, st, d_plan, l, RY, pyr, taps);
     } else {
@@ -1844,7 +1845,11 @@ cudaError_t launch_octree(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframe
         configured[dev & 63] = smem;
     }
     // 1024 threads halve the key sweeps of huge levels (4K: ~28k candidates) but cost residency on small ones
-    const int threads = (long long)hp.lv[0].w * hp.lv[0].h >= 4000000LL ? 1024 : 512;
+    static const int env_threads = getenv("ORBX_OT_THREADS") ? atoi(getenv("ORBX_OT_THREADS")) : 0;     // tuning override
+    // ... and of a lone big frame (latency mode: 1080p single frame 42.8 -> 37.8 us, while a batch of 32 gets slower)
+    const long long area0 = (long long)hp.lv[0].w * hp.lv[0].h;
+    const int threads = env_threads == 512 || env_threads == 1024 ? env_threads
+                        : (area0 >= 4000000LL || (nframes <= 2 && area0 >= 1000000LL)) ? 1024 : 512;
     const cudaError_t le = launch_k(octree_kernel, dim3(nframes * hp.nlevels), dim3(threads), smem, st, d_plan, nframes, cand,
                                     cell_rec, cand_sorted, key_node, sorted_counts, kept, kept_counts, status);
     if (le != cudaSuccess) return le;
