@@ -324,7 +324,10 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
     if (P->max_cell_h < 7) P->max_cell_h = 7;
     // FAST tiling: NC cells per TMA tile, NB tile buffers per warp, W warps per CTA (env overrides are for tuning runs)
     const char* e_nc = getenv("ORBX_FAST_NC"); const char* e_nb = getenv("ORBX_FAST_NB"); const char* e_w = getenv("ORBX_FAST_WARPS");
-    P->fast_nc = e_nc ? atoi(e_nc) : 2;       // measured best on B200 at 1080p: 2 cells per tile, single buffer, 8 warps
+    // measured best on B200 at batched 1080p: 2 cells per tile, single buffer, 8 warps.  A latency-mode handle (max_batch
+    // <= 2: the C++ adapter, one frame or one stereo pair per call) has fewer strips than resident warps, so one cell per
+    // tile halves the longest per-warp chain: single frame 640x480 0.090 -> 0.074 ms, 1080p 0.115 -> 0.111 ms
+    P->fast_nc = e_nc ? atoi(e_nc) : (h->cfg.max_batch <= 2 ? 1 : 2);
     P->fast_nb = e_nb ? atoi(e_nb) : 1;
     P->fast_warps = e_w ? atoi(e_w) : 8;
     if (P->fast_nc < 1 || P->fast_nc > 8 || P->fast_nb < 1 || P->fast_nb > 2 || P->fast_warps < 1 || P->fast_warps > ORBX_FAST_WARPS)
