@@ -104,12 +104,19 @@ def run_reference_cpu(name, frames_per_step, steps, warmup, cores):
     run(warmup, False)
     el = run(steps, True)
     fps = frames_per_step * steps / el
+    # single-thread per-image latency (the other host threads idle), SURVEY.md §8(d)
+    solo = []
+    for i in range(4):
+        t0 = time.perf_counter()
+        exs[0](imgs[i % len(imgs)])
+        solo.append((time.perf_counter() - t0) * 1e3)
     lat_ms = np.asarray(lat) * 1e3
     return {"value": fps, "unit": UNIT, "cores": nthreads, "kind": "reference",
             "sample": "%d frames/step x %d steps of %s, one thread per frame on %d host threads; "
                       "unmodified reference ORBextractor.cc on the scalar OpenCV shim (oracle/_ref)" % (
                           frames_per_step, steps, name, nthreads),
             "image_latency_ms_p50": float(np.percentile(lat_ms, 50)), "image_latency_ms_p99": float(np.percentile(lat_ms, 99)),
+            "single_thread_image_latency_ms_p50": float(np.percentile(solo, 50)),
             "elapsed_s": el}
 
 
@@ -258,6 +265,8 @@ def own_arm(args):
     ex.synchronize()
     res = ex.fetch_results(nimgs)
     kp_counts = [len(k) for k, _ in res]
+    from orbslam2_with_quadrics_b200 import _capi as _cap
+    cand_per_level = [int(len(ex.stage_dump(0, l, _cap.STAGE_CANDIDATES))) for l in range(nl)]     # FAST corners handed to the quadtree, frame 0
     if min(kp_counts) == 0:
         raise SystemExit("bench: a frame produced no keypoints; refusing to time a degenerate run")
 
@@ -414,7 +423,7 @@ def own_arm(args):
                        "distinct_frames": DISTINCT_FRAMES, "parallelism": "one camera stream per GPU, no collective",
                        "l2_policy": "per-step working set (inputs %.0f MB + pyramids %.0f MB per GPU) exceeds the 126 MB L2" % (
                            nimgs * h * pitch / 1e6, nimgs * slab / 1e6),
-                       "keypoints_per_image": n_out},
+                       "keypoints_per_image": n_out, "fast_candidates_per_level_frame0": cand_per_level},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nimgs * w * h, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "pyramid_d2h": need_pyr, "host_threads": T,
@@ -433,7 +442,7 @@ def main():
     ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
     ap.add_argument("--config", default="rgbd_1080p", choices=list(fr.CONFIGS))
     ap.add_argument("--batch", type=int, default=32, help="frames per step per GPU")
-    ap.add_argument("--latency-frames", type=int, default=200)
+    ap.add_argument("--latency-frames", type=int, default=1000, help="single-frame calls timed for p50/p99 (SURVEY §8d: >= 1000)")
     ap.add_argument("--e2e-threads", type=int, default=4, help="host threads (one handle each) in the e2e measurement; 4 measured best (640x480: 2 threads 76.8k, 3-4 threads 99.9k frames/s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stereo-match", default="device", choices=["device", "host"],
