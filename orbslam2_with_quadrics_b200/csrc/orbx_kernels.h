@@ -6,7 +6,9 @@
 
 #include "orbx_plan.h"
 
+#ifndef ORBX_FAST_WARPS
 #define ORBX_FAST_WARPS 8
+#endif
 #define ORBX_OT_THREADS 1024
 #define ORBX_OT_KEYCAP 8192     // candidates of one level kept in shared memory by the octree kernel (6 bytes each)
 
