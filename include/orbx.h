@@ -138,6 +138,25 @@ ORBX_API int orbx_extract_batch_color(orbx_handle* h, int n, const uint8_t* cons
 ORBX_API int orbx_extract_device_color(orbx_handle* h, int n, const uint8_t* d_imgs, int width, int height, size_t pitch,
                                        size_t frame_stride, int format);
 
+/* ---- Frame::UndistortKeyPoints + Frame::AssignFeaturesToGrid (reference src/Frame.cc:404-434, :230-245, PosInGrid
+ * :382-392, ComputeImageBounds :436-464) on the keypoints the last extract left in HBM: the step after the path in
+ * every Frame constructor (:88-92, :141-145, :198-202).  K4 = {fx, fy, cx, cy} (Frame::mK), dist = mDistCoef
+ * (k1, k2, p1, p2[, k3]; ndist = 4 or 5).  cv::undistortPoints is restated as the published 5-iteration algorithm in
+ * double, bit-identical to OpenCV 4.13; k1 == 0 copies the points, as the reference does.
+ * Result per frame: mvKeysUn[i].pt as n x 2 floats (all other KeyPoint fields equal mvKeys[i]), mGrid as CSR
+ * (cell gx * 48 + gy = mGrid[gx][gy], 64 x 48 cells, keypoint indices in push_back order) and mnMinX, mnMaxX, mnMinY,
+ * mnMaxY.  Pinned host memory owned by the handle, valid until its next orbx_undistort_grid call. */
+typedef struct orbx_grid_result {
+    int n;                     /* keypoints of the frame */
+    int n_in_grid;             /* entries of cell_items (keypoints that fall outside the grid are dropped, :387-388) */
+    const float* xy_un;        /* n x 2 */
+    const int32_t* cell_start; /* 64 * 48 + 1 */
+    const int32_t* cell_items;
+    float bounds[4];           /* mnMinX, mnMaxX, mnMinY, mnMaxY */
+} orbx_grid_result;
+ORBX_API int orbx_undistort_grid(orbx_handle* h, int nframes, const int* frames, const float* K4, const float* dist, int ndist,
+                                 orbx_grid_result* results);
+
 /* Pinned host buffers callers may fill with frames so that H2D copies are asynchronous DMA. */
 ORBX_API int orbx_alloc_host(size_t bytes, void** out);
 ORBX_API int orbx_free_host(void* p);

@@ -13,6 +13,10 @@ M=$REF/src/ORBmatcher.cc
 sed -n '466p' "$F" | grep -q 'void Frame::ComputeStereoMatches()' || { echo "Frame.cc:466 is not ComputeStereoMatches"; exit 1; }
 sed -n '640p' "$F" | grep -q '^}' || { echo "Frame.cc:640 is not the end of ComputeStereoMatches"; exit 1; }
 sed -n '1647p' "$M" | grep -q 'int ORBmatcher::DescriptorDistance' || { echo "ORBmatcher.cc:1647 is not DescriptorDistance"; exit 1; }
+sed -n '230p' "$F" | grep -q 'void Frame::AssignFeaturesToGrid()' || { echo "Frame.cc:230 is not AssignFeaturesToGrid"; exit 1; }
+sed -n '382p' "$F" | grep -q 'bool Frame::PosInGrid' || { echo "Frame.cc:382 is not PosInGrid"; exit 1; }
+sed -n '404p' "$F" | grep -q 'void Frame::UndistortKeyPoints()' || { echo "Frame.cc:404 is not UndistortKeyPoints"; exit 1; }
+sed -n '436p' "$F" | grep -q 'void Frame::ComputeImageBounds' || { echo "Frame.cc:436 is not ComputeImageBounds"; exit 1; }
 TMP=$(mktemp -d)
 trap 'rm -rf "$TMP"' EXIT
 {
@@ -21,6 +25,10 @@ trap 'rm -rf "$TMP"' EXIT
   sed -n '37,39p' "$M"
   sed -n '1647,1663p' "$M"
   sed -n '466,640p' "$F"
+  sed -n '230,245p' "$F"
+  sed -n '382,392p' "$F"
+  sed -n '404,434p' "$F"
+  sed -n '436,464p' "$F"
   echo '}'
 } > "$TMP/stereo_ref_gen.cpp"
 mkdir -p "$OUT"

@@ -1,9 +1,10 @@
-// OpenCV / ORB-SLAM2 *stub* for the stereo matcher -- TEST INFRASTRUCTURE (oracle/), not product code.
+// OpenCV / ORB-SLAM2 *stub* for the Frame-level consumers -- TEST INFRASTRUCTURE (oracle/), not product code.
 //
 // oracle/build_stereo_ref.sh compiles the reference's own lines of Frame::ComputeStereoMatches
-// (/root/reference/src/Frame.cc:466-640) and ORBmatcher::DescriptorDistance / TH_HIGH / TH_LOW
-// (/root/reference/src/ORBmatcher.cc:37-38, :1647-1663), taken from where they lie at build time, against
-// this header: the handful of cv:: types those lines use (8U / 32F Mat views, convertTo, ones, scalar * Mat,
+// (/root/reference/src/Frame.cc:466-640), ORBmatcher::DescriptorDistance / TH_HIGH / TH_LOW
+// (/root/reference/src/ORBmatcher.cc:37-38, :1647-1663) and Frame::AssignFeaturesToGrid / PosInGrid /
+// UndistortKeyPoints / ComputeImageBounds (Frame.cc:230-245, :382-392, :404-434, :436-464), taken from where they lie at
+// build time, against this header: the handful of cv:: types those lines use (8U / 32F Mat views, convertTo, ones, scalar * Mat,
 // Mat - Mat, norm L1) and the members of Frame / ORBextractor / ORBmatcher they touch.  Written from scratch.
 #ifndef ORBX_ORACLE_STEREO_SHIM_H
 #define ORBX_ORACLE_STEREO_SHIM_H
@@ -62,6 +63,8 @@ public:
     template <typename T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * step); }
     template <typename T> T& at(int r, int c) { return ((T*)(data + (size_t)r * step))[c]; }
     template <typename T> const T& at(int r, int c) const { return ((const T*)(data + (size_t)r * step))[c]; }
+    template <typename T> T& at(int i) { return cols == 1 ? at<T>(i, 0) : at<T>(0, i); }                 // vectors (Frame.cc:406)
+    template <typename T> const T& at(int i) const { return cols == 1 ? at<T>(i, 0) : at<T>(0, i); }
     // dst may be *this (IL.convertTo(IL, CV_32F), Frame.cc:566): build the result first, then assign
     void convertTo(Mat& dst, int d) const {
         Mat out(rows, cols, d);
@@ -72,6 +75,7 @@ public:
             }
         dst = out;
     }
+    Mat reshape(int cn) const { (void)cn; return *this; }      // N x 2 floats either way (Frame.cc:421-423, :449-451)
     static Mat ones(int r, int c, int d) {
         Mat m(r, c, d);
         for (int i = 0; i < r; ++i)
@@ -101,7 +105,40 @@ static inline double norm(const Mat& a, const Mat& b, int type) {    // NORM_L1 
     return s;
 }
 
+// cv::undistortPoints(src, dst, K, D, R = empty, P = K) for N x 2 float points: the iterative inverse of OpenCV's
+// distortion model, 5 iterations, evaluated in double (restated from the published algorithm; pinned against the real
+// cv2.undistortPoints bit for bit by tests/test_frame_oracle.py).  K, D: CV_32F; D holds k1 k2 p1 p2 [k3].
+static inline void undistortPoints(const Mat& src, Mat& dst, const Mat& K, const Mat& D, const Mat& R, const Mat& P) {
+    (void)R;
+    const double fx = K.at<float>(0, 0), fy = K.at<float>(1, 1), cx = K.at<float>(0, 2), cy = K.at<float>(1, 2);
+    const double pfx = P.at<float>(0, 0), pfy = P.at<float>(1, 1), pcx = P.at<float>(0, 2), pcy = P.at<float>(1, 2);
+    double k[12] = {0};
+    const int nd = D.rows * D.cols;
+    for (int i = 0; i < nd && i < 12; ++i) k[i] = ((const float*)D.data)[i];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    Mat out(src.rows, 2, CV_32F);
+    for (int i = 0; i < src.rows; ++i) {
+        double x = (src.at<float>(i, 0) - cx) * ifx, y = (src.at<float>(i, 1) - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; ++j) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+            const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        const double xx = pfx * x + 0 * y + pcx, yy = 0 * x + pfy * y + pcy, ww = 1. / (0 * x + 0 * y + 1.);
+        out.at<float>(i, 0) = (float)(xx * ww);
+        out.at<float>(i, 1) = (float)(yy * ww);
+    }
+    dst = out;
+}
+
 }  // namespace cv
+
+#define FRAME_GRID_ROWS 48          // include/Frame.h:39-40
+#define FRAME_GRID_COLS 64
 
 namespace ORB_SLAM2 {
 
@@ -120,6 +157,14 @@ struct ORBextractor {
 class Frame {
 public:
     void ComputeStereoMatches();
+    void AssignFeaturesToGrid();
+    bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
+    void UndistortKeyPoints();
+    void ComputeImageBounds(const cv::Mat& imLeft);
+    std::vector<cv::KeyPoint> mvKeysUn;
+    cv::Mat mK, mDistCoef;
+    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    static float mnMinX, mnMaxX, mnMinY, mnMaxY, mfGridElementWidthInv, mfGridElementHeightInv;
     int N;
     std::vector<cv::KeyPoint> mvKeys, mvKeysRight;
     std::vector<float> mvuRight, mvDepth;

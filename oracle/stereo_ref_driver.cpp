@@ -37,3 +37,45 @@ extern "C" int stereoref_match(int nL, const float* kpL /* nL x 7, cv::KeyPoint 
     for (int i = 0; i < nL; ++i) { uRight[i] = F.mvuRight[i]; depth[i] = F.mvDepth[i]; }
     return 0;
 }
+
+// Frame::ComputeImageBounds + the grid scale set-up of the Frame constructors (src/Frame.cc:148-156) +
+// UndistortKeyPoints + AssignFeaturesToGrid, the reference's own lines.  K = {fx, fy, cx, cy}; D = nd distortion floats.
+// Outputs: undistorted (x, y) per keypoint, the 64 x 48 grid as CSR (cell gx * 48 + gy = mGrid[gx][gy], indices in
+// push_back order) and the four image bounds.
+namespace ORB_SLAM2 {
+float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv;
+}
+extern "C" int frameref_undistort_grid(int n, const float* kp, const float* K, const float* D, int nd, int width, int height,
+                                       float* xy_un, int* cell_start, int* cell_items, float* bounds) {
+    using namespace ORB_SLAM2;
+    Frame F;
+    F.N = n;
+    F.mvKeys.resize(n);
+    for (int i = 0; i < n; ++i) {
+        const float* q = kp + 7 * i;
+        F.mvKeys[i].pt.x = q[0]; F.mvKeys[i].pt.y = q[1]; F.mvKeys[i].size = q[2]; F.mvKeys[i].angle = q[3];
+        F.mvKeys[i].response = q[4];
+        memcpy(&F.mvKeys[i].octave, q + 5, 4); memcpy(&F.mvKeys[i].class_id, q + 6, 4);
+    }
+    F.mK = cv::Mat(3, 3, CV_32F);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) F.mK.at<float>(r, c) = r == c ? 1.f : 0.f;
+    F.mK.at<float>(0, 0) = K[0]; F.mK.at<float>(1, 1) = K[1]; F.mK.at<float>(0, 2) = K[2]; F.mK.at<float>(1, 2) = K[3];
+    F.mDistCoef = cv::Mat(nd, 1, CV_32F);
+    for (int i = 0; i < nd; ++i) F.mDistCoef.at<float>(i, 0) = D[i];
+    cv::Mat im(height, width, CV_8U);
+    F.ComputeImageBounds(im);
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(Frame::mnMaxX - Frame::mnMinX);    // (:155)
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(Frame::mnMaxY - Frame::mnMinY);   // (:156)
+    F.UndistortKeyPoints();
+    F.AssignFeaturesToGrid();
+    for (int i = 0; i < n; ++i) { xy_un[2 * i] = F.mvKeysUn[i].pt.x; xy_un[2 * i + 1] = F.mvKeysUn[i].pt.y; }
+    int pos = 0;
+    for (int gx = 0; gx < FRAME_GRID_COLS; ++gx)
+        for (int gy = 0; gy < FRAME_GRID_ROWS; ++gy) {
+            cell_start[gx * FRAME_GRID_ROWS + gy] = pos;
+            for (size_t k = 0; k < F.mGrid[gx][gy].size(); ++k) cell_items[pos++] = (int)F.mGrid[gx][gy][k];
+        }
+    cell_start[FRAME_GRID_COLS * FRAME_GRID_ROWS] = pos;
+    bounds[0] = Frame::mnMinX; bounds[1] = Frame::mnMaxX; bounds[2] = Frame::mnMinY; bounds[3] = Frame::mnMaxY;
+    return pos;
+}

@@ -87,6 +87,9 @@ struct orbx_handle {
     int st_right_cap, st_pairs_n;
     int* d_st_rows;           // row table of the RIGHT handle's frames (vRowIndices): row_start, (height + 1) per frame
     uint16_t* d_st_bucket;    // ... and the keypoint indices listed per row
+    // undistort + grid (orbx_undistort_grid; allocated on first use)
+    float *d_un_xy, *h_un_xy;
+    int *d_un_start, *d_un_items, *d_un_frames, *h_un_start, *h_un_items, *h_un_frames;
     cudaEvent_t ev_stereo;
     int last_n;
     bool pyramid_valid;
@@ -377,6 +380,9 @@ void free_geometry(orbx_handle* h) {
     cudaFreeHost(h->h_counters); cudaFreeHost(h->h_out_kp); cudaFreeHost(h->h_out_desc); cudaFreeHost(h->h_pyr);
     cudaFreeHost(h->h_input);
     cudaFree(h->d_color); cudaFreeHost(h->h_color); h->d_color = h->h_color = 0; h->color_bytes = 0;
+    cudaFree(h->d_un_xy); cudaFree(h->d_un_start); cudaFree(h->d_un_items); cudaFree(h->d_un_frames);
+    cudaFreeHost(h->h_un_xy); cudaFreeHost(h->h_un_start); cudaFreeHost(h->h_un_items); cudaFreeHost(h->h_un_frames);
+    h->d_un_xy = h->h_un_xy = 0; h->d_un_start = h->d_un_items = h->d_un_frames = h->h_un_start = h->h_un_items = h->h_un_frames = 0;
     cudaFree(h->d_st_u); cudaFree(h->d_st_depth); cudaFree(h->d_st_sad); cudaFree(h->d_st_pairs); cudaFree(h->d_st_rows); cudaFree(h->d_st_bucket); h->d_st_rows = 0; h->d_st_bucket = 0;
     cudaFreeHost(h->h_st); cudaFreeHost(h->h_st_pairs);
     h->d_st_u = h->d_st_depth = h->h_st = 0; h->d_st_sad = h->d_st_pairs = h->h_st_pairs = 0;
@@ -681,6 +687,7 @@ int orbx_create(const orbx_config* cfg, orbx_handle** out) {
     h->d_st_u = h->d_st_depth = h->h_st = 0; h->d_st_sad = h->d_st_pairs = h->h_st_pairs = 0; h->d_st_rows = 0; h->d_st_bucket = 0;
     h->last_n = 0; h->pyramid_valid = false;
     h->use_graphs = getenv("ORBX_NO_GRAPHS") == nullptr;
+    h->d_un_xy = h->h_un_xy = 0; h->d_un_start = h->d_un_items = h->d_un_frames = h->h_un_start = h->h_un_items = h->h_un_frames = 0;
     h->d_color = h->h_color = 0; h->color_bytes = 0;
     h->timing = false; h->ev_created = false; h->ev_head = 0; h->ev_pending = 0;
     memset(h->stage_ms, 0, sizeof h->stage_ms);
@@ -1020,6 +1027,99 @@ int orbx_extract_batch_color(orbx_handle* h, int n, const uint8_t* const* imgs, 
     rc = orbx_extract_device_color(h, n, h->d_color, width, height, cp, cf, format);
     if (rc != ORBX_OK) return rc;
     return fetch(h, n, results);
+}
+
+// ---- Frame::UndistortKeyPoints + AssignFeaturesToGrid on the device-resident keypoints
+namespace {
+// cv::undistortPoints(K, D, R = I, P = K) of one point, the published 5-iteration algorithm in double (the kernel
+// evaluates the same expression tree); used here for the four image corners of Frame::ComputeImageBounds (:436-464).
+void undistort_point_host(const double* cam, double u, double v, float* ox, float* oy) {
+    const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
+    const double k1 = cam[4], k2 = cam[5], p1 = cam[6], p2 = cam[7], k3 = cam[8];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    double x = (u - cx) * ifx, y = (v - cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; ++j) {
+        const double r2 = x * x + y * y;
+        const double icdist = 1. / (1 + ((k3 * r2 + k2) * r2 + k1) * r2);
+        const double deltaX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x) + 0. * r2 + 0. * r2 * r2;
+        const double deltaY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y + 0. * r2 + 0. * r2 * r2;
+        x = (x0 - deltaX) * icdist;
+        y = (y0 - deltaY) * icdist;
+    }
+    *ox = (float)(fx * x + 0 * y + cx);
+    *oy = (float)(0 * x + fy * y + cy);
+}
+}  // namespace
+
+int orbx_undistort_grid(orbx_handle* h, int nframes, const int* frames, const float* K4, const float* dist, int ndist,
+                        orbx_grid_result* results) {
+    if (!h || !K4 || !dist || !results || nframes < 1 || nframes > h->cfg.max_batch || ndist < 4 || ndist > 5 || !h->have_plan)
+        return ORBX_ERR_BAD_ARGS;
+    if (!(K4[0] != 0.f) || !(K4[1] != 0.f)) return ORBX_ERR_BAD_ARGS;
+    for (int i = 0; i < nframes; ++i) {
+        const int f = frames ? frames[i] : i;
+        if (f < 0 || f >= h->last_n) return ORBX_ERR_BAD_ARGS;
+        for (int k = 0; k < i; ++k)
+            if ((frames ? frames[k] : k) == f) return ORBX_ERR_BAD_ARGS;      // results are stored per frame
+    }
+    CK(h, cudaSetDevice(h->cfg.device));
+    const OrbxPlan& P = h->plan;
+    const size_t B = (size_t)h->cfg.max_batch, kpf = (size_t)P.kept_per_frame, NC = 64 * 48 + 1;
+    if (!h->d_un_xy) {
+        CK(h, cudaMalloc(&h->d_un_xy, B * kpf * 8));
+        CK(h, cudaMalloc(&h->d_un_start, B * NC * 4));
+        CK(h, cudaMalloc(&h->d_un_items, B * kpf * 4));
+        CK(h, cudaMalloc(&h->d_un_frames, B * 4));
+        CK(h, cudaMallocHost(&h->h_un_xy, B * kpf * 8));
+        CK(h, cudaMallocHost(&h->h_un_start, B * NC * 4));
+        CK(h, cudaMallocHost(&h->h_un_items, B * kpf * 4));
+        CK(h, cudaMallocHost(&h->h_un_frames, B * 4));
+    }
+    // Frame::ComputeImageBounds (:436-464) and the grid scale of the Frame constructors (:155-156)
+    double cam[9] = {K4[0], K4[1], K4[2], K4[3], dist[0], dist[1], dist[2], dist[3], ndist > 4 ? dist[4] : 0.f};
+    const int distorted = dist[0] != 0.0f;                                   // mDistCoef.at<float>(0) != 0.0 (:406, :438)
+    float bounds[4];
+    if (distorted) {
+        float cx[4], cy[4];
+        const double W = (double)(float)P.width, H = (double)(float)P.height;
+        undistort_point_host(cam, 0., 0., &cx[0], &cy[0]);
+        undistort_point_host(cam, W, 0., &cx[1], &cy[1]);
+        undistort_point_host(cam, 0., H, &cx[2], &cy[2]);
+        undistort_point_host(cam, W, H, &cx[3], &cy[3]);
+        bounds[0] = cx[0] < cx[2] ? cx[0] : cx[2];                             // mnMinX = min(corner 0, corner 2)
+        bounds[1] = cx[1] > cx[3] ? cx[1] : cx[3];                             // mnMaxX
+        bounds[2] = cy[0] < cy[1] ? cy[0] : cy[1];                             // mnMinY
+        bounds[3] = cy[2] > cy[3] ? cy[2] : cy[3];                             // mnMaxY
+    } else {
+        bounds[0] = 0.f; bounds[1] = (float)P.width; bounds[2] = 0.f; bounds[3] = (float)P.height;
+    }
+    const float grid[4] = {bounds[0], bounds[2], 64.f / (bounds[1] - bounds[0]), 48.f / (bounds[3] - bounds[2])};
+    cudaStream_t st = h->stream;
+    CK(h, cudaStreamSynchronize(st));                                        // the pinned staging of a previous call is free
+    for (int i = 0; i < nframes; ++i) h->h_un_frames[i] = frames ? frames[i] : i;
+    CK(h, cudaMemcpyAsync(h->d_un_frames, h->h_un_frames, (size_t)nframes * 4, cudaMemcpyHostToDevice, st));
+    CK(h, orbx::launch_undistort_grid(h->d_plan, P, h->d_out_kp, h->d_kept_counts(), h->d_un_frames, nframes, cam, distorted, grid,
+                                      h->d_un_xy, h->d_un_start, h->d_un_items, st));
+    h->launches += 1;
+    const size_t n = (size_t)h->last_n;
+    CK(h, cudaMemcpyAsync(h->h_un_xy, h->d_un_xy, n * kpf * 8, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h->h_un_start, h->d_un_start, n * NC * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h->h_un_items, h->d_un_items, n * kpf * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int) * h->counters_count(), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    for (int i = 0; i < nframes; ++i) {
+        const int f = h->h_un_frames[i];
+        int total = 0;
+        for (int l = 0; l < P.nlevels; ++l) total += h->h_kept_counts()[f * P.nlevels + l];
+        results[i].n = total;
+        results[i].xy_un = h->h_un_xy + (size_t)f * kpf * 2;
+        results[i].cell_start = h->h_un_start + (size_t)f * NC;
+        results[i].cell_items = h->h_un_items + (size_t)f * kpf;
+        results[i].n_in_grid = results[i].cell_start[NC - 1];
+        for (int k = 0; k < 4; ++k) results[i].bounds[k] = bounds[k];
+    }
+    return ORBX_OK;
 }
 
 int orbx_alloc_host(size_t bytes, void** out) {

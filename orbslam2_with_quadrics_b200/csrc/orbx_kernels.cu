@@ -1684,6 +1684,104 @@ stereo_filter_kernel(const OrbxPlan* __restrict__ plan, const int* __restrict__ 
 }
 
 // =====================================================================================
+// Frame::UndistortKeyPoints + Frame::AssignFeaturesToGrid (reference src/Frame.cc:404-434, :230-245, PosInGrid :382-392;
+// SURVEY.md §8(f) row 3), one CTA per frame on the keypoints the extraction left in HBM.
+//   1. cv::undistortPoints(K, D, R = I, P = K): the 5-iteration inverse of OpenCV's distortion model in double with
+//      individually rounded operations (bit-identical to cv2 4.13 on 60 000 test points), result narrowed to float;
+//      k1 == 0 copies the points (:406-410).
+//   2. PosInGrid: round((x - mnMinX) * mfGridElementWidthInv) in float32, cells outside 64 x 48 dropped.
+//   3. mGrid[gx][gy] as CSR: per-cell counts (shared-memory atomics), exclusive scan, and a STABLE fill -- a keypoint's
+//      slot inside its cell is the number of earlier keypoints of the same cell, i.e. the reference's push_back order.
+// =====================================================================================
+struct UndistortParams {
+    double fx, fy, cx, cy, ifx, ify;
+    double k[5];                    // k1 k2 p1 p2 k3
+    int distorted;                  // mDistCoef(0) != 0
+    float min_x, min_y, winv, hinv; // mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv
+};
+#define UG_COLS 64
+#define UG_ROWS 48
+
+__global__ void __launch_bounds__(1024)
+undistort_grid_kernel(const OrbxPlan* __restrict__ plan, const float* __restrict__ kp, const int* __restrict__ kept_counts,
+                      const int* __restrict__ frames, UndistortParams P, float* __restrict__ xy_un, int* __restrict__ cell_start,
+                      int* __restrict__ cell_items) {
+    extern __shared__ int ug_smem[];
+    __shared__ int s_warp[33];
+    int* cnt = ug_smem;                                  // UG_COLS * UG_ROWS counters, then running starts
+    int* cell = ug_smem + UG_COLS * UG_ROWS;             // cell of every keypoint (-1: outside the grid)
+    const int kpf = plan->kept_per_frame, nl = plan->nlevels;
+    const int f = frames[blockIdx.x];
+    int N = 0;
+    for (int l = 0; l < nl; ++l) N += kept_counts[f * nl + l];
+    for (int c = threadIdx.x; c < UG_COLS * UG_ROWS; c += blockDim.x) cnt[c] = 0;
+    __syncthreads();
+    const float* k0 = kp + (size_t)f * kpf * 7;
+    float* out = xy_un + (size_t)f * kpf * 2;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        float ux = k0[(size_t)i * 7], uy = k0[(size_t)i * 7 + 1];
+        if (P.distorted) {
+            double x = __dmul_rn(__dsub_rn((double)ux, P.cx), P.ifx), y = __dmul_rn(__dsub_rn((double)uy, P.cy), P.ify);
+            const double x0 = x, y0 = y;
+#pragma unroll 1
+            for (int j = 0; j < 5; ++j) {
+                const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+                // k4..k6 = 0: the numerator polynomial is 1 + ((0*r2 + 0)*r2 + 0)*r2 = 1
+                const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(P.k[4], r2), P.k[1]), r2), P.k[0]), r2));
+                const double icdist = __ddiv_rn(1.0, den);
+                const double xy2 = __dmul_rn(__dmul_rn(__dmul_rn(2.0, P.k[2]), x), y);                   // 2*p1*x*y
+                const double dX = __dadd_rn(__dadd_rn(__dadd_rn(xy2, __dmul_rn(P.k[3], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x)))),
+                                                      __dmul_rn(0.0, r2)), __dmul_rn(__dmul_rn(0.0, r2), r2));
+                const double yx2 = __dmul_rn(__dmul_rn(__dmul_rn(2.0, P.k[3]), x), y);                   // 2*p2*x*y
+                const double dY = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.k[2], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y))), yx2),
+                                                      __dmul_rn(0.0, r2)), __dmul_rn(__dmul_rn(0.0, r2), r2));
+                x = __dmul_rn(__dsub_rn(x0, dX), icdist);
+                y = __dmul_rn(__dsub_rn(y0, dY), icdist);
+            }
+            const double xx = __dadd_rn(__dadd_rn(__dmul_rn(P.fx, x), __dmul_rn(0.0, y)), P.cx);
+            const double yy = __dadd_rn(__dadd_rn(__dmul_rn(0.0, x), __dmul_rn(P.fy, y)), P.cy);
+            ux = (float)xx;                                                // ww = 1 / (0*x + 0*y + 1) = 1
+            uy = (float)yy;
+        }
+        out[2 * i] = ux;
+        out[2 * i + 1] = uy;
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(ux, P.min_x), P.winv));          // PosInGrid (:384-385)
+        const int py = (int)roundf(__fmul_rn(__fsub_rn(uy, P.min_y), P.hinv));
+        int c = -1;
+        if (px >= 0 && px < UG_COLS && py >= 0 && py < UG_ROWS) {
+            c = px * UG_ROWS + py;
+            atomicAdd(&cnt[c], 1);
+        }
+        cell[i] = c;
+    }
+    __syncthreads();
+    // exclusive scan over the 3072 cells: thread t owns 3 consecutive cells
+    const int per = (UG_COLS * UG_ROWS + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int c0 = threadIdx.x * per, c1 = min(c0 + per, UG_COLS * UG_ROWS);
+    int local = 0;
+    for (int c = c0; c < c1; ++c) local += cnt[c];
+    int total;
+    int run = block_excl_scan(local, &total, s_warp);
+    int* cs = cell_start + (size_t)f * (UG_COLS * UG_ROWS + 1);
+    for (int c = c0; c < c1; ++c) {
+        const int v = cnt[c];
+        cnt[c] = run;
+        cs[c] = run;
+        run += v;
+    }
+    if (threadIdx.x == 0) cs[UG_COLS * UG_ROWS] = total;
+    __syncthreads();
+    int* items = cell_items + (size_t)f * kpf;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const int c = cell[i];
+        if (c < 0) continue;
+        int rank = 0;
+        for (int j = 0; j < i; ++j) rank += cell[j] == c;                  // push_back order (:243)
+        items[cnt[c] + rank] = i;
+    }
+}
+
+// =====================================================================================
 // launch wrappers (called from orbx_api.cu)
 // =====================================================================================
 // format: 1 BGR8, 2 RGB8, 3 BGRA8, 4 RGBA8 (orbx_pixel_format)
@@ -1890,6 +1988,30 @@ cudaError_t launch_describe(const OrbxPlan* d_plan, const OrbxPlan& hp, const vo
     memcpy(&fm, maps, sizeof fm);
     return launch_k(describe_kernel, dim3((unsigned)blocks), dim3(KP_WARPS * 32), smem, st, fm, d_plan, frame0, nframes, kept,
                     kept_counts, angles, out_kp, out_desc);
+}
+
+cudaError_t launch_undistort_grid(const OrbxPlan* d_plan, const OrbxPlan& hp, const float* kp, const int* kept_counts,
+                                  const int* d_frames, int nframes, const double* cam /* fx fy cx cy k1 k2 p1 p2 k3 */, int distorted,
+                                  const float* grid /* mnMinX mnMinY winv hinv */, float* xy_un, int* cell_start, int* cell_items,
+                                  cudaStream_t st) {
+    UndistortParams P;
+    P.fx = cam[0]; P.fy = cam[1]; P.cx = cam[2]; P.cy = cam[3];
+    P.ifx = 1. / cam[0]; P.ify = 1. / cam[1];
+    for (int i = 0; i < 5; ++i) P.k[i] = cam[4 + i];
+    P.distorted = distorted;
+    P.min_x = grid[0]; P.min_y = grid[1]; P.winv = grid[2]; P.hinv = grid[3];
+    const size_t smem = (size_t)(UG_COLS * UG_ROWS + hp.kept_per_frame) * sizeof(int);
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> config_lock(g_config_mutex);
+    if (smem > 48 * 1024 && smem > configured[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(undistort_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev & 63] = smem;
+    }
+    return launch_k(undistort_grid_kernel, dim3((unsigned)nframes), dim3(1024), smem, st, d_plan, kp, kept_counts, d_frames, P, xy_un,
+                    cell_start, cell_items);
 }
 
 size_t stereo_bucket_entries(const OrbxPlan& hp) { return (size_t)hp.kept_per_frame * ST_MAX_SPAN; }

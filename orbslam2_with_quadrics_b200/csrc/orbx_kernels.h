@@ -47,4 +47,9 @@ cudaError_t launch_stereo(const OrbxPlan* d_plan, const OrbxPlan& hp, int num_sm
                           int* sad, int* row_start, uint16_t* bucket, cudaStream_t st);
 size_t stereo_bucket_entries(const OrbxPlan& hp);     // uint16 entries of one right frame's row table
 
+// Frame::UndistortKeyPoints + AssignFeaturesToGrid (src/Frame.cc:404-434, :230-245) on the device-resident keypoints
+cudaError_t launch_undistort_grid(const OrbxPlan* d_plan, const OrbxPlan& hp, const float* kp, const int* kept_counts,
+                                  const int* d_frames, int nframes, const double* cam, int distorted, const float* grid, float* xy_un,
+                                  int* cell_start, int* cell_items, cudaStream_t st);
+
 }  // namespace orbx

@@ -231,6 +231,24 @@ class ORBextractor:
         check(self._L.orbx_stereo_match_device(self._h, right._h, n, (C.c_int * n)(*left_frames), (C.c_int * n)(*right_frames),
                                                mbf, mb), self._h)
 
+    # ---------------------------------------------------------------- Frame::UndistortKeyPoints + AssignFeaturesToGrid
+    def undistort_grid(self, K4, dist, frames=None):
+        """(src/Frame.cc:404-434, :230-245) on the keypoints of the last extract.  K4 = (fx, fy, cx, cy); dist = (k1, k2,
+        p1, p2[, k3]).  Returns per frame (xy_un (n, 2), cell_start (64*48+1,), cell_items, bounds (4,))."""
+        n = len(frames) if frames is not None else self._last_n
+        fr_ = (C.c_int * n)(*frames) if frames is not None else None
+        k = (C.c_float * 4)(*K4)
+        d = (C.c_float * len(dist))(*dist)
+        res = (_capi.OrbxGridResult * n)()
+        check(self._L.orbx_undistort_grid(self._h, n, fr_, k, d, len(dist), res), self._h)
+        out = []
+        for r in res:
+            xy = np.ctypeslib.as_array(C.cast(r.xy_un, C.POINTER(C.c_float)), shape=(max(r.n, 1) * 2,))[:2 * r.n].reshape(-1, 2).copy()
+            st = np.ctypeslib.as_array(C.cast(r.cell_start, C.POINTER(C.c_int32)), shape=(64 * 48 + 1,)).copy()
+            it = np.ctypeslib.as_array(C.cast(r.cell_items, C.POINTER(C.c_int32)), shape=(max(r.n_in_grid, 1),))[:r.n_in_grid].copy()
+            out.append((xy, st, it, np.array(list(r.bounds), np.float32)))
+        return out
+
     # ---------------------------------------------------------------- stage dumps (parity tests)
     def stage_dump(self, frame: int, level: int, stage: int):
         nbytes = C.c_size_t()
