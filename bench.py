@@ -441,7 +441,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
     ap.add_argument("--config", default="rgbd_1080p", choices=list(fr.CONFIGS))
-    ap.add_argument("--batch", type=int, default=32, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU (1080p: 32 -> 37.2k, 64 -> 39.4k, 128 -> 40.2k, 256 -> 40.7k frames/s)")
     ap.add_argument("--latency-frames", type=int, default=1000, help="single-frame calls timed for p50/p99 (SURVEY §8d: >= 1000)")
     ap.add_argument("--e2e-threads", type=int, default=4, help="host threads (one handle each) in the e2e measurement; 4 measured best (640x480: 2 threads 76.8k, 3-4 threads 99.9k frames/s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
