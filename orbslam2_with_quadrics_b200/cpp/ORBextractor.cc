@@ -151,4 +151,28 @@ void ORBextractor::ComputeStereoMatches(ORBextractor& left, ORBextractor& right,
     mvDepth.assign(r.depth, r.depth + r.n);
 }
 
+void ORBextractor::UndistortAndAssignToGrid(const cv::Mat& mK, const cv::Mat& mDistCoef, const std::vector<cv::KeyPoint>& mvKeys,
+                                            std::vector<cv::KeyPoint>& mvKeysUn, std::vector<std::size_t> (*mGrid)[48],
+                                            float& mnMinX, float& mnMaxX, float& mnMinY, float& mnMaxY)
+{
+    const float K4[4] = {mK.at<float>(0,0), mK.at<float>(1,1), mK.at<float>(0,2), mK.at<float>(1,2)};
+    float dist[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    const int nd = mDistCoef.rows * mDistCoef.cols >= 5 ? 5 : 4;
+    for (int i = 0; i < nd; ++i)
+        dist[i] = mDistCoef.cols == 1 ? mDistCoef.at<float>(i,0) : mDistCoef.at<float>(0,i);
+    orbx_grid_result r;
+    int rc = orbx_undistort_grid(handle_, 1, 0, K4, dist, nd, &r);
+    if (rc != ORBX_OK) orbx_throw(handle_, rc, "orbx_undistort_grid");
+    if ((size_t)r.n != mvKeys.size()) throw std::runtime_error("ORBextractor (orbx): mvKeys is not the result of the last operator()");
+    mvKeysUn = mvKeys;                                 // (:427-432) every field but pt is copied
+    for (int i = 0; i < r.n; ++i) { mvKeysUn[i].pt.x = r.xy_un[2*i]; mvKeysUn[i].pt.y = r.xy_un[2*i+1]; }
+    for (int gx = 0; gx < 64; ++gx)
+        for (int gy = 0; gy < 48; ++gy)
+        {
+            const int c = gx * 48 + gy;
+            mGrid[gx][gy].assign(r.cell_items + r.cell_start[c], r.cell_items + r.cell_start[c+1]);
+        }
+    mnMinX = r.bounds[0]; mnMaxX = r.bounds[1]; mnMinY = r.bounds[2]; mnMaxY = r.bounds[3];
+}
+
 } //namespace ORB_SLAM

@@ -68,6 +68,14 @@ public:
     static void ComputeStereoMatches(ORBextractor& left, ORBextractor& right, float mbf, float mb,
                                      std::vector<float>& mvuRight, std::vector<float>& mvDepth);
 
+    // Frame::UndistortKeyPoints + Frame::AssignFeaturesToGrid (reference src/Frame.cc:404-434, :230-245) on the GPU, over
+    // the keypoints this extractor still holds in HBM from its last operator(): fills mvKeysUn (= mvKeys with undistorted
+    // pt), mGrid[FRAME_GRID_COLS = 64][FRAME_GRID_ROWS = 48] in the reference's push_back order and the image bounds of
+    // Frame::ComputeImageBounds (:436-464).  mK, mDistCoef: Frame::mK (3x3 CV_32F), Frame::mDistCoef (4 or 5 x 1 CV_32F).
+    void UndistortAndAssignToGrid(const cv::Mat& mK, const cv::Mat& mDistCoef, const std::vector<cv::KeyPoint>& mvKeys,
+                                  std::vector<cv::KeyPoint>& mvKeysUn, std::vector<std::size_t> (*mGrid)[48],
+                                  float& mnMinX, float& mnMaxX, float& mnMinY, float& mnMaxY);
+
 private:
     ORBextractor(const ORBextractor&);
     ORBextractor& operator=(const ORBextractor&);

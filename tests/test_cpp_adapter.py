@@ -35,7 +35,9 @@ def test_adapter_compiles_against_the_reference_api_surface():
     for sym in ("ORB_SLAM2::ORBextractor::ORBextractor(int, float, int, int, int)",
                 "ORB_SLAM2::ORBextractor::operator()(cv::_InputArray const&, cv::_InputArray const&, std::vector<cv::KeyPoint",
                 "ORB_SLAM2::ORBextractor::GetScaleFactors()", "ORB_SLAM2::ORBextractor::GetInverseScaleSigmaSquares()",
-                "ORB_SLAM2::ORBextractor::GetLevels()", "ORB_SLAM2::ORBextractor::GetScaleFactor()"):
+                "ORB_SLAM2::ORBextractor::GetLevels()", "ORB_SLAM2::ORBextractor::GetScaleFactor()",
+                "ORB_SLAM2::ORBextractor::ComputeStereoMatches(", "ORB_SLAM2::ORBextractor::UndistortAndAssignToGrid(",
+                "ORB_SLAM2::ORBextractor::SetColorOrder(bool)"):
         assert sym in out, sym
 
 
