@@ -265,8 +265,7 @@ def own_arm(args):
     ex.synchronize()
     res = ex.fetch_results(nimgs)
     kp_counts = [len(k) for k, _ in res]
-    from orbslam2_with_quadrics_b200 import _capi as _cap
-    cand_per_level = [int(len(ex.stage_dump(0, l, _cap.STAGE_CANDIDATES))) for l in range(nl)]     # FAST corners handed to the quadtree, frame 0
+    cand_per_level, retries_per_level = ex.fast_stats(0)     # FAST corners handed to the quadtree / cells re-run at minThFAST, frame 0
     if min(kp_counts) == 0:
         raise SystemExit("bench: a frame produced no keypoints; refusing to time a degenerate run")
 
@@ -349,9 +348,9 @@ def own_arm(args):
     slab = sum(((32 + lw + 19 + 63) // 64 * 64) * (lh + 38) for lw, lh in geo.level_sizes(w, h, sf, nl))
     kept_cap = sum(q + 4 * int(np.floor(float(np.float32(lw - 32) / np.float32(lh - 32)) + 0.5)) + 8
                    for q, (lw, lh) in zip(geo.level_quotas(nf, sf, nl), geo.level_sizes(w, h, sf, nl)))
-    d2h = nimgs * kept_cap * 60 + 4 * (nimgs * (3 * nl + 1) + 8) + (nimgs * slab if need_pyr else 0)   # what the library copies
+    d2h = nimgs * kept_cap * 60 + 4 * (nimgs * (4 * nl + 1) + 16) + (nimgs * slab if need_pyr else 0)   # what the library copies
     if stereo_dev:
-        d2h += nimgs * kept_cap * 8 + 4 * (nimgs * (3 * nl + 1) + 8)     # mvuRight + mvDepth of the batch, counters again
+        d2h += nimgs * kept_cap * 8 + 4 * (nimgs * (4 * nl + 1) + 16)     # mvuRight + mvDepth of the batch, counters again
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-frame latency through the C ABI, batch = 1 frame (rank 0 reports)
@@ -423,7 +422,8 @@ def own_arm(args):
                        "distinct_frames": DISTINCT_FRAMES, "parallelism": "one camera stream per GPU, no collective",
                        "l2_policy": "per-step working set (inputs %.0f MB + pyramids %.0f MB per GPU) exceeds the 126 MB L2" % (
                            nimgs * h * pitch / 1e6, nimgs * slab / 1e6),
-                       "keypoints_per_image": n_out, "fast_candidates_per_level_frame0": cand_per_level},
+                       "keypoints_per_image": n_out, "fast_candidates_per_level_frame0": cand_per_level,
+                       "fast_retried_cells_per_level_frame0": retries_per_level},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nimgs * w * h, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "pyramid_d2h": need_pyr, "host_threads": T,

@@ -201,6 +201,11 @@ ORBX_API int orbx_synchronize(orbx_handle* h);
 ORBX_API int orbx_stage_timing_enable(orbx_handle* h, int enable);
 ORBX_API int orbx_stage_timing_read(orbx_handle* h, int cap, const char** names, float* ms, int* launches);
 
+/* Workload statistics of frame `frame` of the last extract whose results were fetched: FAST corners handed to the quadtree
+ * per level (vToDistributeKeys.size(), src/ORBextractor.cc:818-826) and cells re-run at minThFAST per level (:812).  Either
+ * output may be NULL; nlevels ints each. */
+ORBX_API int orbx_fast_stats(orbx_handle* h, int frame, int* candidates, int* retries);
+
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 ORBX_API long long orbx_launch_count(orbx_handle* h);
 

@@ -1,6 +1,7 @@
 #!/bin/sh
-# Builds oracle/_ref/libstereoref.so: the reference's OWN lines of Frame::ComputeStereoMatches and
-# ORBmatcher::DescriptorDistance, taken at build time from where they lie under $REF (never copied into this
+# Builds oracle/_ref/libstereoref.so: the reference's OWN lines of Frame::ComputeStereoMatches,
+# ORBmatcher::DescriptorDistance, the Frame undistort/grid functions, Frame::GetFeaturesInArea and
+# ORBmatcher::SearchByProjection(Frame&, const Frame&) / ComputeThreeMaxima, taken at build time from where they lie under $REF (never copied into this
 # repo: the generated translation unit lives in a temporary directory and only the .so is kept), compiled against
 # oracle/shim_stereo/stereo_shim.h.  TEST INFRASTRUCTURE only.
 set -e
@@ -17,18 +18,25 @@ sed -n '230p' "$F" | grep -q 'void Frame::AssignFeaturesToGrid()' || { echo "Fra
 sed -n '382p' "$F" | grep -q 'bool Frame::PosInGrid' || { echo "Frame.cc:382 is not PosInGrid"; exit 1; }
 sed -n '404p' "$F" | grep -q 'void Frame::UndistortKeyPoints()' || { echo "Frame.cc:404 is not UndistortKeyPoints"; exit 1; }
 sed -n '436p' "$F" | grep -q 'void Frame::ComputeImageBounds' || { echo "Frame.cc:436 is not ComputeImageBounds"; exit 1; }
+sed -n '327p' "$F" | grep -q 'Frame::GetFeaturesInArea' || { echo "Frame.cc:327 is not GetFeaturesInArea"; exit 1; }
+sed -n '1328p' "$M" | grep -q 'int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame' || { echo "ORBmatcher.cc:1328 is not SearchByProjection(Frame&, const Frame&)"; exit 1; }
+sed -n '1470p' "$M" | grep -q '^}' || { echo "ORBmatcher.cc:1470 is not the end of SearchByProjection"; exit 1; }
+sed -n '1601p' "$M" | grep -q 'void ORBmatcher::ComputeThreeMaxima' || { echo "ORBmatcher.cc:1601 is not ComputeThreeMaxima"; exit 1; }
 TMP=$(mktemp -d)
 trap 'rm -rf "$TMP"' EXIT
 {
   echo '#include "stereo_shim.h"'
   echo 'namespace ORB_SLAM2 {'
-  sed -n '37,39p' "$M"
+  sed -n '37,43p' "$M"
   sed -n '1647,1663p' "$M"
   sed -n '466,640p' "$F"
   sed -n '230,245p' "$F"
   sed -n '382,392p' "$F"
   sed -n '404,434p' "$F"
   sed -n '436,464p' "$F"
+  sed -n '327,380p' "$F"
+  sed -n '1328,1470p' "$M"
+  sed -n '1601,1642p' "$M"
   echo '}'
 } > "$TMP/stereo_ref_gen.cpp"
 mkdir -p "$OUT"

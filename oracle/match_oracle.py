@@ -1,0 +1,219 @@
+"""CPU restatement of ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)
+(reference src/ORBmatcher.cc:1328-1470) with Frame::GetFeaturesInArea (src/Frame.cc:327-380), DescriptorDistance
+(src/ORBmatcher.cc:1647-1663) and ComputeThreeMaxima (:1601-1642): the per-frame descriptor consumer of
+Tracking::TrackWithMotionModel (src/Tracking.cc:885, :891).
+
+TEST INFRASTRUCTURE: the checker of ``orbx_search_by_projection``; only tests/ may import it.  The three small matrix
+products are the REAL OpenCV (cv2.gemm, 4.13.0), everything else is float32 numpy scalars without FMA (rule B-2).
+Pinned against the reference's own lines compiled against a stub (oracle/_ref/libstereoref.so,
+``ref_search_by_projection`` below) by tests/test_match_oracle.py.
+
+State convention (the reference's only call sites fill CurrentFrame.mvpMapPoints with NULL first, src/Tracking.cc:871,
+:890): the current frame starts without map points.  The result names, per current keypoint, the index of the LastFrame
+keypoint whose map point it holds at return, or -1.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+f32 = np.float32
+GRID_COLS, GRID_ROWS = 64, 48          # include/Frame.h:39-40
+TH_HIGH, HISTO_LENGTH = 100, 30        # src/ORBmatcher.cc:37, :39
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _gemm(A, B, Cm=None, alpha=1.0, flags=0):
+    import cv2
+    return cv2.gemm(np.ascontiguousarray(A, f32), np.ascontiguousarray(B, f32), alpha, None if Cm is None else
+                    np.ascontiguousarray(Cm, f32), 0.0 if Cm is None else 1.0, flags=flags)
+
+
+def motion_flags(Tcw_cur, Tcw_last, mb, mono):
+    """bForward / bBackward (:1337-1349)."""
+    import cv2
+    Tc = np.asarray(Tcw_cur, f32).reshape(4, 4)
+    Tl = np.asarray(Tcw_last, f32).reshape(4, 4)
+    twc = _gemm(Tc[:3, :3], Tc[:3, 3:4], None, -1.0, cv2.GEMM_1_T)            # -Rcw.t() * tcw
+    tlc = _gemm(Tl[:3, :3], twc, Tl[:3, 3:4])                                  # Rlw * twc + tlw
+    z = f32(tlc[2, 0])
+    return bool(z > f32(mb) and not mono), bool(-z > f32(mb) and not mono)
+
+
+def _round_half_away(x) -> int:
+    x = float(x)
+    return int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
+
+
+def features_in_area(x, y, r, min_level, max_level, xy_un, octave, cell_start, cell_items, bounds):
+    """Frame::GetFeaturesInArea (src/Frame.cc:327-380), candidates in the reference's visiting order."""
+    mnx, mxx, mny, mxy = [f32(b) for b in bounds]
+    winv = f32(f32(GRID_COLS) / f32(mxx - mnx))
+    hinv = f32(f32(GRID_ROWS) / f32(mxy - mny))
+    x, y, r = f32(x), f32(y), f32(r)
+    out = []
+    c0 = max(0, int(math.floor(f32(f32(f32(x - mnx) - r) * winv))))
+    if c0 >= GRID_COLS:
+        return out
+    c1 = min(GRID_COLS - 1, int(math.ceil(f32(f32(f32(x - mnx) + r) * winv))))
+    if c1 < 0:
+        return out
+    r0 = max(0, int(math.floor(f32(f32(f32(y - mny) - r) * hinv))))
+    if r0 >= GRID_ROWS:
+        return out
+    r1 = min(GRID_ROWS - 1, int(math.ceil(f32(f32(f32(y - mny) + r) * hinv))))
+    if r1 < 0:
+        return out
+    check = (min_level > 0) or (max_level >= 0)
+    for ix in range(c0, c1 + 1):
+        for iy in range(r0, r1 + 1):
+            c = ix * GRID_ROWS + iy
+            for k in cell_items[cell_start[c]:cell_start[c + 1]]:
+                if check:
+                    if octave[k] < min_level:
+                        continue
+                    if max_level >= 0 and octave[k] > max_level:
+                        continue
+                if abs(f32(xy_un[k, 0] - x)) < r and abs(f32(xy_un[k, 1] - y)) < r:
+                    out.append(int(k))
+    return out
+
+
+def search_by_projection(world, mp_desc, mp_obs, outlier, last_octave, last_angle, Tcw_cur, Tcw_last, xy_un, cur_octave,
+                         cur_angle, desc, u_right, cell_start, cell_items, bounds, K4, mbf, mb, sf, th, mono,
+                         check_orientation=True):
+    """Returns (nmatches, cur_match int32[nC])."""
+    nL, nC = len(mp_obs), len(desc)
+    Tc = np.asarray(Tcw_cur, f32).reshape(4, 4)
+    fx, fy, cx, cy = [f32(v) for v in K4]
+    mnx, mxx, mny, mxy = [f32(b) for b in bounds]
+    fwd, bwd = motion_flags(Tcw_cur, Tcw_last, mb, mono)
+    factor = f32(f32(1.0) / f32(HISTO_LENGTH))
+    desc64 = np.ascontiguousarray(desc).view(np.uint64).reshape(nC, 4) if nC else np.zeros((0, 4), np.uint64)
+    q64 = np.ascontiguousarray(mp_desc).view(np.uint64).reshape(nL, 4) if nL else np.zeros((0, 4), np.uint64)
+    holder = np.full(nC, -1, np.int64)            # CurrentFrame.mvpMapPoints as LastFrame indices
+    rot_hist = [[] for _ in range(HISTO_LENGTH)]
+    nmatches = 0
+    W = np.asarray(world, f32).reshape(nL, 3)
+    for i in range(nL):
+        if mp_obs[i] < 0 or outlier[i]:
+            continue
+        X = _gemm(Tc[:3, :3], W[i].reshape(3, 1), Tc[:3, 3:4])                 # Rcw*x3Dw+tcw, one 3x1 product as in the reference
+        xc, yc, zc = f32(X[0, 0]), f32(X[1, 0]), f32(X[2, 0])
+        with np.errstate(divide="ignore"):
+            invzc = f32(np.float64(1.0) / np.float64(zc))
+        if invzc < 0:
+            continue
+        u = f32(f32(f32(fx * xc) * invzc) + cx)
+        v = f32(f32(f32(fy * yc) * invzc) + cy)
+        if u < mnx or u > mxx or v < mny or v > mxy:
+            continue
+        if not (np.isfinite(u) and np.isfinite(v)):
+            continue                               # NaN would index the grid with an undefined int cast; defined as "no candidates"
+        lo = int(last_octave[i])
+        radius = f32(f32(th) * f32(sf[lo]))
+        if fwd:
+            cands = features_in_area(u, v, radius, lo, -1, xy_un, cur_octave, cell_start, cell_items, bounds)
+        elif bwd:
+            cands = features_in_area(u, v, radius, 0, lo, xy_un, cur_octave, cell_start, cell_items, bounds)
+        else:
+            cands = features_in_area(u, v, radius, lo - 1, lo + 1, xy_un, cur_octave, cell_start, cell_items, bounds)
+        if not cands:
+            continue
+        best, best_idx = 256, -1
+        for i2 in cands:
+            if holder[i2] >= 0 and mp_obs[holder[i2]] > 0:
+                continue
+            if u_right is not None and u_right[i2] > 0:
+                ur = f32(u - f32(f32(mbf) * invzc))
+                if abs(f32(ur - f32(u_right[i2]))) > radius:
+                    continue
+            d = int(sum(bin(int(a ^ b)).count("1") for a, b in zip(q64[i], desc64[i2])))
+            if d < best:
+                best, best_idx = d, i2
+        if best <= TH_HIGH:
+            holder[best_idx] = i
+            nmatches += 1
+            if check_orientation:
+                rot = f32(f32(last_angle[i]) - f32(cur_angle[best_idx]))
+                if rot < 0.0:
+                    rot = f32(rot + f32(360.0))
+                b = _round_half_away(f32(rot * factor))
+                if b == HISTO_LENGTH:
+                    b = 0
+                rot_hist[b].append(best_idx)
+    if check_orientation:
+        ind = compute_three_maxima([len(h) for h in rot_hist])
+        for b in range(HISTO_LENGTH):
+            if b not in ind:
+                for i2 in rot_hist[b]:
+                    holder[i2] = -1
+                    nmatches -= 1
+    return nmatches, holder.astype(np.int32)
+
+
+def compute_three_maxima(sizes):
+    """ORBmatcher::ComputeThreeMaxima (:1601-1642) on the bin sizes; returns (ind1, ind2, ind3), -1 = none."""
+    max1 = max2 = max3 = 0
+    ind1 = ind2 = ind3 = -1
+    for i, s in enumerate(sizes):
+        if s > max1:
+            max3, max2, max1 = max2, max1, s
+            ind3, ind2, ind1 = ind2, ind1, i
+        elif s > max2:
+            max3, max2 = max2, s
+            ind3, ind2 = ind2, i
+        elif s > max3:
+            max3, ind3 = s, i
+    if f32(max2) < f32(f32(0.1) * f32(max1)):
+        ind2 = ind3 = -1
+    elif f32(max3) < f32(f32(0.1) * f32(max1)):
+        ind3 = -1
+    return ind1, ind2, ind3
+
+
+# ----------------------------------------------------------------------------- the reference's own lines
+_ref = None
+
+
+def ref_available() -> bool:
+    if not os.path.exists(os.path.join(_HERE, "_ref", "libstereoref.so")):
+        return False
+    try:
+        return hasattr(C.CDLL(os.path.join(_HERE, "_ref", "libstereoref.so")), "matchref_search_by_projection")
+    except OSError:
+        return False
+
+
+def ref_search_by_projection(world, mp_desc, mp_obs, outlier, last_octave, last_angle, Tcw_cur, Tcw_last, xy_un, cur_octave,
+                             cur_angle, desc, u_right, cell_start, cell_items, bounds, K4, mbf, mb, sf, th, mono,
+                             check_orientation=True):
+    """Same call shape, executed by the reference's own lines (oracle/_ref/libstereoref.so)."""
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(os.path.join(_HERE, "_ref", "libstereoref.so"))
+        _ref.matchref_search_by_projection.restype = C.c_int
+    nL, nC = len(mp_obs), len(desc)
+    kp = np.zeros((nC, 7), f32)
+    kp[:, 0:2] = np.asarray(xy_un, f32).reshape(nC, 2)
+    kp[:, 3] = np.asarray(cur_angle, f32)
+    kp[:, 5] = np.asarray(cur_octave, np.int32).view(f32)
+    arrs = dict(world=np.ascontiguousarray(world, f32), mp_desc=np.ascontiguousarray(mp_desc, np.uint8),
+                mp_obs=np.ascontiguousarray(mp_obs, np.int32), outlier=np.ascontiguousarray(outlier, np.uint8),
+                lo=np.ascontiguousarray(last_octave, np.int32), la=np.ascontiguousarray(last_angle, f32),
+                tc=np.ascontiguousarray(Tcw_cur, f32).reshape(16), tl=np.ascontiguousarray(Tcw_last, f32).reshape(16),
+                desc=np.ascontiguousarray(desc, np.uint8), cs=np.ascontiguousarray(cell_start, np.int32),
+                ci=np.ascontiguousarray(cell_items, np.int32), b=np.ascontiguousarray(bounds, f32),
+                k=np.ascontiguousarray(K4, f32), sf=np.ascontiguousarray(sf, f32))
+    ur = None if u_right is None else np.ascontiguousarray(u_right, f32)
+    out = np.full(nC, -1, np.int32)
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    n = _ref.matchref_search_by_projection(
+        C.c_int(nL), p(arrs["world"]), p(arrs["mp_desc"]), p(arrs["mp_obs"]), p(arrs["outlier"]), p(arrs["lo"]), p(arrs["la"]),
+        p(arrs["tc"]), p(arrs["tl"]), C.c_int(nC), p(kp), p(arrs["desc"]), C.c_void_p(0) if ur is None else p(ur),
+        p(arrs["cs"]), p(arrs["ci"]), p(arrs["b"]), p(arrs["k"]), C.c_float(mbf), C.c_float(mb), p(arrs["sf"]),
+        C.c_int(len(arrs["sf"])), C.c_float(th), C.c_int(int(mono)), C.c_int(int(check_orientation)), p(out))
+    return int(n), out

@@ -3,14 +3,18 @@
 // oracle/build_stereo_ref.sh compiles the reference's own lines of Frame::ComputeStereoMatches
 // (/root/reference/src/Frame.cc:466-640), ORBmatcher::DescriptorDistance / TH_HIGH / TH_LOW
 // (/root/reference/src/ORBmatcher.cc:37-38, :1647-1663) and Frame::AssignFeaturesToGrid / PosInGrid /
-// UndistortKeyPoints / ComputeImageBounds (Frame.cc:230-245, :382-392, :404-434, :436-464), taken from where they lie at
+// UndistortKeyPoints / ComputeImageBounds (Frame.cc:230-245, :382-392, :404-434, :436-464), Frame::GetFeaturesInArea
+// (:327-380) and ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) / ComputeThreeMaxima
+// (ORBmatcher.cc:1328-1470, :1601-1642), taken from where they lie at
 // build time, against this header: the handful of cv:: types those lines use (8U / 32F Mat views, convertTo, ones, scalar * Mat,
 // Mat - Mat, norm L1) and the members of Frame / ORBextractor / ORBmatcher they touch.  Written from scratch.
 #ifndef ORBX_ORACLE_STEREO_SHIM_H
 #define ORBX_ORACLE_STEREO_SHIM_H
 #include <algorithm>
+#include <cassert>
 #include <climits>
 #include <cmath>
+#include <cstddef>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -32,6 +36,10 @@ struct KeyPoint {
 };
 
 enum { NORM_L1 = 2 };
+
+class Mat;
+struct MatT;      // Mat::t() with a scale (MatExpr of OpenCV, only as far as ORBmatcher.cc:1340-1348 needs it)
+struct MatMul;    // A * B, evaluated when it meets "+ C" or a Mat
 
 class Mat {
 public:
@@ -59,6 +67,9 @@ public:
     Mat row(int r) const { return sub(r, r + 1, 0, cols); }
     Mat rowRange(int a, int b) const { return sub(a, b, 0, cols); }
     Mat colRange(int a, int b) const { return sub(0, rows, a, b); }
+    Mat col(int c) const { return sub(0, rows, c, c + 1); }
+    inline MatT t() const;
+    inline Mat(const MatMul& e);
     template <typename T> T* ptr(int r = 0) { return (T*)(data + (size_t)r * step); }
     template <typename T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * step); }
     template <typename T> T& at(int r, int c) { return ((T*)(data + (size_t)r * step))[c]; }
@@ -105,6 +116,39 @@ static inline double norm(const Mat& a, const Mat& b, int type) {    // NORM_L1 
     return s;
 }
 
+// cv::gemm for the 3x3 * 3x1 float products of ORBmatcher.cc:1337-1348, restated from OpenCV's published algorithm and
+// pinned bit for bit against the real cv2.gemm (tests/test_match_oracle.py):
+//   A * B (+ C), no flags (the len <= 4 special case): t0 = fl32(fl32(a0*b0 + a1*b1) + a2*b2) in float32, then
+//                 d = fl32(double(t0) * alpha + double(c) * beta);
+//   A.t() * B scaled (GEMM_1_T, general path): products and sum in double, d = fl32(alpha * s).
+struct MatT { Mat m; double alpha; };
+struct MatMul { Mat a, b; };
+inline MatT Mat::t() const { MatT r; r.m = *this; r.alpha = 1.0; return r; }
+static inline MatT operator-(const MatT& a) { MatT r = a; r.alpha = -a.alpha; return r; }
+static inline MatMul operator*(const Mat& a, const Mat& b) { MatMul r; r.a = a; r.b = b; return r; }
+static inline Mat gemm_small(const Mat& a, const Mat& b, const Mat* c) {
+    Mat o(a.rows, b.cols, CV_32F);
+    for (int r = 0; r < a.rows; ++r)
+        for (int q = 0; q < b.cols; ++q) {
+            float t0 = a.at<float>(r, 0) * b.at<float>(0, q);
+            for (int k = 1; k < a.cols; ++k) { const float p = a.at<float>(r, k) * b.at<float>(k, q); t0 = t0 + p; }
+            o.at<float>(r, q) = (float)((double)t0 * 1.0 + (c ? (double)c->at<float>(r, q) * 1.0 : 0.0));
+        }
+    return o;
+}
+inline Mat::Mat(const MatMul& e) { *this = gemm_small(e.a, e.b, 0); }
+static inline Mat operator+(const MatMul& e, const Mat& c) { return gemm_small(e.a, e.b, &c); }
+static inline Mat operator*(const MatT& a, const Mat& b) {       // (alpha * A^T) * B
+    Mat o(a.m.cols, b.cols, CV_32F);
+    for (int r = 0; r < a.m.cols; ++r)
+        for (int q = 0; q < b.cols; ++q) {
+            double s = 0;
+            for (int k = 0; k < a.m.rows; ++k) s += (double)a.m.at<float>(k, r) * (double)b.at<float>(k, q);
+            o.at<float>(r, q) = (float)(s * a.alpha);
+        }
+    return o;
+}
+
 // cv::undistortPoints(src, dst, K, D, R = empty, P = K) for N x 2 float points: the iterative inverse of OpenCV's
 // distortion model, 5 iterations, evaluated in double (restated from the published algorithm; pinned against the real
 // cv2.undistortPoints bit for bit by tests/test_frame_oracle.py).  K, D: CV_32F; D holds k1 k2 p1 p2 [k3].
@@ -142,12 +186,27 @@ static inline void undistortPoints(const Mat& src, Mat& dst, const Mat& K, const
 
 namespace ORB_SLAM2 {
 
+class Frame;
+
+struct MapPoint {                     // the three accessors ORBmatcher.cc:1328-1470 calls
+    cv::Mat mWorldPos, mDescriptor;
+    int nObs;
+    cv::Mat GetWorldPos() { return mWorldPos; }
+    cv::Mat GetDescriptor() { return mDescriptor; }
+    int Observations() { return nObs; }
+};
+
 class ORBmatcher {
 public:
     static const int TH_LOW;
     static const int TH_HIGH;
     static const int HISTO_LENGTH;
+    ORBmatcher(float nnratio = 0.6, bool checkOri = true);
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    void ComputeThreeMaxima(vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
+    float mfNNratio;
+    bool mbCheckOrientation;
 };
 
 struct ORBextractor {
@@ -161,6 +220,12 @@ public:
     bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
     void UndistortKeyPoints();
     void ComputeImageBounds(const cv::Mat& imLeft);
+    vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1,
+                                     const int maxLevel = -1) const;               // include/Frame.h:92
+    static float fx, fy, cx, cy;
+    cv::Mat mTcw;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
     std::vector<cv::KeyPoint> mvKeysUn;
     cv::Mat mK, mDistCoef;
     std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];

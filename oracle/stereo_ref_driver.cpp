@@ -79,3 +79,77 @@ extern "C" int frameref_undistort_grid(int n, const float* kp, const float* K, c
     bounds[0] = Frame::mnMinX; bounds[1] = Frame::mnMaxX; bounds[2] = Frame::mnMinY; bounds[3] = Frame::mnMaxY;
     return pos;
 }
+
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (src/ORBmatcher.cc:1328-1470,
+// called by Tracking::TrackWithMotionModel, src/Tracking.cc:885/:891, right after the current frame's map points are
+// filled with NULL), the reference's own lines, with Frame::GetFeaturesInArea (src/Frame.cc:327-380) and
+// ComputeThreeMaxima.  LastFrame side: world positions / representative descriptors / Observations() of its map points
+// (mp_obs < 0: no map point), outlier flags, octaves and angles of its keypoints, its pose.  CurrentFrame side:
+// undistorted keypoint records, descriptors, mvuRight, the grid as CSR, bounds, K4 = {fx, fy, cx, cy}, pose.
+// cur_match[i2] = index of the LastFrame keypoint whose map point CurrentFrame.mvpMapPoints[i2] ends up holding, else -1.
+namespace ORB_SLAM2 {
+float Frame::fx, Frame::fy, Frame::cx, Frame::cy;
+}
+extern "C" int matchref_search_by_projection(int nL, const float* world, const unsigned char* mp_desc, const int* mp_obs,
+                                             const unsigned char* outlier, const int* last_octave, const float* last_angle,
+                                             const float* Tcw_cur, const float* Tcw_last, int nC, const float* kp_un,
+                                             const unsigned char* desc, const float* u_right, const int* cell_start,
+                                             const int* cell_items, const float* bounds, const float* K4, float mbf, float mb,
+                                             const float* sf, int nlevels, float th, int mono, int check_ori, int* cur_match) {
+    using namespace ORB_SLAM2;
+    Frame C, L;
+    std::vector<MapPoint> mps(nL);
+    L.N = nL;
+    L.mvKeys.resize(nL);
+    L.mvKeysUn.resize(nL);
+    L.mvpMapPoints.assign(nL, (MapPoint*)0);
+    L.mvbOutlier.assign(nL, false);
+    for (int i = 0; i < nL; ++i) {
+        L.mvKeys[i].octave = last_octave[i];
+        L.mvKeysUn[i].octave = last_octave[i];
+        L.mvKeysUn[i].angle = last_angle[i];
+        L.mvbOutlier[i] = outlier[i] != 0;
+        if (mp_obs[i] >= 0) {
+            mps[i].mWorldPos = cv::Mat(3, 1, CV_32F);
+            for (int k = 0; k < 3; ++k) mps[i].mWorldPos.at<float>(k, 0) = world[3 * i + k];
+            mps[i].mDescriptor = cv::Mat(1, 32, CV_8U, (void*)(mp_desc + 32 * (size_t)i), 32);
+            mps[i].nObs = mp_obs[i];
+            L.mvpMapPoints[i] = &mps[i];
+        }
+    }
+    auto pose = [](const float* T) {
+        cv::Mat m(4, 4, CV_32F);
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) m.at<float>(r, c) = T[4 * r + c];
+        return m;
+    };
+    L.mTcw = pose(Tcw_last);
+    C.mTcw = pose(Tcw_cur);
+    C.N = nC;
+    C.mvKeysUn.resize(nC);
+    for (int i = 0; i < nC; ++i) {
+        const float* q = kp_un + 7 * i;
+        C.mvKeysUn[i].pt.x = q[0]; C.mvKeysUn[i].pt.y = q[1]; C.mvKeysUn[i].size = q[2]; C.mvKeysUn[i].angle = q[3];
+        C.mvKeysUn[i].response = q[4];
+        memcpy(&C.mvKeysUn[i].octave, q + 5, 4); memcpy(&C.mvKeysUn[i].class_id, q + 6, 4);
+    }
+    C.mvpMapPoints.assign(nC, (MapPoint*)0);
+    C.mvuRight.assign(nC, -1.f);
+    if (u_right) C.mvuRight.assign(u_right, u_right + nC);
+    C.mDescriptors = cv::Mat(nC, 32, CV_8U, (void*)desc, 32);
+    C.mvScaleFactors.assign(sf, sf + nlevels);
+    C.mbf = mbf;
+    C.mb = mb;
+    Frame::fx = K4[0]; Frame::fy = K4[1]; Frame::cx = K4[2]; Frame::cy = K4[3];
+    Frame::mnMinX = bounds[0]; Frame::mnMaxX = bounds[1]; Frame::mnMinY = bounds[2]; Frame::mnMaxY = bounds[3];
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(Frame::mnMaxX - Frame::mnMinX);
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(Frame::mnMaxY - Frame::mnMinY);
+    for (int gx = 0; gx < FRAME_GRID_COLS; ++gx)
+        for (int gy = 0; gy < FRAME_GRID_ROWS; ++gy) {
+            const int c = gx * FRAME_GRID_ROWS + gy;
+            C.mGrid[gx][gy].assign(cell_items + cell_start[c], cell_items + cell_start[c + 1]);
+        }
+    ORBmatcher matcher(0.9, check_ori != 0);                       // src/Tracking.cc:868
+    const int nmatches = matcher.SearchByProjection(C, L, th, mono != 0);
+    for (int i = 0; i < nC; ++i) cur_match[i] = C.mvpMapPoints[i] ? (int)(C.mvpMapPoints[i] - &mps[0]) : -1;
+    return nmatches;
+}

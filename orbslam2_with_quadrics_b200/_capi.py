@@ -23,7 +23,7 @@ SYMBOLS = [
     "orbx_stream", "orbx_synchronize", "orbx_stage_timing_enable", "orbx_stage_timing_read",
     "orbx_launch_count", "orbx_algorithmic_bytes", "orbx_strerror", "orbx_last_cuda_error", "orbx_version",
     "orbx_stereo_match", "orbx_stereo_match_device", "orbx_stereo_fetch",
-    "orbx_extract_batch_color", "orbx_extract_device_color", "orbx_undistort_grid",
+    "orbx_extract_batch_color", "orbx_extract_device_color", "orbx_undistort_grid", "orbx_fast_stats",
 ]
 GRAY8, BGR8, RGB8, BGRA8, RGBA8 = range(5)
 
@@ -107,6 +107,7 @@ def lib():
     L.orbx_stereo_fetch.argtypes = [vp, i, C.POINTER(i), C.POINTER(OrbxStereoResult)]
     L.orbx_extract_batch_color.argtypes = [vp, i, C.POINTER(vp), i, i, C.POINTER(sz), i, C.POINTER(OrbxResult)]
     L.orbx_extract_device_color.argtypes = [vp, i, vp, i, i, sz, sz, i]
+    L.orbx_fast_stats.argtypes = [vp, i, C.POINTER(i), C.POINTER(i)]
     L.orbx_undistort_grid.argtypes = [vp, i, C.POINTER(i), C.POINTER(C.c_float), C.POINTER(C.c_float), i, C.POINTER(OrbxGridResult)]
     _lib = L
     return L

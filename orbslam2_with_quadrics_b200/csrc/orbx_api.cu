@@ -58,7 +58,7 @@ struct orbx_handle {
     uint32_t *d_cand, *d_cand_sorted, *d_kept;
     uint16_t* d_key_node;
     uint2* d_cell_rec;
-    int* d_counters;             // [level_counts B*L][sorted_counts B*L][kept_counts B*L][status B][work counter]
+    int* d_counters;             // [level_counts B*L][sorted_counts B*L][kept_counts B*L][status B][work counters][retry_counts B*L]
     std::vector<unsigned char> fast_maps;   // per-level TMA descriptors of the pyramid slabs (box = strip of FAST windows)
     std::vector<unsigned char> desc_maps;   // the same planes with box = one keypoint's raw window
     float* d_angles;
@@ -102,12 +102,15 @@ struct orbx_handle {
     double stage_ms[ST_COUNT];
     int stage_launches[ST_COUNT];
 
-    int counters_count() const { return cfg.max_batch * (3 * plan.nlevels + 1) + 2 * kMaxChunks; }
+    int counters_count() const { return cfg.max_batch * (4 * plan.nlevels + 1) + 2 * kMaxChunks; }
     int* d_level_counts() const { return d_counters; }
     int* d_sorted_counts() const { return d_counters + cfg.max_batch * plan.nlevels; }
     int* d_kept_counts() const { return d_counters + 2 * cfg.max_batch * plan.nlevels; }
     int* d_status() const { return d_counters + 3 * cfg.max_batch * plan.nlevels; }
     int* d_work_counter() const { return d_counters + cfg.max_batch * (3 * plan.nlevels + 1); }
+    int* d_retry_counts() const { return d_counters + cfg.max_batch * (3 * plan.nlevels + 1) + 2 * kMaxChunks; }
+    const int* h_retry_counts() const { return h_counters + cfg.max_batch * (3 * plan.nlevels + 1) + 2 * kMaxChunks; }
+    const int* h_level_counts() const { return h_counters; }
     const int* h_sorted_counts() const { return h_counters + cfg.max_batch * plan.nlevels; }
     const int* h_kept_counts() const { return h_counters + 2 * cfg.max_batch * plan.nlevels; }
     const int* h_status() const { return h_counters + 3 * cfg.max_batch * plan.nlevels; }
@@ -478,6 +481,7 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
     int* sorted_counts = h->d_sorted_counts() + f0 * L;
     int* kept_counts = h->d_kept_counts() + f0 * L;
     int* status = h->d_status() + f0;
+    int* retry_counts = h->d_retry_counts() + f0 * L;
     // Two schedules.  With per-stage timing on, every kernel runs alone on `st`, so its duration is its own.
     // Otherwise the dependency graph is exploited with a side stream:
     //   st : pyramid L0..1 | pyramid L2..  (small, latency-bound levels)  | FAST L2.. | octree | describe
@@ -495,14 +499,14 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
             CK(h, cudaEventRecord(h->ev_low[si], st));
             CK(h, cudaStreamWaitEvent(ax, h->ev_low[si], 0));
             CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), f0, n, 0, ls, h->num_sms, cand, cell_rec, level_counts,
-                                    wc, status, ax));
+                                    wc, status, retry_counts, ax));
             CK(h, cudaEventRecord(h->ev_fast_low[si], ax));
         }
     }
     if (ev) CK(h, cudaEventRecord(ev[ST_FAST], st));
     if (ls) CK(h, cudaStreamWaitEvent(st, h->ev_fast_low[si], 0));
     CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), f0, n, ls, L, h->num_sms, cand, cell_rec, level_counts,
-                            wc + 1, status, st));
+                            wc + 1, status, retry_counts, st));
     if (ev) CK(h, cudaEventRecord(ev[ST_OCTREE], st));
     CK(h, orbx::launch_octree(h->d_plan, P, n, cand, cell_rec, cand_sorted, key_node, sorted_counts, kept, kept_counts,
                               status, st));
@@ -1118,6 +1122,16 @@ int orbx_undistort_grid(orbx_handle* h, int nframes, const int* frames, const fl
         results[i].cell_items = h->h_un_items + (size_t)f * kpf;
         results[i].n_in_grid = results[i].cell_start[NC - 1];
         for (int k = 0; k < 4; ++k) results[i].bounds[k] = bounds[k];
+    }
+    return ORBX_OK;
+}
+
+int orbx_fast_stats(orbx_handle* h, int frame, int* candidates, int* retries) {
+    if (!h || !h->have_plan || frame < 0 || frame >= h->last_n) return ORBX_ERR_BAD_ARGS;
+    const int L = h->plan.nlevels;
+    for (int l = 0; l < L; ++l) {
+        if (candidates) candidates[l] = h->h_level_counts()[frame * L + l];
+        if (retries) retries[l] = h->h_retry_counts()[frame * L + l];
     }
     return ORBX_OK;
 }

@@ -513,7 +513,7 @@ template <int BW_T>
 __global__ void __launch_bounds__(ORBX_FAST_WARPS * 32, ORBX_FAST_MINB)
 fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, int frame0, int nframes,
                   int l0, int l1, uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec, int* __restrict__ level_counts,
-                  int* __restrict__ work_counter, int* __restrict__ status) {
+                  int* __restrict__ work_counter, int* __restrict__ status, int* __restrict__ retry_counts) {
     ORBX_PDL_WAIT();
     extern __shared__ uint8_t fast_smem_raw[];
     __shared__ uint64_t s_bar[ORBX_FAST_WARPS][2];
@@ -609,6 +609,7 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
             const uint32_t vmask = (ry < RPI && nvalid > 0) ? (0x80808080u >> (8 * (4 - nvalid))) : 0u;
             for (int pass = 0; pass < 2 && count == 0; ++pass) {
                 const int t = pass == 0 ? plan->ini_th : plan->min_th;
+                if (pass == 1 && lane == 0) atomicAdd(&retry_counts[cc.frame * nlevels + cc.l], 1);      // (:812) statistics only
                 const uint32_t C = (uint32_t)(0x7f - min(t, 0x7f)) * 0x01010101u;
                 // ---- phase 1, in chunks of 8 warp iterations (RPI rows each): first all pre-tests (independent
                 //      loads and SIMD math, nothing serialises), then ONE pair of packed warp scans for the chunk
@@ -1882,14 +1883,14 @@ size_t fast_maps_bytes() { return sizeof(FastMaps); }
 
 cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, int frame0, int nframes, int l0,
                         int l1, int num_sms, uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counter, int* status,
-                        cudaStream_t st) {
+                        int* retry_counts, cudaStream_t st) {
     const size_t smem = fast_smem_bytes(hp);
     static size_t configured[64] = {0};
     static int per_sm_cache[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> config_lock(g_config_mutex);
-    typedef void (*fast_fn)(const FastMaps, const OrbxPlan*, int, int, int, int, uint32_t*, uint2*, int*, int*, int*);
+    typedef void (*fast_fn)(const FastMaps, const OrbxPlan*, int, int, int, int, uint32_t*, uint2*, int*, int*, int*, int*);
     fast_fn fn = hp.fast_bw == 64 ? fast_cells_kernel<64> : hp.fast_bw == 96 ? fast_cells_kernel<96> :
                  hp.fast_bw == 128 ? fast_cells_kernel<128> : fast_cells_kernel<0>;
     if (smem != configured[dev & 63]) {
@@ -1918,7 +1919,7 @@ cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* 
     FastMaps fm;
     memcpy(&fm, maps, sizeof fm);
     const cudaError_t le = launch_k(fn, dim3((unsigned)blocks), dim3(W * 32), smem, st, fm, d_plan, frame0, nframes, l0, l1, cand,
-                                    cell_rec, level_counts, work_counter, status);
+                                    cell_rec, level_counts, work_counter, status, retry_counts);
     if (le != cudaSuccess) return le;
     return cudaSuccess;
 }

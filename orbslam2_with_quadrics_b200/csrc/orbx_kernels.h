@@ -27,7 +27,7 @@ size_t fast_smem_bytes(const OrbxPlan& hp);
 int build_fast_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* out_maps);
 size_t fast_maps_bytes();
 cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, int frame0, int nframes, int l0, int l1, int num_sms,
-                        uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counter, int* status,
+                        uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counter, int* status, int* retry_counts,
                         cudaStream_t st);
 size_t octree_smem_bytes(const OrbxPlan& hp);
 cudaError_t launch_octree(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, const uint32_t* cand,

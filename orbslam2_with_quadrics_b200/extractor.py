@@ -184,6 +184,13 @@ class ORBextractor:
         self._refresh_pyramids(n)
         return out
 
+    def fast_stats(self, frame: int = 0):
+        """(FAST corners handed to the quadtree per level, cells re-run at minThFAST per level) of a fetched frame."""
+        c = (C.c_int * self.nlevels)()
+        r = (C.c_int * self.nlevels)()
+        check(self._L.orbx_fast_stats(self._h, frame, c, r), self._h)
+        return list(c), list(r)
+
     def synchronize(self):
         check(self._L.orbx_synchronize(self._h), self._h)
 

@@ -1,0 +1,80 @@
+"""Seeded LastFrame / CurrentFrame scenarios for ORBmatcher::SearchByProjection(Frame&, const Frame&) parity tests.
+
+A scenario takes the current frame's keypoints (positions, octaves, angles, descriptors, grid) as given and builds a
+LastFrame whose map points re-project onto them: world point = back-projection of a current keypoint at a random depth
+through the current pose, plus pixel-level noise; the map point's descriptor = the keypoint's with random bit flips.
+Contention (several map points landing on one keypoint, with and without observations), outliers, missing map points,
+points behind the camera / outside the image and unrelated descriptors are mixed in."""
+import numpy as np
+
+f32 = np.float32
+
+
+def rot(rx, ry, rz):
+    cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def pose(rng, scale_r=0.05, t=(0.0, 0.0, 0.0)):
+    T = np.eye(4)
+    T[:3, :3] = rot(*(rng.normal(0, scale_r, 3)))
+    T[:3, 3] = np.asarray(t) + rng.normal(0, 0.05, 3)
+    return T.astype(f32)
+
+
+def make_last_frame(rng, xy_un, cur_octave, cur_angle, desc, K4, Tcw_cur, n_last, nlevels, dup_frac=0.3, flip_bits=25,
+                    angle_noise=8.0, angle_outlier_frac=0.15):
+    nC = len(desc)
+    fx, fy, cx, cy = [float(v) for v in K4]
+    Tc = np.asarray(Tcw_cur, np.float64).reshape(4, 4)
+    Rwc, twc = Tc[:3, :3].T, -Tc[:3, :3].T @ Tc[:3, 3]
+    # which current keypoint every last-frame point is aimed at: a mix of distinct targets and deliberate duplicates
+    tgt = rng.integers(0, nC, n_last)
+    ndup = int(dup_frac * n_last)
+    tgt[rng.integers(0, n_last, ndup)] = tgt[rng.integers(0, n_last, ndup)]
+    z = rng.uniform(0.8, 12.0, n_last)
+    px = xy_un[tgt, 0].astype(np.float64) + rng.normal(0, 2.0, n_last)
+    py = xy_un[tgt, 1].astype(np.float64) + rng.normal(0, 2.0, n_last)
+    Xc = np.stack([(px - cx) / fx * z, (py - cy) / fy * z, z], 1)
+    behind = rng.random(n_last) < 0.03
+    Xc[behind] *= -1.0
+    far = rng.random(n_last) < 0.03
+    Xc[far, 0] += 50.0 * z[far]
+    world = (Xc @ Rwc.T + twc).astype(f32)
+    mp_desc = desc[tgt].copy()
+    flips = rng.integers(0, 256, (n_last, flip_bits))
+    for k in range(flip_bits):
+        on = rng.random(n_last) < 0.6
+        mp_desc[np.arange(n_last)[on], flips[on, k] // 8] ^= (1 << (flips[on, k] % 8)).astype(np.uint8)
+    unrelated = rng.random(n_last) < 0.1
+    mp_desc[unrelated] = rng.integers(0, 256, (int(unrelated.sum()), 32), dtype=np.uint8)
+    mp_obs = rng.choice([-1, 0, 0, 1, 2, 5], n_last).astype(np.int32)
+    outlier = (rng.random(n_last) < 0.05).astype(np.uint8)
+    last_octave = np.clip(cur_octave[tgt] + rng.choice([-2, -1, 0, 0, 0, 1, 2], n_last), 0, nlevels - 1).astype(np.int32)
+    last_angle = (cur_angle[tgt] + rng.normal(0, angle_noise, n_last)).astype(f32)
+    wild = rng.random(n_last) < angle_outlier_frac
+    last_angle[wild] = rng.uniform(0, 360, int(wild.sum())).astype(f32)
+    last_angle = np.mod(last_angle, f32(360.0)).astype(f32)
+    return dict(world=world, mp_desc=mp_desc, mp_obs=mp_obs, outlier=outlier, last_octave=last_octave, last_angle=last_angle)
+
+
+def grid_from_points(xy_un, bounds):
+    """Frame::AssignFeaturesToGrid / PosInGrid (src/Frame.cc:230-245, :382-392) for a synthetic keypoint set (tests that
+    do not go through orbx_undistort_grid)."""
+    mnx, mxx, mny, mxy = [f32(b) for b in bounds]
+    winv = f32(f32(64) / f32(mxx - mnx))
+    hinv = f32(f32(48) / f32(mxy - mny))
+    cells = [[] for _ in range(64 * 48)]
+    for i in range(len(xy_un)):
+        gx = int(np.round(f32(f32(xy_un[i, 0] - mnx) * winv)))      # roundf on non-ties; ties do not occur for these inputs
+        gy = int(np.round(f32(f32(xy_un[i, 1] - mny) * hinv)))
+        if gx < 0 or gx >= 64 or gy < 0 or gy >= 48:
+            continue
+        cells[gx * 48 + gy].append(i)
+    start = np.zeros(64 * 48 + 1, np.int32)
+    start[1:] = np.cumsum([len(c) for c in cells])
+    items = np.array([i for c in cells for i in c], np.int32)
+    return start, items
