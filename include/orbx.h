@@ -157,6 +157,44 @@ typedef struct orbx_grid_result {
 ORBX_API int orbx_undistort_grid(orbx_handle* h, int nframes, const int* frames, const float* K4, const float* dist, int ndist,
                                  orbx_grid_result* results);
 
+/* ---- ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (reference
+ * src/ORBmatcher.cc:1328-1470, with Frame::GetFeaturesInArea src/Frame.cc:327-380, DescriptorDistance
+ * src/ORBmatcher.cc:1647-1663 and ComputeThreeMaxima :1601-1642): the descriptor consumer of every tracked frame
+ * (Tracking::TrackWithMotionModel, src/Tracking.cc:885, :891).  The CurrentFrame side is what this handle holds in HBM:
+ * frame `cur_frame` of the last extract, its mvKeysUn / mGrid from orbx_undistort_grid (which must have run for that
+ * frame; its K4 must be the K4 passed here) and, with use_stereo = 1, its mvuRight from orbx_stereo_match on this
+ * handle (use_stereo = 0: every mvuRight is -1, the monocular Frame).  The LastFrame side comes from the caller's map.
+ * As at both call sites of the reference, CurrentFrame.mvpMapPoints starts all NULL.
+ * Result: match[i2] = index i of the LastFrame keypoint whose map point CurrentFrame.mvpMapPoints[i2] holds at
+ * return, -1 for NULL; nmatches = the function's return value (it counts overwritten matches, as the reference does).
+ * Pinned host memory owned by the handle, valid until its next search call. */
+typedef struct orbx_projection_query {
+    int cur_frame;            /* frame of this handle's last extract */
+    int n_last;               /* LastFrame.N */
+    const float* world_pos;   /* n_last x 3: pMP->GetWorldPos() (ignored where there is no map point) */
+    const uint8_t* mp_desc;   /* n_last x 32: pMP->GetDescriptor() */
+    const int32_t* mp_obs;    /* n_last: pMP->Observations(); < 0 where LastFrame.mvpMapPoints[i] is NULL */
+    const uint8_t* outlier;   /* n_last: LastFrame.mvbOutlier[i]; NULL = none */
+    const int32_t* octave;    /* n_last: LastFrame.mvKeys[i].octave */
+    const float* angle;       /* n_last: LastFrame.mvKeysUn[i].angle */
+    float Tcw_cur[16];        /* CurrentFrame.mTcw, row-major 4 x 4 */
+    float Tcw_last[16];       /* LastFrame.mTcw */
+} orbx_projection_query;
+typedef struct orbx_projection_result {
+    int n;                    /* CurrentFrame.N */
+    int nmatches;
+    int rounds;               /* fixed-point rounds the device needed (diagnostic) */
+    const int32_t* match;     /* n */
+} orbx_projection_result;
+ORBX_API int orbx_search_by_projection(orbx_handle* h, int nqueries, const orbx_projection_query* queries, const float* K4, float mbf,
+                                       float mb, float th, int mono, int check_orientation, int use_stereo,
+                                       orbx_projection_result* results);
+/* The same split in two for device-side timing: stage + enqueue only / copy back and wait. */
+ORBX_API int orbx_search_by_projection_device(orbx_handle* h, int nqueries, const orbx_projection_query* queries, const float* K4,
+                                              float mbf, float mb, float th, int mono, int check_orientation, int use_stereo);
+ORBX_API int orbx_search_by_projection_fetch(orbx_handle* h, int nqueries, const orbx_projection_query* queries,
+                                             orbx_projection_result* results);
+
 /* Pinned host buffers callers may fill with frames so that H2D copies are asynchronous DMA. */
 ORBX_API int orbx_alloc_host(size_t bytes, void** out);
 ORBX_API int orbx_free_host(void* p);

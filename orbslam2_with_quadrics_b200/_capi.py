@@ -24,6 +24,7 @@ SYMBOLS = [
     "orbx_launch_count", "orbx_algorithmic_bytes", "orbx_strerror", "orbx_last_cuda_error", "orbx_version",
     "orbx_stereo_match", "orbx_stereo_match_device", "orbx_stereo_fetch",
     "orbx_extract_batch_color", "orbx_extract_device_color", "orbx_undistort_grid", "orbx_fast_stats",
+    "orbx_search_by_projection", "orbx_search_by_projection_device", "orbx_search_by_projection_fetch",
 ]
 GRAY8, BGR8, RGB8, BGRA8, RGBA8 = range(5)
 
@@ -49,6 +50,16 @@ class OrbxStereoResult(C.Structure):
 class OrbxGridResult(C.Structure):
     _fields_ = [("n", C.c_int), ("n_in_grid", C.c_int), ("xy_un", C.c_void_p), ("cell_start", C.c_void_p),
                 ("cell_items", C.c_void_p), ("bounds", C.c_float * 4)]
+
+
+class OrbxProjectionQuery(C.Structure):
+    _fields_ = [("cur_frame", C.c_int), ("n_last", C.c_int), ("world_pos", C.c_void_p), ("mp_desc", C.c_void_p),
+                ("mp_obs", C.c_void_p), ("outlier", C.c_void_p), ("octave", C.c_void_p), ("angle", C.c_void_p),
+                ("Tcw_cur", C.c_float * 16), ("Tcw_last", C.c_float * 16)]
+
+
+class OrbxProjectionResult(C.Structure):
+    _fields_ = [("n", C.c_int), ("nmatches", C.c_int), ("rounds", C.c_int), ("match", C.c_void_p)]
 
 
 class OrbxError(RuntimeError):
@@ -108,6 +119,11 @@ def lib():
     L.orbx_extract_batch_color.argtypes = [vp, i, C.POINTER(vp), i, i, C.POINTER(sz), i, C.POINTER(OrbxResult)]
     L.orbx_extract_device_color.argtypes = [vp, i, vp, i, i, sz, sz, i]
     L.orbx_fast_stats.argtypes = [vp, i, C.POINTER(i), C.POINTER(i)]
+    f = C.c_float
+    L.orbx_search_by_projection.argtypes = [vp, i, C.POINTER(OrbxProjectionQuery), C.POINTER(f), f, f, f, i, i, i,
+                                            C.POINTER(OrbxProjectionResult)]
+    L.orbx_search_by_projection_device.argtypes = [vp, i, C.POINTER(OrbxProjectionQuery), C.POINTER(f), f, f, f, i, i, i]
+    L.orbx_search_by_projection_fetch.argtypes = [vp, i, C.POINTER(OrbxProjectionQuery), C.POINTER(OrbxProjectionResult)]
     L.orbx_undistort_grid.argtypes = [vp, i, C.POINTER(i), C.POINTER(C.c_float), C.POINTER(C.c_float), i, C.POINTER(OrbxGridResult)]
     _lib = L
     return L

@@ -90,6 +90,12 @@ struct orbx_handle {
     // undistort + grid (orbx_undistort_grid; allocated on first use)
     float *d_un_xy, *h_un_xy;
     int *d_un_start, *d_un_items, *d_un_frames, *h_un_start, *h_un_items, *h_un_frames;
+    float un_bounds[4];       // mnMinX, mnMaxX, mnMinY, mnMaxY of the last orbx_undistort_grid
+    // SearchByProjection (orbx_search_by_projection; staging grows on demand)
+    unsigned char *d_sp, *h_sp;
+    size_t sp_bytes;
+    int *d_sp_out, *h_sp_out;  // [match nq * kpf][stats nq * 2]
+    size_t sp_out_ints;
     cudaEvent_t ev_stereo;
     int last_n;
     bool pyramid_valid;
@@ -385,6 +391,8 @@ void free_geometry(orbx_handle* h) {
     cudaFree(h->d_color); cudaFreeHost(h->h_color); h->d_color = h->h_color = 0; h->color_bytes = 0;
     cudaFree(h->d_un_xy); cudaFree(h->d_un_start); cudaFree(h->d_un_items); cudaFree(h->d_un_frames);
     cudaFreeHost(h->h_un_xy); cudaFreeHost(h->h_un_start); cudaFreeHost(h->h_un_items); cudaFreeHost(h->h_un_frames);
+    cudaFree(h->d_sp); cudaFreeHost(h->h_sp); cudaFree(h->d_sp_out); cudaFreeHost(h->h_sp_out);
+    h->d_sp = h->h_sp = 0; h->sp_bytes = 0; h->d_sp_out = h->h_sp_out = 0; h->sp_out_ints = 0;
     h->d_un_xy = h->h_un_xy = 0; h->d_un_start = h->d_un_items = h->d_un_frames = h->h_un_start = h->h_un_items = h->h_un_frames = 0;
     cudaFree(h->d_st_u); cudaFree(h->d_st_depth); cudaFree(h->d_st_sad); cudaFree(h->d_st_pairs); cudaFree(h->d_st_rows); cudaFree(h->d_st_bucket); h->d_st_rows = 0; h->d_st_bucket = 0;
     cudaFreeHost(h->h_st); cudaFreeHost(h->h_st_pairs);
@@ -693,6 +701,7 @@ int orbx_create(const orbx_config* cfg, orbx_handle** out) {
     h->use_graphs = getenv("ORBX_NO_GRAPHS") == nullptr;
     h->d_un_xy = h->h_un_xy = 0; h->d_un_start = h->d_un_items = h->d_un_frames = h->h_un_start = h->h_un_items = h->h_un_frames = 0;
     h->d_color = h->h_color = 0; h->color_bytes = 0;
+    h->d_sp = h->h_sp = 0; h->sp_bytes = 0; h->d_sp_out = h->h_sp_out = 0; h->sp_out_ints = 0;
     h->timing = false; h->ev_created = false; h->ev_head = 0; h->ev_pending = 0;
     memset(h->stage_ms, 0, sizeof h->stage_ms);
     memset(h->stage_launches, 0, sizeof h->stage_launches);
@@ -1099,6 +1108,7 @@ int orbx_undistort_grid(orbx_handle* h, int nframes, const int* frames, const fl
         bounds[0] = 0.f; bounds[1] = (float)P.width; bounds[2] = 0.f; bounds[3] = (float)P.height;
     }
     const float grid[4] = {bounds[0], bounds[2], 64.f / (bounds[1] - bounds[0]), 48.f / (bounds[3] - bounds[2])};
+    for (int k = 0; k < 4; ++k) h->un_bounds[k] = bounds[k];
     cudaStream_t st = h->stream;
     CK(h, cudaStreamSynchronize(st));                                        // the pinned staging of a previous call is free
     for (int i = 0; i < nframes; ++i) h->h_un_frames[i] = frames ? frames[i] : i;
@@ -1124,6 +1134,123 @@ int orbx_undistort_grid(orbx_handle* h, int nframes, const int* frames, const fl
         for (int k = 0; k < 4; ++k) results[i].bounds[k] = bounds[k];
     }
     return ORBX_OK;
+}
+
+// ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono), src/ORBmatcher.cc:1328-1470.
+static int sp_enqueue(orbx_handle* h, int nq, const orbx_projection_query* q, const float* K4, float mbf, float mb, float th,
+                      int mono, int check_orientation, int use_stereo, int* cap_out) {
+    if (!h || !q || !K4 || nq < 1 || nq > h->cfg.max_batch || !h->have_plan) return ORBX_ERR_BAD_ARGS;
+    if (!h->d_un_xy) return ORBX_ERR_BAD_ARGS;                      // orbx_undistort_grid has to run first (mvKeysUn, mGrid)
+    if (use_stereo && !h->d_st_u) return ORBX_ERR_BAD_ARGS;          // mvuRight comes from orbx_stereo_match on this handle
+    const OrbxPlan& P = h->plan;
+    if (P.kept_per_frame > 65535) return ORBX_ERR_BAD_ARGS;
+    int cap = 1;
+    for (int i = 0; i < nq; ++i) {
+        if (q[i].cur_frame < 0 || q[i].cur_frame >= h->last_n || q[i].n_last < 0) return ORBX_ERR_BAD_ARGS;
+        if (q[i].n_last && (!q[i].world_pos || !q[i].mp_desc || !q[i].mp_obs || !q[i].octave || !q[i].angle)) return ORBX_ERR_BAD_ARGS;
+        if (q[i].n_last > cap) cap = q[i].n_last;
+    }
+    cap = (cap + 3) & ~3;
+    if ((size_t)(cap + P.kept_per_frame) * sizeof(int) > 200 * 1024) return ORBX_ERR_BAD_ARGS;
+    CK(h, cudaSetDevice(h->cfg.device));
+    const size_t qbytes = (orbx::search_projection_query_bytes() + 15) & ~(size_t)15;
+    // staging layout: [queries][mp_desc nq*cap*32][world nq*cap*3 f32][obs nq*cap][octave nq*cap][angle nq*cap]
+    const size_t o_desc = (size_t)nq * qbytes, o_world = o_desc + (size_t)nq * cap * 32, o_obs = o_world + (size_t)nq * cap * 12,
+                 o_oct = o_obs + (size_t)nq * cap * 4, o_ang = o_oct + (size_t)nq * cap * 4, total = o_ang + (size_t)nq * cap * 4;
+    cudaStream_t st = h->stream;
+    CK(h, cudaStreamSynchronize(st));                                // the staging of a previous call is free
+    if (total > h->sp_bytes) {
+        cudaFree(h->d_sp); cudaFreeHost(h->h_sp); h->d_sp = h->h_sp = 0; h->sp_bytes = 0;
+        CK(h, cudaMalloc(&h->d_sp, total));
+        CK(h, cudaMallocHost(&h->h_sp, total));
+        h->sp_bytes = total;
+    }
+    const size_t out_ints = (size_t)h->cfg.max_batch * ((size_t)P.kept_per_frame + 2);
+    if (!h->d_sp_out) {
+        CK(h, cudaMalloc(&h->d_sp_out, out_ints * 4));
+        CK(h, cudaMallocHost(&h->h_sp_out, out_ints * 4));
+        h->sp_out_ints = out_ints;
+    }
+    for (int i = 0; i < nq; ++i) {
+        const orbx_projection_query& Q = q[i];
+        // twc = -Rcw.t() * tcw (general gemm path: double products and sum), tlc = Rlw * twc + tlw (the 3x3 path: float
+        // products and sums, "+ C" in double), bForward / bBackward (:1337-1349)
+        const float* Tc = Q.Tcw_cur;
+        const float* Tl = Q.Tcw_last;
+        float twc[3];
+        for (int r = 0; r < 3; ++r) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += (double)Tc[4 * k + r] * (double)Tc[4 * k + 3];
+            twc[r] = (float)(s * -1.0);
+        }
+        volatile float p0 = Tl[8] * twc[0], p1 = Tl[9] * twc[1], p2 = Tl[10] * twc[2];     // volatile: no contraction
+        volatile float t0 = p0 + p1;
+        t0 = t0 + p2;
+        const float tlcz = (float)((double)t0 + (double)Tl[11]);
+        const int fwd = tlcz > mb && !mono, bwd = -tlcz > mb && !mono;
+        const float R[9] = {Tc[0], Tc[1], Tc[2], Tc[4], Tc[5], Tc[6], Tc[8], Tc[9], Tc[10]}, t[3] = {Tc[3], Tc[7], Tc[11]};
+        orbx::search_projection_fill_query(h->h_sp + (size_t)i * qbytes, R, t, Q.n_last, Q.cur_frame, fwd, bwd);
+        const size_t n = (size_t)Q.n_last, b = (size_t)i * cap;
+        if (n) {
+            memcpy(h->h_sp + o_desc + b * 32, Q.mp_desc, n * 32);
+            memcpy(h->h_sp + o_world + b * 12, Q.world_pos, n * 12);
+            int* obs = reinterpret_cast<int*>(h->h_sp + o_obs) + b;
+            for (size_t k = 0; k < n; ++k) obs[k] = (Q.outlier && Q.outlier[k]) ? -1 : Q.mp_obs[k];     // (:1356-1360)
+            memcpy(h->h_sp + o_oct + b * 4, Q.octave, n * 4);
+            memcpy(h->h_sp + o_ang + b * 4, Q.angle, n * 4);
+        }
+    }
+    for (int i = 0; i < nq; ++i)
+        for (int k = 0; k < q[i].n_last; ++k) {
+            const int o = q[i].octave[k];
+            if (o < 0 || o >= P.nlevels) return ORBX_ERR_BAD_ARGS;
+        }
+    CK(h, cudaMemcpyAsync(h->d_sp, h->h_sp, total, cudaMemcpyHostToDevice, st));
+    CK(h, orbx::launch_search_projection(h->d_plan, P, nq, h->d_sp, K4, h->un_bounds, mbf, th, check_orientation, cap,
+                                         reinterpret_cast<const float*>(h->d_sp + o_world), h->d_sp + o_desc,
+                                         reinterpret_cast<const int*>(h->d_sp + o_obs), reinterpret_cast<const int*>(h->d_sp + o_oct),
+                                         reinterpret_cast<const float*>(h->d_sp + o_ang), h->d_out_kp, h->d_out_desc, h->d_kept_counts(),
+                                         h->d_un_xy, h->d_un_start, h->d_un_items, use_stereo ? h->d_st_u : nullptr, h->d_sp_out,
+                                         h->d_sp_out + (size_t)h->cfg.max_batch * P.kept_per_frame, st));
+    h->launches += 1;
+    if (cap_out) *cap_out = cap;
+    return ORBX_OK;
+}
+
+int orbx_search_by_projection_device(orbx_handle* h, int nqueries, const orbx_projection_query* queries, const float* K4, float mbf,
+                                     float mb, float th, int mono, int check_orientation, int use_stereo) {
+    return sp_enqueue(h, nqueries, queries, K4, mbf, mb, th, mono, check_orientation, use_stereo, nullptr);
+}
+
+int orbx_search_by_projection_fetch(orbx_handle* h, int nqueries, const orbx_projection_query* queries, orbx_projection_result* results) {
+    if (!h || !queries || !results || nqueries < 1 || nqueries > h->cfg.max_batch || !h->d_sp_out) return ORBX_ERR_BAD_ARGS;
+    CK(h, cudaSetDevice(h->cfg.device));
+    const OrbxPlan& P = h->plan;
+    const size_t kpf = (size_t)P.kept_per_frame, B = (size_t)h->cfg.max_batch;
+    cudaStream_t st = h->stream;
+    CK(h, cudaMemcpyAsync(h->h_sp_out, h->d_sp_out, (size_t)nqueries * kpf * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h->h_sp_out + B * kpf, h->d_sp_out + B * kpf, (size_t)nqueries * 2 * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int) * h->counters_count(), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    for (int i = 0; i < nqueries; ++i) {
+        const int f = queries[i].cur_frame;
+        if (f < 0 || f >= h->last_n) return ORBX_ERR_BAD_ARGS;
+        int total = 0;
+        for (int l = 0; l < P.nlevels; ++l) total += h->h_kept_counts()[f * P.nlevels + l];
+        results[i].n = total;
+        results[i].nmatches = h->h_sp_out[B * kpf + 2 * i];
+        results[i].rounds = h->h_sp_out[B * kpf + 2 * i + 1];
+        results[i].match = h->h_sp_out + (size_t)i * kpf;
+    }
+    return ORBX_OK;
+}
+
+int orbx_search_by_projection(orbx_handle* h, int nqueries, const orbx_projection_query* queries, const float* K4, float mbf, float mb,
+                              float th, int mono, int check_orientation, int use_stereo, orbx_projection_result* results) {
+    if (!results) return ORBX_ERR_BAD_ARGS;
+    const int rc = sp_enqueue(h, nqueries, queries, K4, mbf, mb, th, mono, check_orientation, use_stereo, nullptr);
+    if (rc != ORBX_OK) return rc;
+    return orbx_search_by_projection_fetch(h, nqueries, queries, results);
 }
 
 int orbx_fast_stats(orbx_handle* h, int frame, int* candidates, int* retries) {

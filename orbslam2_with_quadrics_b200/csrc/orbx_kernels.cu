@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1783,6 +1784,210 @@ undistort_grid_kernel(const OrbxPlan* __restrict__ plan, const float* __restrict
 }
 
 // =====================================================================================
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (src/ORBmatcher.cc:1328-1470)
+// with Frame::GetFeaturesInArea (src/Frame.cc:327-380), DescriptorDistance (src/ORBmatcher.cc:1647-1663) and
+// ComputeThreeMaxima (:1601-1642): the per-frame descriptor consumer of Tracking::TrackWithMotionModel.  One CTA per
+// (LastFrame, CurrentFrame) query, a warp per LastFrame map point.  The current frame's undistorted keypoints,
+// descriptors, mGrid (CSR) and mvuRight are what the extraction, orbx_undistort_grid and orbx_stereo_match left in HBM.
+//
+// The reference loop is sequential: a current keypoint claimed by a map point with Observations() > 0 is skipped by
+// every LATER map point (:1401-1403), one claimed by a point without observations is overwritten by a later one.  The
+// choice of point i therefore depends only on the choices of points j < i, so the sequential result is the unique
+// fixed point of   match[i] = best candidate not claimed by {j < i : obs[j] > 0 and match[j] = that candidate},
+// reached by Jacobi iteration (every point re-evaluated against the previous round's claims; round k fixes at least
+// the first k points, in practice 3-6 rounds).  Candidates are visited in CSR position order, which IS the reference's
+// visiting order (cells ix-major, iy, push_back order), so "first strictly smaller distance wins" (:1418) is the
+// minimum of (distance << 16 | position).  Afterwards: rotation histogram, three maxima, culling (:1425-1466); the
+// holder of a keypoint is the last point that matched it, a keypoint with ANY matcher in a culled bin ends up NULL and
+// nmatches counts overwritten matches exactly as the reference does.
+// =====================================================================================
+struct SpParams {
+    float fx, fy, cx, cy;                 // Frame::fx ... (static members)
+    float min_x, max_x, min_y, max_y;     // mnMinX, mnMaxX, mnMinY, mnMaxY
+    float winv, hinv;                     // mfGridElementWidthInv / HeightInv
+    float mbf, th;
+    int check_ori, cap, use_stereo;
+};
+struct SpQuery {
+    float R[9], t[3];                     // Rcw, tcw of the CURRENT frame
+    int n_last, frame, fwd, bwd;
+};
+#define SP_TH_HIGH 100                    // ORBmatcher::TH_HIGH (src/ORBmatcher.cc:37)
+#define SP_HISTO 30                       // ORBmatcher::HISTO_LENGTH (:39)
+
+__device__ __forceinline__ int sp_rot_bin(float last_angle, float cur_angle) {
+    float rot = __fsub_rn(last_angle, cur_angle);                           // (:1432-1437)
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, __fdiv_rn(1.0f, (float)SP_HISTO)));
+    if (bin == SP_HISTO) bin = 0;
+    return min(max(bin, 0), SP_HISTO - 1);                                  // the reference asserts the range
+}
+
+__global__ void __launch_bounds__(1024)
+search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __restrict__ queries, SpParams P,
+                         const float* __restrict__ world, const uint4* __restrict__ mp_desc, const int* __restrict__ mp_obs,
+                         const int* __restrict__ last_octave, const float* __restrict__ last_angle,
+                         const float* __restrict__ kp, const uint8_t* __restrict__ desc, const int* __restrict__ kept_counts,
+                         const float* __restrict__ xy_un, const int* __restrict__ cell_start, const int* __restrict__ cell_items,
+                         const float* __restrict__ u_right, int* __restrict__ match_out, int* __restrict__ stats_out) {
+    extern __shared__ int sp_smem[];
+    __shared__ int s_hist[SP_HISTO];
+    __shared__ int s_changed, s_nm, s_ncull;
+    __shared__ unsigned s_keep;
+    const SpQuery q = queries[blockIdx.x];
+    const int kpf = plan->kept_per_frame, nl = plan->nlevels;
+    const int f = q.frame, nL = q.n_last;
+    int N = 0;
+    for (int l = 0; l < nl; ++l) N += kept_counts[f * nl + l];
+    int* s_match = sp_smem;                   // [cap]  current keypoint chosen by LastFrame point i, -1: none
+    int* s_claim = sp_smem + P.cap;           // [kpf]  first j with obs > 0 that matched the keypoint; later: its holder
+    const size_t qb = (size_t)blockIdx.x * P.cap;
+    const float* W = world + qb * 3;
+    const uint4* QD = mp_desc + qb * 2;
+    const int* OBS = mp_obs + qb;
+    const int* LO = last_octave + qb;
+    const float* LA = last_angle + qb;
+    const float* K0 = kp + (size_t)f * kpf * 7;
+    const uint4* D0 = reinterpret_cast<const uint4*>(desc + (size_t)f * kpf * 32);
+    const float* XY = xy_un + (size_t)f * kpf * 2;
+    const int* CS = cell_start + (size_t)f * (UG_COLS * UG_ROWS + 1);
+    const int* IT = cell_items + (size_t)f * kpf;
+    const float* UR = P.use_stereo ? u_right + (size_t)f * kpf : nullptr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+
+    for (int i = threadIdx.x; i < nL; i += blockDim.x) s_match[i] = -1;
+    for (int k = threadIdx.x; k < kpf; k += blockDim.x) s_claim[k] = INT_MAX;
+    if (threadIdx.x == 0) { s_changed = 0; s_nm = 0; s_ncull = 0; s_keep = 0xffffffffu; }
+    if (threadIdx.x < SP_HISTO) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+
+    int rounds = 0;
+    for (;;) {
+        for (int i = warp; i < nL; i += nwarps) {
+            int newm = -1;
+            const int o = OBS[i];
+            if (o >= 0) {                                                  // has a map point and is no outlier (:1356-1360)
+                const float wx = W[3 * i], wy = W[3 * i + 1], wz = W[3 * i + 2];
+                // x3Dc = Rcw * x3Dw + tcw: cv::gemm's 3x3 path -- float products and sums, the "+ C" in double
+                float c3[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float t0 = __fadd_rn(__fadd_rn(__fmul_rn(q.R[3 * r], wx), __fmul_rn(q.R[3 * r + 1], wy)), __fmul_rn(q.R[3 * r + 2], wz));
+                    c3[r] = __double2float_rn(__dadd_rn((double)t0, (double)q.t[r]));
+                }
+                const float invzc = __double2float_rn(__ddiv_rn(1.0, (double)c3[2]));           // (:1368)
+                const float u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, c3[0]), invzc), P.cx);      // (:1373-1374)
+                const float v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, c3[1]), invzc), P.cy);
+                // written so that NaN fails (the reference would index the grid with an undefined int cast)
+                const bool inside = !(invzc < 0.f) && u >= P.min_x && u <= P.max_x && v >= P.min_y && v <= P.max_y;
+                if (inside) {
+                    const int lo = LO[i];
+                    const float radius = __fmul_rn(P.th, plan->lv[lo].scale);                   // (:1384)
+                    const int minL = q.fwd ? lo : q.bwd ? 0 : lo - 1;                           // (:1388-1393)
+                    const int maxL = q.fwd ? -1 : q.bwd ? lo : lo + 1;
+                    // Frame::GetFeaturesInArea (src/Frame.cc:332-346)
+                    const int c0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, P.min_x), radius), P.winv)));
+                    const int c1 = min(UG_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, P.min_x), radius), P.winv)));
+                    const int r0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, P.min_y), radius), P.hinv)));
+                    const int r1 = min(UG_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, P.min_y), radius), P.hinv)));
+                    unsigned best = 0xffffffffu;
+                    if (c0 < UG_COLS && c1 >= 0 && r0 < UG_ROWS && r1 >= 0) {
+                        const bool check = minL > 0 || maxL >= 0;
+                        const uint4 qa = QD[2 * i], qc = QD[2 * i + 1];
+                        const float ur = __fsub_rn(u, __fmul_rn(P.mbf, invzc));                 // (:1407)
+                        for (int ix = c0; ix <= c1; ++ix) {
+                            const int p0 = CS[ix * UG_ROWS + r0], p1 = CS[ix * UG_ROWS + r1 + 1];   // cells (ix, r0..r1) are contiguous
+                            for (int p = p0 + lane; p < p1; p += 32) {
+                                const int k = IT[p];
+                                const int oct = __float_as_int(K0[(size_t)k * 7 + 5]);
+                                if (check && (oct < minL || (maxL >= 0 && oct > maxL))) continue;
+                                const float dx = __fsub_rn(XY[2 * k], u), dy = __fsub_rn(XY[2 * k + 1], v);
+                                if (!(fabsf(dx) < radius && fabsf(dy) < radius)) continue;
+                                if (s_claim[k] < i) continue;                                  // (:1401-1403)
+                                if (UR) {
+                                    const float urk = UR[k];
+                                    if (urk > 0.f && fabsf(__fsub_rn(ur, urk)) > radius) continue;   // (:1405-1411)
+                                }
+                                const uint4 da = D0[2 * k], dc = D0[2 * k + 1];
+                                const unsigned dist = __popc(qa.x ^ da.x) + __popc(qa.y ^ da.y) + __popc(qa.z ^ da.z) + __popc(qa.w ^ da.w) +
+                                                      __popc(qc.x ^ dc.x) + __popc(qc.y ^ dc.y) + __popc(qc.z ^ dc.z) + __popc(qc.w ^ dc.w);
+                                best = min(best, (dist << 16) | (unsigned)p);
+                            }
+                        }
+                    }
+                    best = __reduce_min_sync(0xffffffffu, best);
+                    if ((best >> 16) <= SP_TH_HIGH) newm = IT[best & 0xffffu];                  // (:1425)
+                }
+            }
+            if (lane == 0 && s_match[i] != newm) { s_match[i] = newm; s_changed = 1; }
+        }
+        __syncthreads();
+        const int changed = s_changed;
+        ++rounds;
+        __syncthreads();
+        if (!changed) break;
+        if (threadIdx.x == 0) s_changed = 0;
+        for (int k = threadIdx.x; k < kpf; k += blockDim.x) s_claim[k] = INT_MAX;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nL; i += blockDim.x) {
+            const int m = s_match[i];
+            if (m >= 0 && OBS[i] > 0) atomicMin(&s_claim[m], i);
+        }
+        __syncthreads();
+    }
+
+    // ---- rotation histogram and three maxima (:1428-1441, :1446-1453, :1601-1642)
+    int mine = 0;
+    for (int i = threadIdx.x; i < nL; i += blockDim.x) {
+        const int m = s_match[i];
+        if (m < 0) continue;
+        ++mine;
+        if (P.check_ori) atomicAdd(&s_hist[sp_rot_bin(LA[i], K0[(size_t)m * 7 + 3])], 1);
+    }
+    if (mine) atomicAdd(&s_nm, mine);
+    for (int k = threadIdx.x; k < kpf; k += blockDim.x) s_claim[k] = -1;      // from here on: the holder of keypoint k
+    __syncthreads();
+    if (threadIdx.x == 0 && P.check_ori) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int b = 0; b < SP_HISTO; ++b) {
+            const int s = s_hist[b];
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = b; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = b; }
+            else if (s > max3) { max3 = s; ind3 = b; }
+        }
+        if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+        else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+        unsigned keep = 0;
+        if (ind1 >= 0) keep |= 1u << ind1;
+        if (ind2 >= 0) keep |= 1u << ind2;
+        if (ind3 >= 0) keep |= 1u << ind3;
+        s_keep = keep;
+    }
+    for (int i = threadIdx.x; i < nL; i += blockDim.x) {
+        const int m = s_match[i];
+        if (m >= 0) atomicMax(&s_claim[m], i);                                 // the last writer holds the keypoint (:1427)
+    }
+    __syncthreads();
+    if (P.check_ori) {
+        const unsigned keep = s_keep;
+        int culled = 0;
+        for (int i = threadIdx.x; i < nL; i += blockDim.x) {
+            const int m = s_match[i];
+            if (m < 0) continue;
+            if (!((keep >> sp_rot_bin(LA[i], K0[(size_t)m * 7 + 3])) & 1u)) { s_claim[m] = -1; ++culled; }   // (:1455-1463)
+        }
+        if (culled) atomicAdd(&s_ncull, culled);
+    }
+    __syncthreads();
+    int* out = match_out + (size_t)blockIdx.x * kpf;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) out[k] = s_claim[k];
+    if (threadIdx.x == 0) {
+        stats_out[2 * blockIdx.x] = s_nm - s_ncull;
+        stats_out[2 * blockIdx.x + 1] = rounds;
+    }
+}
+
+// =====================================================================================
 // launch wrappers (called from orbx_api.cu)
 // =====================================================================================
 // format: 1 BGR8, 2 RGB8, 3 BGRA8, 4 RGBA8 (orbx_pixel_format)
@@ -2013,6 +2218,43 @@ cudaError_t launch_undistort_grid(const OrbxPlan* d_plan, const OrbxPlan& hp, co
     }
     return launch_k(undistort_grid_kernel, dim3((unsigned)nframes), dim3(1024), smem, st, d_plan, kp, kept_counts, d_frames, P, xy_un,
                     cell_start, cell_items);
+}
+
+size_t search_projection_query_bytes() { return sizeof(SpQuery); }
+
+void search_projection_fill_query(void* dst, const float* Rcw, const float* tcw, int n_last, int frame, int fwd, int bwd) {
+    SpQuery q;
+    for (int i = 0; i < 9; ++i) q.R[i] = Rcw[i];
+    for (int i = 0; i < 3; ++i) q.t[i] = tcw[i];
+    q.n_last = n_last; q.frame = frame; q.fwd = fwd; q.bwd = bwd;
+    memcpy(dst, &q, sizeof q);
+}
+
+cudaError_t launch_search_projection(const OrbxPlan* d_plan, const OrbxPlan& hp, int nq, const void* d_queries, const float* K4,
+                                     const float* bounds, float mbf, float th, int check_ori, int cap, const float* world,
+                                     const uint8_t* mp_desc, const int* mp_obs, const int* last_octave, const float* last_angle,
+                                     const float* kp, const uint8_t* desc, const int* kept_counts, const float* xy_un,
+                                     const int* cell_start, const int* cell_items, const float* u_right, int* match_out,
+                                     int* stats_out, cudaStream_t st) {
+    SpParams P;
+    P.fx = K4[0]; P.fy = K4[1]; P.cx = K4[2]; P.cy = K4[3];
+    P.min_x = bounds[0]; P.max_x = bounds[1]; P.min_y = bounds[2]; P.max_y = bounds[3];
+    P.winv = 64.f / (bounds[1] - bounds[0]);
+    P.hinv = 48.f / (bounds[3] - bounds[2]);
+    P.mbf = mbf; P.th = th; P.check_ori = check_ori; P.cap = cap; P.use_stereo = u_right != nullptr;
+    const size_t smem = (size_t)(cap + hp.kept_per_frame) * sizeof(int);
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> config_lock(g_config_mutex);
+    if (smem > 48 * 1024 && smem > configured[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(search_projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev & 63] = smem;
+    }
+    return launch_k(search_projection_kernel, dim3((unsigned)nq), dim3(1024), smem, st, d_plan, (const SpQuery*)d_queries, P, world,
+                    (const uint4*)mp_desc, mp_obs, last_octave, last_angle, kp, desc, kept_counts, xy_un, cell_start, cell_items,
+                    u_right, match_out, stats_out);
 }
 
 size_t stereo_bucket_entries(const OrbxPlan& hp) { return (size_t)hp.kept_per_frame * ST_MAX_SPAN; }

@@ -256,6 +256,47 @@ class ORBextractor:
             out.append((xy, st, it, np.array(list(r.bounds), np.float32)))
         return out
 
+    # ---------------------------------------------------------------- ORBmatcher::SearchByProjection(Frame&, const Frame&)
+    def _projection_queries(self, queries):
+        """queries: dicts with cur_frame, world (n, 3), mp_desc (n, 32), mp_obs (n,), outlier (n,) or None, last_octave,
+        last_angle, Tcw_cur, Tcw_last.  Returns (ctypes array, keep-alive list)."""
+        qs = (_capi.OrbxProjectionQuery * len(queries))()
+        keep = []
+        for q, d in zip(qs, queries):
+            a = dict(world=np.ascontiguousarray(d["world"], np.float32), mp_desc=np.ascontiguousarray(d["mp_desc"], np.uint8),
+                     mp_obs=np.ascontiguousarray(d["mp_obs"], np.int32), octave=np.ascontiguousarray(d["last_octave"], np.int32),
+                     angle=np.ascontiguousarray(d["last_angle"], np.float32))
+            out = None if d.get("outlier") is None else np.ascontiguousarray(d["outlier"], np.uint8)
+            keep.append((a, out))
+            q.cur_frame, q.n_last = int(d.get("cur_frame", 0)), len(a["mp_obs"])
+            q.world_pos, q.mp_desc, q.mp_obs = a["world"].ctypes.data, a["mp_desc"].ctypes.data, a["mp_obs"].ctypes.data
+            q.outlier = None if out is None else out.ctypes.data
+            q.octave, q.angle = a["octave"].ctypes.data, a["angle"].ctypes.data
+            q.Tcw_cur = (C.c_float * 16)(*np.asarray(d["Tcw_cur"], np.float32).reshape(16))
+            q.Tcw_last = (C.c_float * 16)(*np.asarray(d["Tcw_last"], np.float32).reshape(16))
+        return qs, keep
+
+    def search_by_projection(self, queries, K4, mbf: float, mb: float, th: float, mono: bool, check_orientation: bool = True,
+                             use_stereo: bool = False):
+        """(src/ORBmatcher.cc:1328-1470) for each query against frame `cur_frame` of the last extract (orbx_undistort_grid
+        must have run with the same K4).  Returns [(nmatches, match int32[N], rounds)]."""
+        qs, keep = self._projection_queries(queries)
+        res = (_capi.OrbxProjectionResult * len(queries))()
+        check(self._L.orbx_search_by_projection(self._h, len(queries), qs, (C.c_float * 4)(*K4), mbf, mb, th, int(mono),
+                                                int(check_orientation), int(use_stereo), res), self._h)
+        out = []
+        for r in res:
+            m = np.ctypeslib.as_array(C.cast(r.match, C.POINTER(C.c_int32)), shape=(max(r.n, 1),))[:r.n].copy()
+            out.append((r.nmatches, m, r.rounds))
+        del keep
+        return out
+
+    def search_by_projection_device(self, prepared, K4, mbf, mb, th, mono, check_orientation=True, use_stereo=False):
+        """Stage + enqueue only (device-side timing); `prepared` = self._projection_queries(queries)."""
+        qs, _ = prepared
+        check(self._L.orbx_search_by_projection_device(self._h, len(qs), qs, (C.c_float * 4)(*K4), mbf, mb, th, int(mono),
+                                                       int(check_orientation), int(use_stereo)), self._h)
+
     # ---------------------------------------------------------------- stage dumps (parity tests)
     def stage_dump(self, frame: int, level: int, stage: int):
         nbytes = C.c_size_t()

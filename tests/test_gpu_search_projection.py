@@ -1,0 +1,102 @@
+"""GPU parity of orbx_search_by_projection (ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono), reference
+src/ORBmatcher.cc:1328-1470 with Frame::GetFeaturesInArea src/Frame.cc:327-380) against oracle/match_oracle.py, which is
+pinned against the reference's own lines.  Bar: nmatches and the map-point assignment of every current keypoint identical
+(integer results; the float32 projection feeding them is bit-reproduced, tolerance 0)."""
+import numpy as np
+import pytest
+
+from oracle import match_oracle
+from orbslam2_with_quadrics_b200 import ORBextractor, OrbxError
+from orbslam2_with_quadrics_b200 import frames as fr
+from orbslam2_with_quadrics_b200 import match_cases as mc
+
+pytestmark = pytest.mark.gpu
+K_TUM1, D_TUM1 = (517.306408, 516.469215, 318.643040, 255.313989), (0.262383, -0.953104, -0.005358, 0.002628, 1.163314)
+K_KITTI, D_RECT = (718.856, 718.856, 607.1928, 185.2157), (0.0, 0.0, 0.0, 0.0)
+
+
+def build_query(rng, frame, kps, desc, grid, K4, n_last, nlevels, motion):
+    xy, start, items, bounds = grid
+    Tc = mc.pose(rng)
+    Tl = mc.pose(rng, t=(0.0, 0.0, {"still": 0.0, "forward": 0.9, "backward": -0.9}[motion]))
+    last = mc.make_last_frame(rng, xy, kps["octave"].astype(np.int32), kps["angle"].astype(np.float32), desc, K4, Tc, n_last, nlevels)
+    return dict(cur_frame=frame, Tcw_cur=Tc, Tcw_last=Tl, **last)
+
+
+def oracle_result(q, kps, desc, grid, K4, mbf, mb, sf, th, mono, check, u_right):
+    xy, start, items, bounds = grid
+    return match_oracle.search_by_projection(
+        q["world"], q["mp_desc"], q["mp_obs"], q["outlier"], q["last_octave"], q["last_angle"], q["Tcw_cur"], q["Tcw_last"], xy,
+        kps["octave"].astype(np.int32), kps["angle"].astype(np.float32), desc, u_right, start, items, bounds, K4, mbf, mb, sf, th,
+        mono, check)
+
+
+def test_monocular_batch_matches_oracle():
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["mono_tum"]
+    gx = ORBextractor(nf, sf, nl, it, mt, max_batch=4)
+    res = gx.extract_batch([fr.cluttered_scene(w, h, 900 + i) for i in range(3)] + [fr.flat_frame(w, h)])
+    grids = gx.undistort_grid(K_TUM1, D_TUM1)
+    rng = np.random.default_rng(11)
+    qs = [build_query(rng, f, res[f][0], res[f][1], grids[f], K_TUM1, n, nl, "still") for f, n in ((0, 1000), (1, 350), (2, 1700))]
+    for th, check in ((15.0, True), (30.0, True), (15.0, False)):
+        out = gx.search_by_projection(qs, K_TUM1, 40.0, 0.08, th, True, check)
+        for q, (n, m, rounds) in zip(qs, out):
+            f = q["cur_frame"]
+            n0, m0 = oracle_result(q, res[f][0], res[f][1], grids[f], K_TUM1, 40.0, 0.08, gx.GetScaleFactors(), th, True, check, None)
+            assert n == n0 and np.array_equal(m, m0)
+            assert n > 0.2 * len(q["mp_obs"]) and rounds >= 2          # contention really needed more than one round
+    # queries in another order, one of them against the frame without keypoints, one with an empty LastFrame
+    empty = dict(qs[0]); empty.update(cur_frame=3)
+    none = {k: (v[:0] if isinstance(v, np.ndarray) and v.ndim and len(v) == len(qs[1]["mp_obs"]) else v) for k, v in qs[1].items()}
+    out = gx.search_by_projection([qs[2], empty, none], K_TUM1, 40.0, 0.08, 15.0, True)
+    n0, m0 = oracle_result(qs[2], res[2][0], res[2][1], grids[2], K_TUM1, 40.0, 0.08, gx.GetScaleFactors(), 15.0, True, True, None)
+    assert out[0][0] == n0 and np.array_equal(out[0][1], m0)
+    assert out[1][0] == 0 and len(out[1][1]) == 0
+    assert out[2][0] == 0 and np.all(out[2][1] == -1) and len(out[2][1]) == len(res[1][0])
+    gx.close()
+
+
+@pytest.mark.parametrize("motion", ["still", "forward", "backward"])
+def test_stereo_frame_with_device_uright_matches_oracle(motion):
+    """The stereo Frame: mvuRight comes from orbx_stereo_match on the same handle and never leaves HBM."""
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["stereo_kitti"]
+    left, right = fr.stereo_pair(w, h, 40)
+    gx = ORBextractor(nf, sf, nl, it, mt, max_batch=2)
+    res = gx.extract_batch([left, right])
+    mbf, mb = 386.1448, 0.5371657
+    (u_right, _), = gx.stereo_match(gx, mbf, mb, left_frames=[0], right_frames=[1])
+    grids = gx.undistort_grid(K_KITTI, D_RECT)
+    rng = np.random.default_rng({"still": 21, "forward": 22, "backward": 23}[motion])
+    q = build_query(rng, 0, res[0][0], res[0][1], grids[0], K_KITTI, 1900, nl, motion)
+    assert match_oracle.motion_flags(q["Tcw_cur"], q["Tcw_last"], mb, False) == (motion == "forward", motion == "backward")
+    for th in (7.0, 14.0):
+        (n, m, rounds), = gx.search_by_projection([q], K_KITTI, mbf, mb, th, False, True, use_stereo=True)
+        n0, m0 = oracle_result(q, res[0][0], res[0][1], grids[0], K_KITTI, mbf, mb, gx.GetScaleFactors(), th, False, True, u_right)
+        assert n == n0 and np.array_equal(m, m0) and n > 100
+    assert (u_right > 0).sum() > 100                                     # the mvuRight test (:1405-1411) really ran
+    gx.close()
+
+
+def test_4k_and_bad_arguments():
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["mono_4k"]
+    K4, D = (3100.0, 3098.0, 1915.5, 1082.25), (0.12, -0.31, 0.0007, -0.0004, 0.09)
+    gx = ORBextractor(nf, sf, nl, it, mt)
+    kps, desc = gx(fr.cluttered_scene(w, h, 9))
+    rng = np.random.default_rng(5)
+    with pytest.raises(OrbxError):
+        gx.search_by_projection([dict(cur_frame=0, world=np.zeros((1, 3)), mp_desc=np.zeros((1, 32)), mp_obs=[1], last_octave=[0],
+                                      last_angle=[0.0], Tcw_cur=np.eye(4), Tcw_last=np.eye(4))], K4, 0.0, 0.0, 15.0, True)   # no grid yet
+    (grid,) = gx.undistort_grid(K4, D)
+    q = build_query(rng, 0, kps, desc, grid, K4, 4000, nl, "still")
+    (n, m, rounds), = gx.search_by_projection([q], K4, 0.0, 0.0, 15.0, True)
+    n0, m0 = oracle_result(q, kps, desc, grid, K4, 0.0, 0.0, gx.GetScaleFactors(), 15.0, True, True, None)
+    assert n == n0 and np.array_equal(m, m0)
+    bad = dict(q); bad.update(cur_frame=1)
+    with pytest.raises(OrbxError):
+        gx.search_by_projection([bad], K4, 0.0, 0.0, 15.0, True)
+    bad = dict(q); bad["last_octave"] = np.full(len(q["mp_obs"]), nl, np.int32)
+    with pytest.raises(OrbxError):
+        gx.search_by_projection([bad], K4, 0.0, 0.0, 15.0, True)
+    with pytest.raises(OrbxError):
+        gx.search_by_projection([q], K4, 0.0, 0.0, 15.0, False, True, use_stereo=True)      # no stereo match on this handle
+    gx.close()
