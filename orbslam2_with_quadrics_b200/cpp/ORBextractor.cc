@@ -175,4 +175,34 @@ void ORBextractor::UndistortAndAssignToGrid(const cv::Mat& mK, const cv::Mat& mD
     mnMinX = r.bounds[0]; mnMaxX = r.bounds[1]; mnMinY = r.bounds[2]; mnMaxY = r.bounds[3];
 }
 
+int ORBextractor::SearchByProjection(const std::vector<float>& lastWorldPos, const std::vector<unsigned char>& lastDescriptors,
+                                     const std::vector<int>& lastObservations, const std::vector<cv::KeyPoint>& lastKeysUn,
+                                     const cv::Mat& TcwCurrent, const cv::Mat& TcwLast, const cv::Mat& mK, float mbf, float mb, float th,
+                                     bool bMono, bool checkOrientation, bool useStereo, std::vector<int>& matchedLast)
+{
+    const size_t n = lastKeysUn.size();
+    if (lastWorldPos.size() != 3 * n || lastDescriptors.size() != 32 * n || lastObservations.size() != n)
+        throw std::runtime_error("ORBextractor (orbx): SearchByProjection needs 3 floats, 32 bytes and 1 int per LastFrame keypoint");
+    std::vector<int> octave(n);
+    std::vector<float> angle(n);
+    for (size_t i = 0; i < n; ++i) { octave[i] = lastKeysUn[i].octave; angle[i] = lastKeysUn[i].angle; }
+    orbx_projection_query q;
+    q.cur_frame = 0;
+    q.n_last = (int)n;
+    q.world_pos = lastWorldPos.data();
+    q.mp_desc = lastDescriptors.data();
+    q.mp_obs = lastObservations.data();
+    q.outlier = 0;
+    q.octave = octave.data();
+    q.angle = angle.data();
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) { q.Tcw_cur[4*r+c] = TcwCurrent.at<float>(r,c); q.Tcw_last[4*r+c] = TcwLast.at<float>(r,c); }
+    const float K4[4] = {mK.at<float>(0,0), mK.at<float>(1,1), mK.at<float>(0,2), mK.at<float>(1,2)};
+    orbx_projection_result r;
+    int rc = orbx_search_by_projection(handle_, 1, &q, K4, mbf, mb, th, bMono ? 1 : 0, checkOrientation ? 1 : 0, useStereo ? 1 : 0, &r);
+    if (rc != ORBX_OK) orbx_throw(handle_, rc, "orbx_search_by_projection");
+    matchedLast.assign(r.match, r.match + r.n);
+    return r.nmatches;
+}
+
 } //namespace ORB_SLAM

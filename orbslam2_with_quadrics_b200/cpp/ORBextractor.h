@@ -76,6 +76,19 @@ public:
                                   std::vector<cv::KeyPoint>& mvKeysUn, std::vector<std::size_t> (*mGrid)[48],
                                   float& mnMinX, float& mnMaxX, float& mnMinY, float& mnMaxY);
 
+    // ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (reference
+    // src/ORBmatcher.cc:1328-1470) on the GPU: `this` is CurrentFrame.mpORBextractorLeft, whose last operator(),
+    // UndistortAndAssignToGrid and (with useStereo) ComputeStereoMatches left mvKeysUn, mDescriptors, mGrid and mvuRight in
+    // HBM.  The LastFrame side is gathered by the caller from LastFrame.mvpMapPoints: world position (3 floats),
+    // representative descriptor (32 bytes) and Observations() per keypoint, obs < 0 where there is no map point or
+    // mvbOutlier is set.  matchedLast[i2] = index into LastFrame of the map point CurrentFrame.mvpMapPoints[i2] receives,
+    // -1 = NULL.  Returns nmatches.  CurrentFrame.mvpMapPoints is taken to be all NULL on entry, as at both call sites
+    // (src/Tracking.cc:871, :890).
+    int SearchByProjection(const std::vector<float>& lastWorldPos, const std::vector<unsigned char>& lastDescriptors,
+                           const std::vector<int>& lastObservations, const std::vector<cv::KeyPoint>& lastKeysUn,
+                           const cv::Mat& TcwCurrent, const cv::Mat& TcwLast, const cv::Mat& mK, float mbf, float mb, float th,
+                           bool bMono, bool checkOrientation, bool useStereo, std::vector<int>& matchedLast);
+
 private:
     ORBextractor(const ORBextractor&);
     ORBextractor& operator=(const ORBextractor&);

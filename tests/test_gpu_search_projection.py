@@ -100,3 +100,66 @@ def test_4k_and_bad_arguments():
     with pytest.raises(OrbxError):
         gx.search_by_projection([q], K4, 0.0, 0.0, 15.0, False, True, use_stereo=True)      # no stereo match on this handle
     gx.close()
+
+
+def test_timing_report_beside_reference_lines():
+    """Measurement of the row: device time of one launch over a batch of (LastFrame, CurrentFrame) queries (CUDA events on
+    the handle's stream, staging H2D included), end-to-end wall time through the C ABI, and the reference's own lines
+    (oracle/_ref, one host thread) on the same queries.  Written to gpurun_out/r01_search_projection.json when that
+    directory exists; the assertions are parity only."""
+    import json
+    import os
+    import time
+
+    import torch
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["rgbd_1080p"]
+    B = 16
+    gx = ORBextractor(nf, sf, nl, it, mt, max_batch=B, download_pyramid=False)
+    imgs = [fr.cluttered_scene(w, h, 3000 + i) for i in range(4)]
+    res = gx.extract_batch([imgs[i % 4] for i in range(B)])
+    K4, D = (1050.0, 1050.0, 959.5, 539.5), (0.05, -0.11, 0.0004, -0.0003, 0.02)
+    grids = gx.undistort_grid(K4, D)
+    rng = np.random.default_rng(77)
+    qs = [build_query(rng, f, res[f][0], res[f][1], grids[f], K4, len(res[f][0]), nl, "still") for f in range(B)]
+    out = gx.search_by_projection(qs, K4, 0.0, 0.0, 15.0, True)
+    prepared = gx._projection_queries(qs)
+    st = torch.cuda.ExternalStream(gx.stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        gx.search_by_projection_device(prepared, K4, 0.0, 0.0, 15.0, True)
+    gx.synchronize()
+    K = 20
+    t0 = time.perf_counter()
+    e0.record(st)
+    for _ in range(K):
+        gx.search_by_projection_device(prepared, K4, 0.0, 0.0, 15.0, True)
+    e1.record(st)
+    gx.synchronize()
+    wall_dev = (time.perf_counter() - t0) / K * 1e3
+    dev_ms = e0.elapsed_time(e1) / K
+    t0 = time.perf_counter()
+    for _ in range(K):
+        gx.search_by_projection(qs, K4, 0.0, 0.0, 15.0, True)
+    e2e_ms = (time.perf_counter() - t0) / K * 1e3
+    cpu_ms = None
+    if match_oracle.ref_available():
+        t0 = time.perf_counter()
+        for q, (n, m, _) in zip(qs[:4], out[:4]):
+            f = q["cur_frame"]
+            xy, start, items, bounds = grids[f]
+            n0, m0 = match_oracle.ref_search_by_projection(
+                q["world"], q["mp_desc"], q["mp_obs"], q["outlier"], q["last_octave"], q["last_angle"], q["Tcw_cur"], q["Tcw_last"],
+                xy, res[f][0]["octave"].astype(np.int32), res[f][0]["angle"].astype(np.float32), res[f][1], None, start, items,
+                bounds, K4, 0.0, 0.0, gx.GetScaleFactors(), 15.0, True, True)
+            assert n == n0 and np.array_equal(m, m0)
+        cpu_ms = (time.perf_counter() - t0) / 4 * 1e3
+    rep = {"workload": "SearchByProjection, %d queries of %d LastFrame map points against 1920x1080 frames of ~%d keypoints, th 15, mono"
+                       % (B, len(qs[0]["mp_obs"]), len(res[0][0])),
+           "device_ms_per_batch_incl_staging_h2d": dev_ms, "device_us_per_query": dev_ms / B * 1e3,
+           "host_wall_ms_per_batch_enqueue_only": wall_dev, "e2e_ms_per_batch_with_d2h": e2e_ms, "e2e_us_per_query": e2e_ms / B * 1e3,
+           "reference_lines_cpu_ms_per_query_1_thread": cpu_ms, "rounds": [r for _, _, r in out],
+           "nmatches": [n for n, _, _ in out]}
+    print(json.dumps(rep))
+    if os.path.isdir("gpurun_out"):
+        json.dump(rep, open("gpurun_out/r01_search_projection.json", "w"), indent=1)
+    gx.close()
