@@ -1154,15 +1154,23 @@ static int sp_enqueue(orbx_handle* h, int nq, const orbx_projection_query* q, co
     if ((size_t)(cap + P.kept_per_frame) * sizeof(int) > 200 * 1024) return ORBX_ERR_BAD_ARGS;
     CK(h, cudaSetDevice(h->cfg.device));
     const size_t qbytes = (orbx::search_projection_query_bytes() + 15) & ~(size_t)15;
-    // staging layout: [queries][mp_desc nq*cap*32][world nq*cap*3 f32][obs nq*cap][octave nq*cap][angle nq*cap]
+    // staging layout: [queries][mp_desc nq*cap*32][world nq*cap*3 f32][obs nq*cap][octave nq*cap][angle nq*cap]; device only,
+    // behind it: [candidate counts nq*cap][candidate lists nq*cap*list_cap u16]
+    int list_cap = 32;                                               // entries a point's candidate list may hold (test knob: small
+    if (const char* e = getenv("ORBX_SP_LIST_CAP")) {                // values force the full-search path of the resolve kernel)
+        const int v = atoi(e);
+        if (v >= 1 && v <= 32) list_cap = v;
+    }
     const size_t o_desc = (size_t)nq * qbytes, o_world = o_desc + (size_t)nq * cap * 32, o_obs = o_world + (size_t)nq * cap * 12,
-                 o_oct = o_obs + (size_t)nq * cap * 4, o_ang = o_oct + (size_t)nq * cap * 4, total = o_ang + (size_t)nq * cap * 4;
+                 o_oct = o_obs + (size_t)nq * cap * 4, o_ang = o_oct + (size_t)nq * cap * 4, staged = o_ang + (size_t)nq * cap * 4,
+                 o_cnt = (staged + 15) & ~(size_t)15, o_list = o_cnt + (size_t)nq * cap * 4,
+                 total = o_list + (size_t)nq * cap * 32 * 2;
     cudaStream_t st = h->stream;
     CK(h, cudaStreamSynchronize(st));                                // the staging of a previous call is free
     if (total > h->sp_bytes) {
         cudaFree(h->d_sp); cudaFreeHost(h->h_sp); h->d_sp = h->h_sp = 0; h->sp_bytes = 0;
         CK(h, cudaMalloc(&h->d_sp, total));
-        CK(h, cudaMallocHost(&h->h_sp, total));
+        CK(h, cudaMallocHost(&h->h_sp, staged));
         h->sp_bytes = total;
     }
     const size_t out_ints = (size_t)h->cfg.max_batch * ((size_t)P.kept_per_frame + 2);
@@ -1205,14 +1213,15 @@ static int sp_enqueue(orbx_handle* h, int nq, const orbx_projection_query* q, co
             const int o = q[i].octave[k];
             if (o < 0 || o >= P.nlevels) return ORBX_ERR_BAD_ARGS;
         }
-    CK(h, cudaMemcpyAsync(h->d_sp, h->h_sp, total, cudaMemcpyHostToDevice, st));
-    CK(h, orbx::launch_search_projection(h->d_plan, P, nq, h->d_sp, K4, h->un_bounds, mbf, th, check_orientation, cap,
+    CK(h, cudaMemcpyAsync(h->d_sp, h->h_sp, staged, cudaMemcpyHostToDevice, st));
+    CK(h, orbx::launch_search_projection(h->d_plan, P, nq, h->d_sp, K4, h->un_bounds, mbf, th, check_orientation, cap, list_cap,
                                          reinterpret_cast<const float*>(h->d_sp + o_world), h->d_sp + o_desc,
                                          reinterpret_cast<const int*>(h->d_sp + o_obs), reinterpret_cast<const int*>(h->d_sp + o_oct),
                                          reinterpret_cast<const float*>(h->d_sp + o_ang), h->d_out_kp, h->d_out_desc, h->d_kept_counts(),
-                                         h->d_un_xy, h->d_un_start, h->d_un_items, use_stereo ? h->d_st_u : nullptr, h->d_sp_out,
+                                         h->d_un_xy, h->d_un_start, h->d_un_items, use_stereo ? h->d_st_u : nullptr,
+                                         reinterpret_cast<uint16_t*>(h->d_sp + o_list), reinterpret_cast<int*>(h->d_sp + o_cnt), h->d_sp_out,
                                          h->d_sp_out + (size_t)h->cfg.max_batch * P.kept_per_frame, st));
-    h->launches += 1;
+    h->launches += 2;
     if (cap_out) *cap_out = cap;
     return ORBX_OK;
 }

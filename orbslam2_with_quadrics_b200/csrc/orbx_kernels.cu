@@ -1823,16 +1823,153 @@ __device__ __forceinline__ int sp_rot_bin(float last_angle, float cur_angle) {
     return min(max(bin, 0), SP_HISTO - 1);                                  // the reference asserts the range
 }
 
+// Per-frame views of what the extraction, orbx_undistort_grid and orbx_stereo_match left in HBM.
+struct SpFrame {
+    const float* K0;       // keypoint records (7 floats)
+    const uint4* D0;       // descriptors
+    const float* XY;       // mvKeysUn[].pt
+    const int* CS;         // mGrid as CSR
+    const int* IT;
+    const float* UR;       // mvuRight or nullptr
+};
+
+// One LastFrame map point against the current frame: projection (:1362-1380), search window (:1384-1393),
+// GetFeaturesInArea + the mvuRight test + DescriptorDistance over the candidates.  Executed by a whole warp; every lane
+// returns the warp's best key (distance << 16 | CSR position), 0xffffffff when nothing qualifies.
+//   s_claim != nullptr : candidates claimed by an earlier point with observations are skipped (:1401-1403);
+//   buf != nullptr     : every candidate with distance <= TH_HIGH is appended to buf (first `lc` of them), *total counts them.
+__device__ __forceinline__ unsigned sp_scan(const OrbxPlan* __restrict__ plan, const SpQuery& q, const SpParams& P, const SpFrame& F,
+                                            const float* __restrict__ W, const uint4* __restrict__ QD, const int* __restrict__ LO,
+                                            int i, int lane, const int* s_claim, unsigned* buf, int lc, int* total) {
+    const float wx = W[3 * i], wy = W[3 * i + 1], wz = W[3 * i + 2];
+    // x3Dc = Rcw * x3Dw + tcw: cv::gemm's 3x3 path -- float products and sums, the "+ C" in double
+    float c3[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float t0 = __fadd_rn(__fadd_rn(__fmul_rn(q.R[3 * r], wx), __fmul_rn(q.R[3 * r + 1], wy)), __fmul_rn(q.R[3 * r + 2], wz));
+        c3[r] = __double2float_rn(__dadd_rn((double)t0, (double)q.t[r]));
+    }
+    const float invzc = __double2float_rn(__ddiv_rn(1.0, (double)c3[2]));           // (:1368)
+    const float u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, c3[0]), invzc), P.cx);      // (:1373-1374)
+    const float v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, c3[1]), invzc), P.cy);
+    // written so that NaN fails (the reference would index the grid with an undefined int cast)
+    const bool inside = !(invzc < 0.f) && u >= P.min_x && u <= P.max_x && v >= P.min_y && v <= P.max_y;
+    if (!inside) return 0xffffffffu;
+    const int lo = LO[i];
+    const float radius = __fmul_rn(P.th, plan->lv[lo].scale);                       // (:1384)
+    const int minL = q.fwd ? lo : q.bwd ? 0 : lo - 1;                               // (:1388-1393)
+    const int maxL = q.fwd ? -1 : q.bwd ? lo : lo + 1;
+    // Frame::GetFeaturesInArea (src/Frame.cc:332-346)
+    const int c0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, P.min_x), radius), P.winv)));
+    const int c1 = min(UG_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, P.min_x), radius), P.winv)));
+    const int r0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, P.min_y), radius), P.hinv)));
+    const int r1 = min(UG_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, P.min_y), radius), P.hinv)));
+    if (!(c0 < UG_COLS && c1 >= 0 && r0 < UG_ROWS && r1 >= 0)) return 0xffffffffu;
+    unsigned best = 0xffffffffu;
+    const bool check = minL > 0 || maxL >= 0;
+    const uint4 qa = QD[2 * i], qc = QD[2 * i + 1];
+    const float ur = __fsub_rn(u, __fmul_rn(P.mbf, invzc));                         // (:1407)
+    int tot = 0;
+    for (int ix = c0; ix <= c1; ++ix) {
+        const int p0 = F.CS[ix * UG_ROWS + r0], p1 = F.CS[ix * UG_ROWS + r1 + 1];   // cells (ix, r0..r1) are contiguous
+        for (int pb = p0; pb < p1; pb += 32) {
+            const int p = pb + lane;
+            unsigned key = 0xffffffffu;
+            if (p < p1) {
+                const int k = F.IT[p];
+                const int oct = __float_as_int(F.K0[(size_t)k * 7 + 5]);
+                bool ok = !(check && (oct < minL || (maxL >= 0 && oct > maxL)));
+                const float dx = __fsub_rn(F.XY[2 * k], u), dy = __fsub_rn(F.XY[2 * k + 1], v);
+                ok = ok && fabsf(dx) < radius && fabsf(dy) < radius;
+                if (ok && s_claim) ok = !(s_claim[k] < i);                            // (:1401-1403)
+                if (ok && F.UR) {
+                    const float urk = F.UR[k];
+                    ok = !(urk > 0.f && fabsf(__fsub_rn(ur, urk)) > radius);          // (:1405-1411)
+                }
+                if (ok) {
+                    const uint4 da = F.D0[2 * k], dc = F.D0[2 * k + 1];
+                    const unsigned dist = __popc(qa.x ^ da.x) + __popc(qa.y ^ da.y) + __popc(qa.z ^ da.z) + __popc(qa.w ^ da.w) +
+                                          __popc(qc.x ^ dc.x) + __popc(qc.y ^ dc.y) + __popc(qc.z ^ dc.z) + __popc(qc.w ^ dc.w);
+                    key = (dist << 16) | (unsigned)p;
+                }
+            }
+            best = min(best, key);
+            if (buf) {
+                const bool pass = (key >> 16) <= SP_TH_HIGH;
+                const unsigned m = __ballot_sync(0xffffffffu, pass);
+                if (pass) {
+                    const int slot = tot + __popc(m & ((1u << lane) - 1u));
+                    if (slot < lc) buf[slot] = key;
+                }
+                tot += __popc(m);
+            }
+        }
+    }
+    if (total) *total = tot;
+    return __reduce_min_sync(0xffffffffu, best);
+}
+
+// Pass 1, state-free and GPU-wide: a warp per (query, LastFrame point) lists the point's acceptable candidates
+// (distance <= TH_HIGH) in the reference's preference order -- ascending (distance, visiting position).  Whatever the
+// claims turn out to be, the point's match is the first unclaimed entry of this list (:1396-1423), so the sequential
+// part (pass 2) never touches a descriptor again.  cand_count > lc marks a list that did not fit.
+#define SP_LIST_WARPS 8
+__global__ void __launch_bounds__(SP_LIST_WARPS * 32)
+search_projection_list_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __restrict__ queries, SpParams P, int nq, int lc,
+                              const float* __restrict__ world, const uint4* __restrict__ mp_desc, const int* __restrict__ mp_obs,
+                              const int* __restrict__ last_octave, const float* __restrict__ kp, const uint8_t* __restrict__ desc,
+                              const float* __restrict__ xy_un, const int* __restrict__ cell_start, const int* __restrict__ cell_items,
+                              const float* __restrict__ u_right, uint16_t* __restrict__ cand_list, int* __restrict__ cand_count) {
+    __shared__ unsigned s_buf[SP_LIST_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kpf = plan->kept_per_frame;
+    const long long slot = (long long)blockIdx.x * SP_LIST_WARPS + warp;
+    if (slot >= (long long)nq * P.cap) return;
+    const int qi = (int)(slot / P.cap), i = (int)(slot % P.cap);
+    const SpQuery q = queries[qi];
+    if (i >= q.n_last) return;
+    const size_t qb = (size_t)qi * P.cap;
+    int total = 0;
+    if (mp_obs[qb + i] >= 0) {                                              // has a map point and is no outlier (:1356-1360)
+        const int f = q.frame;
+        SpFrame F;
+        F.K0 = kp + (size_t)f * kpf * 7;
+        F.D0 = reinterpret_cast<const uint4*>(desc + (size_t)f * kpf * 32);
+        F.XY = xy_un + (size_t)f * kpf * 2;
+        F.CS = cell_start + (size_t)f * (UG_COLS * UG_ROWS + 1);
+        F.IT = cell_items + (size_t)f * kpf;
+        F.UR = P.use_stereo ? u_right + (size_t)f * kpf : nullptr;
+        sp_scan(plan, q, P, F, world + qb * 3, mp_desc + qb * 2, last_octave + qb, i, lane, nullptr, s_buf[warp], lc, &total);
+        __syncwarp();
+        if (total > 0 && total <= lc) {
+            // bitonic sort of the (at most 32) keys across the warp, ascending
+            unsigned v = lane < total ? s_buf[warp][lane] : 0xffffffffu;
+#pragma unroll
+            for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    const unsigned o = __shfl_xor_sync(0xffffffffu, v, j);
+                    const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+                    v = (lower == up) ? min(v, o) : max(v, o);
+                }
+            if (lane < total) cand_list[(qb + i) * (size_t)lc + lane] = (uint16_t)F.IT[v & 0xffffu];
+        }
+    }
+    if (lane == 0) cand_count[qb + i] = total;
+}
+
+// Pass 2: one CTA per query resolves the claims (see the header comment), then histogram, maxima and culling.
 __global__ void __launch_bounds__(1024)
-search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __restrict__ queries, SpParams P,
+search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __restrict__ queries, SpParams P, int lc,
                          const float* __restrict__ world, const uint4* __restrict__ mp_desc, const int* __restrict__ mp_obs,
                          const int* __restrict__ last_octave, const float* __restrict__ last_angle,
                          const float* __restrict__ kp, const uint8_t* __restrict__ desc, const int* __restrict__ kept_counts,
                          const float* __restrict__ xy_un, const int* __restrict__ cell_start, const int* __restrict__ cell_items,
-                         const float* __restrict__ u_right, int* __restrict__ match_out, int* __restrict__ stats_out) {
+                         const float* __restrict__ u_right, const uint16_t* __restrict__ cand_list,
+                         const int* __restrict__ cand_count, int* __restrict__ match_out, int* __restrict__ stats_out) {
     extern __shared__ int sp_smem[];
     __shared__ int s_hist[SP_HISTO];
-    __shared__ int s_changed, s_nm, s_ncull;
+    __shared__ int s_changed, s_nm, s_ncull, s_nover;
     __shared__ unsigned s_keep;
     const SpQuery q = queries[blockIdx.x];
     const int kpf = plan->kept_per_frame, nl = plan->nlevels;
@@ -1847,80 +1984,47 @@ search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __res
     const int* OBS = mp_obs + qb;
     const int* LO = last_octave + qb;
     const float* LA = last_angle + qb;
-    const float* K0 = kp + (size_t)f * kpf * 7;
-    const uint4* D0 = reinterpret_cast<const uint4*>(desc + (size_t)f * kpf * 32);
-    const float* XY = xy_un + (size_t)f * kpf * 2;
-    const int* CS = cell_start + (size_t)f * (UG_COLS * UG_ROWS + 1);
-    const int* IT = cell_items + (size_t)f * kpf;
-    const float* UR = P.use_stereo ? u_right + (size_t)f * kpf : nullptr;
+    const uint16_t* CL = cand_list + qb * (size_t)lc;
+    const int* CC = cand_count + qb;
+    SpFrame F;
+    F.K0 = kp + (size_t)f * kpf * 7;
+    F.D0 = reinterpret_cast<const uint4*>(desc + (size_t)f * kpf * 32);
+    F.XY = xy_un + (size_t)f * kpf * 2;
+    F.CS = cell_start + (size_t)f * (UG_COLS * UG_ROWS + 1);
+    F.IT = cell_items + (size_t)f * kpf;
+    F.UR = P.use_stereo ? u_right + (size_t)f * kpf : nullptr;
+    const float* K0 = F.K0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
-    for (int i = threadIdx.x; i < nL; i += blockDim.x) s_match[i] = -1;
-    for (int k = threadIdx.x; k < kpf; k += blockDim.x) s_claim[k] = INT_MAX;
-    if (threadIdx.x == 0) { s_changed = 0; s_nm = 0; s_ncull = 0; s_keep = 0xffffffffu; }
+    if (threadIdx.x == 0) { s_changed = 0; s_nm = 0; s_ncull = 0; s_keep = 0xffffffffu; s_nover = 0; }
     if (threadIdx.x < SP_HISTO) s_hist[threadIdx.x] = 0;
     __syncthreads();
+    int over = 0;
+    for (int i = threadIdx.x; i < nL; i += blockDim.x) { s_match[i] = -1; over += CC[i] > lc; }
+    if (over) atomicAdd(&s_nover, over);
+    for (int k = threadIdx.x; k < kpf; k += blockDim.x) s_claim[k] = INT_MAX;
+    __syncthreads();
+    const int nover = s_nover;
 
     int rounds = 0;
     for (;;) {
-        for (int i = warp; i < nL; i += nwarps) {
+        for (int i = threadIdx.x; i < nL; i += blockDim.x) {               // a thread per point: first unclaimed list entry
+            const int c = CC[i];
+            if (c > lc) continue;
             int newm = -1;
-            const int o = OBS[i];
-            if (o >= 0) {                                                  // has a map point and is no outlier (:1356-1360)
-                const float wx = W[3 * i], wy = W[3 * i + 1], wz = W[3 * i + 2];
-                // x3Dc = Rcw * x3Dw + tcw: cv::gemm's 3x3 path -- float products and sums, the "+ C" in double
-                float c3[3];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const float t0 = __fadd_rn(__fadd_rn(__fmul_rn(q.R[3 * r], wx), __fmul_rn(q.R[3 * r + 1], wy)), __fmul_rn(q.R[3 * r + 2], wz));
-                    c3[r] = __double2float_rn(__dadd_rn((double)t0, (double)q.t[r]));
-                }
-                const float invzc = __double2float_rn(__ddiv_rn(1.0, (double)c3[2]));           // (:1368)
-                const float u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, c3[0]), invzc), P.cx);      // (:1373-1374)
-                const float v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, c3[1]), invzc), P.cy);
-                // written so that NaN fails (the reference would index the grid with an undefined int cast)
-                const bool inside = !(invzc < 0.f) && u >= P.min_x && u <= P.max_x && v >= P.min_y && v <= P.max_y;
-                if (inside) {
-                    const int lo = LO[i];
-                    const float radius = __fmul_rn(P.th, plan->lv[lo].scale);                   // (:1384)
-                    const int minL = q.fwd ? lo : q.bwd ? 0 : lo - 1;                           // (:1388-1393)
-                    const int maxL = q.fwd ? -1 : q.bwd ? lo : lo + 1;
-                    // Frame::GetFeaturesInArea (src/Frame.cc:332-346)
-                    const int c0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, P.min_x), radius), P.winv)));
-                    const int c1 = min(UG_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, P.min_x), radius), P.winv)));
-                    const int r0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, P.min_y), radius), P.hinv)));
-                    const int r1 = min(UG_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, P.min_y), radius), P.hinv)));
-                    unsigned best = 0xffffffffu;
-                    if (c0 < UG_COLS && c1 >= 0 && r0 < UG_ROWS && r1 >= 0) {
-                        const bool check = minL > 0 || maxL >= 0;
-                        const uint4 qa = QD[2 * i], qc = QD[2 * i + 1];
-                        const float ur = __fsub_rn(u, __fmul_rn(P.mbf, invzc));                 // (:1407)
-                        for (int ix = c0; ix <= c1; ++ix) {
-                            const int p0 = CS[ix * UG_ROWS + r0], p1 = CS[ix * UG_ROWS + r1 + 1];   // cells (ix, r0..r1) are contiguous
-                            for (int p = p0 + lane; p < p1; p += 32) {
-                                const int k = IT[p];
-                                const int oct = __float_as_int(K0[(size_t)k * 7 + 5]);
-                                if (check && (oct < minL || (maxL >= 0 && oct > maxL))) continue;
-                                const float dx = __fsub_rn(XY[2 * k], u), dy = __fsub_rn(XY[2 * k + 1], v);
-                                if (!(fabsf(dx) < radius && fabsf(dy) < radius)) continue;
-                                if (s_claim[k] < i) continue;                                  // (:1401-1403)
-                                if (UR) {
-                                    const float urk = UR[k];
-                                    if (urk > 0.f && fabsf(__fsub_rn(ur, urk)) > radius) continue;   // (:1405-1411)
-                                }
-                                const uint4 da = D0[2 * k], dc = D0[2 * k + 1];
-                                const unsigned dist = __popc(qa.x ^ da.x) + __popc(qa.y ^ da.y) + __popc(qa.z ^ da.z) + __popc(qa.w ^ da.w) +
-                                                      __popc(qc.x ^ dc.x) + __popc(qc.y ^ dc.y) + __popc(qc.z ^ dc.z) + __popc(qc.w ^ dc.w);
-                                best = min(best, (dist << 16) | (unsigned)p);
-                            }
-                        }
-                    }
-                    best = __reduce_min_sync(0xffffffffu, best);
-                    if ((best >> 16) <= SP_TH_HIGH) newm = IT[best & 0xffffu];                  // (:1425)
-                }
+            for (int j = 0; j < c; ++j) {
+                const int k = CL[(size_t)i * lc + j];
+                if (!(s_claim[k] < i)) { newm = k; break; }
             }
-            if (lane == 0 && s_match[i] != newm) { s_match[i] = newm; s_changed = 1; }
+            if (s_match[i] != newm) { s_match[i] = newm; s_changed = 1; }
         }
+        if (nover)                                                          // lists that did not fit: the full search, a warp per point
+            for (int i = warp; i < nL; i += nwarps) {
+                if (CC[i] <= lc) continue;
+                const unsigned best = sp_scan(plan, q, P, F, W, QD, LO, i, lane, s_claim, nullptr, 0, nullptr);
+                const int newm = (best >> 16) <= SP_TH_HIGH ? F.IT[best & 0xffffu] : -1;      // (:1425)
+                if (lane == 0 && s_match[i] != newm) { s_match[i] = newm; s_changed = 1; }
+            }
         __syncthreads();
         const int changed = s_changed;
         ++rounds;
@@ -2231,11 +2335,11 @@ void search_projection_fill_query(void* dst, const float* Rcw, const float* tcw,
 }
 
 cudaError_t launch_search_projection(const OrbxPlan* d_plan, const OrbxPlan& hp, int nq, const void* d_queries, const float* K4,
-                                     const float* bounds, float mbf, float th, int check_ori, int cap, const float* world,
+                                     const float* bounds, float mbf, float th, int check_ori, int cap, int list_cap, const float* world,
                                      const uint8_t* mp_desc, const int* mp_obs, const int* last_octave, const float* last_angle,
                                      const float* kp, const uint8_t* desc, const int* kept_counts, const float* xy_un,
-                                     const int* cell_start, const int* cell_items, const float* u_right, int* match_out,
-                                     int* stats_out, cudaStream_t st) {
+                                     const int* cell_start, const int* cell_items, const float* u_right, uint16_t* cand_list,
+                                     int* cand_count, int* match_out, int* stats_out, cudaStream_t st) {
     SpParams P;
     P.fx = K4[0]; P.fy = K4[1]; P.cx = K4[2]; P.cy = K4[3];
     P.min_x = bounds[0]; P.max_x = bounds[1]; P.min_y = bounds[2]; P.max_y = bounds[3];
@@ -2246,15 +2350,23 @@ cudaError_t launch_search_projection(const OrbxPlan* d_plan, const OrbxPlan& hp,
     static size_t configured[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> config_lock(g_config_mutex);
-    if (smem > 48 * 1024 && smem > configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(search_projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured[dev & 63] = smem;
+    {
+        std::lock_guard<std::mutex> config_lock(g_config_mutex);
+        if (smem > 48 * 1024 && smem > configured[dev & 63]) {
+            cudaError_t e = cudaFuncSetAttribute(search_projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured[dev & 63] = smem;
+        }
     }
-    return launch_k(search_projection_kernel, dim3((unsigned)nq), dim3(1024), smem, st, d_plan, (const SpQuery*)d_queries, P, world,
-                    (const uint4*)mp_desc, mp_obs, last_octave, last_angle, kp, desc, kept_counts, xy_un, cell_start, cell_items,
-                    u_right, match_out, stats_out);
+    const long long warps = (long long)nq * cap;
+    cudaError_t e = launch_k(search_projection_list_kernel, dim3((unsigned)((warps + SP_LIST_WARPS - 1) / SP_LIST_WARPS)),
+                             dim3(SP_LIST_WARPS * 32), 0, st, d_plan, (const SpQuery*)d_queries, P, nq, list_cap, world,
+                             (const uint4*)mp_desc, mp_obs, last_octave, kp, desc, xy_un, cell_start, cell_items, u_right, cand_list,
+                             cand_count);
+    if (e != cudaSuccess) return e;
+    return launch_k(search_projection_kernel, dim3((unsigned)nq), dim3(1024), smem, st, d_plan, (const SpQuery*)d_queries, P, list_cap,
+                    world, (const uint4*)mp_desc, mp_obs, last_octave, last_angle, kp, desc, kept_counts, xy_un, cell_start, cell_items,
+                    u_right, (const uint16_t*)cand_list, (const int*)cand_count, match_out, stats_out);
 }
 
 size_t stereo_bucket_entries(const OrbxPlan& hp) { return (size_t)hp.kept_per_frame * ST_MAX_SPAN; }

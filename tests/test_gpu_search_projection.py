@@ -56,6 +56,33 @@ def test_monocular_batch_matches_oracle():
     gx.close()
 
 
+@pytest.mark.parametrize("list_cap", ["1", "2"])
+def test_full_search_path_of_the_resolve_kernel(list_cap, monkeypatch):
+    """Candidate lists that do not fit (forced here by shrinking them to 1 or 2 entries) fall back to the full search
+    inside the resolve kernel; the result is the same."""
+    monkeypatch.setenv("ORBX_SP_LIST_CAP", list_cap)
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["stereo_euroc"]
+    gx = ORBextractor(nf, sf, nl, it, mt, max_batch=2)
+    res = gx.extract_batch([fr.cluttered_scene(w, h, 51), fr.cluttered_scene(w, h, 52)])
+    K4, D = (458.654, 457.296, 367.215, 248.375), (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05)
+    grids = gx.undistort_grid(K4, D)
+    rng = np.random.default_rng(int(list_cap))
+    # few flipped bits and a wide window: many candidates at distance <= TH_HIGH per point
+    qs = []
+    for f in (0, 1):
+        xy, start, items, bounds = grids[f]
+        Tc = mc.pose(rng)
+        last = mc.make_last_frame(rng, xy, res[f][0]["octave"].astype(np.int32), res[f][0]["angle"].astype(np.float32), res[f][1], K4, Tc,
+                                  1500, nl, dup_frac=0.6, flip_bits=6)
+        qs.append(dict(cur_frame=f, Tcw_cur=Tc, Tcw_last=mc.pose(rng), **last))
+    out = gx.search_by_projection(qs, K4, 47.9, 0.11, 40.0, True)
+    for q, (n, m, rounds) in zip(qs, out):
+        f = q["cur_frame"]
+        n0, m0 = oracle_result(q, res[f][0], res[f][1], grids[f], K4, 47.9, 0.11, gx.GetScaleFactors(), 40.0, True, True, None)
+        assert n == n0 and np.array_equal(m, m0) and n > 300
+    gx.close()
+
+
 @pytest.mark.parametrize("motion", ["still", "forward", "backward"])
 def test_stereo_frame_with_device_uright_matches_oracle(motion):
     """The stereo Frame: mvuRight comes from orbx_stereo_match on the same handle and never leaves HBM."""
