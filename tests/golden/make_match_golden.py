@@ -1,0 +1,79 @@
+#!/usr/bin/env python3
+"""Regenerates tests/golden/match_golden.json: nmatches and the SHA-256 of the per-keypoint assignment that the
+REFERENCE'S OWN LINES of ORBmatcher::SearchByProjection(Frame&, const Frame&) (oracle/_ref/libstereoref.so, built from
+/root/reference/src/ORBmatcher.cc:1328-1470 + src/Frame.cc:327-380 by oracle/build_stereo_ref.sh) produce on the seeded
+scenarios below; the restatement (oracle/match_oracle.py) and the CUDA path are compared against these digests where the
+reference sources are absent.
+
+    python tests/golden/make_match_golden.py
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import frame_oracle, match_oracle, orb_oracle      # noqa: E402
+from orbslam2_with_quadrics_b200 import frames as fr           # noqa: E402
+from orbslam2_with_quadrics_b200 import match_cases as mc      # noqa: E402
+
+K_TUM1 = (517.306408, 516.469215, 318.643040, 255.313989)      # Examples/Monocular/TUM1.yaml:9-17
+D_TUM1 = (0.262383, -0.953104, -0.005358, 0.002628, 1.163314)
+# (seed, LastFrame.N, motion, stereo Frame (mvuRight set), th, bMono)
+CASES = [(1, 900, "still", False, 15.0, True), (2, 1500, "forward", True, 7.0, False), (3, 1500, "backward", True, 7.0, False),
+         (4, 1200, "still", True, 14.0, False), (5, 600, "forward", False, 30.0, True), (6, 40, "still", False, 15.0, True)]
+
+
+def current_frame():
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["mono_tum"]
+    ex = orb_oracle.ORBextractor(nf, sf, nl, it, mt)
+    res = ex(fr.cluttered_scene(w, h, 77))
+    xy, start, items, b = frame_oracle.undistort_and_grid(res.keypoints, K_TUM1, D_TUM1, w, h)
+    return dict(xy_un=xy, cur_octave=res.keypoints["octave"].astype(np.int32), cur_angle=res.keypoints["angle"].astype(np.float32),
+                desc=res.descriptors, cell_start=start, cell_items=items, bounds=b, sf=np.asarray(ex.GetScaleFactors(), np.float32),
+                nlevels=nl)
+
+
+def scenario(cf, seed, n_last, motion, stereo):
+    rng = np.random.default_rng(seed)
+    Tc = mc.pose(rng)
+    tz = {"still": 0.0, "forward": 0.6, "backward": -0.6}[motion]
+    Tl = mc.pose(rng, t=(0.0, 0.0, tz))
+    last = mc.make_last_frame(rng, cf["xy_un"], cf["cur_octave"], cf["cur_angle"], cf["desc"], K_TUM1, Tc, n_last, cf["nlevels"])
+    u_right = None
+    if stereo:
+        u_right = np.where(rng.random(len(cf["desc"])) < 0.6, cf["xy_un"][:, 0] - rng.uniform(2, 40, len(cf["desc"])), -1).astype(np.float32)
+    return dict(**last, Tcw_cur=Tc, Tcw_last=Tl, xy_un=cf["xy_un"], cur_octave=cf["cur_octave"], cur_angle=cf["cur_angle"],
+                desc=cf["desc"], u_right=u_right, cell_start=cf["cell_start"], cell_items=cf["cell_items"], bounds=cf["bounds"],
+                K4=K_TUM1, mbf=40.0, mb=0.08, sf=cf["sf"])
+
+
+def digest(sc, n, m):
+    ins = hashlib.sha256()
+    for k in ("world", "mp_desc", "mp_obs", "outlier", "last_octave", "last_angle", "Tcw_cur", "Tcw_last"):
+        ins.update(np.ascontiguousarray(sc[k]).tobytes())
+    return {"nmatches": int(n), "holders": int((m >= 0).sum()), "inputs_sha256": ins.hexdigest(),
+            "match_sha256": hashlib.sha256(np.ascontiguousarray(m, np.int32).tobytes()).hexdigest()}
+
+
+def key(case, check):
+    return "seed%d/n%d/%s/%s/th%g/%s/ori%d" % (case[0], case[1], case[2], "stereo" if case[3] else "mono-frame", case[4],
+                                              "bMono" if case[5] else "bStereo", int(check))
+
+
+if __name__ == "__main__":
+    from oracle import stereo_oracle
+    stereo_oracle.ref_build()
+    assert match_oracle.ref_available(), "the reference's own lines are needed to make the golden file"
+    cf = current_frame()
+    out = {}
+    for case in CASES:
+        sc = scenario(cf, *case[:4])
+        for check in (True, False):
+            n, m = match_oracle.ref_search_by_projection(th=case[4], mono=case[5], check_orientation=check, **sc)
+            out[key(case, check)] = digest(sc, n, m)
+            print(key(case, check), out[key(case, check)]["nmatches"], out[key(case, check)]["holders"])
+    json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "match_golden.json"), "w"), indent=1, sort_keys=True)

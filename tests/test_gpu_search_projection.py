@@ -190,3 +190,36 @@ def test_timing_report_beside_reference_lines():
     if os.path.isdir("gpurun_out"):
         json.dump(rep, open("gpurun_out/r01_search_projection.json", "w"), indent=1)
     gx.close()
+
+
+def test_against_golden_of_the_reference_lines():
+    """tests/golden/match_golden.json was produced by the reference's own lines on the ORACLE's extraction of the same
+    frame; the GPU extraction is bit-identical, so the whole chain extract -> undistort/grid -> search lands on the digests."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_match_golden", os.path.join(here, "golden", "make_match_golden.py"))
+    mmg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mmg)
+    gold = json.load(open(os.path.join(here, "golden", "match_golden.json")))
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["mono_tum"]
+    gx = ORBextractor(nf, sf, nl, it, mt)
+    kps, desc = gx(fr.cluttered_scene(w, h, 77))
+    (grid,) = gx.undistort_grid(mmg.K_TUM1, mmg.D_TUM1)
+    xy, start, items, bounds = grid
+    cf = dict(xy_un=xy, cur_octave=kps["octave"].astype(np.int32), cur_angle=kps["angle"].astype(np.float32), desc=desc,
+              cell_start=start, cell_items=items, bounds=bounds, sf=np.asarray(gx.GetScaleFactors(), np.float32), nlevels=nl)
+    done = 0
+    for case in mmg.CASES:
+        if case[3]:
+            continue                                   # stereo Frames take mvuRight from orbx_stereo_match (test above)
+        sc = mmg.scenario(cf, *case[:4])
+        q = dict(cur_frame=0, world=sc["world"], mp_desc=sc["mp_desc"], mp_obs=sc["mp_obs"], outlier=sc["outlier"],
+                 last_octave=sc["last_octave"], last_angle=sc["last_angle"], Tcw_cur=sc["Tcw_cur"], Tcw_last=sc["Tcw_last"])
+        for check in (True, False):
+            (n, m, _), = gx.search_by_projection([q], mmg.K_TUM1, sc["mbf"], sc["mb"], case[4], case[5], check)
+            assert mmg.digest(sc, n, m) == gold[mmg.key(case, check)]
+            done += 1
+    assert done == 6
+    gx.close()

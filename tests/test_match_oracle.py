@@ -2,15 +2,21 @@
 bMono) (reference src/ORBmatcher.cc:1328-1470, with Frame::GetFeaturesInArea src/Frame.cc:327-380, DescriptorDistance and
 ComputeThreeMaxima): the restatement (real cv2.gemm + float32 numpy) against the reference's own lines compiled against a
 stub, plus the stub's two gemm formulas against the real cv2.gemm."""
+import importlib.util
+import json
+import os
+
 import numpy as np
 import pytest
 
-from oracle import frame_oracle, match_oracle, orb_oracle, stereo_oracle
-from orbslam2_with_quadrics_b200 import frames as fr
-from orbslam2_with_quadrics_b200 import match_cases as mc
+from oracle import match_oracle, stereo_oracle
 
-K_TUM1 = (517.306408, 516.469215, 318.643040, 255.313989)
-D_TUM1 = (0.262383, -0.953104, -0.005358, 0.002628, 1.163314)
+HERE = os.path.dirname(os.path.abspath(__file__))
+spec = importlib.util.spec_from_file_location("make_match_golden", os.path.join(HERE, "golden", "make_match_golden.py"))
+mmg = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(mmg)
+GOLD = json.load(open(os.path.join(HERE, "golden", "match_golden.json")))
+CASES, scenario = mmg.CASES, mmg.scenario
 
 
 @pytest.fixture(scope="module")
@@ -26,31 +32,16 @@ def ref():
 
 @pytest.fixture(scope="module")
 def current_frame():
-    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["mono_tum"]
-    ex = orb_oracle.ORBextractor(nf, sf, nl, it, mt)
-    res = ex(fr.cluttered_scene(w, h, 77))
-    xy, start, items, b = frame_oracle.undistort_and_grid(res.keypoints, K_TUM1, D_TUM1, w, h)
-    return dict(xy_un=xy, cur_octave=res.keypoints["octave"].astype(np.int32), cur_angle=res.keypoints["angle"].astype(np.float32),
-                desc=res.descriptors, cell_start=start, cell_items=items, bounds=b, sf=np.asarray(ex.GetScaleFactors(), np.float32),
-                nlevels=nl)
+    return mmg.current_frame()
 
 
-def scenario(cf, seed, n_last, motion, stereo):
-    rng = np.random.default_rng(seed)
-    Tc = mc.pose(rng)
-    tz = {"still": 0.0, "forward": 0.6, "backward": -0.6}[motion]
-    Tl = mc.pose(rng, t=(0.0, 0.0, tz))
-    last = mc.make_last_frame(rng, cf["xy_un"], cf["cur_octave"], cf["cur_angle"], cf["desc"], K_TUM1, Tc, n_last, cf["nlevels"])
-    u_right = None
-    if stereo:
-        u_right = np.where(rng.random(len(cf["desc"])) < 0.6, cf["xy_un"][:, 0] - rng.uniform(2, 40, len(cf["desc"])), -1).astype(np.float32)
-    return dict(**last, Tcw_cur=Tc, Tcw_last=Tl, xy_un=cf["xy_un"], cur_octave=cf["cur_octave"], cur_angle=cf["cur_angle"],
-                desc=cf["desc"], u_right=u_right, cell_start=cf["cell_start"], cell_items=cf["cell_items"], bounds=cf["bounds"],
-                K4=K_TUM1, mbf=40.0, mb=0.08, sf=cf["sf"])
-
-
-CASES = [(1, 900, "still", False, 15.0, True), (2, 1500, "forward", True, 7.0, False), (3, 1500, "backward", True, 7.0, False),
-         (4, 1200, "still", True, 14.0, False), (5, 600, "forward", False, 30.0, True), (6, 40, "still", False, 15.0, True)]
+@pytest.mark.parametrize("case", CASES)
+def test_restatement_matches_golden_of_the_reference_lines(case, current_frame):
+    """Needs neither /root/reference nor oracle/_ref: the digests were made by the reference's own lines."""
+    sc = scenario(current_frame, *case[:4])
+    for check in (True, False):
+        n, m = match_oracle.search_by_projection(th=case[4], mono=case[5], check_orientation=check, **sc)
+        assert mmg.digest(sc, n, m) == GOLD[mmg.key(case, check)]
 
 
 @pytest.mark.parametrize("seed,n_last,motion,stereo,th,mono", CASES)
