@@ -22,6 +22,9 @@ sed -n '327p' "$F" | grep -q 'Frame::GetFeaturesInArea' || { echo "Frame.cc:327 
 sed -n '1328p' "$M" | grep -q 'int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame' || { echo "ORBmatcher.cc:1328 is not SearchByProjection(Frame&, const Frame&)"; exit 1; }
 sed -n '1470p' "$M" | grep -q '^}' || { echo "ORBmatcher.cc:1470 is not the end of SearchByProjection"; exit 1; }
 sed -n '1601p' "$M" | grep -q 'void ORBmatcher::ComputeThreeMaxima' || { echo "ORBmatcher.cc:1601 is not ComputeThreeMaxima"; exit 1; }
+sed -n '45p' "$M" | grep -q 'int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint\*> &vpMapPoints' || { echo "ORBmatcher.cc:45 is not SearchByProjection(Frame&, vpMapPoints)"; exit 1; }
+sed -n '129p' "$M" | grep -q '^}' || { echo "ORBmatcher.cc:129 is not the end of SearchByProjection(Frame&, vpMapPoints)"; exit 1; }
+sed -n '131p' "$M" | grep -q 'float ORBmatcher::RadiusByViewingCos' || { echo "ORBmatcher.cc:131 is not RadiusByViewingCos"; exit 1; }
 TMP=$(mktemp -d)
 trap 'rm -rf "$TMP"' EXIT
 {
@@ -37,6 +40,7 @@ trap 'rm -rf "$TMP"' EXIT
   sed -n '327,380p' "$F"
   sed -n '1328,1470p' "$M"
   sed -n '1601,1642p' "$M"
+  sed -n '45,137p' "$M"
   echo '}'
 } > "$TMP/stereo_ref_gen.cpp"
 mkdir -p "$OUT"

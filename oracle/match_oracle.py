@@ -217,3 +217,83 @@ def ref_search_by_projection(world, mp_desc, mp_obs, outlier, last_octave, last_
         p(arrs["cs"]), p(arrs["ci"]), p(arrs["b"]), p(arrs["k"]), C.c_float(mbf), C.c_float(mb), p(arrs["sf"]),
         C.c_int(len(arrs["sf"])), C.c_float(th), C.c_int(int(mono)), C.c_int(int(check_orientation)), p(out))
     return int(n), out
+
+
+# ============================================================================= SearchLocalPoints' matcher
+def radius_by_viewing_cos(view_cos):
+    """ORBmatcher::RadiusByViewingCos (src/ORBmatcher.cc:131-137): the float is compared with the double 0.998."""
+    return f32(2.5) if float(f32(view_cos)) > 0.998 else f32(4.0)
+
+
+def search_local_points(in_view, proj_x, proj_y, proj_xr, scale_level, view_cos, mp_desc, mp_obs, xy_un, cur_octave, desc, u_right,
+                        cur_obs, cell_start, cell_items, bounds, sf, th, nnratio=0.8):
+    """ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, th) (src/ORBmatcher.cc:45-129).
+    cur_obs[i2] < 0: F.mvpMapPoints[i2] is NULL, else the Observations() of the point it holds.
+    Returns (nmatches, new_match int32[nC]: index into vpMapPoints F.mvpMapPoints[i2] was set to, else -1)."""
+    nP, nC = len(mp_obs), len(desc)
+    desc64 = np.ascontiguousarray(desc).view(np.uint64).reshape(nC, 4) if nC else np.zeros((0, 4), np.uint64)
+    q64 = np.ascontiguousarray(mp_desc).view(np.uint64).reshape(nP, 4) if nP else np.zeros((0, 4), np.uint64)
+    holder_obs = np.asarray(cur_obs, np.int64).copy()          # Observations() of what each keypoint holds, -1 = NULL
+    new_match = np.full(nC, -1, np.int32)
+    b_factor = float(f32(th)) != 1.0
+    nmatches = 0
+    for i in range(nP):
+        if not in_view[i]:
+            continue
+        lvl = int(scale_level[i])
+        r = radius_by_viewing_cos(view_cos[i])
+        if b_factor:
+            r = f32(r * f32(th))
+        rad = f32(r * f32(sf[lvl]))
+        cands = features_in_area(proj_x[i], proj_y[i], rad, lvl - 1, lvl, xy_un, cur_octave, cell_start, cell_items, bounds)
+        if not cands:
+            continue
+        best = best2 = 256
+        lvl1 = lvl2 = -1
+        best_idx = -1
+        for i2 in cands:
+            if holder_obs[i2] > 0:
+                continue
+            if u_right is not None and u_right[i2] > 0:
+                if abs(f32(f32(proj_xr[i]) - f32(u_right[i2]))) > rad:
+                    continue
+            d = int(sum(bin(int(a ^ b)).count("1") for a, b in zip(q64[i], desc64[i2])))
+            if d < best:
+                best2, best = best, d
+                lvl2, lvl1 = lvl1, int(cur_octave[i2])
+                best_idx = i2
+            elif d < best2:
+                lvl2 = int(cur_octave[i2])
+                best2 = d
+        if best <= TH_HIGH:
+            if lvl1 == lvl2 and f32(best) > f32(f32(nnratio) * f32(best2)):
+                continue
+            holder_obs[best_idx] = mp_obs[i]
+            new_match[best_idx] = i
+            nmatches += 1
+    return nmatches, new_match
+
+
+def ref_search_local_points(in_view, proj_x, proj_y, proj_xr, scale_level, view_cos, mp_desc, mp_obs, xy_un, cur_octave, desc,
+                            u_right, cur_obs, cell_start, cell_items, bounds, sf, th, nnratio=0.8):
+    """Same call shape, executed by the reference's own lines (oracle/_ref/libstereoref.so)."""
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(os.path.join(_HERE, "_ref", "libstereoref.so"))
+        _ref.matchref_search_by_projection.restype = C.c_int
+    _ref.matchref_search_local_points.restype = C.c_int
+    nP, nC = len(mp_obs), len(desc)
+    kp = np.zeros((nC, 7), f32)
+    kp[:, 0:2] = np.asarray(xy_un, f32).reshape(nC, 2)
+    kp[:, 5] = np.asarray(cur_octave, np.int32).view(f32)
+    a = [np.ascontiguousarray(in_view, np.uint8), np.ascontiguousarray(proj_x, f32), np.ascontiguousarray(proj_y, f32),
+         np.ascontiguousarray(proj_xr, f32), np.ascontiguousarray(scale_level, np.int32), np.ascontiguousarray(view_cos, f32),
+         np.ascontiguousarray(mp_desc, np.uint8), np.ascontiguousarray(mp_obs, np.int32)]
+    b = [np.ascontiguousarray(desc, np.uint8), None if u_right is None else np.ascontiguousarray(u_right, f32),
+         np.ascontiguousarray(cur_obs, np.int32), np.ascontiguousarray(cell_start, np.int32), np.ascontiguousarray(cell_items, np.int32),
+         np.ascontiguousarray(bounds, f32), np.ascontiguousarray(sf, f32)]
+    out = np.full(nC, -1, np.int32)
+    p = lambda x: C.c_void_p(0) if x is None else C.c_void_p(x.ctypes.data)
+    n = _ref.matchref_search_local_points(C.c_int(nP), *[p(x) for x in a], C.c_int(nC), p(kp), p(b[0]), p(b[1]), p(b[2]), p(b[3]),
+                                          p(b[4]), p(b[5]), p(b[6]), C.c_int(len(b[6])), C.c_float(th), C.c_float(nnratio), p(out))
+    return int(n), out

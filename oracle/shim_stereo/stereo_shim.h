@@ -4,8 +4,9 @@
 // (/root/reference/src/Frame.cc:466-640), ORBmatcher::DescriptorDistance / TH_HIGH / TH_LOW
 // (/root/reference/src/ORBmatcher.cc:37-38, :1647-1663) and Frame::AssignFeaturesToGrid / PosInGrid /
 // UndistortKeyPoints / ComputeImageBounds (Frame.cc:230-245, :382-392, :404-434, :436-464), Frame::GetFeaturesInArea
-// (:327-380) and ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) / ComputeThreeMaxima
-// (ORBmatcher.cc:1328-1470, :1601-1642), taken from where they lie at
+// (:327-380), ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) / ComputeThreeMaxima
+// (ORBmatcher.cc:1328-1470, :1601-1642) and ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) /
+// RadiusByViewingCos (ORBmatcher.cc:45-129, :131-137), taken from where they lie at
 // build time, against this header: the handful of cv:: types those lines use (8U / 32F Mat views, convertTo, ones, scalar * Mat,
 // Mat - Mat, norm L1) and the members of Frame / ORBextractor / ORBmatcher they touch.  Written from scratch.
 #ifndef ORBX_ORACLE_STEREO_SHIM_H
@@ -188,9 +189,13 @@ namespace ORB_SLAM2 {
 
 class Frame;
 
-struct MapPoint {                     // the three accessors ORBmatcher.cc:1328-1470 calls
+struct MapPoint {                     // the accessors and tracking fields ORBmatcher.cc:45-129, :1328-1470 touch
     cv::Mat mWorldPos, mDescriptor;
     int nObs;
+    bool mbTrackInView, mbBad;        // include/MapPoint.h:92-97
+    float mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos;
+    int mnTrackScaleLevel;
+    bool isBad() { return mbBad; }
     cv::Mat GetWorldPos() { return mWorldPos; }
     cv::Mat GetDescriptor() { return mDescriptor; }
     int Observations() { return nObs; }
@@ -204,6 +209,8 @@ public:
     ORBmatcher(float nnratio = 0.6, bool checkOri = true);
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    int SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, const float th = 3);    // include/ORBmatcher.h
+    float RadiusByViewingCos(const float& viewCos);
     void ComputeThreeMaxima(vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
     float mfNNratio;
     bool mbCheckOrientation;

@@ -153,3 +153,59 @@ extern "C" int matchref_search_by_projection(int nL, const float* world, const u
     for (int i = 0; i < nC; ++i) cur_match[i] = C.mvpMapPoints[i] ? (int)(C.mvpMapPoints[i] - &mps[0]) : -1;
     return nmatches;
 }
+
+// ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, th) (src/ORBmatcher.cc:45-129, called by
+// Tracking::SearchLocalPoints, src/Tracking.cc:1184-1194, with ORBmatcher(0.8)), the reference's own lines.  Map point
+// side: the tracking fields Frame::isInFrustum left on each point (mbTrackInView && !isBad as `in_view`, mTrackProjX/Y/XR,
+// mnTrackScaleLevel, mTrackViewCos), descriptor, Observations().  Frame side as above plus the map points the frame
+// already holds: cur_obs[i2] < 0 = NULL, else that point's Observations().
+// new_match[i2] = index into vpMapPoints of the point F.mvpMapPoints[i2] was SET to by this call, else -1.
+extern "C" int matchref_search_local_points(int nP, const unsigned char* in_view, const float* proj_x, const float* proj_y,
+                                            const float* proj_xr, const int* scale_level, const float* view_cos,
+                                            const unsigned char* mp_desc, const int* mp_obs, int nC, const float* kp_un,
+                                            const unsigned char* desc, const float* u_right, const int* cur_obs,
+                                            const int* cell_start, const int* cell_items, const float* bounds, const float* sf,
+                                            int nlevels, float th, float nnratio, int* new_match) {
+    using namespace ORB_SLAM2;
+    Frame C;
+    std::vector<MapPoint> mps(nP), held(nC);
+    std::vector<MapPoint*> vp(nP);
+    for (int i = 0; i < nP; ++i) {
+        mps[i].mbTrackInView = in_view[i] != 0;
+        mps[i].mbBad = false;
+        mps[i].mTrackProjX = proj_x[i]; mps[i].mTrackProjY = proj_y[i]; mps[i].mTrackProjXR = proj_xr[i];
+        mps[i].mnTrackScaleLevel = scale_level[i];
+        mps[i].mTrackViewCos = view_cos[i];
+        mps[i].mDescriptor = cv::Mat(1, 32, CV_8U, (void*)(mp_desc + 32 * (size_t)i), 32);
+        mps[i].nObs = mp_obs[i];
+        vp[i] = &mps[i];
+    }
+    C.N = nC;
+    C.mvKeysUn.resize(nC);
+    C.mvpMapPoints.assign(nC, (MapPoint*)0);
+    for (int i = 0; i < nC; ++i) {
+        const float* q = kp_un + 7 * i;
+        C.mvKeysUn[i].pt.x = q[0]; C.mvKeysUn[i].pt.y = q[1]; C.mvKeysUn[i].angle = q[3];
+        memcpy(&C.mvKeysUn[i].octave, q + 5, 4);
+        if (cur_obs[i] >= 0) { held[i].nObs = cur_obs[i]; C.mvpMapPoints[i] = &held[i]; }
+    }
+    C.mvuRight.assign(nC, -1.f);
+    if (u_right) C.mvuRight.assign(u_right, u_right + nC);
+    C.mDescriptors = cv::Mat(nC, 32, CV_8U, (void*)desc, 32);
+    C.mvScaleFactors.assign(sf, sf + nlevels);
+    Frame::mnMinX = bounds[0]; Frame::mnMaxX = bounds[1]; Frame::mnMinY = bounds[2]; Frame::mnMaxY = bounds[3];
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(Frame::mnMaxX - Frame::mnMinX);
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(Frame::mnMaxY - Frame::mnMinY);
+    for (int gx = 0; gx < FRAME_GRID_COLS; ++gx)
+        for (int gy = 0; gy < FRAME_GRID_ROWS; ++gy) {
+            const int c = gx * FRAME_GRID_ROWS + gy;
+            C.mGrid[gx][gy].assign(cell_items + cell_start[c], cell_items + cell_start[c + 1]);
+        }
+    ORBmatcher matcher(nnratio, true);
+    const int nmatches = matcher.SearchByProjection(C, vp, th);
+    for (int i = 0; i < nC; ++i) {
+        MapPoint* p = C.mvpMapPoints[i];
+        new_match[i] = (p && p >= &mps[0] && p < &mps[0] + nP) ? (int)(p - &mps[0]) : -1;
+    }
+    return nmatches;
+}

@@ -78,3 +78,31 @@ def grid_from_points(xy_un, bounds):
     start[1:] = np.cumsum([len(c) for c in cells])
     items = np.array([i for c in cells for i in c], np.int32)
     return start, items
+
+
+def make_local_points(rng, xy_un, cur_octave, desc, n_points, nlevels, dup_frac=0.3, flip_bits=25, held_frac=0.35):
+    """Map points of the local map as Frame::isInFrustum leaves them for ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th)
+    (src/ORBmatcher.cc:45-129): projections near current keypoints (with duplicates that collide), predicted levels around the
+    keypoint's octave, viewing cosines on both sides of 0.998, descriptors = the keypoint's with flipped bits (near-duplicates
+    make the second-best ratio test bite), and the map points the frame already holds from the motion-model step."""
+    nC = len(desc)
+    tgt = rng.integers(0, nC, n_points)
+    ndup = int(dup_frac * n_points)
+    tgt[rng.integers(0, n_points, ndup)] = tgt[rng.integers(0, n_points, ndup)]
+    proj_x = (xy_un[tgt, 0] + rng.normal(0, 1.5, n_points)).astype(f32)
+    proj_y = (xy_un[tgt, 1] + rng.normal(0, 1.5, n_points)).astype(f32)
+    proj_xr = (proj_x - rng.uniform(1, 40, n_points)).astype(f32)
+    scale_level = np.clip(cur_octave[tgt] + rng.choice([0, 0, 0, 1, 1, -1], n_points), 0, nlevels - 1).astype(np.int32)
+    view_cos = np.where(rng.random(n_points) < 0.5, rng.uniform(0.9981, 1.0, n_points), rng.uniform(0.5, 0.998, n_points)).astype(f32)
+    mp_desc = desc[tgt].copy()
+    flips = rng.integers(0, 256, (n_points, flip_bits))
+    for k in range(flip_bits):
+        on = rng.random(n_points) < 0.6
+        mp_desc[np.arange(n_points)[on], flips[on, k] // 8] ^= (1 << (flips[on, k] % 8)).astype(np.uint8)
+    unrelated = rng.random(n_points) < 0.1
+    mp_desc[unrelated] = rng.integers(0, 256, (int(unrelated.sum()), 32), dtype=np.uint8)
+    mp_obs = rng.choice([0, 1, 2, 3, 7], n_points).astype(np.int32)
+    in_view = (rng.random(n_points) < 0.9).astype(np.uint8)
+    cur_obs = np.where(rng.random(nC) < held_frac, rng.choice([0, 1, 4], nC), -1).astype(np.int32)
+    return dict(in_view=in_view, proj_x=proj_x, proj_y=proj_y, proj_xr=proj_xr, scale_level=scale_level, view_cos=view_cos,
+                mp_desc=mp_desc, mp_obs=mp_obs, cur_obs=cur_obs)

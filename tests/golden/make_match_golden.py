@@ -51,6 +51,33 @@ def scenario(cf, seed, n_last, motion, stereo):
                 K4=K_TUM1, mbf=40.0, mb=0.08, sf=cf["sf"])
 
 
+# SearchLocalPoints' matcher: (seed, vpMapPoints.size(), stereo Frame, th)  -- th = 1 / 3 (RGB-D) / 5 (after relocalisation),
+# src/Tracking.cc:1185-1191
+LOCAL_CASES = [(1, 1200, False, 1.0), (2, 2000, True, 3.0), (3, 800, False, 5.0), (4, 1500, True, 1.0), (5, 30, False, 3.0)]
+
+
+def local_scenario(cf, seed, n_points, stereo):
+    rng = np.random.default_rng(1000 + seed)
+    lp = mc.make_local_points(rng, cf["xy_un"], cf["cur_octave"], cf["desc"], n_points, cf["nlevels"])
+    u_right = None
+    if stereo:
+        u_right = np.where(rng.random(len(cf["desc"])) < 0.6, cf["xy_un"][:, 0] - rng.uniform(2, 40, len(cf["desc"])), -1).astype(np.float32)
+    return dict(**lp, xy_un=cf["xy_un"], cur_octave=cf["cur_octave"], desc=cf["desc"], u_right=u_right, cell_start=cf["cell_start"],
+                cell_items=cf["cell_items"], bounds=cf["bounds"], sf=cf["sf"])
+
+
+def local_digest(sc, n, m):
+    ins = hashlib.sha256()
+    for k in ("in_view", "proj_x", "proj_y", "proj_xr", "scale_level", "view_cos", "mp_desc", "mp_obs", "cur_obs"):
+        ins.update(np.ascontiguousarray(sc[k]).tobytes())
+    return {"nmatches": int(n), "set": int((m >= 0).sum()), "inputs_sha256": ins.hexdigest(),
+            "match_sha256": hashlib.sha256(np.ascontiguousarray(m, np.int32).tobytes()).hexdigest()}
+
+
+def local_key(case):
+    return "local/seed%d/n%d/%s/th%g" % (case[0], case[1], "stereo" if case[2] else "mono-frame", case[3])
+
+
 def digest(sc, n, m):
     ins = hashlib.sha256()
     for k in ("world", "mp_desc", "mp_obs", "outlier", "last_octave", "last_angle", "Tcw_cur", "Tcw_last"):
@@ -76,4 +103,9 @@ if __name__ == "__main__":
             n, m = match_oracle.ref_search_by_projection(th=case[4], mono=case[5], check_orientation=check, **sc)
             out[key(case, check)] = digest(sc, n, m)
             print(key(case, check), out[key(case, check)]["nmatches"], out[key(case, check)]["holders"])
+    for case in LOCAL_CASES:
+        sc = local_scenario(cf, *case[:3])
+        n, m = match_oracle.ref_search_local_points(th=case[3], **sc)
+        out[local_key(case)] = local_digest(sc, n, m)
+        print(local_key(case), n, int((m >= 0).sum()))
     json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "match_golden.json"), "w"), indent=1, sort_keys=True)

@@ -83,3 +83,26 @@ def test_shim_gemm_formulas_match_cv2():
         b = [f32(-(np.float64(R[0, r]) * np.float64(t[0, 0]) + np.float64(R[1, r]) * np.float64(t[1, 0])
                    + np.float64(R[2, r]) * np.float64(t[2, 0]))) for r in range(3)]
         assert np.array_equal(np.array(b, f32).reshape(3, 1), y)
+
+
+# ----------------------------------------------------------------------------- SearchLocalPoints' matcher (:45-129)
+@pytest.mark.parametrize("case", mmg.LOCAL_CASES)
+def test_local_points_restatement_matches_reference_lines_and_golden(case, current_frame):
+    sc = mmg.local_scenario(current_frame, *case[:3])
+    n1, m1 = match_oracle.search_local_points(th=case[3], **sc)
+    assert mmg.local_digest(sc, n1, m1) == GOLD[mmg.local_key(case)]
+    if match_oracle.ref_available():
+        n2, m2 = match_oracle.ref_search_local_points(th=case[3], **sc)
+        assert n1 == n2 and np.array_equal(m1, m2)
+    assert n1 >= int((m1 >= 0).sum()) > 0.2 * case[1]
+
+
+def test_local_points_ratio_test_and_held_points_are_exercised(current_frame):
+    sc = mmg.local_scenario(current_frame, 2, 2000, True)
+    n, m = match_oracle.search_local_points(th=3.0, **sc)
+    n_no_ratio, _ = match_oracle.search_local_points(th=3.0, nnratio=0.0, **sc)      # best > 0 * best2 rejects every same-level pair
+    n_never, _ = match_oracle.search_local_points(th=3.0, nnratio=1e9, **sc)        # never rejects
+    assert n_no_ratio < n < n_never
+    assert not np.any((m >= 0) & (sc["cur_obs"] > 0))           # keypoints holding an observed point are never taken (:96-98)
+    assert np.any((m >= 0) & (sc["cur_obs"] == 0))              # ... those holding an unobserved one are
+    assert match_oracle.radius_by_viewing_cos(np.float32(0.998)) == 2.5 and match_oracle.radius_by_viewing_cos(0.99799) == 4.0
