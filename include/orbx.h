@@ -195,6 +195,29 @@ ORBX_API int orbx_search_by_projection_device(orbx_handle* h, int nqueries, cons
 ORBX_API int orbx_search_by_projection_fetch(orbx_handle* h, int nqueries, const orbx_projection_query* queries,
                                              orbx_projection_result* results);
 
+/* ---- ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, th) (reference src/ORBmatcher.cc:45-129
+ * with RadiusByViewingCos :131-137): the matcher of Tracking::SearchLocalPoints (src/Tracking.cc:1184-1194, ORBmatcher(0.8),
+ * th = 1 / 3 for RGB-D / 5 after a relocalisation), every tracked frame.  The map points carry the tracking fields
+ * Frame::isInFrustum (src/Frame.cc:255-325) left on them; the frame side is the handle's device-resident state as for
+ * orbx_search_by_projection.  Unlike there, the frame already holds map points: cur_obs names them.
+ * Result (orbx_projection_result): match[i2] = index into vpMapPoints of the point F.mvpMapPoints[i2] was SET to by
+ * this call, -1 = left as it was; nmatches = the function's return value. */
+typedef struct orbx_local_points_query {
+    int cur_frame;             /* frame of this handle's last extract */
+    int n_points;              /* vpMapPoints.size() */
+    const uint8_t* in_view;    /* n: pMP->mbTrackInView && !pMP->isBad(); NULL = all */
+    const float* proj_xy_xr;   /* n x 3: mTrackProjX, mTrackProjY, mTrackProjXR */
+    const int32_t* scale_level;/* n: mnTrackScaleLevel */
+    const float* view_cos;     /* n: mTrackViewCos */
+    const uint8_t* mp_desc;    /* n x 32: pMP->GetDescriptor() */
+    const int32_t* mp_obs;     /* n: pMP->Observations() */
+    const int32_t* cur_obs;    /* F.N: < 0 where F.mvpMapPoints[i2] is NULL, else its Observations(); NULL = all NULL */
+} orbx_local_points_query;
+ORBX_API int orbx_search_local_points(orbx_handle* h, int nqueries, const orbx_local_points_query* queries, float th, float nnratio,
+                                      int use_stereo, orbx_projection_result* results);
+ORBX_API int orbx_search_local_points_device(orbx_handle* h, int nqueries, const orbx_local_points_query* queries, float th,
+                                             float nnratio, int use_stereo);
+
 /* Pinned host buffers callers may fill with frames so that H2D copies are asynchronous DMA. */
 ORBX_API int orbx_alloc_host(size_t bytes, void** out);
 ORBX_API int orbx_free_host(void* p);

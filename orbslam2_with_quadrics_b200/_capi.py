@@ -25,6 +25,7 @@ SYMBOLS = [
     "orbx_stereo_match", "orbx_stereo_match_device", "orbx_stereo_fetch",
     "orbx_extract_batch_color", "orbx_extract_device_color", "orbx_undistort_grid", "orbx_fast_stats",
     "orbx_search_by_projection", "orbx_search_by_projection_device", "orbx_search_by_projection_fetch",
+    "orbx_search_local_points", "orbx_search_local_points_device",
 ]
 GRAY8, BGR8, RGB8, BGRA8, RGBA8 = range(5)
 
@@ -56,6 +57,12 @@ class OrbxProjectionQuery(C.Structure):
     _fields_ = [("cur_frame", C.c_int), ("n_last", C.c_int), ("world_pos", C.c_void_p), ("mp_desc", C.c_void_p),
                 ("mp_obs", C.c_void_p), ("outlier", C.c_void_p), ("octave", C.c_void_p), ("angle", C.c_void_p),
                 ("Tcw_cur", C.c_float * 16), ("Tcw_last", C.c_float * 16)]
+
+
+class OrbxLocalPointsQuery(C.Structure):
+    _fields_ = [("cur_frame", C.c_int), ("n_points", C.c_int), ("in_view", C.c_void_p), ("proj_xy_xr", C.c_void_p),
+                ("scale_level", C.c_void_p), ("view_cos", C.c_void_p), ("mp_desc", C.c_void_p), ("mp_obs", C.c_void_p),
+                ("cur_obs", C.c_void_p)]
 
 
 class OrbxProjectionResult(C.Structure):
@@ -124,6 +131,8 @@ def lib():
                                             C.POINTER(OrbxProjectionResult)]
     L.orbx_search_by_projection_device.argtypes = [vp, i, C.POINTER(OrbxProjectionQuery), C.POINTER(f), f, f, f, i, i, i]
     L.orbx_search_by_projection_fetch.argtypes = [vp, i, C.POINTER(OrbxProjectionQuery), C.POINTER(OrbxProjectionResult)]
+    L.orbx_search_local_points.argtypes = [vp, i, C.POINTER(OrbxLocalPointsQuery), f, f, i, C.POINTER(OrbxProjectionResult)]
+    L.orbx_search_local_points_device.argtypes = [vp, i, C.POINTER(OrbxLocalPointsQuery), f, f, i]
     L.orbx_undistort_grid.argtypes = [vp, i, C.POINTER(i), C.POINTER(C.c_float), C.POINTER(C.c_float), i, C.POINTER(OrbxGridResult)]
     _lib = L
     return L

@@ -1136,113 +1136,142 @@ int orbx_undistort_grid(orbx_handle* h, int nframes, const int* frames, const fl
     return ORBX_OK;
 }
 
-// ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono), src/ORBmatcher.cc:1328-1470.
-static int sp_enqueue(orbx_handle* h, int nq, const orbx_projection_query* q, const float* K4, float mbf, float mb, float th,
-                      int mono, int check_orientation, int use_stereo, int* cap_out) {
-    if (!h || !q || !K4 || nq < 1 || nq > h->cfg.max_batch || !h->have_plan) return ORBX_ERR_BAD_ARGS;
+// ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono), src/ORBmatcher.cc:1328-1470, and
+// ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th), src/ORBmatcher.cc:45-129: one staging / launch path.
+namespace {
+struct SpHostQuery {
+    int cur_frame, n;
+    const float* w3;           // n x 3: world position | (mTrackProjX, mTrackProjY, mTrackProjXR)
+    const uint8_t* desc;       // n x 32
+    const int32_t* obs;        // Observations(); < 0: no map point
+    const uint8_t* flag;       // mvbOutlier (skip where set) | in-view flag (skip where clear); may be NULL
+    const int32_t* oct;        // keypoint octave | mnTrackScaleLevel
+    const float* ang;          // keypoint angle | mTrackViewCos
+    const int32_t* cur_obs;    // local variant: what the frame's keypoints hold; NULL = nothing
+    const float *Tc, *Tl;      // LastFrame variant: the two poses
+};
+
+int sp_enqueue(orbx_handle* h, int local, int nq, const SpHostQuery* q, const float* K4, float mbf, float mb, float th, float nnratio,
+               int mono, int check_orientation, int use_stereo) {
+    if (!h || !q || nq < 1 || nq > h->cfg.max_batch || !h->have_plan) return ORBX_ERR_BAD_ARGS;
     if (!h->d_un_xy) return ORBX_ERR_BAD_ARGS;                      // orbx_undistort_grid has to run first (mvKeysUn, mGrid)
     if (use_stereo && !h->d_st_u) return ORBX_ERR_BAD_ARGS;          // mvuRight comes from orbx_stereo_match on this handle
     const OrbxPlan& P = h->plan;
-    if (P.kept_per_frame > 65535) return ORBX_ERR_BAD_ARGS;
+    const size_t kpf = (size_t)P.kept_per_frame;
+    if (kpf > 65535) return ORBX_ERR_BAD_ARGS;
     int cap = 1;
     for (int i = 0; i < nq; ++i) {
-        if (q[i].cur_frame < 0 || q[i].cur_frame >= h->last_n || q[i].n_last < 0) return ORBX_ERR_BAD_ARGS;
-        if (q[i].n_last && (!q[i].world_pos || !q[i].mp_desc || !q[i].mp_obs || !q[i].octave || !q[i].angle)) return ORBX_ERR_BAD_ARGS;
-        if (q[i].n_last > cap) cap = q[i].n_last;
+        if (q[i].cur_frame < 0 || q[i].cur_frame >= h->last_n || q[i].n < 0) return ORBX_ERR_BAD_ARGS;
+        if (q[i].n && (!q[i].w3 || !q[i].desc || !q[i].obs || !q[i].oct || !q[i].ang)) return ORBX_ERR_BAD_ARGS;
+        if (q[i].n > cap) cap = q[i].n;
+        for (int k = 0; k < q[i].n; ++k)
+            if (q[i].oct[k] < 0 || q[i].oct[k] >= P.nlevels) return ORBX_ERR_BAD_ARGS;
     }
     cap = (cap + 3) & ~3;
     if ((size_t)(cap + P.kept_per_frame) * sizeof(int) > 200 * 1024) return ORBX_ERR_BAD_ARGS;
     CK(h, cudaSetDevice(h->cfg.device));
     const size_t qbytes = (orbx::search_projection_query_bytes() + 15) & ~(size_t)15;
-    // staging layout: [queries][mp_desc nq*cap*32][world nq*cap*3 f32][obs nq*cap][octave nq*cap][angle nq*cap]; device only,
-    // behind it: [candidate counts nq*cap][candidate lists nq*cap*list_cap u16]
     int list_cap = 32;                                               // entries a point's candidate list may hold (test knob: small
     if (const char* e = getenv("ORBX_SP_LIST_CAP")) {                // values force the full-search path of the resolve kernel)
         const int v = atoi(e);
         if (v >= 1 && v <= 32) list_cap = v;
     }
+    // staging layout: [queries][mp_desc nq*cap*32][w3 nq*cap*3 f32][obs nq*cap][octave nq*cap][angle nq*cap][cur_obs nq*kpf];
+    // device only, behind it: [candidate counts nq*cap][candidate lists nq*cap*32 u32]
     const size_t o_desc = (size_t)nq * qbytes, o_world = o_desc + (size_t)nq * cap * 32, o_obs = o_world + (size_t)nq * cap * 12,
-                 o_oct = o_obs + (size_t)nq * cap * 4, o_ang = o_oct + (size_t)nq * cap * 4, staged = o_ang + (size_t)nq * cap * 4,
-                 o_cnt = (staged + 15) & ~(size_t)15, o_list = o_cnt + (size_t)nq * cap * 4,
-                 total = o_list + (size_t)nq * cap * 32 * 2;
+                 o_oct = o_obs + (size_t)nq * cap * 4, o_ang = o_oct + (size_t)nq * cap * 4, o_cur = o_ang + (size_t)nq * cap * 4,
+                 staged = o_cur + (local ? (size_t)nq * kpf * 4 : 0), o_cnt = (staged + 15) & ~(size_t)15,
+                 o_list = o_cnt + (size_t)nq * cap * 4, total = o_list + (size_t)nq * cap * 32 * 4;
     cudaStream_t st = h->stream;
     CK(h, cudaStreamSynchronize(st));                                // the staging of a previous call is free
     if (total > h->sp_bytes) {
         cudaFree(h->d_sp); cudaFreeHost(h->h_sp); h->d_sp = h->h_sp = 0; h->sp_bytes = 0;
         CK(h, cudaMalloc(&h->d_sp, total));
-        CK(h, cudaMallocHost(&h->h_sp, staged));
+        CK(h, cudaMallocHost(&h->h_sp, total));
         h->sp_bytes = total;
     }
-    const size_t out_ints = (size_t)h->cfg.max_batch * ((size_t)P.kept_per_frame + 2);
+    const size_t out_ints = (size_t)h->cfg.max_batch * (kpf + 2);
     if (!h->d_sp_out) {
         CK(h, cudaMalloc(&h->d_sp_out, out_ints * 4));
         CK(h, cudaMallocHost(&h->h_sp_out, out_ints * 4));
         h->sp_out_ints = out_ints;
     }
     for (int i = 0; i < nq; ++i) {
-        const orbx_projection_query& Q = q[i];
-        // twc = -Rcw.t() * tcw (general gemm path: double products and sum), tlc = Rlw * twc + tlw (the 3x3 path: float
-        // products and sums, "+ C" in double), bForward / bBackward (:1337-1349)
-        const float* Tc = Q.Tcw_cur;
-        const float* Tl = Q.Tcw_last;
-        float twc[3];
-        for (int r = 0; r < 3; ++r) {
-            double s = 0;
-            for (int k = 0; k < 3; ++k) s += (double)Tc[4 * k + r] * (double)Tc[4 * k + 3];
-            twc[r] = (float)(s * -1.0);
+        const SpHostQuery& Q = q[i];
+        int fwd = 0, bwd = 0;
+        float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
+        if (!local) {
+            // twc = -Rcw.t() * tcw (general gemm path: double products and sum), tlc = Rlw * twc + tlw (the 3x3 path: float
+            // products and sums, "+ C" in double), bForward / bBackward (:1337-1349)
+            const float* Tc = Q.Tc;
+            const float* Tl = Q.Tl;
+            float twc[3];
+            for (int r = 0; r < 3; ++r) {
+                double s = 0;
+                for (int k = 0; k < 3; ++k) s += (double)Tc[4 * k + r] * (double)Tc[4 * k + 3];
+                twc[r] = (float)(s * -1.0);
+            }
+            volatile float p0 = Tl[8] * twc[0], p1 = Tl[9] * twc[1], p2 = Tl[10] * twc[2];     // volatile: no contraction
+            volatile float t0 = p0 + p1;
+            t0 = t0 + p2;
+            const float tlcz = (float)((double)t0 + (double)Tl[11]);
+            fwd = tlcz > mb && !mono;
+            bwd = -tlcz > mb && !mono;
+            const float Rc[9] = {Tc[0], Tc[1], Tc[2], Tc[4], Tc[5], Tc[6], Tc[8], Tc[9], Tc[10]};
+            memcpy(R, Rc, sizeof R);
+            t[0] = Tc[3]; t[1] = Tc[7]; t[2] = Tc[11];
         }
-        volatile float p0 = Tl[8] * twc[0], p1 = Tl[9] * twc[1], p2 = Tl[10] * twc[2];     // volatile: no contraction
-        volatile float t0 = p0 + p1;
-        t0 = t0 + p2;
-        const float tlcz = (float)((double)t0 + (double)Tl[11]);
-        const int fwd = tlcz > mb && !mono, bwd = -tlcz > mb && !mono;
-        const float R[9] = {Tc[0], Tc[1], Tc[2], Tc[4], Tc[5], Tc[6], Tc[8], Tc[9], Tc[10]}, t[3] = {Tc[3], Tc[7], Tc[11]};
-        orbx::search_projection_fill_query(h->h_sp + (size_t)i * qbytes, R, t, Q.n_last, Q.cur_frame, fwd, bwd);
-        const size_t n = (size_t)Q.n_last, b = (size_t)i * cap;
+        orbx::search_projection_fill_query(h->h_sp + (size_t)i * qbytes, R, t, Q.n, Q.cur_frame, fwd, bwd);
+        const size_t n = (size_t)Q.n, b = (size_t)i * cap;
         if (n) {
-            memcpy(h->h_sp + o_desc + b * 32, Q.mp_desc, n * 32);
-            memcpy(h->h_sp + o_world + b * 12, Q.world_pos, n * 12);
+            memcpy(h->h_sp + o_desc + b * 32, Q.desc, n * 32);
+            memcpy(h->h_sp + o_world + b * 12, Q.w3, n * 12);
             int* obs = reinterpret_cast<int*>(h->h_sp + o_obs) + b;
-            for (size_t k = 0; k < n; ++k) obs[k] = (Q.outlier && Q.outlier[k]) ? -1 : Q.mp_obs[k];     // (:1356-1360)
-            memcpy(h->h_sp + o_oct + b * 4, Q.octave, n * 4);
-            memcpy(h->h_sp + o_ang + b * 4, Q.angle, n * 4);
+            if (local)                                               // mbTrackInView && !isBad (:54-58)
+                for (size_t k = 0; k < n; ++k) obs[k] = (Q.flag && !Q.flag[k]) ? -1 : (Q.obs[k] < 0 ? 0 : Q.obs[k]);
+            else                                                     // pMP && !mvbOutlier (:1356-1360)
+                for (size_t k = 0; k < n; ++k) obs[k] = (Q.flag && Q.flag[k]) ? -1 : Q.obs[k];
+            memcpy(h->h_sp + o_oct + b * 4, Q.oct, n * 4);
+            memcpy(h->h_sp + o_ang + b * 4, Q.ang, n * 4);
+        }
+        if (local) {
+            int* co = reinterpret_cast<int*>(h->h_sp + o_cur) + (size_t)i * kpf;
+            if (Q.cur_obs) {
+                int N = 0;                                           // CurrentFrame.N as of the last fetch of the counters
+                for (int l = 0; l < P.nlevels; ++l) N += h->h_kept_counts()[Q.cur_frame * P.nlevels + l];
+                memcpy(co, Q.cur_obs, (size_t)N * 4);
+                for (size_t k = (size_t)N; k < kpf; ++k) co[k] = -1;
+            } else {
+                for (size_t k = 0; k < kpf; ++k) co[k] = -1;
+            }
         }
     }
-    for (int i = 0; i < nq; ++i)
-        for (int k = 0; k < q[i].n_last; ++k) {
-            const int o = q[i].octave[k];
-            if (o < 0 || o >= P.nlevels) return ORBX_ERR_BAD_ARGS;
-        }
+    const float K1[4] = {1.f, 1.f, 0.f, 0.f};
     CK(h, cudaMemcpyAsync(h->d_sp, h->h_sp, staged, cudaMemcpyHostToDevice, st));
-    CK(h, orbx::launch_search_projection(h->d_plan, P, nq, h->d_sp, K4, h->un_bounds, mbf, th, check_orientation, cap, list_cap,
-                                         reinterpret_cast<const float*>(h->d_sp + o_world), h->d_sp + o_desc,
+    CK(h, orbx::launch_search_projection(h->d_plan, P, local, nq, h->d_sp, K4 ? K4 : K1, h->un_bounds, mbf, th, nnratio, check_orientation,
+                                         cap, list_cap, reinterpret_cast<const float*>(h->d_sp + o_world), h->d_sp + o_desc,
                                          reinterpret_cast<const int*>(h->d_sp + o_obs), reinterpret_cast<const int*>(h->d_sp + o_oct),
                                          reinterpret_cast<const float*>(h->d_sp + o_ang), h->d_out_kp, h->d_out_desc, h->d_kept_counts(),
                                          h->d_un_xy, h->d_un_start, h->d_un_items, use_stereo ? h->d_st_u : nullptr,
-                                         reinterpret_cast<uint16_t*>(h->d_sp + o_list), reinterpret_cast<int*>(h->d_sp + o_cnt), h->d_sp_out,
+                                         local ? reinterpret_cast<const int*>(h->d_sp + o_cur) : nullptr,
+                                         reinterpret_cast<uint32_t*>(h->d_sp + o_list), reinterpret_cast<int*>(h->d_sp + o_cnt), h->d_sp_out,
                                          h->d_sp_out + (size_t)h->cfg.max_batch * P.kept_per_frame, st));
     h->launches += 2;
-    if (cap_out) *cap_out = cap;
     return ORBX_OK;
 }
 
-int orbx_search_by_projection_device(orbx_handle* h, int nqueries, const orbx_projection_query* queries, const float* K4, float mbf,
-                                     float mb, float th, int mono, int check_orientation, int use_stereo) {
-    return sp_enqueue(h, nqueries, queries, K4, mbf, mb, th, mono, check_orientation, use_stereo, nullptr);
-}
-
-int orbx_search_by_projection_fetch(orbx_handle* h, int nqueries, const orbx_projection_query* queries, orbx_projection_result* results) {
-    if (!h || !queries || !results || nqueries < 1 || nqueries > h->cfg.max_batch || !h->d_sp_out) return ORBX_ERR_BAD_ARGS;
+int sp_fetch(orbx_handle* h, int nq, const int* frames, orbx_projection_result* results) {
+    if (!h || !results || nq < 1 || nq > h->cfg.max_batch || !h->d_sp_out) return ORBX_ERR_BAD_ARGS;
     CK(h, cudaSetDevice(h->cfg.device));
     const OrbxPlan& P = h->plan;
     const size_t kpf = (size_t)P.kept_per_frame, B = (size_t)h->cfg.max_batch;
     cudaStream_t st = h->stream;
-    CK(h, cudaMemcpyAsync(h->h_sp_out, h->d_sp_out, (size_t)nqueries * kpf * 4, cudaMemcpyDeviceToHost, st));
-    CK(h, cudaMemcpyAsync(h->h_sp_out + B * kpf, h->d_sp_out + B * kpf, (size_t)nqueries * 2 * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h->h_sp_out, h->d_sp_out, (size_t)nq * kpf * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h->h_sp_out + B * kpf, h->d_sp_out + B * kpf, (size_t)nq * 2 * 4, cudaMemcpyDeviceToHost, st));
     CK(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int) * h->counters_count(), cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
-    for (int i = 0; i < nqueries; ++i) {
-        const int f = queries[i].cur_frame;
+    for (int i = 0; i < nq; ++i) {
+        const int f = frames[i];
         if (f < 0 || f >= h->last_n) return ORBX_ERR_BAD_ARGS;
         int total = 0;
         for (int l = 0; l < P.nlevels; ++l) total += h->h_kept_counts()[f * P.nlevels + l];
@@ -1254,12 +1283,69 @@ int orbx_search_by_projection_fetch(orbx_handle* h, int nqueries, const orbx_pro
     return ORBX_OK;
 }
 
+int sp_convert(int nq, const orbx_projection_query* q, std::vector<SpHostQuery>& out) {
+    if (!q || nq < 1) return ORBX_ERR_BAD_ARGS;
+    out.resize(nq);
+    for (int i = 0; i < nq; ++i) {
+        SpHostQuery& o = out[i];
+        o.cur_frame = q[i].cur_frame; o.n = q[i].n_last; o.w3 = q[i].world_pos; o.desc = q[i].mp_desc; o.obs = q[i].mp_obs;
+        o.flag = q[i].outlier; o.oct = q[i].octave; o.ang = q[i].angle; o.cur_obs = nullptr; o.Tc = q[i].Tcw_cur; o.Tl = q[i].Tcw_last;
+    }
+    return ORBX_OK;
+}
+
+int lp_convert(int nq, const orbx_local_points_query* q, std::vector<SpHostQuery>& out) {
+    if (!q || nq < 1) return ORBX_ERR_BAD_ARGS;
+    out.resize(nq);
+    for (int i = 0; i < nq; ++i) {
+        SpHostQuery& o = out[i];
+        o.cur_frame = q[i].cur_frame; o.n = q[i].n_points; o.w3 = q[i].proj_xy_xr; o.desc = q[i].mp_desc; o.obs = q[i].mp_obs;
+        o.flag = q[i].in_view; o.oct = q[i].scale_level; o.ang = q[i].view_cos; o.cur_obs = q[i].cur_obs; o.Tc = o.Tl = nullptr;
+    }
+    return ORBX_OK;
+}
+}  // namespace
+
+int orbx_search_by_projection_device(orbx_handle* h, int nqueries, const orbx_projection_query* queries, const float* K4, float mbf,
+                                     float mb, float th, int mono, int check_orientation, int use_stereo) {
+    if (!K4) return ORBX_ERR_BAD_ARGS;
+    std::vector<SpHostQuery> q;
+    const int rc = sp_convert(nqueries, queries, q);
+    if (rc != ORBX_OK) return rc;
+    return sp_enqueue(h, 0, nqueries, q.data(), K4, mbf, mb, th, 0.f, mono, check_orientation, use_stereo);
+}
+
+int orbx_search_by_projection_fetch(orbx_handle* h, int nqueries, const orbx_projection_query* queries, orbx_projection_result* results) {
+    if (!queries || nqueries < 1) return ORBX_ERR_BAD_ARGS;
+    std::vector<int> frames(nqueries);
+    for (int i = 0; i < nqueries; ++i) frames[i] = queries[i].cur_frame;
+    return sp_fetch(h, nqueries, frames.data(), results);
+}
+
 int orbx_search_by_projection(orbx_handle* h, int nqueries, const orbx_projection_query* queries, const float* K4, float mbf, float mb,
                               float th, int mono, int check_orientation, int use_stereo, orbx_projection_result* results) {
     if (!results) return ORBX_ERR_BAD_ARGS;
-    const int rc = sp_enqueue(h, nqueries, queries, K4, mbf, mb, th, mono, check_orientation, use_stereo, nullptr);
+    const int rc = orbx_search_by_projection_device(h, nqueries, queries, K4, mbf, mb, th, mono, check_orientation, use_stereo);
     if (rc != ORBX_OK) return rc;
     return orbx_search_by_projection_fetch(h, nqueries, queries, results);
+}
+
+int orbx_search_local_points_device(orbx_handle* h, int nqueries, const orbx_local_points_query* queries, float th, float nnratio,
+                                    int use_stereo) {
+    std::vector<SpHostQuery> q;
+    const int rc = lp_convert(nqueries, queries, q);
+    if (rc != ORBX_OK) return rc;
+    return sp_enqueue(h, 1, nqueries, q.data(), nullptr, 0.f, 0.f, th, nnratio, 1, 0, use_stereo);
+}
+
+int orbx_search_local_points(orbx_handle* h, int nqueries, const orbx_local_points_query* queries, float th, float nnratio,
+                             int use_stereo, orbx_projection_result* results) {
+    if (!results) return ORBX_ERR_BAD_ARGS;
+    const int rc = orbx_search_local_points_device(h, nqueries, queries, th, nnratio, use_stereo);
+    if (rc != ORBX_OK) return rc;
+    std::vector<int> frames(nqueries);
+    for (int i = 0; i < nqueries; ++i) frames[i] = queries[i].cur_frame;
+    return sp_fetch(h, nqueries, frames.data(), results);
 }
 
 int orbx_fast_stats(orbx_handle* h, int frame, int* candidates, int* retries) {

@@ -1806,7 +1806,9 @@ struct SpParams {
     float min_x, max_x, min_y, max_y;     // mnMinX, mnMaxX, mnMinY, mnMaxY
     float winv, hinv;                     // mfGridElementWidthInv / HeightInv
     float mbf, th;
+    float nnratio;                        // ORBmatcher::mfNNratio (the local-points variant)
     int check_ori, cap, use_stereo;
+    int list_th;                          // largest distance a candidate-list entry may have
 };
 struct SpQuery {
     float R[9], t[3];                     // Rcw, tcw of the CURRENT frame
@@ -1832,15 +1834,29 @@ struct SpFrame {
     const int* IT;
     const float* UR;       // mvuRight or nullptr
 };
+__device__ __forceinline__ SpFrame sp_frame(const OrbxPlan* __restrict__ plan, const SpParams& P, int f, const float* kp,
+                                            const uint8_t* desc, const float* xy_un, const int* cell_start, const int* cell_items,
+                                            const float* u_right) {
+    const int kpf = plan->kept_per_frame;
+    SpFrame F;
+    F.K0 = kp + (size_t)f * kpf * 7;
+    F.D0 = reinterpret_cast<const uint4*>(desc + (size_t)f * kpf * 32);
+    F.XY = xy_un + (size_t)f * kpf * 2;
+    F.CS = cell_start + (size_t)f * (UG_COLS * UG_ROWS + 1);
+    F.IT = cell_items + (size_t)f * kpf;
+    F.UR = P.use_stereo ? u_right + (size_t)f * kpf : nullptr;
+    return F;
+}
 
-// One LastFrame map point against the current frame: projection (:1362-1380), search window (:1384-1393),
-// GetFeaturesInArea + the mvuRight test + DescriptorDistance over the candidates.  Executed by a whole warp; every lane
-// returns the warp's best key (distance << 16 | CSR position), 0xffffffff when nothing qualifies.
-//   s_claim != nullptr : candidates claimed by an earlier point with observations are skipped (:1401-1403);
-//   buf != nullptr     : every candidate with distance <= TH_HIGH is appended to buf (first `lc` of them), *total counts them.
-__device__ __forceinline__ unsigned sp_scan(const OrbxPlan* __restrict__ plan, const SpQuery& q, const SpParams& P, const SpFrame& F,
-                                            const float* __restrict__ W, const uint4* __restrict__ QD, const int* __restrict__ LO,
-                                            int i, int lane, const int* s_claim, unsigned* buf, int lc, int* total) {
+// Search window of one map point in the current frame.
+struct SpWin {
+    float u, v, radius, ur;               // centre, GetFeaturesInArea's r, the expected right coordinate
+    int minL, maxL;
+};
+
+// LastFrame variant (src/ORBmatcher.cc:1362-1393): project the map point with the current pose.  W = world positions.
+__device__ __forceinline__ bool sp_project(const OrbxPlan* __restrict__ plan, const SpQuery& q, const SpParams& P,
+                                           const float* __restrict__ W, const int* __restrict__ LO, int i, SpWin& w) {
     const float wx = W[3 * i], wy = W[3 * i + 1], wz = W[3 * i + 2];
     // x3Dc = Rcw * x3Dw + tcw: cv::gemm's 3x3 path -- float products and sums, the "+ C" in double
     float c3[3];
@@ -1850,25 +1866,52 @@ __device__ __forceinline__ unsigned sp_scan(const OrbxPlan* __restrict__ plan, c
         c3[r] = __double2float_rn(__dadd_rn((double)t0, (double)q.t[r]));
     }
     const float invzc = __double2float_rn(__ddiv_rn(1.0, (double)c3[2]));           // (:1368)
-    const float u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, c3[0]), invzc), P.cx);      // (:1373-1374)
-    const float v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, c3[1]), invzc), P.cy);
+    w.u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, c3[0]), invzc), P.cx);                // (:1373-1374)
+    w.v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, c3[1]), invzc), P.cy);
     // written so that NaN fails (the reference would index the grid with an undefined int cast)
-    const bool inside = !(invzc < 0.f) && u >= P.min_x && u <= P.max_x && v >= P.min_y && v <= P.max_y;
-    if (!inside) return 0xffffffffu;
+    if (!(!(invzc < 0.f) && w.u >= P.min_x && w.u <= P.max_x && w.v >= P.min_y && w.v <= P.max_y)) return false;
     const int lo = LO[i];
-    const float radius = __fmul_rn(P.th, plan->lv[lo].scale);                       // (:1384)
-    const int minL = q.fwd ? lo : q.bwd ? 0 : lo - 1;                               // (:1388-1393)
-    const int maxL = q.fwd ? -1 : q.bwd ? lo : lo + 1;
-    // Frame::GetFeaturesInArea (src/Frame.cc:332-346)
+    w.radius = __fmul_rn(P.th, plan->lv[lo].scale);                                 // (:1384)
+    w.minL = q.fwd ? lo : q.bwd ? 0 : lo - 1;                                       // (:1388-1393)
+    w.maxL = q.fwd ? -1 : q.bwd ? lo : lo + 1;
+    w.ur = __fsub_rn(w.u, __fmul_rn(P.mbf, invzc));                                 // (:1407)
+    return true;
+}
+
+// Local-map variant (src/ORBmatcher.cc:58-70): the window comes from the tracking fields Frame::isInFrustum left on the
+// point.  W = (mTrackProjX, mTrackProjY, mTrackProjXR) triples, LO = mnTrackScaleLevel, VC = mTrackViewCos.
+__device__ __forceinline__ bool sp_track_window(const OrbxPlan* __restrict__ plan, const SpParams& P, const float* __restrict__ W,
+                                                const int* __restrict__ LO, const float* __restrict__ VC, int i, SpWin& w) {
+    w.u = W[3 * i];
+    w.v = W[3 * i + 1];
+    w.ur = W[3 * i + 2];
+    if (!(w.u == w.u && w.v == w.v)) return false;                                  // NaN: undefined in the reference
+    const int lvl = LO[i];
+    float r = (double)VC[i] > 0.998 ? 2.5f : 4.0f;                                  // RadiusByViewingCos (:131-137)
+    if (P.th != 1.0f) r = __fmul_rn(r, P.th);                                       // bFactor (:49, :65-66)
+    w.radius = __fmul_rn(r, plan->lv[lvl].scale);
+    w.minL = lvl - 1;
+    w.maxL = lvl;
+    return true;
+}
+
+// Frame::GetFeaturesInArea (src/Frame.cc:327-380) + the mvuRight test + DescriptorDistance over the candidates of one
+// window, executed by a whole warp; every lane returns the warp's best key (distance << 16 | CSR position), 0xffffffff
+// when nothing qualifies, and *second receives the runner-up.
+//   s_claim != nullptr : candidates claimed by an earlier point with observations are skipped (:96-98, :1401-1403);
+//   buf != nullptr     : every candidate with distance <= P.list_th is appended to buf (first `lc` of them), *total counts them.
+__device__ __forceinline__ unsigned sp_window(const SpParams& P, const SpFrame& F, const SpWin& w, const uint4* __restrict__ QD, int i,
+                                              int lane, const int* s_claim, unsigned* buf, int lc, int* total, unsigned* second) {
+    const float u = w.u, v = w.v, radius = w.radius;
     const int c0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, P.min_x), radius), P.winv)));
     const int c1 = min(UG_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, P.min_x), radius), P.winv)));
     const int r0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, P.min_y), radius), P.hinv)));
     const int r1 = min(UG_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, P.min_y), radius), P.hinv)));
+    if (second) *second = 0xffffffffu;
     if (!(c0 < UG_COLS && c1 >= 0 && r0 < UG_ROWS && r1 >= 0)) return 0xffffffffu;
-    unsigned best = 0xffffffffu;
-    const bool check = minL > 0 || maxL >= 0;
+    unsigned best = 0xffffffffu, best2 = 0xffffffffu;
+    const bool check = w.minL > 0 || w.maxL >= 0;
     const uint4 qa = QD[2 * i], qc = QD[2 * i + 1];
-    const float ur = __fsub_rn(u, __fmul_rn(P.mbf, invzc));                         // (:1407)
     int tot = 0;
     for (int ix = c0; ix <= c1; ++ix) {
         const int p0 = F.CS[ix * UG_ROWS + r0], p1 = F.CS[ix * UG_ROWS + r1 + 1];   // cells (ix, r0..r1) are contiguous
@@ -1878,13 +1921,13 @@ __device__ __forceinline__ unsigned sp_scan(const OrbxPlan* __restrict__ plan, c
             if (p < p1) {
                 const int k = F.IT[p];
                 const int oct = __float_as_int(F.K0[(size_t)k * 7 + 5]);
-                bool ok = !(check && (oct < minL || (maxL >= 0 && oct > maxL)));
+                bool ok = !(check && (oct < w.minL || (w.maxL >= 0 && oct > w.maxL)));
                 const float dx = __fsub_rn(F.XY[2 * k], u), dy = __fsub_rn(F.XY[2 * k + 1], v);
                 ok = ok && fabsf(dx) < radius && fabsf(dy) < radius;
-                if (ok && s_claim) ok = !(s_claim[k] < i);                            // (:1401-1403)
+                if (ok && s_claim) ok = !(s_claim[k] < i);
                 if (ok && F.UR) {
                     const float urk = F.UR[k];
-                    ok = !(urk > 0.f && fabsf(__fsub_rn(ur, urk)) > radius);          // (:1405-1411)
+                    ok = !(urk > 0.f && fabsf(__fsub_rn(w.ur, urk)) > radius);        // (:100-105, :1405-1411)
                 }
                 if (ok) {
                     const uint4 da = F.D0[2 * k], dc = F.D0[2 * k + 1];
@@ -1893,9 +1936,10 @@ __device__ __forceinline__ unsigned sp_scan(const OrbxPlan* __restrict__ plan, c
                     key = (dist << 16) | (unsigned)p;
                 }
             }
+            best2 = min(best2, max(best, key));
             best = min(best, key);
             if (buf) {
-                const bool pass = (key >> 16) <= SP_TH_HIGH;
+                const bool pass = (key >> 16) <= (unsigned)P.list_th;
                 const unsigned m = __ballot_sync(0xffffffffu, pass);
                 if (pass) {
                     const int slot = tot + __popc(m & ((1u << lane) - 1u));
@@ -1906,23 +1950,33 @@ __device__ __forceinline__ unsigned sp_scan(const OrbxPlan* __restrict__ plan, c
         }
     }
     if (total) *total = tot;
-    return __reduce_min_sync(0xffffffffu, best);
+    const unsigned m1 = __reduce_min_sync(0xffffffffu, best);
+    if (second) *second = __reduce_min_sync(0xffffffffu, best == m1 ? best2 : best);     // keys are unique (positions differ)
+    return m1;
 }
 
-// Pass 1, state-free and GPU-wide: a warp per (query, LastFrame point) lists the point's acceptable candidates
-// (distance <= TH_HIGH) in the reference's preference order -- ascending (distance, visiting position).  Whatever the
-// claims turn out to be, the point's match is the first unclaimed entry of this list (:1396-1423), so the sequential
-// part (pass 2) never touches a descriptor again.  cand_count > lc marks a list that did not fit.
+// Decision of the local-map variant from the best and second-best (distance, level) (src/ORBmatcher.cc:117-127).
+__device__ __forceinline__ bool sp_accept(const SpParams& P, unsigned d1, int lvl1, unsigned d2, int lvl2) {
+    if (d1 > SP_TH_HIGH) return false;
+    return !(lvl1 == lvl2 && (float)d1 > __fmul_rn(P.nnratio, (float)d2));
+}
+
+// Pass 1, state-free and GPU-wide: a warp per (query, map point) lists the point's candidates of interest
+// (distance <= list_th) in the reference's preference order -- ascending (distance, visiting position) -- as
+// distance << 16 | keypoint index.  Whatever the claims turn out to be, the point's decision only looks at the first
+// unclaimed entries of this list, so the sequential part (pass 2) never touches a descriptor again.
+// cand_count > lc marks a list that did not fit.
 #define SP_LIST_WARPS 8
+template <bool LOCAL>
 __global__ void __launch_bounds__(SP_LIST_WARPS * 32)
 search_projection_list_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __restrict__ queries, SpParams P, int nq, int lc,
                               const float* __restrict__ world, const uint4* __restrict__ mp_desc, const int* __restrict__ mp_obs,
-                              const int* __restrict__ last_octave, const float* __restrict__ kp, const uint8_t* __restrict__ desc,
-                              const float* __restrict__ xy_un, const int* __restrict__ cell_start, const int* __restrict__ cell_items,
-                              const float* __restrict__ u_right, uint16_t* __restrict__ cand_list, int* __restrict__ cand_count) {
+                              const int* __restrict__ last_octave, const float* __restrict__ last_angle, const float* __restrict__ kp,
+                              const uint8_t* __restrict__ desc, const float* __restrict__ xy_un, const int* __restrict__ cell_start,
+                              const int* __restrict__ cell_items, const float* __restrict__ u_right, uint32_t* __restrict__ cand_list,
+                              int* __restrict__ cand_count) {
     __shared__ unsigned s_buf[SP_LIST_WARPS][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int kpf = plan->kept_per_frame;
     const long long slot = (long long)blockIdx.x * SP_LIST_WARPS + warp;
     if (slot >= (long long)nq * P.cap) return;
     const int qi = (int)(slot / P.cap), i = (int)(slot % P.cap);
@@ -1930,16 +1984,12 @@ search_projection_list_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* 
     if (i >= q.n_last) return;
     const size_t qb = (size_t)qi * P.cap;
     int total = 0;
-    if (mp_obs[qb + i] >= 0) {                                              // has a map point and is no outlier (:1356-1360)
-        const int f = q.frame;
-        SpFrame F;
-        F.K0 = kp + (size_t)f * kpf * 7;
-        F.D0 = reinterpret_cast<const uint4*>(desc + (size_t)f * kpf * 32);
-        F.XY = xy_un + (size_t)f * kpf * 2;
-        F.CS = cell_start + (size_t)f * (UG_COLS * UG_ROWS + 1);
-        F.IT = cell_items + (size_t)f * kpf;
-        F.UR = P.use_stereo ? u_right + (size_t)f * kpf : nullptr;
-        sp_scan(plan, q, P, F, world + qb * 3, mp_desc + qb * 2, last_octave + qb, i, lane, nullptr, s_buf[warp], lc, &total);
+    if (mp_obs[qb + i] >= 0) {                           // has a map point, no outlier (:1356-1360) / in view, not bad (:54-58)
+        const SpFrame F = sp_frame(plan, P, q.frame, kp, desc, xy_un, cell_start, cell_items, u_right);
+        SpWin w;
+        const bool ok = LOCAL ? sp_track_window(plan, P, world + qb * 3, last_octave + qb, last_angle + qb, i, w)
+                              : sp_project(plan, q, P, world + qb * 3, last_octave + qb, i, w);
+        if (ok) sp_window(P, F, w, mp_desc + qb * 2, i, lane, nullptr, s_buf[warp], lc, &total, nullptr);
         __syncwarp();
         if (total > 0 && total <= lc) {
             // bitonic sort of the (at most 32) keys across the warp, ascending
@@ -1952,20 +2002,23 @@ search_projection_list_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* 
                     const bool up = (lane & k) == 0, lower = (lane & j) == 0;
                     v = (lower == up) ? min(v, o) : max(v, o);
                 }
-            if (lane < total) cand_list[(qb + i) * (size_t)lc + lane] = (uint16_t)F.IT[v & 0xffffu];
+            if (lane < total) cand_list[(qb + i) * (size_t)lc + lane] = (v & 0xffff0000u) | (unsigned)F.IT[v & 0xffffu];
         }
     }
     if (lane == 0) cand_count[qb + i] = total;
 }
 
-// Pass 2: one CTA per query resolves the claims (see the header comment), then histogram, maxima and culling.
+// Pass 2: one CTA per query resolves the claims (see the header comment).  LastFrame variant: then histogram, maxima
+// and culling.  Local-map variant (LOCAL): keypoints that already hold an observed map point (cur_obs > 0) are claimed
+// from the start, the decision takes the two best unclaimed candidates (ratio test, :117-121), no orientation check.
+template <bool LOCAL>
 __global__ void __launch_bounds__(1024)
 search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __restrict__ queries, SpParams P, int lc,
                          const float* __restrict__ world, const uint4* __restrict__ mp_desc, const int* __restrict__ mp_obs,
                          const int* __restrict__ last_octave, const float* __restrict__ last_angle,
                          const float* __restrict__ kp, const uint8_t* __restrict__ desc, const int* __restrict__ kept_counts,
                          const float* __restrict__ xy_un, const int* __restrict__ cell_start, const int* __restrict__ cell_items,
-                         const float* __restrict__ u_right, const uint16_t* __restrict__ cand_list,
+                         const float* __restrict__ u_right, const int* __restrict__ cur_obs, const uint32_t* __restrict__ cand_list,
                          const int* __restrict__ cand_count, int* __restrict__ match_out, int* __restrict__ stats_out) {
     extern __shared__ int sp_smem[];
     __shared__ int s_hist[SP_HISTO];
@@ -1976,7 +2029,7 @@ search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __res
     const int f = q.frame, nL = q.n_last;
     int N = 0;
     for (int l = 0; l < nl; ++l) N += kept_counts[f * nl + l];
-    int* s_match = sp_smem;                   // [cap]  current keypoint chosen by LastFrame point i, -1: none
+    int* s_match = sp_smem;                   // [cap]  current keypoint chosen by map point i, -1: none
     int* s_claim = sp_smem + P.cap;           // [kpf]  first j with obs > 0 that matched the keypoint; later: its holder
     const size_t qb = (size_t)blockIdx.x * P.cap;
     const float* W = world + qb * 3;
@@ -1984,15 +2037,10 @@ search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __res
     const int* OBS = mp_obs + qb;
     const int* LO = last_octave + qb;
     const float* LA = last_angle + qb;
-    const uint16_t* CL = cand_list + qb * (size_t)lc;
+    const uint32_t* CL = cand_list + qb * (size_t)lc;
     const int* CC = cand_count + qb;
-    SpFrame F;
-    F.K0 = kp + (size_t)f * kpf * 7;
-    F.D0 = reinterpret_cast<const uint4*>(desc + (size_t)f * kpf * 32);
-    F.XY = xy_un + (size_t)f * kpf * 2;
-    F.CS = cell_start + (size_t)f * (UG_COLS * UG_ROWS + 1);
-    F.IT = cell_items + (size_t)f * kpf;
-    F.UR = P.use_stereo ? u_right + (size_t)f * kpf : nullptr;
+    const int* CO = LOCAL ? cur_obs + (size_t)blockIdx.x * kpf : nullptr;
+    const SpFrame F = sp_frame(plan, P, f, kp, desc, xy_un, cell_start, cell_items, u_right);
     const float* K0 = F.K0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
@@ -2002,27 +2050,57 @@ search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __res
     int over = 0;
     for (int i = threadIdx.x; i < nL; i += blockDim.x) { s_match[i] = -1; over += CC[i] > lc; }
     if (over) atomicAdd(&s_nover, over);
-    for (int k = threadIdx.x; k < kpf; k += blockDim.x) s_claim[k] = INT_MAX;
+    for (int k = threadIdx.x; k < kpf; k += blockDim.x) s_claim[k] = (LOCAL && k < N && CO[k] > 0) ? -1 : INT_MAX;   // (:96-98)
     __syncthreads();
     const int nover = s_nover;
 
     int rounds = 0;
     for (;;) {
-        for (int i = threadIdx.x; i < nL; i += blockDim.x) {               // a thread per point: first unclaimed list entry
+        for (int i = threadIdx.x; i < nL; i += blockDim.x) {               // a thread per point: first unclaimed list entries
             const int c = CC[i];
             if (c > lc) continue;
             int newm = -1;
-            for (int j = 0; j < c; ++j) {
-                const int k = CL[(size_t)i * lc + j];
-                if (!(s_claim[k] < i)) { newm = k; break; }
+            if (!LOCAL) {
+                for (int j = 0; j < c; ++j) {
+                    const unsigned e = CL[(size_t)i * lc + j];
+                    const int k = (int)(e & 0xffffu);
+                    if (!(s_claim[k] < i)) { newm = (e >> 16) <= SP_TH_HIGH ? k : -1; break; }
+                }
+            } else {
+                unsigned e1 = 0xffffffffu, e2 = 0xffffffffu;
+                for (int j = 0; j < c; ++j) {
+                    const unsigned e = CL[(size_t)i * lc + j];
+                    if (s_claim[e & 0xffffu] < i) continue;
+                    if (e1 == 0xffffffffu) e1 = e; else { e2 = e; break; }
+                }
+                if (e1 != 0xffffffffu) {
+                    const int k1 = (int)(e1 & 0xffffu);
+                    // a runner-up outside the list has distance > list_th >= TH_HIGH / mfNNratio and cannot reject
+                    const unsigned d2 = e2 == 0xffffffffu ? 0xffffu : (e2 >> 16);
+                    const int lvl2 = e2 == 0xffffffffu ? -1 : __float_as_int(K0[(size_t)(e2 & 0xffffu) * 7 + 5]);
+                    if (sp_accept(P, e1 >> 16, __float_as_int(K0[(size_t)k1 * 7 + 5]), d2, lvl2)) newm = k1;
+                }
             }
             if (s_match[i] != newm) { s_match[i] = newm; s_changed = 1; }
         }
         if (nover)                                                          // lists that did not fit: the full search, a warp per point
             for (int i = warp; i < nL; i += nwarps) {
                 if (CC[i] <= lc) continue;
-                const unsigned best = sp_scan(plan, q, P, F, W, QD, LO, i, lane, s_claim, nullptr, 0, nullptr);
-                const int newm = (best >> 16) <= SP_TH_HIGH ? F.IT[best & 0xffffu] : -1;      // (:1425)
+                SpWin w;
+                const bool ok = LOCAL ? sp_track_window(plan, P, W, LO, LA, i, w) : sp_project(plan, q, P, W, LO, i, w);
+                unsigned best = 0xffffffffu, second = 0xffffffffu;
+                if (ok) best = sp_window(P, F, w, QD, i, lane, s_claim, nullptr, 0, nullptr, &second);
+                int newm = -1;
+                if (best != 0xffffffffu) {
+                    const int k1 = F.IT[best & 0xffffu];
+                    if (!LOCAL) newm = (best >> 16) <= SP_TH_HIGH ? k1 : -1;                   // (:1425)
+                    else {
+                        // no runner-up: bestDist2 stays 256 and bestLevel2 -1 (:77-81)
+                        const unsigned d2 = second == 0xffffffffu ? 256u : (second >> 16);
+                        const int lvl2 = second == 0xffffffffu ? -1 : __float_as_int(K0[(size_t)F.IT[second & 0xffffu] * 7 + 5]);
+                        if (sp_accept(P, best >> 16, __float_as_int(K0[(size_t)k1 * 7 + 5]), d2, lvl2)) newm = k1;
+                    }
+                }
                 if (lane == 0 && s_match[i] != newm) { s_match[i] = newm; s_changed = 1; }
             }
         __syncthreads();
@@ -2031,7 +2109,7 @@ search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __res
         __syncthreads();
         if (!changed) break;
         if (threadIdx.x == 0) s_changed = 0;
-        for (int k = threadIdx.x; k < kpf; k += blockDim.x) s_claim[k] = INT_MAX;
+        for (int k = threadIdx.x; k < kpf; k += blockDim.x) s_claim[k] = (LOCAL && k < N && CO[k] > 0) ? -1 : INT_MAX;
         __syncthreads();
         for (int i = threadIdx.x; i < nL; i += blockDim.x) {
             const int m = s_match[i];
@@ -2041,17 +2119,18 @@ search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __res
     }
 
     // ---- rotation histogram and three maxima (:1428-1441, :1446-1453, :1601-1642)
+    const int check_ori = LOCAL ? 0 : P.check_ori;
     int mine = 0;
     for (int i = threadIdx.x; i < nL; i += blockDim.x) {
         const int m = s_match[i];
         if (m < 0) continue;
         ++mine;
-        if (P.check_ori) atomicAdd(&s_hist[sp_rot_bin(LA[i], K0[(size_t)m * 7 + 3])], 1);
+        if (check_ori) atomicAdd(&s_hist[sp_rot_bin(LA[i], K0[(size_t)m * 7 + 3])], 1);
     }
     if (mine) atomicAdd(&s_nm, mine);
     for (int k = threadIdx.x; k < kpf; k += blockDim.x) s_claim[k] = -1;      // from here on: the holder of keypoint k
     __syncthreads();
-    if (threadIdx.x == 0 && P.check_ori) {
+    if (threadIdx.x == 0 && check_ori) {
         int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
         for (int b = 0; b < SP_HISTO; ++b) {
             const int s = s_hist[b];
@@ -2069,10 +2148,10 @@ search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __res
     }
     for (int i = threadIdx.x; i < nL; i += blockDim.x) {
         const int m = s_match[i];
-        if (m >= 0) atomicMax(&s_claim[m], i);                                 // the last writer holds the keypoint (:1427)
+        if (m >= 0) atomicMax(&s_claim[m], i);                                 // the last writer holds the keypoint (:124, :1427)
     }
     __syncthreads();
-    if (P.check_ori) {
+    if (check_ori) {
         const unsigned keep = s_keep;
         int culled = 0;
         for (int i = threadIdx.x; i < nL; i += blockDim.x) {
@@ -2334,39 +2413,58 @@ void search_projection_fill_query(void* dst, const float* Rcw, const float* tcw,
     memcpy(dst, &q, sizeof q);
 }
 
-cudaError_t launch_search_projection(const OrbxPlan* d_plan, const OrbxPlan& hp, int nq, const void* d_queries, const float* K4,
-                                     const float* bounds, float mbf, float th, int check_ori, int cap, int list_cap, const float* world,
-                                     const uint8_t* mp_desc, const int* mp_obs, const int* last_octave, const float* last_angle,
-                                     const float* kp, const uint8_t* desc, const int* kept_counts, const float* xy_un,
-                                     const int* cell_start, const int* cell_items, const float* u_right, uint16_t* cand_list,
-                                     int* cand_count, int* match_out, int* stats_out, cudaStream_t st) {
+// local = 0: SearchByProjection(CurrentFrame, LastFrame) -- world = positions, last_octave / last_angle of the LastFrame keypoints;
+// local = 1: SearchByProjection(F, vpMapPoints, th) -- world = (mTrackProjX, mTrackProjY, mTrackProjXR), last_octave =
+//            mnTrackScaleLevel, last_angle = mTrackViewCos, cur_obs = Observations() of what the frame's keypoints hold.
+cudaError_t launch_search_projection(const OrbxPlan* d_plan, const OrbxPlan& hp, int local, int nq, const void* d_queries, const float* K4,
+                                     const float* bounds, float mbf, float th, float nnratio, int check_ori, int cap, int list_cap,
+                                     const float* world, const uint8_t* mp_desc, const int* mp_obs, const int* last_octave,
+                                     const float* last_angle, const float* kp, const uint8_t* desc, const int* kept_counts,
+                                     const float* xy_un, const int* cell_start, const int* cell_items, const float* u_right,
+                                     const int* cur_obs, uint32_t* cand_list, int* cand_count, int* match_out, int* stats_out,
+                                     cudaStream_t st) {
     SpParams P;
     P.fx = K4[0]; P.fy = K4[1]; P.cx = K4[2]; P.cy = K4[3];
     P.min_x = bounds[0]; P.max_x = bounds[1]; P.min_y = bounds[2]; P.max_y = bounds[3];
     P.winv = 64.f / (bounds[1] - bounds[0]);
     P.hinv = 48.f / (bounds[3] - bounds[2]);
-    P.mbf = mbf; P.th = th; P.check_ori = check_ori; P.cap = cap; P.use_stereo = u_right != nullptr;
+    P.mbf = mbf; P.th = th; P.nnratio = nnratio; P.check_ori = check_ori; P.cap = cap; P.use_stereo = u_right != nullptr;
+    // entries worth listing: the match itself needs distance <= TH_HIGH; a runner-up can only reject (best > ratio * second)
+    // while second < TH_HIGH / ratio
+    P.list_th = SP_TH_HIGH;
+    if (local) P.list_th = nnratio > 0.4f ? (int)(SP_TH_HIGH / nnratio) + 1 : 256;
     const size_t smem = (size_t)(cap + hp.kept_per_frame) * sizeof(int);
-    static size_t configured[64] = {0};
+    static size_t configured[64][2] = {{0}};
     int dev = 0;
     cudaGetDevice(&dev);
     {
         std::lock_guard<std::mutex> config_lock(g_config_mutex);
-        if (smem > 48 * 1024 && smem > configured[dev & 63]) {
-            cudaError_t e = cudaFuncSetAttribute(search_projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > 48 * 1024 && smem > configured[dev & 63][local ? 1 : 0]) {
+            cudaError_t e = local ? cudaFuncSetAttribute(search_projection_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                  : cudaFuncSetAttribute(search_projection_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            configured[dev & 63] = smem;
+            configured[dev & 63][local ? 1 : 0] = smem;
         }
     }
     const long long warps = (long long)nq * cap;
-    cudaError_t e = launch_k(search_projection_list_kernel, dim3((unsigned)((warps + SP_LIST_WARPS - 1) / SP_LIST_WARPS)),
-                             dim3(SP_LIST_WARPS * 32), 0, st, d_plan, (const SpQuery*)d_queries, P, nq, list_cap, world,
-                             (const uint4*)mp_desc, mp_obs, last_octave, kp, desc, xy_un, cell_start, cell_items, u_right, cand_list,
-                             cand_count);
+    const dim3 lgrid((unsigned)((warps + SP_LIST_WARPS - 1) / SP_LIST_WARPS)), lblock(SP_LIST_WARPS * 32);
+    cudaError_t e;
+    if (local)
+        e = launch_k(search_projection_list_kernel<true>, lgrid, lblock, 0, st, d_plan, (const SpQuery*)d_queries, P, nq, list_cap, world,
+                     (const uint4*)mp_desc, mp_obs, last_octave, last_angle, kp, desc, xy_un, cell_start, cell_items, u_right, cand_list,
+                     cand_count);
+    else
+        e = launch_k(search_projection_list_kernel<false>, lgrid, lblock, 0, st, d_plan, (const SpQuery*)d_queries, P, nq, list_cap, world,
+                     (const uint4*)mp_desc, mp_obs, last_octave, last_angle, kp, desc, xy_un, cell_start, cell_items, u_right, cand_list,
+                     cand_count);
     if (e != cudaSuccess) return e;
-    return launch_k(search_projection_kernel, dim3((unsigned)nq), dim3(1024), smem, st, d_plan, (const SpQuery*)d_queries, P, list_cap,
-                    world, (const uint4*)mp_desc, mp_obs, last_octave, last_angle, kp, desc, kept_counts, xy_un, cell_start, cell_items,
-                    u_right, (const uint16_t*)cand_list, (const int*)cand_count, match_out, stats_out);
+    if (local)
+        return launch_k(search_projection_kernel<true>, dim3((unsigned)nq), dim3(1024), smem, st, d_plan, (const SpQuery*)d_queries, P,
+                        list_cap, world, (const uint4*)mp_desc, mp_obs, last_octave, last_angle, kp, desc, kept_counts, xy_un, cell_start,
+                        cell_items, u_right, cur_obs, (const uint32_t*)cand_list, (const int*)cand_count, match_out, stats_out);
+    return launch_k(search_projection_kernel<false>, dim3((unsigned)nq), dim3(1024), smem, st, d_plan, (const SpQuery*)d_queries, P,
+                    list_cap, world, (const uint4*)mp_desc, mp_obs, last_octave, last_angle, kp, desc, kept_counts, xy_un, cell_start,
+                    cell_items, u_right, cur_obs, (const uint32_t*)cand_list, (const int*)cand_count, match_out, stats_out);
 }
 
 size_t stereo_bucket_entries(const OrbxPlan& hp) { return (size_t)hp.kept_per_frame * ST_MAX_SPAN; }

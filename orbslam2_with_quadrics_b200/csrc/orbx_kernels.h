@@ -47,12 +47,13 @@ cudaError_t launch_stereo(const OrbxPlan* d_plan, const OrbxPlan& hp, int num_sm
                           int* sad, int* row_start, uint16_t* bucket, cudaStream_t st);
 size_t search_projection_query_bytes();
 void search_projection_fill_query(void* dst, const float* Rcw, const float* tcw, int n_last, int frame, int fwd, int bwd);
-cudaError_t launch_search_projection(const OrbxPlan* d_plan, const OrbxPlan& hp, int nq, const void* d_queries, const float* K4,
-                                     const float* bounds, float mbf, float th, int check_ori, int cap, int list_cap, const float* world,
-                                     const uint8_t* mp_desc, const int* mp_obs, const int* last_octave, const float* last_angle,
-                                     const float* kp, const uint8_t* desc, const int* kept_counts, const float* xy_un,
-                                     const int* cell_start, const int* cell_items, const float* u_right, uint16_t* cand_list,
-                                     int* cand_count, int* match_out, int* stats_out, cudaStream_t st);
+cudaError_t launch_search_projection(const OrbxPlan* d_plan, const OrbxPlan& hp, int local, int nq, const void* d_queries, const float* K4,
+                                     const float* bounds, float mbf, float th, float nnratio, int check_ori, int cap, int list_cap,
+                                     const float* world, const uint8_t* mp_desc, const int* mp_obs, const int* last_octave,
+                                     const float* last_angle, const float* kp, const uint8_t* desc, const int* kept_counts,
+                                     const float* xy_un, const int* cell_start, const int* cell_items, const float* u_right,
+                                     const int* cur_obs, uint32_t* cand_list, int* cand_count, int* match_out, int* stats_out,
+                                     cudaStream_t st);
 size_t stereo_bucket_entries(const OrbxPlan& hp);     // uint16 entries of one right frame's row table
 
 // Frame::UndistortKeyPoints + AssignFeaturesToGrid (src/Frame.cc:404-434, :230-245) on the device-resident keypoints

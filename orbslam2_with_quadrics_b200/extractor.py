@@ -297,6 +297,32 @@ class ORBextractor:
         check(self._L.orbx_search_by_projection_device(self._h, len(qs), qs, (C.c_float * 4)(*K4), mbf, mb, th, int(mono),
                                                        int(check_orientation), int(use_stereo)), self._h)
 
+    # ---------------------------------------------------------------- ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th)
+    def search_local_points(self, queries, th: float, nnratio: float = 0.8, use_stereo: bool = False):
+        """(src/ORBmatcher.cc:45-129) for each query: dicts with cur_frame, in_view, proj_x, proj_y, proj_xr, scale_level,
+        view_cos, mp_desc, mp_obs, cur_obs (or None).  Returns [(nmatches, new_match int32[N], rounds)]."""
+        qs = (_capi.OrbxLocalPointsQuery * len(queries))()
+        keep = []
+        for q, d in zip(qs, queries):
+            a = dict(in_view=np.ascontiguousarray(d["in_view"], np.uint8),
+                     w3=np.ascontiguousarray(np.stack([d["proj_x"], d["proj_y"], d["proj_xr"]], axis=1), np.float32),
+                     lvl=np.ascontiguousarray(d["scale_level"], np.int32), vc=np.ascontiguousarray(d["view_cos"], np.float32),
+                     desc=np.ascontiguousarray(d["mp_desc"], np.uint8), obs=np.ascontiguousarray(d["mp_obs"], np.int32))
+            co = None if d.get("cur_obs") is None else np.ascontiguousarray(d["cur_obs"], np.int32)
+            keep.append((a, co))
+            q.cur_frame, q.n_points = int(d.get("cur_frame", 0)), len(a["obs"])
+            q.in_view, q.proj_xy_xr, q.scale_level = a["in_view"].ctypes.data, a["w3"].ctypes.data, a["lvl"].ctypes.data
+            q.view_cos, q.mp_desc, q.mp_obs = a["vc"].ctypes.data, a["desc"].ctypes.data, a["obs"].ctypes.data
+            q.cur_obs = None if co is None else co.ctypes.data
+        res = (_capi.OrbxProjectionResult * len(queries))()
+        check(self._L.orbx_search_local_points(self._h, len(queries), qs, th, nnratio, int(use_stereo), res), self._h)
+        out = []
+        for r in res:
+            m = np.ctypeslib.as_array(C.cast(r.match, C.POINTER(C.c_int32)), shape=(max(r.n, 1),))[:r.n].copy()
+            out.append((r.nmatches, m, r.rounds))
+        del keep
+        return out
+
     # ---------------------------------------------------------------- stage dumps (parity tests)
     def stage_dump(self, frame: int, level: int, stage: int):
         nbytes = C.c_size_t()

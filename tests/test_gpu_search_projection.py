@@ -223,3 +223,89 @@ def test_against_golden_of_the_reference_lines():
             done += 1
     assert done == 6
     gx.close()
+
+
+# ----------------------------------------------------------------------------- SearchLocalPoints' matcher (:45-129)
+def local_oracle(q, kps, desc, grid, sf, th, nnratio, u_right):
+    xy, start, items, bounds = grid
+    return match_oracle.search_local_points(q["in_view"], q["proj_x"], q["proj_y"], q["proj_xr"], q["scale_level"], q["view_cos"],
+                                            q["mp_desc"], q["mp_obs"], xy, kps["octave"].astype(np.int32), desc, u_right, q["cur_obs"],
+                                            start, items, bounds, sf, th, nnratio)
+
+
+@pytest.mark.parametrize("list_cap", [None, "2"])
+def test_local_points_batch_matches_oracle(list_cap, monkeypatch):
+    if list_cap:
+        monkeypatch.setenv("ORBX_SP_LIST_CAP", list_cap)
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["mono_tum"]
+    gx = ORBextractor(nf, sf, nl, it, mt, max_batch=3)
+    res = gx.extract_batch([fr.cluttered_scene(w, h, 700 + i) for i in range(3)])
+    grids = gx.undistort_grid(K_TUM1, D_TUM1)
+    rng = np.random.default_rng(31)
+    qs = []
+    for f, n in ((0, 1500), (1, 400), (2, 2500)):
+        lp = mc.make_local_points(rng, grids[f][0], res[f][0]["octave"].astype(np.int32), res[f][1], n, nl)
+        qs.append(dict(cur_frame=f, **lp))
+    for th, ratio in ((1.0, 0.8), (3.0, 0.8), (5.0, 0.9), (3.0, 0.3)):
+        out = gx.search_local_points(qs, th, ratio)
+        for q, (n, m, rounds) in zip(qs, out):
+            f = q["cur_frame"]
+            n0, m0 = local_oracle(q, res[f][0], res[f][1], grids[f], gx.GetScaleFactors(), th, ratio, None)
+            assert n == n0 and np.array_equal(m, m0)
+            assert ratio < 0.5 or n > 0.15 * len(q["mp_obs"])
+    # no held points at all (cur_obs NULL) == all -1
+    q = dict(qs[0]); q["cur_obs"] = None
+    (n, m, _), = gx.search_local_points([q], 3.0)
+    q2 = dict(qs[0]); q2["cur_obs"] = np.full(len(res[0][0]), -1, np.int32)
+    n0, m0 = local_oracle(q2, res[0][0], res[0][1], grids[0], gx.GetScaleFactors(), 3.0, 0.8, None)
+    assert n == n0 and np.array_equal(m, m0)
+    gx.close()
+
+
+def test_local_points_stereo_frame_and_golden():
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_match_golden", os.path.join(here, "golden", "make_match_golden.py"))
+    mmg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mmg)
+    gold = json.load(open(os.path.join(here, "golden", "match_golden.json")))
+    # golden digests (made by the reference's own lines) on the mono-frame cases
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["mono_tum"]
+    gx = ORBextractor(nf, sf, nl, it, mt)
+    kps, desc = gx(fr.cluttered_scene(w, h, 77))
+    (grid,) = gx.undistort_grid(mmg.K_TUM1, mmg.D_TUM1)
+    cf = dict(xy_un=grid[0], cur_octave=kps["octave"].astype(np.int32), cur_angle=kps["angle"].astype(np.float32), desc=desc,
+              cell_start=grid[1], cell_items=grid[2], bounds=grid[3], sf=np.asarray(gx.GetScaleFactors(), np.float32), nlevels=nl)
+    done = 0
+    for case in mmg.LOCAL_CASES:
+        if case[2]:
+            continue
+        sc = mmg.local_scenario(cf, *case[:3])
+        (n, m, _), = gx.search_local_points([dict(cur_frame=0, **{k: sc[k] for k in (
+            "in_view", "proj_x", "proj_y", "proj_xr", "scale_level", "view_cos", "mp_desc", "mp_obs", "cur_obs")})], case[3])
+        assert mmg.local_digest(sc, n, m) == gold[mmg.local_key(case)]
+        done += 1
+    assert done == 3
+    gx.close()
+    # stereo Frame: mvuRight from orbx_stereo_match stays in HBM
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["stereo_kitti"]
+    left, right = fr.stereo_pair(w, h, 41)
+    gx = ORBextractor(nf, sf, nl, it, mt, max_batch=2)
+    res = gx.extract_batch([left, right])
+    (u_right, _), = gx.stereo_match(gx, 386.1448, 0.5371657, left_frames=[0], right_frames=[1])
+    grids = gx.undistort_grid(K_KITTI, D_RECT)
+    rng = np.random.default_rng(8)
+    lp = mc.make_local_points(rng, grids[0][0], res[0][0]["octave"].astype(np.int32), res[0][1], 3000, nl)
+    # expected right coordinates near the measured ones for half of the points, so that both outcomes of :100-105 occur
+    tgt_ur = u_right[np.argmin(np.abs(grids[0][0][:, 0][None, :] - lp["proj_x"][:, None]) + np.abs(grids[0][0][:, 1][None, :] - lp["proj_y"][:, None]), axis=1)]
+    lp["proj_xr"] = np.where((rng.random(3000) < 0.5) & (tgt_ur > 0), tgt_ur + rng.normal(0, 1.0, 3000), lp["proj_xr"]).astype(np.float32)
+    q = dict(cur_frame=0, **lp)
+    for th in (1.0, 3.0):
+        (n, m, _), = gx.search_local_points([q], th, 0.8, use_stereo=True)
+        n0, m0 = local_oracle(q, res[0][0], res[0][1], grids[0], gx.GetScaleFactors(), th, 0.8, u_right)
+        assert n == n0 and np.array_equal(m, m0) and n > 300
+        n1, _ = local_oracle(q, res[0][0], res[0][1], grids[0], gx.GetScaleFactors(), th, 0.8, None)
+        assert n1 != n0                                                    # the mvuRight test changed the outcome
+    gx.close()
