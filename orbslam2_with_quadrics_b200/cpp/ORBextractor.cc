@@ -205,4 +205,32 @@ int ORBextractor::SearchByProjection(const std::vector<float>& lastWorldPos, con
     return r.nmatches;
 }
 
+int ORBextractor::SearchLocalPoints(const std::vector<unsigned char>& inView, const std::vector<float>& projXYXR,
+                                    const std::vector<int>& scaleLevel, const std::vector<float>& viewCos,
+                                    const std::vector<unsigned char>& descriptors, const std::vector<int>& observations,
+                                    const std::vector<int>& currentObservations, float th, float nnRatio, bool useStereo,
+                                    std::vector<int>& matched)
+{
+    const size_t n = observations.size();
+    if (inView.size() != n || projXYXR.size() != 3 * n || scaleLevel.size() != n || viewCos.size() != n || descriptors.size() != 32 * n)
+        throw std::runtime_error("ORBextractor (orbx): SearchLocalPoints needs one entry per map point in every array");
+    orbx_local_points_query q;
+    q.cur_frame = 0;
+    q.n_points = (int)n;
+    q.in_view = inView.data();
+    q.proj_xy_xr = projXYXR.data();
+    q.scale_level = scaleLevel.data();
+    q.view_cos = viewCos.data();
+    q.mp_desc = descriptors.data();
+    q.mp_obs = observations.data();
+    q.cur_obs = currentObservations.empty() ? 0 : currentObservations.data();
+    orbx_projection_result r;
+    int rc = orbx_search_local_points(handle_, 1, &q, th, nnRatio, useStereo ? 1 : 0, &r);
+    if (rc != ORBX_OK) orbx_throw(handle_, rc, "orbx_search_local_points");
+    if (!currentObservations.empty() && (size_t)r.n != currentObservations.size())
+        throw std::runtime_error("ORBextractor (orbx): currentObservations is not sized like the last operator()'s keypoints");
+    matched.assign(r.match, r.match + r.n);
+    return r.nmatches;
+}
+
 } //namespace ORB_SLAM

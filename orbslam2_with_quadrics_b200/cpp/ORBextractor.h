@@ -89,6 +89,18 @@ public:
                            const cv::Mat& TcwCurrent, const cv::Mat& TcwLast, const cv::Mat& mK, float mbf, float mb, float th,
                            bool bMono, bool checkOrientation, bool useStereo, std::vector<int>& matchedLast);
 
+    // ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, th) (reference src/ORBmatcher.cc:45-129,
+    // the matcher of Tracking::SearchLocalPoints) on the GPU; `this` is F.mpORBextractorLeft as above.  Per map point: the
+    // tracking fields Frame::isInFrustum left on it -- inView = mbTrackInView && !isBad(), (mTrackProjX, mTrackProjY,
+    // mTrackProjXR) as 3 floats, mnTrackScaleLevel, mTrackViewCos -- its descriptor (32 bytes) and Observations().
+    // currentObservations[i2] = -1 where F.mvpMapPoints[i2] is NULL, else that point's Observations().
+    // matched[i2] = index into vpMapPoints F.mvpMapPoints[i2] has to be set to, -1 = leave it.  Returns nmatches.
+    int SearchLocalPoints(const std::vector<unsigned char>& inView, const std::vector<float>& projXYXR,
+                          const std::vector<int>& scaleLevel, const std::vector<float>& viewCos,
+                          const std::vector<unsigned char>& descriptors, const std::vector<int>& observations,
+                          const std::vector<int>& currentObservations, float th, float nnRatio, bool useStereo,
+                          std::vector<int>& matched);
+
 private:
     ORBextractor(const ORBextractor&);
     ORBextractor& operator=(const ORBextractor&);
