@@ -218,6 +218,33 @@ ORBX_API int orbx_search_local_points(orbx_handle* h, int nqueries, const orbx_l
 ORBX_API int orbx_search_local_points_device(orbx_handle* h, int nqueries, const orbx_local_points_query* queries, float th,
                                              float nnratio, int use_stereo);
 
+/* ---- Frame::ComputeBoW (reference src/Frame.cc:395-402): DBoW2's TemplatedVocabulary::transform(features, BowVector&,
+ * FeatureVector&, levelsup = 4) (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1126-1194, :1217-1259) with the ORB
+ * vocabulary's settings -- TF-IDF weighting, L1 scoring -- on the descriptors the last extract left in HBM.
+ * The vocabulary is uploaded once: node i (0 = root) has the children child_items[child_start[i] .. child_start[i+1]) in
+ * DBoW2's order (m_nodes[i].children), a 32-byte descriptor, a weight and, for leaves, a word id (ignored for inner
+ * nodes).  child_items lists every node but the root exactly once.  L = the vocabulary's depth (m_L).
+ * Result per frame: the BowVector as (word id, value) in std::map order, values L1-normalised doubles bit-identical to
+ * the reference's; the FeatureVector as (node id, feature index) pairs in std::map order with each node's features in
+ * push_back order.  Stopped words (weight 0) appear in neither (:1157).  Pinned host memory owned by the handle, valid
+ * until its next orbx_compute_bow call. */
+typedef struct orbx_vocabulary orbx_vocabulary;
+ORBX_API int orbx_vocabulary_create(int device, int n_nodes, int L, const int32_t* child_start, const int32_t* child_items,
+                                    const uint8_t* node_desc, const double* node_weight, const int32_t* node_word,
+                                    orbx_vocabulary** out);
+ORBX_API int orbx_vocabulary_destroy(orbx_vocabulary* voc);
+typedef struct orbx_bow_result {
+    int n_words;                 /* mBowVec.size() */
+    const uint32_t* word_ids;
+    const double* word_values;
+    int n_features;              /* features listed in mFeatVec */
+    const uint32_t* fv_nodes;
+    const uint32_t* fv_features;
+} orbx_bow_result;
+ORBX_API int orbx_compute_bow(orbx_handle* h, const orbx_vocabulary* voc, int nframes, const int* frames, int levelsup,
+                              orbx_bow_result* results);
+ORBX_API int orbx_compute_bow_device(orbx_handle* h, const orbx_vocabulary* voc, int nframes, const int* frames, int levelsup);
+
 /* Pinned host buffers callers may fill with frames so that H2D copies are asynchronous DMA. */
 ORBX_API int orbx_alloc_host(size_t bytes, void** out);
 ORBX_API int orbx_free_host(void* p);

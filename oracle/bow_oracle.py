@@ -90,3 +90,9 @@ def ref_transform(voc, desc, levelsup=4):
     k = _ref.bowref_transform(C.c_int(voc["n_nodes"]), p(a[0]), p(a[1]), p(a[2]), p(a[3]), p(a[4]), C.c_int(voc["L"]), C.c_int(n),
                               p(d), C.c_int(levelsup), p(ids), p(vals), p(fn), p(ff), C.byref(nfv))
     return ids[:k].copy(), vals[:k].copy(), fn[:nfv.value].copy(), ff[:nfv.value].copy()
+
+
+def ref_last_transform_seconds() -> float:
+    """Wall time of the transform() call inside the last ref_transform (without the stub's tree set-up)."""
+    _ref.bowref_last_transform_seconds.restype = C.c_double
+    return float(_ref.bowref_last_transform_seconds())

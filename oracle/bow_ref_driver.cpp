@@ -2,6 +2,12 @@
 // TEST INFRASTRUCTURE: the checker of orbx_compute_bow, never on the product path.
 #include "bow_shim.h"
 
+#include <chrono>
+
+static double g_last_transform_seconds = 0;
+// wall time of the last voc.transform() call alone (building the stub's tree from the flat arrays is not the reference's cost)
+extern "C" double bowref_last_transform_seconds() { return g_last_transform_seconds; }
+
 namespace {
 struct L1Stub : public DBoW2::GeneralScoring {       // L1Scoring's mustNormalize (ScoringObject.h) without ScoringObject.cpp
     virtual double score(const DBoW2::BowVector&, const DBoW2::BowVector&) const { return 0; }
@@ -36,7 +42,9 @@ extern "C" int bowref_transform(int n_nodes, const int* child_start, const int* 
     for (int i = 0; i < n; ++i) memcpy(feats[i].bytes, desc + 32 * (size_t)i, 32);
     BowVector v;
     FeatureVector fv;
+    const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     voc.transform(feats, v, fv, levelsup);
+    g_last_transform_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     int k = 0;
     for (BowVector::const_iterator it = v.begin(); it != v.end(); ++it, ++k) { bow_ids[k] = it->first; bow_values[k] = it->second; }
     int m = 0;

@@ -26,6 +26,7 @@ SYMBOLS = [
     "orbx_extract_batch_color", "orbx_extract_device_color", "orbx_undistort_grid", "orbx_fast_stats",
     "orbx_search_by_projection", "orbx_search_by_projection_device", "orbx_search_by_projection_fetch",
     "orbx_search_local_points", "orbx_search_local_points_device",
+    "orbx_vocabulary_create", "orbx_vocabulary_destroy", "orbx_compute_bow", "orbx_compute_bow_device",
 ]
 GRAY8, BGR8, RGB8, BGRA8, RGBA8 = range(5)
 
@@ -63,6 +64,11 @@ class OrbxLocalPointsQuery(C.Structure):
     _fields_ = [("cur_frame", C.c_int), ("n_points", C.c_int), ("in_view", C.c_void_p), ("proj_xy_xr", C.c_void_p),
                 ("scale_level", C.c_void_p), ("view_cos", C.c_void_p), ("mp_desc", C.c_void_p), ("mp_obs", C.c_void_p),
                 ("cur_obs", C.c_void_p)]
+
+
+class OrbxBowResult(C.Structure):
+    _fields_ = [("n_words", C.c_int), ("word_ids", C.c_void_p), ("word_values", C.c_void_p), ("n_features", C.c_int),
+                ("fv_nodes", C.c_void_p), ("fv_features", C.c_void_p)]
 
 
 class OrbxProjectionResult(C.Structure):
@@ -133,6 +139,10 @@ def lib():
     L.orbx_search_by_projection_fetch.argtypes = [vp, i, C.POINTER(OrbxProjectionQuery), C.POINTER(OrbxProjectionResult)]
     L.orbx_search_local_points.argtypes = [vp, i, C.POINTER(OrbxLocalPointsQuery), f, f, i, C.POINTER(OrbxProjectionResult)]
     L.orbx_search_local_points_device.argtypes = [vp, i, C.POINTER(OrbxLocalPointsQuery), f, f, i]
+    L.orbx_vocabulary_create.argtypes = [i, i, i, vp, vp, vp, vp, vp, C.POINTER(vp)]
+    L.orbx_vocabulary_destroy.argtypes = [vp]
+    L.orbx_compute_bow.argtypes = [vp, vp, i, C.POINTER(i), i, C.POINTER(OrbxBowResult)]
+    L.orbx_compute_bow_device.argtypes = [vp, vp, i, C.POINTER(i), i]
     L.orbx_undistort_grid.argtypes = [vp, i, C.POINTER(i), C.POINTER(C.c_float), C.POINTER(C.c_float), i, C.POINTER(OrbxGridResult)]
     _lib = L
     return L

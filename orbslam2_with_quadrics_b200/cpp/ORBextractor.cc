@@ -233,4 +233,16 @@ int ORBextractor::SearchLocalPoints(const std::vector<unsigned char>& inView, co
     return r.nmatches;
 }
 
+void ORBextractor::ComputeBoW(const orbx_vocabulary* voc, std::vector<std::pair<unsigned int, double> >& bow,
+                              std::vector<std::pair<unsigned int, unsigned int> >& featVec, int levelsup)
+{
+    orbx_bow_result r;
+    int rc = orbx_compute_bow(handle_, voc, 1, 0, levelsup, &r);
+    if (rc != ORBX_OK) orbx_throw(handle_, rc, "orbx_compute_bow");
+    bow.resize(r.n_words);
+    for (int i = 0; i < r.n_words; ++i) bow[i] = std::make_pair(r.word_ids[i], r.word_values[i]);
+    featVec.resize(r.n_features);
+    for (int i = 0; i < r.n_features; ++i) featVec[i] = std::make_pair(r.fv_nodes[i], r.fv_features[i]);
+}
+
 } //namespace ORB_SLAM

@@ -16,10 +16,12 @@
 #ifndef ORBEXTRACTOR_H
 #define ORBEXTRACTOR_H
 
+#include <utility>
 #include <vector>
 #include <opencv2/core/core.hpp>
 
 struct orbx_handle;
+struct orbx_vocabulary;
 
 namespace ORB_SLAM2
 {
@@ -100,6 +102,14 @@ public:
                           const std::vector<unsigned char>& descriptors, const std::vector<int>& observations,
                           const std::vector<int>& currentObservations, float th, float nnRatio, bool useStereo,
                           std::vector<int>& matched);
+
+    // Frame::ComputeBoW (reference src/Frame.cc:395-402: mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4)) on
+    // the GPU, over the descriptors this extractor still holds in HBM from its last operator().  `voc` is the ORB
+    // vocabulary uploaded once with orbx_vocabulary_create (include/orbx.h; INTEGRATION.md shows the flattening of
+    // DBoW2's m_nodes).  bow: (word id, value) in std::map order, L1-normalised doubles bit-identical to DBoW2's;
+    // featVec: (node id, feature index) in std::map / push_back order.
+    void ComputeBoW(const orbx_vocabulary* voc, std::vector<std::pair<unsigned int, double> >& bow,
+                    std::vector<std::pair<unsigned int, unsigned int> >& featVec, int levelsup = 4);
 
 private:
     ORBextractor(const ORBextractor&);

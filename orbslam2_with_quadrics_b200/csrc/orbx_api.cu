@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <string>
+#include <new>
 #include <vector>
 
 #include "../../include/orbx.h"
@@ -96,6 +97,10 @@ struct orbx_handle {
     size_t sp_bytes;
     int *d_sp_out, *h_sp_out;  // [match nq * kpf][stats nq * 2]
     size_t sp_out_ints;
+    // ComputeBoW (orbx_compute_bow; allocated on first use): [leaf B*kpf][nid B*kpf][word ids B*kpf][fv nodes B*kpf]
+    // [fv features B*kpf][counts 2B][frames B] as 32-bit words, and the word values as doubles
+    unsigned *d_bow, *h_bow;
+    double *d_bow_val, *h_bow_val;
     cudaEvent_t ev_stereo;
     int last_n;
     bool pyramid_valid;
@@ -392,6 +397,8 @@ void free_geometry(orbx_handle* h) {
     cudaFree(h->d_un_xy); cudaFree(h->d_un_start); cudaFree(h->d_un_items); cudaFree(h->d_un_frames);
     cudaFreeHost(h->h_un_xy); cudaFreeHost(h->h_un_start); cudaFreeHost(h->h_un_items); cudaFreeHost(h->h_un_frames);
     cudaFree(h->d_sp); cudaFreeHost(h->h_sp); cudaFree(h->d_sp_out); cudaFreeHost(h->h_sp_out);
+    cudaFree(h->d_bow); cudaFreeHost(h->h_bow); cudaFree(h->d_bow_val); cudaFreeHost(h->h_bow_val);
+    h->d_bow = h->h_bow = 0; h->d_bow_val = h->h_bow_val = 0;
     h->d_sp = h->h_sp = 0; h->sp_bytes = 0; h->d_sp_out = h->h_sp_out = 0; h->sp_out_ints = 0;
     h->d_un_xy = h->h_un_xy = 0; h->d_un_start = h->d_un_items = h->d_un_frames = h->h_un_start = h->h_un_items = h->h_un_frames = 0;
     cudaFree(h->d_st_u); cudaFree(h->d_st_depth); cudaFree(h->d_st_sad); cudaFree(h->d_st_pairs); cudaFree(h->d_st_rows); cudaFree(h->d_st_bucket); h->d_st_rows = 0; h->d_st_bucket = 0;
@@ -702,6 +709,7 @@ int orbx_create(const orbx_config* cfg, orbx_handle** out) {
     h->d_un_xy = h->h_un_xy = 0; h->d_un_start = h->d_un_items = h->d_un_frames = h->h_un_start = h->h_un_items = h->h_un_frames = 0;
     h->d_color = h->h_color = 0; h->color_bytes = 0;
     h->d_sp = h->h_sp = 0; h->sp_bytes = 0; h->d_sp_out = h->h_sp_out = 0; h->sp_out_ints = 0;
+    h->d_bow = h->h_bow = 0; h->d_bow_val = h->h_bow_val = 0;
     h->timing = false; h->ev_created = false; h->ev_head = 0; h->ev_pending = 0;
     memset(h->stage_ms, 0, sizeof h->stage_ms);
     memset(h->stage_launches, 0, sizeof h->stage_launches);
@@ -1346,6 +1354,121 @@ int orbx_search_local_points(orbx_handle* h, int nqueries, const orbx_local_poin
     std::vector<int> frames(nqueries);
     for (int i = 0; i < nqueries; ++i) frames[i] = queries[i].cur_frame;
     return sp_fetch(h, nqueries, frames.data(), results);
+}
+
+// ---- Frame::ComputeBoW: the vocabulary lives in HBM, independent of any handle.
+struct orbx_vocabulary {
+    int device, n_nodes, L;
+    int *d_child_start, *d_child_items, *d_word;
+    uint8_t* d_desc;
+    double* d_weight;
+};
+
+int orbx_vocabulary_create(int device, int n_nodes, int L, const int32_t* child_start, const int32_t* child_items,
+                           const uint8_t* node_desc, const double* node_weight, const int32_t* node_word, orbx_vocabulary** out) {
+    if (!out || !child_start || !child_items || !node_desc || !node_weight || !node_word || n_nodes < 2 || L < 1 || L > 32)
+        return ORBX_ERR_BAD_ARGS;
+    // a tree in DBoW2's sense: every node but the root is the child of exactly one node, the root has children
+    if (child_start[0] != 0 || child_start[n_nodes] != n_nodes - 1 || child_start[1] == 0) return ORBX_ERR_BAD_ARGS;
+    std::vector<unsigned char> seen((size_t)n_nodes, 0);
+    for (int i = 0; i < n_nodes; ++i) {
+        if (child_start[i + 1] < child_start[i]) return ORBX_ERR_BAD_ARGS;
+        for (int c = child_start[i]; c < child_start[i + 1]; ++c) {
+            const int id = child_items[c];
+            if (id < 1 || id >= n_nodes || seen[id]) return ORBX_ERR_BAD_ARGS;
+            seen[id] = 1;
+        }
+        if (child_start[i + 1] - child_start[i] > (1 << 20)) return ORBX_ERR_BAD_ARGS;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return ORBX_ERR_CUDA;
+    orbx_vocabulary* v = new (std::nothrow) orbx_vocabulary();
+    if (!v) return ORBX_ERR_BAD_ARGS;
+    v->device = device; v->n_nodes = n_nodes; v->L = L;
+    v->d_child_start = v->d_child_items = v->d_word = 0; v->d_desc = 0; v->d_weight = 0;
+    const size_t n = (size_t)n_nodes;
+    cudaError_t e = cudaMalloc(&v->d_child_start, (n + 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_child_items, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_word, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_desc, n * 32);
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_weight, n * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_child_start, child_start, (n + 1) * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_child_items, child_items, (n - 1) * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_word, node_word, n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_desc, node_desc, n * 32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_weight, node_weight, n * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { orbx_vocabulary_destroy(v); return ORBX_ERR_CUDA; }
+    *out = v;
+    return ORBX_OK;
+}
+
+int orbx_vocabulary_destroy(orbx_vocabulary* v) {
+    if (!v) return ORBX_OK;
+    cudaSetDevice(v->device);
+    cudaFree(v->d_child_start); cudaFree(v->d_child_items); cudaFree(v->d_word); cudaFree(v->d_desc); cudaFree(v->d_weight);
+    delete v;
+    return ORBX_OK;
+}
+
+static int bow_enqueue(orbx_handle* h, const orbx_vocabulary* voc, int nframes, const int* frames, int levelsup) {
+    if (!h || !voc || nframes < 1 || nframes > h->cfg.max_batch || !h->have_plan || voc->device != h->cfg.device || levelsup < 0)
+        return ORBX_ERR_BAD_ARGS;
+    for (int i = 0; i < nframes; ++i) {
+        const int f = frames ? frames[i] : i;
+        if (f < 0 || f >= h->last_n) return ORBX_ERR_BAD_ARGS;
+    }
+    CK(h, cudaSetDevice(h->cfg.device));
+    const OrbxPlan& P = h->plan;
+    const size_t B = (size_t)h->cfg.max_batch, kpf = (size_t)P.kept_per_frame;
+    if (kpf > 8192) return ORBX_ERR_BAD_ARGS;
+    const size_t words = 5 * B * kpf + 3 * B;
+    if (!h->d_bow) {
+        CK(h, cudaMalloc(&h->d_bow, words * 4));
+        CK(h, cudaMallocHost(&h->h_bow, words * 4));
+        CK(h, cudaMalloc(&h->d_bow_val, B * kpf * 8));
+        CK(h, cudaMallocHost(&h->h_bow_val, B * kpf * 8));
+    }
+    cudaStream_t st = h->stream;
+    CK(h, cudaStreamSynchronize(st));
+    unsigned* hf = h->h_bow + 5 * B * kpf + 2 * B;
+    for (int i = 0; i < nframes; ++i) hf[i] = (unsigned)(frames ? frames[i] : i);
+    unsigned* df = h->d_bow + 5 * B * kpf + 2 * B;
+    CK(h, cudaMemcpyAsync(df, hf, (size_t)nframes * 4, cudaMemcpyHostToDevice, st));
+    CK(h, orbx::launch_compute_bow(h->d_plan, P, voc->d_child_start, voc->d_child_items, voc->d_desc, voc->d_weight, voc->d_word,
+                                   voc->n_nodes, voc->L, reinterpret_cast<const int*>(df), nframes, levelsup, h->d_out_desc,
+                                   h->d_kept_counts(), reinterpret_cast<int*>(h->d_bow), reinterpret_cast<int*>(h->d_bow + B * kpf),
+                                   h->d_bow + 2 * B * kpf, h->d_bow_val, h->d_bow + 3 * B * kpf, h->d_bow + 4 * B * kpf,
+                                   reinterpret_cast<int*>(h->d_bow + 5 * B * kpf), st));
+    h->launches += 2;
+    return ORBX_OK;
+}
+
+int orbx_compute_bow_device(orbx_handle* h, const orbx_vocabulary* voc, int nframes, const int* frames, int levelsup) {
+    return bow_enqueue(h, voc, nframes, frames, levelsup);
+}
+
+int orbx_compute_bow(orbx_handle* h, const orbx_vocabulary* voc, int nframes, const int* frames, int levelsup, orbx_bow_result* results) {
+    if (!results) return ORBX_ERR_BAD_ARGS;
+    const int rc = bow_enqueue(h, voc, nframes, frames, levelsup);
+    if (rc != ORBX_OK) return rc;
+    const OrbxPlan& P = h->plan;
+    const size_t B = (size_t)h->cfg.max_batch, kpf = (size_t)P.kept_per_frame, n = (size_t)nframes;
+    cudaStream_t st = h->stream;
+    CK(h, cudaMemcpyAsync(h->h_bow + 2 * B * kpf, h->d_bow + 2 * B * kpf, n * kpf * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h->h_bow + 3 * B * kpf, h->d_bow + 3 * B * kpf, n * kpf * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h->h_bow + 4 * B * kpf, h->d_bow + 4 * B * kpf, n * kpf * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h->h_bow + 5 * B * kpf, h->d_bow + 5 * B * kpf, n * 2 * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(h->h_bow_val, h->d_bow_val, n * kpf * 8, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    for (int i = 0; i < nframes; ++i) {
+        const int* cnt = reinterpret_cast<const int*>(h->h_bow + 5 * B * kpf) + 2 * i;
+        results[i].n_words = cnt[0];
+        results[i].word_ids = h->h_bow + 2 * B * kpf + (size_t)i * kpf;
+        results[i].word_values = h->h_bow_val + (size_t)i * kpf;
+        results[i].n_features = cnt[1];
+        results[i].fv_nodes = h->h_bow + 3 * B * kpf + (size_t)i * kpf;
+        results[i].fv_features = h->h_bow + 4 * B * kpf + (size_t)i * kpf;
+    }
+    return ORBX_OK;
 }
 
 int orbx_fast_stats(orbx_handle* h, int frame, int* candidates, int* retries) {

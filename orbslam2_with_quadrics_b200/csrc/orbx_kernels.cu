@@ -2171,6 +2171,173 @@ search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __res
 }
 
 // =====================================================================================
+// Frame::ComputeBoW (src/Frame.cc:395-402) = DBoW2 TemplatedVocabulary::transform(features, BowVector&, FeatureVector&,
+// levelsup) (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1126-1194, descent :1217-1259, FORB::distance FORB.cpp:81-101,
+// BowVector::addWeight / normalize BowVector.cpp:34-46, :62-84, FeatureVector::addFeature FeatureVector.cpp:31-45) for
+// the ORB vocabulary's TF-IDF weighting and L1 scoring, on the descriptors the extraction left in HBM.
+//   bow_descend_kernel : 16 lanes per descriptor walk the tree; at each node the lanes take the children, Hamming
+//                        distance by POPC, "first strictly smaller wins" (:1244-1248) = minimum of (distance << 20 | child
+//                        position).  Output: the leaf node and the node at level L - levelsup.
+//   bow_reduce_kernel  : one CTA per frame.  Bitonic sort of (word id, leaf) in shared memory -> distinct words and
+//                        their multiplicities; a word's value is its weight added c times IN SEQUENCE (what c addWeight
+//                        calls produce), the L1 norm is the sequential sum in word order (map order), both in double
+//                        with __dadd_rn so the bits are the reference's; then (node, feature) keys are sorted for the
+//                        FeatureVector (map order, push_back order).  Stopped words (weight 0) drop out of both (:1157).
+// =====================================================================================
+struct BowVoc {
+    const int* child_start;
+    const int* child_items;
+    const uint4* node_desc;
+    const double* node_weight;
+    const int* node_word;
+    int n_nodes, L;
+};
+#define BOW_GROUP 16
+#define BOW_THREADS 256
+
+__global__ void __launch_bounds__(BOW_THREADS)
+bow_descend_kernel(const OrbxPlan* __restrict__ plan, BowVoc V, const int* __restrict__ frames, int nframes, int levelsup,
+                   const uint8_t* __restrict__ desc, const int* __restrict__ kept_counts, int* __restrict__ leaf_out,
+                   int* __restrict__ nid_out) {
+    const int kpf = plan->kept_per_frame, nl = plan->nlevels;
+    const long long g = ((long long)blockIdx.x * BOW_THREADS + threadIdx.x) / BOW_GROUP;
+    if (g >= (long long)nframes * kpf) return;                               // whole groups leave together
+    const int fi = (int)(g / kpf), i = (int)(g % kpf);
+    const int f = frames[fi];
+    int N = 0;
+    for (int l = 0; l < nl; ++l) N += kept_counts[f * nl + l];
+    if (i >= N) return;
+    const int sub = threadIdx.x & (BOW_GROUP - 1);
+    const unsigned gmask = 0xffffu << (threadIdx.x & 16);
+    const uint4* D = reinterpret_cast<const uint4*>(desc + ((size_t)f * kpf + i) * 32);
+    const uint4 qa = D[0], qc = D[1];
+    const int nid_level = V.L - levelsup;
+    int nid = 0, final_id = 0, level = 0;                                    // root when nid_level <= 0 (:1227)
+    for (int guard = 0; guard < 64; ++guard) {
+        ++level;
+        const int cs = V.child_start[final_id], ce = V.child_start[final_id + 1];
+        unsigned best = 0xffffffffu;
+        for (int c = cs + sub; c < ce; c += BOW_GROUP) {
+            const int id = V.child_items[c];
+            const uint4 da = V.node_desc[2 * (size_t)id], dc = V.node_desc[2 * (size_t)id + 1];
+            const unsigned dist = __popc(qa.x ^ da.x) + __popc(qa.y ^ da.y) + __popc(qa.z ^ da.z) + __popc(qa.w ^ da.w) +
+                                  __popc(qc.x ^ dc.x) + __popc(qc.y ^ dc.y) + __popc(qc.z ^ dc.z) + __popc(qc.w ^ dc.w);
+            best = min(best, (dist << 20) | (unsigned)(c - cs));
+        }
+#pragma unroll
+        for (int o = BOW_GROUP / 2; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(gmask, best, o, BOW_GROUP));
+        final_id = V.child_items[cs + (int)(best & 0xfffffu)];
+        if (level == nid_level) nid = final_id;
+        if (V.child_start[final_id + 1] == V.child_start[final_id]) break;   // isLeaf (:1254)
+    }
+    if (sub == 0) {
+        leaf_out[(size_t)fi * kpf + i] = final_id;
+        nid_out[(size_t)fi * kpf + i] = nid;
+    }
+}
+
+__device__ __forceinline__ void bow_bitonic_sort(unsigned long long* keys, int n /* power of two */) {
+    for (int k = 2; k <= n; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < n; t += blockDim.x) {
+                const int p = t ^ j;
+                if (p > t) {
+                    const unsigned long long a = keys[t], b = keys[p];
+                    const bool up = (t & k) == 0;
+                    if ((a > b) == up) { keys[t] = b; keys[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+__global__ void __launch_bounds__(1024)
+bow_reduce_kernel(const OrbxPlan* __restrict__ plan, BowVoc V, const int* __restrict__ frames, int sort_n,
+                  const int* __restrict__ kept_counts, const int* __restrict__ leaf_in, const int* __restrict__ nid_in,
+                  unsigned* __restrict__ word_ids, double* __restrict__ word_values, unsigned* __restrict__ fv_nodes,
+                  unsigned* __restrict__ fv_features, int* __restrict__ counts_out) {
+    extern __shared__ unsigned long long bow_keys[];
+    __shared__ int s_warp[33];
+    __shared__ int s_nwords, s_nfeat;
+    __shared__ double s_norm;
+    const int kpf = plan->kept_per_frame, nl = plan->nlevels;
+    const int fi = blockIdx.x, f = frames[fi];
+    int N = 0;
+    for (int l = 0; l < nl; ++l) N += kept_counts[f * nl + l];
+    const int* leaf = leaf_in + (size_t)fi * kpf;
+    const int* nid = nid_in + (size_t)fi * kpf;
+    unsigned* wid = word_ids + (size_t)fi * kpf;
+    double* wval = word_values + (size_t)fi * kpf;
+    unsigned* fn = fv_nodes + (size_t)fi * kpf;
+    unsigned* ff = fv_features + (size_t)fi * kpf;
+    const unsigned long long NONE = ~0ull;
+
+    // ---- BowVector: distinct words with multiplicities
+    for (int i = threadIdx.x; i < sort_n; i += blockDim.x) {
+        unsigned long long key = NONE;
+        if (i < N) {
+            const int lf = leaf[i];
+            if (V.node_weight[lf] > 0.0) key = ((unsigned long long)(unsigned)V.node_word[lf] << 32) | (unsigned)lf;   // (:1157)
+        }
+        bow_keys[i] = key;
+    }
+    __syncthreads();
+    bow_bitonic_sort(bow_keys, sort_n);
+    // heads of runs -> output slots (block scan over chunks of blockDim)
+    int base = 0;
+    for (int i0 = 0; i0 < sort_n; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        const unsigned long long key = i < sort_n ? bow_keys[i] : NONE;
+        const int head = key != NONE && (i == 0 || bow_keys[i - 1] != key);
+        int tot;
+        const int e = block_excl_scan(head, &tot, s_warp);
+        if (head) {
+            int c = 1;
+            while (i + c < sort_n && bow_keys[i + c] == key) ++c;              // multiplicity (runs are short)
+            const double w = V.node_weight[(unsigned)(key & 0xffffffffu)];
+            double s = w;
+            for (int r = 1; r < c; ++r) s = __dadd_rn(s, w);                    // c addWeight calls (BowVector.cpp:40)
+            wid[base + e] = (unsigned)(key >> 32);
+            wval[base + e] = s;
+        }
+        base += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) s_nwords = base;
+    __syncthreads();
+    const int nwords = s_nwords;
+    if (threadIdx.x == 0) {                                                     // BowVector::normalize(L1): map order, in sequence
+        double norm = 0.0;
+        for (int j = 0; j < nwords; ++j) norm = __dadd_rn(norm, fabs(wval[j]));
+        s_norm = norm;
+    }
+    __syncthreads();
+    const double norm = s_norm;
+    if (norm > 0.0)
+        for (int j = threadIdx.x; j < nwords; j += blockDim.x) wval[j] = __ddiv_rn(wval[j], norm);
+
+    // ---- FeatureVector: (node at level L - levelsup, feature index) in map / push_back order
+    __syncthreads();
+    for (int i = threadIdx.x; i < sort_n; i += blockDim.x) {
+        unsigned long long key = NONE;
+        if (i < N && V.node_weight[leaf[i]] > 0.0) key = ((unsigned long long)(unsigned)nid[i] << 32) | (unsigned)i;
+        bow_keys[i] = key;
+    }
+    __syncthreads();
+    bow_bitonic_sort(bow_keys, sort_n);
+    int nfeat = 0;
+    for (int i = threadIdx.x; i < sort_n; i += blockDim.x) {
+        const unsigned long long key = bow_keys[i];
+        if (key != NONE) { fn[i] = (unsigned)(key >> 32); ff[i] = (unsigned)(key & 0xffffffffu); ++nfeat; }   // valid keys sort first
+    }
+    if (threadIdx.x == 0) s_nfeat = 0;
+    __syncthreads();
+    if (nfeat) atomicAdd(&s_nfeat, nfeat);
+    __syncthreads();
+    if (threadIdx.x == 0) { counts_out[2 * fi] = nwords; counts_out[2 * fi + 1] = s_nfeat; }
+}
+
+// =====================================================================================
 // launch wrappers (called from orbx_api.cu)
 // =====================================================================================
 // format: 1 BGR8, 2 RGB8, 3 BGRA8, 4 RGBA8 (orbx_pixel_format)
@@ -2465,6 +2632,37 @@ cudaError_t launch_search_projection(const OrbxPlan* d_plan, const OrbxPlan& hp,
     return launch_k(search_projection_kernel<false>, dim3((unsigned)nq), dim3(1024), smem, st, d_plan, (const SpQuery*)d_queries, P,
                     list_cap, world, (const uint4*)mp_desc, mp_obs, last_octave, last_angle, kp, desc, kept_counts, xy_un, cell_start,
                     cell_items, u_right, cur_obs, (const uint32_t*)cand_list, (const int*)cand_count, match_out, stats_out);
+}
+
+cudaError_t launch_compute_bow(const OrbxPlan* d_plan, const OrbxPlan& hp, const int* voc_child_start, const int* voc_child_items,
+                               const uint8_t* voc_desc, const double* voc_weight, const int* voc_word, int n_nodes, int L,
+                               const int* d_frames, int nframes, int levelsup, const uint8_t* desc, const int* kept_counts, int* leaf,
+                               int* nid, unsigned* word_ids, double* word_values, unsigned* fv_nodes, unsigned* fv_features,
+                               int* counts_out, cudaStream_t st) {
+    BowVoc V;
+    V.child_start = voc_child_start; V.child_items = voc_child_items; V.node_desc = reinterpret_cast<const uint4*>(voc_desc);
+    V.node_weight = voc_weight; V.node_word = voc_word; V.n_nodes = n_nodes; V.L = L;
+    const long long groups = (long long)nframes * hp.kept_per_frame;
+    const long long blocks = (groups * BOW_GROUP + BOW_THREADS - 1) / BOW_THREADS;
+    cudaError_t e = launch_k(bow_descend_kernel, dim3((unsigned)blocks), dim3(BOW_THREADS), 0, st, d_plan, V, d_frames, nframes, levelsup,
+                             desc, kept_counts, leaf, nid);
+    if (e != cudaSuccess) return e;
+    int sort_n = 1024;
+    while (sort_n < hp.kept_per_frame) sort_n <<= 1;
+    const size_t smem = (size_t)sort_n * sizeof(unsigned long long);
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> config_lock(g_config_mutex);
+        if (smem > 48 * 1024 && smem > configured[dev & 63]) {
+            e = cudaFuncSetAttribute(bow_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured[dev & 63] = smem;
+        }
+    }
+    return launch_k(bow_reduce_kernel, dim3((unsigned)nframes), dim3(1024), smem, st, d_plan, V, d_frames, sort_n, kept_counts,
+                    (const int*)leaf, (const int*)nid, word_ids, word_values, fv_nodes, fv_features, counts_out);
 }
 
 size_t stereo_bucket_entries(const OrbxPlan& hp) { return (size_t)hp.kept_per_frame * ST_MAX_SPAN; }

@@ -54,6 +54,11 @@ cudaError_t launch_search_projection(const OrbxPlan* d_plan, const OrbxPlan& hp,
                                      const float* xy_un, const int* cell_start, const int* cell_items, const float* u_right,
                                      const int* cur_obs, uint32_t* cand_list, int* cand_count, int* match_out, int* stats_out,
                                      cudaStream_t st);
+cudaError_t launch_compute_bow(const OrbxPlan* d_plan, const OrbxPlan& hp, const int* voc_child_start, const int* voc_child_items,
+                               const uint8_t* voc_desc, const double* voc_weight, const int* voc_word, int n_nodes, int L,
+                               const int* d_frames, int nframes, int levelsup, const uint8_t* desc, const int* kept_counts, int* leaf,
+                               int* nid, unsigned* word_ids, double* word_values, unsigned* fv_nodes, unsigned* fv_features,
+                               int* counts_out, cudaStream_t st);
 size_t stereo_bucket_entries(const OrbxPlan& hp);     // uint16 entries of one right frame's row table
 
 // Frame::UndistortKeyPoints + AssignFeaturesToGrid (src/Frame.cc:404-434, :230-245) on the device-resident keypoints

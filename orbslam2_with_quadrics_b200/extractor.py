@@ -323,6 +323,26 @@ class ORBextractor:
         del keep
         return out
 
+    # ---------------------------------------------------------------- Frame::ComputeBoW
+    def compute_bow(self, voc: "Vocabulary", frames=None, levelsup: int = 4):
+        """(src/Frame.cc:395-402) on the descriptors of the last extract.  Returns per frame (word_ids uint32[], word_values
+        float64[], fv_nodes uint32[], fv_features uint32[])."""
+        n = len(frames) if frames is not None else self._last_n
+        fr_ = (C.c_int * n)(*frames) if frames is not None else None
+        res = (_capi.OrbxBowResult * n)()
+        check(self._L.orbx_compute_bow(self._h, voc._v, n, fr_, levelsup, res), self._h)
+        out = []
+        for r in res:
+            arr = lambda p, t, k: np.ctypeslib.as_array(C.cast(p, C.POINTER(t)), shape=(max(k, 1),))[:k].copy()
+            out.append((arr(r.word_ids, C.c_uint32, r.n_words), arr(r.word_values, C.c_double, r.n_words),
+                        arr(r.fv_nodes, C.c_uint32, r.n_features), arr(r.fv_features, C.c_uint32, r.n_features)))
+        return out
+
+    def compute_bow_device(self, voc: "Vocabulary", frames, levelsup: int = 4):
+        """Enqueue only (device-side timing)."""
+        n = len(frames)
+        check(self._L.orbx_compute_bow_device(self._h, voc._v, n, (C.c_int * n)(*frames), levelsup), self._h)
+
     # ---------------------------------------------------------------- stage dumps (parity tests)
     def stage_dump(self, frame: int, level: int, stage: int):
         nbytes = C.c_size_t()
@@ -341,3 +361,27 @@ class ORBextractor:
         if stage == _capi.STAGE_ANGLES:
             return buf.view(np.float32)
         raise ValueError(stage)
+
+
+class Vocabulary:
+    """An ORB vocabulary (DBoW2 tree) resident in HBM: `voc` is the flat layout of orbslam2_with_quadrics_b200.vocabulary."""
+
+    def __init__(self, voc: dict, device: int = 0):
+        self._L = _capi.lib()
+        self._v = C.c_void_p()
+        a = [np.ascontiguousarray(voc["child_start"], np.int32), np.ascontiguousarray(voc["child_items"], np.int32),
+             np.ascontiguousarray(voc["node_desc"], np.uint8), np.ascontiguousarray(voc["node_weight"], np.float64),
+             np.ascontiguousarray(voc["node_word"], np.int32)]
+        check(self._L.orbx_vocabulary_create(device, int(voc["n_nodes"]), int(voc["L"]), a[0].ctypes.data, a[1].ctypes.data,
+                                             a[2].ctypes.data, a[3].ctypes.data, a[4].ctypes.data, C.byref(self._v)), None)
+
+    def close(self):
+        if self._v:
+            self._L.orbx_vocabulary_destroy(self._v)
+            self._v = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

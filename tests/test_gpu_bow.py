@@ -1,0 +1,113 @@
+"""GPU parity of orbx_compute_bow (Frame::ComputeBoW, reference src/Frame.cc:395-402 -> DBoW2
+TemplatedVocabulary::transform) against oracle/bow_oracle.py, which is pinned against the reference's own DBoW2 lines.
+Bar: word ids, FeatureVector pairs and their order identical; BowVector values bit-exact as float64 (tolerance 0: the
+additions and the division are done in the reference's order with IEEE double operations)."""
+import json
+import os
+import time
+
+import numpy as np
+import pytest
+
+from oracle import bow_oracle
+from orbslam2_with_quadrics_b200 import ORBextractor, OrbxError, Vocabulary
+from orbslam2_with_quadrics_b200 import frames as fr
+from orbslam2_with_quadrics_b200 import vocabulary as vc
+
+pytestmark = pytest.mark.gpu
+
+
+def same(got, want):
+    ids, vals, fn, ff = got
+    ids0, vals0, fn0, ff0 = want
+    assert np.array_equal(ids, ids0) and np.array_equal(vals.view(np.uint64), vals0.view(np.uint64))
+    assert np.array_equal(fn, fn0) and np.array_equal(ff, ff0)
+
+
+@pytest.mark.parametrize("k,L,irregular", [(10, 3, False), (10, 4, True), (4, 6, True)])
+def test_batch_matches_oracle(k, L, irregular):
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["mono_tum"]
+    gx = ORBextractor(nf, sf, nl, it, mt, max_batch=4)
+    res = gx.extract_batch([fr.cluttered_scene(w, h, 800 + i) for i in range(3)] + [fr.flat_frame(w, h)])
+    voc = vc.random_vocabulary(k, L, seed=10 * k + L, irregular=irregular)
+    gv = Vocabulary(voc)
+    for levelsup in (4, 1, L + 2):
+        out = gx.compute_bow(gv, levelsup=levelsup)
+        assert len(out) == 4
+        for (kps, desc), got in zip(res, out):
+            same(got, bow_oracle.transform(voc, desc, levelsup))
+        assert len(out[3][0]) == 0 and len(out[3][2]) == 0                        # no keypoints: empty vectors
+        assert len(out[0][0]) < len(out[0][2]) or L > 3                            # small vocabulary: words repeat
+    out = gx.compute_bow(gv, frames=[2, 0])
+    same(out[0], bow_oracle.transform(voc, res[2][1], 4))
+    same(out[1], bow_oracle.transform(voc, res[0][1], 4))
+    gv.close()
+    gx.close()
+
+
+def test_orbvoc_shape_1080p_4k_timing_and_bad_arguments():
+    voc = vc.random_vocabulary(10, 6, seed=1)                                      # ORBvoc's shape: 10^6 words
+    gv = Vocabulary(voc)
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["rgbd_1080p"]
+    B = 16
+    gx = ORBextractor(nf, sf, nl, it, mt, max_batch=B, download_pyramid=False)
+    imgs = [fr.cluttered_scene(w, h, 3100 + i) for i in range(4)]
+    res = gx.extract_batch([imgs[i % 4] for i in range(B)])
+    out = gx.compute_bow(gv)
+    for f in range(4):
+        same(out[f], bow_oracle.transform(voc, res[f][1], 4))
+    # measurement of the row: device time per batch, end to end, and the reference's own lines on one host thread
+    import torch
+    st = torch.cuda.ExternalStream(gx.stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    frames = list(range(B))
+    for _ in range(3):
+        gx.compute_bow_device(gv, frames)
+    gx.synchronize()
+    K = 20
+    e0.record(st)
+    for _ in range(K):
+        gx.compute_bow_device(gv, frames)
+    e1.record(st)
+    gx.synchronize()
+    dev_ms = e0.elapsed_time(e1) / K
+    import ctypes as C
+    from orbslam2_with_quadrics_b200 import _capi
+    cres = (_capi.OrbxBowResult * B)()
+    t0 = time.perf_counter()
+    for _ in range(K):                                                             # the C ABI call itself (no numpy copies)
+        _capi.check(gx._L.orbx_compute_bow(gx._h, gv._v, B, None, 4, cres), gx._h)
+    e2e_ms = (time.perf_counter() - t0) / K * 1e3
+    cpu_ms = None
+    if bow_oracle.ref_available():
+        secs = []
+        for f in range(4):
+            same(out[f], bow_oracle.ref_transform(voc, res[f][1], 4))
+            secs.append(bow_oracle.ref_last_transform_seconds())
+        cpu_ms = float(np.median(secs)) * 1e3                                      # the transform() call alone
+    rep = {"workload": "ComputeBoW, %d frames of ~%d ORB descriptors, vocabulary k=10 L=6 (1 111 111 nodes, 35.6 MB), levelsup 4" % (
+               B, len(res[0][1])), "device_ms_per_batch": dev_ms, "device_us_per_frame": dev_ms / B * 1e3,
+           "e2e_ms_per_batch_with_d2h": e2e_ms, "e2e_us_per_frame": e2e_ms / B * 1e3,
+           "reference_lines_cpu_ms_per_frame_1_thread": cpu_ms,
+           "words_per_frame": [len(o[0]) for o in out[:4]]}
+    print(json.dumps(rep))
+    if os.path.isdir("gpurun_out"):
+        json.dump(rep, open("gpurun_out/r01_compute_bow.json", "w"), indent=1)
+    gx.close()
+    # 4K: more than 4096 keypoint slots per frame (8192-entry sort)
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["mono_4k"]
+    gx = ORBextractor(nf, sf, nl, it, mt)
+    with pytest.raises(OrbxError):
+        gx.compute_bow(gv, frames=[0])                                             # nothing extracted yet
+    kps, desc = gx(fr.cluttered_scene(w, h, 9))
+    (got,) = gx.compute_bow(gv)
+    same(got, bow_oracle.transform(voc, desc, 4))
+    with pytest.raises(OrbxError):
+        gx.compute_bow(gv, frames=[1])
+    gx.close()
+    gv.close()
+    bad = vc.random_vocabulary(3, 2, seed=1)
+    bad["child_items"] = bad["child_items"].copy()
+    bad["child_items"][0] = bad["child_items"][1]                                  # a node listed twice
+    with pytest.raises(OrbxError):
+        Vocabulary(bad)
