@@ -25,6 +25,8 @@ sed -n '1601p' "$M" | grep -q 'void ORBmatcher::ComputeThreeMaxima' || { echo "O
 sed -n '45p' "$M" | grep -q 'int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint\*> &vpMapPoints' || { echo "ORBmatcher.cc:45 is not SearchByProjection(Frame&, vpMapPoints)"; exit 1; }
 sed -n '129p' "$M" | grep -q '^}' || { echo "ORBmatcher.cc:129 is not the end of SearchByProjection(Frame&, vpMapPoints)"; exit 1; }
 sed -n '131p' "$M" | grep -q 'float ORBmatcher::RadiusByViewingCos' || { echo "ORBmatcher.cc:131 is not RadiusByViewingCos"; exit 1; }
+sed -n '159p' "$M" | grep -q 'int ORBmatcher::SearchByBoW(KeyFrame\* pKF,Frame &F' || { echo "ORBmatcher.cc:159 is not SearchByBoW(KeyFrame*, Frame&)"; exit 1; }
+sed -n '288p' "$M" | grep -q '^}' || { echo "ORBmatcher.cc:288 is not the end of SearchByBoW(KeyFrame*, Frame&)"; exit 1; }
 TMP=$(mktemp -d)
 trap 'rm -rf "$TMP"' EXIT
 {
@@ -41,6 +43,7 @@ trap 'rm -rf "$TMP"' EXIT
   sed -n '1328,1470p' "$M"
   sed -n '1601,1642p' "$M"
   sed -n '45,137p' "$M"
+  sed -n '159,288p' "$M"
   echo '}'
 } > "$TMP/stereo_ref_gen.cpp"
 mkdir -p "$OUT"

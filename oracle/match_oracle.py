@@ -297,3 +297,81 @@ def ref_search_local_points(in_view, proj_x, proj_y, proj_xr, scale_level, view_
     n = _ref.matchref_search_local_points(C.c_int(nP), *[p(x) for x in a], C.c_int(nC), p(kp), p(b[0]), p(b[1]), p(b[2]), p(b[3]),
                                           p(b[4]), p(b[5]), p(b[6]), C.c_int(len(b[6])), C.c_float(th), C.c_float(nnratio), p(out))
     return int(n), out
+
+
+# ============================================================================= SearchByBoW(KeyFrame*, Frame&)
+TH_LOW = 50                               # src/ORBmatcher.cc:38
+
+
+def search_by_bow(kf_desc, kf_valid, kf_angle, kf_fv_nodes, kf_fv_features, f_desc, f_angle, f_fv_nodes, f_fv_features, nnratio=0.7,
+                  check_orientation=True):
+    """ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches) (src/ORBmatcher.cc:159-288).  kf_valid: 0 = no map
+    point, 1 = good, 2 = isBad().  FeatureVectors as (node, feature) pairs in map / push_back order.
+    Returns (nmatches, match int32[F.N]: KeyFrame feature index or -1)."""
+    nF = len(f_desc)
+    kd = np.ascontiguousarray(kf_desc).view(np.uint64).reshape(-1, 4)
+    fd = np.ascontiguousarray(f_desc).view(np.uint64).reshape(-1, 4) if nF else np.zeros((0, 4), np.uint64)
+    match = np.full(nF, -1, np.int32)
+    rot_hist = [[] for _ in range(HISTO_LENGTH)]
+    factor = f32(f32(1.0) / f32(HISTO_LENGTH))
+    nmatches = 0
+    kf_groups, f_groups = {}, {}
+    for n, i in zip(kf_fv_nodes, kf_fv_features):
+        kf_groups.setdefault(int(n), []).append(int(i))
+    for n, i in zip(f_fv_nodes, f_fv_features):
+        f_groups.setdefault(int(n), []).append(int(i))
+    for node in sorted(kf_groups):                        # the merge walk visits the common nodes in ascending order
+        if node not in f_groups:
+            continue
+        for ikf in kf_groups[node]:
+            if kf_valid[ikf] != 1:
+                continue
+            best1 = best2 = 256
+            best_idx = -1
+            for i_f in f_groups[node]:
+                if match[i_f] >= 0:
+                    continue
+                d = int(sum(bin(int(a ^ b)).count("1") for a, b in zip(kd[ikf], fd[i_f])))
+                if d < best1:
+                    best2, best1, best_idx = best1, d, i_f
+                elif d < best2:
+                    best2 = d
+            if best1 <= TH_LOW and f32(best1) < f32(f32(nnratio) * f32(best2)):
+                match[best_idx] = ikf
+                if check_orientation:
+                    rot = f32(f32(kf_angle[ikf]) - f32(f_angle[best_idx]))
+                    if rot < 0.0:
+                        rot = f32(rot + f32(360.0))
+                    b = _round_half_away(f32(rot * factor))
+                    if b == HISTO_LENGTH:
+                        b = 0
+                    rot_hist[b].append(best_idx)
+                nmatches += 1
+    if check_orientation:
+        ind = compute_three_maxima([len(h) for h in rot_hist])
+        for b in range(HISTO_LENGTH):
+            if b in ind:
+                continue
+            for i_f in rot_hist[b]:
+                match[i_f] = -1
+                nmatches -= 1
+    return nmatches, match
+
+
+def ref_search_by_bow(kf_desc, kf_valid, kf_angle, kf_fv_nodes, kf_fv_features, f_desc, f_angle, f_fv_nodes, f_fv_features,
+                      nnratio=0.7, check_orientation=True):
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(os.path.join(_HERE, "_ref", "libstereoref.so"))
+        _ref.matchref_search_by_projection.restype = C.c_int
+    _ref.matchref_search_by_bow.restype = C.c_int
+    a = [np.ascontiguousarray(kf_desc, np.uint8), np.ascontiguousarray(kf_valid, np.uint8), np.ascontiguousarray(kf_angle, f32)]
+    b = [np.ascontiguousarray(kf_fv_nodes, np.uint32), np.ascontiguousarray(kf_fv_features, np.uint32)]
+    c = [np.ascontiguousarray(f_desc, np.uint8), np.ascontiguousarray(f_angle, f32)]
+    d = [np.ascontiguousarray(f_fv_nodes, np.uint32), np.ascontiguousarray(f_fv_features, np.uint32)]
+    out = np.full(len(c[0]), -1, np.int32)
+    p = lambda x: C.c_void_p(x.ctypes.data)
+    n = _ref.matchref_search_by_bow(C.c_int(len(a[1])), p(a[0]), p(a[1]), p(a[2]), C.c_int(len(b[0])), p(b[0]), p(b[1]),
+                                    C.c_int(len(c[0])), p(c[0]), p(c[1]), C.c_int(len(d[0])), p(d[0]), p(d[1]), C.c_float(nnratio),
+                                    C.c_int(int(check_orientation)), p(out))
+    return int(n), out

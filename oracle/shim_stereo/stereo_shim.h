@@ -6,7 +6,8 @@
 // UndistortKeyPoints / ComputeImageBounds (Frame.cc:230-245, :382-392, :404-434, :436-464), Frame::GetFeaturesInArea
 // (:327-380), ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) / ComputeThreeMaxima
 // (ORBmatcher.cc:1328-1470, :1601-1642) and ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) /
-// RadiusByViewingCos (ORBmatcher.cc:45-129, :131-137), taken from where they lie at
+// RadiusByViewingCos (ORBmatcher.cc:45-129, :131-137) and ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (ORBmatcher.cc:159-288),
+// taken from where they lie at
 // build time, against this header: the handful of cv:: types those lines use (8U / 32F Mat views, convertTo, ones, scalar * Mat,
 // Mat - Mat, norm L1) and the members of Frame / ORBextractor / ORBmatcher they touch.  Written from scratch.
 #ifndef ORBX_ORACLE_STEREO_SHIM_H
@@ -18,6 +19,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <utility>
 #include <vector>
@@ -185,9 +187,14 @@ static inline void undistortPoints(const Mat& src, Mat& dst, const Mat& K, const
 #define FRAME_GRID_ROWS 48          // include/Frame.h:39-40
 #define FRAME_GRID_COLS 64
 
+namespace DBoW2 {                       // Thirdparty/DBoW2/DBoW2/FeatureVector.h:21-22 is a std::map with one extra method
+typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector;
+}
+
 namespace ORB_SLAM2 {
 
 class Frame;
+class KeyFrame;
 
 struct MapPoint {                     // the accessors and tracking fields ORBmatcher.cc:45-129, :1328-1470 touch
     cv::Mat mWorldPos, mDescriptor;
@@ -210,6 +217,7 @@ public:
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
     int SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, const float th = 3);    // include/ORBmatcher.h
+    int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
     float RadiusByViewingCos(const float& viewCos);
     void ComputeThreeMaxima(vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
     float mfNNratio;
@@ -230,6 +238,7 @@ public:
     vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1,
                                      const int maxLevel = -1) const;               // include/Frame.h:92
     static float fx, fy, cx, cy;
+    DBoW2::FeatureVector mFeatVec;
     cv::Mat mTcw;
     std::vector<MapPoint*> mvpMapPoints;
     std::vector<bool> mvbOutlier;
@@ -244,6 +253,15 @@ public:
     ORBextractor *mpORBextractorLeft, *mpORBextractorRight;
     std::vector<float> mvScaleFactors, mvInvScaleFactors;
     float mbf, mb;
+};
+
+class KeyFrame {                        // what ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) reads (src/ORBmatcher.cc:159-288)
+public:
+    std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    std::vector<MapPoint*> mvpMapPoints;
+    DBoW2::FeatureVector mFeatVec;
+    cv::Mat mDescriptors;
+    std::vector<cv::KeyPoint> mvKeysUn;
 };
 
 }  // namespace ORB_SLAM2

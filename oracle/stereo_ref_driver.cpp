@@ -209,3 +209,36 @@ extern "C" int matchref_search_local_points(int nP, const unsigned char* in_view
     }
     return nmatches;
 }
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (src/ORBmatcher.cc:159-288, called by
+// Tracking::TrackReferenceKeyFrame src/Tracking.cc:771-776 with ORBmatcher(0.7, true) and by Relocalization :1376 with 0.75),
+// the reference's own lines.  Both FeatureVectors come as (node, feature) pairs in map / push_back order.
+// match[iF] = index of the KeyFrame feature whose map point vpMapPointMatches[iF] holds, else -1.
+extern "C" int matchref_search_by_bow(int nKF, const unsigned char* kf_desc, const unsigned char* kf_valid, const float* kf_angle,
+                                      int nKFfv, const unsigned int* kf_fv_nodes, const unsigned int* kf_fv_features, int nF,
+                                      const unsigned char* f_desc, const float* f_angle, int nFfv, const unsigned int* f_fv_nodes,
+                                      const unsigned int* f_fv_features, float nnratio, int check_ori, int* match) {
+    using namespace ORB_SLAM2;
+    KeyFrame KF;
+    Frame F;
+    std::vector<MapPoint> mps(nKF > 0 ? nKF : 1);
+    KF.mvpMapPoints.assign(nKF, (MapPoint*)0);
+    KF.mvKeysUn.resize(nKF);
+    for (int i = 0; i < nKF; ++i) {
+        mps[i].mbBad = kf_valid[i] == 2;                                 // 0: no map point, 1: good, 2: bad
+        if (kf_valid[i]) KF.mvpMapPoints[i] = &mps[i];
+        KF.mvKeysUn[i].angle = kf_angle[i];
+    }
+    KF.mDescriptors = cv::Mat(nKF, 32, CV_8U, (void*)kf_desc, 32);
+    for (int i = 0; i < nKFfv; ++i) KF.mFeatVec[kf_fv_nodes[i]].push_back(kf_fv_features[i]);
+    F.N = nF;
+    F.mvKeys.resize(nF);
+    for (int i = 0; i < nF; ++i) F.mvKeys[i].angle = f_angle[i];
+    F.mDescriptors = cv::Mat(nF, 32, CV_8U, (void*)f_desc, 32);
+    for (int i = 0; i < nFfv; ++i) F.mFeatVec[f_fv_nodes[i]].push_back(f_fv_features[i]);
+    ORBmatcher matcher(nnratio, check_ori != 0);
+    std::vector<MapPoint*> out;
+    const int nmatches = matcher.SearchByBoW(&KF, F, out);
+    for (int i = 0; i < nF; ++i) match[i] = out[i] ? (int)(out[i] - &mps[0]) : -1;
+    return nmatches;
+}

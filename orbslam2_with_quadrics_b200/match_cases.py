@@ -106,3 +106,27 @@ def make_local_points(rng, xy_un, cur_octave, desc, n_points, nlevels, dup_frac=
     cur_obs = np.where(rng.random(nC) < held_frac, rng.choice([0, 1, 4], nC), -1).astype(np.int32)
     return dict(in_view=in_view, proj_x=proj_x, proj_y=proj_y, proj_xr=proj_xr, scale_level=scale_level, view_cos=view_cos,
                 mp_desc=mp_desc, mp_obs=mp_obs, cur_obs=cur_obs)
+
+
+def make_keyframe(rng, f_desc, f_angle, n_kf, flip_bits=12, angle_noise=6.0, angle_outlier_frac=0.15):
+    """A reference KeyFrame for ORBmatcher::SearchByBoW(KeyFrame*, Frame&) (src/ORBmatcher.cc:159-288) that really matches the
+    frame: its descriptors are the frame's with a few flipped bits (so that most land in the same vocabulary node and under
+    TH_LOW), in shuffled order, with duplicates (two KeyFrame features competing for one frame feature), unrelated ones,
+    features without / with bad map points, and angles that agree up to noise except for a fraction of outliers."""
+    nF = len(f_desc)
+    src = rng.integers(0, nF, n_kf)
+    ndup = n_kf // 5
+    src[rng.integers(0, n_kf, ndup)] = src[rng.integers(0, n_kf, ndup)]
+    kf_desc = f_desc[src].copy()
+    flips = rng.integers(0, 256, (n_kf, flip_bits))
+    for k in range(flip_bits):
+        on = rng.random(n_kf) < 0.5
+        kf_desc[np.arange(n_kf)[on], flips[on, k] // 8] ^= (1 << (flips[on, k] % 8)).astype(np.uint8)
+    unrelated = rng.random(n_kf) < 0.1
+    kf_desc[unrelated] = rng.integers(0, 256, (int(unrelated.sum()), 32), dtype=np.uint8)
+    kf_valid = rng.choice([0, 1, 1, 1, 1, 1, 2], n_kf).astype(np.uint8)
+    kf_angle = (f_angle[src] + rng.normal(0, angle_noise, n_kf)).astype(f32)
+    wild = rng.random(n_kf) < angle_outlier_frac
+    kf_angle[wild] = rng.uniform(0, 360, int(wild.sum())).astype(f32)
+    kf_angle = np.mod(kf_angle, f32(360.0)).astype(f32)
+    return dict(kf_desc=kf_desc, kf_valid=kf_valid, kf_angle=kf_angle)

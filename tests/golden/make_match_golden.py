@@ -78,6 +78,37 @@ def local_key(case):
     return "local/seed%d/n%d/%s/th%g" % (case[0], case[1], "stereo" if case[2] else "mono-frame", case[3])
 
 
+# SearchByBoW(KeyFrame*, Frame&): (vocabulary k, L, levelsup, seed, pKF->N, mfNNratio, mbCheckOrientation) -- ratio 0.7 in
+# TrackReferenceKeyFrame (src/Tracking.cc:771), 0.75 in Relocalization (:1376)
+BOW_CASES = [(10, 3, 1, 1, 900, 0.7, True), (10, 4, 2, 2, 1500, 0.75, True), (10, 4, 2, 3, 1200, 0.7, False), (4, 6, 4, 4, 700, 0.9, True),
+             (10, 4, 6, 5, 500, 0.7, True)]
+
+
+def bow_scenario(cf, case):
+    from oracle import bow_oracle
+    from orbslam2_with_quadrics_b200 import vocabulary as vc
+    k, L, levelsup, seed, n_kf = case[:5]
+    voc = vc.random_vocabulary(k, L, seed=seed)
+    rng = np.random.default_rng(2000 + seed)
+    kf = mc.make_keyframe(rng, cf["desc"], cf["cur_angle"], n_kf)
+    _, _, kn, kfeat = bow_oracle.transform(voc, kf["kf_desc"], levelsup)
+    _, _, fn, ff = bow_oracle.transform(voc, cf["desc"], levelsup)
+    return voc, dict(**kf, kf_fv_nodes=kn, kf_fv_features=kfeat, f_desc=cf["desc"], f_angle=cf["cur_angle"], f_fv_nodes=fn,
+                     f_fv_features=ff)
+
+
+def bow_digest(sc, n, m):
+    ins = hashlib.sha256()
+    for k in ("kf_desc", "kf_valid", "kf_angle", "kf_fv_nodes", "kf_fv_features", "f_fv_nodes", "f_fv_features"):
+        ins.update(np.ascontiguousarray(sc[k]).tobytes())
+    return {"nmatches": int(n), "inputs_sha256": ins.hexdigest(),
+            "match_sha256": hashlib.sha256(np.ascontiguousarray(m, np.int32).tobytes()).hexdigest()}
+
+
+def bow_key(case):
+    return "bow/k%d/L%d/up%d/seed%d/n%d/ratio%g/ori%d" % (case[0], case[1], case[2], case[3], case[4], case[5], int(case[6]))
+
+
 def digest(sc, n, m):
     ins = hashlib.sha256()
     for k in ("world", "mp_desc", "mp_obs", "outlier", "last_octave", "last_angle", "Tcw_cur", "Tcw_last"):
@@ -108,4 +139,9 @@ if __name__ == "__main__":
         n, m = match_oracle.ref_search_local_points(th=case[3], **sc)
         out[local_key(case)] = local_digest(sc, n, m)
         print(local_key(case), n, int((m >= 0).sum()))
+    for case in BOW_CASES:
+        _, sc = bow_scenario(cf, case)
+        n, m = match_oracle.ref_search_by_bow(nnratio=case[5], check_orientation=case[6], **sc)
+        out[bow_key(case)] = bow_digest(sc, n, m)
+        print(bow_key(case), n, len(set(sc["f_fv_nodes"].tolist())))
     json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "match_golden.json"), "w"), indent=1, sort_keys=True)

@@ -106,3 +106,17 @@ def test_local_points_ratio_test_and_held_points_are_exercised(current_frame):
     assert not np.any((m >= 0) & (sc["cur_obs"] > 0))           # keypoints holding an observed point are never taken (:96-98)
     assert np.any((m >= 0) & (sc["cur_obs"] == 0))              # ... those holding an unobserved one are
     assert match_oracle.radius_by_viewing_cos(np.float32(0.998)) == 2.5 and match_oracle.radius_by_viewing_cos(0.99799) == 4.0
+
+
+# ----------------------------------------------------------------------------- SearchByBoW(KeyFrame*, Frame&) (:159-288)
+@pytest.mark.parametrize("case", mmg.BOW_CASES)
+def test_search_by_bow_restatement_matches_reference_lines_and_golden(case, current_frame):
+    _, sc = mmg.bow_scenario(current_frame, case)
+    n1, m1 = match_oracle.search_by_bow(nnratio=case[5], check_orientation=case[6], **sc)
+    assert mmg.bow_digest(sc, n1, m1) == GOLD[mmg.bow_key(case)]
+    if match_oracle.ref_available():
+        n2, m2 = match_oracle.ref_search_by_bow(nnratio=case[5], check_orientation=case[6], **sc)
+        assert n1 == n2 and np.array_equal(m1, m2)
+    assert n1 == int((m1 >= 0).sum()) > 0.15 * case[4]          # every counted match holds its keypoint (claims are exclusive)
+    kf_of = m1[m1 >= 0]
+    assert np.all(sc["kf_valid"][kf_of] == 1)                   # features without a good map point never match (:196-202)
