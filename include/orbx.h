@@ -245,6 +245,28 @@ ORBX_API int orbx_compute_bow(orbx_handle* h, const orbx_vocabulary* voc, int nf
                               orbx_bow_result* results);
 ORBX_API int orbx_compute_bow_device(orbx_handle* h, const orbx_vocabulary* voc, int nframes, const int* frames, int levelsup);
 
+/* ---- ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (reference
+ * src/ORBmatcher.cc:159-288; Tracking::TrackReferenceKeyFrame src/Tracking.cc:771-776 with ORBmatcher(0.7, true),
+ * Tracking::Relocalization :1376 with 0.75): matching inside common vocabulary nodes.  The Frame side is frame
+ * `cur_frame` of this handle's last extract together with its FeatureVector from the last orbx_compute_bow (which must
+ * have covered that frame); the KeyFrame side comes from the caller.
+ * Result (orbx_projection_result): match[iF] = index of the KeyFrame feature whose map point vpMapPointMatches[iF]
+ * holds, -1 = NULL; nmatches = the function's return value. */
+typedef struct orbx_bow_match_query {
+    int cur_frame;
+    int n_kf;                      /* pKF->N */
+    const uint8_t* kf_desc;        /* n_kf x 32: pKF->mDescriptors */
+    const uint8_t* kf_valid;       /* n_kf: 0 = no map point, 1 = a good one, 2 = pMP->isBad() */
+    const float* kf_angle;         /* n_kf: pKF->mvKeysUn[i].angle */
+    int n_kf_fv;                   /* entries of pKF->mFeatVec */
+    const uint32_t* kf_fv_nodes;   /* (node id, feature index) pairs in std::map / push_back order */
+    const uint32_t* kf_fv_features;
+} orbx_bow_match_query;
+ORBX_API int orbx_search_by_bow(orbx_handle* h, int nqueries, const orbx_bow_match_query* queries, float nnratio,
+                                int check_orientation, orbx_projection_result* results);
+ORBX_API int orbx_search_by_bow_device(orbx_handle* h, int nqueries, const orbx_bow_match_query* queries, float nnratio,
+                                       int check_orientation);
+
 /* Pinned host buffers callers may fill with frames so that H2D copies are asynchronous DMA. */
 ORBX_API int orbx_alloc_host(size_t bytes, void** out);
 ORBX_API int orbx_free_host(void* p);

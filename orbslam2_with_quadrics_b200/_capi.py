@@ -26,7 +26,7 @@ SYMBOLS = [
     "orbx_extract_batch_color", "orbx_extract_device_color", "orbx_undistort_grid", "orbx_fast_stats",
     "orbx_search_by_projection", "orbx_search_by_projection_device", "orbx_search_by_projection_fetch",
     "orbx_search_local_points", "orbx_search_local_points_device",
-    "orbx_vocabulary_create", "orbx_vocabulary_destroy", "orbx_compute_bow", "orbx_compute_bow_device",
+    "orbx_search_by_bow", "orbx_search_by_bow_device", "orbx_vocabulary_create", "orbx_vocabulary_destroy", "orbx_compute_bow", "orbx_compute_bow_device",
 ]
 GRAY8, BGR8, RGB8, BGRA8, RGBA8 = range(5)
 
@@ -69,6 +69,11 @@ class OrbxLocalPointsQuery(C.Structure):
 class OrbxBowResult(C.Structure):
     _fields_ = [("n_words", C.c_int), ("word_ids", C.c_void_p), ("word_values", C.c_void_p), ("n_features", C.c_int),
                 ("fv_nodes", C.c_void_p), ("fv_features", C.c_void_p)]
+
+
+class OrbxBowMatchQuery(C.Structure):
+    _fields_ = [("cur_frame", C.c_int), ("n_kf", C.c_int), ("kf_desc", C.c_void_p), ("kf_valid", C.c_void_p), ("kf_angle", C.c_void_p),
+                ("n_kf_fv", C.c_int), ("kf_fv_nodes", C.c_void_p), ("kf_fv_features", C.c_void_p)]
 
 
 class OrbxProjectionResult(C.Structure):
@@ -139,6 +144,8 @@ def lib():
     L.orbx_search_by_projection_fetch.argtypes = [vp, i, C.POINTER(OrbxProjectionQuery), C.POINTER(OrbxProjectionResult)]
     L.orbx_search_local_points.argtypes = [vp, i, C.POINTER(OrbxLocalPointsQuery), f, f, i, C.POINTER(OrbxProjectionResult)]
     L.orbx_search_local_points_device.argtypes = [vp, i, C.POINTER(OrbxLocalPointsQuery), f, f, i]
+    L.orbx_search_by_bow.argtypes = [vp, i, C.POINTER(OrbxBowMatchQuery), f, i, C.POINTER(OrbxProjectionResult)]
+    L.orbx_search_by_bow_device.argtypes = [vp, i, C.POINTER(OrbxBowMatchQuery), f, i]
     L.orbx_vocabulary_create.argtypes = [i, i, i, vp, vp, vp, vp, vp, C.POINTER(vp)]
     L.orbx_vocabulary_destroy.argtypes = [vp]
     L.orbx_compute_bow.argtypes = [vp, vp, i, C.POINTER(i), i, C.POINTER(OrbxBowResult)]

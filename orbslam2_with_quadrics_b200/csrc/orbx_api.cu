@@ -101,6 +101,7 @@ struct orbx_handle {
     // [fv features B*kpf][counts 2B][frames B] as 32-bit words, and the word values as doubles
     unsigned *d_bow, *h_bow;
     double *d_bow_val, *h_bow_val;
+    std::vector<int> bow_slot;  // frame -> slot of the last orbx_compute_bow (-1: none)
     cudaEvent_t ev_stereo;
     int last_n;
     bool pyramid_valid;
@@ -1431,6 +1432,8 @@ static int bow_enqueue(orbx_handle* h, const orbx_vocabulary* voc, int nframes, 
     CK(h, cudaStreamSynchronize(st));
     unsigned* hf = h->h_bow + 5 * B * kpf + 2 * B;
     for (int i = 0; i < nframes; ++i) hf[i] = (unsigned)(frames ? frames[i] : i);
+    h->bow_slot.assign(B, -1);
+    for (int i = 0; i < nframes; ++i) h->bow_slot[hf[i]] = i;
     unsigned* df = h->d_bow + 5 * B * kpf + 2 * B;
     CK(h, cudaMemcpyAsync(df, hf, (size_t)nframes * 4, cudaMemcpyHostToDevice, st));
     CK(h, orbx::launch_compute_bow(h->d_plan, P, voc->d_child_start, voc->d_child_items, voc->d_desc, voc->d_weight, voc->d_word,
@@ -1469,6 +1472,80 @@ int orbx_compute_bow(orbx_handle* h, const orbx_vocabulary* voc, int nframes, co
         results[i].fv_features = h->h_bow + 4 * B * kpf + (size_t)i * kpf;
     }
     return ORBX_OK;
+}
+
+// ---- ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches), src/ORBmatcher.cc:159-288
+int orbx_search_by_bow_device(orbx_handle* h, int nq, const orbx_bow_match_query* q, float nnratio, int check_orientation) {
+    if (!h || !q || nq < 1 || nq > h->cfg.max_batch || !h->have_plan || !h->d_bow) return ORBX_ERR_BAD_ARGS;
+    const OrbxPlan& P = h->plan;
+    const size_t kpf = (size_t)P.kept_per_frame, B = (size_t)h->cfg.max_batch;
+    if (kpf > 65535) return ORBX_ERR_BAD_ARGS;
+    int cap = 4;
+    for (int i = 0; i < nq; ++i) {
+        const orbx_bow_match_query& Q = q[i];
+        if (Q.cur_frame < 0 || Q.cur_frame >= h->last_n || (size_t)Q.cur_frame >= h->bow_slot.size() || h->bow_slot[Q.cur_frame] < 0)
+            return ORBX_ERR_BAD_ARGS;                               // orbx_compute_bow has to run for the frame first (F.mFeatVec)
+        if (Q.n_kf < 0 || Q.n_kf_fv < 0 || Q.n_kf_fv > Q.n_kf) return ORBX_ERR_BAD_ARGS;
+        if (Q.n_kf && (!Q.kf_desc || !Q.kf_valid || !Q.kf_angle)) return ORBX_ERR_BAD_ARGS;
+        if (Q.n_kf_fv && (!Q.kf_fv_nodes || !Q.kf_fv_features)) return ORBX_ERR_BAD_ARGS;
+        for (int k = 0; k < Q.n_kf_fv; ++k) {
+            if (Q.kf_fv_features[k] >= (unsigned)Q.n_kf) return ORBX_ERR_BAD_ARGS;
+            if (k && Q.kf_fv_nodes[k] < Q.kf_fv_nodes[k - 1]) return ORBX_ERR_BAD_ARGS;      // std::map order
+        }
+        if (Q.n_kf > cap) cap = Q.n_kf;
+    }
+    cap = (cap + 3) & ~3;
+    CK(h, cudaSetDevice(h->cfg.device));
+    const size_t qbytes = (orbx::search_bow_query_bytes() + 15) & ~(size_t)15;
+    // staging: [queries][kf_desc nq*cap*32][kf_angle nq*cap f32][fv nodes nq*cap][fv features nq*cap][kf_valid nq*cap u8]
+    const size_t o_desc = (size_t)nq * qbytes, o_ang = o_desc + (size_t)nq * cap * 32, o_fn = o_ang + (size_t)nq * cap * 4,
+                 o_ff = o_fn + (size_t)nq * cap * 4, o_val = o_ff + (size_t)nq * cap * 4, total = o_val + (size_t)nq * cap;
+    cudaStream_t st = h->stream;
+    CK(h, cudaStreamSynchronize(st));
+    if (total > h->sp_bytes) {
+        cudaFree(h->d_sp); cudaFreeHost(h->h_sp); h->d_sp = h->h_sp = 0; h->sp_bytes = 0;
+        CK(h, cudaMalloc(&h->d_sp, total));
+        CK(h, cudaMallocHost(&h->h_sp, total));
+        h->sp_bytes = total;
+    }
+    if (!h->d_sp_out) {
+        const size_t out_ints = B * (kpf + 2);
+        CK(h, cudaMalloc(&h->d_sp_out, out_ints * 4));
+        CK(h, cudaMallocHost(&h->h_sp_out, out_ints * 4));
+        h->sp_out_ints = out_ints;
+    }
+    for (int i = 0; i < nq; ++i) {
+        const orbx_bow_match_query& Q = q[i];
+        orbx::search_bow_fill_query(h->h_sp + (size_t)i * qbytes, Q.cur_frame, h->bow_slot[Q.cur_frame], Q.n_kf, Q.n_kf_fv);
+        const size_t b = (size_t)i * cap;
+        if (Q.n_kf) {
+            memcpy(h->h_sp + o_desc + b * 32, Q.kf_desc, (size_t)Q.n_kf * 32);
+            memcpy(h->h_sp + o_ang + b * 4, Q.kf_angle, (size_t)Q.n_kf * 4);
+            memcpy(h->h_sp + o_val + b, Q.kf_valid, (size_t)Q.n_kf);
+        }
+        if (Q.n_kf_fv) {
+            memcpy(h->h_sp + o_fn + b * 4, Q.kf_fv_nodes, (size_t)Q.n_kf_fv * 4);
+            memcpy(h->h_sp + o_ff + b * 4, Q.kf_fv_features, (size_t)Q.n_kf_fv * 4);
+        }
+    }
+    CK(h, cudaMemcpyAsync(h->d_sp, h->h_sp, total, cudaMemcpyHostToDevice, st));
+    CK(h, orbx::launch_search_bow(h->d_plan, P, nq, h->d_sp, cap, nnratio, check_orientation, h->d_sp + o_desc, h->d_sp + o_val,
+                                  reinterpret_cast<const float*>(h->d_sp + o_ang), reinterpret_cast<const unsigned*>(h->d_sp + o_fn),
+                                  reinterpret_cast<const unsigned*>(h->d_sp + o_ff), h->d_out_kp, h->d_out_desc, h->d_kept_counts(),
+                                  h->d_bow + 3 * B * kpf, h->d_bow + 4 * B * kpf, reinterpret_cast<const int*>(h->d_bow + 5 * B * kpf),
+                                  h->d_sp_out, h->d_sp_out + B * kpf, st));
+    h->launches += 1;
+    return ORBX_OK;
+}
+
+int orbx_search_by_bow(orbx_handle* h, int nqueries, const orbx_bow_match_query* queries, float nnratio, int check_orientation,
+                       orbx_projection_result* results) {
+    if (!results) return ORBX_ERR_BAD_ARGS;
+    const int rc = orbx_search_by_bow_device(h, nqueries, queries, nnratio, check_orientation);
+    if (rc != ORBX_OK) return rc;
+    std::vector<int> frames(nqueries);
+    for (int i = 0; i < nqueries; ++i) frames[i] = queries[i].cur_frame;
+    return sp_fetch(h, nqueries, frames.data(), results);
 }
 
 int orbx_fast_stats(orbx_handle* h, int frame, int* candidates, int* retries) {

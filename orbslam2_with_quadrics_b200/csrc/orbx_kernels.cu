@@ -2338,6 +2338,140 @@ bow_reduce_kernel(const OrbxPlan* __restrict__ plan, BowVoc V, const int* __rest
 }
 
 // =====================================================================================
+// ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches) (src/ORBmatcher.cc:159-288): matching restricted to
+// features under the same vocabulary node.  F's FeatureVector is what orbx_compute_bow left in HBM, its descriptors and
+// angles what the extraction left; the KeyFrame side (descriptors, map-point validity, angles, FeatureVector) comes from
+// the caller.  The reference's claim rule -- a frame feature that has been matched is skipped by every later KeyFrame
+// feature (:213-214) -- only couples features of ONE node, so a warp owns a node: it walks the node's KeyFrame features
+// in order (sequential, as the reference), the lanes take the node's unclaimed frame features in parallel (8 POPC
+// each), best / second best by (distance, position) = the reference's strict "<" updates, TH_LOW and the mfNNratio
+// test (:232-236), claim.  Nodes are independent, so warps and CTAs (one per query) run concurrently.  Then the
+// rotation histogram, three maxima and culling (:240-284) as in SearchByProjection.
+// =====================================================================================
+struct BowMatchQuery {
+    int frame, slot, n_kf, n_kf_fv;
+};
+#define SB_TH_LOW 50                      // ORBmatcher::TH_LOW (src/ORBmatcher.cc:38)
+
+__global__ void __launch_bounds__(1024)
+search_bow_kernel(const OrbxPlan* __restrict__ plan, const BowMatchQuery* __restrict__ queries, int cap, float nnratio, int check_ori,
+                  const uint4* __restrict__ kf_desc, const uint8_t* __restrict__ kf_valid, const float* __restrict__ kf_angle,
+                  const unsigned* __restrict__ kf_fv_nodes, const unsigned* __restrict__ kf_fv_features,
+                  const float* __restrict__ kp, const uint8_t* __restrict__ desc, const int* __restrict__ kept_counts,
+                  const unsigned* __restrict__ f_fv_nodes, const unsigned* __restrict__ f_fv_features, const int* __restrict__ bow_counts,
+                  int* __restrict__ match_out, int* __restrict__ stats_out) {
+    extern __shared__ int sb_state[];           // per position of F's FeatureVector: -1 unclaimed, else the match's rotation bin (30: none)
+    __shared__ int s_hist[SP_HISTO];
+    __shared__ int s_nm, s_ncull;
+    __shared__ unsigned s_keep;
+    const BowMatchQuery q = queries[blockIdx.x];
+    const int kpf = plan->kept_per_frame, nl = plan->nlevels;
+    int N = 0;
+    for (int l = 0; l < nl; ++l) N += kept_counts[q.frame * nl + l];
+    const int nF = bow_counts[2 * q.slot + 1];
+    const unsigned* FN = f_fv_nodes + (size_t)q.slot * kpf;
+    const unsigned* FF = f_fv_features + (size_t)q.slot * kpf;
+    const size_t qb = (size_t)blockIdx.x * cap;
+    const uint4* KD = kf_desc + qb * 2;
+    const uint8_t* KV = kf_valid + qb;
+    const float* KA = kf_angle + qb;
+    const unsigned* KN = kf_fv_nodes + qb;
+    const unsigned* KF = kf_fv_features + qb;
+    const float* K0 = kp + (size_t)q.frame * kpf * 7;
+    const uint4* D0 = reinterpret_cast<const uint4*>(desc + (size_t)q.frame * kpf * 32);
+    int* out = match_out + (size_t)blockIdx.x * kpf;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+
+    for (int p = threadIdx.x; p < kpf; p += blockDim.x) sb_state[p] = -1;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) out[k] = -1;            // vector<MapPoint*>(F.N, NULL) (:163)
+    if (threadIdx.x < SP_HISTO) s_hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { s_nm = 0; s_ncull = 0; s_keep = 0xffffffffu; }
+    __syncthreads();
+
+    int nm = 0;
+    for (int i = warp; i < q.n_kf_fv; i += nwarps) {
+        const unsigned node = KN[i];
+        if (i > 0 && KN[i - 1] == node) continue;                             // not the head of a node's run
+        int lo = 0, hi = nF;                                                   // lower_bound of the node in F's FeatureVector
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (FN[mid] < node) lo = mid + 1; else hi = mid; }
+        const int a = lo;
+        if (a >= nF || FN[a] != node) continue;                                // (:275-282) no common node
+        hi = nF;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (FN[mid] <= node) lo = mid + 1; else hi = mid; }
+        const int b = lo;
+        for (int j = i; j < q.n_kf_fv && KN[j] == node; ++j) {
+            const int ikf = (int)KF[j];
+            if (KV[ikf] != 1) continue;                                        // no map point, or a bad one (:196-202)
+            const uint4 qa = KD[2 * ikf], qc = KD[2 * ikf + 1];
+            unsigned best = 0xffffffffu, best2 = 0xffffffffu;
+            for (int pb = a; pb < b; pb += 32) {
+                const int p = pb + lane;
+                unsigned key = 0xffffffffu;
+                if (p < b && sb_state[p] < 0) {                                // vpMapPointMatches[realIdxF] still NULL (:213-214)
+                    const unsigned k = FF[p];
+                    const uint4 da = D0[2 * (size_t)k], dc = D0[2 * (size_t)k + 1];
+                    const unsigned dist = __popc(qa.x ^ da.x) + __popc(qa.y ^ da.y) + __popc(qa.z ^ da.z) + __popc(qa.w ^ da.w) +
+                                          __popc(qc.x ^ dc.x) + __popc(qc.y ^ dc.y) + __popc(qc.z ^ dc.z) + __popc(qc.w ^ dc.w);
+                    key = (dist << 16) | (unsigned)p;
+                }
+                best2 = min(best2, max(best, key));
+                best = min(best, key);
+            }
+            const unsigned m1 = __reduce_min_sync(0xffffffffu, best);
+            const unsigned m2 = __reduce_min_sync(0xffffffffu, best == m1 ? best2 : best);
+            if (m1 != 0xffffffffu) {
+                const unsigned d1 = m1 >> 16, d2 = m2 == 0xffffffffu ? 256u : (m2 >> 16);
+                if (d1 <= SB_TH_LOW && (float)d1 < __fmul_rn(nnratio, (float)d2)) {     // (:232-236)
+                    const int p1 = (int)(m1 & 0xffffu);
+                    const int iF = (int)FF[p1];
+                    const int bin = check_ori ? sp_rot_bin(KA[ikf], K0[(size_t)iF * 7 + 3]) : SP_HISTO;
+                    if (lane == 0) {
+                        sb_state[p1] = bin;
+                        out[iF] = ikf;
+                        if (check_ori) atomicAdd(&s_hist[bin], 1);
+                        ++nm;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && nm) atomicAdd(&s_nm, nm);
+    __syncthreads();
+    if (check_ori) {
+        if (threadIdx.x == 0) {
+            int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+            for (int b = 0; b < SP_HISTO; ++b) {
+                const int s = s_hist[b];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = b; }
+                else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = b; }
+                else if (s > max3) { max3 = s; ind3 = b; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+            unsigned keep = 0;
+            if (ind1 >= 0) keep |= 1u << ind1;
+            if (ind2 >= 0) keep |= 1u << ind2;
+            if (ind3 >= 0) keep |= 1u << ind3;
+            s_keep = keep;
+        }
+        __syncthreads();
+        const unsigned keep = s_keep;
+        int culled = 0;
+        for (int p = threadIdx.x; p < nF; p += blockDim.x) {
+            const int bin = sb_state[p];
+            if (bin >= 0 && bin < SP_HISTO && !((keep >> bin) & 1u)) { out[FF[p]] = -1; ++culled; }     // (:273-281)
+        }
+        if (culled) atomicAdd(&s_ncull, culled);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        stats_out[2 * blockIdx.x] = s_nm - s_ncull;
+        stats_out[2 * blockIdx.x + 1] = 1;
+    }
+}
+
+// =====================================================================================
 // launch wrappers (called from orbx_api.cu)
 // =====================================================================================
 // format: 1 BGR8, 2 RGB8, 3 BGRA8, 4 RGBA8 (orbx_pixel_format)
@@ -2663,6 +2797,24 @@ cudaError_t launch_compute_bow(const OrbxPlan* d_plan, const OrbxPlan& hp, const
     }
     return launch_k(bow_reduce_kernel, dim3((unsigned)nframes), dim3(1024), smem, st, d_plan, V, d_frames, sort_n, kept_counts,
                     (const int*)leaf, (const int*)nid, word_ids, word_values, fv_nodes, fv_features, counts_out);
+}
+
+size_t search_bow_query_bytes() { return sizeof(BowMatchQuery); }
+void search_bow_fill_query(void* dst, int frame, int slot, int n_kf, int n_kf_fv) {
+    BowMatchQuery q;
+    q.frame = frame; q.slot = slot; q.n_kf = n_kf; q.n_kf_fv = n_kf_fv;
+    memcpy(dst, &q, sizeof q);
+}
+
+cudaError_t launch_search_bow(const OrbxPlan* d_plan, const OrbxPlan& hp, int nq, const void* d_queries, int cap, float nnratio,
+                              int check_ori, const uint8_t* kf_desc, const uint8_t* kf_valid, const float* kf_angle,
+                              const unsigned* kf_fv_nodes, const unsigned* kf_fv_features, const float* kp, const uint8_t* desc,
+                              const int* kept_counts, const unsigned* f_fv_nodes, const unsigned* f_fv_features, const int* bow_counts,
+                              int* match_out, int* stats_out, cudaStream_t st) {
+    const size_t smem = (size_t)hp.kept_per_frame * sizeof(int);
+    return launch_k(search_bow_kernel, dim3((unsigned)nq), dim3(1024), smem, st, d_plan, (const BowMatchQuery*)d_queries, cap, nnratio,
+                    check_ori, (const uint4*)kf_desc, kf_valid, kf_angle, kf_fv_nodes, kf_fv_features, kp, desc, kept_counts, f_fv_nodes,
+                    f_fv_features, bow_counts, match_out, stats_out);
 }
 
 size_t stereo_bucket_entries(const OrbxPlan& hp) { return (size_t)hp.kept_per_frame * ST_MAX_SPAN; }

@@ -59,6 +59,13 @@ cudaError_t launch_compute_bow(const OrbxPlan* d_plan, const OrbxPlan& hp, const
                                const int* d_frames, int nframes, int levelsup, const uint8_t* desc, const int* kept_counts, int* leaf,
                                int* nid, unsigned* word_ids, double* word_values, unsigned* fv_nodes, unsigned* fv_features,
                                int* counts_out, cudaStream_t st);
+size_t search_bow_query_bytes();
+void search_bow_fill_query(void* dst, int frame, int slot, int n_kf, int n_kf_fv);
+cudaError_t launch_search_bow(const OrbxPlan* d_plan, const OrbxPlan& hp, int nq, const void* d_queries, int cap, float nnratio,
+                              int check_ori, const uint8_t* kf_desc, const uint8_t* kf_valid, const float* kf_angle,
+                              const unsigned* kf_fv_nodes, const unsigned* kf_fv_features, const float* kp, const uint8_t* desc,
+                              const int* kept_counts, const unsigned* f_fv_nodes, const unsigned* f_fv_features, const int* bow_counts,
+                              int* match_out, int* stats_out, cudaStream_t st);
 size_t stereo_bucket_entries(const OrbxPlan& hp);     // uint16 entries of one right frame's row table
 
 // Frame::UndistortKeyPoints + AssignFeaturesToGrid (src/Frame.cc:404-434, :230-245) on the device-resident keypoints

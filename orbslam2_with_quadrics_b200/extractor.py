@@ -343,6 +343,32 @@ class ORBextractor:
         n = len(frames)
         check(self._L.orbx_compute_bow_device(self._h, voc._v, n, (C.c_int * n)(*frames), levelsup), self._h)
 
+    # ---------------------------------------------------------------- ORBmatcher::SearchByBoW(KeyFrame*, Frame&)
+    def _bow_queries(self, queries):
+        qs = (_capi.OrbxBowMatchQuery * len(queries))()
+        keep = []
+        for q, d in zip(qs, queries):
+            a = dict(desc=np.ascontiguousarray(d["kf_desc"], np.uint8), valid=np.ascontiguousarray(d["kf_valid"], np.uint8),
+                     angle=np.ascontiguousarray(d["kf_angle"], np.float32), fn=np.ascontiguousarray(d["kf_fv_nodes"], np.uint32),
+                     ff=np.ascontiguousarray(d["kf_fv_features"], np.uint32))
+            keep.append(a)
+            q.cur_frame, q.n_kf, q.n_kf_fv = int(d.get("cur_frame", 0)), len(a["valid"]), len(a["fn"])
+            q.kf_desc, q.kf_valid, q.kf_angle = a["desc"].ctypes.data, a["valid"].ctypes.data, a["angle"].ctypes.data
+            q.kf_fv_nodes, q.kf_fv_features = a["fn"].ctypes.data, a["ff"].ctypes.data
+        return qs, keep
+
+    def search_by_bow(self, queries, nnratio: float = 0.7, check_orientation: bool = True):
+        """(src/ORBmatcher.cc:159-288) for each query (dicts with cur_frame, kf_desc, kf_valid, kf_angle, kf_fv_nodes,
+        kf_fv_features) against the frame's FeatureVector of the last compute_bow.  Returns [(nmatches, match int32[N])]."""
+        qs, keep = self._bow_queries(queries)
+        res = (_capi.OrbxProjectionResult * len(queries))()
+        check(self._L.orbx_search_by_bow(self._h, len(queries), qs, nnratio, int(check_orientation), res), self._h)
+        out = []
+        for r in res:
+            out.append((r.nmatches, np.ctypeslib.as_array(C.cast(r.match, C.POINTER(C.c_int32)), shape=(max(r.n, 1),))[:r.n].copy()))
+        del keep
+        return out
+
     # ---------------------------------------------------------------- stage dumps (parity tests)
     def stage_dump(self, frame: int, level: int, stage: int):
         nbytes = C.c_size_t()

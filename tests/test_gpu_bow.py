@@ -111,3 +111,54 @@ def test_orbvoc_shape_1080p_4k_timing_and_bad_arguments():
     bad["child_items"][0] = bad["child_items"][1]                                  # a node listed twice
     with pytest.raises(OrbxError):
         Vocabulary(bad)
+
+
+# ----------------------------------------------------------------------------- SearchByBoW(KeyFrame*, Frame&) (:159-288)
+def test_search_by_bow_matches_oracle_and_golden():
+    import importlib.util
+    from oracle import match_oracle
+    from orbslam2_with_quadrics_b200 import match_cases as mc
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_match_golden", os.path.join(here, "golden", "make_match_golden.py"))
+    mmg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mmg)
+    gold = json.load(open(os.path.join(here, "golden", "match_golden.json")))
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["mono_tum"]
+    gx = ORBextractor(nf, sf, nl, it, mt, max_batch=3)
+    # frame 1 of the batch is the golden scenarios' frame (seed 77): the chain extract -> compute_bow -> search lands on
+    # the digests made by the reference's own lines
+    res = gx.extract_batch([fr.cluttered_scene(w, h, 5), fr.cluttered_scene(w, h, 77), fr.cluttered_scene(w, h, 6)])
+    cf = dict(desc=res[1][1], cur_angle=res[1][0]["angle"].astype(np.float32))
+    with pytest.raises(OrbxError):
+        gx.search_by_bow([dict(cur_frame=1, kf_desc=np.zeros((4, 32)), kf_valid=[1] * 4, kf_angle=[0.0] * 4, kf_fv_nodes=[1],
+                               kf_fv_features=[0])])                                     # no FeatureVector yet
+    for case in mmg.BOW_CASES:
+        voc, sc = mmg.bow_scenario(cf, case)
+        gv = Vocabulary(voc)
+        gx.compute_bow(gv, frames=[2, 1], levelsup=case[2])                               # frame 1 sits in slot 1 of this call
+        q = dict(cur_frame=1, **{k: sc[k] for k in ("kf_desc", "kf_valid", "kf_angle", "kf_fv_nodes", "kf_fv_features")})
+        (n, m), = gx.search_by_bow([q], case[5], case[6])
+        assert mmg.bow_digest(sc, n, m) == gold[mmg.bow_key(case)]
+        gv.close()
+    # a batch of different KeyFrames against different frames, one vocabulary
+    voc = vc.random_vocabulary(10, 4, seed=9)
+    gv = Vocabulary(voc)
+    bows = gx.compute_bow(gv, levelsup=2)
+    rng = np.random.default_rng(3)
+    qs, scs = [], []
+    for f, n_kf in ((2, 1800), (0, 600), (1, 1100)):
+        kf = mc.make_keyframe(rng, res[f][1], res[f][0]["angle"].astype(np.float32), n_kf)
+        _, _, kn, kfeat = bow_oracle.transform(voc, kf["kf_desc"], 2)
+        qs.append(dict(cur_frame=f, kf_fv_nodes=kn, kf_fv_features=kfeat, **kf))
+    for ratio, ori in ((0.7, True), (0.75, False), (0.9, True)):
+        out = gx.search_by_bow(qs, ratio, ori)
+        for q, (n, m) in zip(qs, out):
+            f = q["cur_frame"]
+            n0, m0 = match_oracle.search_by_bow(q["kf_desc"], q["kf_valid"], q["kf_angle"], q["kf_fv_nodes"], q["kf_fv_features"],
+                                                res[f][1], res[f][0]["angle"].astype(np.float32), bows[f][2], bows[f][3], ratio, ori)
+            assert n == n0 and np.array_equal(m, m0) and n > 0.15 * len(q["kf_valid"])
+    bad = dict(qs[0]); bad["kf_fv_nodes"] = bad["kf_fv_nodes"][::-1].copy()
+    with pytest.raises(OrbxError):
+        gx.search_by_bow([bad])                                                           # not in map order
+    gv.close()
+    gx.close()
