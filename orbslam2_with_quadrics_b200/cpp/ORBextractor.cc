@@ -245,4 +245,29 @@ void ORBextractor::ComputeBoW(const orbx_vocabulary* voc, std::vector<std::pair<
     for (int i = 0; i < r.n_features; ++i) featVec[i] = std::make_pair(r.fv_nodes[i], r.fv_features[i]);
 }
 
+int ORBextractor::SearchByBoW(const std::vector<unsigned char>& kfDescriptors, const std::vector<unsigned char>& kfValid,
+                              const std::vector<float>& kfAngles, const std::vector<std::pair<unsigned int, unsigned int> >& kfFeatVec,
+                              float nnRatio, bool checkOrientation, std::vector<int>& matchedKF)
+{
+    const size_t n = kfValid.size();
+    if (kfDescriptors.size() != 32 * n || kfAngles.size() != n)
+        throw std::runtime_error("ORBextractor (orbx): SearchByBoW needs 32 bytes, one flag and one angle per KeyFrame feature");
+    std::vector<uint32_t> nodes(kfFeatVec.size()), feats(kfFeatVec.size());
+    for (size_t i = 0; i < kfFeatVec.size(); ++i) { nodes[i] = kfFeatVec[i].first; feats[i] = kfFeatVec[i].second; }
+    orbx_bow_match_query q;
+    q.cur_frame = 0;
+    q.n_kf = (int)n;
+    q.kf_desc = kfDescriptors.data();
+    q.kf_valid = kfValid.data();
+    q.kf_angle = kfAngles.data();
+    q.n_kf_fv = (int)nodes.size();
+    q.kf_fv_nodes = nodes.data();
+    q.kf_fv_features = feats.data();
+    orbx_projection_result r;
+    int rc = orbx_search_by_bow(handle_, 1, &q, nnRatio, checkOrientation ? 1 : 0, &r);
+    if (rc != ORBX_OK) orbx_throw(handle_, rc, "orbx_search_by_bow");
+    matchedKF.assign(r.match, r.match + r.n);
+    return r.nmatches;
+}
+
 } //namespace ORB_SLAM

@@ -111,6 +111,14 @@ public:
     void ComputeBoW(const orbx_vocabulary* voc, std::vector<std::pair<unsigned int, double> >& bow,
                     std::vector<std::pair<unsigned int, unsigned int> >& featVec, int levelsup = 4);
 
+    // ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches) (reference src/ORBmatcher.cc:159-288) on the GPU;
+    // `this` is F.mpORBextractorLeft after ComputeBoW.  KeyFrame side: descriptors (32 bytes per feature), validity
+    // (0 = no map point, 1 = good, 2 = isBad()), pKF->mvKeysUn angles, and pKF->mFeatVec as (node, feature) pairs in map
+    // order.  matchedKF[iF] = KeyFrame feature whose map point vpMapPointMatches[iF] receives, -1 = NULL.  Returns nmatches.
+    int SearchByBoW(const std::vector<unsigned char>& kfDescriptors, const std::vector<unsigned char>& kfValid,
+                    const std::vector<float>& kfAngles, const std::vector<std::pair<unsigned int, unsigned int> >& kfFeatVec,
+                    float nnRatio, bool checkOrientation, std::vector<int>& matchedKF);
+
 private:
     ORBextractor(const ORBextractor&);
     ORBextractor& operator=(const ORBextractor&);

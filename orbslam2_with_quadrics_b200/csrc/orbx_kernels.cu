@@ -2399,17 +2399,24 @@ search_bow_kernel(const OrbxPlan* __restrict__ plan, const BowMatchQuery* __rest
         hi = nF;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (FN[mid] <= node) lo = mid + 1; else hi = mid; }
         const int b = lo;
+        // each lane keeps the descriptor of its first frame feature of the node in registers for the whole run (nodes rarely
+        // hold more than 32 frame features), and the next KeyFrame descriptor is requested before the current one is used
+        uint4 ca = make_uint4(0, 0, 0, 0), cc = ca;
+        if (a + lane < b) { const unsigned k = FF[a + lane]; ca = D0[2 * (size_t)k]; cc = D0[2 * (size_t)k + 1]; }
+        int ikf_n = (int)KF[i];
+        uint4 na = KD[2 * ikf_n], nc = KD[2 * ikf_n + 1];
         for (int j = i; j < q.n_kf_fv && KN[j] == node; ++j) {
-            const int ikf = (int)KF[j];
+            const int ikf = ikf_n;
+            const uint4 qa = na, qc = nc;
+            if (j + 1 < q.n_kf_fv) { ikf_n = (int)KF[j + 1]; na = KD[2 * ikf_n]; nc = KD[2 * ikf_n + 1]; }
             if (KV[ikf] != 1) continue;                                        // no map point, or a bad one (:196-202)
-            const uint4 qa = KD[2 * ikf], qc = KD[2 * ikf + 1];
             unsigned best = 0xffffffffu, best2 = 0xffffffffu;
             for (int pb = a; pb < b; pb += 32) {
                 const int p = pb + lane;
                 unsigned key = 0xffffffffu;
                 if (p < b && sb_state[p] < 0) {                                // vpMapPointMatches[realIdxF] still NULL (:213-214)
-                    const unsigned k = FF[p];
-                    const uint4 da = D0[2 * (size_t)k], dc = D0[2 * (size_t)k + 1];
+                    uint4 da = ca, dc = cc;
+                    if (pb != a) { const unsigned k = FF[p]; da = D0[2 * (size_t)k]; dc = D0[2 * (size_t)k + 1]; }
                     const unsigned dist = __popc(qa.x ^ da.x) + __popc(qa.y ^ da.y) + __popc(qa.z ^ da.z) + __popc(qa.w ^ da.w) +
                                           __popc(qc.x ^ dc.x) + __popc(qc.y ^ dc.y) + __popc(qc.z ^ dc.z) + __popc(qc.w ^ dc.w);
                     key = (dist << 16) | (unsigned)p;

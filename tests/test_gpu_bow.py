@@ -162,3 +162,69 @@ def test_search_by_bow_matches_oracle_and_golden():
         gx.search_by_bow([bad])                                                           # not in map order
     gv.close()
     gx.close()
+
+
+def test_search_by_bow_timing_report():
+    """Measurement of the row: 16 KeyFrame/Frame pairs at 1080p (2000 features each side, 10^6-word vocabulary, nodes at
+    level 2), device time per batch (CUDA events, staging upload included), C-ABI end to end, and the reference's own
+    lines on one host thread."""
+    import ctypes as C
+    import torch
+    from oracle import match_oracle
+    from orbslam2_with_quadrics_b200 import _capi
+    from orbslam2_with_quadrics_b200 import match_cases as mc
+    voc = vc.random_vocabulary(10, 6, seed=1)
+    gv = Vocabulary(voc)
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["rgbd_1080p"]
+    B = 16
+    gx = ORBextractor(nf, sf, nl, it, mt, max_batch=B, download_pyramid=False)
+    imgs = [fr.cluttered_scene(w, h, 3100 + i) for i in range(4)]
+    res = gx.extract_batch([imgs[i % 4] for i in range(B)])
+    bows = gx.compute_bow(gv)
+    rng = np.random.default_rng(1)
+    qs = []
+    for f in range(B):
+        kf = mc.make_keyframe(rng, res[f][1], res[f][0]["angle"].astype(np.float32), len(res[f][1]))
+        if f < 4:
+            _, _, kn, kfeat = bow_oracle.transform(voc, kf["kf_desc"], 4)
+            qs.append(dict(cur_frame=f, kf_fv_nodes=kn, kf_fv_features=kfeat, **kf))
+        else:
+            qs.append(dict(qs[f % 4], cur_frame=f))
+    out = gx.search_by_bow(qs, 0.7, True)
+    cq, keep = gx._bow_queries(qs)
+    cres = (_capi.OrbxProjectionResult * B)()
+    st = torch.cuda.ExternalStream(gx.stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        _capi.check(gx._L.orbx_search_by_bow_device(gx._h, B, cq, 0.7, 1), gx._h)
+    gx.synchronize()
+    K = 20
+    e0.record(st)
+    for _ in range(K):
+        _capi.check(gx._L.orbx_search_by_bow_device(gx._h, B, cq, 0.7, 1), gx._h)
+    e1.record(st)
+    gx.synchronize()
+    dev_ms = e0.elapsed_time(e1) / K
+    t0 = time.perf_counter()
+    for _ in range(K):
+        _capi.check(gx._L.orbx_search_by_bow(gx._h, B, cq, 0.7, 1, cres), gx._h)
+    e2e_ms = (time.perf_counter() - t0) / K * 1e3
+    cpu_ms = None
+    if match_oracle.ref_available():
+        t0 = time.perf_counter()
+        for q, (n, m) in zip(qs[:4], out[:4]):
+            f = q["cur_frame"]
+            n0, m0 = match_oracle.ref_search_by_bow(q["kf_desc"], q["kf_valid"], q["kf_angle"], q["kf_fv_nodes"], q["kf_fv_features"],
+                                                    res[f][1], res[f][0]["angle"].astype(np.float32), bows[f][2], bows[f][3], 0.7, True)
+            assert n == n0 and np.array_equal(m, m0)
+        cpu_ms = (time.perf_counter() - t0) / 4 * 1e3
+    rep = {"workload": "SearchByBoW, %d KeyFrame/Frame pairs, ~%d features per side, %d common nodes" % (
+               B, len(res[0][1]), len(set(bows[0][2].tolist()))), "device_ms_per_batch_incl_staging_h2d": dev_ms,
+           "device_us_per_pair": dev_ms / B * 1e3, "e2e_ms_per_batch_with_d2h": e2e_ms, "e2e_us_per_pair": e2e_ms / B * 1e3,
+           "reference_lines_cpu_ms_per_pair_1_thread_incl_stub_setup": cpu_ms, "nmatches": [n for n, _ in out[:4]]}
+    print(json.dumps(rep))
+    if os.path.isdir("gpurun_out"):
+        json.dump(rep, open("gpurun_out/r01_search_by_bow.json", "w"), indent=1)
+    del keep
+    gv.close()
+    gx.close()
