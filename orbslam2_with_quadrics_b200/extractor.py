@@ -298,9 +298,7 @@ class ORBextractor:
                                                        int(check_orientation), int(use_stereo)), self._h)
 
     # ---------------------------------------------------------------- ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th)
-    def search_local_points(self, queries, th: float, nnratio: float = 0.8, use_stereo: bool = False):
-        """(src/ORBmatcher.cc:45-129) for each query: dicts with cur_frame, in_view, proj_x, proj_y, proj_xr, scale_level,
-        view_cos, mp_desc, mp_obs, cur_obs (or None).  Returns [(nmatches, new_match int32[N], rounds)]."""
+    def _local_queries(self, queries):
         qs = (_capi.OrbxLocalPointsQuery * len(queries))()
         keep = []
         for q, d in zip(qs, queries):
@@ -314,6 +312,12 @@ class ORBextractor:
             q.in_view, q.proj_xy_xr, q.scale_level = a["in_view"].ctypes.data, a["w3"].ctypes.data, a["lvl"].ctypes.data
             q.view_cos, q.mp_desc, q.mp_obs = a["vc"].ctypes.data, a["desc"].ctypes.data, a["obs"].ctypes.data
             q.cur_obs = None if co is None else co.ctypes.data
+        return qs, keep
+
+    def search_local_points(self, queries, th: float, nnratio: float = 0.8, use_stereo: bool = False):
+        """(src/ORBmatcher.cc:45-129) for each query: dicts with cur_frame, in_view, proj_x, proj_y, proj_xr, scale_level,
+        view_cos, mp_desc, mp_obs, cur_obs (or None).  Returns [(nmatches, new_match int32[N], rounds)]."""
+        qs, keep = self._local_queries(queries)
         res = (_capi.OrbxProjectionResult * len(queries))()
         check(self._L.orbx_search_local_points(self._h, len(queries), qs, th, nnratio, int(use_stereo), res), self._h)
         out = []
