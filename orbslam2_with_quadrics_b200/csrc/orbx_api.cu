@@ -385,6 +385,7 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
 }
 
 void free_geometry(orbx_handle* h) {
+    h->bow_slot.clear();
     for (size_t i = 0; i < h->graphs.size(); ++i)
         if (h->graphs[i].exec) cudaGraphExecDestroy(h->graphs[i].exec);
     h->graphs.clear();
