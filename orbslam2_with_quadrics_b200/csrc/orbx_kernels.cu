@@ -2264,6 +2264,10 @@ bow_reduce_kernel(const OrbxPlan* __restrict__ plan, BowVoc V, const int* __rest
     const int fi = blockIdx.x, f = frames[fi];
     int N = 0;
     for (int l = 0; l < nl; ++l) N += kept_counts[f * nl + l];
+    // sort only as many slots as this frame needs (kept_per_frame is often just above a power of two)
+    int need = 32;
+    while (need < N) need <<= 1;
+    sort_n = min(sort_n, need);
     const int* leaf = leaf_in + (size_t)fi * kpf;
     const int* nid = nid_in + (size_t)fi * kpf;
     unsigned* wid = word_ids + (size_t)fi * kpf;
