@@ -30,7 +30,11 @@ D = (0.05, -0.11, 0.0004, -0.0003, 0.02)
 gx = ORBextractor(nf, sf, nl, it, mt, max_batch=B, download_pyramid=False)
 gv = Vocabulary(vc.random_vocabulary(10, 6, seed=1))
 imgs = [fr.cluttered_scene(w, h, 4000 + i) for i in range(4)]
-batch = [imgs[i % 4] for i in range(B)]
+import torch
+pinned = torch.empty((B, h, w), dtype=torch.uint8).pin_memory()          # host frames in pinned memory, as bench.py's e2e leg
+for i in range(B):
+    pinned[i].copy_(torch.from_numpy(imgs[i % 4]))
+batch = [pinned[i].numpy() for i in range(B)]
 res = gx.extract_batch(batch)
 grids = gx.undistort_grid(K4, D)
 rng = np.random.default_rng(5)
@@ -79,6 +83,20 @@ for label, fn in (("extraction_only", extraction_only), ("extraction_plus_consum
         fn()
     dt = (time.perf_counter() - t0) / K
     out[label] = {"ms_per_step": dt * 1e3, "frames_per_s": B / dt}
+# each consumer alone (after one extraction), same calls
+extraction_only()
+parts = {"orbx_undistort_grid": lambda: _capi.check(L.orbx_undistort_grid(H, n, None, k4, dd, len(D), gres), H),
+         "orbx_search_by_projection": lambda: _capi.check(L.orbx_search_by_projection(H, n, pq, k4, 0.0, 0.0, 15.0, 1, 1, 0, pres), H),
+         "orbx_search_local_points": lambda: _capi.check(L.orbx_search_local_points(H, n, lq, 3.0, 0.8, 0, pres), H),
+         "orbx_compute_bow": lambda: _capi.check(L.orbx_compute_bow(H, gv._v, n, None, 4, bres), H)}
+out["per_consumer_ms_per_step"] = {}
+for label, fn in parts.items():
+    for _ in range(3):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        fn()
+    out["per_consumer_ms_per_step"][label] = (time.perf_counter() - t0) / K * 1e3
 out["config"] = {"workload": name, "frames_per_step": B, "steps": K, "host_threads": 1,
                  "consumers": ["orbx_undistort_grid", "orbx_search_by_projection (N map points per frame)",
                                "orbx_search_local_points (2N map points per frame)", "orbx_compute_bow (10^6-word tree)"],
