@@ -1193,6 +1193,8 @@ int sp_enqueue(orbx_handle* h, int local, int nq, const SpHostQuery* q, const fl
                  staged = o_cur + (local ? (size_t)nq * kpf * 4 : 0), o_cnt = (staged + 15) & ~(size_t)15,
                  o_list = o_cnt + (size_t)nq * cap * 4, total = o_list + (size_t)nq * cap * 32 * 4;
     cudaStream_t st = h->stream;
+    if (local)                                                       // F.N of the frames (cur_obs is sized by it), whatever was fetched so far
+        CK(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int) * h->counters_count(), cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));                                // the staging of a previous call is free
     if (total > h->sp_bytes) {
         cudaFree(h->d_sp); cudaFreeHost(h->h_sp); h->d_sp = h->h_sp = 0; h->sp_bytes = 0;
