@@ -313,3 +313,25 @@ def test_local_points_stereo_frame_and_golden():
         n1, _ = local_oracle(q, res[0][0], res[0][1], grids[0], gx.GetScaleFactors(), th, 0.8, None)
         assert n1 != n0                                                    # the mvuRight test changed the outcome
     gx.close()
+
+
+def test_4k_local_points_with_large_shared_memory():
+    """More map points than fit the default 48 KB of dynamic shared memory ((points + keypoint slots) * 4 B): the opt-in
+    attribute path of both template instantiations."""
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["mono_4k"]
+    K4, D = (3100.0, 3098.0, 1915.5, 1082.25), (0.12, -0.31, 0.0007, -0.0004, 0.09)
+    gx = ORBextractor(nf, sf, nl, it, mt)
+    kps, desc = gx(fr.cluttered_scene(w, h, 10))
+    (grid,) = gx.undistort_grid(K4, D)
+    rng = np.random.default_rng(6)
+    octv = kps["octave"].astype(np.int32)
+    lp = mc.make_local_points(rng, grid[0], octv, desc, 12000, nl)
+    q = dict(cur_frame=0, **lp)
+    (n, m, _), = gx.search_local_points([q], 3.0)
+    n0, m0 = local_oracle(q, kps, desc, grid, gx.GetScaleFactors(), 3.0, 0.8, None)
+    assert n == n0 and np.array_equal(m, m0) and n > 1500
+    q2 = build_query(rng, 0, kps, desc, grid, K4, 11000, nl, "still")
+    (n, m, _), = gx.search_by_projection([q2], K4, 0.0, 0.0, 15.0, True)
+    n0, m0 = oracle_result(q2, kps, desc, grid, K4, 0.0, 0.0, gx.GetScaleFactors(), 15.0, True, True, None)
+    assert n == n0 and np.array_equal(m, m0)
+    gx.close()
