@@ -11,6 +11,7 @@
 
 #include <string>
 #include <new>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/orbx.h"
@@ -340,29 +341,52 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
     P->node_cap = round_up(P->node_cap, 32);
     if (P->max_cell_w < 7) P->max_cell_w = 7;
     if (P->max_cell_h < 7) P->max_cell_h = 7;
-    // FAST tiling: NC cells per TMA tile, NB tile buffers per warp, W warps per CTA (env overrides are for tuning runs)
+    // FAST tiling (env overrides are for tuning / A-B runs).  Product: fast_strips_kernel, a warp takes a strip of up to 4
+    // cells whose scoring pixels fit the 32 word columns of its lanes (wCell <= 31: 4 cells, 32: 3), single tile buffer.
+    // ORBX_FAST_LEGACY=1: fast_cells_kernel (round 1), 2 cells per tile (1 for latency-mode handles), NB tile buffers.
     const char* e_nc = getenv("ORBX_FAST_NC"); const char* e_nb = getenv("ORBX_FAST_NB"); const char* e_w = getenv("ORBX_FAST_WARPS");
-    // measured best on B200 at batched 1080p: 2 cells per tile, single buffer, 8 warps.  A latency-mode handle (max_batch
-    // <= 2: the C++ adapter, one frame or one stereo pair per call) has fewer strips than resident warps, so one cell per
-    // tile halves the longest per-warp chain: single frame 640x480 0.090 -> 0.074 ms, 1080p 0.115 -> 0.111 ms
-    P->fast_nc = e_nc ? atoi(e_nc) : (h->cfg.max_batch <= 2 ? 1 : 2);
-    P->fast_nb = e_nb ? atoi(e_nb) : 1;
+    const char* e_q = getenv("ORBX_FAST_QCAP");
+    P->fast_legacy = getenv("ORBX_FAST_LEGACY") != nullptr;
+    P->fast_nc = e_nc ? atoi(e_nc) : (P->fast_legacy ? (h->cfg.max_batch <= 2 ? 1 : 2) : 4);
+    P->fast_nb = (e_nb && P->fast_legacy) ? atoi(e_nb) : 1;
     P->fast_warps = e_w ? atoi(e_w) : 8;
-    if (P->fast_nc < 1 || P->fast_nc > 8 || P->fast_nb < 1 || P->fast_nb > 2 || P->fast_warps < 1 || P->fast_warps > ORBX_FAST_WARPS)
+    if (P->fast_nc < 1 || P->fast_nc > (P->fast_legacy ? 8 : 4) || P->fast_nb < 1 || P->fast_nb > 2 || P->fast_warps < 1 ||
+        P->fast_warps > ORBX_FAST_WARPS)
         return ORBX_ERR_BAD_ARGS;
-    int max_wcell = 0, strips = 0;
+    int strips = 0, bw = 0, sp = P->max_cell_w;
     for (int l = 0; l < n; ++l) {
         OrbxLevel& L = P->lv[l];
-        if (L.wCell > max_wcell) max_wcell = L.wCell;
+        L.wcell_recip = 65536 / L.wCell + 1;
+        L.strip_ok = !P->fast_legacy && L.wCell <= 32 && L.hCell <= 32;
+        L.strip_nc = P->fast_legacy ? P->fast_nc : (L.strip_ok ? std::max(1, std::min(P->fast_nc, 125 / L.wCell)) : 1);
         L.strip_base = strips;
-        L.strips_x = (L.nColsV + P->fast_nc - 1) / P->fast_nc;
+        L.strips_x = (L.nColsV + L.strip_nc - 1) / L.strip_nc;
         strips += L.strips_x * L.nRowsV;
+        // 16-aligned TMA start (delta <= 15), 1-byte shift, the strip's cell steps + the 6-px overlap, 2 words of read-ahead
+        bw = std::max(bw, L.strip_nc * L.wCell + 6 + 24);
+        if (L.strip_ok) sp = std::max(sp, L.strip_nc * (L.wCell + 2));
     }
     P->strips_per_frame = strips;
-    // 16-aligned TMA start (delta <= 15), 1-byte shift, NC cell steps + the 6-px overlap, 2 words of read-ahead
-    P->fast_bw = round_up((P->fast_nc - 1) * max_wcell + P->max_cell_w + 24, 16);
+    {   // strip table of a frame, stored behind the resize tap tables (8-byte units)
+        std::vector<uint32_t> tab;
+        for (int l = 0; l < n; ++l)
+            for (int i = 0; i < P->lv[l].nRowsV; ++i)
+                for (int j = 0; j < P->lv[l].strips_x; ++j)
+                    tab.push_back((uint32_t)l | ((uint32_t)i << 4) | ((uint32_t)(j * P->lv[l].strip_nc) << 16));
+        if (tab.size() & 1) tab.push_back(0);
+        P->strip_tab_off = (int)taps->size();
+        const OrbxTap* raw = reinterpret_cast<const OrbxTap*>(tab.data());
+        taps->insert(taps->end(), raw, raw + tab.size() / 2);
+    }
+    P->fast_bw = round_up(bw, 16);
+    if (!P->fast_legacy) P->fast_bw = P->fast_bw <= 96 ? 96 : P->fast_bw <= 128 ? 128 : P->fast_bw <= 160 ? 160 : P->fast_bw;
     P->fast_bh = P->max_cell_h;
+    P->fast_sp = round_up(sp, 4);
+    // survivor queue of a strip; its halves are the private queues of the two warps that redo single cells (<= 32 x 32 pixels)
+    P->fast_qcap = std::max(e_q ? atoi(e_q) : 2048, std::max(2048, (P->max_cell_w - 6) * (P->max_cell_h - 6)));
     if (P->fast_bw > 256 || P->fast_bh > 127 || P->max_cell_w > 250) return ORBX_ERR_BAD_GEOMETRY;
+    if (!P->fast_legacy && P->fast_bw > 160) return ORBX_ERR_BAD_GEOMETRY;       // cells wider than 130 px: no such level (w >= 62)
+    if (!P->fast_legacy) P->fast_warps = ORBX_FS_WARPS;                           // a CTA per strip
     P->cells_per_frame = cells;
     P->cand_per_frame = cand;
     P->kept_per_frame = kept;
@@ -515,14 +539,14 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
         if (ls && l == ls - 1) {
             CK(h, cudaEventRecord(h->ev_low[si], st));
             CK(h, cudaStreamWaitEvent(ax, h->ev_low[si], 0));
-            CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), f0, n, 0, ls, h->num_sms, cand, cell_rec, level_counts,
+            CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), h->d_taps, f0, n, 0, ls, h->num_sms, cand, cell_rec, level_counts,
                                     wc, status, retry_counts, ax));
             CK(h, cudaEventRecord(h->ev_fast_low[si], ax));
         }
     }
     if (ev) CK(h, cudaEventRecord(ev[ST_FAST], st));
     if (ls) CK(h, cudaStreamWaitEvent(st, h->ev_fast_low[si], 0));
-    CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), f0, n, ls, L, h->num_sms, cand, cell_rec, level_counts,
+    CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), h->d_taps, f0, n, ls, L, h->num_sms, cand, cell_rec, level_counts,
                             wc + 1, status, retry_counts, st));
     if (ev) CK(h, cudaEventRecord(ev[ST_OCTREE], st));
     CK(h, orbx::launch_octree(h->d_plan, P, n, cand, cell_rec, cand_sorted, key_node, sorted_counts, kept, kept_counts,

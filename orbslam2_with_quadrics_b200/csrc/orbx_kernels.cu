@@ -439,7 +439,7 @@ __device__ __forceinline__ FastStrip fast_decode(const OrbxPlan* __restrict__ pl
     c.l = l;
     const OrbxLevel& L = plan->lv[l];
     c.ci = (int)((unsigned)(r - L.strip_base) / (unsigned)L.strips_x);
-    c.cj0 = ((r - L.strip_base) - c.ci * L.strips_x) * plan->fast_nc;
+    c.cj0 = ((r - L.strip_base) - c.ci * L.strips_x) * L.strip_nc;
     return c;
 }
 
@@ -472,13 +472,13 @@ __device__ __forceinline__ int fast_score_packed(const uint8_t* __restrict__ p, 
     q[4] = p[3];             q[5] = p[-BW + 3];       q[6] = p[-2 * BW + 2];   q[7] = p[-3 * BW + 1];
     q[8] = p[-3 * BW];       q[9] = p[-3 * BW - 1];   q[10] = p[-2 * BW - 2];  q[11] = p[-BW - 3];
     q[12] = p[-3];           q[13] = p[BW - 3];       q[14] = p[2 * BW - 2];   q[15] = p[3 * BW - 1];
-    // Z[k] = (e_k + 256, e_{k+8} + 256) as s16x2 with e = ring - centre; Z[k+8] = halves swapped
-    const uint32_t bias = (uint32_t)(256 - v) * 0x00010001u;
+    // Z[k] = (ring k, ring k + 8) as s16x2; Z[k + 8] = halves swapped.  min / max commute with subtracting the centre,
+    // so the network runs on the raw ring values (0 .. 255) and the centre is subtracted once at the end.
     uint32_t Z[16];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        Z[k] = (q[k] | (q[k + 8] << 16)) + bias;
-        Z[k + 8] = __byte_perm(Z[k], 0, 0x1032);
+        Z[k] = q[k] + (q[k + 8] << 16);
+        Z[k + 8] = q[k + 8] + (q[k] << 16);
     }
     uint32_t n3[14], x3[14];
 #pragma unroll
@@ -500,8 +500,8 @@ __device__ __forceinline__ int fast_score_packed(const uint8_t* __restrict__ p, 
     dm = min3_s16x2(dm, x9[3], x9[4]);
     dm = min3_s16x2(dm, x9[5], x9[6]);
     dm = __vmins2(dm, x9[7]);
-    const int Ab = max((int)(bm & 0xffffu), (int)(bm >> 16)) - 256;      // brighter arc: min(ring - centre)
-    const int Ad = 256 - min((int)(dm & 0xffffu), (int)(dm >> 16));      // darker arc: min(centre - ring)
+    const int Ab = max((int)(bm & 0xffffu), (int)(bm >> 16)) - v;        // brighter arc: min(ring) - centre
+    const int Ad = v - min((int)(dm & 0xffffu), (int)(dm >> 16));        // darker arc: centre - max(ring)
     const int A = max(Ab, Ad);
     return A > t ? A - 1 : 0;
 }
@@ -509,134 +509,67 @@ __device__ __forceinline__ int fast_score_packed(const uint8_t* __restrict__ p, 
 #ifndef ORBX_FAST_MINB
 #define ORBX_FAST_MINB 3
 #endif
-// BW_T: tile pitch known at compile time (ring offsets become immediates); 0 = read it from the plan.
+
+// What a warp needs to emit the corners of one cell (all frame-relative pointers already resolved).
+struct FastEmit {
+    uint32_t* cand;            // this frame's candidate region of the level
+    uint2* cell_rec;           // this frame's cell records of the level
+    int* level_count;          // candidates of (frame, level) so far
+    int* status;               // this frame's status word
+    int* retry_count;          // (:812) statistics of (frame, level)
+    int cand_cap;
+};
+
+// One cell window, the way cv::FAST sees it (:805-816): passes [pass0, 2) with iniThFAST / minThFAST until one leaves a
+// keypoint, then NMS and the ordered emission.  `win32` / `sh` address the tile word holding the byte in front of window
+// pixel (0, 0), `tile` is the byte of window pixel (0, 0); `sc` is a zero score map addressed as y * SP + x + 1 whose
+// entries around the window's scoring region are zero and stay zero; it is all-zero again on return.  `queue` holds at
+// least (ww - 6) * (wh - 6) entries.
 template <int BW_T>
-__global__ void __launch_bounds__(ORBX_FAST_WARPS * 32, ORBX_FAST_MINB)
-fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, int frame0, int nframes,
-                  int l0, int l1, uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec, int* __restrict__ level_counts,
-                  int* __restrict__ work_counter, int* __restrict__ status, int* __restrict__ retry_counts) {
-    ORBX_PDL_WAIT();
-    extern __shared__ uint8_t fast_smem_raw[];
-    __shared__ uint64_t s_bar[ORBX_FAST_WARPS][2];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int BW = BW_T ? BW_T : plan->fast_bw, BH = plan->fast_bh;
-    const int NC = plan->fast_nc, NB = plan->fast_nb;                    // cells per tile, tile buffers per warp
-    const int TB = (BW * BH + 127) & ~127;                               // tile bytes
-    const int QN = (plan->max_cell_w - 6) * (plan->max_cell_h - 6);      // queue entries (u16)
-    const int SP = (plan->max_cell_w + 2 + 3) & ~3;                      // score-map pitch; column = window x + 1
-    const int SB = (SP * BH + 127) & ~127;
-    const int per_warp = NB * TB + SB + ((QN * 2 + 127) & ~127);
-    uint8_t* base = fast_smem_raw + ((128 - (smem_u32(fast_smem_raw) & 127)) & 127) + (size_t)warp * per_warp;
-    uint8_t* sc = base + NB * TB;                                        // zero-framed score map
-    uint16_t* queue = reinterpret_cast<uint16_t*>(base + NB * TB + SB);  // entries (y << 8) | x, window coordinates
-    const int nlevels = plan->nlevels;
-    const int first_strip = plan->lv[l0].strip_base;
-    const unsigned spf = (unsigned)((l1 < nlevels ? plan->lv[l1].strip_base : plan->strips_per_frame) - first_strip);
-    const unsigned total = (unsigned)nframes * spf;
+__device__ __forceinline__ void fast_cell_path(const OrbxPlan* __restrict__ plan, const uint8_t* __restrict__ tile,
+                                               const uint32_t* __restrict__ tile32, int sh, int BW, int ww, int wh,
+                                               uint8_t* __restrict__ sc, int SP, uint16_t* __restrict__ queue, int pass0,
+                                               const FastEmit& em, int cell_index, int ox, int oy, int lane) {
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int BW4 = BW >> 2;
-
-    for (int i = lane; i < SB / 4; i += 32) reinterpret_cast<uint32_t*>(sc)[i] = 0;
-    if (lane == 0) {
-        mbar_init(&s_bar[warp][0], 1);
-        mbar_init(&s_bar[warp][1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncwarp();
-
-#ifdef ORBX_EXP_STATIC
-    unsigned static_next = blockIdx.x * (blockDim.x >> 5) + warp;
-    auto fetch = [&]() -> unsigned {
-        const unsigned v = static_next;
-        static_next += gridDim.x * (blockDim.x >> 5);
-        return v;
-    };
-#else
-    auto fetch = [&]() -> unsigned {
-        int v = 0;
-        if (lane == 0) v = atomicAdd(work_counter, 1);
-        return (unsigned)__shfl_sync(0xffffffffu, v, 0);
-    };
-#endif
-    auto issue = [&](const FastStrip& c, int b) {
-        if (lane == 0) {
-            const OrbxLevel& L = plan->lv[c.l];
-            mbar_expect_tx(&s_bar[warp][b], (uint32_t)(BW * BH));
-            tma_load_3d(base + b * TB, &maps.m[c.l], &s_bar[warp][b], (ORBX_XO + ORBX_BOX + c.cj0 * L.wCell - 1) & ~15,
-                        ORBX_EDGE + ORBX_BOX + c.ci * L.hCell, frame0 + c.frame);
-        }
-    };
-
-    // A work item is a strip of NC cells fetched as ONE tile (fewer, wider TMA rows).  The work counter is read
-    // one item further ahead than the tile prefetch, so the atomic's round trip overlaps a whole strip.
-    unsigned cur = fetch();
-    unsigned nxt = fetch();
-    FastStrip cc, nc;
-    if (cur < total) { cc = fast_decode(plan, cur, l0, l1, spf, first_strip); issue(cc, 0); }
-    uint32_t phase[2] = {0, 0};
-    int b = 0;
-    while (cur < total) {
-        if (NB == 2 && nxt < total) { nc = fast_decode(plan, nxt, l0, l1, spf, first_strip); issue(nc, b ^ 1); }
-        const unsigned nxt2 = nxt < total ? fetch() : nxt;
-        mbar_wait(&s_bar[warp][b], phase[b]);
-        phase[b] ^= 1;
-
-        const OrbxLevel& L = plan->lv[cc.l];
-        const int delta0 = (ORBX_XO + ORBX_BOX + cc.cj0 * L.wCell - 1) & 15;
-        const int iniY = ORBX_BOX + cc.ci * L.hCell;
-        const int wh = min(iniY + L.hCell + 6, L.maxBY) - iniY;
-        const int ncell = min(NC, L.nColsV - cc.cj0);
-        for (int cix = 0; cix < ncell; ++cix) {
-        const int cj = cc.cj0 + cix;
-        const int iniX = ORBX_BOX + cj * L.wCell;
-        const int ww = min(iniX + L.wCell + 6, L.maxBX) - iniX;
-        const int delta = delta0 + cix * L.wCell;                        // byte offset of (window x0 - 1) inside the tile
-        const uint8_t* tile = base + b * TB + delta + 1;                 // byte of window pixel (0, 0)
-        const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(base + b * TB) + (delta >> 2);
-        const int sh = (delta & 3) * 8;
-        int count = 0, cn = 0;
-#ifdef ORBX_EXP_SKIP_ALL
-        if (ww >= 7 && wh >= 70000) {
-#else
-        if (ww >= 7 && wh >= 7) {
-#endif
-            const int ew = ww - 6;                                       // emission width
-            const int G = (ew + 3) >> 2;                                 // 4-pixel groups per row
-            const int mg = c_recip16[min(G, 32)];                       // (n * mg) >> 16 == n / G for n <= 32
-            const int RPI = (32 * mg) >> 16;                             // rows per warp iteration
-            const int ry = (lane * mg) >> 16, g = lane - ry * G;
-            const int nvalid = min(max(ew - 4 * g, 0), 4);
-            const uint32_t vmask = (ry < RPI && nvalid > 0) ? (0x80808080u >> (8 * (4 - nvalid))) : 0u;
-            for (int pass = 0; pass < 2 && count == 0; ++pass) {
-                const int t = pass == 0 ? plan->ini_th : plan->min_th;
-                if (pass == 1 && lane == 0) atomicAdd(&retry_counts[cc.frame * nlevels + cc.l], 1);      // (:812) statistics only
-                const uint32_t C = (uint32_t)(0x7f - min(t, 0x7f)) * 0x01010101u;
+    int count = 0, cn = 0;
+    if (ww >= 7 && wh >= 7) {
+        const int ew = ww - 6;                                       // emission width
+        const int G = (ew + 3) >> 2;                                 // 4-pixel groups per row
+        const int mg = c_recip16[min(G, 32)];                       // (n * mg) >> 16 == n / G for n <= 32
+        const int RPI = (32 * mg) >> 16;                             // rows per warp iteration
+        const int ry = (lane * mg) >> 16, g = lane - ry * G;
+        const int nvalid = min(max(ew - 4 * g, 0), 4);
+        const uint32_t vmask = (ry < RPI && nvalid > 0) ? (0x80808080u >> (8 * (4 - nvalid))) : 0u;
+        for (int pass = pass0; pass < 2 && count == 0; ++pass) {
+            const int t = pass == 0 ? plan->ini_th : plan->min_th;
+            if (pass == 1 && lane == 0) atomicAdd(em.retry_count, 1);    // (:812) statistics only
+            const uint32_t C = (uint32_t)(0x7f - min(t, 0x7f)) * 0x01010101u;
+            int qn = 0;
+            {
                 // ---- phase 1, in chunks of 8 warp iterations (RPI rows each): first all pre-tests (independent
                 //      loads and SIMD math, nothing serialises), then ONE pair of packed warp scans for the chunk
                 //      (four 8-bit counts per register), then the ordered queue writes.
-                int qn = 0;
                 for (int yc = 3; yc < wh - 3; yc += 8 * RPI) {
                     uint32_t m[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int y = yc + k * RPI + ry;
-                        {   // rows past the window are clamped (always inside the tile) and masked out: no divergence
-                            const uint32_t* r = tile32 + min(y, wh - 4) * BW4 + g;    // raw word holding tile column 4g + (delta & ~3)
-                            const uint32_t c1 = __funnelshift_r(r[1], r[2], sh);      // pixels x .. x+3, x = 3 + 4g
-                            const uint32_t c0 = __funnelshift_r(r[0], r[1], sh);
-                            const uint32_t c2 = __funnelshift_r(r[2], r[3], sh);
-                            const uint32_t up = __funnelshift_r(r[1 - 3 * BW4], r[2 - 3 * BW4], sh);
-                            const uint32_t dn = __funnelshift_r(r[1 + 3 * BW4], r[2 + 3 * BW4], sh);
-                            const uint32_t r4 = __funnelshift_r(c1, c2, 24);        // pixels x+3 .. x+6
-                            const uint32_t r12 = __funnelshift_r(c0, c1, 8);        // pixels x-3 .. x
-                            const uint32_t a0 = __vabsdiffu4(dn, c1), a8 = __vabsdiffu4(up, c1);
-                            const uint32_t a4 = __vabsdiffu4(r4, c1), a12 = __vabsdiffu4(r12, c1);
-                            // bit 7 of a byte of ((a & 0x7f) + C) | a  <=>  a > t
-                            const uint32_t s0 = (a0 & 0x7f7f7f7fu) + C, s8 = (a8 & 0x7f7f7f7fu) + C;
-                            const uint32_t s4 = (a4 & 0x7f7f7f7fu) + C, s12 = (a12 & 0x7f7f7f7fu) + C;
-                            m[k] = ((s0 | a0) | (s8 | a8)) & ((s4 | a4) | (s12 | a12)) & (y < wh - 3 ? vmask : 0u);
-                        }
+                        // rows past the window are clamped (always inside the tile) and masked out: no divergence
+                        const uint32_t* r = tile32 + min(y, wh - 4) * BW4 + g;    // raw word holding tile column 4g + (delta & ~3)
+                        const uint32_t c1 = __funnelshift_r(r[1], r[2], sh);      // pixels x .. x+3, x = 3 + 4g
+                        const uint32_t c0 = __funnelshift_r(r[0], r[1], sh);
+                        const uint32_t c2 = __funnelshift_r(r[2], r[3], sh);
+                        const uint32_t up = __funnelshift_r(r[1 - 3 * BW4], r[2 - 3 * BW4], sh);
+                        const uint32_t dn = __funnelshift_r(r[1 + 3 * BW4], r[2 + 3 * BW4], sh);
+                        const uint32_t r4 = __funnelshift_r(c1, c2, 24);        // pixels x+3 .. x+6
+                        const uint32_t r12 = __funnelshift_r(c0, c1, 8);        // pixels x-3 .. x
+                        const uint32_t a0 = __vabsdiffu4(dn, c1), a8 = __vabsdiffu4(up, c1);
+                        const uint32_t a4 = __vabsdiffu4(r4, c1), a12 = __vabsdiffu4(r12, c1);
+                        // bit 7 of a byte of ((a & 0x7f) + C) | a  <=>  a > t
+                        const uint32_t s0 = (a0 & 0x7f7f7f7fu) + C, s8 = (a8 & 0x7f7f7f7fu) + C;
+                        const uint32_t s4 = (a4 & 0x7f7f7f7fu) + C, s12 = (a12 & 0x7f7f7f7fu) + C;
+                        m[k] = ((s0 | a0) | (s8 | a8)) & ((s4 | a4) | (s12 | a12)) & (y < wh - 3 ? vmask : 0u);
                     }
                     // per-lane counts are <= 4 and a warp total is <= 128, so four counts fit one register
                     uint32_t pa = (uint32_t)__popc(m[0]) | ((uint32_t)__popc(m[1]) << 8) | ((uint32_t)__popc(m[2]) << 16) | ((uint32_t)__popc(m[3]) << 24);
@@ -665,88 +598,506 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
                         qn += (int)tk;
                     }
                 }
+            }
+            __syncwarp();
+            // ---- phase 2: exact score; corners compacted in place (order kept), scores to the map
+            cn = 0;
+            for (int i0 = 0; i0 < qn; i0 += 32) {
+                const int i = i0 + lane;
+                const int e = queue[min(i, qn - 1)];                         // clamped: every lane scores a real pixel
+                int s = fast_score_packed(tile + (e >> 8) * BW + (e & 0xff), BW, t);
+                if (i >= qn) s = 0;
+                const uint32_t bal = __ballot_sync(0xffffffffu, s > 0);
+                if (s > 0) {
+                    sc[(e >> 8) * SP + (e & 0xff) + 1] = (uint8_t)s;
+                    queue[cn + __popc(bal & lt_mask)] = (uint16_t)e;
+                }
+                cn += __popc(bal);
+            }
+            __syncwarp();
+            // ---- phase 3a: strict 3x3 NMS (the window frame and non-corners score 0); mark + count
+            for (int i0 = 0; i0 < cn; i0 += 32) {
+                const int i = i0 + lane;
+                bool keep = false;
+                if (i < cn) {
+                    const int e = queue[i];
+                    const uint8_t* mp = sc + (e >> 8) * SP + (e & 0xff) + 1;
+                    const int s = mp[0];
+                    keep = s > mp[-1] && s > mp[1] && s > mp[-SP - 1] && s > mp[-SP] && s > mp[-SP + 1] &&
+                           s > mp[SP - 1] && s > mp[SP] && s > mp[SP + 1];
+                    if (keep) queue[i] = (uint16_t)(e | 0x8000);
+                }
+                count += __popc(__ballot_sync(0xffffffffu, keep));
+            }
+            __syncwarp();
+            if (count == 0) {                                                // clear the map before the retry
+                for (int i = lane; i < cn; i += 32) sc[(queue[i] >> 8) * SP + (queue[i] & 0xff) + 1] = 0;
                 __syncwarp();
-                // ---- phase 2: exact score; corners compacted in place (order kept), scores to the map
                 cn = 0;
-                for (int i0 = 0; i0 < qn; i0 += 32) {
-                    const int i = i0 + lane;
-                    const int e = queue[min(i, qn - 1)];                         // clamped: every lane scores a real pixel
-#ifdef ORBX_EXP_SKIP_P2
-                    int s = 0;
-#else
-                    int s = fast_score_packed(tile + (e >> 8) * BW + (e & 0xff), BW, t);
-#endif
-                    if (i >= qn) s = 0;
-                    const uint32_t bal = __ballot_sync(0xffffffffu, s > 0);
-                    if (s > 0) {
-                        sc[(e >> 8) * SP + (e & 0xff) + 1] = (uint8_t)s;
-                        queue[cn + __popc(bal & lt_mask)] = (uint16_t)e;
-                    }
-                    cn += __popc(bal);
-                }
-                __syncwarp();
-                // ---- phase 3a: strict 3x3 NMS (the window frame and non-corners score 0); mark + count
-                for (int i0 = 0; i0 < cn; i0 += 32) {
-                    const int i = i0 + lane;
-                    bool keep = false;
-                    if (i < cn) {
-                        const int e = queue[i];
-                        const uint8_t* mp = sc + (e >> 8) * SP + (e & 0xff) + 1;
-                        const int s = mp[0];
-                        keep = s > mp[-1] && s > mp[1] && s > mp[-SP - 1] && s > mp[-SP] && s > mp[-SP + 1] &&
-                               s > mp[SP - 1] && s > mp[SP] && s > mp[SP + 1];
-                        if (keep) queue[i] = (uint16_t)(e | 0x8000);
-                    }
-                    count += __popc(__ballot_sync(0xffffffffu, keep));
-                }
-                __syncwarp();
-                if (count == 0) {                                                // clear the map before the retry
-                    for (int i = lane; i < cn; i += 32) sc[(queue[i] >> 8) * SP + (queue[i] & 0xff) + 1] = 0;
-                    __syncwarp();
-                    cn = 0;
-                }
             }
         }
-        // ---- emit: claim a contiguous block of the level's candidate region, write in row-major order
-        int gbase = 0;
-        bool overflow = false;
-        if (count > 0) {
-            if (lane == 0) gbase = atomicAdd(&level_counts[cc.frame * nlevels + cc.l], count);
-            gbase = __shfl_sync(0xffffffffu, gbase, 0);
-            if (gbase + count > L.cand_cap) {
-                if (lane == 0) atomicOr(&status[cc.frame], ORBX_DEV_CAND_OVERFLOW);
-                overflow = true;
-            }
+    }
+    // ---- emit: claim a contiguous block of the level's candidate region, write in row-major order
+    int gbase = 0;
+    bool overflow = false;
+    if (count > 0) {
+        if (lane == 0) gbase = atomicAdd(em.level_count, count);
+        gbase = __shfl_sync(0xffffffffu, gbase, 0);
+        if (gbase + count > em.cand_cap) {
+            if (lane == 0) atomicOr(em.status, ORBX_DEV_CAND_OVERFLOW);
+            overflow = true;
         }
-        uint32_t* dst = cand + (size_t)cc.frame * plan->cand_per_frame + L.cand_off + gbase;
-        const int ox = cj * L.wCell, oy = cc.ci * L.hCell;                     // (:822-823)
-        int w = 0;
-        for (int i0 = 0; i0 < cn; i0 += 32) {
-            const int i = i0 + lane;
-            bool keep = false;
-            int x = 0, y = 0, s = 0;
-            if (i < cn) {
-                const int e = queue[i];
-                keep = (e & 0x8000) != 0;
-                y = (e >> 8) & 0x7f;
-                x = e & 0xff;
-                s = sc[y * SP + x + 1];
-            }
-            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-            if (keep && !overflow) dst[w + __popc(bal & lt_mask)] = ORBX_PACK(x + ox, y + oy, s);
-            if (i < cn) sc[y * SP + x + 1] = 0;                               // leave the score map all-zero (NMS is done)
-            w += __popc(bal);
+    }
+    uint32_t* dst = em.cand + gbase;
+    int w = 0;
+    for (int i0 = 0; i0 < cn; i0 += 32) {
+        const int i = i0 + lane;
+        bool keep = false;
+        int x = 0, y = 0, s = 0;
+        if (i < cn) {
+            const int e = queue[i];
+            keep = (e & 0x8000) != 0;
+            y = (e >> 8) & 0x7f;
+            x = e & 0xff;
+            s = sc[y * SP + x + 1];
         }
-        if (lane == 0)
-            cell_rec[(size_t)cc.frame * plan->cells_per_frame + L.cell_base + cc.ci * L.nColsV + cj] =
-                make_uint2((uint32_t)gbase, overflow ? 0u : (uint32_t)count);
-        __syncwarp();
-        }   // cells of the strip
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (keep && !overflow) dst[w + __popc(bal & lt_mask)] = ORBX_PACK(x + ox, y + oy, s);      // (:822-823)
+        if (i < cn) sc[y * SP + x + 1] = 0;                               // leave the score map all-zero (NMS is done)
+        w += __popc(bal);
+    }
+    if (lane == 0) em.cell_rec[cell_index] = make_uint2((uint32_t)gbase, overflow ? 0u : (uint32_t)count);
+    __syncwarp();
+}
+
+// Legacy schedule (ORBX_FAST_LEGACY=1, kept for A/B measurements): one cell at a time, unaligned 4-pixel groups.
+// BW_T: tile pitch known at compile time (ring offsets become immediates); 0 = read it from the plan.
+template <int BW_T>
+__global__ void __launch_bounds__(ORBX_FAST_WARPS * 32, ORBX_FAST_MINB)
+fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, int frame0, int nframes,
+                  int l0, int l1, uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec, int* __restrict__ level_counts,
+                  int* __restrict__ work_counter, int* __restrict__ status, int* __restrict__ retry_counts) {
+    ORBX_PDL_WAIT();
+    extern __shared__ uint8_t fast_smem_raw[];
+    __shared__ uint64_t s_bar[ORBX_FAST_WARPS][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int BW = BW_T ? BW_T : plan->fast_bw, BH = plan->fast_bh;
+    const int NB = plan->fast_nb;                                        // tile buffers per warp
+    const int TB = (BW * BH + 127) & ~127;                               // tile bytes
+    const int QN = (plan->max_cell_w - 6) * (plan->max_cell_h - 6);      // queue entries (u16)
+    const int SP = (plan->max_cell_w + 2 + 3) & ~3;                      // score-map pitch; column = window x + 1
+    const int SB = (SP * BH + 127) & ~127;
+    const int per_warp = NB * TB + SB + ((QN * 2 + 127) & ~127);
+    uint8_t* base = fast_smem_raw + ((128 - (smem_u32(fast_smem_raw) & 127)) & 127) + (size_t)warp * per_warp;
+    uint8_t* sc = base + NB * TB;                                        // zero-framed score map
+    uint16_t* queue = reinterpret_cast<uint16_t*>(base + NB * TB + SB);  // entries (y << 8) | x, window coordinates
+    const int nlevels = plan->nlevels;
+    const int first_strip = plan->lv[l0].strip_base;
+    const unsigned spf = (unsigned)((l1 < nlevels ? plan->lv[l1].strip_base : plan->strips_per_frame) - first_strip);
+    const unsigned total = (unsigned)nframes * spf;
+
+    for (int i = lane; i < SB / 4; i += 32) reinterpret_cast<uint32_t*>(sc)[i] = 0;
+    if (lane == 0) {
+        mbar_init(&s_bar[warp][0], 1);
+        mbar_init(&s_bar[warp][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
+    auto fetch = [&]() -> unsigned {
+        int v = 0;
+        if (lane == 0) v = atomicAdd(work_counter, 1);
+        return (unsigned)__shfl_sync(0xffffffffu, v, 0);
+    };
+    auto issue = [&](const FastStrip& c, int b) {
+        if (lane == 0) {
+            const OrbxLevel& L = plan->lv[c.l];
+            mbar_expect_tx(&s_bar[warp][b], (uint32_t)(BW * BH));
+            tma_load_3d(base + b * TB, &maps.m[c.l], &s_bar[warp][b], (ORBX_XO + ORBX_BOX + c.cj0 * L.wCell - 1) & ~15,
+                        ORBX_EDGE + ORBX_BOX + c.ci * L.hCell, frame0 + c.frame);
+        }
+    };
+
+    // A work item is a strip of NC cells fetched as ONE tile (fewer, wider TMA rows).  The work counter is read
+    // one item further ahead than the tile prefetch, so the atomic's round trip overlaps a whole strip.
+    unsigned cur = fetch();
+    unsigned nxt = fetch();
+    FastStrip cc, nc;
+    if (cur < total) { cc = fast_decode(plan, cur, l0, l1, spf, first_strip); issue(cc, 0); }
+    uint32_t phase[2] = {0, 0};
+    int b = 0;
+    while (cur < total) {
+        if (NB == 2 && nxt < total) { nc = fast_decode(plan, nxt, l0, l1, spf, first_strip); issue(nc, b ^ 1); }
+        const unsigned nxt2 = nxt < total ? fetch() : nxt;
+        mbar_wait(&s_bar[warp][b], phase[b]);
+        phase[b] ^= 1;
+
+        const OrbxLevel& L = plan->lv[cc.l];
+        const int delta0 = (ORBX_XO + ORBX_BOX + cc.cj0 * L.wCell - 1) & 15;
+        const int iniY = ORBX_BOX + cc.ci * L.hCell;
+        const int wh = min(iniY + L.hCell + 6, L.maxBY) - iniY;
+        const int ncell = min(L.strip_nc, L.nColsV - cc.cj0);
+        FastEmit em;
+        em.cand = cand + (size_t)cc.frame * plan->cand_per_frame + L.cand_off;
+        em.cell_rec = cell_rec + (size_t)cc.frame * plan->cells_per_frame + L.cell_base;
+        em.level_count = &level_counts[cc.frame * nlevels + cc.l];
+        em.status = &status[cc.frame];
+        em.retry_count = &retry_counts[cc.frame * nlevels + cc.l];
+        em.cand_cap = L.cand_cap;
+        for (int cix = 0; cix < ncell; ++cix) {
+            const int cj = cc.cj0 + cix;
+            const int iniX = ORBX_BOX + cj * L.wCell;
+            const int ww = min(iniX + L.wCell + 6, L.maxBX) - iniX;
+            const int delta = delta0 + cix * L.wCell;                        // byte offset of (window x0 - 1) inside the tile
+            fast_cell_path<BW_T>(plan, base + b * TB + delta + 1, reinterpret_cast<const uint32_t*>(base + b * TB) + (delta >> 2),
+                                 (delta & 3) * 8, BW, ww, wh, sc, SP, queue, 0, em, cc.ci * L.nColsV + cj, cj * L.wCell,
+                                 cc.ci * L.hCell, lane);
+        }
         if (NB == 1 && nxt < total) { nc = fast_decode(plan, nxt, l0, l1, spf, first_strip); issue(nc, 0); }
         cur = nxt;
         nxt = nxt2;
         cc = nc;
         if (NB == 2) b ^= 1;
+    }
+}
+
+// =====================================================================================
+// fast_strips_kernel -- the product schedule of ComputeKeyPointsOctTree's cell loop (:789-829).
+//
+// The scoring regions of horizontally adjacent cells tile a cell row without gaps (cv::FAST scores the window minus a
+// 3-px frame, and windows overlap by 6), and the iniThFAST pre-test does not depend on the cell.  A CTA of 4 warps
+// therefore takes a strip of strip_nc (4) cells as ONE dense region whose 4-pixel words are aligned with the TMA tile
+// (two tile buffers: the next strip's tile is in flight while this one is processed):
+//   phase 1  warp = group of 8 rows, lane = tile word column: 3-5 aligned LDS, 2 funnel shifts, 4 VABSDIFF4 and the
+//            threshold logic per 4 pixels (no re-alignment shifts, no per-row address math: every offset is an
+//            immediate).  The survivor bits of 8 rows x 4 pixels are packed into one register.
+//   phase 1b one warp scan of the per-lane survivor counts + the four warp totals, then every lane appends its own
+//            survivors to the strip's queue (order is irrelevant here: the emission order comes from a bitmap).
+//   phase 2  exact score in full 32-lane batches over the whole strip (warp w takes batches w, w + 4, ...), corners to
+//            a strip-wide score map in which adjacent cells are separated by two zero columns, so NMS never sees across
+//            a cell boundary (cv::FAST's NMS treats everything outside the window's scoring region as score 0).  A warp
+//            compacts the map indices of its corners into the queue slots of its own consumed batches.
+//   phase 3  strict 3x3 NMS per corner; kept corners set a bit in a bitmap indexed like the score map.
+//   phase 4  warp = cell, lane = row: extract the row's bits, warp scan, claim the cell's block of the candidate
+//            region, write (x, y, score) in row-major order = cv::FAST's keypoint order.
+// A cell whose iniThFAST pass leaves no keypoint is redone with minThFAST (:812-816) by fast_cell_path on the same tile
+// (8.8 % of the cells of a 1080p cluttered frame, and they are the flat ones: few survivors).  Strips with more
+// survivors than the queue holds (noise) and levels whose cells are larger than 32 px go through fast_cell_path
+// entirely.
+// =====================================================================================
+#ifndef ORBX_FS_MINB
+#define ORBX_FS_MINB (24 / ORBX_FS_WARPS)
+#endif
+#define ORBX_FS_GPW (4 / ORBX_FS_WARPS)      // 8-row groups (and cells) per warp
+
+template <int BW_T>
+__device__ __forceinline__ uint32_t fast_pretest_word(const uint32_t* __restrict__ p, uint32_t C, uint32_t colmask) {
+    constexpr int BW4 = BW_T / 4;
+    const uint32_t c1 = p[0], c0 = p[-1], c2 = p[1], up = p[-3 * BW4], dn = p[3 * BW4];
+    const uint32_t r4 = __funnelshift_r(c1, c2, 24);        // pixels x+3 .. x+6
+    const uint32_t r12 = __funnelshift_r(c0, c1, 8);        // pixels x-3 .. x
+    const uint32_t a0 = __vabsdiffu4(dn, c1), a8 = __vabsdiffu4(up, c1);
+    const uint32_t a4 = __vabsdiffu4(r4, c1), a12 = __vabsdiffu4(r12, c1);
+    // bit 7 of a byte of ((a & 0x7f) + C) | a  <=>  a > t
+    const uint32_t s0 = (a0 & 0x7f7f7f7fu) + C, s8 = (a8 & 0x7f7f7f7fu) + C;
+    const uint32_t s4 = (a4 & 0x7f7f7f7fu) + C, s12 = (a12 & 0x7f7f7f7fu) + C;
+    return ((s0 | a0) | (s8 | a8)) & ((s4 | a4) | (s12 | a12)) & colmask;
+}
+
+#define ORBX_FS_NONE 0xffffffffu
+
+template <int BW_T>
+__global__ void __launch_bounds__(ORBX_FS_WARPS * 32, ORBX_FS_MINB)
+fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, const uint32_t* __restrict__ strip_tab,
+                   int frame0, int nframes, int l0, int l1, uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec,
+                   int* __restrict__ level_counts, int* __restrict__ work_counter, int* __restrict__ status,
+                   int* __restrict__ retry_counts) {
+    ORBX_PDL_WAIT();
+    extern __shared__ uint8_t fast_smem_raw[];
+    __shared__ uint64_t s_bar[2];
+    __shared__ int s_wtot[ORBX_FS_WARPS];
+    __shared__ uint2 s_item[2];          // (frame or ORBX_FS_NONE, strip_tab entry) of the strip fetched two iterations ahead
+    __shared__ unsigned s_redo;
+    constexpr int BW = BW_T, BW4 = BW_T / 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int BH = plan->fast_bh;
+    const int TB = (BW * BH + 127) & ~127;                               // tile bytes
+    const int SP = plan->fast_sp;                                        // score-map pitch
+    const int SBYTES = SP * (BH - 4);                                    // map row = window y - 2
+    const int SB = (SBYTES + 15) & ~15;
+    const int KBW = (SBYTES + 31) / 32 + 2;                              // kept-corner bitmap, bit index = map index
+    const int KB = (KBW * 4 + 15) & ~15;
+    const int QCAP = plan->fast_qcap;
+    uint8_t* smem = fast_smem_raw + ((128 - (smem_u32(fast_smem_raw) & 127)) & 127);
+    uint8_t* sc = smem + ORBX_FS_NBUF * TB;
+    uint32_t* kb = reinterpret_cast<uint32_t*>(smem + ORBX_FS_NBUF * TB + SB);
+    uint16_t* queue = reinterpret_cast<uint16_t*>(smem + ORBX_FS_NBUF * TB + SB + KB);
+    const int nlevels = plan->nlevels;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    // thread 0: next work item -> (frame, table entry); the table holds (level, cell row, first cell) of every strip of a frame
+    auto fetch = [&](int slot) {
+        const int first_strip = plan->lv[l0].strip_base;
+        const unsigned spf = (unsigned)((l1 < nlevels ? plan->lv[l1].strip_base : plan->strips_per_frame) - first_strip);
+        const unsigned v = (unsigned)atomicAdd(work_counter, 1);
+        uint2 r = make_uint2(ORBX_FS_NONE, 0u);
+        if (v < (unsigned)nframes * spf) {
+            r.x = v / spf;
+            r.y = __ldg(strip_tab + first_strip + (v - r.x * spf));
+        }
+        s_item[slot] = r;
+    };
+    auto issue = [&](uint2 c, int b) {                   // thread 0 only
+        const int l = c.y & 15, ci = (c.y >> 4) & 0xfff, cj0 = c.y >> 16;
+        const OrbxLevel& L = plan->lv[l];
+        mbar_expect_tx(&s_bar[b], (uint32_t)(BW * BH));
+        tma_load_3d(smem + b * TB, &maps.m[l], &s_bar[b], (ORBX_XO + ORBX_BOX + cj0 * L.wCell - 1) & ~15,
+                    ORBX_EDGE + ORBX_BOX + ci * L.hCell, frame0 + (int)c.x);
+    };
+
+    for (int i = tid; i < (SB + KB) / 4; i += ORBX_FS_WARPS * 32) reinterpret_cast<uint32_t*>(sc)[i] = 0;
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        fetch(0);
+        fetch(1);
+        s_redo = 0;
+    }
+    __syncthreads();
+    uint2 cur = s_item[0], nxt = s_item[1];
+    __syncthreads();                                                         // thread 0 reuses s_item[] below
+    if (tid == 0 && cur.x != ORBX_FS_NONE) issue(cur, 0);
+    uint32_t phase[2] = {0, 0};
+    int b = 0, it = 0;
+    while (cur.x != ORBX_FS_NONE) {
+        if (tid == 0) {
+            if (ORBX_FS_NBUF == 2 && nxt.x != ORBX_FS_NONE) issue(nxt, b ^ 1);   // buffer b ^ 1 was released by the last barrier of the previous strip
+            fetch(it & 1);                                                   // read after the next barrier
+        }
+        mbar_wait(&s_bar[b], phase[b]);
+        phase[b] ^= 1;
+
+        uint8_t* tbuf = smem + b * TB;
+        const int frame = (int)cur.x, lvl = cur.y & 15, ci = (cur.y >> 4) & 0xfff, cj0 = cur.y >> 16;
+        const OrbxLevel& L = plan->lv[lvl];
+        const int wCell = L.wCell;
+        const int delta0 = (ORBX_XO + ORBX_BOX + cj0 * wCell - 1) & 15;      // tile byte of (strip window x0 - 1)
+        const int iniY = ORBX_BOX + ci * L.hCell;
+        const int wh = min(iniY + L.hCell + 6, L.maxBY) - iniY;
+        const int ncell = min(L.strip_nc, L.nColsV - cj0);
+        const int iniX0 = ORBX_BOX + cj0 * wCell;
+        const int sw = min(iniX0 + ncell * wCell + 6, L.maxBX) - iniX0;      // strip window width
+        const int hr = wh - 6;                                               // scoring rows: window y in [3, wh - 3)
+        FastEmit em;
+        em.cand = cand + (size_t)frame * plan->cand_per_frame + L.cand_off;
+        em.cell_rec = cell_rec + (size_t)frame * plan->cells_per_frame + L.cell_base;
+        em.level_count = &level_counts[frame * nlevels + lvl];
+        em.status = &status[frame];
+        em.retry_count = &retry_counts[frame * nlevels + lvl];
+        em.cand_cap = L.cand_cap;
+        const uint8_t* tile = tbuf + delta0 + 1;                             // byte of strip window pixel (0, 0)
+        unsigned todo = (1u << ncell) - 1u;                                  // cells of the strip still without a result
+        unsigned cell_path = 0;              // cells left to fast_cell_path: bit k = minThFAST pass only, bit 8 + k = both passes
+        uint2 nxt2 = make_uint2(ORBX_FS_NONE, 0u);
+        bool have_next = false;
+        if (L.strip_ok && hr >= 1 && sw >= 7) {
+            const int wrecip = L.wcell_recip;
+            const int fb = delta0 + 4;                                       // tile byte of the first scoring pixel (window x = 3)
+            const int W0 = fb >> 2;
+            const int xb0 = 4 * W0 - delta0 - 1;                             // window x of byte 0 of lane 0's word
+            const int wxb = xb0 + 4 * lane;
+            const uint32_t* rp0 = reinterpret_cast<const uint32_t*>(tbuf) + 3 * BW4 + min(W0 + lane, BW4 - 2);
+            for (int pass = 0; pass < 2; ++pass) {
+                // (:805-816) iniThFAST for every cell, then minThFAST for the cells that came back empty
+                const int t = pass == 0 ? plan->ini_th : plan->min_th;
+                const uint32_t C = (uint32_t)(0x7f - min(t, 0x7f)) * 0x01010101u;
+                // ---- phase 1: aligned SIMD pre-test; a warp takes ORBX_FS_GPW groups of 8 rows, lane = word column
+                uint32_t colmask = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int wx = wxb + j;
+                    if (wx >= 3 && wx < sw - 3 && ((todo >> (((wx - 3) * wrecip) >> 16)) & 1u)) colmask |= 0xffu << (8 * j);
+                }
+                uint32_t acc[ORBX_FS_GPW];
+                int cnt = 0;
+#pragma unroll
+                for (int gg = 0; gg < ORBX_FS_GPW; ++gg) {
+                    const int g = warp * ORBX_FS_GPW + gg;
+                    const int nv = hr - 8 * g;                               // rows of this group
+                    uint32_t a = 0;
+                    if (nv > 0) {
+                        const uint32_t* rp = rp0 + 8 * g * BW4;
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            // rows past the window (last group of a short strip) read bytes that exist in shared memory and are masked below
+                            uint32_t m = fast_pretest_word<BW_T>(rp + r * BW4, C, colmask);
+                            // row r of the group goes to the lane 4r further down: a lane collects 8 different word columns, so
+                            // an edge (the typical run of survivors) is spread over many lanes before the per-lane append loop
+                            if (r) m = __shfl_sync(0xffffffffu, m, (lane + 4 * r) & 31);
+                            a |= (r == 7 ? m : (m >> (7 - r))) & (0x01010101u << r);
+                        }
+                        if (nv < 8) a &= ((1u << nv) - 1u) * 0x01010101u;   // byte j = pixel column j, bit r = row 8g + r
+                    }
+                    acc[gg] = a;
+                    cnt += __popc(a);
+                }
+                // ---- phase 1b: scan, then every lane appends its survivors (any order)
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                if (lane == 31) s_wtot[warp] = incl;
+                __syncthreads();                                             // B1
+                if (!have_next) { nxt2 = s_item[it & 1]; have_next = true; }
+                int wbase = 0, qn = 0;
+#pragma unroll
+                for (int w = 0; w < ORBX_FS_WARPS; ++w) {
+                    const int v = s_wtot[w];
+                    if (w < warp) wbase += v;
+                    qn += v;
+                }
+                if (qn > QCAP) {                                             // noise: cell by cell (uniform branch)
+                    cell_path = pass == 0 ? todo << 8 : todo;
+                    break;
+                }
+                {
+                    uint16_t* wq = queue + wbase + (incl - cnt);
+#pragma unroll
+                    for (int gg = 0; gg < ORBX_FS_GPW; ++gg) {
+                        const int e0 = ((warp * ORBX_FS_GPW + gg) << 10) | (lane << 5);    // entry: row group | lane | bit of acc
+                        uint32_t a = acc[gg];
+                        while (a) {
+                            const int bit = __ffs((int)a) - 1;
+                            a &= a - 1;
+                            *wq++ = (uint16_t)(e0 | bit);
+                        }
+                    }
+                }
+                __syncthreads();                                             // B2
+                // ---- phase 2: exact score; corners to the strip map, their map indices compacted into this warp's batches
+                int cn = 0;                                                  // corners of this warp
+                for (int i0 = warp * 32; i0 < qn; i0 += ORBX_FS_WARPS * 32) {
+                    const int i = i0 + lane;
+                    const int e = queue[min(i, qn - 1)];                     // clamped: every lane scores a real pixel
+                    const int r = e & 7;
+                    const int wc = ((e >> 5) + 4 * r) & 31;                  // word column (undo the lane rotation of phase 1)
+                    const int x = xb0 + 4 * wc + ((e >> 3) & 3);
+                    const int y = 3 + ((e >> 7) & 0x18) + r;                 // 8 * group + row
+                    int s = fast_score_packed(tile + y * BW + x, BW, t);
+                    if (i >= qn) s = 0;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, s > 0);
+                    if (s > 0) {
+                        const int k = ((x - 3) * wrecip) >> 16;              // cell of the strip
+                        const int idx = (y - 2) * SP + x - 2 + 2 * k;        // two zero columns between cells
+                        sc[idx] = (uint8_t)s;
+                        const int j = cn + __popc(bal & lt_mask);
+                        queue[(warp + ORBX_FS_WARPS * (j >> 5)) * 32 + (j & 31)] = (uint16_t)idx;
+                    }
+                    cn += __popc(bal);
+                }
+                __syncthreads();                                             // B3
+                // ---- phase 3: strict 3x3 NMS; kept corners -> bitmap
+                for (int j0 = 0; j0 < cn; j0 += 32) {
+                    const int j = j0 + lane;
+                    if (j < cn) {
+                        const int idx = queue[(warp + ORBX_FS_WARPS * (j >> 5)) * 32 + (j & 31)];
+                        const uint8_t* mp = sc + idx;
+                        const int m8 = max(max(max((int)mp[-1], (int)mp[1]), max((int)mp[-SP - 1], (int)mp[-SP])),
+                                           max(max((int)mp[-SP + 1], (int)mp[SP - 1]), max((int)mp[SP], (int)mp[SP + 1])));
+                        if ((int)mp[0] > m8) atomicOr(&kb[idx >> 5], 1u << (idx & 31));
+                    }
+                }
+                __syncthreads();                                             // B4
+                // ---- phase 4: warp = cell, lane = scoring row; ordered emission
+#pragma unroll
+                for (int kk = 0; kk < ORBX_FS_GPW; ++kk)
+                if ((todo >> (warp + kk * ORBX_FS_WARPS)) & 1u) {
+                    const int k = warp + kk * ORBX_FS_WARPS;
+                    const int cstep = wCell + 2;
+                    const uint32_t cmask = wCell >= 32 ? 0xffffffffu : ((1u << wCell) - 1u);
+                    uint32_t bits = 0;
+                    if (lane < hr) {
+                        const int sb = (lane + 1) * SP + k * cstep + 1;
+                        bits = __funnelshift_r(kb[sb >> 5], kb[(sb >> 5) + 1], sb & 31) & cmask;
+                    }
+                    const int c = __popc(bits);
+                    int inc = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += v;
+                    }
+                    const int tot = __shfl_sync(0xffffffffu, inc, 31);
+                    if (pass == 1 && lane == 0) atomicAdd(em.retry_count, 1);                          // (:812) statistics only
+                    if (tot == 0) {
+                        if (lane == 0) {
+                            if (pass == 0) atomicOr(&s_redo, 1u << k);
+                            else em.cell_rec[ci * L.nColsV + cj0 + k] = make_uint2(0u, 0u);
+                        }
+                    } else {
+                        int gbase = 0;
+                        if (lane == 0) gbase = atomicAdd(em.level_count, tot);
+                        gbase = __shfl_sync(0xffffffffu, gbase, 0);
+                        const bool overflow = gbase + tot > em.cand_cap;
+                        if (overflow && lane == 0) atomicOr(em.status, ORBX_DEV_CAND_OVERFLOW);
+                        uint32_t* dst = em.cand + gbase + (inc - c);
+                        const uint8_t* srow = sc + (lane + 1) * SP + k * cstep + 1;
+                        const int ox = (cj0 + k) * wCell + 3, oy = ci * L.hCell + 3 + lane;            // (:822-823)
+                        uint32_t bb = overflow ? 0u : bits;
+                        while (bb) {
+                            const int x = __ffs((int)bb) - 1;
+                            bb &= bb - 1;
+                            *dst++ = ORBX_PACK(x + ox, oy, srow[x]);
+                        }
+                        if (lane == 0)
+                            em.cell_rec[ci * L.nColsV + cj0 + k] = make_uint2((uint32_t)gbase, overflow ? 0u : (uint32_t)tot);
+                    }
+                }
+                __syncthreads();                                             // B5
+                // leave the score map and the bitmap all-zero
+                for (int j = lane; j < cn; j += 32) sc[queue[(warp + ORBX_FS_WARPS * (j >> 5)) * 32 + (j & 31)]] = 0;
+                for (int i = tid; i < KBW; i += ORBX_FS_WARPS * 32) kb[i] = 0;
+                const unsigned redo = pass == 0 ? s_redo : 0u;
+                if (redo == 0) break;                                        // uniform
+                todo = redo;
+            }
+        } else {
+            cell_path = todo << 8;
+        }
+        __syncthreads();                                                     // B6: map / bitmap zero, s_redo consumed
+        if (!have_next) nxt2 = s_item[it & 1];
+        if (tid == 0) s_redo = 0;
+        // ---- cells done one at a time by fast_cell_path: dense strips (noise) and cells larger than 32 px.  Warps 0 and 1
+        //      take the even and odd cells, each with its own half of the queue.
+        if (cell_path != 0) {
+            if (warp < 2) {
+                uint16_t* myq = queue + ((L.strip_ok && ORBX_FS_WARPS > 1) ? warp * (QCAP >> 1) : 0);
+                for (int k = warp; k < ncell; k += (ORBX_FS_WARPS > 1 ? 2 : 1)) {
+                    if (!((cell_path >> k) & 0x101u)) continue;
+                    const int cj = cj0 + k;
+                    const int iniX = ORBX_BOX + cj * wCell;
+                    const int ww = min(iniX + wCell + 6, L.maxBX) - iniX;
+                    const int delta = delta0 + k * wCell;                    // byte offset of (window x0 - 1) inside the tile
+                    fast_cell_path<BW_T>(plan, tbuf + delta + 1, reinterpret_cast<const uint32_t*>(tbuf) + (delta >> 2), (delta & 3) * 8,
+                                         BW, ww, wh, sc + k * (wCell + 2) - 3 - 2 * SP, SP, myq, (cell_path >> k) & 1u ? 1 : 0, em,
+                                         ci * L.nColsV + cj, cj * wCell, ci * L.hCell, lane);
+                }
+            }
+            __syncthreads();                                                 // B7: tile buffer b is free
+        }
+        if (ORBX_FS_NBUF == 1) {
+            if (tid == 0 && nxt.x != ORBX_FS_NONE) issue(nxt, 0);            // every warp is past its last read of the tile (B3 / B7)
+        } else {
+            b ^= 1;
+        }
+        cur = nxt;
+        nxt = nxt2;
+        ++it;
     }
 }
 
@@ -2535,11 +2886,19 @@ void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nfr
 }
 
 size_t fast_smem_bytes(const OrbxPlan& hp) {
+    if (hp.fast_legacy) {
+        const size_t TB = ((size_t)hp.fast_bw * hp.fast_bh + 127) & ~(size_t)127;
+        const size_t SP = (size_t)((hp.max_cell_w + 2 + 3) & ~3);
+        const size_t SB = (SP * hp.fast_bh + 127) & ~(size_t)127;
+        const size_t QB = ((size_t)(hp.max_cell_w - 6) * (hp.max_cell_h - 6) * 2 + 127) & ~(size_t)127;
+        return ((size_t)hp.fast_nb * TB + SB + QB) * hp.fast_warps + 128;
+    }
+    // fast_strips_kernel: two tile buffers + strip score map + kept-corner bitmap + survivor queue per CTA (same carve-up as the kernel)
     const size_t TB = ((size_t)hp.fast_bw * hp.fast_bh + 127) & ~(size_t)127;
-    const size_t SP = (size_t)((hp.max_cell_w + 2 + 3) & ~3);
-    const size_t SB = (SP * hp.fast_bh + 127) & ~(size_t)127;
-    const size_t QB = ((size_t)(hp.max_cell_w - 6) * (hp.max_cell_h - 6) * 2 + 127) & ~(size_t)127;
-    return ((size_t)hp.fast_nb * TB + SB + QB) * hp.fast_warps + 128;
+    const size_t SBYTES = (size_t)hp.fast_sp * (hp.fast_bh - 4);
+    const size_t SB = (SBYTES + 15) & ~(size_t)15;
+    const size_t KB = (((SBYTES + 31) / 32 + 2) * 4 + 15) & ~(size_t)15;
+    return ORBX_FS_NBUF * TB + SB + KB + (size_t)hp.fast_qcap * 2 + 128;
 }
 
 // One {pitch, rows, frames} u8 tensor map per level over the pyramid slabs; box = bw x bh bytes of one frame.
@@ -2581,47 +2940,57 @@ int build_describe_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void
 
 size_t fast_maps_bytes() { return sizeof(FastMaps); }
 
-cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, int frame0, int nframes, int l0,
-                        int l1, int num_sms, uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counter, int* status,
-                        int* retry_counts, cudaStream_t st) {
+cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, const OrbxTap* taps, int frame0, int nframes,
+                        int l0, int l1, int num_sms, uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counter,
+                        int* status, int* retry_counts, cudaStream_t st) {
     const size_t smem = fast_smem_bytes(hp);
-    static size_t configured[64] = {0};
-    static int per_sm_cache[64] = {0};
+    typedef void (*cells_fn)(const FastMaps, const OrbxPlan*, int, int, int, int, uint32_t*, uint2*, int*, int*, int*, int*);
+    typedef void (*strips_fn)(const FastMaps, const OrbxPlan*, const uint32_t*, int, int, int, int, uint32_t*, uint2*, int*, int*, int*, int*);
+    static const strips_fn strips_all[3] = {fast_strips_kernel<96>, fast_strips_kernel<128>, fast_strips_kernel<160>};
+    static const cells_fn cells_all[4] = {fast_cells_kernel<64>, fast_cells_kernel<96>, fast_cells_kernel<128>, fast_cells_kernel<0>};
+    int which;
+    if (!hp.fast_legacy) {
+        which = hp.fast_bw == 96 ? 0 : hp.fast_bw == 128 ? 1 : hp.fast_bw == 160 ? 2 : -1;
+        if (which < 0) return cudaErrorInvalidValue;
+    } else {
+        which = hp.fast_bw == 64 ? 3 : hp.fast_bw == 96 ? 4 : hp.fast_bw == 128 ? 5 : 6;
+    }
+    const void* fn = which < 3 ? (const void*)strips_all[which] : (const void*)cells_all[which - 3];
+    // per device and kernel: the dynamic shared-memory limit that was configured and the resident CTAs per SM it gives
+    static size_t configured[64][7] = {};
+    static int per_sm_cache[64][7] = {};
     int dev = 0;
     cudaGetDevice(&dev);
+    dev &= 63;
     std::lock_guard<std::mutex> config_lock(g_config_mutex);
-    typedef void (*fast_fn)(const FastMaps, const OrbxPlan*, int, int, int, int, uint32_t*, uint2*, int*, int*, int*, int*);
-    fast_fn fn = hp.fast_bw == 64 ? fast_cells_kernel<64> : hp.fast_bw == 96 ? fast_cells_kernel<96> :
-                 hp.fast_bw == 128 ? fast_cells_kernel<128> : fast_cells_kernel<0>;
-    if (smem != configured[dev & 63]) {
-        fast_fn all[4] = {fast_cells_kernel<64>, fast_cells_kernel<96>, fast_cells_kernel<128>, fast_cells_kernel<0>};
-        for (int i = 0; i < 4; ++i) {
-            cudaError_t e = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-        }
-        configured[dev & 63] = smem;
-        int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, hp.fast_warps * 32, smem);
-        per_sm_cache[dev & 63] = per_sm < 1 ? 1 : per_sm;
-    }
     const int W = hp.fast_warps;
+    if (smem != configured[dev][which]) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev][which] = smem;
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, W * 32, smem);
+        per_sm_cache[dev][which] = per_sm < 1 ? 1 : per_sm;
+    }
     const int strips = (l1 < hp.nlevels ? hp.lv[l1].strip_base : hp.strips_per_frame) - hp.lv[l0].strip_base;
     const long long total = (long long)nframes * strips;
-    long long blocks = (total + W - 1) / W;
+    long long blocks = hp.fast_legacy ? (total + W - 1) / W : total;          // legacy: a warp per strip; product: a CTA per strip
     // ORBX_FAST_CTAS_PER_SM (tuning): fewer resident FAST CTAs leave registers / shared memory for the kernels of the
     // other half-batch's stream to co-run
     static const int env_cap = getenv("ORBX_FAST_CTAS_PER_SM") ? atoi(getenv("ORBX_FAST_CTAS_PER_SM")) : 0;
-    int per_sm_eff = per_sm_cache[dev & 63];
+    int per_sm_eff = per_sm_cache[dev][which];
     if (env_cap > 0 && env_cap < per_sm_eff) per_sm_eff = env_cap;
     const long long cap = (long long)num_sms * per_sm_eff;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     FastMaps fm;
     memcpy(&fm, maps, sizeof fm);
-    const cudaError_t le = launch_k(fn, dim3((unsigned)blocks), dim3(W * 32), smem, st, fm, d_plan, frame0, nframes, l0, l1, cand,
-                                    cell_rec, level_counts, work_counter, status, retry_counts);
-    if (le != cudaSuccess) return le;
-    return cudaSuccess;
+    if (which < 3)
+        return launch_k(strips_all[which], dim3((unsigned)blocks), dim3(W * 32), smem, st, fm, d_plan,
+                        reinterpret_cast<const uint32_t*>(taps + hp.strip_tab_off), frame0, nframes, l0, l1, cand, cell_rec,
+                        level_counts, work_counter, status, retry_counts);
+    return launch_k(cells_all[which - 3], dim3((unsigned)blocks), dim3(W * 32), smem, st, fm, d_plan, frame0, nframes, l0, l1, cand,
+                    cell_rec, level_counts, work_counter, status, retry_counts);
 }
 
 size_t octree_smem_bytes(const OrbxPlan& hp) {

@@ -9,6 +9,13 @@
 #ifndef ORBX_FAST_WARPS
 #define ORBX_FAST_WARPS 8
 #endif
+// fast_strips_kernel shape (compile-time; -D overrides are for A/B builds)
+#ifndef ORBX_FS_WARPS
+#define ORBX_FS_WARPS 2          // warps per strip (= per CTA): 1, 2 or 4.  Measured at 64 x 1080p (ms): 1 -> 1.118, 2 -> 0.891, 4 -> 0.993
+#endif
+#ifndef ORBX_FS_NBUF
+#define ORBX_FS_NBUF 1           // tile buffers per CTA.  2 hides the TMA latency but costs resident CTAs: 0.991 vs 0.891 ms
+#endif
 #define ORBX_OT_THREADS 1024
 #define ORBX_OT_KEYCAP 8192     // candidates of one level kept in shared memory by the octree kernel (6 bytes each)
 
@@ -26,9 +33,9 @@ cudaError_t launch_cvt_gray(const uint8_t* src, size_t src_pitch, size_t src_fra
 size_t fast_smem_bytes(const OrbxPlan& hp);
 int build_fast_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* out_maps);
 size_t fast_maps_bytes();
-cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, int frame0, int nframes, int l0, int l1, int num_sms,
-                        uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counter, int* status, int* retry_counts,
-                        cudaStream_t st);
+cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, const OrbxTap* taps, int frame0, int nframes,
+                        int l0, int l1, int num_sms, uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counter,
+                        int* status, int* retry_counts, cudaStream_t st);
 size_t octree_smem_bytes(const OrbxPlan& hp);
 cudaError_t launch_octree(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, const uint32_t* cand,
                           const uint2* cell_rec, uint32_t* cand_sorted, uint16_t* key_node, int* sorted_counts,

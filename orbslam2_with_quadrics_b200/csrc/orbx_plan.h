@@ -26,7 +26,10 @@ struct OrbxLevel {
     int nColsV, nRowsV;       // cells that survive the skip rules (:794, :803)
     int wCell, hCell;
     int cell_base;            // first cell of this level inside a frame (cell_rec index)
-    int strip_base, strips_x; // FAST work items: strips of fast_nc cells; first item of the level, items per cell row
+    int strip_base, strips_x; // FAST work items: strips of strip_nc cells; first item of the level, items per cell row
+    int strip_nc;             // cells per strip of this level (a strip's scoring pixels fit 32 tile words)
+    int strip_ok;             // 1: fast_strips_kernel's dense strip path applies (cells <= 32 x 32), 0: cell by cell
+    int wcell_recip;          // 65536 / wCell + 1: (n * wcell_recip) >> 16 == n / wCell for n < 256
     int cand_off, cand_cap;   // this level's region in a frame's candidate buffers (entries)
     int quota;                // mnFeaturesPerLevel[l]
     int nIni;                 // root nodes of DistributeOctTree (:543)
@@ -53,8 +56,11 @@ struct OrbxPlan {
     int node_cap;             // octree node capacity (max over levels)
     int max_cell_w, max_cell_h;   // largest FAST window (incl. the 6-px overlap)
     int fast_bw, fast_bh;         // TMA box of a FAST tile (bw multiple of 16)
-    int fast_nc, fast_nb, fast_warps;   // cells per tile, tile buffers per warp (1 or 2), warps per CTA
+    int fast_nc, fast_nb, fast_warps;   // max cells per tile, tile buffers per warp (legacy kernel: 1 or 2), warps per CTA
+    int fast_legacy;              // 1: fast_cells_kernel (ORBX_FAST_LEGACY=1, A/B measurements)
+    int fast_sp, fast_qcap;       // fast_strips_kernel: score-map pitch, survivor queue entries per warp
     int strips_per_frame;
+    int strip_tab_off;            // strip table (level | cell row << 4 | first cell << 16 per strip of a frame) inside the tap tables, OrbxTap units
     int ini_th, min_th;
     long long slab_bytes;     // one frame's pyramid slab
     float atan_p1, atan_p3, atan_p5, atan_p7;   // cv::fastAtan2 coefficients (float products)
