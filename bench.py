@@ -214,21 +214,45 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- own arm
-def own_arm(args):
-    import torch
-    from orbslam2_with_quadrics_b200 import ORBextractor, sharding
+def source_hash():
+    """sha256 over the sources the library is built from: profiles/dominant_kernel_traffic.json records the hash of the
+    tree its ncu capture was taken from, and a capture of another tree is not reported (roofline.traffic = null)."""
+    import hashlib
+    hsh = hashlib.sha256()
+    d = os.path.join(ROOT, "orbslam2_with_quadrics_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".h", ".inc")):
+            hsh.update(f.encode()); hsh.update(open(os.path.join(d, f), "rb").read())
+    return hsh.hexdigest()[:16]
 
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
-    rank, world, local = sharding.init_from_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
-    torch.cuda.set_device(local)
-    name = args.config
+
+def h2d_ceiling(host, dev, reps, chunks, sharding, torch):
+    """Pinned host -> device copies of one step's input, no kernels, all ranks at once: what the box's host side can feed."""
+    n = host.numel()
+    hv, dv = host.view(-1), dev.view(-1)
+    step = n // chunks
+    for _ in range(2):
+        dv.copy_(hv, non_blocking=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sharding.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        for c in range(chunks):
+            dv[c * step:(c + 1) * step].copy_(hv[c * step:(c + 1) * step], non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(); sharding.barrier()
+    return sharding.max_over_ranks(e0.elapsed_time(e1)) / reps          # ms per step, slowest rank
+
+
+def measure_config(args, name, B, K, W, rank, world, local, full, sampler):
+    """One BASELINE config on this rank's GPU: device-resident value, per-stage times, e2e through the C ABI.
+    full = the headline config (adds sustained, latency, drop-in defaults); otherwise a short pass for `extra_configs`."""
+    import ctypes as C
+    import torch
+    from orbslam2_with_quadrics_b200 import ORBextractor, sharding, _capi
+
     w, h, nf, sf, nl, it, mt, nimg = fr.CONFIGS[name]
-    B = args.batch                       # frames per step per GPU
     nimgs = B * nimg                     # images per step per GPU
-    K, W = args.steps, args.warmup
     balg = geo.algorithmic_bytes(w, h, nf, sf, nl) * nimg           # per frame
     stage_bytes = geo.stage_algorithmic_bytes(w, h, nf, sf, nl)
 
@@ -256,10 +280,6 @@ def own_arm(args):
     def step_device():
         ex.extract_device(dev.data_ptr(), nimgs, w, h, pitch, h * pitch)
 
-    sampler = ClockSampler(local if "CUDA_VISIBLE_DEVICES" not in os.environ else
-                           os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local])
-    if rank == 0:
-        sampler.start()           # nvidia-smi needs a moment to start: it covers warm-up, the timed region and e2e
     for _ in range(W):
         step_device()
     ex.synchronize()
@@ -279,24 +299,47 @@ def own_arm(args):
     ex.synchronize(); torch.cuda.synchronize(); sharding.barrier()
     dev_ms = e0.elapsed_time(e1)
     launches = ex.launch_count - l0
+    dev_ms_max = sharding.max_over_ranks(dev_ms)
+    value = world * B * K / (dev_ms_max / 1e3)
+
+    # ---- sustained: >= 2 s of back-to-back steps, its own clock sample beside it (the K-step window above is a burst)
+    sustained = None
+    if full and args.sustained_s > 0:
+        Ks = max(K, int(np.ceil(args.sustained_s * 1e3 / (dev_ms / K))))
+        s2 = ClockSampler(sampler.index) if rank == 0 else None
+        if s2:
+            s2.start()
+            time.sleep(0.3)
+        sharding.barrier(); torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(Ks):
+            step_device()
+        e1.record(stream)
+        ex.synchronize(); torch.cuda.synchronize(); sharding.barrier()
+        sus_ms = sharding.max_over_ranks(e0.elapsed_time(e1))
+        sustained = {"value": world * B * Ks / (sus_ms / 1e3), "unit": UNIT, "steps": Ks, "seconds": sus_ms / 1e3,
+                     "ms_per_step": sus_ms / Ks, "clocks": s2.stop() if s2 else None}
+
     # second pass of K steps with per-stage CUDA events (each kernel then runs alone on the stream, i.e. without the
-    # blur/FAST overlap of the timed pass): the per-kernel durations behind the roofline table
+    # FAST / pyramid overlap of the timed pass): the per-kernel durations behind the roofline table
     ex.stage_timing(True)
     for _ in range(K):
         step_device()
     ex.synchronize()
     stages = ex.stage_times()
     ex.stage_timing(False)
-    dev_ms_max = sharding.max_over_ranks(dev_ms)
-    value = world * B * K / (dev_ms_max / 1e3)
+
+    # ---- what the host side of the box can feed: pinned -> device copies of the step's input, no kernels, all ranks at once
+    chunks = 4 if B >= 16 else (2 if B >= 4 else 1)
+    ceil_ms = h2d_ceiling(host, dev, 10, chunks, sharding, torch)
+    in_bytes = nimgs * h * pitch
+    ceil_gbs = world * in_bytes / (ceil_ms / 1e3) / 1e9
 
     # ---- e2e through the C ABI (orbx_extract_batch, the call the C++ adapter makes): pinned HOST frames in,
     #      keypoints + descriptors (+ pyramid for stereo) back in host memory when the call returns
-    import ctypes as C
-    from orbslam2_with_quadrics_b200 import _capi
     capi = _capi.lib()
     views = [hnp[i, :, :w] for i in range(nimgs)]
-    T = max(1, min(args.e2e_threads, B))          # host threads, one handle each (the pattern of src/Frame.cc:78-81)
+    T = max(1, min(args.e2e_threads if args.e2e_threads > 0 else auto_threads(world), B))   # host threads, one handle each (src/Frame.cc:78-81)
     per = [list(range(t * B // T * nimg, (t + 1) * B // T * nimg)) for t in range(T)]        # image indices per thread
     exs2 = [ORBextractor(nf, sf, nl, it, mt, device=local, max_batch=len(per[t]), download_pyramid=need_pyr) for t in range(T)]
     call = []
@@ -313,6 +356,8 @@ def own_arm(args):
                         (_capi.OrbxStereoResult * max(np_t, 1))(), np_t))
 
     def worker(t, steps):
+        if args.numa_bind:
+            sharding.bind_to_gpu_numa(local)
         hd, n_t, p_t, s_t, r_t = call[t]
         lf, rf, sres, np_t = st_args[t]
         for _ in range(steps):
@@ -340,8 +385,7 @@ def own_arm(args):
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     sharding.barrier()
-    e2e_ms = wall * 1e3              # blocking host calls: wall clock between synchronised points, max over ranks below
-    e2e_ms_max = sharding.max_over_ranks(e2e_ms)
+    e2e_ms_max = sharding.max_over_ranks(wall * 1e3)   # blocking host calls: wall clock between synchronised points, slowest rank
     e2e_value = world * B * Ke / (e2e_ms_max / 1e3)
     out = [kd for t in range(T) for kd in exs2[t]._copy_results(call[t][4], call[t][1])]
     n_out = int(np.mean([len(k) for k, _ in out]))
@@ -351,11 +395,20 @@ def own_arm(args):
     d2h = nimgs * kept_cap * 60 + 4 * (nimgs * (4 * nl + 1) + 16) + (nimgs * slab if need_pyr else 0)   # what the library copies
     if stereo_dev:
         d2h += nimgs * kept_cap * 8 + 4 * (nimgs * (4 * nl + 1) + 16)     # mvuRight + mvDepth of the batch, counters again
-    clocks = sampler.stop() if rank == 0 else None
+    e2e_in_gbs = world * nimgs * w * h * Ke / (e2e_ms_max / 1e3) / 1e9
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nimgs * w * h, "d2h_bytes_per_step": d2h,
+           "steps": Ke, "pyramid_d2h": need_pyr, "host_threads": T,
+           "stereo_match": ("device (orbx_stereo_match inside the timed region)" if stereo_dev else "host consumer (pyramid D2H)") if nimg == 2 else None,
+           "call": "orbx_extract_batch (C ABI), %d frames per call per thread, pinned host frames" % (B // T),
+           "h2d_ceiling_gbs": ceil_gbs, "h2d_achieved_gbs": e2e_in_gbs, "frac_of_h2d_ceiling": e2e_in_gbs / ceil_gbs,
+           "h2d_ceiling_note": "pinned->device copies of the same %d bytes per rank per step (%d copies), no kernels, all %d ranks at once; "
+                               "aggregate over ranks, slowest rank's time" % (in_bytes, chunks, world)}
+    for e in exs2:
+        e.close()
 
     # ---- per-frame latency through the C ABI, batch = 1 frame (rank 0 reports)
-    lat = None
-    if rank == 0 and args.latency_frames > 0:
+    lat = dropin = None
+    if full and rank == 0 and args.latency_frames > 0:
         ex1 = ORBextractor(nf, sf, nl, it, mt, device=local, max_batch=nimg, download_pyramid=need_pyr)
         r1 = (_capi.OrbxResult * nimg)()
         psz = C.sizeof(C.c_void_p)
@@ -377,59 +430,144 @@ def own_arm(args):
                "batch": 1, "path": "C ABI, pinned host in, keypoints+descriptors out" + (", pyramid D2H" if need_pyr else "") +
                        (", stereo match on device, mvuRight+mvDepth out" if stereo_dev else "")}
         ex1.close()
+        # ---- the drop-in's defaults (cpp/ORBextractor.cc: max_batch = 1, download_pyramid = 1, the caller's pageable
+        #      cv::Mat): what Frame::ExtractORB (src/Frame.cc:247-253) gets without touching a single setting
+        exd = ORBextractor(nf, sf, nl, it, mt, device=local, max_batch=1, download_pyramid=True)
+        pageable = [np.array(imgs[i], copy=True, order="C") for i in range(min(len(imgs), DISTINCT_FRAMES))]
+        rd = (_capi.OrbxResult * 1)()
+        for i in range(5):
+            _capi.check(capi.orbx_extract(exd._h, pageable[i % len(pageable)].ctypes.data, w, h, w, rd), exd._h)
+        nd = max(50, min(args.latency_frames, 300))
+        td = []
+        tA = time.perf_counter()
+        for i in range(nd):
+            im = pageable[i % len(pageable)]
+            t0 = time.perf_counter()
+            rc = capi.orbx_extract(exd._h, im.ctypes.data, w, h, w, rd)
+            td.append(time.perf_counter() - t0)
+            _capi.check(rc, exd._h)
+        tB = time.perf_counter()
+        td = np.asarray(td) * 1e3
+        dropin = {"p50_ms": float(np.percentile(td, 50)), "p99_ms": float(np.percentile(td, 99)), "images_per_s": nd / (tB - tA),
+                  "images": nd, "path": "orbx_extract, max_batch 1, download_pyramid 1 (%.1f MB D2H per image), pageable input, "
+                                        "one host thread: the C++ adapter's defaults" % (slab / 1e6)}
+        exd.close()
 
-    if world > 1:
-        sharding.barrier()
-        torch.distributed.destroy_process_group()
-    if rank != 0:
-        return 0
+    ex.close()
+    del dev, host
+    torch.cuda.empty_cache()
     # ---- roofline of the whole step and of each stage kernel
-    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_file):
-        peak, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = balg * B * K / (dev_ms / 1e3) / 1e9
     stage_rows = []
     for nm, ms, ln in stages:
         sb = stage_bytes.get(nm, 0) * nimgs * K
         stage_rows.append({"kernel": nm, "ms_per_step": ms / K, "launches_per_step": ln / K,
                            "share": ms / max(sum(m for _, m, _ in stages), 1e-9),
                            "alg_gbs": (sb / (ms / 1e3) / 1e9) if ms > 0 else None})
-    dom = max(stage_rows, key=lambda r: r["ms_per_step"])
-    traffic = None
+    return {"name": name, "B": B, "nimgs": nimgs, "balg": balg, "value": value, "dev_ms": dev_ms, "dev_ms_max": dev_ms_max,
+            "launches": int(launches), "stages": stage_rows, "e2e": e2e, "latency": lat, "dropin": dropin, "sustained": sustained,
+            "n_out": n_out, "cand": cand_per_level, "retries": retries_per_level, "in_mb": nimgs * h * pitch / 1e6, "pyr_mb": nimgs * slab / 1e6}
+
+
+def auto_threads(world):
+    """Host threads per rank in the e2e leg: 4 measured best on one GPU (640x480: 2 threads 76.8k, 3-4 threads 99.9k
+    frames/s); with many ranks on one host the threads of all ranks share the cores (plus one nvidia-smi sampler)."""
+    return max(1, min(4, host_cores() // max(1, 2 * world)))
+
+
+def roofline_of(m, K, peak, peak_src, name):
+    achieved = m["balg"] * m["B"] * K / (m["dev_ms"] / 1e3) / 1e9
+    dom = max(m["stages"], key=lambda r: r["ms_per_step"])
+    traffic, traffic_note = None, "no ncu capture on file for this config"
     tf = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(tf):
         try:
-            t = json.load(open(tf)).get(name)
-            traffic = t["bytes_per_frame"] * B if t else None      # per launch sequence, like `achieved`
+            doc = json.load(open(tf))
+            t = doc.get(name)
+            if t and t.get("source_hash") == source_hash():
+                traffic = t["bytes_per_frame"] * m["B"]      # per launch sequence, like `achieved`
+                traffic_note = t.get("source")
+            elif t:
+                traffic_note = "stale: the capture on file is of source tree %s, this tree is %s" % (t.get("source_hash"), source_hash())
         except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "scope": "whole step (all stage kernels of the batch); algorithmic bytes %d per frame x %d frames per launch sequence" % (balg, B),
-                "dominant_kernel": dom["kernel"], "stages": stage_rows}
+            pass
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
+            "scope": "whole step (all stage kernels of the batch); algorithmic bytes %d per frame x %d frames per launch sequence" % (m["balg"], m["B"]),
+            "dominant_kernel": dom["kernel"], "stages": m["stages"]}
+
+
+def own_arm(args):
+    import torch
+    from orbslam2_with_quadrics_b200 import sharding
+
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    rank, world, local = sharding.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    numa = (-1, 0)
+    if args.numa_bind:                  # this rank's threads and pinned buffers on the CPUs next to its GPU
+        numa = sharding.bind_to_gpu_numa(local)
+    name = args.config
+    K, W = args.steps, args.warmup
+    sampler = ClockSampler(local if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local])
+    if rank == 0:
+        sampler.start()           # nvidia-smi needs a moment to start: it covers warm-up, the timed region and e2e
+    m = measure_config(args, name, args.batch, K, W, rank, world, local, True, sampler)
+    clocks = sampler.stop() if rank == 0 else None
+
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_file):
+        peak, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    # ---- multi-GPU runs also cover the other multi-GPU configs of BASELINE.json with a short pass each:
+    #      mono_4k in 64-frame batches split over the GPUs (config 5) and stereo_kitti batched per GPU (config 3)
+    extras = []
+    if world > 1 and not args.no_extra_configs:
+        for xname, xB in (("mono_4k", max(1, 64 // world)), ("stereo_kitti", 32)):
+            if xname == name:
+                continue
+            xm = measure_config(args, xname, xB, 5, 3, rank, world, local, False, sampler)
+            if rank == 0:
+                xr = roofline_of(xm, 5, peak, peak_src, xname)
+                extras.append({"config": {"workload": workload_desc(xname), "batch_per_gpu": xB, "frames_per_step": world * xB},
+                               "value": xm["value"], "unit": UNIT, "steps": 5, "warmup": 3, "ms_per_step": xm["dev_ms_max"] / 5,
+                               "roofline": {k: xr[k] for k in ("achieved", "peak", "frac", "unit")},
+                               "e2e": {k: xm["e2e"][k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "host_threads",
+                                                                 "h2d_ceiling_gbs", "frac_of_h2d_ceiling", "stereo_match")}})
+    if world > 1:
+        sharding.barrier()
+        torch.distributed.destroy_process_group()
+    if rank != 0:
+        return 0
+    roofline = roofline_of(m, K, peak, peak_src, name)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
         per = max(8, cores)
         cpu = run_reference_cpu(name, per, 2, 1, cores)
         cpu["opencv_primitives_ms"] = opencv_primitive_times(name)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    B = args.batch
+    line = {"metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": m["dev_ms_max"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_desc(name), "batch_per_gpu": B, "frames_per_step": world * B,
                        "distinct_frames": DISTINCT_FRAMES, "parallelism": "one camera stream per GPU, no collective",
                        "l2_policy": "per-step working set (inputs %.0f MB + pyramids %.0f MB per GPU) exceeds the 126 MB L2" % (
-                           nimgs * h * pitch / 1e6, nimgs * slab / 1e6),
-                       "keypoints_per_image": n_out, "fast_candidates_per_level_frame0": cand_per_level,
-                       "fast_retried_cells_per_level_frame0": retries_per_level},
+                           m["in_mb"], m["pyr_mb"]),
+                       "keypoints_per_image": m["n_out"], "fast_candidates_per_level_frame0": m["cand"],
+                       "fast_retried_cells_per_level_frame0": m["retries"],
+                       "host_placement": {"numa_bind": bool(args.numa_bind), "gpu_numa_node_rank0": numa[0], "cpus_bound_rank0": numa[1],
+                                          "host_cores_visible": host_cores()}},
             "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nimgs * w * h, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "pyramid_d2h": need_pyr, "host_threads": T,
-                    "stereo_match": ("device (orbx_stereo_match inside the timed region)" if stereo_dev else "host consumer (pyramid D2H)") if nimg == 2 else None,
-                    "call": "orbx_extract_batch (C ABI), %d frames per call per thread, pinned host frames" % (B // T)},
-            "latency_ms": lat, "gpu_launches": int(launches), "clocks": clocks}
+            "e2e": m["e2e"], "e2e_dropin": m["dropin"], "sustained": m["sustained"],
+            "latency_ms": m["latency"], "gpu_launches": m["launches"], "clocks": clocks}
+    if extras:
+        line["extra_configs"] = extras
     emit(line)
     return 0
 
@@ -443,7 +581,10 @@ def main():
     ap.add_argument("--config", default="rgbd_1080p", choices=list(fr.CONFIGS))
     ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU (1080p: 32 -> 37.2k, 64 -> 39.4k, 128 -> 40.2k, 256 -> 40.7k frames/s)")
     ap.add_argument("--latency-frames", type=int, default=1000, help="single-frame calls timed for p50/p99 (SURVEY §8d: >= 1000)")
-    ap.add_argument("--e2e-threads", type=int, default=4, help="host threads (one handle each) in the e2e measurement; 4 measured best (640x480: 2 threads 76.8k, 3-4 threads 99.9k frames/s)")
+    ap.add_argument("--e2e-threads", type=int, default=0, help="host threads (one handle each) in the e2e measurement; 0 = auto: min(4, cores / (2 * ranks))")
+    ap.add_argument("--no-numa-bind", dest="numa_bind", action="store_false", help="leave the rank's threads where the scheduler puts them")
+    ap.add_argument("--sustained-s", type=float, default=2.0, help="seconds of back-to-back steps for the `sustained` record (0 = skip)")
+    ap.add_argument("--no-extra-configs", action="store_true", help="multi-GPU runs: skip the short mono_4k / stereo_kitti passes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stereo-match", default="device", choices=["device", "host"],
                     help="stereo configs: run Frame::ComputeStereoMatches on the GPU (pyramids stay in HBM) or leave it to a "

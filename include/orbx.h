@@ -326,6 +326,15 @@ ORBX_API const char* orbx_strerror(int status);
 ORBX_API const char* orbx_last_cuda_error(orbx_handle* h);
 ORBX_API const char* orbx_version(void);
 
+/* ---- Host placement for multi-GPU boxes (one camera stream per GPU, fed from host memory).  Binds the
+ * CALLING thread to the CPUs of the NUMA node the device hangs off (sysfs: /sys/bus/pci/devices/<bus id>/numa_node and
+ * /sys/devices/system/node/node<k>/cpulist), intersected with the CPUs the process may use; threads and pinned
+ * allocations (orbx_create, orbx_alloc_host) made afterwards from this thread inherit the placement (first touch).  Call
+ * it once per feeding thread before orbx_create.  *node = the device's NUMA node (-1: unknown / single node),
+ * *ncpus = CPUs the thread is now bound to (0: affinity left unchanged, e.g. the container exposes no CPU of that node).
+ * The reference has no counterpart: its extractor threads run wherever the scheduler puts them (src/Frame.cc:78-81). */
+ORBX_API int orbx_bind_thread_to_device(int device, int* node, int* ncpus);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,7 @@ SYMBOLS = [
     "orbx_search_by_projection", "orbx_search_by_projection_device", "orbx_search_by_projection_fetch",
     "orbx_search_local_points", "orbx_search_local_points_device",
     "orbx_search_by_bow", "orbx_search_by_bow_device", "orbx_vocabulary_create", "orbx_vocabulary_destroy", "orbx_compute_bow", "orbx_compute_bow_device",
+    "orbx_bind_thread_to_device",
 ]
 GRAY8, BGR8, RGB8, BGRA8, RGBA8 = range(5)
 
@@ -151,6 +152,7 @@ def lib():
     L.orbx_compute_bow.argtypes = [vp, vp, i, C.POINTER(i), i, C.POINTER(OrbxBowResult)]
     L.orbx_compute_bow_device.argtypes = [vp, vp, i, C.POINTER(i), i]
     L.orbx_undistort_grid.argtypes = [vp, i, C.POINTER(i), C.POINTER(C.c_float), C.POINTER(C.c_float), i, C.POINTER(OrbxGridResult)]
+    L.orbx_bind_thread_to_device.argtypes = [i, C.POINTER(i), C.POINTER(i)]
     _lib = L
     return L
 

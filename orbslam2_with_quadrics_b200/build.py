@@ -30,25 +30,30 @@ def nvcc() -> str:
     return "nvcc"
 
 
-def stale() -> bool:
-    if not os.path.exists(LIB):
+LIB_BC = os.path.join(PKG, "liborbx_boundscheck.so")     # -DORBX_BOUNDS_CHECK: device-side traps on every tile / queue / map index
+
+
+def stale(lib: str = LIB) -> bool:
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not stale():
-        return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+def build_library(force: bool = False, verbose: bool = False, bounds_check: bool = False) -> str:
+    lib = LIB_BC if bounds_check else LIB
+    if not force and not stale(lib):
+        return lib
+    cmd = [nvcc()] + NVCC_FLAGS + (["-DORBX_BOUNDS_CHECK"] if bounds_check else []) + (["-Xptxas", "-v"] if verbose else []) + \
+        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", lib]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stdout + r.stderr)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_library(force="--force" in sys.argv, bounds_check=True))

@@ -35,6 +35,7 @@ void ORBextractor::Create()
     cfg.device = g_orbx_device;
     cfg.max_batch = 1;
     cfg.download_pyramid = downloadPyramid_ ? 1 : 0;
+    cfg.candidate_divisor = candidateDivisor_;
     int rc = orbx_create(&cfg, &handle_);
     if (rc != ORBX_OK) { handle_ = 0; orbx_throw(0, rc, "orbx_create"); }
 }
@@ -42,7 +43,7 @@ void ORBextractor::Create()
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels,
                            int _iniThFAST, int _minThFAST):
     handle_(0), nfeatures_(_nfeatures), nlevels_(_nlevels), iniThFAST_(_iniThFAST), minThFAST_(_minThFAST),
-    scaleFactor_(_scaleFactor), downloadPyramid_(true), rgb_(false)
+    scaleFactor_(_scaleFactor), downloadPyramid_(true), rgb_(false), candidateDivisor_(8)
 {
     Create();
     mvImagePyramid.resize(nlevels_);       // reference src/ORBextractor.cc:433
@@ -94,15 +95,27 @@ void ORBextractor::operator()( cv::InputArray _image, cv::InputArray _mask, std:
 
     orbx_result r;
     int rc;
-    if (type == CV_8UC1)
-        rc = orbx_extract(handle_, image.data, image.cols, image.rows, (size_t)image.step, &r);
-    else
+    for (;;)
     {
-        // colour frame: cvtColor on the device (reference src/Tracking.cc:172-255 does it on the CPU first)
-        const unsigned char* p = image.data;
-        const size_t step = (size_t)image.step;
-        const int fmt = type == 16 ? (rgb_ ? ORBX_RGB8 : ORBX_BGR8) : (rgb_ ? ORBX_RGBA8 : ORBX_BGRA8);
-        rc = orbx_extract_batch_color(handle_, 1, &p, image.cols, image.rows, &step, fmt, &r);
+        if (type == CV_8UC1)
+            rc = orbx_extract(handle_, image.data, image.cols, image.rows, (size_t)image.step, &r);
+        else
+        {
+            // colour frame: cvtColor on the device (reference src/Tracking.cc:172-255 does it on the CPU first)
+            const unsigned char* p = image.data;
+            const size_t step = (size_t)image.step;
+            const int fmt = type == 16 ? (rgb_ ? ORBX_RGB8 : ORBX_BGR8) : (rgb_ ? ORBX_RGBA8 : ORBX_BGRA8);
+            rc = orbx_extract_batch_color(handle_, 1, &p, image.cols, image.rows, &step, fmt, &r);
+        }
+        if (rc != ORBX_ERR_CANDIDATE_OVERFLOW || candidateDivisor_ == 1) break;
+        // More FAST corners than the candidate buffers were sized for (w*h / divisor + 1024 per level): the reference has
+        // no such failure mode, so the handle is rebuilt with larger buffers and the frame is run again.  Divisor 1 holds
+        // every pixel of a level, which cannot overflow.
+        candidateDivisor_ = candidateDivisor_ > 2 ? candidateDivisor_ / 2 : 1;
+        orbx_destroy(handle_);
+        handle_ = 0;
+        for (size_t l = 0; l < mvImagePyramid.size(); ++l) mvImagePyramid[l] = cv::Mat();
+        Create();
     }
     if (rc != ORBX_OK) orbx_throw(handle_, rc, "orbx_extract");
 

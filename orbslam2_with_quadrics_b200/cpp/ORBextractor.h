@@ -11,8 +11,9 @@
 //  * The destructor is out of line (it releases the GPU handle).
 //  * mvImagePyramid[l] are non-owning cv::Mat headers over the library's pinned host buffer; as in
 //    the reference they are valid until the next operator() on the same object.
-//  * Errors (CUDA failure, unsupported geometry, candidate overflow) throw std::runtime_error;
-//    there is no silent CPU fallback.
+//  * Errors (CUDA failure, unsupported geometry) throw std::runtime_error; there is no silent CPU
+//    fallback.  A FAST candidate-buffer overflow (pathological texture) is not an error: operator()
+//    rebuilds the handle with larger buffers and runs the frame again.
 #ifndef ORBEXTRACTOR_H
 #define ORBEXTRACTOR_H
 
@@ -129,6 +130,7 @@ private:
     float scaleFactor_;
     bool downloadPyramid_;
     bool rgb_;
+    int candidateDivisor_;      // FAST candidate buffers hold w*h / divisor + 1024 corners per level; halved after an overflow
 };
 
 } //namespace ORB_SLAM

@@ -4,7 +4,9 @@
 // kernels; every pixel, keypoint and descriptor is produced on the GPU (orbx_kernels.cu).
 #include <cuda_runtime.h>
 
+#include <ctype.h>
 #include <math.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -103,6 +105,9 @@ struct orbx_handle {
     unsigned *d_bow, *h_bow;
     double *d_bow_val, *h_bow_val;
     std::vector<int> bow_slot;  // frame -> slot of the last orbx_compute_bow (-1: none)
+    // extract generation: bumped by every extraction; the side results (mvKeysUn + mGrid, mvuRight, BoW) remember the
+    // generation they were computed for, and their consumers refuse stale ones instead of matching against an old frame
+    unsigned long long gen = 0, un_gen = ~0ull, st_gen = ~0ull, bow_gen = ~0ull;
     cudaEvent_t ev_stereo;
     int last_n;
     bool pyramid_valid;
@@ -643,6 +648,7 @@ int enqueue_pipeline(orbx_handle* h, int n, const uint8_t* d_imgs, size_t pitch,
         CK(h, cudaStreamWaitEvent(h->stream, h->ev_join[i], 0));
     }
     h->last_n = n;
+    ++h->gen;
     h->pyramid_valid = false;
     return ORBX_OK;
 }
@@ -690,7 +696,51 @@ int finish_results(orbx_handle* h, int n, orbx_result* results) {
 
 extern "C" {
 
-const char* orbx_version(void) { return "orbx-b200 0.1 (sm_100a)"; }
+const char* orbx_version(void) { return "orbx-b200 0.2 (sm_100a)"; }
+
+int orbx_bind_thread_to_device(int device, int* node_out, int* ncpus_out) {
+    if (node_out) *node_out = -1;
+    if (ncpus_out) *ncpus_out = 0;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) {
+        cudaGetLastError();
+        return ORBX_ERR_NO_DEVICE;
+    }
+    for (char* c = bus; *c; ++c) *c = (char)tolower((unsigned char)*c);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    int node = -1;
+    if (FILE* f = fopen(path, "r")) {
+        if (fscanf(f, "%d", &node) != 1) node = -1;
+        fclose(f);
+    }
+    if (node_out) *node_out = node;
+    if (node < 0) return ORBX_OK;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    FILE* f = fopen(path, "r");
+    if (!f) return ORBX_OK;
+    char list[4096] = {0};
+    const bool got = fgets(list, sizeof list, f) != nullptr;
+    fclose(f);
+    if (!got) return ORBX_OK;
+    cpu_set_t allowed, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return ORBX_OK;
+    int n = 0;
+    for (char* p = list; *p;) {                       // "0-31,64-95"
+        char* e;
+        const long a = strtol(p, &e, 10);
+        if (e == p) break;
+        long b = a;
+        if (*e == '-') { p = e + 1; b = strtol(p, &e, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c)
+            if (CPU_ISSET((int)c, &allowed)) { CPU_SET((int)c, &want); ++n; }
+        p = (*e == ',') ? e + 1 : e;
+        if (*e != ',') break;
+    }
+    if (n > 0 && sched_setaffinity(0, sizeof want, &want) == 0 && ncpus_out) *ncpus_out = n;
+    return ORBX_OK;
+}
 
 const char* orbx_strerror(int s) {
     switch (s) {
@@ -868,7 +918,9 @@ int orbx_extract_batch(orbx_handle* h, int n, const uint8_t* const* imgs, int wi
                 // pinned buffer (a ring of camera frames) go as ONE copy
                 int j = i + 1;
                 while (j < f1 && imgs[j] == imgs[j - 1] + fbytes && (strides ? strides[j] : (size_t)width) == stride) ++j;
-                CK(h, cudaMemcpyAsync(h->d_input + i * fbytes, imgs[i], (size_t)(j - i) * fbytes, cudaMemcpyHostToDevice, h2d));
+                // the ABI promises `width` valid bytes in a row, not `stride`: the last row of the run ends at its last pixel
+                CK(h, cudaMemcpyAsync(h->d_input + i * fbytes, imgs[i], (size_t)(j - i) * fbytes - (pitch - (size_t)width),
+                                      cudaMemcpyHostToDevice, h2d));
                 i = j;
                 continue;
             }
@@ -907,6 +959,7 @@ int orbx_extract_batch(orbx_handle* h, int n, const uint8_t* const* imgs, int wi
     if (!one)
         for (int i = 0; i < ns; ++i) CK(h, cudaStreamSynchronize(h->ks[i]));
     h->last_n = n;
+    ++h->gen;
     return finish_results(h, n, results);
 }
 
@@ -970,6 +1023,7 @@ int stereo_enqueue(orbx_handle* L, orbx_handle* R, int npairs, const int* left_f
         CK(L, cudaEventRecord(L->ev_stereo, R->stream));
         CK(L, cudaStreamWaitEvent(st, L->ev_stereo, 0));
     }
+    L->st_gen = L->gen;
     CK(L, orbx::launch_stereo(L->d_plan, P, L->num_sms, L->d_pyr, L->d_out_kp, L->d_out_desc, L->d_kept_counts(), R->d_pyr,
                               R->d_out_kp, R->d_out_desc, R->d_kept_counts(), L->d_st_pairs, npairs, mbf, mb, L->d_st_u,
                               L->d_st_depth, L->d_st_sad, L->d_st_rows, L->d_st_bucket, st));
@@ -1062,7 +1116,7 @@ int orbx_extract_batch_color(orbx_handle* h, int n, const uint8_t* const* imgs, 
         const bool pinned = cudaPointerGetAttributes(&attr, imgs[i]) == cudaSuccess && attr.type == cudaMemoryTypeHost;
         if (!pinned) cudaGetLastError();
         if (pinned && stride == cp) {
-            CK(h, cudaMemcpyAsync(h->d_color + i * cf, imgs[i], cf, cudaMemcpyHostToDevice, st));
+            CK(h, cudaMemcpyAsync(h->d_color + i * cf, imgs[i], cf - (cp - rowb), cudaMemcpyHostToDevice, st));   // last row: rowb bytes
         } else if (pinned) {
             CK(h, cudaMemcpy2DAsync(h->d_color + i * cf, cp, imgs[i], stride, rowb, (size_t)height, cudaMemcpyHostToDevice, st));
         } else {                                                           // pageable: through the pinned colour staging
@@ -1147,6 +1201,7 @@ int orbx_undistort_grid(orbx_handle* h, int nframes, const int* frames, const fl
     CK(h, cudaStreamSynchronize(st));                                        // the pinned staging of a previous call is free
     for (int i = 0; i < nframes; ++i) h->h_un_frames[i] = frames ? frames[i] : i;
     CK(h, cudaMemcpyAsync(h->d_un_frames, h->h_un_frames, (size_t)nframes * 4, cudaMemcpyHostToDevice, st));
+    h->un_gen = h->gen;
     CK(h, orbx::launch_undistort_grid(h->d_plan, P, h->d_out_kp, h->d_kept_counts(), h->d_un_frames, nframes, cam, distorted, grid,
                                       h->d_un_xy, h->d_un_start, h->d_un_items, st));
     h->launches += 1;
@@ -1188,8 +1243,8 @@ struct SpHostQuery {
 int sp_enqueue(orbx_handle* h, int local, int nq, const SpHostQuery* q, const float* K4, float mbf, float mb, float th, float nnratio,
                int mono, int check_orientation, int use_stereo) {
     if (!h || !q || nq < 1 || nq > h->cfg.max_batch || !h->have_plan) return ORBX_ERR_BAD_ARGS;
-    if (!h->d_un_xy) return ORBX_ERR_BAD_ARGS;                      // orbx_undistort_grid has to run first (mvKeysUn, mGrid)
-    if (use_stereo && !h->d_st_u) return ORBX_ERR_BAD_ARGS;          // mvuRight comes from orbx_stereo_match on this handle
+    if (!h->d_un_xy || h->un_gen != h->gen) return ORBX_ERR_BAD_ARGS;          // orbx_undistort_grid has to run first, for THIS extraction (mvKeysUn, mGrid)
+    if (use_stereo && (!h->d_st_u || h->st_gen != h->gen)) return ORBX_ERR_BAD_ARGS;   // mvuRight comes from orbx_stereo_match on this handle, same extraction
     const OrbxPlan& P = h->plan;
     const size_t kpf = (size_t)P.kept_per_frame;
     if (kpf > 65535) return ORBX_ERR_BAD_ARGS;
@@ -1198,8 +1253,13 @@ int sp_enqueue(orbx_handle* h, int local, int nq, const SpHostQuery* q, const fl
         if (q[i].cur_frame < 0 || q[i].cur_frame >= h->last_n || q[i].n < 0) return ORBX_ERR_BAD_ARGS;
         if (q[i].n && (!q[i].w3 || !q[i].desc || !q[i].obs || !q[i].oct || !q[i].ang)) return ORBX_ERR_BAD_ARGS;
         if (q[i].n > cap) cap = q[i].n;
-        for (int k = 0; k < q[i].n; ++k)
-            if (q[i].oct[k] < 0 || q[i].oct[k] >= P.nlevels) return ORBX_ERR_BAD_ARGS;
+        // A level is validated only for the points the kernels will process: the reference leaves mnTrackScaleLevel
+        // uninitialised until Frame::isInFrustum accepts a point (src/Frame.cc:321, src/MapPoint.cc:32-73), so a skipped
+        // point may legitimately carry garbage there; it is staged as level 0 below.
+        for (int k = 0; k < q[i].n; ++k) {
+            const bool processed = local ? !(q[i].flag && !q[i].flag[k]) : (!(q[i].flag && q[i].flag[k]) && q[i].obs[k] >= 0);
+            if (processed && (q[i].oct[k] < 0 || q[i].oct[k] >= P.nlevels)) return ORBX_ERR_BAD_ARGS;
+        }
     }
     cap = (cap + 3) & ~3;
     if ((size_t)(cap + P.kept_per_frame) * sizeof(int) > 200 * 1024) return ORBX_ERR_BAD_ARGS;
@@ -1267,7 +1327,8 @@ int sp_enqueue(orbx_handle* h, int local, int nq, const SpHostQuery* q, const fl
                 for (size_t k = 0; k < n; ++k) obs[k] = (Q.flag && !Q.flag[k]) ? -1 : (Q.obs[k] < 0 ? 0 : Q.obs[k]);
             else                                                     // pMP && !mvbOutlier (:1356-1360)
                 for (size_t k = 0; k < n; ++k) obs[k] = (Q.flag && Q.flag[k]) ? -1 : Q.obs[k];
-            memcpy(h->h_sp + o_oct + b * 4, Q.oct, n * 4);
+            int* oct = reinterpret_cast<int*>(h->h_sp + o_oct) + b;
+            for (size_t k = 0; k < n; ++k) oct[k] = (obs[k] < 0 || Q.oct[k] < 0 || Q.oct[k] >= P.nlevels) ? 0 : Q.oct[k];
             memcpy(h->h_sp + o_ang + b * 4, Q.ang, n * 4);
         }
         if (local) {
@@ -1460,6 +1521,7 @@ static int bow_enqueue(orbx_handle* h, const orbx_vocabulary* voc, int nframes, 
     unsigned* hf = h->h_bow + 5 * B * kpf + 2 * B;
     for (int i = 0; i < nframes; ++i) hf[i] = (unsigned)(frames ? frames[i] : i);
     h->bow_slot.assign(B, -1);
+    h->bow_gen = h->gen;
     for (int i = 0; i < nframes; ++i) h->bow_slot[hf[i]] = i;
     unsigned* df = h->d_bow + 5 * B * kpf + 2 * B;
     CK(h, cudaMemcpyAsync(df, hf, (size_t)nframes * 4, cudaMemcpyHostToDevice, st));
@@ -1510,7 +1572,8 @@ int orbx_search_by_bow_device(orbx_handle* h, int nq, const orbx_bow_match_query
     int cap = 4;
     for (int i = 0; i < nq; ++i) {
         const orbx_bow_match_query& Q = q[i];
-        if (Q.cur_frame < 0 || Q.cur_frame >= h->last_n || (size_t)Q.cur_frame >= h->bow_slot.size() || h->bow_slot[Q.cur_frame] < 0)
+        if (h->bow_gen != h->gen || Q.cur_frame < 0 || Q.cur_frame >= h->last_n || (size_t)Q.cur_frame >= h->bow_slot.size() ||
+            h->bow_slot[Q.cur_frame] < 0)
             return ORBX_ERR_BAD_ARGS;                               // orbx_compute_bow has to run for the frame first (F.mFeatVec)
         if (Q.n_kf < 0 || Q.n_kf_fv < 0 || Q.n_kf_fv > Q.n_kf) return ORBX_ERR_BAD_ARGS;
         if (Q.n_kf && (!Q.kf_desc || !Q.kf_valid || !Q.kf_angle)) return ORBX_ERR_BAD_ARGS;

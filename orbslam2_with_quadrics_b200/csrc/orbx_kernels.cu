@@ -62,6 +62,16 @@ static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+// -DORBX_BOUNDS_CHECK (the liborbx_boundscheck.so build, tests/test_gpu_bounds.py): every shared-memory tile / queue /
+// score-map / bitmap index of the FAST and describe kernels is checked on the device and a violation traps (the launch
+// fails with cudaErrorLaunchFailure instead of silently reading a neighbour's bytes).  compute-sanitizer is closed on the
+// GPU pool this was developed on; this build is the tool-checked substitute.  Compiled out of the product library.
+#ifdef ORBX_BOUNDS_CHECK
+#define ORBX_BC(cond) do { if (!(cond)) __trap(); } while (0)
+#else
+#define ORBX_BC(cond) do { } while (0)
+#endif
+
 __device__ __forceinline__ int reflect_clamp(int i, int n) {
     if (i < 0) i = -i;
     if (i >= n) i = 2 * (n - 1) - i;
@@ -529,10 +539,15 @@ template <int BW_T>
 __device__ __forceinline__ void fast_cell_path(const OrbxPlan* __restrict__ plan, const uint8_t* __restrict__ tile,
                                                const uint32_t* __restrict__ tile32, int sh, int BW, int ww, int wh,
                                                uint8_t* __restrict__ sc, int SP, uint16_t* __restrict__ queue, int pass0,
-                                               const FastEmit& em, int cell_index, int ox, int oy, int lane) {
+                                               const FastEmit& em, int cell_index, int ox, int oy, int lane, int qcap,
+                                               int tile_bytes_left) {
+    // qcap, tile_bytes_left: queue capacity and bytes from `tile` to the end of the tile buffer (bounds-check build only)
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int BW4 = BW >> 2;
     int count = 0, cn = 0;
+    ORBX_BC((ww - 6) * (wh - 6) <= qcap || ww < 7 || wh < 7);
+    ORBX_BC((wh - 1) * BW + ww + 8 <= tile_bytes_left);                  // last window row + the 2 words of read-ahead
+    (void)qcap; (void)tile_bytes_left;
     if (ww >= 7 && wh >= 7) {
         const int ew = ww - 6;                                       // emission width
         const int G = (ew + 3) >> 2;                                 // 4-pixel groups per row
@@ -605,6 +620,7 @@ __device__ __forceinline__ void fast_cell_path(const OrbxPlan* __restrict__ plan
             for (int i0 = 0; i0 < qn; i0 += 32) {
                 const int i = i0 + lane;
                 const int e = queue[min(i, qn - 1)];                         // clamped: every lane scores a real pixel
+                ORBX_BC((e >> 8) >= 3 && (e >> 8) < wh - 3 && (e & 0xff) >= 3 && (e & 0xff) < ww - 3 && qn <= qcap);
                 int s = fast_score_packed(tile + (e >> 8) * BW + (e & 0xff), BW, t);
                 if (i >= qn) s = 0;
                 const uint32_t bal = __ballot_sync(0xffffffffu, s > 0);
@@ -752,7 +768,7 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
             const int delta = delta0 + cix * L.wCell;                        // byte offset of (window x0 - 1) inside the tile
             fast_cell_path<BW_T>(plan, base + b * TB + delta + 1, reinterpret_cast<const uint32_t*>(base + b * TB) + (delta >> 2),
                                  (delta & 3) * 8, BW, ww, wh, sc, SP, queue, 0, em, cc.ci * L.nColsV + cj, cj * L.wCell,
-                                 cc.ci * L.hCell, lane);
+                                 cc.ci * L.hCell, lane, QN, TB - delta - 1);
         }
         if (NB == 1 && nxt < total) { nc = fast_decode(plan, nxt, l0, l1, spf, first_strip); issue(nc, 0); }
         cur = nxt;
@@ -899,6 +915,8 @@ fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __rest
         em.retry_count = &retry_counts[frame * nlevels + lvl];
         em.cand_cap = L.cand_cap;
         const uint8_t* tile = tbuf + delta0 + 1;                             // byte of strip window pixel (0, 0)
+        ORBX_BC(wh <= BH && delta0 + 1 + sw + 7 <= BW && ncell >= 1 && ncell <= 4);
+        ORBX_BC(!L.strip_ok || (hr <= 32 && ncell * (wCell + 2) <= SP && (hr + 2) * SP <= SBYTES));
         unsigned todo = (1u << ncell) - 1u;                                  // cells of the strip still without a result
         unsigned cell_path = 0;              // cells left to fast_cell_path: bit k = minThFAST pass only, bit 8 + k = both passes
         uint2 nxt2 = make_uint2(ORBX_FS_NONE, 0u);
@@ -974,6 +992,7 @@ fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __rest
                         while (a) {
                             const int bit = __ffs((int)a) - 1;
                             a &= a - 1;
+                            ORBX_BC(wq >= queue && wq < queue + QCAP);
                             *wq++ = (uint16_t)(e0 | bit);
                         }
                     }
@@ -988,14 +1007,17 @@ fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __rest
                     const int wc = ((e >> 5) + 4 * r) & 31;                  // word column (undo the lane rotation of phase 1)
                     const int x = xb0 + 4 * wc + ((e >> 3) & 3);
                     const int y = 3 + ((e >> 7) & 0x18) + r;                 // 8 * group + row
+                    ORBX_BC(y >= 3 && y < wh - 3 && x >= 3 && x < sw - 3 && (y + 3) * BW + delta0 + 1 + x + 3 < TB);
                     int s = fast_score_packed(tile + y * BW + x, BW, t);
                     if (i >= qn) s = 0;
                     const uint32_t bal = __ballot_sync(0xffffffffu, s > 0);
                     if (s > 0) {
                         const int k = ((x - 3) * wrecip) >> 16;              // cell of the strip
                         const int idx = (y - 2) * SP + x - 2 + 2 * k;        // two zero columns between cells
+                        ORBX_BC(k >= 0 && k < ncell && idx > SP && idx < SBYTES - SP - 1);
                         sc[idx] = (uint8_t)s;
                         const int j = cn + __popc(bal & lt_mask);
+                        ORBX_BC((warp + ORBX_FS_WARPS * (j >> 5)) * 32 + (j & 31) < i0 + 32);      // in-place: never ahead of the read position
                         queue[(warp + ORBX_FS_WARPS * (j >> 5)) * 32 + (j & 31)] = (uint16_t)idx;
                     }
                     cn += __popc(bal);
@@ -1006,6 +1028,7 @@ fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __rest
                     const int j = j0 + lane;
                     if (j < cn) {
                         const int idx = queue[(warp + ORBX_FS_WARPS * (j >> 5)) * 32 + (j & 31)];
+                        ORBX_BC(idx > SP && idx < SBYTES - SP - 1 && (idx >> 5) < KBW);
                         const uint8_t* mp = sc + idx;
                         const int m8 = max(max(max((int)mp[-1], (int)mp[1]), max((int)mp[-SP - 1], (int)mp[-SP])),
                                            max(max((int)mp[-SP + 1], (int)mp[SP - 1]), max((int)mp[SP], (int)mp[SP + 1])));
@@ -1023,6 +1046,7 @@ fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __rest
                     uint32_t bits = 0;
                     if (lane < hr) {
                         const int sb = (lane + 1) * SP + k * cstep + 1;
+                        ORBX_BC((sb >> 5) + 1 < KBW && sb + wCell <= SBYTES);
                         bits = __funnelshift_r(kb[sb >> 5], kb[(sb >> 5) + 1], sb & 31) & cmask;
                     }
                     const int c = __popc(bits);
@@ -1085,7 +1109,8 @@ fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __rest
                     const int delta = delta0 + k * wCell;                    // byte offset of (window x0 - 1) inside the tile
                     fast_cell_path<BW_T>(plan, tbuf + delta + 1, reinterpret_cast<const uint32_t*>(tbuf) + (delta >> 2), (delta & 3) * 8,
                                          BW, ww, wh, sc + k * (wCell + 2) - 3 - 2 * SP, SP, myq, (cell_path >> k) & 1u ? 1 : 0, em,
-                                         ci * L.nColsV + cj, cj * wCell, ci * L.hCell, lane);
+                                         ci * L.nColsV + cj, cj * wCell, ci * L.hCell, lane,
+                                         (L.strip_ok && ORBX_FS_WARPS > 1) ? (QCAP >> 1) : QCAP, TB - delta - 1);
                 }
             }
             __syncthreads();                                                 // B7: tile buffer b is free
@@ -1689,6 +1714,7 @@ describe_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restric
                 const float x = px[2 * j + e], y = py[2 * j + e];
                 const int rr = __float2int_rn(__fadd_rn(__fmul_rn(x, b), __fmul_rn(y, a)));    // (:119)
                 const int cc = __float2int_rn(__fsub_rn(__fmul_rn(x, a), __fmul_rn(y, b)));    // (:120)
+                ORBX_BC(rr >= -18 && rr <= 18 && cc >= -18 && cc <= 18 && a4 >= 0 && a4 + cc + 18 < KP_HP_COLS);
                 v[e] = bc[cc * KP_BL_PITCH + rr];
             }
             byte |= (uint32_t)(v[0] < v[1]) << j;

@@ -60,3 +60,15 @@ def sum_over_ranks(value: float) -> float:
 def aggregate_throughput(units_this_rank: float, elapsed_s_this_rank: float) -> float:
     """Whole-job units/s: all ranks' units divided by the slowest rank's time."""
     return sum_over_ranks(units_this_rank) / max_over_ranks(elapsed_s_this_rank)
+
+
+def bind_to_gpu_numa(local_rank: int):
+    """Binds the calling thread (call it first thing in a rank: threads and pinned allocations made afterwards inherit
+    it) to the CPUs of the NUMA node GPU `local_rank` hangs off, through the library's own orbx_bind_thread_to_device
+    (host code stays behind the C ABI).  Returns (numa_node, cpus_bound); cpus_bound == 0 means the affinity was left
+    alone (single-node box, or the container exposes no CPU of that node)."""
+    import ctypes as C
+    from . import _capi
+    node, ncpus = C.c_int(-1), C.c_int(0)
+    _capi.check(_capi.lib().orbx_bind_thread_to_device(int(local_rank), C.byref(node), C.byref(ncpus)))
+    return node.value, ncpus.value

@@ -4,6 +4,7 @@
 //   adapter_main <w> <h> <nfeatures> <scale> <nlevels> <ini> <min> <in.raw> <out.bin>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include "ORBextractor.h"
 
@@ -11,12 +12,19 @@ int main(int argc, char** argv)
 {
     if (argc < 10) return 2;
     const int w = atoi(argv[1]), h = atoi(argv[2]);
+    // ORBX_TEST_DEVICE: CUDA device of the extractors (ORBextractor::SetDevice); ORBX_TEST_STRIDE: row step of the cv::Mat
+    // handed to operator() (> w: an odd, unaligned stride in ordinary pageable memory, like a ROI of a larger frame)
+    if (const char* d = getenv("ORBX_TEST_DEVICE")) ORB_SLAM2::ORBextractor::SetDevice(atoi(d));
+    const size_t step = getenv("ORBX_TEST_STRIDE") ? (size_t)atol(getenv("ORBX_TEST_STRIDE")) : (size_t)w;
+    if (step < (size_t)w) return 2;
     ORB_SLAM2::ORBextractor ex(atoi(argv[3]), (float)atof(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]));
     std::vector<unsigned char> buf((size_t)w * h);
     FILE* f = fopen(argv[8], "rb");
     if (!f || fread(buf.data(), 1, buf.size(), f) != buf.size()) return 3;
     fclose(f);
-    cv::Mat im(h, w, CV_8UC1, buf.data(), (size_t)w);
+    std::vector<unsigned char> strided(step * (size_t)(h - 1) + (size_t)w + 1, 0xA5);      // +1: so that data + 1 is odd-aligned
+    for (int y = 0; y < h; ++y) memcpy(strided.data() + 1 + (size_t)y * step, buf.data() + (size_t)y * w, (size_t)w);
+    cv::Mat im(h, w, CV_8UC1, step == (size_t)w ? buf.data() : strided.data() + 1, step);
     std::vector<cv::KeyPoint> keys(3);                 // must be cleared by the call
     cv::Mat desc;
     ex(cv::Mat(), cv::Mat(), keys, desc);              // empty image: outputs untouched

@@ -41,15 +41,16 @@ def test_adapter_compiles_against_the_reference_api_surface():
         assert sym in out, sym
 
 
-@pytest.mark.gpu
-def test_adapter_matches_oracle(tmp_path):
+def _adapter_vs_oracle(tmp_path, config, seed, env=None):
     from oracle import orb_oracle
     exe = build_adapter()
-    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["stereo_euroc"]
-    img = fr.cluttered_scene(w, h, 31)
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS[config]
+    img = fr.cluttered_scene(w, h, seed)
     raw, outp = tmp_path / "in.raw", tmp_path / "out.bin"
     img.tofile(raw)
-    subprocess.run([exe, str(w), str(h), str(nf), str(sf), str(nl), str(it), str(mt), str(raw), str(outp)], check=True)
+    e = dict(os.environ)
+    e.update(env or {})
+    subprocess.run([exe, str(w), str(h), str(nf), str(sf), str(nl), str(it), str(mt), str(raw), str(outp)], check=True, env=e)
     ro = orb_oracle.ORBextractor(nf, sf, nl, it, mt)(img)
     b = outp.read_bytes()
     n, nlv = np.frombuffer(b, np.int32, 2)
@@ -68,6 +69,29 @@ def test_adapter_matches_oracle(tmp_path):
         lw, lh = np.frombuffer(b, np.int32, 2, off); off += 8
         plane = np.frombuffer(b, np.uint8, (lw + 38) * (lh + 38), off).reshape(lh + 38, lw + 38); off += plane.size
         assert np.array_equal(plane, ro.pyramid[l]), l
+
+
+@pytest.mark.gpu
+def test_adapter_matches_oracle(tmp_path):
+    _adapter_vs_oracle(tmp_path, "stereo_euroc", 31)
+
+
+@pytest.mark.gpu
+def test_adapter_pageable_odd_stride_1080p(tmp_path):
+    """What Frame::ExtractORB hands over in practice: an ordinary (pageable) cv::Mat whose rows do not start on any
+    alignment boundary (step 1933, data pointer odd), at the size the headline number is quoted on.  Goes through the
+    library's row-wise staging path; keypoints, descriptors and every padded pyramid plane bit-exact vs the oracle."""
+    _adapter_vs_oracle(tmp_path, "rgbd_1080p", 77, env={"ORBX_TEST_STRIDE": "1933"})
+
+
+@pytest.mark.gpu
+def test_adapter_on_second_device(tmp_path):
+    """ORBextractor::SetDevice(1): the adapter's handle, its streams, pinned buffers and TMA descriptors on a GPU that is not
+    device 0 (needs a 2-GPU box: `gpurun --gpus 2`)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _adapter_vs_oracle(tmp_path, "stereo_euroc", 32, env={"ORBX_TEST_DEVICE": "1", "ORBX_TEST_STRIDE": "765"})
 
 
 @pytest.mark.gpu

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import match_oracle
-from orbslam2_with_quadrics_b200 import ORBextractor, OrbxError
+from orbslam2_with_quadrics_b200 import ORBextractor, OrbxError, _capi
 from orbslam2_with_quadrics_b200 import frames as fr
 from orbslam2_with_quadrics_b200 import match_cases as mc
 
@@ -263,6 +263,27 @@ def test_local_points_batch_matches_oracle(list_cap, monkeypatch):
     q2 = dict(qs[0]); q2["cur_obs"] = np.full(len(res[0][0]), -1, np.int32)
     n0, m0 = local_oracle(q2, res[0][0], res[0][1], grids[0], gx.GetScaleFactors(), 3.0, 0.8, None)
     assert n == n0 and np.array_equal(m, m0)
+    # Points Frame::isInFrustum never accepted carry an UNINITIALISED mnTrackScaleLevel in the reference (set only at
+    # src/Frame.cc:321, neither MapPoint constructor touches it, src/MapPoint.cc:32-73): garbage levels on skipped points
+    # must not fail the call nor change the result; a garbage level on a point that IS processed is still refused.
+    q3 = {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in qs[0].items()}
+    skipped = np.flatnonzero(q3["in_view"] == 0)
+    assert len(skipped) > 10
+    q3["scale_level"][skipped[::2]] = np.iinfo(np.int32).min
+    q3["scale_level"][skipped[1::2]] = 12345
+    (n3, m3, _), = gx.search_local_points([q3], 3.0)
+    n0, m0 = local_oracle(qs[0], res[0][0], res[0][1], grids[0], gx.GetScaleFactors(), 3.0, 0.8, None)
+    assert n3 == n0 and np.array_equal(m3, m0)
+    q4 = {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in qs[0].items()}
+    q4["scale_level"][np.flatnonzero(q4["in_view"] != 0)[0]] = nl
+    with pytest.raises(OrbxError) as ei:
+        gx.search_local_points([q4], 3.0)
+    assert ei.value.status == _capi.ERR_BAD_ARGS
+    # a new extraction invalidates mvKeysUn / mGrid: matching against the previous frame's grid is refused, not silent
+    gx.extract_batch([fr.cluttered_scene(w, h, 900)])
+    with pytest.raises(OrbxError) as ei:
+        gx.search_local_points([dict(qs[0], cur_frame=0)], 3.0)
+    assert ei.value.status == _capi.ERR_BAD_ARGS
     gx.close()
 
 

@@ -17,12 +17,12 @@ def _same(ro, kp, ds, pyr):
         assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("name", ["mono_tum", "stereo_euroc", "stereo_kitti", "rgbd_1080p"])
+@pytest.mark.parametrize("name", ["mono_tum", "stereo_euroc", "stereo_kitti", "rgbd_1080p", "mono_4k"])
 @pytest.mark.parametrize("seed", [1234, 2234])
 def test_full_path_matches_reference_tu(ref_available, name, seed):
     w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS[name]
-    if name == "rgbd_1080p" and seed != 1234:
-        pytest.skip("one 1080p seed keeps the CPU suite short")
+    if name in ("rgbd_1080p", "mono_4k") and seed != 1234:
+        pytest.skip("one 1080p / 4K seed keeps the CPU suite short")
     img = fr.cluttered_scene(w, h, seed)
     ro = orb_oracle.ORBextractor(nf, sf, nl, it, mt)(img)
     r = ref_available.RefORBextractor(nf, sf, nl, it, mt)

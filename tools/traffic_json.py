@@ -1,8 +1,12 @@
 #!/usr/bin/env python3
 """profiles/dominant_kernel_traffic.json from an `ncu --set full` capture of ONE half-batch launch sequence:
 dram__bytes_read.sum + dram__bytes_write.sum of every stage kernel, per frame (feeds bench.py's roofline.traffic).
-usage: traffic_json.py <file.ncu-rep> <frames in the captured launch sequence> [config name]"""
-import csv, json, subprocess, sys, collections
+usage: traffic_json.py <file.ncu-rep> <frames in the captured launch sequence> [config name]
+source_hash = sha256 of csrc/ at the time of writing: run it on the tree the capture was taken from; bench.py reports
+roofline.traffic = null when the hash on file is not the hash of the tree it runs."""
+import csv, json, os, subprocess, sys, collections
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import source_hash
 rep, frames = sys.argv[1], int(sys.argv[2])
 name = sys.argv[3] if len(sys.argv) > 3 else "rgbd_1080p"
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -17,7 +21,7 @@ for r in data:
     k = r[ki].split("(")[0].replace("void ", "").replace("orbx::", "")
     per[k] = per.get(k, 0.0) + to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw])
 total = sum(per.values())
-doc = {name: {"bytes_per_frame": total / frames,
+doc = {name: {"bytes_per_frame": total / frames, "source_hash": source_hash(),
               "per_kernel_MB_per_%d_frames" % frames: {k: v / 1e6 for k, v in per.items()},
               "source": "%s: dram__bytes_read.sum + dram__bytes_write.sum of the %d launches of one %d-frame half-batch (ncu --set full)" % (
                   rep.split("/")[-1], len(data), frames)}}
