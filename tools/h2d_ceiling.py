@@ -49,6 +49,8 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--chunks", type=int, default=4, help="copies per step (the bench sends 4 sub-batches per step)")
     args = ap.parse_args()
+    real_stdout = os.fdopen(os.dup(1), "w")       # NCCL prints its banner on fd 1: keep the JSON line on a private copy
+    os.dup2(2, 1)
     rank, world, local = sharding.init_from_env()
     torch.cuda.set_device(local)
     cpus_before = sorted(os.sched_getaffinity(0))
@@ -97,7 +99,8 @@ def main():
                 "topo": topo}
         best = max(out[m]["aggregate_gbs"] for m in out)
         line["frames_per_s_if_1080p"] = round(best * 1e9 / (1920 * 1080), 0)
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         torch.distributed.destroy_process_group()
 
