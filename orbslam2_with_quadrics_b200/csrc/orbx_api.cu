@@ -120,14 +120,14 @@ struct orbx_handle {
     double stage_ms[ST_COUNT];
     int stage_launches[ST_COUNT];
 
-    int counters_count() const { return cfg.max_batch * (4 * plan.nlevels + 1) + 2 * kMaxChunks; }
+    int counters_count() const { return cfg.max_batch * (4 * plan.nlevels + 1) + ORBX_MAXL * kMaxChunks; }
     int* d_level_counts() const { return d_counters; }
     int* d_sorted_counts() const { return d_counters + cfg.max_batch * plan.nlevels; }
     int* d_kept_counts() const { return d_counters + 2 * cfg.max_batch * plan.nlevels; }
     int* d_status() const { return d_counters + 3 * cfg.max_batch * plan.nlevels; }
     int* d_work_counter() const { return d_counters + cfg.max_batch * (3 * plan.nlevels + 1); }
-    int* d_retry_counts() const { return d_counters + cfg.max_batch * (3 * plan.nlevels + 1) + 2 * kMaxChunks; }
-    const int* h_retry_counts() const { return h_counters + cfg.max_batch * (3 * plan.nlevels + 1) + 2 * kMaxChunks; }
+    int* d_retry_counts() const { return d_counters + cfg.max_batch * (3 * plan.nlevels + 1) + ORBX_MAXL * kMaxChunks; }
+    const int* h_retry_counts() const { return h_counters + cfg.max_batch * (3 * plan.nlevels + 1) + ORBX_MAXL * kMaxChunks; }
     const int* h_level_counts() const { return h_counters; }
     const int* h_sorted_counts() const { return h_counters + cfg.max_batch * plan.nlevels; }
     const int* h_kept_counts() const { return h_counters + 2 * cfg.max_batch * plan.nlevels; }
@@ -346,52 +346,60 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
     P->node_cap = round_up(P->node_cap, 32);
     if (P->max_cell_w < 7) P->max_cell_w = 7;
     if (P->max_cell_h < 7) P->max_cell_h = 7;
-    // FAST tiling (env overrides are for tuning / A-B runs).  Product: fast_strips_kernel, a warp takes a strip of up to 4
-    // cells whose scoring pixels fit the 32 word columns of its lanes (wCell <= 31: 4 cells, 32: 3), single tile buffer.
-    // ORBX_FAST_LEGACY=1: fast_cells_kernel (round 1), 2 cells per tile (1 for latency-mode handles), NB tile buffers.
+    // FAST tiling (env overrides are for tuning / A-B runs).  Product: fast_strips_kernel, a CTA takes a strip of up to 4
+    // cells whose scoring pixels fit the 32 word columns of a warp's lanes (wCell <= 31: 4 cells, 32: 3).  Levels whose cells
+    // are larger than 32 x 32 (tiny levels of unusual geometries) and everything under ORBX_FAST_LEGACY=1 go to
+    // fast_cells_kernel (round 1: a warp per cell), 2 cells per tile (1 for latency-mode handles), NB tile buffers.
     const char* e_nc = getenv("ORBX_FAST_NC"); const char* e_nb = getenv("ORBX_FAST_NB"); const char* e_w = getenv("ORBX_FAST_WARPS");
-    const char* e_q = getenv("ORBX_FAST_QCAP");
     P->fast_legacy = getenv("ORBX_FAST_LEGACY") != nullptr;
     P->fast_nc = e_nc ? atoi(e_nc) : (P->fast_legacy ? (h->cfg.max_batch <= 2 ? 1 : 2) : 4);
     P->fast_nb = (e_nb && P->fast_legacy) ? atoi(e_nb) : 1;
-    P->fast_warps = e_w ? atoi(e_w) : 8;
+    P->fast_warps = e_w ? atoi(e_w) : 8;                                          // fast_cells_kernel: warps per CTA
     if (P->fast_nc < 1 || P->fast_nc > (P->fast_legacy ? 8 : 4) || P->fast_nb < 1 || P->fast_nb > 2 || P->fast_warps < 1 ||
         P->fast_warps > ORBX_FAST_WARPS)
         return ORBX_ERR_BAD_ARGS;
-    int strips = 0, bw = 0, sp = P->max_cell_w;
+    int bw = 0, cbw = 64, cbh = 7;
     for (int l = 0; l < n; ++l) {
         OrbxLevel& L = P->lv[l];
         L.wcell_recip = 65536 / L.wCell + 1;
         L.strip_ok = !P->fast_legacy && L.wCell <= 32 && L.hCell <= 32;
-        L.strip_nc = P->fast_legacy ? P->fast_nc : (L.strip_ok ? std::max(1, std::min(P->fast_nc, 125 / L.wCell)) : 1);
-        L.strip_base = strips;
+        L.strip_nc = L.strip_ok ? std::max(1, std::min(P->fast_nc, 125 / L.wCell))
+                                : (P->fast_legacy ? P->fast_nc : (h->cfg.max_batch <= 2 ? 1 : 2));
         L.strips_x = (L.nColsV + L.strip_nc - 1) / L.strip_nc;
-        strips += L.strips_x * L.nRowsV;
         // 16-aligned TMA start (delta <= 15), 1-byte shift, the strip's cell steps + the 6-px overlap, 2 words of read-ahead
-        bw = std::max(bw, L.strip_nc * L.wCell + 6 + 24);
-        if (L.strip_ok) sp = std::max(sp, L.strip_nc * (L.wCell + 2));
+        if (L.strip_ok) {
+            bw = std::max(bw, L.strip_nc * L.wCell + 6 + 24);
+        } else {
+            cbw = std::max(cbw, L.strip_nc * L.wCell + 6 + 24);
+            cbh = std::max(cbh, std::min(L.hCell + 6, L.maxBY - ORBX_BOX));
+        }
     }
-    P->strips_per_frame = strips;
-    {   // strip table of a frame, stored behind the resize tap tables (8-byte units)
+    {   // strip table of a frame, stored behind the resize tap tables (8-byte units), in four segments so that a launch
+        // covers a contiguous range: (strip levels | big-cell levels) x (levels 0-1, whose FAST starts early | levels 2+)
         std::vector<uint32_t> tab;
-        for (int l = 0; l < n; ++l)
-            for (int i = 0; i < P->lv[l].nRowsV; ++i)
-                for (int j = 0; j < P->lv[l].strips_x; ++j)
-                    tab.push_back((uint32_t)l | ((uint32_t)i << 4) | ((uint32_t)(j * P->lv[l].strip_nc) << 16));
+        for (int seg = 0; seg < 4; ++seg) {
+            P->seg_first[seg] = (int)tab.size();
+            for (int l = 0; l < n; ++l) {
+                if ((P->lv[l].strip_ok != 0) != (seg < 2) || (l < 2) != ((seg & 1) == 0)) continue;
+                for (int i = 0; i < P->lv[l].nRowsV; ++i)
+                    for (int j = 0; j < P->lv[l].strips_x; ++j)
+                        tab.push_back((uint32_t)l | ((uint32_t)i << 4) | ((uint32_t)(j * P->lv[l].strip_nc) << 16));
+            }
+            P->seg_count[seg] = (int)tab.size() - P->seg_first[seg];
+        }
+        P->strips_per_frame = (int)tab.size();
         if (tab.size() & 1) tab.push_back(0);
         P->strip_tab_off = (int)taps->size();
         const OrbxTap* raw = reinterpret_cast<const OrbxTap*>(tab.data());
         taps->insert(taps->end(), raw, raw + tab.size() / 2);
     }
-    P->fast_bw = round_up(bw, 16);
-    if (!P->fast_legacy) P->fast_bw = P->fast_bw <= 96 ? 96 : P->fast_bw <= 128 ? 128 : P->fast_bw <= 160 ? 160 : P->fast_bw;
-    P->fast_bh = P->max_cell_h;
-    P->fast_sp = round_up(sp, 4);
-    // survivor queue of a strip; its halves are the private queues of the two warps that redo single cells (<= 32 x 32 pixels)
-    P->fast_qcap = std::max(e_q ? atoi(e_q) : 2048, std::max(2048, (P->max_cell_w - 6) * (P->max_cell_h - 6)));
-    if (P->fast_bw > 256 || P->fast_bh > 127 || P->max_cell_w > 250) return ORBX_ERR_BAD_GEOMETRY;
-    if (!P->fast_legacy && P->fast_bw > 160) return ORBX_ERR_BAD_GEOMETRY;       // cells wider than 130 px: no such level (w >= 62)
-    if (!P->fast_legacy) P->fast_warps = ORBX_FS_WARPS;                           // a CTA per strip
+    P->fast_bw = bw <= 96 ? 96 : bw <= 128 ? 128 : 160;                           // fast_strips_kernel instantiations
+    P->fast_bh = ORBX_FS_BH;
+    if (bw > 160) return ORBX_ERR_BAD_GEOMETRY;                                   // 4 cells of <= 31 px: cannot happen
+    cbw = round_up(cbw, 16);
+    P->cells_bw = cbw <= 64 ? 64 : cbw <= 96 ? 96 : cbw <= 128 ? 128 : cbw;       // fast_cells_kernel<64 / 96 / 128 / any>
+    P->cells_bh = cbh;
+    if (P->cells_bw > 256 || P->cells_bh > 127 || P->max_cell_w > 250) return ORBX_ERR_BAD_GEOMETRY;
     P->cells_per_frame = cells;
     P->cand_per_frame = cand;
     P->kept_per_frame = kept;
@@ -409,6 +417,7 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
         P->umax[i] = h->umax[i];
         if (h->umax[i] != kUmax[i]) return ORBX_ERR_BAD_ARGS;
     }
+    while (P->fast_warps > 1 && orbx::fast_smem_bytes(*P) > 200 * 1024) --P->fast_warps;
     if (orbx::fast_smem_bytes(*P) > 200 * 1024 || orbx::octree_smem_bytes(*P) > 200 * 1024) return ORBX_ERR_BAD_GEOMETRY;
     return ORBX_OK;
 }
@@ -530,29 +539,46 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
     int* retry_counts = h->d_retry_counts() + f0 * L;
     // Two schedules.  With per-stage timing on, every kernel runs alone on `st`, so its duration is its own.
     // Otherwise the dependency graph is exploited with a side stream:
-    //   st : pyramid L0..1 | pyramid L2..  (small, latency-bound levels)  | FAST L2.. | octree | describe
-    //   aux:               | FAST L0..1 (needs only those levels)         |
+    //   st : pyramid L0..1 | pyramid L2..  (small, latency-bound levels)  | FAST L2.. (strips)            | octree | describe
+    //   aux:               | FAST L0..1 (needs only those levels)         | FAST of levels with big cells |
     int si = 0;
     for (int i = 1; i < 4; ++i) if (st == h->ks[i]) si = i;
     const bool overlap = ev == 0;
     const int ls = (overlap && L > 2) ? 2 : 0;                       // levels [0, ls) get their own FAST launch
     cudaStream_t ax = h->aux[si];
-    int* wc = h->d_work_counter() + 2 * chunk;
+    int* wc = h->d_work_counter() + ORBX_MAXL * chunk;                // FAST work counters of this chunk, one per level
     if (ev) CK(h, cudaEventRecord(ev[ST_PYRAMID], st));
     for (int l = 0; l < L; ++l) {
         orbx::launch_pyr_level(h->d_plan, P, l, n, h->num_sms, d_imgs, pitch, frame_stride, pyr, h->d_taps, st);
         if (ls && l == ls - 1) {
             CK(h, cudaEventRecord(h->ev_low[si], st));
             CK(h, cudaStreamWaitEvent(ax, h->ev_low[si], 0));
-            CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), h->d_taps, f0, n, 0, ls, h->num_sms, cand, cell_rec, level_counts,
-                                    wc, status, retry_counts, ax));
+            for (int seg = 0; seg < 4; seg += 2)                         // levels 0-1: strips, then big cells (if any)
+                CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), h->d_taps, f0, n, seg, 1, h->num_sms, cand, cell_rec,
+                                        level_counts, wc, status, retry_counts, ax));
             CK(h, cudaEventRecord(h->ev_fast_low[si], ax));
         }
     }
     if (ev) CK(h, cudaEventRecord(ev[ST_FAST], st));
-    if (ls) CK(h, cudaStreamWaitEvent(st, h->ev_fast_low[si], 0));
-    CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), h->d_taps, f0, n, ls, L, h->num_sms, cand, cell_rec, level_counts,
-                            wc + 1, status, retry_counts, st));
+    if (ls) {
+        // the (tiny) levels whose cells are too large for fast_strips_kernel run beside it on the side stream
+        if (P.seg_count[3] > 0) {
+            CK(h, cudaEventRecord(h->ev_low[si], st));
+            CK(h, cudaStreamWaitEvent(ax, h->ev_low[si], 0));
+            CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), h->d_taps, f0, n, 3, 1, h->num_sms, cand, cell_rec,
+                                    level_counts, wc, status, retry_counts, ax));
+            CK(h, cudaEventRecord(h->ev_fast_low[si], ax));
+        }
+        CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), h->d_taps, f0, n, 1, 1, h->num_sms, cand, cell_rec, level_counts,
+                                wc, status, retry_counts, st));
+        CK(h, cudaStreamWaitEvent(st, h->ev_fast_low[si], 0));           // the quadtree needs every level's candidates
+    } else {
+        for (int seg = 0; seg < 4; seg += 2)                             // all strip levels, then all big-cell levels
+            CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), h->d_taps, f0, n, seg, 2, h->num_sms, cand, cell_rec,
+                                    level_counts, wc, status, retry_counts, st));
+    }
+    const int fast_launches = ls ? (P.seg_count[0] > 0) + (P.seg_count[1] > 0) + (P.seg_count[2] > 0) + (P.seg_count[3] > 0)
+                                 : (P.seg_count[0] + P.seg_count[1] > 0) + (P.seg_count[2] + P.seg_count[3] > 0);
     if (ev) CK(h, cudaEventRecord(ev[ST_OCTREE], st));
     CK(h, orbx::launch_octree(h->d_plan, P, n, cand, cell_rec, cand_sorted, key_node, sorted_counts, kept, kept_counts,
                               status, st));
@@ -564,9 +590,9 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
         h->ev_head = (h->ev_head + 1) % kTimingRing;
         ++h->ev_pending;
         h->stage_launches[ST_PYRAMID] += L;
-        for (int s = ST_FAST; s < ST_COUNT; ++s) h->stage_launches[s] += 1;
+        for (int s = ST_FAST; s < ST_COUNT; ++s) h->stage_launches[s] += s == ST_FAST ? fast_launches : 1;
     }
-    h->launches += L + 3 + (ls ? 1 : 0);
+    h->launches += L + 2 + fast_launches;
     CK(h, cudaGetLastError());
     return ORBX_OK;
 }

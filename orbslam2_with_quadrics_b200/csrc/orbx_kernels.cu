@@ -438,18 +438,15 @@ struct FastStrip {
     int frame, l, ci, cj0;     // NC horizontally adjacent cells starting at column cj0 of cell row ci
 };
 
-// Items of one launch: the strips of levels [l0, l1) of every frame, frame-major.
-__device__ __forceinline__ FastStrip fast_decode(const OrbxPlan* __restrict__ plan, unsigned item, int l0, int l1,
-                                                 unsigned spf, int first_strip) {
+// Items of one launch: table entries [first, first + spf) of every frame, frame-major.  An entry of the strip table
+// (built with the plan) is level | cell row << 4 | first cell << 16.
+__device__ __forceinline__ FastStrip fast_decode(const uint32_t* __restrict__ strip_tab, unsigned item, unsigned spf, int first) {
     FastStrip c;
     c.frame = (int)(item / spf);
-    const int r = (int)(item - (unsigned)c.frame * spf) + first_strip;
-    int l = l0;
-    while (l + 1 < l1 && r >= plan->lv[l + 1].strip_base) ++l;
-    c.l = l;
-    const OrbxLevel& L = plan->lv[l];
-    c.ci = (int)((unsigned)(r - L.strip_base) / (unsigned)L.strips_x);
-    c.cj0 = ((r - L.strip_base) - c.ci * L.strips_x) * L.strip_nc;
+    const uint32_t e = __ldg(strip_tab + first + (int)(item - (unsigned)c.frame * spf));
+    c.l = (int)(e & 15u);
+    c.ci = (int)((e >> 4) & 0xfffu);
+    c.cj0 = (int)(e >> 16);
     return c;
 }
 
@@ -690,14 +687,15 @@ __device__ __forceinline__ void fast_cell_path(const OrbxPlan* __restrict__ plan
 // BW_T: tile pitch known at compile time (ring offsets become immediates); 0 = read it from the plan.
 template <int BW_T>
 __global__ void __launch_bounds__(ORBX_FAST_WARPS * 32, ORBX_FAST_MINB)
-fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, int frame0, int nframes,
-                  int l0, int l1, uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec, int* __restrict__ level_counts,
-                  int* __restrict__ work_counter, int* __restrict__ status, int* __restrict__ retry_counts) {
+fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, const uint32_t* __restrict__ strip_tab,
+                  int frame0, int nframes, int first_strip, int nstrips, uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec,
+                  int* __restrict__ level_counts, int* __restrict__ work_counter, int* __restrict__ status,
+                  int* __restrict__ retry_counts) {
     ORBX_PDL_WAIT();
     extern __shared__ uint8_t fast_smem_raw[];
     __shared__ uint64_t s_bar[ORBX_FAST_WARPS][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int BW = BW_T ? BW_T : plan->fast_bw, BH = plan->fast_bh;
+    const int BW = BW_T ? BW_T : plan->cells_bw, BH = plan->cells_bh;
     const int NB = plan->fast_nb;                                        // tile buffers per warp
     const int TB = (BW * BH + 127) & ~127;                               // tile bytes
     const int QN = (plan->max_cell_w - 6) * (plan->max_cell_h - 6);      // queue entries (u16)
@@ -708,8 +706,7 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
     uint8_t* sc = base + NB * TB;                                        // zero-framed score map
     uint16_t* queue = reinterpret_cast<uint16_t*>(base + NB * TB + SB);  // entries (y << 8) | x, window coordinates
     const int nlevels = plan->nlevels;
-    const int first_strip = plan->lv[l0].strip_base;
-    const unsigned spf = (unsigned)((l1 < nlevels ? plan->lv[l1].strip_base : plan->strips_per_frame) - first_strip);
+    const unsigned spf = (unsigned)nstrips;
     const unsigned total = (unsigned)nframes * spf;
 
     for (int i = lane; i < SB / 4; i += 32) reinterpret_cast<uint32_t*>(sc)[i] = 0;
@@ -740,11 +737,11 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
     unsigned cur = fetch();
     unsigned nxt = fetch();
     FastStrip cc, nc;
-    if (cur < total) { cc = fast_decode(plan, cur, l0, l1, spf, first_strip); issue(cc, 0); }
+    if (cur < total) { cc = fast_decode(strip_tab, cur, spf, first_strip); issue(cc, 0); }
     uint32_t phase[2] = {0, 0};
     int b = 0;
     while (cur < total) {
-        if (NB == 2 && nxt < total) { nc = fast_decode(plan, nxt, l0, l1, spf, first_strip); issue(nc, b ^ 1); }
+        if (NB == 2 && nxt < total) { nc = fast_decode(strip_tab, nxt, spf, first_strip); issue(nc, b ^ 1); }
         const unsigned nxt2 = nxt < total ? fetch() : nxt;
         mbar_wait(&s_bar[warp][b], phase[b]);
         phase[b] ^= 1;
@@ -770,7 +767,7 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
                                  (delta & 3) * 8, BW, ww, wh, sc, SP, queue, 0, em, cc.ci * L.nColsV + cj, cj * L.wCell,
                                  cc.ci * L.hCell, lane, QN, TB - delta - 1);
         }
-        if (NB == 1 && nxt < total) { nc = fast_decode(plan, nxt, l0, l1, spf, first_strip); issue(nc, 0); }
+        if (NB == 1 && nxt < total) { nc = fast_decode(strip_tab, nxt, spf, first_strip); issue(nc, 0); }
         cur = nxt;
         nxt = nxt2;
         cc = nc;
@@ -826,36 +823,35 @@ __device__ __forceinline__ uint32_t fast_pretest_word(const uint32_t* __restrict
 template <int BW_T>
 __global__ void __launch_bounds__(ORBX_FS_WARPS * 32, ORBX_FS_MINB)
 fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, const uint32_t* __restrict__ strip_tab,
-                   int frame0, int nframes, int l0, int l1, uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec,
+                   int frame0, int nframes, int first_strip, int nstrips, uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec,
                    int* __restrict__ level_counts, int* __restrict__ work_counter, int* __restrict__ status,
                    int* __restrict__ retry_counts) {
     ORBX_PDL_WAIT();
-    extern __shared__ uint8_t fast_smem_raw[];
+    // Everything a strip needs lives at fixed shared-memory addresses (sizes are compile-time: the plan only sends levels
+    // with cells <= 32 x 32 here), so every LDS / STS below takes an immediate offset.
+    constexpr int BW = BW_T, BW4 = BW_T / 4;
+    constexpr int BH = ORBX_FS_BH;                                       // tile rows: 32 scoring rows + the 6-px frame
+    constexpr int TB = (BW * BH + 127) & ~127;                           // tile bytes
+    constexpr int SP = BW_T - 20;                                        // score-map pitch >= cells * (wCell + 2)
+    constexpr int SBYTES = SP * (BH - 4);                                // map row = window y - 2
+    constexpr int KBW = (SBYTES + 31) / 32 + 2;                          // kept-corner bitmap, bit index = map index
+    constexpr int QCAP = ORBX_FS_QCAP;
+    __shared__ __align__(128) uint8_t s_tile[ORBX_FS_NBUF * TB];
+    __shared__ __align__(16) uint8_t sc[(SBYTES + 15) & ~15];
+    __shared__ uint32_t kb[KBW];
+    __shared__ __align__(16) uint16_t queue[QCAP];
     __shared__ uint64_t s_bar[2];
     __shared__ int s_wtot[ORBX_FS_WARPS];
     __shared__ uint2 s_item[2];          // (frame or ORBX_FS_NONE, strip_tab entry) of the strip fetched two iterations ahead
     __shared__ unsigned s_redo;
-    constexpr int BW = BW_T, BW4 = BW_T / 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int BH = plan->fast_bh;
-    const int TB = (BW * BH + 127) & ~127;                               // tile bytes
-    const int SP = plan->fast_sp;                                        // score-map pitch
-    const int SBYTES = SP * (BH - 4);                                    // map row = window y - 2
-    const int SB = (SBYTES + 15) & ~15;
-    const int KBW = (SBYTES + 31) / 32 + 2;                              // kept-corner bitmap, bit index = map index
-    const int KB = (KBW * 4 + 15) & ~15;
-    const int QCAP = plan->fast_qcap;
-    uint8_t* smem = fast_smem_raw + ((128 - (smem_u32(fast_smem_raw) & 127)) & 127);
-    uint8_t* sc = smem + ORBX_FS_NBUF * TB;
-    uint32_t* kb = reinterpret_cast<uint32_t*>(smem + ORBX_FS_NBUF * TB + SB);
-    uint16_t* queue = reinterpret_cast<uint16_t*>(smem + ORBX_FS_NBUF * TB + SB + KB);
+    uint8_t* const smem = s_tile;
     const int nlevels = plan->nlevels;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     // thread 0: next work item -> (frame, table entry); the table holds (level, cell row, first cell) of every strip of a frame
     auto fetch = [&](int slot) {
-        const int first_strip = plan->lv[l0].strip_base;
-        const unsigned spf = (unsigned)((l1 < nlevels ? plan->lv[l1].strip_base : plan->strips_per_frame) - first_strip);
+        const unsigned spf = (unsigned)nstrips;
         const unsigned v = (unsigned)atomicAdd(work_counter, 1);
         uint2 r = make_uint2(ORBX_FS_NONE, 0u);
         if (v < (unsigned)nframes * spf) {
@@ -872,7 +868,8 @@ fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __rest
                     ORBX_EDGE + ORBX_BOX + ci * L.hCell, frame0 + (int)c.x);
     };
 
-    for (int i = tid; i < (SB + KB) / 4; i += ORBX_FS_WARPS * 32) reinterpret_cast<uint32_t*>(sc)[i] = 0;
+    for (int i = tid; i < (int)sizeof(sc) / 4; i += ORBX_FS_WARPS * 32) reinterpret_cast<uint32_t*>(sc)[i] = 0;
+    for (int i = tid; i < KBW; i += ORBX_FS_WARPS * 32) kb[i] = 0;
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
@@ -916,12 +913,12 @@ fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __rest
         em.cand_cap = L.cand_cap;
         const uint8_t* tile = tbuf + delta0 + 1;                             // byte of strip window pixel (0, 0)
         ORBX_BC(wh <= BH && delta0 + 1 + sw + 7 <= BW && ncell >= 1 && ncell <= 4);
-        ORBX_BC(!L.strip_ok || (hr <= 32 && ncell * (wCell + 2) <= SP && (hr + 2) * SP <= SBYTES));
+        ORBX_BC(L.strip_ok && hr <= 32 && ncell * (wCell + 2) <= SP && (hr + 2) * SP <= SBYTES);
         unsigned todo = (1u << ncell) - 1u;                                  // cells of the strip still without a result
         unsigned cell_path = 0;              // cells left to fast_cell_path: bit k = minThFAST pass only, bit 8 + k = both passes
         uint2 nxt2 = make_uint2(ORBX_FS_NONE, 0u);
         bool have_next = false;
-        if (L.strip_ok && hr >= 1 && sw >= 7) {
+        if (hr >= 1 && sw >= 7) {
             const int wrecip = L.wcell_recip;
             const int fb = delta0 + 4;                                       // tile byte of the first scoring pixel (window x = 3)
             const int W0 = fb >> 2;
@@ -1096,11 +1093,11 @@ fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __rest
         __syncthreads();                                                     // B6: map / bitmap zero, s_redo consumed
         if (!have_next) nxt2 = s_item[it & 1];
         if (tid == 0) s_redo = 0;
-        // ---- cells done one at a time by fast_cell_path: dense strips (noise) and cells larger than 32 px.  Warps 0 and 1
+        // ---- cells done one at a time by fast_cell_path: dense strips (noise) and strips shorter than 7 rows.  Warps 0 and 1
         //      take the even and odd cells, each with its own half of the queue.
         if (cell_path != 0) {
             if (warp < 2) {
-                uint16_t* myq = queue + ((L.strip_ok && ORBX_FS_WARPS > 1) ? warp * (QCAP >> 1) : 0);
+                uint16_t* myq = queue + (ORBX_FS_WARPS > 1 ? warp * (QCAP >> 1) : 0);
                 for (int k = warp; k < ncell; k += (ORBX_FS_WARPS > 1 ? 2 : 1)) {
                     if (!((cell_path >> k) & 0x101u)) continue;
                     const int cj = cj0 + k;
@@ -1110,7 +1107,7 @@ fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __rest
                     fast_cell_path<BW_T>(plan, tbuf + delta + 1, reinterpret_cast<const uint32_t*>(tbuf) + (delta >> 2), (delta & 3) * 8,
                                          BW, ww, wh, sc + k * (wCell + 2) - 3 - 2 * SP, SP, myq, (cell_path >> k) & 1u ? 1 : 0, em,
                                          ci * L.nColsV + cj, cj * wCell, ci * L.hCell, lane,
-                                         (L.strip_ok && ORBX_FS_WARPS > 1) ? (QCAP >> 1) : QCAP, TB - delta - 1);
+                                         ORBX_FS_WARPS > 1 ? (QCAP >> 1) : QCAP, TB - delta - 1);
                 }
             }
             __syncthreads();                                                 // B7: tile buffer b is free
@@ -2911,24 +2908,17 @@ void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nfr
     }
 }
 
+// dynamic shared memory of fast_cells_kernel (fast_strips_kernel's is static)
 size_t fast_smem_bytes(const OrbxPlan& hp) {
-    if (hp.fast_legacy) {
-        const size_t TB = ((size_t)hp.fast_bw * hp.fast_bh + 127) & ~(size_t)127;
-        const size_t SP = (size_t)((hp.max_cell_w + 2 + 3) & ~3);
-        const size_t SB = (SP * hp.fast_bh + 127) & ~(size_t)127;
-        const size_t QB = ((size_t)(hp.max_cell_w - 6) * (hp.max_cell_h - 6) * 2 + 127) & ~(size_t)127;
-        return ((size_t)hp.fast_nb * TB + SB + QB) * hp.fast_warps + 128;
-    }
-    // fast_strips_kernel: two tile buffers + strip score map + kept-corner bitmap + survivor queue per CTA (same carve-up as the kernel)
-    const size_t TB = ((size_t)hp.fast_bw * hp.fast_bh + 127) & ~(size_t)127;
-    const size_t SBYTES = (size_t)hp.fast_sp * (hp.fast_bh - 4);
-    const size_t SB = (SBYTES + 15) & ~(size_t)15;
-    const size_t KB = (((SBYTES + 31) / 32 + 2) * 4 + 15) & ~(size_t)15;
-    return ORBX_FS_NBUF * TB + SB + KB + (size_t)hp.fast_qcap * 2 + 128;
+    const size_t TB = ((size_t)hp.cells_bw * hp.cells_bh + 127) & ~(size_t)127;
+    const size_t SP = (size_t)((hp.max_cell_w + 2 + 3) & ~3);
+    const size_t SB = (SP * hp.cells_bh + 127) & ~(size_t)127;
+    const size_t QB = ((size_t)(hp.max_cell_w - 6) * (hp.max_cell_h - 6) * 2 + 127) & ~(size_t)127;
+    return ((size_t)hp.fast_nb * TB + SB + QB) * hp.fast_warps + 128;
 }
 
 // One {pitch, rows, frames} u8 tensor map per level over the pyramid slabs; box = bw x bh bytes of one frame.
-static int build_tile_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, int bw, int bh, void* out_maps) {
+static int build_tile_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, int bw, int bh, void* out_maps, bool fast_boxes = false) {
     static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -2944,6 +2934,10 @@ static int build_tile_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, i
         const OrbxLevel& L = hp.lv[l];
         cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.rows, (cuuint64_t)max_frames};
         cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)hp.slab_bytes};
+        if (fast_boxes) {              // strips of <= 32-px cells -> fast_strips_kernel's box, everything else -> fast_cells_kernel's
+            bw = L.strip_ok ? hp.fast_bw : hp.cells_bw;
+            bh = L.strip_ok ? hp.fast_bh : hp.cells_bh;
+        }
         cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = encode(&fm->m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_pyr + L.plane_off, dims, strides, box, estr,
@@ -2956,7 +2950,7 @@ static int build_tile_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, i
 
 // box = one strip of FAST cell windows
 int build_fast_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* out_maps) {
-    return build_tile_maps(hp, d_pyr, max_frames, hp.fast_bw, hp.fast_bh, out_maps);
+    return build_tile_maps(hp, d_pyr, max_frames, hp.fast_bw, hp.fast_bh, out_maps, true);
 }
 
 // box = the raw window of one keypoint (describe_kernel)
@@ -2966,57 +2960,66 @@ int build_describe_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void
 
 size_t fast_maps_bytes() { return sizeof(FastMaps); }
 
+// One segment of the strip table (hp.seg_first / hp.seg_count: strips of levels 0-1, strips of levels 2+, big-cell levels
+// 0-1, big-cell levels 2+) for nframes frames: segments 0-1 go to fast_strips_kernel, 2-3 (levels whose cells are larger
+// than 32 x 32, or everything under ORBX_FAST_LEGACY=1) to fast_cells_kernel.  nseg = 2 launches two adjacent segments
+// as one.  Each segment has its own work counter (work_counters[seg]).
 cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, const OrbxTap* taps, int frame0, int nframes,
-                        int l0, int l1, int num_sms, uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counter,
+                        int seg, int nseg, int num_sms, uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counters,
                         int* status, int* retry_counts, cudaStream_t st) {
-    const size_t smem = fast_smem_bytes(hp);
-    typedef void (*cells_fn)(const FastMaps, const OrbxPlan*, int, int, int, int, uint32_t*, uint2*, int*, int*, int*, int*);
-    typedef void (*strips_fn)(const FastMaps, const OrbxPlan*, const uint32_t*, int, int, int, int, uint32_t*, uint2*, int*, int*, int*, int*);
-    static const strips_fn strips_all[3] = {fast_strips_kernel<96>, fast_strips_kernel<128>, fast_strips_kernel<160>};
-    static const cells_fn cells_all[4] = {fast_cells_kernel<64>, fast_cells_kernel<96>, fast_cells_kernel<128>, fast_cells_kernel<0>};
+    typedef void (*fast_fn)(const FastMaps, const OrbxPlan*, const uint32_t*, int, int, int, int, uint32_t*, uint2*, int*, int*, int*, int*);
+    static const fast_fn all[7] = {fast_strips_kernel<96>, fast_strips_kernel<128>, fast_strips_kernel<160>,
+                                   fast_cells_kernel<64>,  fast_cells_kernel<96>,   fast_cells_kernel<128>, fast_cells_kernel<0>};
+    const int first = hp.seg_first[seg];
+    int nstrips = 0;
+    for (int i = 0; i < nseg; ++i) nstrips += hp.seg_count[seg + i];
+    if (nstrips == 0) return cudaSuccess;
+    const bool strips = seg < 2;
     int which;
-    if (!hp.fast_legacy) {
+    if (strips) {
         which = hp.fast_bw == 96 ? 0 : hp.fast_bw == 128 ? 1 : hp.fast_bw == 160 ? 2 : -1;
         if (which < 0) return cudaErrorInvalidValue;
     } else {
-        which = hp.fast_bw == 64 ? 3 : hp.fast_bw == 96 ? 4 : hp.fast_bw == 128 ? 5 : 6;
+        which = hp.cells_bw == 64 ? 3 : hp.cells_bw == 96 ? 4 : hp.cells_bw == 128 ? 5 : 6;
     }
-    const void* fn = which < 3 ? (const void*)strips_all[which] : (const void*)cells_all[which - 3];
+    const fast_fn fn = all[which];
+    const size_t smem = strips ? 0 : fast_smem_bytes(hp);
+    const int W = strips ? ORBX_FS_WARPS : hp.fast_warps;
     // per device and kernel: the dynamic shared-memory limit that was configured and the resident CTAs per SM it gives
     static size_t configured[64][7] = {};
     static int per_sm_cache[64][7] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    std::lock_guard<std::mutex> config_lock(g_config_mutex);
-    const int W = hp.fast_warps;
-    if (smem != configured[dev][which]) {
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured[dev][which] = smem;
-        int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, W * 32, smem);
-        per_sm_cache[dev][which] = per_sm < 1 ? 1 : per_sm;
+    int per_sm_eff;
+    {
+        std::lock_guard<std::mutex> config_lock(g_config_mutex);
+        if (smem + 1 != configured[dev][which]) {
+            if (smem) {
+                cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+            }
+            configured[dev][which] = smem + 1;
+            int per_sm = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, W * 32, smem);
+            per_sm_cache[dev][which] = per_sm < 1 ? 1 : per_sm;
+        }
+        per_sm_eff = per_sm_cache[dev][which];
     }
-    const int strips = (l1 < hp.nlevels ? hp.lv[l1].strip_base : hp.strips_per_frame) - hp.lv[l0].strip_base;
-    const long long total = (long long)nframes * strips;
-    long long blocks = hp.fast_legacy ? (total + W - 1) / W : total;          // legacy: a warp per strip; product: a CTA per strip
+    const long long total = (long long)nframes * nstrips;
+    long long blocks = strips ? total : (total + W - 1) / W;                  // a CTA per strip / a warp per strip
     // ORBX_FAST_CTAS_PER_SM (tuning): fewer resident FAST CTAs leave registers / shared memory for the kernels of the
     // other half-batch's stream to co-run
     static const int env_cap = getenv("ORBX_FAST_CTAS_PER_SM") ? atoi(getenv("ORBX_FAST_CTAS_PER_SM")) : 0;
-    int per_sm_eff = per_sm_cache[dev][which];
     if (env_cap > 0 && env_cap < per_sm_eff) per_sm_eff = env_cap;
     const long long cap = (long long)num_sms * per_sm_eff;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     FastMaps fm;
     memcpy(&fm, maps, sizeof fm);
-    if (which < 3)
-        return launch_k(strips_all[which], dim3((unsigned)blocks), dim3(W * 32), smem, st, fm, d_plan,
-                        reinterpret_cast<const uint32_t*>(taps + hp.strip_tab_off), frame0, nframes, l0, l1, cand, cell_rec,
-                        level_counts, work_counter, status, retry_counts);
-    return launch_k(cells_all[which - 3], dim3((unsigned)blocks), dim3(W * 32), smem, st, fm, d_plan, frame0, nframes, l0, l1, cand,
-                    cell_rec, level_counts, work_counter, status, retry_counts);
+    return launch_k(fn, dim3((unsigned)blocks), dim3(W * 32), smem, st, fm, d_plan,
+                    reinterpret_cast<const uint32_t*>(taps + hp.strip_tab_off), frame0, nframes, first, nstrips, cand, cell_rec,
+                    level_counts, work_counters + seg, status, retry_counts);
 }
 
 size_t octree_smem_bytes(const OrbxPlan& hp) {

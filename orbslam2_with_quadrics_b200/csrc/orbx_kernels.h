@@ -16,6 +16,8 @@
 #ifndef ORBX_FS_NBUF
 #define ORBX_FS_NBUF 1           // tile buffers per CTA.  2 hides the TMA latency but costs resident CTAs: 0.991 vs 0.891 ms
 #endif
+#define ORBX_FS_BH 38            // tile rows of a strip: cells of <= 32 scoring rows + the 6-px frame
+#define ORBX_FS_QCAP 2048        // survivor queue entries of a strip (its halves serve the per-cell path: 32 x 32 pixels each)
 #define ORBX_OT_THREADS 1024
 #define ORBX_OT_KEYCAP 8192     // candidates of one level kept in shared memory by the octree kernel (6 bytes each)
 
@@ -34,7 +36,7 @@ size_t fast_smem_bytes(const OrbxPlan& hp);
 int build_fast_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* out_maps);
 size_t fast_maps_bytes();
 cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, const OrbxTap* taps, int frame0, int nframes,
-                        int l0, int l1, int num_sms, uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counter,
+                        int seg, int nseg, int num_sms, uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counters,
                         int* status, int* retry_counts, cudaStream_t st);
 size_t octree_smem_bytes(const OrbxPlan& hp);
 cudaError_t launch_octree(const OrbxPlan* d_plan, const OrbxPlan& hp, int nframes, const uint32_t* cand,

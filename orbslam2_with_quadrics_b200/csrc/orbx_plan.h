@@ -26,7 +26,7 @@ struct OrbxLevel {
     int nColsV, nRowsV;       // cells that survive the skip rules (:794, :803)
     int wCell, hCell;
     int cell_base;            // first cell of this level inside a frame (cell_rec index)
-    int strip_base, strips_x; // FAST work items: strips of strip_nc cells; first item of the level, items per cell row
+    int strips_x;             // FAST work items: strips of strip_nc cells per cell row
     int strip_nc;             // cells per strip of this level (a strip's scoring pixels fit 32 tile words)
     int strip_ok;             // 1: fast_strips_kernel's dense strip path applies (cells <= 32 x 32), 0: cell by cell
     int wcell_recip;          // 65536 / wCell + 1: (n * wcell_recip) >> 16 == n / wCell for n < 256
@@ -55,12 +55,13 @@ struct OrbxPlan {
     int blur_tiles_per_frame;
     int node_cap;             // octree node capacity (max over levels)
     int max_cell_w, max_cell_h;   // largest FAST window (incl. the 6-px overlap)
-    int fast_bw, fast_bh;         // TMA box of a FAST tile (bw multiple of 16)
+    int fast_bw, fast_bh;         // TMA box of a fast_strips_kernel tile (bw: 96 / 128 / 160, bh = ORBX_FS_BH)
+    int cells_bw, cells_bh;       // TMA box of a fast_cells_kernel tile (levels with cells > 32 x 32, ORBX_FAST_LEGACY=1)
     int fast_nc, fast_nb, fast_warps;   // max cells per tile, tile buffers per warp (legacy kernel: 1 or 2), warps per CTA
     int fast_legacy;              // 1: fast_cells_kernel (ORBX_FAST_LEGACY=1, A/B measurements)
-    int fast_sp, fast_qcap;       // fast_strips_kernel: score-map pitch, survivor queue entries per warp
     int strips_per_frame;
     int strip_tab_off;            // strip table (level | cell row << 4 | first cell << 16 per strip of a frame) inside the tap tables, OrbxTap units
+    int seg_first[4], seg_count[4];   // table segments: strips of levels 0-1, strips of levels 2+, big-cell levels 0-1, big-cell levels 2+
     int ini_th, min_th;
     long long slab_bytes;     // one frame's pyramid slab
     float atan_p1, atan_p3, atan_p5, atan_p7;   // cv::fastAtan2 coefficients (float products)
