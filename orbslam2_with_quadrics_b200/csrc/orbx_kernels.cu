@@ -1096,9 +1096,12 @@ fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __rest
         // ---- cells done one at a time by fast_cell_path: dense strips (noise) and strips shorter than 7 rows.  Warps 0 and 1
         //      take the even and odd cells, each with its own half of the queue.
         if (cell_path != 0) {
-            if (warp < 2) {
-                uint16_t* myq = queue + (ORBX_FS_WARPS > 1 ? warp * (QCAP >> 1) : 0);
-                for (int k = warp; k < ncell; k += (ORBX_FS_WARPS > 1 ? 2 : 1)) {
+            // (QCAP >= 2048: warps 0 and 1 take the even and odd cells, each with its own half of the queue; smaller queues:
+            // warp 0 takes them all)
+            constexpr int CPW = (ORBX_FS_WARPS > 1 && QCAP >= 2048) ? 2 : 1;
+            if (warp < CPW) {
+                uint16_t* myq = queue + warp * (QCAP / CPW);
+                for (int k = warp; k < ncell; k += CPW) {
                     if (!((cell_path >> k) & 0x101u)) continue;
                     const int cj = cj0 + k;
                     const int iniX = ORBX_BOX + cj * wCell;
@@ -1107,7 +1110,7 @@ fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __rest
                     fast_cell_path<BW_T>(plan, tbuf + delta + 1, reinterpret_cast<const uint32_t*>(tbuf) + (delta >> 2), (delta & 3) * 8,
                                          BW, ww, wh, sc + k * (wCell + 2) - 3 - 2 * SP, SP, myq, (cell_path >> k) & 1u ? 1 : 0, em,
                                          ci * L.nColsV + cj, cj * wCell, ci * L.hCell, lane,
-                                         ORBX_FS_WARPS > 1 ? (QCAP >> 1) : QCAP, TB - delta - 1);
+                                         QCAP / CPW, TB - delta - 1);
                 }
             }
             __syncthreads();                                                 // B7: tile buffer b is free

@@ -17,7 +17,9 @@
 #define ORBX_FS_NBUF 1           // tile buffers per CTA.  2 hides the TMA latency but costs resident CTAs: 0.991 vs 0.891 ms
 #endif
 #define ORBX_FS_BH 38            // tile rows of a strip: cells of <= 32 scoring rows + the 6-px frame
-#define ORBX_FS_QCAP 2048        // survivor queue entries of a strip (its halves serve the per-cell path: 32 x 32 pixels each)
+#ifndef ORBX_FS_QCAP
+#define ORBX_FS_QCAP 2048        // survivor queue entries of a strip (>= 1024: the per-cell path needs 32 x 32; from 2048 on two warps share it)
+#endif
 #define ORBX_OT_THREADS 1024
 #define ORBX_OT_KEYCAP 8192     // candidates of one level kept in shared memory by the octree kernel (6 bytes each)
 
