@@ -97,16 +97,14 @@ __device__ __forceinline__ const uint8_t* level_px(const uint8_t* slab, const Or
 // row.  H[sy][dx] >> 4 is cached for the two most recent source rows, so going down one output
 // row costs ~1.2 row passes; the column pass is two IMAD.HI per pixel.
 // =====================================================================================
-__global__ void __launch_bounds__(256) pyr_level0_kernel(const OrbxPlan* __restrict__ plan,
-                                                         const uint8_t* __restrict__ imgs, size_t img_pitch,
-                                                         size_t img_frame_stride, int aligned16,
-                                                         uint8_t* __restrict__ pyr) {
-    ORBX_PDL_WAIT();
+// One work item = 32 x 8 threads' worth of level 0 (32 lanes x 16 bytes wide, 8 plane rows); (tx, ty) = the thread's place in it.
+__device__ __forceinline__ void pyr_level0_item(const OrbxPlan* __restrict__ plan, const uint8_t* __restrict__ imgs, size_t img_pitch,
+                                                size_t img_frame_stride, int aligned16, uint8_t* pyr, int bx, int by, int frame,
+                                                int tx, int ty) {
     const OrbxLevel& L = plan->lv[0];
     const int w = L.w, h = L.h;
-    const int frame = blockIdx.z;
-    const int c = (blockIdx.x * 32 + threadIdx.x) * 16;            // plane column, multiple of 16 (XO is too)
-    const int row = blockIdx.y * 8 + threadIdx.y;                  // plane row
+    const int c = (bx * 32 + tx) * 16;                             // plane column, multiple of 16 (XO is too)
+    const int row = by * 8 + ty;                                   // plane row
     if (row >= L.rows || c >= ORBX_XO + w + ORBX_EDGE) return;
     const int dy = reflect_clamp(row - ORBX_EDGE, h);
     const uint8_t* src = imgs + (size_t)frame * img_frame_stride + (size_t)dy * img_pitch;
@@ -130,6 +128,14 @@ __global__ void __launch_bounds__(256) pyr_level0_kernel(const OrbxPlan* __restr
         out = make_uint4(o[0], o[1], o[2], o[3]);
     }
     *reinterpret_cast<uint4*>(pyr + (size_t)frame * plan->slab_bytes + L.plane_off + (size_t)row * L.pitch + c) = out;
+}
+
+__global__ void __launch_bounds__(256) pyr_level0_kernel(const OrbxPlan* __restrict__ plan,
+                                                         const uint8_t* __restrict__ imgs, size_t img_pitch,
+                                                         size_t img_frame_stride, int aligned16,
+                                                         uint8_t* __restrict__ pyr) {
+    ORBX_PDL_WAIT();
+    pyr_level0_item(plan, imgs, img_pitch, img_frame_stride, aligned16, pyr, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, threadIdx.y);
 }
 
 // =====================================================================================
@@ -173,18 +179,17 @@ __global__ void __launch_bounds__(256) cvt_gray_kernel(const uint8_t* __restrict
     }
 }
 
+#ifndef PYR_RY
 #define PYR_RY 16
+#endif
 template <bool WIDE>
-__global__ void __launch_bounds__(128) pyr_resize_kernel(const OrbxPlan* __restrict__ plan, int l, int RY,
-                                                         uint8_t* __restrict__ pyr,
-                                                         const OrbxTap* __restrict__ taps) {
-    ORBX_PDL_WAIT();
+__device__ __forceinline__ void pyr_resize_item(const OrbxPlan* __restrict__ plan, int l, int RY, uint8_t* pyr,
+                                                const OrbxTap* __restrict__ taps, int bx, int by, int frame, int tid) {
     const OrbxLevel& L = plan->lv[l];
     const OrbxLevel& S = plan->lv[l - 1];
     const int w = L.w, h = L.h;
-    const int frame = blockIdx.z;
-    const int c = 12 + (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;             // plane column, multiple of 4
-    const int row0 = (blockIdx.y * 4 + (threadIdx.x >> 5)) * RY;              // first plane row of this warp
+    const int c = 12 + (bx * 32 + (tid & 31)) * 4;                             // plane column, multiple of 4
+    const int row0 = (by * 4 + (tid >> 5)) * RY;                              // first plane row of this warp
     if (row0 >= L.rows || c >= ORBX_XO + w + ORBX_EDGE) return;
     uint8_t* slab = pyr + (size_t)frame * plan->slab_bytes;
     // ---- column taps of the 4 pixels
@@ -286,6 +291,13 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const OrbxPlan* __restr
     }
 }
 
+template <bool WIDE>
+__global__ void __launch_bounds__(128) pyr_resize_kernel(const OrbxPlan* __restrict__ plan, int l, int RY, uint8_t* pyr,
+                                                         const OrbxTap* __restrict__ taps) {
+    ORBX_PDL_WAIT();
+    pyr_resize_item<WIDE>(plan, l, RY, pyr, taps, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+}
+
 // pyr_resize8_kernel: the same arithmetic with 8 adjacent plane columns per lane (one 64-bit store per row) and every
 // column decision moved into a host-built OrbxCol8 record.  A half (4 pixels) reads 3 aligned source words; one funnel
 // shift pair leaves the 8 bytes from the half's smallest tap offset on in (U, V), a pixel PAIR's two source byte
@@ -297,15 +309,23 @@ struct Row6 { uint32_t a0, a1, a2, b0, b1, b2; };
 #ifndef ORBX_R8_MINB
 #define ORBX_R8_MINB 1
 #endif
-__global__ void __launch_bounds__(128, ORBX_R8_MINB) pyr_resize8_kernel(const OrbxPlan* __restrict__ plan, int l, int RY,
-                                                          uint8_t* __restrict__ pyr, const OrbxTap* __restrict__ taps) {
-    ORBX_PDL_WAIT();
+// Cache-line prefetch of the source rows ORBX_R8_PF rows beyond the register prefetch (costs one instruction and no
+// register per output row).  Measured at 64 x 1080p, pyramid ms per step: off 0.425, 2 rows 0.388, 3 rows 0.393, 4 rows
+// 0.394, 6 rows 0.400; into L1 or only into L2 makes no difference (0.3925 / 0.3928 at 3 rows).
+#ifndef ORBX_R8_PF
+#define ORBX_R8_PF 2
+#endif
+#ifndef ORBX_R8_PF_L1
+#define ORBX_R8_PF_L1 1         // 1: prefetch.global.L1, 0: prefetch.global.L2
+#endif
+__device__ __forceinline__ void pyr_resize8_item(const OrbxPlan* __restrict__ plan, int l, int RY, uint8_t* pyr,
+                                                 const OrbxTap* __restrict__ taps, int bx, int by, int frame, int tid) {
     const OrbxLevel& L = plan->lv[l];
     const OrbxLevel& S = plan->lv[l - 1];
-    const int g = blockIdx.x * 32 + (threadIdx.x & 31);                        // group of 8 plane columns from column 8 on
-    const int row0 = (blockIdx.y * 4 + (threadIdx.x >> 5)) * RY;              // first plane row of this warp
+    const int g = bx * 32 + (tid & 31);                                        // group of 8 plane columns from column 8 on
+    const int row0 = (by * 4 + (tid >> 5)) * RY;                              // first plane row of this warp
     if (row0 >= L.rows || g >= L.ngroups8) return;
-    uint8_t* slab = pyr + (size_t)blockIdx.z * plan->slab_bytes;
+    uint8_t* slab = pyr + (size_t)frame * plan->slab_bytes;
     const uint4* cgp = reinterpret_cast<const uint4*>(taps + L.col8_off) + 4 * g;
     const uint4 c0 = __ldg(cgp), c1 = __ldg(cgp + 1), c2 = __ldg(cgp + 2), c3 = __ldg(cgp + 3);
     const uint8_t* sbase = slab + S.plane_off + (size_t)ORBX_EDGE * S.pitch + ORBX_XO;     // source pixel (0, 0)
@@ -350,6 +370,16 @@ __global__ void __launch_bounds__(128, ORBX_R8_MINB) pyr_resize8_kernel(const Or
         const uint2 tyn = __ldg(yt + min(i + 1, nrow - 1));
         const int pren_id = min((int)tyn.x + 1, hs1);
         const Row6 pren = load_row(pren_id);
+#if ORBX_R8_PF > 0
+        {   // the source rows ORBX_R8_PF output rows further down: a cache-line prefetch costs no register
+            const unsigned o = (unsigned)(min(pren_id + ORBX_R8_PF, hs1) * spitch);
+#if ORBX_R8_PF_L1
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(plo + o));
+#else
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(plo + o));
+#endif
+        }
+#endif
         const int r0 = (int)ty.x, r1 = min(r0 + 1, hs1);
         uint32_t b0, b1;                                                      // row weights of H0, H1, << 16
         if (r0 == id1) {                                                      // the usual step: last row's lower row is the upper one
@@ -378,6 +408,12 @@ __global__ void __launch_bounds__(128, ORBX_R8_MINB) pyr_resize8_kernel(const Or
         pre = pren;
         pre_id = pren_id;
     }
+}
+
+__global__ void __launch_bounds__(128, ORBX_R8_MINB) pyr_resize8_kernel(const OrbxPlan* __restrict__ plan, int l, int RY, uint8_t* pyr,
+                                                                        const OrbxTap* __restrict__ taps) {
+    ORBX_PDL_WAIT();
+    pyr_resize8_item(plan, l, RY, pyr, taps, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
 }
 
 // =====================================================================================
@@ -2886,28 +2922,46 @@ static bool force_resize4() {          // ORBX_RESIZE4=1: A/B switch back to the
 
 void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nframes, int num_sms, const uint8_t* imgs,
                       size_t img_pitch, size_t img_frame_stride, uint8_t* pyr, const OrbxTap* taps,
-                      cudaStream_t st) {
+                      cudaStream_t st);
+
+// Block geometry of one pyramid level, shared by the per-level launches and the chained kernel.
+struct PyrGeom { int gx, gy, ry, kind; };
+static PyrGeom pyr_geometry(const OrbxPlan& hp, int l, int nframes, int num_sms) {
     const OrbxLevel& L = hp.lv[l];
-    const int cols4 = (ORBX_XO + L.w + ORBX_EDGE - 12 + 3) / 4;
+    PyrGeom g;
     if (l == 0) {
-        const int aligned16 = ((reinterpret_cast<uintptr_t>(imgs) | img_pitch | img_frame_stride) & 15) == 0;
         const int cols16 = (ORBX_XO + L.w + ORBX_EDGE + 15) / 16;          // 16-byte chunks from plane column 0
-        dim3 block(32, 8), grid((cols16 + 31) / 32, (L.rows + 7) / 8, nframes);
-        launch_k(pyr_level0_kernel, grid, block, 0, st, d_plan, imgs, img_pitch, img_frame_stride, aligned16, pyr);
+        g.gx = (cols16 + 31) / 32; g.gy = (L.rows + 7) / 8; g.ry = 0; g.kind = 0;
     } else if (L.resize8_ok && !force_resize4()) {
-        const int gx = (L.ngroups8 + 31) / 32;
+        g.gx = (L.ngroups8 + 31) / 32;
         static const int min_ry = getenv("ORBX_PYR_MINRY") ? atoi(getenv("ORBX_PYR_MINRY")) : 2;      // 2: single 640x480 frame 50 -> 38 us
         int RY = PYR_RY;
-        while (RY > min_ry && (long long)gx * ((L.rows + RY - 1) / RY) * nframes < (long long)num_sms * 32) RY >>= 1;
-        dim3 grid(gx, (L.rows + 4 * RY - 1) / (4 * RY), nframes);
-        launch_k(pyr_resize8_kernel, grid, dim3(128), 0, st, d_plan, l, RY, pyr, taps);
+        while (RY > min_ry && (long long)g.gx * ((L.rows + RY - 1) / RY) * nframes < (long long)num_sms * 32) RY >>= 1;
+        g.ry = RY; g.gy = (L.rows + 4 * RY - 1) / (4 * RY); g.kind = 1;
     } else {
         // rows per warp: long strips reuse row passes (1 + 1/RY... per row) but small levels need warps
+        const int cols4 = (ORBX_XO + L.w + ORBX_EDGE - 12 + 3) / 4;
+        g.gx = (cols4 + 31) / 32;
         int RY = PYR_RY;
-        while (RY > 4 && (long long)((cols4 + 31) / 32) * ((L.rows + RY - 1) / RY) * nframes < (long long)num_sms * 32) RY >>= 1;
-        dim3 grid((cols4 + 31) / 32, (L.rows + 4 * RY - 1) / (4 * RY), nframes);
-        if (L.resize_wide) launch_k(pyr_resize_kernel<true>, grid, dim3(128), 0, st, d_plan, l, RY, pyr, taps);
-        else launch_k(pyr_resize_kernel<false>, grid, dim3(128), 0, st, d_plan, l, RY, pyr, taps);
+        while (RY > 4 && (long long)g.gx * ((L.rows + RY - 1) / RY) * nframes < (long long)num_sms * 32) RY >>= 1;
+        g.ry = RY; g.gy = (L.rows + 4 * RY - 1) / (4 * RY); g.kind = L.resize_wide ? 3 : 2;
+    }
+    return g;
+}
+
+void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nframes, int num_sms, const uint8_t* imgs,
+                      size_t img_pitch, size_t img_frame_stride, uint8_t* pyr, const OrbxTap* taps,
+                      cudaStream_t st) {
+    const PyrGeom g = pyr_geometry(hp, l, nframes, num_sms);
+    if (g.kind == 0) {
+        const int aligned16 = ((reinterpret_cast<uintptr_t>(imgs) | img_pitch | img_frame_stride) & 15) == 0;
+        launch_k(pyr_level0_kernel, dim3(g.gx, g.gy, nframes), dim3(32, 8), 0, st, d_plan, imgs, img_pitch, img_frame_stride, aligned16, pyr);
+    } else if (g.kind == 1) {
+        launch_k(pyr_resize8_kernel, dim3(g.gx, g.gy, nframes), dim3(128), 0, st, d_plan, l, g.ry, pyr, taps);
+    } else if (g.kind == 3) {
+        launch_k(pyr_resize_kernel<true>, dim3(g.gx, g.gy, nframes), dim3(128), 0, st, d_plan, l, g.ry, pyr, taps);
+    } else {
+        launch_k(pyr_resize_kernel<false>, dim3(g.gx, g.gy, nframes), dim3(128), 0, st, d_plan, l, g.ry, pyr, taps);
     }
 }
 
