@@ -362,7 +362,8 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
     for (int l = 0; l < n; ++l) {
         OrbxLevel& L = P->lv[l];
         L.wcell_recip = 65536 / L.wCell + 1;
-        L.strip_ok = !P->fast_legacy && L.wCell <= 32 && L.hCell <= 32;
+        L.strip_ok = !P->fast_legacy && L.wCell <= 32 && L.hCell <= 40;
+        L.strip_tall = L.strip_ok && L.hCell > 32;
         L.strip_nc = L.strip_ok ? std::max(1, std::min(P->fast_nc, 125 / L.wCell))
                                 : (P->fast_legacy ? P->fast_nc : (h->cfg.max_batch <= 2 ? 1 : 2));
         L.strips_x = (L.nColsV + L.strip_nc - 1) / L.strip_nc;
@@ -377,10 +378,11 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
     {   // strip table of a frame, stored behind the resize tap tables (8-byte units), in four segments so that a launch
         // covers a contiguous range: (strip levels | big-cell levels) x (levels 0-1, whose FAST starts early | levels 2+)
         std::vector<uint32_t> tab;
-        for (int seg = 0; seg < 4; ++seg) {
+        for (int seg = 0; seg < 6; ++seg) {
             P->seg_first[seg] = (int)tab.size();
             for (int l = 0; l < n; ++l) {
-                if ((P->lv[l].strip_ok != 0) != (seg < 2) || (l < 2) != ((seg & 1) == 0)) continue;
+                const int kind = !P->lv[l].strip_ok ? 1 : (P->lv[l].strip_tall ? 2 : 0);     // segment pair of the level
+                if (kind != seg / 2 || (l < 2) != ((seg & 1) == 0)) continue;
                 for (int i = 0; i < P->lv[l].nRowsV; ++i)
                     for (int j = 0; j < P->lv[l].strips_x; ++j)
                         tab.push_back((uint32_t)l | ((uint32_t)i << 4) | ((uint32_t)(j * P->lv[l].strip_nc) << 16));
@@ -388,10 +390,40 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
             P->seg_count[seg] = (int)tab.size() - P->seg_first[seg];
         }
         P->strips_per_frame = (int)tab.size();
+        // fast_strips_kernel's records, one per table entry
+        std::vector<OrbxStripRec> recs(tab.size());
+        for (size_t s = 0; s < tab.size(); ++s) {
+            const int l = (int)(tab[s] & 15u), ci = (int)((tab[s] >> 4) & 0xfffu), cj0 = (int)(tab[s] >> 16);
+            const OrbxLevel& L = P->lv[l];
+            OrbxStripRec& r = recs[s];
+            memset(&r, 0, sizeof r);
+            if (!L.strip_ok) continue;
+            const int x0 = ORBX_XO + ORBX_BOX + cj0 * L.wCell - 1;               // plane column of (strip window x0 - 1)
+            const int delta0 = x0 & 15;
+            const int iniY = ORBX_BOX + ci * L.hCell, iniX0 = ORBX_BOX + cj0 * L.wCell;
+            const int wh = std::min(iniY + L.hCell + 6, L.maxBY) - iniY;
+            const int ncell = std::min(L.strip_nc, L.nColsV - cj0);
+            const int sw = std::min(iniX0 + ncell * L.wCell + 6, L.maxBX) - iniX0;
+            const int hr = (wh >= 7 && sw >= 7) ? wh - 6 : 0;
+            const int lo = delta0 + 4, hi = std::max(lo, delta0 + sw - 2);
+            if (hr > (L.strip_tall ? 40 : 32) || ncell < 1 || ncell > 4 || hi > 160 - 4 || L.wcell_recip > 0xffff) return ORBX_ERR_BAD_GEOMETRY;
+            r.tile_xy = (uint32_t)(x0 & ~15) | ((uint32_t)(ORBX_EDGE + iniY) << 16);
+            r.shape = (uint32_t)l | ((uint32_t)ncell << 4) | ((uint32_t)hr << 8) | ((uint32_t)delta0 << 16) | ((uint32_t)(lo >> 2) << 24);
+            r.cols = (uint32_t)lo | ((uint32_t)hi << 16);
+            r.cellw = (uint32_t)L.wCell | ((uint32_t)L.wcell_recip << 16);
+            r.cell0 = (uint32_t)(L.cell_base + ci * L.nColsV + cj0);
+            r.origin = (uint32_t)(cj0 * L.wCell + 3) | ((uint32_t)(ci * L.hCell + 3) << 16);
+            r.window = (uint32_t)sw | ((uint32_t)wh << 16);
+        }
         if (tab.size() & 1) tab.push_back(0);
         P->strip_tab_off = (int)taps->size();
         const OrbxTap* raw = reinterpret_cast<const OrbxTap*>(tab.data());
         taps->insert(taps->end(), raw, raw + tab.size() / 2);
+        if (taps->size() & 1) taps->push_back(OrbxTap());                        // records are read as 16-byte vectors
+        P->strip_rec_off = (int)taps->size();
+        static_assert(sizeof(OrbxStripRec) == 4 * sizeof(OrbxTap), "record = 4 tap units");
+        const OrbxTap* rraw = reinterpret_cast<const OrbxTap*>(recs.data());
+        taps->insert(taps->end(), rraw, rraw + recs.size() * 4);
     }
     P->fast_bw = bw <= 96 ? 96 : bw <= 128 ? 128 : 160;                           // fast_strips_kernel instantiations
     P->fast_bh = ORBX_FS_BH;
@@ -553,7 +585,7 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
         if (ls && l == ls - 1) {
             CK(h, cudaEventRecord(h->ev_low[si], st));
             CK(h, cudaStreamWaitEvent(ax, h->ev_low[si], 0));
-            for (int seg = 0; seg < 4; seg += 2)                         // levels 0-1: strips, then big cells (if any)
+            for (int seg = 0; seg < 6; seg += 2)                         // levels 0-1: strips, then big cells and tall cells (if any)
                 CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), h->d_taps, f0, n, seg, 1, h->num_sms, cand, cell_rec,
                                         level_counts, wc, status, retry_counts, ax));
             CK(h, cudaEventRecord(h->ev_fast_low[si], ax));
@@ -561,24 +593,27 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
     }
     if (ev) CK(h, cudaEventRecord(ev[ST_FAST], st));
     if (ls) {
-        // the (tiny) levels whose cells are too large for fast_strips_kernel run beside it on the side stream
-        if (P.seg_count[3] > 0) {
+        // the (small) levels with tall cells, or cells too large for fast_strips_kernel, run beside it on the side stream
+        // (a single frame's critical path is one strip per CTA either way: 17 us each, measured)
+        if (P.seg_count[3] + P.seg_count[5] > 0) {
             CK(h, cudaEventRecord(h->ev_low[si], st));
             CK(h, cudaStreamWaitEvent(ax, h->ev_low[si], 0));
-            CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), h->d_taps, f0, n, 3, 1, h->num_sms, cand, cell_rec,
-                                    level_counts, wc, status, retry_counts, ax));
+            for (int seg = 5; seg >= 3; seg -= 2)
+                CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), h->d_taps, f0, n, seg, 1, h->num_sms, cand, cell_rec,
+                                        level_counts, wc, status, retry_counts, ax));
             CK(h, cudaEventRecord(h->ev_fast_low[si], ax));
         }
         CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), h->d_taps, f0, n, 1, 1, h->num_sms, cand, cell_rec, level_counts,
                                 wc, status, retry_counts, st));
         CK(h, cudaStreamWaitEvent(st, h->ev_fast_low[si], 0));           // the quadtree needs every level's candidates
     } else {
-        for (int seg = 0; seg < 4; seg += 2)                             // all strip levels, then all big-cell levels
+        for (int seg = 0; seg < 6; seg += 2)                             // all strip levels, all big-cell levels, all tall-cell levels
             CK(h, orbx::launch_fast(h->d_plan, P, h->fast_maps.data(), h->d_taps, f0, n, seg, 2, h->num_sms, cand, cell_rec,
                                     level_counts, wc, status, retry_counts, st));
     }
-    const int fast_launches = ls ? (P.seg_count[0] > 0) + (P.seg_count[1] > 0) + (P.seg_count[2] > 0) + (P.seg_count[3] > 0)
-                                 : (P.seg_count[0] + P.seg_count[1] > 0) + (P.seg_count[2] + P.seg_count[3] > 0);
+    int fast_launches = 0;
+    for (int seg = 0; seg < 6; seg += 2)
+        fast_launches += ls ? (P.seg_count[seg] > 0) + (P.seg_count[seg + 1] > 0) : (P.seg_count[seg] + P.seg_count[seg + 1] > 0);
     if (ev) CK(h, cudaEventRecord(ev[ST_OCTREE], st));
     CK(h, orbx::launch_octree(h->d_plan, P, n, cand, cell_rec, cand_sorted, key_node, sorted_counts, kept, kept_counts,
                               status, st));

@@ -507,7 +507,16 @@ __device__ __forceinline__ uint32_t max3_s16x2(uint32_t a, uint32_t b, uint32_t 
 #endif
 }
 
-// exact FAST score of the pixel at tile byte p (pitch BW): A - 1 if A > t else 0
+// exact FAST score of the pixel at tile byte p (pitch BW): A - 1 if A > t else 0, with
+//   A = max over the 16 arcs of 9 contiguous ring pixels of max(min(ring) - centre, centre - max(ring))
+// (cv::FAST's cornerScore<16>: the largest threshold for which the pixel is still a corner, + 1).
+// ORBX_SCORE_NET 1 (product): Z[k] = (ring k, 255 - ring k) as s16x2, so ONE min network yields both polarities --
+// low half: min over the arc, high half: 255 - max over the arc.  16 + 16 three-input minima (arcs of 3, then of 9) and
+// 8 three-input maxima: 40 VIMNMX3 per pixel.  ORBX_SCORE_NET 0 (round 1, kept for A/B): Z[k] = (ring k, ring k + 8),
+// a min network and a max network over 8 arcs each (26 + 26 three-input equivalents).
+#ifndef ORBX_SCORE_NET
+#define ORBX_SCORE_NET 1
+#endif
 __device__ __forceinline__ int fast_score_packed(const uint8_t* __restrict__ p, int BW, int t) {
     const int v = p[0];
     uint32_t q[16];
@@ -515,6 +524,27 @@ __device__ __forceinline__ int fast_score_packed(const uint8_t* __restrict__ p, 
     q[4] = p[3];             q[5] = p[-BW + 3];       q[6] = p[-2 * BW + 2];   q[7] = p[-3 * BW + 1];
     q[8] = p[-3 * BW];       q[9] = p[-3 * BW - 1];   q[10] = p[-2 * BW - 2];  q[11] = p[-BW - 3];
     q[12] = p[-3];           q[13] = p[BW - 3];       q[14] = p[2 * BW - 2];   q[15] = p[3 * BW - 1];
+#if ORBX_SCORE_NET == 1
+    uint32_t Z[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) Z[k] = q[k] * 0xFFFF0001u + 0x00FF0000u;      // q | (255 - q) << 16, one IMAD
+    uint32_t n3[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) n3[k] = min3_s16x2(Z[k], Z[(k + 1) & 15], Z[(k + 2) & 15]);
+    uint32_t n9[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) n9[k] = min3_s16x2(n3[k], n3[(k + 3) & 15], n3[(k + 6) & 15]);   // arc k .. k + 8
+    uint32_t m0 = max3_s16x2(n9[0], n9[1], n9[2]), m1 = max3_s16x2(n9[3], n9[4], n9[5]);
+    uint32_t m2 = max3_s16x2(n9[6], n9[7], n9[8]), m3 = max3_s16x2(n9[9], n9[10], n9[11]);
+    uint32_t m4 = max3_s16x2(n9[12], n9[13], n9[14]);
+    m0 = max3_s16x2(m0, m1, m2);
+    m3 = max3_s16x2(m3, m4, n9[15]);
+    const uint32_t M = __vmaxs2(m0, m3);
+    const int Ab = (int)(M & 0xffffu) - v;                               // brighter arc: min(ring) - centre
+    const int Ad = v + (int)(M >> 16) - 255;                             // darker arc: centre - max(ring)
+    const int A = max(Ab, Ad);
+    return A > t ? A - 1 : 0;
+#else
     // Z[k] = (ring k, ring k + 8) as s16x2; Z[k + 8] = halves swapped.  min / max commute with subtracting the centre,
     // so the network runs on the raw ring values (0 .. 255) and the centre is subtracted once at the end.
     uint32_t Z[16];
@@ -547,6 +577,7 @@ __device__ __forceinline__ int fast_score_packed(const uint8_t* __restrict__ p, 
     const int Ad = v - min((int)(dm & 0xffffu), (int)(dm >> 16));        // darker arc: centre - max(ring)
     const int A = max(Ab, Ad);
     return A > t ? A - 1 : 0;
+#endif
 }
 
 #ifndef ORBX_FAST_MINB
@@ -815,30 +846,36 @@ fast_cells_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restr
 // fast_strips_kernel -- the product schedule of ComputeKeyPointsOctTree's cell loop (:789-829).
 //
 // The scoring regions of horizontally adjacent cells tile a cell row without gaps (cv::FAST scores the window minus a
-// 3-px frame, and windows overlap by 6), and the iniThFAST pre-test does not depend on the cell.  A CTA of 4 warps
-// therefore takes a strip of strip_nc (4) cells as ONE dense region whose 4-pixel words are aligned with the TMA tile
-// (two tile buffers: the next strip's tile is in flight while this one is processed):
-//   phase 1  warp = group of 8 rows, lane = tile word column: 3-5 aligned LDS, 2 funnel shifts, 4 VABSDIFF4 and the
-//            threshold logic per 4 pixels (no re-alignment shifts, no per-row address math: every offset is an
-//            immediate).  The survivor bits of 8 rows x 4 pixels are packed into one register.
-//   phase 1b one warp scan of the per-lane survivor counts + the four warp totals, then every lane appends its own
+// 3-px frame, and windows overlap by 6), and the iniThFAST pre-test does not depend on the cell.  A CTA therefore takes
+// a strip of strip_nc (4) cells as ONE dense region whose 4-pixel words are aligned with the TMA tile.  Everything a
+// strip needs that does not depend on the frame comes from a host-built 32-byte record (OrbxStripRec), and every
+// shared-memory structure (survivor queue entries aside) is indexed by the TILE BYTE OFFSET of the pixel, so no stage
+// converts coordinates:
+//   phase 1  warp = group of 8 rows, lane = tile word column: 5 aligned LDS, 2 funnel shifts, 4 VABSDIFF4 and the
+//            threshold logic per 4 pixels (every offset is an immediate).  The survivor bits of 8 rows x 4 pixels are
+//            packed into one register.
+//   phase 1b one warp scan of the per-lane survivor counts + the warp totals, then every lane appends its own
 //            survivors to the strip's queue (order is irrelevant here: the emission order comes from a bitmap).
-//   phase 2  exact score in full 32-lane batches over the whole strip (warp w takes batches w, w + 4, ...), corners to
-//            a strip-wide score map in which adjacent cells are separated by two zero columns, so NMS never sees across
-//            a cell boundary (cv::FAST's NMS treats everything outside the window's scoring region as score 0).  A warp
-//            compacts the map indices of its corners into the queue slots of its own consumed batches.
-//   phase 3  strict 3x3 NMS per corner; kept corners set a bit in a bitmap indexed like the score map.
+//   phase 2  exact score in full 32-lane batches over the whole strip (warp w takes batches w, w + W, ...); a corner's
+//            score goes to the score map and its tile offset is compacted into the queue slots of the warp's own
+//            consumed batches.
+//   phase 3  strict 3x3 NMS per corner.  cv::FAST's NMS treats everything outside the window's scoring region as score
+//            0, so a corner in the first / last scoring column of its cell ignores the neighbours in the adjacent cell.
+//            Kept corners set a bit in a bitmap.
 //   phase 4  warp = cell, lane = row: extract the row's bits, warp scan, claim the cell's block of the candidate
 //            region, write (x, y, score) in row-major order = cv::FAST's keypoint order.
-// A cell whose iniThFAST pass leaves no keypoint is redone with minThFAST (:812-816) by fast_cell_path on the same tile
-// (8.8 % of the cells of a 1080p cluttered frame, and they are the flat ones: few survivors).  Strips with more
-// survivors than the queue holds (noise) and levels whose cells are larger than 32 px go through fast_cell_path
-// entirely.
+// A cell whose iniThFAST pass leaves no keypoint is redone with minThFAST (:812-816) by a second pass over the same tile
+// restricted to those cells' columns (8.8 % of the cells of a 1080p cluttered frame, and they are the flat ones: few
+// survivors).  Strips with more survivors than the queue holds (noise) and levels whose cells are larger than 32 px go
+// through fast_cell_path.
 // =====================================================================================
 #ifndef ORBX_FS_MINB
-#define ORBX_FS_MINB (24 / ORBX_FS_WARPS)
+#define ORBX_FS_MINB (32 / ORBX_FS_WARPS)
 #endif
-#define ORBX_FS_GPW (4 / ORBX_FS_WARPS)      // 8-row groups (and cells) per warp
+#define ORBX_FS_CPW (4 / ORBX_FS_WARPS)      // cells per warp (phase 4)
+#ifndef ORBX_FS_P2U
+#define ORBX_FS_P2U 1                        // score batches per iteration of phase 2 (1 or 2; 2 measured no faster: 0.801 vs 0.806 ms)
+#endif
 
 template <int BW_T>
 __device__ __forceinline__ uint32_t fast_pretest_word(const uint32_t* __restrict__ p, uint32_t C, uint32_t colmask) {
@@ -856,9 +893,11 @@ __device__ __forceinline__ uint32_t fast_pretest_word(const uint32_t* __restrict
 
 #define ORBX_FS_NONE 0xffffffffu
 
-template <int BW_T>
+// NG: 8-row groups of a strip.  4 = cells of <= 32 scoring rows (nearly every level); 5 = cells of 33 .. 40 rows (the
+// "tall" cells of small levels: hCell = ceil(H / floor(H / 30)) reaches 40 when a level has 3 cell rows), own launch.
+template <int BW_T, int NG>
 __global__ void __launch_bounds__(ORBX_FS_WARPS * 32, ORBX_FS_MINB)
-fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, const uint32_t* __restrict__ strip_tab,
+fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restrict__ plan, const uint4* __restrict__ strip_rec,
                    int frame0, int nframes, int first_strip, int nstrips, uint32_t* __restrict__ cand, uint2* __restrict__ cell_rec,
                    int* __restrict__ level_counts, int* __restrict__ work_counter, int* __restrict__ status,
                    int* __restrict__ retry_counts) {
@@ -866,46 +905,55 @@ fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __rest
     // Everything a strip needs lives at fixed shared-memory addresses (sizes are compile-time: the plan only sends levels
     // with cells <= 32 x 32 here), so every LDS / STS below takes an immediate offset.
     constexpr int BW = BW_T, BW4 = BW_T / 4;
-    constexpr int BH = ORBX_FS_BH;                                       // tile rows: 32 scoring rows + the 6-px frame
+    constexpr int BH = 8 * NG + 6;                                       // tile rows: the scoring rows + the 6-px frame
+    constexpr int GPW = (NG + ORBX_FS_WARPS - 1) / ORBX_FS_WARPS;        // 8-row groups per warp (warp w takes groups w, w + W, ...)
+    constexpr int NR = (8 * NG + 31) / 32;                               // phase 4: rounds of 32 scoring rows
     constexpr int TB = (BW * BH + 127) & ~127;                           // tile bytes
-    constexpr int SP = BW_T - 20;                                        // score-map pitch >= cells * (wCell + 2)
-    constexpr int SBYTES = SP * (BH - 4);                                // map row = window y - 2
-    constexpr int KBW = (SBYTES + 31) / 32 + 2;                          // kept-corner bitmap, bit index = map index
-    constexpr int QCAP = ORBX_FS_QCAP;
+    constexpr int MOFF = 2 * BW;                                         // score map / bitmap index = tile byte offset - MOFF
+    constexpr int SBYTES = (BH - 4) * BW;                                // map rows = tile rows 2 .. BH - 3
+    constexpr int KBW = SBYTES / 32 + 1;                                 // kept-corner bitmap (+ 1: funnel read-ahead)
+    constexpr int QCAP = ORBX_FS_QCAP > 256 * NG ? ORBX_FS_QCAP : 256 * NG;   // one cell (32 x 8 NG pixels) always fits
+    constexpr int NT = ORBX_FS_WARPS * 32;
+    static_assert(BW_T % 32 == 0, "bitmap rows are whole words");
     __shared__ __align__(128) uint8_t s_tile[ORBX_FS_NBUF * TB];
-    __shared__ __align__(16) uint8_t sc[(SBYTES + 15) & ~15];
+    __shared__ __align__(16) uint8_t sc[SBYTES];
     __shared__ uint32_t kb[KBW];
     __shared__ __align__(16) uint16_t queue[QCAP];
     __shared__ uint64_t s_bar[2];
     __shared__ int s_wtot[ORBX_FS_WARPS];
-    __shared__ uint2 s_item[2];          // (frame or ORBX_FS_NONE, strip_tab entry) of the strip fetched two iterations ahead
+    __shared__ __align__(16) uint4 s_item[3][2];     // ring of strip records: this strip, the next one, the one being fetched
     __shared__ unsigned s_redo;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint8_t* const smem = s_tile;
     const int nlevels = plan->nlevels;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
-    // thread 0: next work item -> (frame, table entry); the table holds (level, cell row, first cell) of every strip of a frame
+    // thread 0: next work item -> its record (b.z = frame or ORBX_FS_NONE)
     auto fetch = [&](int slot) {
         const unsigned spf = (unsigned)nstrips;
         const unsigned v = (unsigned)atomicAdd(work_counter, 1);
-        uint2 r = make_uint2(ORBX_FS_NONE, 0u);
+        uint4 a = make_uint4(0u, 0u, 0u, 0u), b = make_uint4(0u, 0u, ORBX_FS_NONE, 0u);
         if (v < (unsigned)nframes * spf) {
-            r.x = v / spf;
-            r.y = __ldg(strip_tab + first_strip + (v - r.x * spf));
+            const unsigned f = v / spf;
+            const uint4* r = strip_rec + 2 * (size_t)(first_strip + (int)(v - f * spf));
+            a = __ldg(r);
+            b = __ldg(r + 1);
+            b.z = f;
         }
-        s_item[slot] = r;
+        s_item[slot][0] = a;
+        s_item[slot][1] = b;
     };
-    auto issue = [&](uint2 c, int b) {                   // thread 0 only
-        const int l = c.y & 15, ci = (c.y >> 4) & 0xfff, cj0 = c.y >> 16;
-        const OrbxLevel& L = plan->lv[l];
-        mbar_expect_tx(&s_bar[b], (uint32_t)(BW * BH));
-        tma_load_3d(smem + b * TB, &maps.m[l], &s_bar[b], (ORBX_XO + ORBX_BOX + cj0 * L.wCell - 1) & ~15,
-                    ORBX_EDGE + ORBX_BOX + ci * L.hCell, frame0 + (int)c.x);
+    auto issue = [&](int slot, int bi) {                 // thread 0 only (reads its own earlier writes)
+        const uint4 a = s_item[slot][0];
+        const unsigned f = s_item[slot][1].z;
+        if (f == ORBX_FS_NONE) return;
+        mbar_expect_tx(&s_bar[bi], (uint32_t)(BW * BH));
+        tma_load_3d(s_tile + bi * TB, &maps.m[a.y & 15u], &s_bar[bi], (int)(a.x & 0xffffu), (int)(a.x >> 16), frame0 + (int)f);
     };
+    // corner j of this warp lives in the queue slots of the warp's own consumed batches
+    auto cslot = [&](int j) { return (warp + ORBX_FS_WARPS * (j >> 5)) * 32 + (j & 31); };
 
-    for (int i = tid; i < (int)sizeof(sc) / 4; i += ORBX_FS_WARPS * 32) reinterpret_cast<uint32_t*>(sc)[i] = 0;
-    for (int i = tid; i < KBW; i += ORBX_FS_WARPS * 32) kb[i] = 0;
+    for (int i = tid; i < SBYTES / 4; i += NT) reinterpret_cast<uint32_t*>(sc)[i] = 0;
+    for (int i = tid; i < KBW; i += NT) kb[i] = 0;
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
@@ -914,69 +962,55 @@ fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __rest
         fetch(0);
         fetch(1);
         s_redo = 0;
+        issue(0, 0);
     }
     __syncthreads();
-    uint2 cur = s_item[0], nxt = s_item[1];
-    __syncthreads();                                                         // thread 0 reuses s_item[] below
-    if (tid == 0 && cur.x != ORBX_FS_NONE) issue(cur, 0);
     uint32_t phase[2] = {0, 0};
-    int b = 0, it = 0;
-    while (cur.x != ORBX_FS_NONE) {
+    int b = 0, slot = 0;
+    for (;;) {
+        const uint4 ra = s_item[slot][0], rb = s_item[slot][1];
+        if (rb.z == ORBX_FS_NONE) break;                                     // uniform
+        const int slot1 = slot == 2 ? 0 : slot + 1, slot2 = slot1 == 2 ? 0 : slot1 + 1;
         if (tid == 0) {
-            if (ORBX_FS_NBUF == 2 && nxt.x != ORBX_FS_NONE) issue(nxt, b ^ 1);   // buffer b ^ 1 was released by the last barrier of the previous strip
-            fetch(it & 1);                                                   // read after the next barrier
+            if (ORBX_FS_NBUF == 2) issue(slot1, b ^ 1);                      // buffer b ^ 1 was released by the last barrier of the previous strip
+            fetch(slot2);                                                    // slot2 held the previous strip: every thread is past reading it
         }
+        const int frame = (int)rb.z;
+        const int lvl = ra.y & 15, ncell = (ra.y >> 4) & 15, hr = (ra.y >> 8) & 0xff, delta0 = (ra.y >> 16) & 0xff, W0 = ra.y >> 24;
+        const int lo = ra.z & 0xffff, hi = ra.z >> 16;                       // tile byte columns of the strip's scoring pixels: [lo, hi)
+        const int wCell = ra.w & 0xffff, wrecip = ra.w >> 16;
         mbar_wait(&s_bar[b], phase[b]);
         phase[b] ^= 1;
 
-        uint8_t* tbuf = smem + b * TB;
-        const int frame = (int)cur.x, lvl = cur.y & 15, ci = (cur.y >> 4) & 0xfff, cj0 = cur.y >> 16;
-        const OrbxLevel& L = plan->lv[lvl];
-        const int wCell = L.wCell;
-        const int delta0 = (ORBX_XO + ORBX_BOX + cj0 * wCell - 1) & 15;      // tile byte of (strip window x0 - 1)
-        const int iniY = ORBX_BOX + ci * L.hCell;
-        const int wh = min(iniY + L.hCell + 6, L.maxBY) - iniY;
-        const int ncell = min(L.strip_nc, L.nColsV - cj0);
-        const int iniX0 = ORBX_BOX + cj0 * wCell;
-        const int sw = min(iniX0 + ncell * wCell + 6, L.maxBX) - iniX0;      // strip window width
-        const int hr = wh - 6;                                               // scoring rows: window y in [3, wh - 3)
-        FastEmit em;
-        em.cand = cand + (size_t)frame * plan->cand_per_frame + L.cand_off;
-        em.cell_rec = cell_rec + (size_t)frame * plan->cells_per_frame + L.cell_base;
-        em.level_count = &level_counts[frame * nlevels + lvl];
-        em.status = &status[frame];
-        em.retry_count = &retry_counts[frame * nlevels + lvl];
-        em.cand_cap = L.cand_cap;
-        const uint8_t* tile = tbuf + delta0 + 1;                             // byte of strip window pixel (0, 0)
-        ORBX_BC(wh <= BH && delta0 + 1 + sw + 7 <= BW && ncell >= 1 && ncell <= 4);
-        ORBX_BC(L.strip_ok && hr <= 32 && ncell * (wCell + 2) <= SP && (hr + 2) * SP <= SBYTES);
-        unsigned todo = (1u << ncell) - 1u;                                  // cells of the strip still without a result
-        unsigned cell_path = 0;              // cells left to fast_cell_path: bit k = minThFAST pass only, bit 8 + k = both passes
-        uint2 nxt2 = make_uint2(ORBX_FS_NONE, 0u);
-        bool have_next = false;
-        if (hr >= 1 && sw >= 7) {
-            const int wrecip = L.wcell_recip;
-            const int fb = delta0 + 4;                                       // tile byte of the first scoring pixel (window x = 3)
-            const int W0 = fb >> 2;
-            const int xb0 = 4 * W0 - delta0 - 1;                             // window x of byte 0 of lane 0's word
-            const int wxb = xb0 + 4 * lane;
+        uint8_t* const tbuf = s_tile + b * TB;
+        ORBX_BC(hr <= 8 * NG && ncell >= 1 && ncell <= 4 && lo == delta0 + 4 && hi <= BW - 4 && W0 == (lo >> 2));
+        // (:805-816) iniThFAST for every cell, then minThFAST for the cells that came back empty.  A task = one threshold
+        // applied to a set of cells (all of them unless their survivors exceed the queue: then the set is halved and the
+        // pre-test redone for fewer columns -- noise only; one cell always fits: 32 x 40 <= QCAP).
+        unsigned pend_ini = (1u << ncell) - 1u, pend_min = 0;                // cells waiting for their iniThFAST / minThFAST pass
+        int limit = 4;                                                       // cells per task
+        static_assert(QCAP >= 32 * 8 * NG, "a single cell's survivors must fit the queue");
+        if (hr >= 1) {                                                       // (the record says hr = 0 for windows smaller than 7 x 7)
+            const int bcol0 = 4 * (W0 + lane);                               // tile byte column of byte 0 of this lane's word
             const uint32_t* rp0 = reinterpret_cast<const uint32_t*>(tbuf) + 3 * BW4 + min(W0 + lane, BW4 - 2);
-            for (int pass = 0; pass < 2; ++pass) {
-                // (:805-816) iniThFAST for every cell, then minThFAST for the cells that came back empty
+            while ((pend_ini | pend_min) != 0) {                             // uniform
+                const int pass = pend_ini != 0 ? 0 : 1;
+                unsigned todo = pass == 0 ? pend_ini : pend_min;
+                while (__popc(todo) > limit) todo &= ~(0x80000000u >> __clz(todo));      // keep the lowest `limit` cells
                 const int t = pass == 0 ? plan->ini_th : plan->min_th;
                 const uint32_t C = (uint32_t)(0x7f - min(t, 0x7f)) * 0x01010101u;
                 // ---- phase 1: aligned SIMD pre-test; a warp takes ORBX_FS_GPW groups of 8 rows, lane = word column
                 uint32_t colmask = 0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int wx = wxb + j;
-                    if (wx >= 3 && wx < sw - 3 && ((todo >> (((wx - 3) * wrecip) >> 16)) & 1u)) colmask |= 0xffu << (8 * j);
+                    const int bc = bcol0 + j;
+                    if (bc >= lo && bc < hi && ((todo >> (((bc - lo) * wrecip) >> 16)) & 1u)) colmask |= 0xffu << (8 * j);
                 }
-                uint32_t acc[ORBX_FS_GPW];
+                uint32_t acc[GPW];
                 int cnt = 0;
 #pragma unroll
-                for (int gg = 0; gg < ORBX_FS_GPW; ++gg) {
-                    const int g = warp * ORBX_FS_GPW + gg;
+                for (int gg = 0; gg < GPW; ++gg) {
+                    const int g = warp + ORBX_FS_WARPS * gg;
                     const int nv = hr - 8 * g;                               // rows of this group
                     uint32_t a = 0;
                     if (nv > 0) {
@@ -1004,7 +1038,6 @@ fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __rest
                 }
                 if (lane == 31) s_wtot[warp] = incl;
                 __syncthreads();                                             // B1
-                if (!have_next) { nxt2 = s_item[it & 1]; have_next = true; }
                 int wbase = 0, qn = 0;
 #pragma unroll
                 for (int w = 0; w < ORBX_FS_WARPS; ++w) {
@@ -1012,15 +1045,17 @@ fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __rest
                     if (w < warp) wbase += v;
                     qn += v;
                 }
-                if (qn > QCAP) {                                             // noise: cell by cell (uniform branch)
-                    cell_path = pass == 0 ? todo << 8 : todo;
-                    break;
+                if (qn > QCAP) {                                             // noise (uniform branch): fewer cells per task
+                    ORBX_BC(limit > 1);
+                    limit >>= 1;
+                    __syncthreads();                                         // s_wtot is rewritten by the next task
+                    continue;
                 }
                 {
                     uint16_t* wq = queue + wbase + (incl - cnt);
 #pragma unroll
-                    for (int gg = 0; gg < ORBX_FS_GPW; ++gg) {
-                        const int e0 = ((warp * ORBX_FS_GPW + gg) << 10) | (lane << 5);    // entry: row group | lane | bit of acc
+                    for (int gg = 0; gg < GPW; ++gg) {
+                        const int e0 = ((warp + ORBX_FS_WARPS * gg) << 10) | (lane << 5);  // entry: row group | lane | bit of acc
                         uint32_t a = acc[gg];
                         while (a) {
                             const int bit = __ffs((int)a) - 1;
@@ -1031,134 +1066,147 @@ fast_strips_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __rest
                     }
                 }
                 __syncthreads();                                             // B2
-                // ---- phase 2: exact score; corners to the strip map, their map indices compacted into this warp's batches
+                // ---- phase 2: exact score; corners to the score map, their tile offsets compacted into this warp's batches
                 int cn = 0;                                                  // corners of this warp
-                for (int i0 = warp * 32; i0 < qn; i0 += ORBX_FS_WARPS * 32) {
-                    const int i = i0 + lane;
+                const int off0 = 3 * BW + 4 * W0;                            // tile byte of (scoring row 0, this strip's word column 0, byte 0)
+                auto entry_off = [&](int i) {                                // queue entry -> tile byte offset
                     const int e = queue[min(i, qn - 1)];                     // clamped: every lane scores a real pixel
                     const int r = e & 7;
                     const int wc = ((e >> 5) + 4 * r) & 31;                  // word column (undo the lane rotation of phase 1)
-                    const int x = xb0 + 4 * wc + ((e >> 3) & 3);
-                    const int y = 3 + ((e >> 7) & 0x18) + r;                 // 8 * group + row
-                    ORBX_BC(y >= 3 && y < wh - 3 && x >= 3 && x < sw - 3 && (y + 3) * BW + delta0 + 1 + x + 3 < TB);
-                    int s = fast_score_packed(tile + y * BW + x, BW, t);
-                    if (i >= qn) s = 0;
+                    const int off = off0 + (((e >> 7) & 0x38) + r) * BW + 4 * wc + ((e >> 3) & 3);
+                    ORBX_BC(off >= 3 * BW + lo && off < (3 + hr) * BW && off % BW >= lo && off % BW < hi);
+                    return off;
+                };
+                auto put_corners = [&](int off, int s, int i0) {             // i0: first queue index of the batch just consumed
                     const uint32_t bal = __ballot_sync(0xffffffffu, s > 0);
                     if (s > 0) {
-                        const int k = ((x - 3) * wrecip) >> 16;              // cell of the strip
-                        const int idx = (y - 2) * SP + x - 2 + 2 * k;        // two zero columns between cells
-                        ORBX_BC(k >= 0 && k < ncell && idx > SP && idx < SBYTES - SP - 1);
-                        sc[idx] = (uint8_t)s;
+                        sc[off - MOFF] = (uint8_t)s;
                         const int j = cn + __popc(bal & lt_mask);
-                        ORBX_BC((warp + ORBX_FS_WARPS * (j >> 5)) * 32 + (j & 31) < i0 + 32);      // in-place: never ahead of the read position
-                        queue[(warp + ORBX_FS_WARPS * (j >> 5)) * 32 + (j & 31)] = (uint16_t)idx;
+                        ORBX_BC(cslot(j) < i0 + 32);                         // in place: never ahead of the read position
+                        (void)i0;
+                        queue[cslot(j)] = (uint16_t)off;
                     }
                     cn += __popc(bal);
+                };
+                int i0 = warp * 32;
+#if ORBX_FS_P2U == 2
+                // two batches per iteration: their queue reads, ring loads and score networks are independent chains
+                for (; i0 + NT < qn; i0 += 2 * NT) {
+                    const int ia = i0 + lane, ib = ia + NT;
+                    const int offa = entry_off(ia), offb = entry_off(ib);
+                    int sa = fast_score_packed(tbuf + offa, BW, t);
+                    int sb = fast_score_packed(tbuf + offb, BW, t);
+                    if (ib >= qn) sb = 0;
+                    put_corners(offa, sa, i0);
+                    put_corners(offb, sb, i0 + NT);
+                }
+#endif
+                for (; i0 < qn; i0 += NT) {
+                    const int i = i0 + lane;
+                    const int off = entry_off(i);
+                    int s = fast_score_packed(tbuf + off, BW, t);
+                    if (i >= qn) s = 0;
+                    put_corners(off, s, i0);
                 }
                 __syncthreads();                                             // B3
-                // ---- phase 3: strict 3x3 NMS; kept corners -> bitmap
+                // ---- phase 3: strict 3x3 NMS inside the corner's own cell; kept corners -> bitmap
                 for (int j0 = 0; j0 < cn; j0 += 32) {
                     const int j = j0 + lane;
                     if (j < cn) {
-                        const int idx = queue[(warp + ORBX_FS_WARPS * (j >> 5)) * 32 + (j & 31)];
-                        ORBX_BC(idx > SP && idx < SBYTES - SP - 1 && (idx >> 5) < KBW);
-                        const uint8_t* mp = sc + idx;
-                        const int m8 = max(max(max((int)mp[-1], (int)mp[1]), max((int)mp[-SP - 1], (int)mp[-SP])),
-                                           max(max((int)mp[-SP + 1], (int)mp[SP - 1]), max((int)mp[SP], (int)mp[SP + 1])));
-                        if ((int)mp[0] > m8) atomicOr(&kb[idx >> 5], 1u << (idx & 31));
+                        const int off = queue[cslot(j)];
+                        const int y = off / BW;
+                        const int c = off - y * BW - lo;                     // scoring column of the strip
+                        const int xin = c - ((c * wrecip) >> 16) * wCell;    // ... of the cell
+                        ORBX_BC(c >= 0 && xin >= 0 && xin < wCell && off - MOFF > BW && off - MOFF < SBYTES - BW - 1);
+                        const uint8_t* mp = sc + (off - MOFF);
+                        int m8 = max((int)mp[-BW], (int)mp[BW]);
+                        if (xin != 0) m8 = max(m8, max(max((int)mp[-BW - 1], (int)mp[-1]), (int)mp[BW - 1]));
+                        if (xin != wCell - 1) m8 = max(m8, max(max((int)mp[-BW + 1], (int)mp[1]), (int)mp[BW + 1]));
+                        if ((int)mp[0] > m8) atomicOr(&kb[(off - MOFF) >> 5], 1u << (off & 31));
                     }
                 }
                 __syncthreads();                                             // B4
                 // ---- phase 4: warp = cell, lane = scoring row; ordered emission
+                const OrbxLevel& L = plan->lv[lvl];
 #pragma unroll
-                for (int kk = 0; kk < ORBX_FS_GPW; ++kk)
+                for (int kk = 0; kk < ORBX_FS_CPW; ++kk)
                 if ((todo >> (warp + kk * ORBX_FS_WARPS)) & 1u) {
                     const int k = warp + kk * ORBX_FS_WARPS;
-                    const int cstep = wCell + 2;
+                    const int x0 = lo + k * wCell;                           // tile byte column of the cell's first scoring column
                     const uint32_t cmask = wCell >= 32 ? 0xffffffffu : ((1u << wCell) - 1u);
-                    uint32_t bits = 0;
-                    if (lane < hr) {
-                        const int sb = (lane + 1) * SP + k * cstep + 1;
-                        ORBX_BC((sb >> 5) + 1 < KBW && sb + wCell <= SBYTES);
-                        bits = __funnelshift_r(kb[sb >> 5], kb[(sb >> 5) + 1], sb & 31) & cmask;
-                    }
-                    const int c = __popc(bits);
-                    int inc = c;
+                    uint32_t bits[NR];
+                    int excl[NR];
+                    int tot = 0;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int v = __shfl_up_sync(0xffffffffu, inc, o);
-                        if (lane >= o) inc += v;
+                    for (int q = 0; q < NR; ++q) {                           // scoring row 32 q + lane
+                        const int mrow = (32 * q + lane + 1) * BW + x0;      // map index of (that row, x0)
+                        bits[q] = 0;
+                        if (32 * q + lane < hr) {
+                            ORBX_BC((mrow >> 5) + 1 < KBW && mrow + wCell <= SBYTES);
+                            bits[q] = __funnelshift_r(kb[mrow >> 5], kb[(mrow >> 5) + 1], x0 & 31) & cmask;
+                        }
+                        const int c = __popc(bits[q]);
+                        int inc = c;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                            if (lane >= o) inc += v;
+                        }
+                        excl[q] = tot + inc - c;
+                        tot += __shfl_sync(0xffffffffu, inc, 31);
                     }
-                    const int tot = __shfl_sync(0xffffffffu, inc, 31);
-                    if (pass == 1 && lane == 0) atomicAdd(em.retry_count, 1);                          // (:812) statistics only
+                    if (pass == 1 && lane == 0) atomicAdd(&retry_counts[frame * nlevels + lvl], 1);    // (:812) statistics only
+                    uint2* rec = cell_rec + (size_t)frame * plan->cells_per_frame + rb.x + k;
                     if (tot == 0) {
                         if (lane == 0) {
                             if (pass == 0) atomicOr(&s_redo, 1u << k);
-                            else em.cell_rec[ci * L.nColsV + cj0 + k] = make_uint2(0u, 0u);
+                            else *rec = make_uint2(0u, 0u);
                         }
                     } else {
                         int gbase = 0;
-                        if (lane == 0) gbase = atomicAdd(em.level_count, tot);
+                        if (lane == 0) gbase = atomicAdd(&level_counts[frame * nlevels + lvl], tot);
                         gbase = __shfl_sync(0xffffffffu, gbase, 0);
-                        const bool overflow = gbase + tot > em.cand_cap;
-                        if (overflow && lane == 0) atomicOr(em.status, ORBX_DEV_CAND_OVERFLOW);
-                        uint32_t* dst = em.cand + gbase + (inc - c);
-                        const uint8_t* srow = sc + (lane + 1) * SP + k * cstep + 1;
-                        const int ox = (cj0 + k) * wCell + 3, oy = ci * L.hCell + 3 + lane;            // (:822-823)
-                        uint32_t bb = overflow ? 0u : bits;
-                        while (bb) {
-                            const int x = __ffs((int)bb) - 1;
-                            bb &= bb - 1;
-                            *dst++ = ORBX_PACK(x + ox, oy, srow[x]);
+                        const bool overflow = gbase + tot > L.cand_cap;
+                        if (overflow && lane == 0) atomicOr(&status[frame], ORBX_DEV_CAND_OVERFLOW);
+                        uint32_t* const dst0 = cand + (size_t)frame * plan->cand_per_frame + L.cand_off + gbase;
+                        const int ox = (int)(rb.y & 0xffffu) + k * wCell;    // (:822-823)
+#pragma unroll
+                        for (int q = 0; q < NR; ++q) {
+                            uint32_t* dst = dst0 + excl[q];
+                            const uint8_t* srow = sc + (32 * q + lane + 1) * BW + x0;
+                            const int oy = (int)(rb.y >> 16) + 32 * q + lane;
+                            uint32_t bb = overflow ? 0u : bits[q];
+                            while (bb) {
+                                const int x = __ffs((int)bb) - 1;
+                                bb &= bb - 1;
+                                *dst++ = ORBX_PACK(x + ox, oy, srow[x]);
+                            }
                         }
-                        if (lane == 0)
-                            em.cell_rec[ci * L.nColsV + cj0 + k] = make_uint2((uint32_t)gbase, overflow ? 0u : (uint32_t)tot);
+                        if (lane == 0) *rec = make_uint2((uint32_t)gbase, overflow ? 0u : (uint32_t)tot);
                     }
                 }
                 __syncthreads();                                             // B5
                 // leave the score map and the bitmap all-zero
-                for (int j = lane; j < cn; j += 32) sc[queue[(warp + ORBX_FS_WARPS * (j >> 5)) * 32 + (j & 31)]] = 0;
-                for (int i = tid; i < KBW; i += ORBX_FS_WARPS * 32) kb[i] = 0;
-                const unsigned redo = pass == 0 ? s_redo : 0u;
-                if (redo == 0) break;                                        // uniform
-                todo = redo;
-            }
-        } else {
-            cell_path = todo << 8;
-        }
-        __syncthreads();                                                     // B6: map / bitmap zero, s_redo consumed
-        if (!have_next) nxt2 = s_item[it & 1];
-        if (tid == 0) s_redo = 0;
-        // ---- cells done one at a time by fast_cell_path: dense strips (noise) and strips shorter than 7 rows.  Warps 0 and 1
-        //      take the even and odd cells, each with its own half of the queue.
-        if (cell_path != 0) {
-            // (QCAP >= 2048: warps 0 and 1 take the even and odd cells, each with its own half of the queue; smaller queues:
-            // warp 0 takes them all)
-            constexpr int CPW = (ORBX_FS_WARPS > 1 && QCAP >= 2048) ? 2 : 1;
-            if (warp < CPW) {
-                uint16_t* myq = queue + warp * (QCAP / CPW);
-                for (int k = warp; k < ncell; k += CPW) {
-                    if (!((cell_path >> k) & 0x101u)) continue;
-                    const int cj = cj0 + k;
-                    const int iniX = ORBX_BOX + cj * wCell;
-                    const int ww = min(iniX + wCell + 6, L.maxBX) - iniX;
-                    const int delta = delta0 + k * wCell;                    // byte offset of (window x0 - 1) inside the tile
-                    fast_cell_path<BW_T>(plan, tbuf + delta + 1, reinterpret_cast<const uint32_t*>(tbuf) + (delta >> 2), (delta & 3) * 8,
-                                         BW, ww, wh, sc + k * (wCell + 2) - 3 - 2 * SP, SP, myq, (cell_path >> k) & 1u ? 1 : 0, em,
-                                         ci * L.nColsV + cj, cj * wCell, ci * L.hCell, lane,
-                                         QCAP / CPW, TB - delta - 1);
+                for (int j = lane; j < cn; j += 32) sc[queue[cslot(j)] - MOFF] = 0;
+                for (int i = tid; i < KBW; i += NT) kb[i] = 0;
+                if (pass == 0) {
+                    pend_ini &= ~todo;
+                    pend_min |= s_redo;                                      // (cumulative over this strip's iniThFAST tasks)
+                } else {
+                    pend_min &= ~todo;
                 }
             }
-            __syncthreads();                                                 // B7: tile buffer b is free
+        } else if (tid < ncell) {
+            cell_rec[(size_t)frame * plan->cells_per_frame + rb.x + tid] = make_uint2(0u, 0u);     // cv::FAST returns nothing for such a window
         }
+        __syncthreads();                                                     // B6: map / bitmap zero, s_redo consumed, tile buffer b free
+        if (tid == 0) s_redo = 0;
         if (ORBX_FS_NBUF == 1) {
-            if (tid == 0 && nxt.x != ORBX_FS_NONE) issue(nxt, 0);            // every warp is past its last read of the tile (B3 / B7)
+            if (tid == 0) issue(slot1, 0);                                   // every warp is past its last read of the tile (B3 / B7)
         } else {
             b ^= 1;
         }
-        cur = nxt;
-        nxt = nxt2;
-        ++it;
+        slot = slot1;
     }
 }
 
@@ -2993,7 +3041,7 @@ static int build_tile_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, i
         cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)hp.slab_bytes};
         if (fast_boxes) {              // strips of <= 32-px cells -> fast_strips_kernel's box, everything else -> fast_cells_kernel's
             bw = L.strip_ok ? hp.fast_bw : hp.cells_bw;
-            bh = L.strip_ok ? hp.fast_bh : hp.cells_bh;
+            bh = L.strip_ok ? (L.strip_tall ? ORBX_FS_BH_TALL : ORBX_FS_BH) : hp.cells_bh;
         }
         cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
         cuuint32_t estr[3] = {1, 1, 1};
@@ -3018,33 +3066,37 @@ int build_describe_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void
 size_t fast_maps_bytes() { return sizeof(FastMaps); }
 
 // One segment of the strip table (hp.seg_first / hp.seg_count: strips of levels 0-1, strips of levels 2+, big-cell levels
-// 0-1, big-cell levels 2+) for nframes frames: segments 0-1 go to fast_strips_kernel, 2-3 (levels whose cells are larger
-// than 32 x 32, or everything under ORBX_FAST_LEGACY=1) to fast_cells_kernel.  nseg = 2 launches two adjacent segments
+// 0-1, big-cell levels 2+, tall-cell strips of levels 0-1, of levels 2+) for nframes frames: segments 0-1 and 4-5 go to
+// fast_strips_kernel (4 / 5 row groups), 2-3 (levels whose cells are wider than 32 or taller than 40, or everything under
+// ORBX_FAST_LEGACY=1) to fast_cells_kernel.  nseg = 2 launches two adjacent segments
 // as one.  Each segment has its own work counter (work_counters[seg]).
 cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* maps, const OrbxTap* taps, int frame0, int nframes,
                         int seg, int nseg, int num_sms, uint32_t* cand, uint2* cell_rec, int* level_counts, int* work_counters,
                         int* status, int* retry_counts, cudaStream_t st) {
     typedef void (*fast_fn)(const FastMaps, const OrbxPlan*, const uint32_t*, int, int, int, int, uint32_t*, uint2*, int*, int*, int*, int*);
-    static const fast_fn all[7] = {fast_strips_kernel<96>, fast_strips_kernel<128>, fast_strips_kernel<160>,
-                                   fast_cells_kernel<64>,  fast_cells_kernel<96>,   fast_cells_kernel<128>, fast_cells_kernel<0>};
+    typedef void (*strips_fn)(const FastMaps, const OrbxPlan*, const uint4*, int, int, int, int, uint32_t*, uint2*, int*, int*, int*, int*);
+    static const strips_fn all_strips[6] = {fast_strips_kernel<96, 4>, fast_strips_kernel<128, 4>, fast_strips_kernel<160, 4>,
+                                            fast_strips_kernel<96, 5>, fast_strips_kernel<128, 5>, fast_strips_kernel<160, 5>};
+    static const fast_fn all_cells[4] = {fast_cells_kernel<64>, fast_cells_kernel<96>, fast_cells_kernel<128>, fast_cells_kernel<0>};
     const int first = hp.seg_first[seg];
     int nstrips = 0;
     for (int i = 0; i < nseg; ++i) nstrips += hp.seg_count[seg + i];
     if (nstrips == 0) return cudaSuccess;
-    const bool strips = seg < 2;
+    const bool strips = seg < 2 || seg >= 4;
     int which;
     if (strips) {
         which = hp.fast_bw == 96 ? 0 : hp.fast_bw == 128 ? 1 : hp.fast_bw == 160 ? 2 : -1;
         if (which < 0) return cudaErrorInvalidValue;
+        if (seg >= 4) which += 3;                                                // tall cells: 5 row groups
     } else {
-        which = hp.cells_bw == 64 ? 3 : hp.cells_bw == 96 ? 4 : hp.cells_bw == 128 ? 5 : 6;
+        which = 6 + (hp.cells_bw == 64 ? 0 : hp.cells_bw == 96 ? 1 : hp.cells_bw == 128 ? 2 : 3);
     }
-    const fast_fn fn = all[which];
+    const void* fn = strips ? reinterpret_cast<const void*>(all_strips[which]) : reinterpret_cast<const void*>(all_cells[which - 6]);
     const size_t smem = strips ? 0 : fast_smem_bytes(hp);
     const int W = strips ? ORBX_FS_WARPS : hp.fast_warps;
     // per device and kernel: the dynamic shared-memory limit that was configured and the resident CTAs per SM it gives
-    static size_t configured[64][7] = {};
-    static int per_sm_cache[64][7] = {};
+    static size_t configured[64][10] = {};
+    static int per_sm_cache[64][10] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
@@ -3074,7 +3126,11 @@ cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* 
     if (blocks < 1) blocks = 1;
     FastMaps fm;
     memcpy(&fm, maps, sizeof fm);
-    return launch_k(fn, dim3((unsigned)blocks), dim3(W * 32), smem, st, fm, d_plan,
+    if (strips)
+        return launch_k(all_strips[which], dim3((unsigned)blocks), dim3(W * 32), smem, st, fm, d_plan,
+                        reinterpret_cast<const uint4*>(taps + hp.strip_rec_off), frame0, nframes, first, nstrips, cand, cell_rec,
+                        level_counts, work_counters + seg, status, retry_counts);
+    return launch_k(all_cells[which - 6], dim3((unsigned)blocks), dim3(W * 32), smem, st, fm, d_plan,
                     reinterpret_cast<const uint32_t*>(taps + hp.strip_tab_off), frame0, nframes, first, nstrips, cand, cell_rec,
                     level_counts, work_counters + seg, status, retry_counts);
 }

@@ -17,8 +17,9 @@
 #define ORBX_FS_NBUF 1           // tile buffers per CTA.  2 hides the TMA latency but costs resident CTAs: 0.991 vs 0.891 ms
 #endif
 #define ORBX_FS_BH 38            // tile rows of a strip: cells of <= 32 scoring rows + the 6-px frame
+#define ORBX_FS_BH_TALL 46       // ... of 33 .. 40 scoring rows (fast_strips_kernel<BW, 5>)
 #ifndef ORBX_FS_QCAP
-#define ORBX_FS_QCAP 2048        // survivor queue entries of a strip (>= 1024: the per-cell path needs 32 x 32; from 2048 on two warps share it)
+#define ORBX_FS_QCAP 1536        // survivor queue entries of a strip (>= 1280: the per-cell path needs 32 x 40).  1536 lets 14 CTAs share an SM (0.790 vs 0.806 ms with 2048 / 12 CTAs); 1024 sends cluttered strips to the per-cell path (1.00 ms)
 #endif
 #define ORBX_OT_THREADS 1024
 #define ORBX_OT_KEYCAP 8192     // candidates of one level kept in shared memory by the octree kernel (6 bytes each)

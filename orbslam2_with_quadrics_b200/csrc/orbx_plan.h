@@ -28,7 +28,8 @@ struct OrbxLevel {
     int cell_base;            // first cell of this level inside a frame (cell_rec index)
     int strips_x;             // FAST work items: strips of strip_nc cells per cell row
     int strip_nc;             // cells per strip of this level (a strip's scoring pixels fit 32 tile words)
-    int strip_ok;             // 1: fast_strips_kernel's dense strip path applies (cells <= 32 x 32), 0: cell by cell
+    int strip_ok;             // 1: fast_strips_kernel's dense strip path applies (cells <= 32 wide, <= 40 tall), 0: cell by cell
+    int strip_tall;           // 1: cells of 33 .. 40 rows (fast_strips_kernel<BW, 5>, own table segment)
     int wcell_recip;          // 65536 / wCell + 1: (n * wcell_recip) >> 16 == n / wCell for n < 256
     int cand_off, cand_cap;   // this level's region in a frame's candidate buffers (entries)
     int quota;                // mnFeaturesPerLevel[l]
@@ -61,13 +62,28 @@ struct OrbxPlan {
     int fast_legacy;              // 1: fast_cells_kernel (ORBX_FAST_LEGACY=1, A/B measurements)
     int strips_per_frame;
     int strip_tab_off;            // strip table (level | cell row << 4 | first cell << 16 per strip of a frame) inside the tap tables, OrbxTap units
-    int seg_first[4], seg_count[4];   // table segments: strips of levels 0-1, strips of levels 2+, big-cell levels 0-1, big-cell levels 2+
+    int strip_rec_off;            // OrbxStripRec of every strip of a frame (same order as the strip table), OrbxTap units, 16-byte aligned
+    int seg_first[6], seg_count[6];   // table segments: strips of levels 0-1, strips of levels 2+, big-cell levels 0-1, big-cell levels 2+, tall-cell strips of levels 0-1, of levels 2+
     int ini_th, min_th;
     long long slab_bytes;     // one frame's pyramid slab
     float atan_p1, atan_p3, atan_p5, atan_p7;   // cv::fastAtan2 coefficients (float products)
     float factor_pi;          // (float)(CV_PI/180.f) (:107)
     int umax[16];             // (:454-469)
     OrbxLevel lv[ORBX_MAXL];
+};
+
+// Everything fast_strips_kernel needs to know about one strip of a frame (frame-independent, built with the plan).
+// "tile byte" = byte offset inside the strip's TMA tile row; the strip's scoring pixels (window x in [3, sw - 3)) are
+// tile byte columns [lo, hi).
+struct OrbxStripRec {
+    uint32_t tile_xy;         // TMA start: plane column (multiple of 16) | plane row << 16
+    uint32_t shape;           // level | cells << 4 | scoring rows (0: window smaller than 7 x 7) << 8 | delta0 << 16 | lo / 4 << 24
+    uint32_t cols;            // lo | hi << 16
+    uint32_t cellw;           // wCell | wcell_recip << 16
+    uint32_t cell0;           // cell_rec index of the strip's first cell inside a frame
+    uint32_t origin;          // level x | y << 16 of the first scoring pixel (:822-823 offsets included)
+    uint32_t frame;           // filled in by the kernel
+    uint32_t window;          // strip window width | height << 16
 };
 
 // Column plan of one lane of pyr_resize8_kernel: 8 adjacent plane columns (from plane column 8 + 8 * group), as two
