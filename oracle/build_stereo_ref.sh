@@ -1,7 +1,8 @@
 #!/bin/sh
 # Builds oracle/_ref/libstereoref.so: the reference's OWN lines of Frame::ComputeStereoMatches,
 # ORBmatcher::DescriptorDistance, the Frame undistort/grid functions, Frame::GetFeaturesInArea and
-# ORBmatcher::SearchByProjection(Frame&, const Frame&) / ComputeThreeMaxima, taken at build time from where they lie under $REF (never copied into this
+# ORBmatcher::SearchByProjection(Frame&, const Frame&) / ComputeThreeMaxima, SearchByProjection(Frame&, vpMapPoints), SearchByBoW(KeyFrame*,
+# Frame&), SearchForInitialization, SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) and MapPoint::PredictScale, taken at build time from where they lie under $REF (never copied into this
 # repo: the generated translation unit lives in a temporary directory and only the .so is kept), compiled against
 # oracle/shim_stereo/stereo_shim.h.  TEST INFRASTRUCTURE only.
 set -e
@@ -10,6 +11,7 @@ HERE=$(cd "$(dirname "$0")" && pwd)
 OUT=$HERE/_ref
 F=$REF/src/Frame.cc
 M=$REF/src/ORBmatcher.cc
+P=$REF/src/MapPoint.cc
 # the line ranges are pinned to the reference revision surveyed in SURVEY.md; refuse to build from anything else
 sed -n '466p' "$F" | grep -q 'void Frame::ComputeStereoMatches()' || { echo "Frame.cc:466 is not ComputeStereoMatches"; exit 1; }
 sed -n '640p' "$F" | grep -q '^}' || { echo "Frame.cc:640 is not the end of ComputeStereoMatches"; exit 1; }
@@ -27,6 +29,13 @@ sed -n '129p' "$M" | grep -q '^}' || { echo "ORBmatcher.cc:129 is not the end of
 sed -n '131p' "$M" | grep -q 'float ORBmatcher::RadiusByViewingCos' || { echo "ORBmatcher.cc:131 is not RadiusByViewingCos"; exit 1; }
 sed -n '159p' "$M" | grep -q 'int ORBmatcher::SearchByBoW(KeyFrame\* pKF,Frame &F' || { echo "ORBmatcher.cc:159 is not SearchByBoW(KeyFrame*, Frame&)"; exit 1; }
 sed -n '288p' "$M" | grep -q '^}' || { echo "ORBmatcher.cc:288 is not the end of SearchByBoW(KeyFrame*, Frame&)"; exit 1; }
+sed -n '405p' "$M" | grep -q 'int ORBmatcher::SearchForInitialization' || { echo "ORBmatcher.cc:405 is not SearchForInitialization"; exit 1; }
+sed -n '520p' "$M" | grep -q '^}' || { echo "ORBmatcher.cc:520 is not the end of SearchForInitialization"; exit 1; }
+sed -n '1472p' "$M" | grep -q 'int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame \*pKF' || { echo "ORBmatcher.cc:1472 is not SearchByProjection(Frame&, KeyFrame*, ...)"; exit 1; }
+sed -n '1599p' "$M" | grep -q '^}' || { echo "ORBmatcher.cc:1599 is not the end of SearchByProjection(Frame&, KeyFrame*, ...)"; exit 1; }
+sed -n '373p' "$P" | grep -q 'float MapPoint::GetMinDistanceInvariance' || { echo "MapPoint.cc:373 is not GetMinDistanceInvariance"; exit 1; }
+sed -n '402p' "$P" | grep -q 'int MapPoint::PredictScale(const float &currentDist, Frame\* pF)' || { echo "MapPoint.cc:402 is not PredictScale(dist, Frame*)"; exit 1; }
+sed -n '417p' "$P" | grep -q '^}' || { echo "MapPoint.cc:417 is not the end of PredictScale"; exit 1; }
 TMP=$(mktemp -d)
 trap 'rm -rf "$TMP"' EXIT
 {
@@ -44,6 +53,10 @@ trap 'rm -rf "$TMP"' EXIT
   sed -n '1601,1642p' "$M"
   sed -n '45,137p' "$M"
   sed -n '159,288p' "$M"
+  sed -n '405,520p' "$M"
+  sed -n '1472,1599p' "$M"
+  sed -n '373,383p' "$P"
+  sed -n '402,417p' "$P"
   echo '}'
 } > "$TMP/stereo_ref_gen.cpp"
 mkdir -p "$OUT"

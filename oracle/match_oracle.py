@@ -375,3 +375,244 @@ def ref_search_by_bow(kf_desc, kf_valid, kf_angle, kf_fv_nodes, kf_fv_features, 
                                     C.c_int(len(c[0])), p(c[0]), p(c[1]), C.c_int(len(d[0])), p(d[0]), p(d[1]), C.c_float(nnratio),
                                     C.c_int(int(check_orientation)), p(out))
     return int(n), out
+
+
+# ============================================================================= Relocalization's SearchByProjection(Frame&, KeyFrame*)
+_libm = None
+
+
+def _logf(x) -> np.float32:
+    """std::log(float) of the C library the reference links (MapPoint.cc:410: `log(ratio)` with a float argument under
+    `using namespace std` resolves to the float overload)."""
+    global _libm
+    if _libm is None:
+        _libm = C.CDLL("libm.so.6")
+        _libm.logf.restype = C.c_float
+        _libm.logf.argtypes = [C.c_float]
+    return f32(_libm.logf(C.c_float(float(x))))
+
+
+def kf_prepare(valid, world, min_dist, max_dist, Tcw_cur, log_scale_factor, nlevels):
+    """What a caller of orbx_search_by_projection_kf stages per KeyFrame map point, by the arithmetic of the reference's lines:
+    Ow = -Rcw.t()*tcw (src/ORBmatcher.cc:1476-1478), dist3D = cv::norm(x3Dw - Ow) and the distance-invariance test (:1510-1518,
+    src/MapPoint.cc:373-383), nPredictedLevel = pMP->PredictScale(dist3D, &CurrentFrame) (:1520, src/MapPoint.cc:402-417).
+    Returns (in_range uint8[n], pred_level int32[n])."""
+    import cv2
+    n = len(valid)
+    Tc = np.asarray(Tcw_cur, f32).reshape(4, 4)
+    Ow = _gemm(Tc[:3, :3], Tc[:3, 3:4], None, -1.0, cv2.GEMM_1_T)
+    W = np.asarray(world, f32).reshape(n, 3)
+    in_range = np.zeros(n, np.uint8)
+    pred = np.zeros(n, np.int32)
+    for i in range(n):
+        if not valid[i]:
+            continue
+        PO = (W[i].reshape(3, 1) - Ow).astype(f32)
+        dist3D = f32(cv2.norm(PO))
+        if dist3D < f32(f32(0.8) * f32(min_dist[i])) or dist3D > f32(f32(1.2) * f32(max_dist[i])):
+            continue
+        in_range[i] = 1
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = f32(f32(max_dist[i]) / dist3D)
+        q = f32(_logf(ratio) / f32(log_scale_factor))
+        ns = int(math.ceil(float(q))) if np.isfinite(q) else 0
+        pred[i] = 0 if ns < 0 else (nlevels - 1 if ns >= nlevels else ns)
+    return in_range, pred
+
+
+def search_by_projection_kf(valid, world, mp_desc, in_range, pred_level, kf_angle, Tcw_cur, xy_un, cur_octave, cur_angle, desc,
+                            cur_held, cell_start, cell_items, bounds, K4, sf, th, orb_dist, check_orientation=True):
+    """ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1472-1599).
+    valid[i]: 0 = no map point, 1 = good, 2 = isBad(), 3 = in sAlreadyFound; (in_range, pred_level) from kf_prepare;
+    cur_held[i2] != 0: CurrentFrame.mvpMapPoints[i2] is not NULL at entry.
+    Returns (nmatches, new_match int32[nC]: index of the KeyFrame point the call set mvpMapPoints[i2] to and kept, else -1)."""
+    nP, nC = len(valid), len(desc)
+    Tc = np.asarray(Tcw_cur, f32).reshape(4, 4)
+    fx, fy, cx, cy = [f32(v) for v in K4]
+    mnx, mxx, mny, mxy = [f32(b) for b in bounds]
+    factor = f32(f32(1.0) / f32(HISTO_LENGTH))
+    desc64 = np.ascontiguousarray(desc).view(np.uint64).reshape(nC, 4) if nC else np.zeros((0, 4), np.uint64)
+    q64 = np.ascontiguousarray(mp_desc).view(np.uint64).reshape(nP, 4) if nP else np.zeros((0, 4), np.uint64)
+    held = np.asarray(cur_held).astype(bool).copy()
+    new_match = np.full(nC, -1, np.int32)
+    rot_hist = [[] for _ in range(HISTO_LENGTH)]
+    nmatches = 0
+    W = np.asarray(world, f32).reshape(nP, 3)
+    for i in range(nP):
+        if valid[i] != 1:
+            continue
+        X = _gemm(Tc[:3, :3], W[i].reshape(3, 1), Tc[:3, 3:4])
+        xc, yc, zc = f32(X[0, 0]), f32(X[1, 0]), f32(X[2, 0])
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            invzc = f32(np.float64(1.0) / np.float64(zc))
+            u = f32(f32(f32(fx * xc) * invzc) + cx)
+            v = f32(f32(f32(fy * yc) * invzc) + cy)
+        if u < mnx or u > mxx or v < mny or v > mxy:
+            continue
+        if not (np.isfinite(u) and np.isfinite(v)):
+            continue                               # NaN: undefined grid index in the reference; defined as "no candidates"
+        if not in_range[i]:
+            continue
+        lvl = int(pred_level[i])
+        radius = f32(f32(th) * f32(sf[lvl]))
+        cands = features_in_area(u, v, radius, lvl - 1, lvl + 1, xy_un, cur_octave, cell_start, cell_items, bounds)
+        if not cands:
+            continue
+        best, best_idx = 256, -1
+        for i2 in cands:
+            if held[i2]:
+                continue
+            d = int(sum(bin(int(a ^ b)).count("1") for a, b in zip(q64[i], desc64[i2])))
+            if d < best:
+                best, best_idx = d, i2
+        if best <= orb_dist:
+            held[best_idx] = True
+            new_match[best_idx] = i
+            nmatches += 1
+            if check_orientation:
+                rot = f32(f32(kf_angle[i]) - f32(cur_angle[best_idx]))
+                if rot < 0.0:
+                    rot = f32(rot + f32(360.0))
+                b = _round_half_away(f32(rot * factor))
+                if b == HISTO_LENGTH:
+                    b = 0
+                rot_hist[b].append(best_idx)
+    if check_orientation:
+        ind = compute_three_maxima([len(h) for h in rot_hist])
+        for b in range(HISTO_LENGTH):
+            if b not in ind:
+                for i2 in rot_hist[b]:
+                    new_match[i2] = -1
+                    nmatches -= 1
+    return nmatches, new_match
+
+
+def _kp7(xy_un, angle, octave):
+    n = len(octave)
+    kp = np.zeros((n, 7), f32)
+    kp[:, 0:2] = np.asarray(xy_un, f32).reshape(n, 2)
+    kp[:, 3] = np.asarray(angle, f32)
+    kp[:, 5] = np.asarray(octave, np.int32).view(f32)
+    return kp
+
+
+def _load_ref():
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(os.path.join(_HERE, "_ref", "libstereoref.so"))
+        _ref.matchref_search_by_projection.restype = C.c_int
+    return _ref
+
+
+def ref_has(name: str) -> bool:
+    return ref_available() and hasattr(_load_ref(), name)
+
+
+def ref_search_by_projection_kf(valid, world, mp_desc, min_dist, max_dist, kf_angle, Tcw_cur, xy_un, cur_octave, cur_angle, desc,
+                                cur_held, cell_start, cell_items, bounds, K4, sf, log_scale_factor, th, orb_dist,
+                                check_orientation=True):
+    """The reference's own lines (oracle/_ref/libstereoref.so).  Returns (nmatches, new_match, in_range, pred_level): the last two
+    are what its own distance test and MapPoint::PredictScale say per point."""
+    r = _load_ref()
+    r.matchref_search_by_projection_kf.restype = C.c_int
+    nP, nC = len(valid), len(desc)
+    kp = _kp7(xy_un, cur_angle, cur_octave)
+    a = [np.ascontiguousarray(valid, np.uint8), np.ascontiguousarray(world, f32), np.ascontiguousarray(mp_desc, np.uint8),
+         np.ascontiguousarray(min_dist, f32), np.ascontiguousarray(max_dist, f32), np.ascontiguousarray(kf_angle, f32),
+         np.ascontiguousarray(Tcw_cur, f32).reshape(16)]
+    b = [np.ascontiguousarray(desc, np.uint8), np.ascontiguousarray(cur_held, np.uint8), np.ascontiguousarray(cell_start, np.int32),
+         np.ascontiguousarray(cell_items, np.int32), np.ascontiguousarray(bounds, f32), np.ascontiguousarray(K4, f32),
+         np.ascontiguousarray(sf, f32)]
+    out = np.full(nC, -1, np.int32)
+    pred = np.zeros(nP, np.int32)
+    inr = np.zeros(nP, np.uint8)
+    p = lambda x: C.c_void_p(x.ctypes.data)
+    n = r.matchref_search_by_projection_kf(C.c_int(nP), *[p(x) for x in a], C.c_int(nC), p(kp), *[p(x) for x in b], C.c_int(len(b[6])),
+                                           C.c_float(log_scale_factor), C.c_float(th), C.c_int(int(orb_dist)),
+                                           C.c_int(int(check_orientation)), p(out), p(pred), p(inr))
+    return int(n), out, inr, pred
+
+
+# ============================================================================= MonocularInitialization's SearchForInitialization
+INT_MAX = 2 ** 31 - 1
+
+
+def search_for_initialization(xy_un1, octave1, angle1, desc1, prev_matched, xy_un2, octave2, angle2, desc2, cell_start, cell_items,
+                              bounds, nnratio=0.9, check_orientation=True, window=100):
+    """ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:405-520).
+    Returns (nmatches, matches12 int32[n1], prev_matched float32[n1, 2] as updated at :515-517)."""
+    n1, n2 = len(desc1), len(desc2)
+    d1 = np.ascontiguousarray(desc1).view(np.uint64).reshape(n1, 4) if n1 else np.zeros((0, 4), np.uint64)
+    d2 = np.ascontiguousarray(desc2).view(np.uint64).reshape(n2, 4) if n2 else np.zeros((0, 4), np.uint64)
+    prev = np.asarray(prev_matched, f32).reshape(n1, 2).copy()
+    m12 = np.full(n1, -1, np.int32)
+    m21 = np.full(n2, -1, np.int64)
+    matched_dist = np.full(n2, INT_MAX, np.int64)
+    rot_hist = [[] for _ in range(HISTO_LENGTH)]
+    factor = f32(f32(1.0) / f32(HISTO_LENGTH))
+    nmatches = 0
+    for i1 in range(n1):
+        level1 = int(octave1[i1])
+        if level1 > 0:
+            continue
+        cands = features_in_area(prev[i1, 0], prev[i1, 1], f32(window), level1, level1, xy_un2, octave2, cell_start, cell_items, bounds)
+        if not cands:
+            continue
+        best = best2 = INT_MAX
+        best_idx = -1
+        for i2 in cands:
+            d = int(sum(bin(int(a ^ b)).count("1") for a, b in zip(d1[i1], d2[i2])))
+            if matched_dist[i2] <= d:
+                continue
+            if d < best:
+                best2, best, best_idx = best, d, i2
+            elif d < best2:
+                best2 = d
+        if best <= TH_LOW:
+            if f32(best) < f32(f32(best2) * f32(nnratio)):
+                if m21[best_idx] >= 0:
+                    m12[m21[best_idx]] = -1
+                    nmatches -= 1
+                m12[i1] = best_idx
+                m21[best_idx] = i1
+                matched_dist[best_idx] = best
+                nmatches += 1
+                if check_orientation:
+                    rot = f32(f32(angle1[i1]) - f32(angle2[best_idx]))
+                    if rot < 0.0:
+                        rot = f32(rot + f32(360.0))
+                    b = _round_half_away(f32(rot * factor))
+                    if b == HISTO_LENGTH:
+                        b = 0
+                    rot_hist[b].append(i1)
+    if check_orientation:
+        ind = compute_three_maxima([len(h) for h in rot_hist])
+        for b in range(HISTO_LENGTH):
+            if b in ind:
+                continue
+            for idx1 in rot_hist[b]:
+                if m12[idx1] >= 0:
+                    m12[idx1] = -1
+                    nmatches -= 1
+    xy2 = np.asarray(xy_un2, f32).reshape(n2, 2)
+    for i1 in range(n1):
+        if m12[i1] >= 0:
+            prev[i1] = xy2[m12[i1]]
+    return nmatches, m12, prev
+
+
+def ref_search_for_initialization(xy_un1, octave1, angle1, desc1, prev_matched, xy_un2, octave2, angle2, desc2, cell_start,
+                                  cell_items, bounds, sf, nnratio=0.9, check_orientation=True, window=100):
+    r = _load_ref()
+    r.matchref_search_for_initialization.restype = C.c_int
+    n1, n2 = len(desc1), len(desc2)
+    kp1, kp2 = _kp7(xy_un1, angle1, octave1), _kp7(xy_un2, angle2, octave2)
+    prev = np.ascontiguousarray(prev_matched, f32).reshape(n1, 2).copy()
+    a = [np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8), np.ascontiguousarray(cell_start, np.int32),
+         np.ascontiguousarray(cell_items, np.int32), np.ascontiguousarray(bounds, f32), np.ascontiguousarray(sf, f32)]
+    out = np.full(n1, -1, np.int32)
+    p = lambda x: C.c_void_p(x.ctypes.data)
+    n = r.matchref_search_for_initialization(C.c_int(n1), p(kp1), p(a[0]), p(prev), C.c_int(n2), p(kp2), p(a[1]), p(a[2]), p(a[3]),
+                                             p(a[4]), p(a[5]), C.c_int(len(a[5])), C.c_float(nnratio), C.c_int(int(check_orientation)),
+                                             C.c_int(int(window)), p(out))
+    return int(n), out, prev

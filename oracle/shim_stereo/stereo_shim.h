@@ -6,7 +6,9 @@
 // UndistortKeyPoints / ComputeImageBounds (Frame.cc:230-245, :382-392, :404-434, :436-464), Frame::GetFeaturesInArea
 // (:327-380), ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) / ComputeThreeMaxima
 // (ORBmatcher.cc:1328-1470, :1601-1642) and ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) /
-// RadiusByViewingCos (ORBmatcher.cc:45-129, :131-137) and ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (ORBmatcher.cc:159-288),
+// RadiusByViewingCos (ORBmatcher.cc:45-129, :131-137), ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (ORBmatcher.cc:159-288),
+// ORBmatcher::SearchForInitialization (ORBmatcher.cc:405-520), ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th,
+// ORBdist) (ORBmatcher.cc:1472-1599) and MapPoint::GetMin/MaxDistanceInvariance / PredictScale(dist, Frame*) (MapPoint.cc:373-383, :402-417),
 // taken from where they lie at
 // build time, against this header: the handful of cv:: types those lines use (8U / 32F Mat views, convertTo, ones, scalar * Mat,
 // Mat - Mat, norm L1) and the members of Frame / ORBextractor / ORBmatcher they touch.  Written from scratch.
@@ -21,6 +23,8 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
+#include <set>
 #include <utility>
 #include <vector>
 
@@ -111,6 +115,14 @@ static inline Mat operator-(const Mat& a, const Mat& b) {       // 32F only
         for (int c = 0; c < a.cols; ++c) o.at<float>(r, c) = a.at<float>(r, c) - b.at<float>(r, c);
     return o;
 }
+// cv::norm(m) of a CV_32F matrix: NORM_L2, squares accumulated in double (OpenCV's normL2_32f returns the double sum, then
+// std::sqrt) -- used for the 3 x 1 vector PO (ORBmatcher.cc:1511); pinned against the real cv2.norm by tests/test_match_oracle.py
+static inline double norm(const Mat& a) {
+    double s = 0;
+    for (int r = 0; r < a.rows; ++r)
+        for (int c = 0; c < a.cols; ++c) { const double v = (double)a.at<float>(r, c); s += v * v; }
+    return std::sqrt(s);
+}
 static inline double norm(const Mat& a, const Mat& b, int type) {    // NORM_L1 of 32F matrices, accumulated in double
     (void)type;
     double s = 0;
@@ -196,16 +208,27 @@ namespace ORB_SLAM2 {
 class Frame;
 class KeyFrame;
 
-struct MapPoint {                     // the accessors and tracking fields ORBmatcher.cc:45-129, :1328-1470 touch
+struct MapPoint {                     // the accessors and tracking fields ORBmatcher.cc:45-129, :1328-1470, :1472-1599 touch
     cv::Mat mWorldPos, mDescriptor;
     int nObs;
     bool mbTrackInView, mbBad;        // include/MapPoint.h:92-97
     float mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos;
     int mnTrackScaleLevel;
+    float mfMinDistance, mfMaxDistance;   // include/MapPoint.h:140-141
+    std::mutex mMutexPos;
+    MapPoint() : nObs(0), mbTrackInView(false), mbBad(false), mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), mTrackViewCos(0),
+                 mnTrackScaleLevel(0), mfMinDistance(0), mfMaxDistance(0) {}
+    MapPoint(const MapPoint& o) : mWorldPos(o.mWorldPos), mDescriptor(o.mDescriptor), nObs(o.nObs), mbTrackInView(o.mbTrackInView),
+                                  mbBad(o.mbBad), mTrackProjX(o.mTrackProjX), mTrackProjY(o.mTrackProjY), mTrackProjXR(o.mTrackProjXR),
+                                  mTrackViewCos(o.mTrackViewCos), mnTrackScaleLevel(o.mnTrackScaleLevel),
+                                  mfMinDistance(o.mfMinDistance), mfMaxDistance(o.mfMaxDistance) {}
     bool isBad() { return mbBad; }
     cv::Mat GetWorldPos() { return mWorldPos; }
     cv::Mat GetDescriptor() { return mDescriptor; }
     int Observations() { return nObs; }
+    float GetMinDistanceInvariance();                       // the reference's own lines (MapPoint.cc:373-383, :402-417)
+    float GetMaxDistanceInvariance();
+    int PredictScale(const float& currentDist, Frame* pF);
 };
 
 class ORBmatcher {
@@ -218,6 +241,10 @@ public:
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
     int SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, const float th = 3);    // include/ORBmatcher.h
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
+    int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
+                                int windowSize = 10);                                             // include/ORBmatcher.h:69
+    int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th,
+                           const int ORBdist);                                                    // include/ORBmatcher.h:56
     float RadiusByViewingCos(const float& viewCos);
     void ComputeThreeMaxima(vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
     float mfNNratio;
@@ -253,6 +280,8 @@ public:
     ORBextractor *mpORBextractorLeft, *mpORBextractorRight;
     std::vector<float> mvScaleFactors, mvInvScaleFactors;
     float mbf, mb;
+    int mnScaleLevels;                  // include/Frame.h:182-184
+    float mfLogScaleFactor;
 };
 
 class KeyFrame {                        // what ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) reads (src/ORBmatcher.cc:159-288)

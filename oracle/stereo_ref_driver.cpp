@@ -242,3 +242,125 @@ extern "C" int matchref_search_by_bow(int nKF, const unsigned char* kf_desc, con
     for (int i = 0; i < nF; ++i) match[i] = out[i] ? (int)(out[i] - &mps[0]) : -1;
     return nmatches;
 }
+
+namespace {
+// the current frame's side shared by the two entries below: keypoint records, descriptors, grid, bounds
+void fill_frame(ORB_SLAM2::Frame& C, int nC, const float* kp_un, const unsigned char* desc, const int* cell_start,
+                const int* cell_items, const float* bounds, const float* sf, int nlevels) {
+    using namespace ORB_SLAM2;
+    C.N = nC;
+    C.mvKeysUn.resize(nC);
+    for (int i = 0; i < nC; ++i) {
+        const float* q = kp_un + 7 * i;
+        C.mvKeysUn[i].pt.x = q[0]; C.mvKeysUn[i].pt.y = q[1]; C.mvKeysUn[i].size = q[2]; C.mvKeysUn[i].angle = q[3];
+        C.mvKeysUn[i].response = q[4];
+        memcpy(&C.mvKeysUn[i].octave, q + 5, 4); memcpy(&C.mvKeysUn[i].class_id, q + 6, 4);
+    }
+    C.mvpMapPoints.assign(nC, (MapPoint*)0);
+    C.mDescriptors = cv::Mat(nC, 32, CV_8U, (void*)desc, 32);
+    C.mvScaleFactors.assign(sf, sf + nlevels);
+    C.mnScaleLevels = nlevels;
+    Frame::mnMinX = bounds[0]; Frame::mnMaxX = bounds[1]; Frame::mnMinY = bounds[2]; Frame::mnMaxY = bounds[3];
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(Frame::mnMaxX - Frame::mnMinX);
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(Frame::mnMaxY - Frame::mnMinY);
+    for (int gx = 0; gx < FRAME_GRID_COLS; ++gx)
+        for (int gy = 0; gy < FRAME_GRID_ROWS; ++gy) {
+            const int c = gx * FRAME_GRID_ROWS + gy;
+            C.mGrid[gx][gy].assign(cell_items + cell_start[c], cell_items + cell_start[c + 1]);
+        }
+}
+}  // namespace
+
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist)
+// (src/ORBmatcher.cc:1472-1599, called by Tracking::Relocalization, src/Tracking.cc:1452 / :1466, with ORBmatcher(0.9, true)),
+// the reference's own lines, with MapPoint::GetMin/MaxDistanceInvariance and PredictScale (src/MapPoint.cc:373-383, :402-417).
+// KeyFrame side: valid[i] = 0: no map point, 1: good, 2: isBad(), 3: in sAlreadyFound; world position, descriptor,
+// mfMinDistance / mfMaxDistance of the point, angle of the KeyFrame's keypoint.  Frame side as above; cur_held[i2] != 0:
+// CurrentFrame.mvpMapPoints[i2] is not NULL at entry.  new_match[i2] = index i of the KeyFrame point the call SET
+// CurrentFrame.mvpMapPoints[i2] to (and did not cull), else -1.  pred_level[i] / in_range[i] (may be NULL) receive what the
+// reference's own PredictScale and distance test say for point i with the frame's pose (what a caller of the C ABI stages).
+extern "C" int matchref_search_by_projection_kf(int nP, const unsigned char* valid, const float* world, const unsigned char* mp_desc,
+                                                const float* min_dist, const float* max_dist, const float* kf_angle,
+                                                const float* Tcw_cur, int nC, const float* kp_un, const unsigned char* desc,
+                                                const unsigned char* cur_held, const int* cell_start, const int* cell_items,
+                                                const float* bounds, const float* K4, const float* sf, int nlevels,
+                                                float log_scale_factor, float th, int orb_dist, int check_ori, int* new_match,
+                                                int* pred_level, unsigned char* in_range) {
+    using namespace ORB_SLAM2;
+    Frame C;
+    KeyFrame KF;
+    std::vector<MapPoint> mps(nP > 0 ? nP : 1), held(nC > 0 ? nC : 1);
+    std::set<MapPoint*> found;
+    KF.mvpMapPoints.assign(nP, (MapPoint*)0);
+    KF.mvKeysUn.resize(nP);
+    for (int i = 0; i < nP; ++i) {
+        KF.mvKeysUn[i].angle = kf_angle[i];
+        if (!valid[i]) continue;
+        mps[i].mWorldPos = cv::Mat(3, 1, CV_32F);
+        for (int k = 0; k < 3; ++k) mps[i].mWorldPos.at<float>(k, 0) = world[3 * i + k];
+        mps[i].mDescriptor = cv::Mat(1, 32, CV_8U, (void*)(mp_desc + 32 * (size_t)i), 32);
+        mps[i].mbBad = valid[i] == 2;
+        mps[i].mfMinDistance = min_dist[i];
+        mps[i].mfMaxDistance = max_dist[i];
+        KF.mvpMapPoints[i] = &mps[i];
+        if (valid[i] == 3) found.insert(&mps[i]);
+    }
+    fill_frame(C, nC, kp_un, desc, cell_start, cell_items, bounds, sf, nlevels);
+    C.mfLogScaleFactor = log_scale_factor;
+    for (int i = 0; i < nC; ++i) if (cur_held[i]) C.mvpMapPoints[i] = &held[i];
+    C.mTcw = cv::Mat(4, 4, CV_32F);
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) C.mTcw.at<float>(r, c) = Tcw_cur[4 * r + c];
+    Frame::fx = K4[0]; Frame::fy = K4[1]; Frame::cx = K4[2]; Frame::cy = K4[3];
+    if (pred_level && in_range) {
+        // what the caller of orbx_search_by_projection_kf stages per point (ORBmatcher.cc:1476-1478, :1510-1522), by the same lines' arithmetic
+        const cv::Mat Rcw = C.mTcw.rowRange(0, 3).colRange(0, 3);
+        const cv::Mat tcw = C.mTcw.rowRange(0, 3).col(3);
+        const cv::Mat Ow = -Rcw.t() * tcw;
+        for (int i = 0; i < nP; ++i) {
+            pred_level[i] = 0;
+            in_range[i] = 0;
+            if (!valid[i]) continue;
+            cv::Mat PO = mps[i].mWorldPos - Ow;
+            float dist3D = cv::norm(PO);
+            if (dist3D < mps[i].GetMinDistanceInvariance() || dist3D > mps[i].GetMaxDistanceInvariance()) continue;
+            in_range[i] = 1;
+            pred_level[i] = mps[i].PredictScale(dist3D, &C);
+        }
+    }
+    ORBmatcher matcher(0.9, check_ori != 0);                       // src/Tracking.cc:1437
+    const int nmatches = matcher.SearchByProjection(C, &KF, found, th, orb_dist);
+    for (int i = 0; i < nC; ++i) {
+        MapPoint* p = C.mvpMapPoints[i];
+        new_match[i] = (p && p >= &mps[0] && p < &mps[0] + nP) ? (int)(p - &mps[0]) : -1;
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:405-520,
+// called by Tracking::MonocularInitialization, src/Tracking.cc:600, with ORBmatcher(0.9, true) and windowSize 100), the reference's
+// own lines.  F1 side: octave / angle of its undistorted keypoints, descriptors, vbPrevMatched (n1 x 2, updated in place).
+// F2 side: keypoint records, descriptors, grid, bounds.  matches12[i1] = index in F2 or -1.
+extern "C" int matchref_search_for_initialization(int n1, const float* kp1_un, const unsigned char* desc1, float* prev_matched, int n2,
+                                                  const float* kp2_un, const unsigned char* desc2, const int* cell_start,
+                                                  const int* cell_items, const float* bounds, const float* sf, int nlevels,
+                                                  float nnratio, int check_ori, int window, int* matches12) {
+    using namespace ORB_SLAM2;
+    Frame F1, F2;
+    F1.N = n1;
+    F1.mvKeysUn.resize(n1);
+    for (int i = 0; i < n1; ++i) {
+        const float* q = kp1_un + 7 * i;
+        F1.mvKeysUn[i].pt.x = q[0]; F1.mvKeysUn[i].pt.y = q[1]; F1.mvKeysUn[i].size = q[2]; F1.mvKeysUn[i].angle = q[3];
+        F1.mvKeysUn[i].response = q[4];
+        memcpy(&F1.mvKeysUn[i].octave, q + 5, 4); memcpy(&F1.mvKeysUn[i].class_id, q + 6, 4);
+    }
+    F1.mDescriptors = cv::Mat(n1, 32, CV_8U, (void*)desc1, 32);
+    fill_frame(F2, n2, kp2_un, desc2, cell_start, cell_items, bounds, sf, nlevels);
+    std::vector<cv::Point2f> prev(n1);
+    for (int i = 0; i < n1; ++i) { prev[i].x = prev_matched[2 * i]; prev[i].y = prev_matched[2 * i + 1]; }
+    std::vector<int> m12;
+    ORBmatcher matcher(nnratio, check_ori != 0);
+    const int nmatches = matcher.SearchForInitialization(F1, F2, prev, m12, window);
+    for (int i = 0; i < n1; ++i) { matches12[i] = m12[i]; prev_matched[2 * i] = prev[i].x; prev_matched[2 * i + 1] = prev[i].y; }
+    return nmatches;
+}

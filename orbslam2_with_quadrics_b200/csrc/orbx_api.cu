@@ -362,7 +362,9 @@ int build_plan(orbx_handle* h, int w, int hgt, OrbxPlan* P, std::vector<OrbxTap>
     for (int l = 0; l < n; ++l) {
         OrbxLevel& L = P->lv[l];
         L.wcell_recip = 65536 / L.wCell + 1;
-        L.strip_ok = !P->fast_legacy && L.wCell <= 32 && L.hCell <= 40;
+        // latency-mode handles (max_batch <= 2) keep tall cells on the per-cell kernel: a single frame's tall strips would be
+        // one more 17-us launch behind the per-cell one on the side stream (640 x 480: 0.087 vs 0.072 ms per frame)
+        L.strip_ok = !P->fast_legacy && L.wCell <= 32 && L.hCell <= (h->cfg.max_batch <= 2 ? 32 : 40);
         L.strip_tall = L.strip_ok && L.hCell > 32;
         L.strip_nc = L.strip_ok ? std::max(1, std::min(P->fast_nc, 125 / L.wCell))
                                 : (P->fast_legacy ? P->fast_nc : (h->cfg.max_batch <= 2 ? 1 : 2));

@@ -130,3 +130,76 @@ def make_keyframe(rng, f_desc, f_angle, n_kf, flip_bits=12, angle_noise=6.0, ang
     kf_angle[wild] = rng.uniform(0, 360, int(wild.sum())).astype(f32)
     kf_angle = np.mod(kf_angle, f32(360.0)).astype(f32)
     return dict(kf_desc=kf_desc, kf_valid=kf_valid, kf_angle=kf_angle)
+
+
+def make_reloc_keyframe(rng, xy_un, cur_octave, cur_angle, desc, K4, Tcw_cur, n_points, sf, dup_frac=0.3, flip_bits=25,
+                        angle_noise=8.0, angle_outlier_frac=0.15, held_frac=0.3):
+    """A candidate KeyFrame for ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist)
+    (src/ORBmatcher.cc:1472-1599, Tracking::Relocalization): map points back-projected from current keypoints (with collisions,
+    points behind the camera / outside the image), distance-invariance ranges built so that the predicted level lands around the
+    keypoint's octave (some out of range), bad / already-found / missing points, and the keypoints the frame already holds."""
+    nC = len(desc)
+    fx, fy, cx, cy = [float(v) for v in K4]
+    Tc = np.asarray(Tcw_cur, np.float64).reshape(4, 4)
+    Rwc, twc = Tc[:3, :3].T, -Tc[:3, :3].T @ Tc[:3, 3]
+    tgt = rng.integers(0, nC, n_points)
+    ndup = int(dup_frac * n_points)
+    tgt[rng.integers(0, n_points, ndup)] = tgt[rng.integers(0, n_points, ndup)]
+    z = rng.uniform(0.8, 12.0, n_points)
+    px = xy_un[tgt, 0].astype(np.float64) + rng.normal(0, 2.0, n_points)
+    py = xy_un[tgt, 1].astype(np.float64) + rng.normal(0, 2.0, n_points)
+    Xc = np.stack([(px - cx) / fx * z, (py - cy) / fy * z, z], 1)
+    behind = rng.random(n_points) < 0.03
+    Xc[behind] *= -1.0
+    far = rng.random(n_points) < 0.03
+    Xc[far, 0] += 50.0 * z[far]
+    world = (Xc @ Rwc.T + twc).astype(f32)
+    dist = np.linalg.norm(world.astype(np.float64) - twc, axis=1)
+    # mfMaxDistance = dist * scale^(level + jitter): PredictScale = ceil(log(max / dist) / log(scale)) ~ the target level
+    lvl = np.clip(cur_octave[tgt] + rng.choice([-1, 0, 0, 0, 1], n_points), 0, len(sf) - 1)
+    jitter = rng.uniform(-0.9, 0.0, n_points)
+    max_dist = (dist * np.power(float(sf[1]), lvl + jitter)).astype(f32)
+    min_dist = (max_dist / f32(sf[-1])).astype(f32)
+    out_of_range = rng.random(n_points) < 0.05
+    max_dist[out_of_range] = (dist[out_of_range] * 0.5).astype(f32)
+    mp_desc = desc[tgt].copy()
+    flips = rng.integers(0, 256, (n_points, flip_bits))
+    for k in range(flip_bits):
+        on = rng.random(n_points) < 0.6
+        mp_desc[np.arange(n_points)[on], flips[on, k] // 8] ^= (1 << (flips[on, k] % 8)).astype(np.uint8)
+    unrelated = rng.random(n_points) < 0.1
+    mp_desc[unrelated] = rng.integers(0, 256, (int(unrelated.sum()), 32), dtype=np.uint8)
+    valid = rng.choice([0, 1, 1, 1, 1, 1, 1, 2, 3], n_points).astype(np.uint8)
+    kf_angle = (cur_angle[tgt] + rng.normal(0, angle_noise, n_points)).astype(f32)
+    wild = rng.random(n_points) < angle_outlier_frac
+    kf_angle[wild] = rng.uniform(0, 360, int(wild.sum())).astype(f32)
+    kf_angle = np.mod(kf_angle, f32(360.0)).astype(f32)
+    cur_held = (rng.random(nC) < held_frac).astype(np.uint8)
+    return dict(valid=valid, world=world, mp_desc=mp_desc, min_dist=min_dist, max_dist=max_dist, kf_angle=kf_angle, cur_held=cur_held)
+
+
+def make_initial_frame(rng, xy_un2, octave2, angle2, desc2, n1, flip_bits=10, shift=(6.0, -4.0), angle_noise=6.0,
+                       angle_outlier_frac=0.15, dup_frac=0.25):
+    """An initial frame F1 for ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:405-520): its level-0 keypoints are the
+    second frame's moved by a small image motion (so the 100-px window holds the true partner and many distractors), descriptors
+    with a few flipped bits, duplicates (two F1 keypoints competing for one F2 keypoint, the later one stealing it when it is
+    strictly closer), unrelated descriptors, keypoints of higher octaves (skipped) and angles with outliers."""
+    n2 = len(desc2)
+    lvl0 = np.nonzero(np.asarray(octave2) == 0)[0]
+    src = lvl0[rng.integers(0, len(lvl0), n1)] if len(lvl0) else rng.integers(0, n2, n1)
+    ndup = int(dup_frac * n1)
+    src[rng.integers(0, n1, ndup)] = src[rng.integers(0, n1, ndup)]
+    xy1 = (xy_un2[src] + np.asarray(shift, f32) + rng.normal(0, 3.0, (n1, 2))).astype(f32)
+    octave1 = np.where(rng.random(n1) < 0.8, 0, rng.integers(1, 4, n1)).astype(np.int32)
+    desc1 = desc2[src].copy()
+    flips = rng.integers(0, 256, (n1, flip_bits))
+    for k in range(flip_bits):
+        on = rng.random(n1) < 0.5
+        desc1[np.arange(n1)[on], flips[on, k] // 8] ^= (1 << (flips[on, k] % 8)).astype(np.uint8)
+    unrelated = rng.random(n1) < 0.1
+    desc1[unrelated] = rng.integers(0, 256, (int(unrelated.sum()), 32), dtype=np.uint8)
+    angle1 = (angle2[src] + rng.normal(0, angle_noise, n1)).astype(f32)
+    wild = rng.random(n1) < angle_outlier_frac
+    angle1[wild] = rng.uniform(0, 360, int(wild.sum())).astype(f32)
+    angle1 = np.mod(angle1, f32(360.0)).astype(f32)
+    return dict(xy_un1=xy1, octave1=octave1, angle1=angle1, desc1=desc1, prev_matched=xy1.copy())

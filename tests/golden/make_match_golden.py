@@ -109,6 +109,64 @@ def bow_key(case):
     return "bow/k%d/L%d/up%d/seed%d/n%d/ratio%g/ori%d" % (case[0], case[1], case[2], case[3], case[4], case[5], int(case[6]))
 
 
+# Relocalization's SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist): (seed, pKF->N, th, ORBdist, mbCheckOrientation)
+# -- th 10 / ORBdist 100, then th 3 / ORBdist 64 (src/Tracking.cc:1452, :1466)
+KF_CASES = [(1, 1200, 10.0, 100, True), (2, 1500, 3.0, 64, True), (3, 900, 10.0, 100, False), (4, 40, 3.0, 64, True),
+            (5, 2000, 10.0, 100, True)]
+
+
+def kf_scenario(cf, seed, n_points):
+    rng = np.random.default_rng(3000 + seed)
+    Tc = mc.pose(rng)
+    kf = mc.make_reloc_keyframe(rng, cf["xy_un"], cf["cur_octave"], cf["cur_angle"], cf["desc"], K_TUM1, Tc, n_points, cf["sf"])
+    return dict(**kf, Tcw_cur=Tc, xy_un=cf["xy_un"], cur_octave=cf["cur_octave"], cur_angle=cf["cur_angle"], desc=cf["desc"],
+                cell_start=cf["cell_start"], cell_items=cf["cell_items"], bounds=cf["bounds"], K4=K_TUM1, sf=cf["sf"])
+
+
+def kf_log_scale(cf):
+    return float(np.float32(np.log(np.float32(cf["sf"][1]))))      # Frame::mfLogScaleFactor = log(mfScaleFactor) (src/Frame.cc:69)
+
+
+def kf_digest(sc, n, m, in_range, pred):
+    ins = hashlib.sha256()
+    for k in ("valid", "world", "mp_desc", "min_dist", "max_dist", "kf_angle", "cur_held", "Tcw_cur"):
+        ins.update(np.ascontiguousarray(sc[k]).tobytes())
+    return {"nmatches": int(n), "set": int((m >= 0).sum()), "inputs_sha256": ins.hexdigest(),
+            "match_sha256": hashlib.sha256(np.ascontiguousarray(m, np.int32).tobytes()).hexdigest(),
+            "staged_sha256": hashlib.sha256(np.ascontiguousarray(in_range, np.uint8).tobytes()
+                                            + np.ascontiguousarray(pred, np.int32).tobytes()).hexdigest()}
+
+
+def kf_key(case):
+    return "kf/seed%d/n%d/th%g/dist%d/ori%d" % (case[0], case[1], case[2], case[3], int(case[4]))
+
+
+# MonocularInitialization's SearchForInitialization: (seed, F1.N, mfNNratio, mbCheckOrientation, windowSize) -- ORBmatcher(0.9, true),
+# window 100 (src/Tracking.cc:597-600)
+INIT_CASES = [(1, 1000, 0.9, True, 100), (2, 1000, 0.9, False, 100), (3, 600, 0.7, True, 50), (4, 30, 0.9, True, 100),
+              (5, 1000, 0.95, True, 200)]
+
+
+def init_scenario(cf, seed, n1):
+    rng = np.random.default_rng(4000 + seed)
+    f1 = mc.make_initial_frame(rng, cf["xy_un"], cf["cur_octave"], cf["cur_angle"], cf["desc"], n1)
+    return dict(**f1, xy_un2=cf["xy_un"], octave2=cf["cur_octave"], angle2=cf["cur_angle"], desc2=cf["desc"],
+                cell_start=cf["cell_start"], cell_items=cf["cell_items"], bounds=cf["bounds"])
+
+
+def init_digest(sc, n, m, prev):
+    ins = hashlib.sha256()
+    for k in ("xy_un1", "octave1", "angle1", "desc1", "prev_matched"):
+        ins.update(np.ascontiguousarray(sc[k]).tobytes())
+    return {"nmatches": int(n), "inputs_sha256": ins.hexdigest(),
+            "match_sha256": hashlib.sha256(np.ascontiguousarray(m, np.int32).tobytes()).hexdigest(),
+            "prev_sha256": hashlib.sha256(np.ascontiguousarray(prev, np.float32).tobytes()).hexdigest()}
+
+
+def init_key(case):
+    return "init/seed%d/n%d/ratio%g/ori%d/win%d" % (case[0], case[1], case[2], int(case[3]), case[4])
+
+
 def digest(sc, n, m):
     ins = hashlib.sha256()
     for k in ("world", "mp_desc", "mp_obs", "outlier", "last_octave", "last_angle", "Tcw_cur", "Tcw_last"):
@@ -144,4 +202,15 @@ if __name__ == "__main__":
         n, m = match_oracle.ref_search_by_bow(nnratio=case[5], check_orientation=case[6], **sc)
         out[bow_key(case)] = bow_digest(sc, n, m)
         print(bow_key(case), n, len(set(sc["f_fv_nodes"].tolist())))
+    for case in KF_CASES:
+        sc = kf_scenario(cf, *case[:2])
+        n, m, inr, pred = match_oracle.ref_search_by_projection_kf(log_scale_factor=kf_log_scale(cf), th=case[2], orb_dist=case[3],
+                                                                   check_orientation=case[4], **sc)
+        out[kf_key(case)] = kf_digest(sc, n, m, inr, pred)
+        print(kf_key(case), n, int(inr.sum()))
+    for case in INIT_CASES:
+        sc = init_scenario(cf, *case[:2])
+        n, m, prev = match_oracle.ref_search_for_initialization(sf=cf["sf"], nnratio=case[2], check_orientation=case[3], window=case[4], **sc)
+        out[init_key(case)] = init_digest(sc, n, m, prev)
+        print(init_key(case), n)
     json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "match_golden.json"), "w"), indent=1, sort_keys=True)

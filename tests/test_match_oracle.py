@@ -120,3 +120,75 @@ def test_search_by_bow_restatement_matches_reference_lines_and_golden(case, curr
     assert n1 == int((m1 >= 0).sum()) > 0.15 * case[4]          # every counted match holds its keypoint (claims are exclusive)
     kf_of = m1[m1 >= 0]
     assert np.all(sc["kf_valid"][kf_of] == 1)                   # features without a good map point never match (:196-202)
+
+
+# ----------------------------------------------------------------------------- Relocalization's SearchByProjection(Frame&, KeyFrame*) (:1472-1599)
+@pytest.mark.parametrize("case", mmg.KF_CASES)
+def test_keyframe_projection_restatement_matches_reference_lines_and_golden(case, current_frame):
+    sc = mmg.kf_scenario(current_frame, *case[:2])
+    lsf = mmg.kf_log_scale(current_frame)
+    inr, pred = match_oracle.kf_prepare(sc["valid"], sc["world"], sc["min_dist"], sc["max_dist"], sc["Tcw_cur"], lsf, current_frame["nlevels"])
+    args = {k: v for k, v in sc.items() if k not in ("min_dist", "max_dist")}
+    n1, m1 = match_oracle.search_by_projection_kf(in_range=inr, pred_level=pred, th=case[2], orb_dist=case[3], check_orientation=case[4], **args)
+    assert mmg.kf_digest(sc, n1, m1, inr, pred) == GOLD[mmg.kf_key(case)]
+    if match_oracle.ref_has("matchref_search_by_projection_kf"):
+        n2, m2, inr2, pred2 = match_oracle.ref_search_by_projection_kf(log_scale_factor=lsf, th=case[2], orb_dist=case[3],
+                                                                       check_orientation=case[4], **sc)
+        assert n1 == n2 and np.array_equal(m1, m2)
+        assert np.array_equal(inr, inr2) and np.array_equal(pred[inr2 > 0], pred2[inr2 > 0])
+    assert n1 == int((m1 >= 0).sum()) > 0.1 * case[1]           # every keypoint is taken at most once (any holder blocks, :1540-1541)
+    assert not np.any((m1 >= 0) & (sc["cur_held"] > 0))         # keypoints the frame already holds are never taken
+    assert np.all(sc["valid"][m1[m1 >= 0]] == 1)                # bad / already found / missing points never match (:1493-1495)
+    assert 0 < int(inr.sum()) < int((sc["valid"] > 0).sum())    # the distance-invariance test rejects some points
+    assert len(set(pred[inr > 0].tolist())) > 3                 # several predicted levels occur
+
+
+def test_shim_norm_matches_cv2():
+    """cv::norm of a 3 x 1 float vector as the stub evaluates it (sum of squares in double, sqrt) is cv2.norm bit for bit."""
+    import cv2
+    rng = np.random.default_rng(9)
+    for _ in range(3000):
+        v = (rng.standard_normal((3, 1)) * rng.choice([0.01, 1.0, 30.0])).astype(np.float32)
+        s = np.float64(0)
+        for k in range(3):
+            s += np.float64(v[k, 0]) * np.float64(v[k, 0])
+        assert np.sqrt(s) == cv2.norm(v)
+
+
+# ----------------------------------------------------------------------------- SearchForInitialization (:405-520)
+@pytest.mark.parametrize("case", mmg.INIT_CASES)
+def test_search_for_initialization_restatement_matches_reference_lines_and_golden(case, current_frame):
+    sc = mmg.init_scenario(current_frame, *case[:2])
+    n1, m1, p1 = match_oracle.search_for_initialization(nnratio=case[2], check_orientation=case[3], window=case[4], **sc)
+    assert mmg.init_digest(sc, n1, m1, p1) == GOLD[mmg.init_key(case)]
+    if match_oracle.ref_has("matchref_search_for_initialization"):
+        n2, m2, p2 = match_oracle.ref_search_for_initialization(sf=current_frame["sf"], nnratio=case[2], check_orientation=case[3],
+                                                                window=case[4], **sc)
+        assert n1 == n2 and np.array_equal(m1, m2) and np.array_equal(p1, p2)
+    assert n1 == int((m1 >= 0).sum()) > 0.1 * case[1]
+    assert np.all(sc["octave1"][m1 >= 0] == 0)                  # only level-0 keypoints of F1 are matched (:424-426)
+    taken = m1[m1 >= 0]
+    assert len(set(taken.tolist())) == len(taken)               # a second-frame keypoint has one owner (:471-475)
+
+
+def test_search_for_initialization_stealing_is_exercised(current_frame):
+    """A later F1 keypoint takes an F2 keypoint from an earlier one when it is strictly closer (:447-448, :471-478)."""
+    sc = mmg.init_scenario(current_frame, 1, 1000)
+    n, m, _ = match_oracle.search_for_initialization(nnratio=0.9, check_orientation=False, window=100, **sc)
+    # replay without the stealing rule: more F1 keypoints would keep a match
+    import oracle.match_oracle as mo
+    d1 = np.ascontiguousarray(sc["desc1"]).view(np.uint64).reshape(-1, 4)
+    d2 = np.ascontiguousarray(sc["desc2"]).view(np.uint64).reshape(-1, 4)
+    owners = {}
+    for i1 in np.nonzero(m >= 0)[0]:
+        owners[int(m[i1])] = int(i1)
+    stolen = 0
+    for i1 in range(len(m)):
+        if m[i1] >= 0 or sc["octave1"][i1] > 0:
+            continue
+        cands = mo.features_in_area(sc["prev_matched"][i1, 0], sc["prev_matched"][i1, 1], np.float32(100), 0, 0, sc["xy_un2"],
+                                    sc["octave2"], sc["cell_start"], sc["cell_items"], sc["bounds"])
+        ds = [(int(sum(bin(int(a ^ b)).count("1") for a, b in zip(d1[i1], d2[i2]))), i2) for i2 in cands]
+        if ds and min(ds)[0] <= mo.TH_LOW and min(ds)[1] in owners and owners[min(ds)[1]] > i1:
+            stolen += 1
+    assert stolen > 0
