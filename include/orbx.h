@@ -218,6 +218,60 @@ ORBX_API int orbx_search_local_points(orbx_handle* h, int nqueries, const orbx_l
 ORBX_API int orbx_search_local_points_device(orbx_handle* h, int nqueries, const orbx_local_points_query* queries, float th,
                                              float nnratio, int use_stereo);
 
+/* ---- ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist)
+ * (reference src/ORBmatcher.cc:1472-1599): the projection matcher of Tracking::Relocalization (src/Tracking.cc:1452 with th 10 /
+ * ORBdist 100, :1466 with th 3 / ORBdist 64, ORBmatcher(0.9, true)).  The frame side is the handle's device-resident state
+ * as for orbx_search_by_projection (no mvuRight test in this overload).  The KeyFrame side comes from the caller's map; the two
+ * scalar steps that go through the host's libm and the map's mutexes stay with the caller, who stages their result per point:
+ *   search[i]     = pMP && !pMP->isBad() && !sAlreadyFound.count(pMP) && dist3D within [GetMinDistanceInvariance(),
+ *                   GetMaxDistanceInvariance()] (:1491-1495, :1510-1518; dist3D = cv::norm(x3Dw - Ow), Ow = -Rcw.t()*tcw)
+ *   pred_level[i] = pMP->PredictScale(dist3D, &CurrentFrame) (:1520; read only where search[i] is set)
+ * Projection, image-bounds test, window search over levels pred_level-1 .. +1, "any holder blocks" (:1540-1541), the ORBdist
+ * test, rotation histogram and culling run on the device.
+ * Result (orbx_projection_result): match[i2] = index i of the KeyFrame point CurrentFrame.mvpMapPoints[i2] was SET to by this
+ * call and kept after the orientation check, -1 = left as it was; nmatches = the function's return value. */
+typedef struct orbx_keyframe_projection_query {
+    int cur_frame;             /* frame of this handle's last extract */
+    int n_points;              /* pKF->GetMapPointMatches().size() */
+    const uint8_t* search;     /* n: see above */
+    const float* world_pos;    /* n x 3: pMP->GetWorldPos() (ignored where search[i] is 0) */
+    const int32_t* pred_level; /* n */
+    const uint8_t* mp_desc;    /* n x 32: pMP->GetDescriptor() */
+    const float* kf_angle;     /* n: pKF->mvKeysUn[i].angle */
+    const int32_t* cur_held;   /* F.N: > 0 where CurrentFrame.mvpMapPoints[i2] is not NULL at entry; NULL = all NULL */
+    float Tcw_cur[16];         /* CurrentFrame.mTcw, row-major 4 x 4 */
+} orbx_keyframe_projection_query;
+ORBX_API int orbx_search_by_projection_kf(orbx_handle* h, int nqueries, const orbx_keyframe_projection_query* queries, const float* K4,
+                                          float th, int orb_dist, int check_orientation, orbx_projection_result* results);
+ORBX_API int orbx_search_by_projection_kf_device(orbx_handle* h, int nqueries, const orbx_keyframe_projection_query* queries,
+                                                 const float* K4, float th, int orb_dist, int check_orientation);
+
+/* ---- ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched, vector<int>& vnMatches12,
+ * int windowSize) (reference src/ORBmatcher.cc:405-520): the matcher of Tracking::MonocularInitialization (src/Tracking.cc:597-600,
+ * ORBmatcher(0.9, true), windowSize 100).  F2 (the current frame) is the handle's device-resident state: frame `cur_frame` of
+ * the last extract with its mvKeysUn / mGrid from orbx_undistort_grid.  F1 (mInitialFrame, which the caller keeps) comes as
+ * arrays over its undistorted keypoints.  The sequential rules of the reference loop -- a later F1 keypoint takes an F2
+ * keypoint from an earlier one when its distance is strictly smaller, and only candidates that survive that filter enter the
+ * ratio test -- are replayed in order on the device.
+ * Result: matches12[i1] = vnMatches12[i1] (index in F2 or -1), nmatches = the return value, prev_matched = vbPrevMatched as
+ * updated at :515-517.  Pinned host memory owned by the handle, valid until its next search call. */
+typedef struct orbx_initialization_query {
+    int cur_frame;             /* F2: frame of this handle's last extract */
+    int n1;                    /* F1.mvKeysUn.size() */
+    const int32_t* octave1;    /* n1: F1.mvKeysUn[i1].octave */
+    const float* angle1;       /* n1: F1.mvKeysUn[i1].angle */
+    const uint8_t* desc1;      /* n1 x 32: F1.mDescriptors */
+    const float* prev_matched; /* n1 x 2: vbPrevMatched at entry */
+} orbx_initialization_query;
+typedef struct orbx_initialization_result {
+    int n1;
+    int nmatches;
+    const int32_t* matches12;  /* n1 */
+    const float* prev_matched; /* n1 x 2 */
+} orbx_initialization_result;
+ORBX_API int orbx_search_for_initialization(orbx_handle* h, int nqueries, const orbx_initialization_query* queries, float nnratio,
+                                            int check_orientation, int window, orbx_initialization_result* results);
+
 /* ---- Frame::ComputeBoW (reference src/Frame.cc:395-402): DBoW2's TemplatedVocabulary::transform(features, BowVector&,
  * FeatureVector&, levelsup = 4) (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1126-1194, :1217-1259) with the ORB
  * vocabulary's settings -- TF-IDF weighting, L1 scoring -- on the descriptors the last extract left in HBM.

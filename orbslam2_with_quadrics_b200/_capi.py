@@ -26,6 +26,7 @@ SYMBOLS = [
     "orbx_extract_batch_color", "orbx_extract_device_color", "orbx_undistort_grid", "orbx_fast_stats",
     "orbx_search_by_projection", "orbx_search_by_projection_device", "orbx_search_by_projection_fetch",
     "orbx_search_local_points", "orbx_search_local_points_device",
+    "orbx_search_by_projection_kf", "orbx_search_by_projection_kf_device", "orbx_search_for_initialization",
     "orbx_search_by_bow", "orbx_search_by_bow_device", "orbx_vocabulary_create", "orbx_vocabulary_destroy", "orbx_compute_bow", "orbx_compute_bow_device",
     "orbx_bind_thread_to_device",
 ]
@@ -65,6 +66,21 @@ class OrbxLocalPointsQuery(C.Structure):
     _fields_ = [("cur_frame", C.c_int), ("n_points", C.c_int), ("in_view", C.c_void_p), ("proj_xy_xr", C.c_void_p),
                 ("scale_level", C.c_void_p), ("view_cos", C.c_void_p), ("mp_desc", C.c_void_p), ("mp_obs", C.c_void_p),
                 ("cur_obs", C.c_void_p)]
+
+
+class OrbxKeyframeProjectionQuery(C.Structure):
+    _fields_ = [("cur_frame", C.c_int), ("n_points", C.c_int), ("search", C.c_void_p), ("world_pos", C.c_void_p),
+                ("pred_level", C.c_void_p), ("mp_desc", C.c_void_p), ("kf_angle", C.c_void_p), ("cur_held", C.c_void_p),
+                ("Tcw_cur", C.c_float * 16)]
+
+
+class OrbxInitializationQuery(C.Structure):
+    _fields_ = [("cur_frame", C.c_int), ("n1", C.c_int), ("octave1", C.c_void_p), ("angle1", C.c_void_p), ("desc1", C.c_void_p),
+                ("prev_matched", C.c_void_p)]
+
+
+class OrbxInitializationResult(C.Structure):
+    _fields_ = [("n1", C.c_int), ("nmatches", C.c_int), ("matches12", C.c_void_p), ("prev_matched", C.c_void_p)]
 
 
 class OrbxBowResult(C.Structure):
@@ -145,6 +161,10 @@ def lib():
     L.orbx_search_by_projection_fetch.argtypes = [vp, i, C.POINTER(OrbxProjectionQuery), C.POINTER(OrbxProjectionResult)]
     L.orbx_search_local_points.argtypes = [vp, i, C.POINTER(OrbxLocalPointsQuery), f, f, i, C.POINTER(OrbxProjectionResult)]
     L.orbx_search_local_points_device.argtypes = [vp, i, C.POINTER(OrbxLocalPointsQuery), f, f, i]
+    L.orbx_search_by_projection_kf.argtypes = [vp, i, C.POINTER(OrbxKeyframeProjectionQuery), C.POINTER(C.c_float), f, i, i,
+                                               C.POINTER(OrbxProjectionResult)]
+    L.orbx_search_by_projection_kf_device.argtypes = [vp, i, C.POINTER(OrbxKeyframeProjectionQuery), C.POINTER(C.c_float), f, i, i]
+    L.orbx_search_for_initialization.argtypes = [vp, i, C.POINTER(OrbxInitializationQuery), f, i, i, C.POINTER(OrbxInitializationResult)]
     L.orbx_search_by_bow.argtypes = [vp, i, C.POINTER(OrbxBowMatchQuery), f, i, C.POINTER(OrbxProjectionResult)]
     L.orbx_search_by_bow_device.argtypes = [vp, i, C.POINTER(OrbxBowMatchQuery), f, i]
     L.orbx_vocabulary_create.argtypes = [i, i, i, vp, vp, vp, vp, vp, C.POINTER(vp)]

@@ -1303,8 +1303,10 @@ struct SpHostQuery {
     const float *Tc, *Tl;      // LastFrame variant: the two poses
 };
 
-int sp_enqueue(orbx_handle* h, int local, int nq, const SpHostQuery* q, const float* K4, float mbf, float mb, float th, float nnratio,
-               int mono, int check_orientation, int use_stereo) {
+// mode 0: LastFrame variant, 1: local-map variant, 2: KeyFrame variant (Relocalization, match_th = ORBdist)
+int sp_enqueue(orbx_handle* h, int mode, int nq, const SpHostQuery* q, const float* K4, float mbf, float mb, float th, float nnratio,
+               int mono, int check_orientation, int use_stereo, int match_th = 0) {
+    const bool local = mode == 1, held = mode != 0;                      // held: cur_obs names what the frame's keypoints hold at entry
     if (!h || !q || nq < 1 || nq > h->cfg.max_batch || !h->have_plan) return ORBX_ERR_BAD_ARGS;
     if (!h->d_un_xy || h->un_gen != h->gen) return ORBX_ERR_BAD_ARGS;          // orbx_undistort_grid has to run first, for THIS extraction (mvKeysUn, mGrid)
     if (use_stereo && (!h->d_st_u || h->st_gen != h->gen)) return ORBX_ERR_BAD_ARGS;   // mvuRight comes from orbx_stereo_match on this handle, same extraction
@@ -1314,13 +1316,15 @@ int sp_enqueue(orbx_handle* h, int local, int nq, const SpHostQuery* q, const fl
     int cap = 1;
     for (int i = 0; i < nq; ++i) {
         if (q[i].cur_frame < 0 || q[i].cur_frame >= h->last_n || q[i].n < 0) return ORBX_ERR_BAD_ARGS;
-        if (q[i].n && (!q[i].w3 || !q[i].desc || !q[i].obs || !q[i].oct || !q[i].ang)) return ORBX_ERR_BAD_ARGS;
+        if (q[i].n && (!q[i].w3 || !q[i].desc || (!q[i].obs && mode != 2) || !q[i].oct || !q[i].ang)) return ORBX_ERR_BAD_ARGS;
+        if (mode == 2 && q[i].n && (!q[i].flag || !q[i].Tc)) return ORBX_ERR_BAD_ARGS;
         if (q[i].n > cap) cap = q[i].n;
         // A level is validated only for the points the kernels will process: the reference leaves mnTrackScaleLevel
         // uninitialised until Frame::isInFrustum accepts a point (src/Frame.cc:321, src/MapPoint.cc:32-73), so a skipped
         // point may legitimately carry garbage there; it is staged as level 0 below.
         for (int k = 0; k < q[i].n; ++k) {
-            const bool processed = local ? !(q[i].flag && !q[i].flag[k]) : (!(q[i].flag && q[i].flag[k]) && q[i].obs[k] >= 0);
+            const bool processed = mode == 1 ? !(q[i].flag && !q[i].flag[k])
+                                 : mode == 2 ? (q[i].flag && q[i].flag[k]) : (!(q[i].flag && q[i].flag[k]) && q[i].obs[k] >= 0);
             if (processed && (q[i].oct[k] < 0 || q[i].oct[k] >= P.nlevels)) return ORBX_ERR_BAD_ARGS;
         }
     }
@@ -1337,10 +1341,10 @@ int sp_enqueue(orbx_handle* h, int local, int nq, const SpHostQuery* q, const fl
     // device only, behind it: [candidate counts nq*cap][candidate lists nq*cap*32 u32]
     const size_t o_desc = (size_t)nq * qbytes, o_world = o_desc + (size_t)nq * cap * 32, o_obs = o_world + (size_t)nq * cap * 12,
                  o_oct = o_obs + (size_t)nq * cap * 4, o_ang = o_oct + (size_t)nq * cap * 4, o_cur = o_ang + (size_t)nq * cap * 4,
-                 staged = o_cur + (local ? (size_t)nq * kpf * 4 : 0), o_cnt = (staged + 15) & ~(size_t)15,
+                 staged = o_cur + (held ? (size_t)nq * kpf * 4 : 0), o_cnt = (staged + 15) & ~(size_t)15,
                  o_list = o_cnt + (size_t)nq * cap * 4, total = o_list + (size_t)nq * cap * 32 * 4;
     cudaStream_t st = h->stream;
-    if (local)                                                       // F.N of the frames (cur_obs is sized by it), whatever was fetched so far
+    if (held)                                                        // F.N of the frames (cur_obs is sized by it), whatever was fetched so far
         CK(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int) * h->counters_count(), cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));                                // the staging of a previous call is free
     if (total > h->sp_bytes) {
@@ -1359,7 +1363,12 @@ int sp_enqueue(orbx_handle* h, int local, int nq, const SpHostQuery* q, const fl
         const SpHostQuery& Q = q[i];
         int fwd = 0, bwd = 0;
         float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
-        if (!local) {
+        if (mode == 2) {                                             // only the current pose is needed (:1476-1477)
+            const float* Tc = Q.Tc;
+            const float Rc[9] = {Tc[0], Tc[1], Tc[2], Tc[4], Tc[5], Tc[6], Tc[8], Tc[9], Tc[10]};
+            memcpy(R, Rc, sizeof R);
+            t[0] = Tc[3]; t[1] = Tc[7]; t[2] = Tc[11];
+        } else if (!local) {
             // twc = -Rcw.t() * tcw (general gemm path: double products and sum), tlc = Rlw * twc + tlw (the 3x3 path: float
             // products and sums, "+ C" in double), bForward / bBackward (:1337-1349)
             const float* Tc = Q.Tc;
@@ -1388,13 +1397,15 @@ int sp_enqueue(orbx_handle* h, int local, int nq, const SpHostQuery* q, const fl
             int* obs = reinterpret_cast<int*>(h->h_sp + o_obs) + b;
             if (local)                                               // mbTrackInView && !isBad (:54-58)
                 for (size_t k = 0; k < n; ++k) obs[k] = (Q.flag && !Q.flag[k]) ? -1 : (Q.obs[k] < 0 ? 0 : Q.obs[k]);
+            else if (mode == 2)                                      // a good, not yet found point in range (:1491-1495, :1516-1518); every match claims (:1540)
+                for (size_t k = 0; k < n; ++k) obs[k] = Q.flag[k] ? 1 : -1;
             else                                                     // pMP && !mvbOutlier (:1356-1360)
                 for (size_t k = 0; k < n; ++k) obs[k] = (Q.flag && Q.flag[k]) ? -1 : Q.obs[k];
             int* oct = reinterpret_cast<int*>(h->h_sp + o_oct) + b;
             for (size_t k = 0; k < n; ++k) oct[k] = (obs[k] < 0 || Q.oct[k] < 0 || Q.oct[k] >= P.nlevels) ? 0 : Q.oct[k];
             memcpy(h->h_sp + o_ang + b * 4, Q.ang, n * 4);
         }
-        if (local) {
+        if (held) {
             int* co = reinterpret_cast<int*>(h->h_sp + o_cur) + (size_t)i * kpf;
             if (Q.cur_obs) {
                 int N = 0;                                           // CurrentFrame.N as of the last fetch of the counters
@@ -1408,12 +1419,12 @@ int sp_enqueue(orbx_handle* h, int local, int nq, const SpHostQuery* q, const fl
     }
     const float K1[4] = {1.f, 1.f, 0.f, 0.f};
     CK(h, cudaMemcpyAsync(h->d_sp, h->h_sp, staged, cudaMemcpyHostToDevice, st));
-    CK(h, orbx::launch_search_projection(h->d_plan, P, local, nq, h->d_sp, K4 ? K4 : K1, h->un_bounds, mbf, th, nnratio, check_orientation,
-                                         cap, list_cap, reinterpret_cast<const float*>(h->d_sp + o_world), h->d_sp + o_desc,
+    CK(h, orbx::launch_search_projection(h->d_plan, P, mode, nq, h->d_sp, K4 ? K4 : K1, h->un_bounds, mbf, th, nnratio, check_orientation,
+                                         match_th, cap, list_cap, reinterpret_cast<const float*>(h->d_sp + o_world), h->d_sp + o_desc,
                                          reinterpret_cast<const int*>(h->d_sp + o_obs), reinterpret_cast<const int*>(h->d_sp + o_oct),
                                          reinterpret_cast<const float*>(h->d_sp + o_ang), h->d_out_kp, h->d_out_desc, h->d_kept_counts(),
                                          h->d_un_xy, h->d_un_start, h->d_un_items, use_stereo ? h->d_st_u : nullptr,
-                                         local ? reinterpret_cast<const int*>(h->d_sp + o_cur) : nullptr,
+                                         held ? reinterpret_cast<const int*>(h->d_sp + o_cur) : nullptr,
                                          reinterpret_cast<uint32_t*>(h->d_sp + o_list), reinterpret_cast<int*>(h->d_sp + o_cnt), h->d_sp_out,
                                          h->d_sp_out + (size_t)h->cfg.max_batch * P.kept_per_frame, st));
     h->launches += 2;
@@ -1506,6 +1517,99 @@ int orbx_search_local_points(orbx_handle* h, int nqueries, const orbx_local_poin
     std::vector<int> frames(nqueries);
     for (int i = 0; i < nqueries; ++i) frames[i] = queries[i].cur_frame;
     return sp_fetch(h, nqueries, frames.data(), results);
+}
+
+// ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:1472-1599 (Tracking::Relocalization)
+int orbx_search_by_projection_kf_device(orbx_handle* h, int nqueries, const orbx_keyframe_projection_query* queries, const float* K4,
+                                        float th, int orb_dist, int check_orientation) {
+    if (!queries || nqueries < 1 || !K4 || orb_dist < 0 || orb_dist > 255) return ORBX_ERR_BAD_ARGS;     // bestDist starts at 256 (:1532)
+    std::vector<SpHostQuery> q(nqueries);
+    for (int i = 0; i < nqueries; ++i) {
+        SpHostQuery& o = q[i];
+        o.cur_frame = queries[i].cur_frame; o.n = queries[i].n_points; o.w3 = queries[i].world_pos; o.desc = queries[i].mp_desc;
+        o.obs = nullptr; o.flag = queries[i].search; o.oct = queries[i].pred_level; o.ang = queries[i].kf_angle;
+        o.cur_obs = queries[i].cur_held; o.Tc = queries[i].Tcw_cur; o.Tl = nullptr;
+    }
+    return sp_enqueue(h, 2, nqueries, q.data(), K4, 0.f, 0.f, th, 0.f, 1, check_orientation, 0, orb_dist);
+}
+
+int orbx_search_by_projection_kf(orbx_handle* h, int nqueries, const orbx_keyframe_projection_query* queries, const float* K4, float th,
+                                 int orb_dist, int check_orientation, orbx_projection_result* results) {
+    if (!results) return ORBX_ERR_BAD_ARGS;
+    const int rc = orbx_search_by_projection_kf_device(h, nqueries, queries, K4, th, orb_dist, check_orientation);
+    if (rc != ORBX_OK) return rc;
+    std::vector<int> frames(nqueries);
+    for (int i = 0; i < nqueries; ++i) frames[i] = queries[i].cur_frame;
+    return sp_fetch(h, nqueries, frames.data(), results);
+}
+
+// ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize), src/ORBmatcher.cc:405-520
+// (Tracking::MonocularInitialization, src/Tracking.cc:600)
+int orbx_search_for_initialization(orbx_handle* h, int nq, const orbx_initialization_query* q, float nnratio, int check_orientation,
+                                   int window, orbx_initialization_result* results) {
+    if (!h || !q || !results || nq < 1 || nq > h->cfg.max_batch || !h->have_plan || window < 0) return ORBX_ERR_BAD_ARGS;
+    if (!h->d_un_xy || h->un_gen != h->gen) return ORBX_ERR_BAD_ARGS;          // orbx_undistort_grid has to run first, for THIS extraction (F2's mvKeysUn, mGrid)
+    const OrbxPlan& P = h->plan;
+    const size_t kpf = (size_t)P.kept_per_frame;
+    if (kpf > 65535) return ORBX_ERR_BAD_ARGS;
+    int cap = 1;
+    for (int i = 0; i < nq; ++i) {
+        if (q[i].cur_frame < 0 || q[i].cur_frame >= h->last_n || q[i].n1 < 0) return ORBX_ERR_BAD_ARGS;
+        if (q[i].n1 && (!q[i].octave1 || !q[i].angle1 || !q[i].desc1 || !q[i].prev_matched)) return ORBX_ERR_BAD_ARGS;
+        if (q[i].n1 > cap) cap = q[i].n1;
+    }
+    cap = (cap + 3) & ~3;
+    if (kpf * 2 * sizeof(int) > 200 * 1024) return ORBX_ERR_BAD_ARGS;
+    CK(h, cudaSetDevice(h->cfg.device));
+    int lc = 96;                                                     // entries of a keypoint's candidate list (test knob: small values
+    if (const char* e = getenv("ORBX_INIT_LIST_CAP")) {              // force the window re-scan of the resolve kernel)
+        const int v = atoi(e);
+        if (v >= 1 && v <= 4096) lc = v;
+    }
+    // layout: [queries nq*8][desc1 nq*cap*32][prev nq*cap*8][octave nq*cap*4][angle nq*cap*4]            (staged, host -> device)
+    //         [counts nq*cap*4][lists nq*cap*lc*4][bins nq*cap]                                          (device only)
+    //         [matches12 nq*cap*4][prev out nq*cap*8][nmatches nq*4]                                     (device -> host)
+    const size_t n = (size_t)nq * cap;
+    const size_t o_desc = ((size_t)nq * 8 + 15) & ~(size_t)15, o_prev = o_desc + n * 32, o_oct = o_prev + n * 8, o_ang = o_oct + n * 4,
+                 staged = o_ang + n * 4, o_cnt = (staged + 15) & ~(size_t)15, o_list = o_cnt + n * 4, o_bin = o_list + n * lc * 4,
+                 o_m12 = (o_bin + n + 15) & ~(size_t)15, o_pout = o_m12 + n * 4, o_nm = o_pout + n * 8, total = o_nm + (size_t)nq * 4;
+    cudaStream_t st = h->stream;
+    CK(h, cudaStreamSynchronize(st));                                // the staging of a previous call is free
+    if (total > h->sp_bytes) {
+        cudaFree(h->d_sp); cudaFreeHost(h->h_sp); h->d_sp = h->h_sp = 0; h->sp_bytes = 0;
+        CK(h, cudaMalloc(&h->d_sp, total));
+        CK(h, cudaMallocHost(&h->h_sp, total));
+        h->sp_bytes = total;
+    }
+    for (int i = 0; i < nq; ++i) {
+        int* qi = reinterpret_cast<int*>(h->h_sp) + 2 * i;
+        qi[0] = q[i].n1;
+        qi[1] = q[i].cur_frame;
+        const size_t m = (size_t)q[i].n1, b = (size_t)i * cap;
+        if (!m) continue;
+        memcpy(h->h_sp + o_desc + b * 32, q[i].desc1, m * 32);
+        memcpy(h->h_sp + o_prev + b * 8, q[i].prev_matched, m * 8);
+        memcpy(h->h_sp + o_oct + b * 4, q[i].octave1, m * 4);
+        memcpy(h->h_sp + o_ang + b * 4, q[i].angle1, m * 4);
+    }
+    CK(h, cudaMemcpyAsync(h->d_sp, h->h_sp, staged, cudaMemcpyHostToDevice, st));
+    CK(h, orbx::launch_search_init(h->d_plan, P, nq, h->d_sp, h->un_bounds, (float)window, nnratio, check_orientation, cap, lc,
+                                   reinterpret_cast<const float*>(h->d_sp + o_prev), h->d_sp + o_desc,
+                                   reinterpret_cast<const int*>(h->d_sp + o_oct), reinterpret_cast<const float*>(h->d_sp + o_ang),
+                                   h->d_out_kp, h->d_out_desc, h->d_kept_counts(), h->d_un_xy, h->d_un_start, h->d_un_items,
+                                   reinterpret_cast<uint32_t*>(h->d_sp + o_list), reinterpret_cast<int*>(h->d_sp + o_cnt), h->d_sp + o_bin,
+                                   reinterpret_cast<int*>(h->d_sp + o_m12), reinterpret_cast<float*>(h->d_sp + o_pout),
+                                   reinterpret_cast<int*>(h->d_sp + o_nm), st));
+    h->launches += 2;
+    CK(h, cudaMemcpyAsync(h->h_sp + o_m12, h->d_sp + o_m12, total - o_m12, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    for (int i = 0; i < nq; ++i) {
+        results[i].n1 = q[i].n1;
+        results[i].nmatches = reinterpret_cast<const int*>(h->h_sp + o_nm)[i];
+        results[i].matches12 = reinterpret_cast<const int32_t*>(h->h_sp + o_m12) + (size_t)i * cap;
+        results[i].prev_matched = reinterpret_cast<const float*>(h->h_sp + o_pout) + (size_t)i * cap * 2;
+    }
+    return ORBX_OK;
 }
 
 // ---- Frame::ComputeBoW: the vocabulary lives in HBM, independent of any handle.

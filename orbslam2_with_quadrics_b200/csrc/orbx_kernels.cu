@@ -2270,6 +2270,8 @@ struct SpParams {
     float nnratio;                        // ORBmatcher::mfNNratio (the local-points variant)
     int check_ori, cap, use_stereo;
     int list_th;                          // largest distance a candidate-list entry may have
+    int match_th;                         // projection variants: best distance that still matches (TH_HIGH, :1425; ORBdist, :1555)
+    int check_z;                          // 1: points behind the camera are skipped (:1370-1371); the KeyFrame variant has no such test
 };
 struct SpQuery {
     float R[9], t[3];                     // Rcw, tcw of the CURRENT frame
@@ -2315,7 +2317,8 @@ struct SpWin {
     int minL, maxL;
 };
 
-// LastFrame variant (src/ORBmatcher.cc:1362-1393): project the map point with the current pose.  W = world positions.
+// LastFrame variant (src/ORBmatcher.cc:1362-1393) and KeyFrame variant (:1497-1526, fwd = bwd = 0, LO = the level
+// MapPoint::PredictScale gave the caller): project the map point with the current pose.  W = world positions.
 __device__ __forceinline__ bool sp_project(const OrbxPlan* __restrict__ plan, const SpQuery& q, const SpParams& P,
                                            const float* __restrict__ W, const int* __restrict__ LO, int i, SpWin& w) {
     const float wx = W[3 * i], wy = W[3 * i + 1], wz = W[3 * i + 2];
@@ -2330,7 +2333,7 @@ __device__ __forceinline__ bool sp_project(const OrbxPlan* __restrict__ plan, co
     w.u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, c3[0]), invzc), P.cx);                // (:1373-1374)
     w.v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, c3[1]), invzc), P.cy);
     // written so that NaN fails (the reference would index the grid with an undefined int cast)
-    if (!(!(invzc < 0.f) && w.u >= P.min_x && w.u <= P.max_x && w.v >= P.min_y && w.v <= P.max_y)) return false;
+    if (!(!(P.check_z && invzc < 0.f) && w.u >= P.min_x && w.u <= P.max_x && w.v >= P.min_y && w.v <= P.max_y)) return false;
     const int lo = LO[i];
     w.radius = __fmul_rn(P.th, plan->lv[lo].scale);                                 // (:1384)
     w.minL = q.fwd ? lo : q.bwd ? 0 : lo - 1;                                       // (:1388-1393)
@@ -2361,8 +2364,11 @@ __device__ __forceinline__ bool sp_track_window(const OrbxPlan* __restrict__ pla
 // when nothing qualifies, and *second receives the runner-up.
 //   s_claim != nullptr : candidates claimed by an earlier point with observations are skipped (:96-98, :1401-1403);
 //   buf != nullptr     : every candidate with distance <= P.list_th is appended to buf (first `lc` of them), *total counts them.
+//   s_dist != nullptr  : SearchForInitialization's rule -- a candidate is skipped while vMatchedDistance <= distance (:447-448);
+//                        s_dist is indexed by CSR position.
 __device__ __forceinline__ unsigned sp_window(const SpParams& P, const SpFrame& F, const SpWin& w, const uint4* __restrict__ QD, int i,
-                                              int lane, const int* s_claim, unsigned* buf, int lc, int* total, unsigned* second) {
+                                              int lane, const int* s_claim, unsigned* buf, int lc, int* total, unsigned* second,
+                                              const int* s_dist = nullptr) {
     const float u = w.u, v = w.v, radius = w.radius;
     const int c0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, P.min_x), radius), P.winv)));
     const int c1 = min(UG_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, P.min_x), radius), P.winv)));
@@ -2395,6 +2401,7 @@ __device__ __forceinline__ unsigned sp_window(const SpParams& P, const SpFrame& 
                     const unsigned dist = __popc(qa.x ^ da.x) + __popc(qa.y ^ da.y) + __popc(qa.z ^ da.z) + __popc(qa.w ^ da.w) +
                                           __popc(qc.x ^ dc.x) + __popc(qc.y ^ dc.y) + __popc(qc.z ^ dc.z) + __popc(qc.w ^ dc.w);
                     key = (dist << 16) | (unsigned)p;
+                    if (s_dist && s_dist[p] <= (int)dist) key = 0xffffffffu;
                 }
             }
             best2 = min(best2, max(best, key));
@@ -2500,7 +2507,7 @@ search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __res
     const float* LA = last_angle + qb;
     const uint32_t* CL = cand_list + qb * (size_t)lc;
     const int* CC = cand_count + qb;
-    const int* CO = LOCAL ? cur_obs + (size_t)blockIdx.x * kpf : nullptr;
+    const int* CO = cur_obs ? cur_obs + (size_t)blockIdx.x * kpf : nullptr;     // what the frame's keypoints hold at entry (local-map and KeyFrame variants)
     const SpFrame F = sp_frame(plan, P, f, kp, desc, xy_un, cell_start, cell_items, u_right);
     const float* K0 = F.K0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -2511,7 +2518,7 @@ search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __res
     int over = 0;
     for (int i = threadIdx.x; i < nL; i += blockDim.x) { s_match[i] = -1; over += CC[i] > lc; }
     if (over) atomicAdd(&s_nover, over);
-    for (int k = threadIdx.x; k < kpf; k += blockDim.x) s_claim[k] = (LOCAL && k < N && CO[k] > 0) ? -1 : INT_MAX;   // (:96-98)
+    for (int k = threadIdx.x; k < kpf; k += blockDim.x) s_claim[k] = (CO && k < N && CO[k] > 0) ? -1 : INT_MAX;   // (:96-98, :1540-1541)
     __syncthreads();
     const int nover = s_nover;
 
@@ -2525,7 +2532,7 @@ search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __res
                 for (int j = 0; j < c; ++j) {
                     const unsigned e = CL[(size_t)i * lc + j];
                     const int k = (int)(e & 0xffffu);
-                    if (!(s_claim[k] < i)) { newm = (e >> 16) <= SP_TH_HIGH ? k : -1; break; }
+                    if (!(s_claim[k] < i)) { newm = (e >> 16) <= (unsigned)P.match_th ? k : -1; break; }
                 }
             } else {
                 unsigned e1 = 0xffffffffu, e2 = 0xffffffffu;
@@ -2554,7 +2561,7 @@ search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __res
                 int newm = -1;
                 if (best != 0xffffffffu) {
                     const int k1 = F.IT[best & 0xffffu];
-                    if (!LOCAL) newm = (best >> 16) <= SP_TH_HIGH ? k1 : -1;                   // (:1425)
+                    if (!LOCAL) newm = (best >> 16) <= (unsigned)P.match_th ? k1 : -1;         // (:1425, :1555)
                     else {
                         // no runner-up: bestDist2 stays 256 and bestLevel2 -1 (:77-81)
                         const unsigned d2 = second == 0xffffffffu ? 256u : (second >> 16);
@@ -2570,7 +2577,7 @@ search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __res
         __syncthreads();
         if (!changed) break;
         if (threadIdx.x == 0) s_changed = 0;
-        for (int k = threadIdx.x; k < kpf; k += blockDim.x) s_claim[k] = (LOCAL && k < N && CO[k] > 0) ? -1 : INT_MAX;
+        for (int k = threadIdx.x; k < kpf; k += blockDim.x) s_claim[k] = (CO && k < N && CO[k] > 0) ? -1 : INT_MAX;
         __syncthreads();
         for (int i = threadIdx.x; i < nL; i += blockDim.x) {
             const int m = s_match[i];
@@ -2629,6 +2636,169 @@ search_projection_kernel(const OrbxPlan* __restrict__ plan, const SpQuery* __res
         stats_out[2 * blockIdx.x] = s_nm - s_ncull;
         stats_out[2 * blockIdx.x + 1] = rounds;
     }
+}
+
+// =====================================================================================
+// ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:405-520),
+// the matcher of Tracking::MonocularInitialization (src/Tracking.cc:600).  F2 is the handle's device-resident frame
+// (keypoints, descriptors, mvKeysUn / mGrid from orbx_undistort_grid), F1 -- the initial frame the caller keeps -- comes
+// staged: octave, angle and descriptor of its undistorted keypoints and vbPrevMatched.
+//
+// The reference loop over F1's level-0 keypoints is sequential in a stronger way than the projection matchers: a later
+// keypoint STEALS an F2 keypoint from an earlier one when its distance is strictly smaller (vMatchedDistance, :447-448,
+// :471-478), and the ratio test only sees the candidates that survive that filter.  So:
+//   init_list_kernel    state-free, GPU-wide, a warp per F1 keypoint: every candidate of its window (Frame::GetFeaturesInArea
+//                       at level 0, :428) with its Hamming distance, in the reference's visiting order, as distance << 16 |
+//                       CSR position;
+//   init_resolve_kernel one warp per query replays the loop in order against vMatchedDistance / vnMatches21 in shared memory
+//                       (indexed by CSR position): per keypoint one or two 32-entry list chunks, no descriptor is touched
+//                       again; the next keypoint's chunk is in flight while the current one is decided.  Lists that did not
+//                       fit are re-scanned from the grid.  Then rotation histogram, three maxima, culling (:489-512) and
+//                       the vbPrevMatched update (:515-517).
+// =====================================================================================
+struct InitQuery {
+    int n1, frame;
+};
+#define SP_TH_LOW 50                      // ORBmatcher::TH_LOW (src/ORBmatcher.cc:38)
+
+__global__ void __launch_bounds__(SP_LIST_WARPS * 32)
+init_list_kernel(const OrbxPlan* __restrict__ plan, const InitQuery* __restrict__ queries, SpParams P, int nq, int lc,
+                 const float* __restrict__ prev, const uint4* __restrict__ desc1, const int* __restrict__ octave1,
+                 const float* __restrict__ kp, const uint8_t* __restrict__ desc, const float* __restrict__ xy_un,
+                 const int* __restrict__ cell_start, const int* __restrict__ cell_items, uint32_t* __restrict__ cand_list,
+                 int* __restrict__ cand_count) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long slot = (long long)blockIdx.x * SP_LIST_WARPS + warp;
+    if (slot >= (long long)nq * P.cap) return;
+    const int qi = (int)(slot / P.cap), i = (int)(slot % P.cap);
+    const InitQuery q = queries[qi];
+    if (i >= q.n1) return;
+    const size_t qb = (size_t)qi * P.cap;
+    int total = 0;
+    if (octave1[qb + i] <= 0) {                                           // (:424-426) level1 > 0: continue
+        const SpFrame F = sp_frame(plan, P, q.frame, kp, desc, xy_un, cell_start, cell_items, nullptr);
+        SpWin w;
+        w.u = prev[2 * (qb + i)];
+        w.v = prev[2 * (qb + i) + 1];
+        w.radius = P.th;                                                  // windowSize, converted to float at the call (:428)
+        w.ur = 0.f;
+        w.minL = w.maxL = octave1[qb + i];                                // (level1, level1)
+        if (w.u == w.u && w.v == w.v)                                     // NaN: undefined in the reference, no candidates here
+            sp_window(P, F, w, desc1 + qb * 2, i, lane, nullptr, cand_list + (qb + i) * (size_t)lc, lc, &total, nullptr);
+    }
+    if (lane == 0) cand_count[qb + i] = total;
+}
+
+__global__ void __launch_bounds__(32)
+init_resolve_kernel(const OrbxPlan* __restrict__ plan, const InitQuery* __restrict__ queries, SpParams P, int lc,
+                    const float* __restrict__ prev, const uint4* __restrict__ desc1, const int* __restrict__ octave1,
+                    const float* __restrict__ angle1, const float* __restrict__ kp, const uint8_t* __restrict__ desc,
+                    const int* __restrict__ kept_counts, const float* __restrict__ xy_un, const int* __restrict__ cell_start,
+                    const int* __restrict__ cell_items, const uint32_t* __restrict__ cand_list, const int* __restrict__ cand_count,
+                    int* __restrict__ match_out, float* __restrict__ prev_out, uint8_t* __restrict__ bin_scratch,
+                    int* __restrict__ stats_out) {
+    extern __shared__ int init_smem[];
+    __shared__ int s_hist[SP_HISTO];
+    const InitQuery q = queries[blockIdx.x];
+    const int kpf = plan->kept_per_frame;
+    const int n1 = q.n1, lane = threadIdx.x;
+    int* s_dist = init_smem;                 // [kpf] vMatchedDistance, by CSR position
+    int* s_owner = init_smem + kpf;          // [kpf] vnMatches21
+    const size_t qb = (size_t)blockIdx.x * P.cap;
+    const uint32_t* CL = cand_list + qb * (size_t)lc;
+    const int* CC = cand_count + qb;
+    int* M12 = match_out + qb;               // vnMatches12 as CSR positions until the end
+    uint8_t* BIN = bin_scratch + qb;
+    const SpFrame F = sp_frame(plan, P, q.frame, kp, desc, xy_un, cell_start, cell_items, nullptr);
+    for (int k = lane; k < kpf; k += 32) { s_dist[k] = INT_MAX; s_owner[k] = -1; }
+    if (lane < SP_HISTO) s_hist[lane] = 0;
+    for (int i = lane; i < n1; i += 32) { M12[i] = -1; BIN[i] = 255; }
+    __syncwarp();
+    int nmatches = 0;
+    int cnt_n = n1 > 0 ? CC[0] : 0;
+    uint32_t e_n = n1 > 0 ? CL[lane] : 0u;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        const int cnt = cnt_n;
+        const uint32_t e0 = e_n;
+        if (i1 + 1 < n1) {                                                // the next keypoint's first chunk: in flight during this decision
+            cnt_n = CC[i1 + 1];
+            e_n = CL[(size_t)(i1 + 1) * lc + lane];
+        }
+        if (cnt == 0) continue;                                           // higher octave or empty window (:424-431)
+        unsigned m1, m2;
+        if (cnt <= lc) {
+            unsigned best = 0xffffffffu, best2 = 0xffffffffu;
+            for (int j0 = 0; j0 < cnt; j0 += 32) {
+                const int j = j0 + lane;
+                unsigned key = 0xffffffffu;
+                if (j < cnt) {
+                    const uint32_t e = j0 == 0 ? e0 : CL[(size_t)i1 * lc + j];
+                    if (s_dist[e & 0xffffu] > (int)(e >> 16)) key = e;    // (:447-448)
+                }
+                best2 = min(best2, max(best, key));
+                best = min(best, key);
+            }
+            m1 = __reduce_min_sync(0xffffffffu, best);
+            m2 = __reduce_min_sync(0xffffffffu, best == m1 ? best2 : best);
+        } else {                                                          // the list did not fit: scan the window again
+            SpWin w;
+            w.u = prev[2 * (qb + i1)];
+            w.v = prev[2 * (qb + i1) + 1];
+            w.radius = P.th;
+            w.ur = 0.f;
+            w.minL = w.maxL = octave1[qb + i1];
+            m1 = sp_window(P, F, w, desc1 + qb * 2, i1, lane, nullptr, nullptr, 0, nullptr, &m2, s_dist);
+        }
+        if (m1 == 0xffffffffu) continue;
+        const int d1 = (int)(m1 >> 16), p = (int)(m1 & 0xffffu);
+        // bestDist2 stays INT_MAX without a runner-up (:439); (float)bestDist2 * mfNNratio in float (:469)
+        const float lim = __fmul_rn(m2 == 0xffffffffu ? (float)INT_MAX : (float)(int)(m2 >> 16), P.nnratio);
+        if (d1 <= SP_TH_LOW && (float)d1 < lim) {
+            if (lane == 0) {
+                const int old = s_owner[p];
+                if (old >= 0) M12[old] = -1;                              // (:471-475)
+                M12[i1] = p;
+                s_owner[p] = i1;
+                s_dist[p] = d1;
+                if (P.check_ori) {
+                    const int b = sp_rot_bin(angle1[qb + i1], F.K0[(size_t)F.IT[p] * 7 + 3]);      // (:481-490)
+                    s_hist[b] += 1;
+                    BIN[i1] = (uint8_t)b;
+                }
+            }
+            __syncwarp();                                                 // (nmatches is counted at the end: every steal is -1 + 1)
+        }
+    }
+    __syncwarp();
+    __threadfence_block();
+    unsigned keep = 0xffffffffu;
+    if (P.check_ori) {                                                    // ComputeThreeMaxima (:1601-1642), every lane the same scalars
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int b = 0; b < SP_HISTO; ++b) {
+            const int sz = s_hist[b];
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = b; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = b; }
+            else if (sz > max3) { max3 = sz; ind3 = b; }
+        }
+        if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+        else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+        keep = 0;
+        if (ind1 >= 0) keep |= 1u << ind1;
+        if (ind2 >= 0) keep |= 1u << ind2;
+        if (ind3 >= 0) keep |= 1u << ind3;
+    }
+    for (int i = lane; i < n1; i += 32) {
+        int p = M12[i];
+        if (p >= 0 && P.check_ori && BIN[i] < SP_HISTO && !((keep >> BIN[i]) & 1u)) p = -1;     // (:497-511)
+        const int k = p >= 0 ? F.IT[p] : -1;
+        M12[i] = k;
+        float px = prev[2 * (qb + i)], py = prev[2 * (qb + i) + 1];
+        if (k >= 0) { px = F.XY[2 * k]; py = F.XY[2 * k + 1]; ++nmatches; }                       // (:515-517)
+        prev_out[2 * (qb + i)] = px;
+        prev_out[2 * (qb + i) + 1] = py;
+    }
+    nmatches = __reduce_add_sync(0xffffffffu, nmatches);
+    if (lane == 0) stats_out[blockIdx.x] = nmatches;
 }
 
 // =====================================================================================
@@ -3239,8 +3409,9 @@ void search_projection_fill_query(void* dst, const float* Rcw, const float* tcw,
 // local = 0: SearchByProjection(CurrentFrame, LastFrame) -- world = positions, last_octave / last_angle of the LastFrame keypoints;
 // local = 1: SearchByProjection(F, vpMapPoints, th) -- world = (mTrackProjX, mTrackProjY, mTrackProjXR), last_octave =
 //            mnTrackScaleLevel, last_angle = mTrackViewCos, cur_obs = Observations() of what the frame's keypoints hold.
-cudaError_t launch_search_projection(const OrbxPlan* d_plan, const OrbxPlan& hp, int local, int nq, const void* d_queries, const float* K4,
-                                     const float* bounds, float mbf, float th, float nnratio, int check_ori, int cap, int list_cap,
+// mode 0: LastFrame variant (:1328-1470), 1: local-map variant (:45-129), 2: KeyFrame variant (:1472-1599, match_th = ORBdist)
+cudaError_t launch_search_projection(const OrbxPlan* d_plan, const OrbxPlan& hp, int mode, int nq, const void* d_queries, const float* K4,
+                                     const float* bounds, float mbf, float th, float nnratio, int check_ori, int match_th, int cap, int list_cap,
                                      const float* world, const uint8_t* mp_desc, const int* mp_obs, const int* last_octave,
                                      const float* last_angle, const float* kp, const uint8_t* desc, const int* kept_counts,
                                      const float* xy_un, const int* cell_start, const int* cell_items, const float* u_right,
@@ -3254,7 +3425,10 @@ cudaError_t launch_search_projection(const OrbxPlan* d_plan, const OrbxPlan& hp,
     P.mbf = mbf; P.th = th; P.nnratio = nnratio; P.check_ori = check_ori; P.cap = cap; P.use_stereo = u_right != nullptr;
     // entries worth listing: the match itself needs distance <= TH_HIGH; a runner-up can only reject (best > ratio * second)
     // while second < TH_HIGH / ratio
-    P.list_th = SP_TH_HIGH;
+    const bool local = mode == 1;
+    P.match_th = mode == 2 ? match_th : SP_TH_HIGH;
+    P.check_z = mode == 0;
+    P.list_th = P.match_th;
     if (local) P.list_th = nnratio > 0.4f ? (int)(SP_TH_HIGH / nnratio) + 1 : 256;
     const size_t smem = (size_t)(cap + hp.kept_per_frame) * sizeof(int);
     static size_t configured[64][2] = {{0}};
@@ -3319,6 +3493,41 @@ cudaError_t launch_compute_bow(const OrbxPlan* d_plan, const OrbxPlan& hp, const
     }
     return launch_k(bow_reduce_kernel, dim3((unsigned)nframes), dim3(1024), smem, st, d_plan, V, d_frames, sort_n, kept_counts,
                     (const int*)leaf, (const int*)nid, word_ids, word_values, fv_nodes, fv_features, counts_out);
+}
+
+// ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:405-520): d_queries = nq x {n1, frame} (8 bytes each)
+cudaError_t launch_search_init(const OrbxPlan* d_plan, const OrbxPlan& hp, int nq, const void* d_queries, const float* bounds, float window,
+                               float nnratio, int check_ori, int cap, int list_cap, const float* prev, const uint8_t* desc1,
+                               const int* octave1, const float* angle1, const float* kp, const uint8_t* desc, const int* kept_counts,
+                               const float* xy_un, const int* cell_start, const int* cell_items, uint32_t* cand_list, int* cand_count,
+                               uint8_t* bin_scratch, int* match_out, float* prev_out, int* stats_out, cudaStream_t st) {
+    SpParams P;
+    memset(&P, 0, sizeof P);
+    P.min_x = bounds[0]; P.max_x = bounds[1]; P.min_y = bounds[2]; P.max_y = bounds[3];
+    P.winv = 64.f / (bounds[1] - bounds[0]);
+    P.hinv = 48.f / (bounds[3] - bounds[2]);
+    P.th = window; P.nnratio = nnratio; P.check_ori = check_ori; P.cap = cap;
+    P.list_th = 256;                                                          // every candidate is listed
+    const size_t smem = (size_t)hp.kept_per_frame * 2 * sizeof(int);
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> config_lock(g_config_mutex);
+        if (smem > 48 * 1024 && smem > configured[dev & 63]) {
+            cudaError_t e = cudaFuncSetAttribute(init_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured[dev & 63] = smem;
+        }
+    }
+    const long long warps = (long long)nq * cap;
+    const dim3 lgrid((unsigned)((warps + SP_LIST_WARPS - 1) / SP_LIST_WARPS)), lblock(SP_LIST_WARPS * 32);
+    cudaError_t e = launch_k(init_list_kernel, lgrid, lblock, 0, st, d_plan, (const InitQuery*)d_queries, P, nq, list_cap, prev,
+                             (const uint4*)desc1, octave1, kp, desc, xy_un, cell_start, cell_items, cand_list, cand_count);
+    if (e != cudaSuccess) return e;
+    return launch_k(init_resolve_kernel, dim3((unsigned)nq), dim3(32), smem, st, d_plan, (const InitQuery*)d_queries, P, list_cap, prev,
+                    (const uint4*)desc1, octave1, angle1, kp, desc, kept_counts, xy_un, cell_start, cell_items,
+                    (const uint32_t*)cand_list, (const int*)cand_count, match_out, prev_out, bin_scratch, stats_out);
 }
 
 size_t search_bow_query_bytes() { return sizeof(BowMatchQuery); }

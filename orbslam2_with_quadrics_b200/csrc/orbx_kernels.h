@@ -59,8 +59,8 @@ cudaError_t launch_stereo(const OrbxPlan* d_plan, const OrbxPlan& hp, int num_sm
                           int* sad, int* row_start, uint16_t* bucket, cudaStream_t st);
 size_t search_projection_query_bytes();
 void search_projection_fill_query(void* dst, const float* Rcw, const float* tcw, int n_last, int frame, int fwd, int bwd);
-cudaError_t launch_search_projection(const OrbxPlan* d_plan, const OrbxPlan& hp, int local, int nq, const void* d_queries, const float* K4,
-                                     const float* bounds, float mbf, float th, float nnratio, int check_ori, int cap, int list_cap,
+cudaError_t launch_search_projection(const OrbxPlan* d_plan, const OrbxPlan& hp, int mode, int nq, const void* d_queries, const float* K4,
+                                     const float* bounds, float mbf, float th, float nnratio, int check_ori, int match_th, int cap, int list_cap,
                                      const float* world, const uint8_t* mp_desc, const int* mp_obs, const int* last_octave,
                                      const float* last_angle, const float* kp, const uint8_t* desc, const int* kept_counts,
                                      const float* xy_un, const int* cell_start, const int* cell_items, const float* u_right,
@@ -71,6 +71,11 @@ cudaError_t launch_compute_bow(const OrbxPlan* d_plan, const OrbxPlan& hp, const
                                const int* d_frames, int nframes, int levelsup, const uint8_t* desc, const int* kept_counts, int* leaf,
                                int* nid, unsigned* word_ids, double* word_values, unsigned* fv_nodes, unsigned* fv_features,
                                int* counts_out, cudaStream_t st);
+cudaError_t launch_search_init(const OrbxPlan* d_plan, const OrbxPlan& hp, int nq, const void* d_queries, const float* bounds, float window,
+                               float nnratio, int check_ori, int cap, int list_cap, const float* prev, const uint8_t* desc1,
+                               const int* octave1, const float* angle1, const float* kp, const uint8_t* desc, const int* kept_counts,
+                               const float* xy_un, const int* cell_start, const int* cell_items, uint32_t* cand_list, int* cand_count,
+                               uint8_t* bin_scratch, int* match_out, float* prev_out, int* stats_out, cudaStream_t st);
 size_t search_bow_query_bytes();
 void search_bow_fill_query(void* dst, int frame, int slot, int n_kf, int n_kf_fv);
 cudaError_t launch_search_bow(const OrbxPlan* d_plan, const OrbxPlan& hp, int nq, const void* d_queries, int cap, float nnratio,

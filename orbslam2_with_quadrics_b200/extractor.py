@@ -327,6 +327,57 @@ class ORBextractor:
         del keep
         return out
 
+    # ---------------------------------------------------------------- ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist)
+    def search_by_projection_kf(self, queries, K4, th: float, orb_dist: int, check_orientation: bool = True):
+        """(src/ORBmatcher.cc:1472-1599, Tracking::Relocalization) for each query: dicts with cur_frame, search (uint8: good, not yet
+        found, inside the distance-invariance range), world (n x 3), pred_level (MapPoint::PredictScale), mp_desc, kf_angle, Tcw_cur,
+        cur_held (or None).  Returns [(nmatches, new_match int32[N], rounds)]."""
+        qs = (_capi.OrbxKeyframeProjectionQuery * len(queries))()
+        keep = []
+        for q, d in zip(qs, queries):
+            a = dict(s=np.ascontiguousarray(d["search"], np.uint8), w=np.ascontiguousarray(d["world"], np.float32),
+                     lvl=np.ascontiguousarray(d["pred_level"], np.int32), desc=np.ascontiguousarray(d["mp_desc"], np.uint8),
+                     ang=np.ascontiguousarray(d["kf_angle"], np.float32))
+            ch = None if d.get("cur_held") is None else np.ascontiguousarray(d["cur_held"], np.int32)
+            keep.append((a, ch))
+            q.cur_frame, q.n_points = int(d.get("cur_frame", 0)), len(a["s"])
+            q.search, q.world_pos, q.pred_level = a["s"].ctypes.data, a["w"].ctypes.data, a["lvl"].ctypes.data
+            q.mp_desc, q.kf_angle = a["desc"].ctypes.data, a["ang"].ctypes.data
+            q.cur_held = None if ch is None else ch.ctypes.data
+            q.Tcw_cur = (C.c_float * 16)(*np.asarray(d["Tcw_cur"], np.float32).reshape(16))
+        res = (_capi.OrbxProjectionResult * len(queries))()
+        check(self._L.orbx_search_by_projection_kf(self._h, len(queries), qs, (C.c_float * 4)(*K4), th, int(orb_dist),
+                                                   int(check_orientation), res), self._h)
+        out = []
+        for r in res:
+            m = np.ctypeslib.as_array(C.cast(r.match, C.POINTER(C.c_int32)), shape=(max(r.n, 1),))[:r.n].copy()
+            out.append((r.nmatches, m, r.rounds))
+        del keep
+        return out
+
+    # ---------------------------------------------------------------- ORBmatcher::SearchForInitialization
+    def search_for_initialization(self, queries, nnratio: float = 0.9, check_orientation: bool = True, window: int = 100):
+        """(src/ORBmatcher.cc:405-520, Tracking::MonocularInitialization) for each query: dicts with cur_frame (F2, on the device),
+        octave1, angle1, desc1 (F1's undistorted keypoints), prev_matched (n1 x 2).  Returns [(nmatches, matches12 int32[n1],
+        prev_matched float32[n1, 2] as updated at :515-517)]."""
+        qs = (_capi.OrbxInitializationQuery * len(queries))()
+        keep = []
+        for q, d in zip(qs, queries):
+            a = dict(o=np.ascontiguousarray(d["octave1"], np.int32), a=np.ascontiguousarray(d["angle1"], np.float32),
+                     d=np.ascontiguousarray(d["desc1"], np.uint8), p=np.ascontiguousarray(d["prev_matched"], np.float32))
+            keep.append(a)
+            q.cur_frame, q.n1 = int(d.get("cur_frame", 0)), len(a["o"])
+            q.octave1, q.angle1, q.desc1, q.prev_matched = a["o"].ctypes.data, a["a"].ctypes.data, a["d"].ctypes.data, a["p"].ctypes.data
+        res = (_capi.OrbxInitializationResult * len(queries))()
+        check(self._L.orbx_search_for_initialization(self._h, len(queries), qs, nnratio, int(check_orientation), int(window), res), self._h)
+        out = []
+        for r in res:
+            m = np.ctypeslib.as_array(C.cast(r.matches12, C.POINTER(C.c_int32)), shape=(max(r.n1, 1),))[:r.n1].copy()
+            pm = np.ctypeslib.as_array(C.cast(r.prev_matched, C.POINTER(C.c_float)), shape=(max(r.n1, 1) * 2,))[:2 * r.n1].copy()
+            out.append((r.nmatches, m, pm.reshape(-1, 2)))
+        del keep
+        return out
+
     # ---------------------------------------------------------------- Frame::ComputeBoW
     def compute_bow(self, voc: "Vocabulary", frames=None, levelsup: int = 4):
         """(src/Frame.cc:395-402) on the descriptors of the last extract.  Returns per frame (word_ids uint32[], word_values
