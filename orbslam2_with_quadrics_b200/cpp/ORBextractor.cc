@@ -283,4 +283,66 @@ int ORBextractor::SearchByBoW(const std::vector<unsigned char>& kfDescriptors, c
     return r.nmatches;
 }
 
+int ORBextractor::SearchByProjectionKF(const std::vector<unsigned char>& search, const std::vector<float>& worldPos,
+                                       const std::vector<int>& predLevel, const std::vector<unsigned char>& descriptors,
+                                       const std::vector<float>& kfAngles, const std::vector<int>& currentHeld, const cv::Mat& TcwCurrent,
+                                       const cv::Mat& mK, float th, int ORBdist, bool checkOrientation, std::vector<int>& matched)
+{
+    const size_t n = search.size();
+    if (worldPos.size() != 3 * n || predLevel.size() != n || descriptors.size() != 32 * n || kfAngles.size() != n)
+        throw std::runtime_error("ORBextractor (orbx): SearchByProjectionKF needs one entry per KeyFrame map point in every array");
+    orbx_keyframe_projection_query q;
+    q.cur_frame = 0;
+    q.n_points = (int)n;
+    q.search = search.data();
+    q.world_pos = worldPos.data();
+    q.pred_level = predLevel.data();
+    q.mp_desc = descriptors.data();
+    q.kf_angle = kfAngles.data();
+    q.cur_held = currentHeld.empty() ? 0 : currentHeld.data();
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) q.Tcw_cur[4 * r + c] = TcwCurrent.at<float>(r, c);
+    const float K4[4] = {mK.at<float>(0, 0), mK.at<float>(1, 1), mK.at<float>(0, 2), mK.at<float>(1, 2)};
+    orbx_projection_result r;
+    int rc = orbx_search_by_projection_kf(handle_, 1, &q, K4, th, ORBdist, checkOrientation ? 1 : 0, &r);
+    if (rc != ORBX_OK) orbx_throw(handle_, rc, "orbx_search_by_projection_kf");
+    if (!currentHeld.empty() && (size_t)r.n != currentHeld.size())
+        throw std::runtime_error("ORBextractor (orbx): currentHeld is not sized like the last operator()'s keypoints");
+    matched.assign(r.match, r.match + r.n);
+    return r.nmatches;
+}
+
+int ORBextractor::SearchForInitialization(const std::vector<cv::KeyPoint>& keysUn1, const std::vector<unsigned char>& descriptors1,
+                                          std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, float nnRatio,
+                                          bool checkOrientation, int windowSize)
+{
+    const size_t n = keysUn1.size();
+    if (descriptors1.size() != 32 * n || vbPrevMatched.size() != n)
+        throw std::runtime_error("ORBextractor (orbx): SearchForInitialization needs one descriptor and one vbPrevMatched entry per F1 keypoint");
+    std::vector<int> octave(n);
+    std::vector<float> angle(n), prev(2 * n);
+    for (size_t i = 0; i < n; ++i) {
+        octave[i] = keysUn1[i].octave;
+        angle[i] = keysUn1[i].angle;
+        prev[2 * i] = vbPrevMatched[i].x;
+        prev[2 * i + 1] = vbPrevMatched[i].y;
+    }
+    orbx_initialization_query q;
+    q.cur_frame = 0;
+    q.n1 = (int)n;
+    q.octave1 = octave.data();
+    q.angle1 = angle.data();
+    q.desc1 = descriptors1.data();
+    q.prev_matched = prev.data();
+    orbx_initialization_result r;
+    int rc = orbx_search_for_initialization(handle_, 1, &q, nnRatio, checkOrientation ? 1 : 0, windowSize, &r);
+    if (rc != ORBX_OK) orbx_throw(handle_, rc, "orbx_search_for_initialization");
+    vnMatches12.assign(r.matches12, r.matches12 + r.n1);
+    for (size_t i = 0; i < n; ++i) {
+        vbPrevMatched[i].x = r.prev_matched[2 * i];
+        vbPrevMatched[i].y = r.prev_matched[2 * i + 1];
+    }
+    return r.nmatches;
+}
+
 } //namespace ORB_SLAM

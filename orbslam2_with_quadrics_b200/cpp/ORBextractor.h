@@ -120,6 +120,25 @@ public:
                     const std::vector<float>& kfAngles, const std::vector<std::pair<unsigned int, unsigned int> >& kfFeatVec,
                     float nnRatio, bool checkOrientation, std::vector<int>& matchedKF);
 
+    // ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist)
+    // (reference src/ORBmatcher.cc:1472-1599, Tracking::Relocalization) on the GPU; `this` is CurrentFrame.mpORBextractorLeft.
+    // Per KeyFrame map point the caller stages what the reference computes on the host with the map's own accessors:
+    // search = pMP && !isBad() && !sAlreadyFound.count(pMP) && dist3D inside [GetMinDistanceInvariance(),
+    // GetMaxDistanceInvariance()], predLevel = pMP->PredictScale(dist3D, &CurrentFrame), plus world position (3 floats),
+    // descriptor (32 bytes) and pKF->mvKeysUn[i].angle.  currentHeld[i2] > 0 where CurrentFrame.mvpMapPoints[i2] is not NULL.
+    // matched[i2] = index i of the KeyFrame point CurrentFrame.mvpMapPoints[i2] has to be set to, -1 = leave it.  Returns nmatches.
+    int SearchByProjectionKF(const std::vector<unsigned char>& search, const std::vector<float>& worldPos,
+                             const std::vector<int>& predLevel, const std::vector<unsigned char>& descriptors,
+                             const std::vector<float>& kfAngles, const std::vector<int>& currentHeld, const cv::Mat& TcwCurrent,
+                             const cv::Mat& mK, float th, int ORBdist, bool checkOrientation, std::vector<int>& matched);
+
+    // ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (reference src/ORBmatcher.cc:405-520,
+    // Tracking::MonocularInitialization) on the GPU; `this` is F2.mpORBextractorLeft (the current frame), F1 = mInitialFrame
+    // comes as its undistorted keypoints and descriptors (32 bytes per keypoint).  vbPrevMatched is updated as at :515-517.
+    int SearchForInitialization(const std::vector<cv::KeyPoint>& keysUn1, const std::vector<unsigned char>& descriptors1,
+                                std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, float nnRatio,
+                                bool checkOrientation, int windowSize = 10);
+
 private:
     ORBextractor(const ORBextractor&);
     ORBextractor& operator=(const ORBextractor&);
