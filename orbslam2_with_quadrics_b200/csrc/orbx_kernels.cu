@@ -1645,10 +1645,30 @@ describe_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restric
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncwarp();
-
     const int kpf = plan->kept_per_frame;
     const int nl = plan->nlevels;
+    __shared__ int s_koff[ORBX_MAXL + 2];                                  // first output slot of every level, INT_MAX behind the last
+    if (threadIdx.x < ORBX_MAXL + 2) s_koff[threadIdx.x] = (int)threadIdx.x < nl ? plan->lv[threadIdx.x].kept_off : INT_MAX;
+    __syncthreads();
+    // IC_Angle lane roles (phase 1): lane = (row group icg, word icw); word icw holds patch columns u = -16 + 4 icw .. + 3,
+    // row group icg takes rows v = -15 + icg + 4 i, i = 0 .. 7.  icmask[i]: bytes of the word inside the circular patch
+    // (|u| <= umax[|v|], :86-101), icwt: the four u as signed bytes.
+    const int icw = lane & 7, icg = lane >> 3;
+    uint32_t icmask[8], icwt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) icwt |= (uint32_t)((-16 + 4 * icw + j) & 0xff) << (8 * j);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int v = -15 + icg + 4 * i;
+        const int um = v <= 15 ? plan->umax[v < 0 ? -v : v] : -1;        // (== UMAX, checked when the plan is built)
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int u = -16 + 4 * icw + j;
+            if ((u < 0 ? -u : u) <= um) m |= 0xffu << (8 * j);
+        }
+        icmask[i] = m;
+    }
     const unsigned total = (unsigned)nframes * (unsigned)kpf;
     const unsigned nwarps = gridDim.x * KP_WARPS;
     const uint32_t K0123 = 18u | (34u << 8) | (48u << 16) | (56u << 24);
@@ -1658,22 +1678,29 @@ describe_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restric
     const uint32_t KC = (18u << 8) | (34u << 16) | (48u << 24);           // odd row:  pairs m (lo), m+1 (hi)
     const uint32_t KD = 56u | (48u << 8) | (34u << 16) | (18u << 24);     //           pairs m+2 (lo), m+3 (hi)
 
-    // next occupied slot at or after `it` (slots past a level's kept count are empty)
-    auto next_item = [&](unsigned it) -> KpItem {
+    // next occupied slot at or after the cursor (slots past a level's kept count are empty); the cursor carries (frame, slot)
+    // along, so a step costs neither a division nor a walk over the plan's level records
+    unsigned c_it = blockIdx.x * KP_WARPS + warp;
+    int c_frame = (int)(c_it / (unsigned)kpf), c_s = (int)(c_it - (unsigned)c_frame * (unsigned)kpf);
+    auto next_item = [&]() -> KpItem {
         KpItem k;
         k.frame = k.l = k.sl = 0;
         k.p = 0;
-        for (; it < total; it += nwarps) {
-            k.frame = (int)(it / (unsigned)kpf);
-            const int s = (int)(it - (unsigned)k.frame * (unsigned)kpf);
-            k.l = level_of_slot(plan, s);
-            k.sl = s - plan->lv[k.l].kept_off;
-            if (k.sl < kept_counts[k.frame * nl + k.l]) {
-                k.p = kept[it];
+        for (; c_it < total;) {
+            int l = 0;
+            while (c_s >= s_koff[l + 1]) ++l;
+            const int sl = c_s - s_koff[l];
+            if (sl < kept_counts[c_frame * nl + l]) {
+                k.frame = c_frame; k.l = l; k.sl = sl;
+                k.p = kept[c_it];
                 break;
             }
+            c_it += nwarps; c_s += (int)nwarps;
+            while (c_s >= kpf) { c_s -= kpf; ++c_frame; }
         }
-        k.it = it;
+        k.it = c_it;
+        c_it += nwarps; c_s += (int)nwarps;                                // the cursor rests on the slot after the returned one
+        while (c_s >= kpf) { c_s -= kpf; ++c_frame; }
         return k;
     };
     auto issue = [&](const KpItem& k) {
@@ -1684,30 +1711,34 @@ describe_kernel(const __grid_constant__ FastMaps maps, const OrbxPlan* __restric
         }
     };
 
-    KpItem cur = next_item(blockIdx.x * KP_WARPS + warp);
+    KpItem cur = next_item();
     if (cur.it < total) issue(cur);
     uint32_t phase = 0;
     while (cur.it < total) {
-        const KpItem nxt = next_item(cur.it + nwarps);
+        const KpItem nxt = next_item();
         const OrbxLevel& L = plan->lv[cur.l];
         const int kx = ORBX_PX(cur.p), ky = ORBX_PY(cur.p);
         const int a16 = (ORBX_XO + kx - 21) & 15;                         // byte column of patch column -21 inside the window
         mbar_wait(bar, phase);
         phase ^= 1;
 
-        // ---- phase 1: IC_Angle.  lane = column u = lane - 15; row v reads +-umax[|v|] (:86-101)
+        // ---- phase 1: IC_Angle (:77-104).  Integer moments, so any summation order gives the reference's m_10 / m_01: a lane
+        //      sums 4 columns of 8 rows with two byte dot products per row (row sum, and the sum weighted by u)
         int m10 = 0, m01 = 0;
-        if (lane < 31) {
-            const int u = lane - 15, au = abs(u);
-            const uint8_t* c = raw + 21 * KP_RAW_W + a16 + 21 + u;
-            int colsum = 0;
+        {
+            const int ub = a16 + 5;                                        // window byte column of patch column u = -16
+            const int sh = (ub & 3) * 8;
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(raw) + (6 + icg) * (KP_RAW_W / 4) + (ub >> 2) + icw;
+            int s0 = 0, s1 = 0;
 #pragma unroll
-            for (int v = -15; v <= 15; ++v) {
-                const int val = au <= UMAX[v < 0 ? -v : v] ? (int)c[v * KP_RAW_W] : 0;
-                colsum += val;
-                m01 += v * val;
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t px = __funnelshift_r(rw[i * KP_RAW_W], rw[i * KP_RAW_W + 1], sh) & icmask[i];
+                const int rs = (int)__dp4a(px, 0x01010101u, 0u);
+                asm("dp4a.s32.u32 %0, %1, %2, %0;" : "+r"(m10) : "r"(icwt), "r"(px));
+                s0 += rs;
+                s1 += i * rs;
             }
-            m10 = u * colsum;
+            m01 = (icg - 15) * s0 + 4 * s1;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
