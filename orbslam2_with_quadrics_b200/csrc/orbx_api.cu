@@ -65,6 +65,7 @@ struct orbx_handle {
     int* d_counters;             // [level_counts B*L][sorted_counts B*L][kept_counts B*L][status B][work counters][retry_counts B*L]
     std::vector<unsigned char> fast_maps;   // per-level TMA descriptors of the pyramid slabs (box = strip of FAST windows)
     std::vector<unsigned char> desc_maps;   // the same planes with box = one keypoint's raw window
+    std::vector<unsigned char> pyr_maps;    // the same planes as u32 elements, box = pyr_resize8_tile_kernel's source tile
     float* d_angles;
     float* d_out_kp;
     uint8_t* d_out_desc;
@@ -243,12 +244,31 @@ void build_resize8_tables(std::vector<OrbxTap>& taps, const OrbxLevel& S, OrbxLe
             }
         }
     }
-    (void)S;
     L.col8_off = (int)taps.size();
     const OrbxTap* raw = reinterpret_cast<const OrbxTap*>(cols.data());
     taps.insert(taps.end(), raw, raw + (size_t)L.ngroups8 * 8);
     L.yrow_off = (int)taps.size();
     for (int r = 0; r < L.rows; ++r) taps.push_back(taps[L.ytab_off + reflect_clamp_host(r - ORBX_EDGE, L.h)]);
+    // pyr_resize8_tile_kernel: does every CTA's source footprint (32 groups x 64 plane rows) fit its 336 x 80 byte TMA tile?
+    L.resize_tile_ok = L.resize8_ok;
+    for (int g0 = 0; g0 < L.ngroups8 && L.resize_tile_ok; g0 += 32) {
+        int mn = 1 << 30, mx = 0;
+        for (int g = g0; g < g0 + 32 && g < L.ngroups8; ++g)
+            for (int hf = 0; hf < 2; ++hf) {
+                mn = std::min(mn, cols[g].base[hf]);
+                mx = std::max(mx, cols[g].base[hf] + 12);
+            }
+        if (mx - ((mn + ORBX_XO) & ~15) + ORBX_XO > 336) L.resize_tile_ok = 0;
+    }
+    for (int r0 = 0; r0 < L.rows && L.resize_tile_ok; r0 += 64) {
+        int mn = 1 << 30, mx = 0;
+        for (int r = r0; r < r0 + 64 && r < L.rows; ++r) {
+            const int sy = taps[L.yrow_off + r].ofs;
+            mn = std::min(mn, sy);
+            mx = std::max(mx, std::min(sy + 1, S.h - 1));
+        }
+        if (mx - mn + 1 > 80) L.resize_tile_ok = 0;
+    }
 }
 
 void level_size(const orbx_handle* h, int w, int hgt, int l, int* lw, int* lh) {
@@ -519,7 +539,9 @@ int ensure_geometry(orbx_handle* h, int w, int hgt) {
     if (h->cfg.download_pyramid) CK(h, cudaMallocHost(&h->h_pyr, B * P.slab_bytes));
     h->fast_maps.resize(orbx::fast_maps_bytes());
     h->desc_maps.resize(orbx::fast_maps_bytes());
-    if (orbx::build_fast_maps(h->plan, h->d_pyr, h->cfg.max_batch, h->fast_maps.data()) != 0 ||
+    h->pyr_maps.resize(orbx::fast_maps_bytes());
+    if (orbx::build_pyr_tile_maps(h->plan, h->d_pyr, h->cfg.max_batch, h->pyr_maps.data()) != 0 ||
+        orbx::build_fast_maps(h->plan, h->d_pyr, h->cfg.max_batch, h->fast_maps.data()) != 0 ||
         orbx::build_describe_maps(h->plan, h->d_pyr, h->cfg.max_batch, h->desc_maps.data()) != 0) {
         h->last_error = "cuTensorMapEncodeTiled failed";
         return ORBX_ERR_CUDA;
@@ -583,7 +605,7 @@ int enqueue_frames(orbx_handle* h, int f0, int n, const uint8_t* d_imgs, size_t 
     int* wc = h->d_work_counter() + ORBX_MAXL * chunk;                // FAST work counters of this chunk, one per level
     if (ev) CK(h, cudaEventRecord(ev[ST_PYRAMID], st));
     for (int l = 0; l < L; ++l) {
-        orbx::launch_pyr_level(h->d_plan, P, l, n, h->num_sms, d_imgs, pitch, frame_stride, pyr, h->d_taps, st);
+        orbx::launch_pyr_level(h->d_plan, P, l, n, h->num_sms, d_imgs, pitch, frame_stride, pyr, h->d_taps, st, h->pyr_maps.data(), f0);
         if (ls && l == ls - 1) {
             CK(h, cudaEventRecord(h->ev_low[si], st));
             CK(h, cudaStreamWaitEvent(ax, h->ev_low[si], 0));

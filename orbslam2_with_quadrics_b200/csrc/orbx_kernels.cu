@@ -470,6 +470,109 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
+// pyr_resize8_tile_kernel: the same lanes, tables and arithmetic as pyr_resize8_kernel, but the source pixels of a CTA's
+// 256 x 64 output block (<= 307 x 79 source pixels + alignment) arrive as ONE TMA tile in shared memory (u32 tensor map over
+// the source plane: the 336-byte box is wider than a u8 box may be), so a source row costs six LDS instead of six dependent
+// global loads and no register prefetch is needed.  Used for the launches whose warps take full PYR_RY-row strips (the
+// large levels of a batch).  A CTA always covers 64 plane rows: with shorter strips (RY = 8 / 4 / 2 rows per warp, the smaller
+// levels) it simply has 8 / 16 / 32 warps sharing the one tile.
+#define PYR_TILE_W 336                       // bytes per tile row: 256 * 1.2 + 15 (alignment) + 12 (three words per half) <= 336
+#define PYR_TILE_H 80                        // source rows of 64 output rows: 64 * 1.2 + 2 <= 80
+template <int RY>
+__global__ void __launch_bounds__(64 / RY * 32) pyr_resize8_tile_kernel(const __grid_constant__ CUtensorMap src_map, const OrbxPlan* __restrict__ plan,
+                                                                        int l, int frame0, uint8_t* pyr, const OrbxTap* __restrict__ taps) {
+    // (`pyr` is the slab of the sub-batch's first frame, the tensor map covers the handle's whole pyramid: frame0 = that frame)
+    ORBX_PDL_WAIT();
+    constexpr int NW = 64 / RY;                                               // warps per CTA
+    __shared__ __align__(128) uint8_t s_tile[PYR_TILE_W * PYR_TILE_H];
+    __shared__ uint64_t s_bar;
+    __shared__ int s_org[2];
+    const OrbxLevel& L = plan->lv[l];
+    const OrbxLevel& S = plan->lv[l - 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = blockIdx.z;
+    const int g = blockIdx.x * 32 + lane;                                      // group of 8 plane columns from column 8 on
+    const int gc = min(g, L.ngroups8 - 1);
+    const int row0 = (blockIdx.y * NW + warp) * RY;                            // first plane row of this warp
+    const uint4* cgp = reinterpret_cast<const uint4*>(taps + L.col8_off) + 4 * gc;
+    const uint4 c0 = __ldg(cgp), c1 = __ldg(cgp + 1), c2 = __ldg(cgp + 2), c3 = __ldg(cgp + 3);
+    const int hs1 = S.h - 1;
+    // tile origin: smallest source column of the CTA's 32 groups (16-byte aligned, plane coordinates) and smallest source
+    // row of its 64 plane rows (border rows reflect, so neither is simply the first entry)
+    if (warp == 0) {
+        int mn = min((int)c0.x, (int)c0.y);
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        const int cta_row0 = blockIdx.y * 64;
+        int r = INT_MAX;
+        for (int i = lane; i < 64; i += 32)
+            if (cta_row0 + i < L.rows) r = min(r, (int)__ldg(reinterpret_cast<const uint2*>(taps + L.yrow_off + cta_row0 + i)).x);
+        r = __reduce_min_sync(0xffffffffu, r);
+        if (lane == 0) {
+            const int tx0 = (mn + ORBX_XO) & ~15, ty0 = r + ORBX_EDGE;
+            s_org[0] = tx0;
+            s_org[1] = ty0;
+            mbar_init(&s_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&s_bar, (uint32_t)(PYR_TILE_W * PYR_TILE_H));
+            tma_load_3d(s_tile, &src_map, &s_bar, tx0 >> 2, ty0, frame0 + frame);
+        }
+    }
+    __syncthreads();
+    const int tx0 = s_org[0], ty0 = s_org[1];
+    mbar_wait(&s_bar, 0);
+    if (row0 >= L.rows || g >= L.ngroups8) return;
+    uint8_t* slab = pyr + (size_t)frame * plan->slab_bytes;
+    const uint8_t* tlo = s_tile + ((int)c0.x + ORBX_XO - tx0) + (ORBX_EDGE - ty0) * PYR_TILE_W;      // source pixel (0, 0) of each half
+    const uint8_t* thi = s_tile + ((int)c0.y + ORBX_XO - tx0) + (ORBX_EDGE - ty0) * PYR_TILE_W;
+    const uint32_t shl = c0.z & 31u, shh = (c0.z >> 8) & 31u;
+    const uint32_t sel0 = c1.x, sel1 = c1.y, sel2 = c1.z, sel3 = c1.w;
+    const uint32_t k0 = c2.x, k1 = c2.y, k2 = c2.z, k3 = c2.w, k4 = c3.x, k5 = c3.y, k6 = c3.z, k7 = c3.w;
+    auto pass = [&](int sy, uint32_t* H) {                                     // H[j] = (S[sx]*a0 + S[sx+1]*a1) >> 4 of source row sy
+        const uint32_t* pa = reinterpret_cast<const uint32_t*>(tlo + sy * PYR_TILE_W);
+        const uint32_t* pb = reinterpret_cast<const uint32_t*>(thi + sy * PYR_TILE_W);
+        ORBX_BC(reinterpret_cast<const uint8_t*>(pa) >= s_tile && reinterpret_cast<const uint8_t*>(pa + 3) <= s_tile + sizeof(s_tile) &&
+                reinterpret_cast<const uint8_t*>(pb) >= s_tile && reinterpret_cast<const uint8_t*>(pb + 3) <= s_tile + sizeof(s_tile));
+        const uint32_t a0 = pa[0], a1 = pa[1], a2 = pa[2], b0 = pb[0], b1 = pb[1], b2 = pb[2];
+        const uint32_t U = __funnelshift_r(a0, a1, shl), V = __funnelshift_r(a1, a2, shl);
+        const uint32_t X = __funnelshift_r(b0, b1, shh), Y = __funnelshift_r(b1, b2, shh);
+        const uint32_t p0 = __byte_perm(U, V, sel0), p1 = __byte_perm(U, V, sel1);
+        const uint32_t p2 = __byte_perm(X, Y, sel2), p3 = __byte_perm(X, Y, sel3);
+        H[0] = __dp2a_lo(k0, p0, 0u) >> 4; H[1] = __dp2a_hi(k1, p0, 0u) >> 4;
+        H[2] = __dp2a_lo(k2, p1, 0u) >> 4; H[3] = __dp2a_hi(k3, p1, 0u) >> 4;
+        H[4] = __dp2a_lo(k4, p2, 0u) >> 4; H[5] = __dp2a_hi(k5, p2, 0u) >> 4;
+        H[6] = __dp2a_lo(k6, p3, 0u) >> 4; H[7] = __dp2a_hi(k7, p3, 0u) >> 4;
+    };
+    const int nrow = min(RY, L.rows - row0);
+    const uint2* yt = reinterpret_cast<const uint2*>(taps + L.yrow_off + row0);     // (source row, c0 | c1 << 16)
+    uint8_t* dst = slab + L.plane_off + (size_t)row0 * L.pitch + 8 + 8 * g;
+    uint32_t H0[8], H1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) H0[j] = H1[j] = 0;
+    int id0 = -1, id1 = -1;
+    uint2 ty = __ldg(yt);
+    for (int i = 0; i < nrow; ++i, dst += L.pitch) {
+        const uint2 tyn = __ldg(yt + min(i + 1, nrow - 1));                   // one output row ahead
+        const int r0 = (int)ty.x, r1 = min(r0 + 1, hs1);
+        uint32_t b0, b1;                                                      // row weights of H0, H1, << 16
+        if (r0 == id1) {                                                      // the usual step: last row's lower row is the upper one
+            if (r1 != r0 && id0 != r1) { pass(r1, H0); id0 = r1; }
+            b0 = ty.y & 0xffff0000u; b1 = ty.y << 16;
+        } else {
+            if (r0 != id0) { pass(r0, H0); id0 = r0; }
+            if (r1 != r0 && id1 != r1) { pass(r1, H1); id1 = r1; }
+            b0 = ty.y << 16; b1 = ty.y & 0xffff0000u;
+        }
+        uint32_t sv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sv[j] = __umulhi(b0, H0[j]) + __umulhi(b1, H1[j]);    // <= 1020: weights sum to 2048
+        const uint32_t t01 = (sv[0] + (sv[1] << 16) + 0x00020002u) >> 2, t23 = (sv[2] + (sv[3] << 16) + 0x00020002u) >> 2;
+        const uint32_t t45 = (sv[4] + (sv[5] << 16) + 0x00020002u) >> 2, t67 = (sv[6] + (sv[7] << 16) + 0x00020002u) >> 2;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(__byte_perm(t01, t23, 0x6420), __byte_perm(t45, t67, 0x6420));
+        ty = tyn;
+    }
+}
+
 struct FastStrip {
     int frame, l, ci, cj0;     // NC horizontally adjacent cells starting at column cj0 of cell row ci
 };
@@ -3171,7 +3274,7 @@ static bool force_resize4() {          // ORBX_RESIZE4=1: A/B switch back to the
 
 void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nframes, int num_sms, const uint8_t* imgs,
                       size_t img_pitch, size_t img_frame_stride, uint8_t* pyr, const OrbxTap* taps,
-                      cudaStream_t st);
+                      cudaStream_t st, const void* tile_maps, int frame0);
 
 // Block geometry of one pyramid level, shared by the per-level launches and the chained kernel.
 struct PyrGeom { int gx, gy, ry, kind; };
@@ -3200,11 +3303,20 @@ static PyrGeom pyr_geometry(const OrbxPlan& hp, int l, int nframes, int num_sms)
 
 void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nframes, int num_sms, const uint8_t* imgs,
                       size_t img_pitch, size_t img_frame_stride, uint8_t* pyr, const OrbxTap* taps,
-                      cudaStream_t st) {
+                      cudaStream_t st, const void* tile_maps, int frame0) {
     const PyrGeom g = pyr_geometry(hp, l, nframes, num_sms);
+    static const bool no_tile = getenv("ORBX_PYR_NO_TILE") != nullptr;         // A/B switch
+    static const int min_tile_ry = getenv("ORBX_PYR_TILE_MINRY") ? atoi(getenv("ORBX_PYR_TILE_MINRY")) : 8;   // strips shorter than this keep pyr_resize8_kernel (measured: 64 x 1080p 1.425 -> 1.378 ms with 8, 1.376 with 4; 64 x 640x480 0.438 / 0.439 / 0.446 ms without / 8 / 4; 2-row strips = 1024-thread CTAs, a single 1080p frame 0.120 vs 0.098 ms)
     if (g.kind == 0) {
         const int aligned16 = ((reinterpret_cast<uintptr_t>(imgs) | img_pitch | img_frame_stride) & 15) == 0;
         launch_k(pyr_level0_kernel, dim3(g.gx, g.gy, nframes), dim3(32, 8), 0, st, d_plan, imgs, img_pitch, img_frame_stride, aligned16, pyr);
+    } else if (g.kind == 1 && g.ry >= min_tile_ry && g.ry <= 16 && hp.lv[l].resize_tile_ok && tile_maps && !no_tile) {
+        const CUtensorMap& m = reinterpret_cast<const FastMaps*>(tile_maps)->m[l - 1];
+        const dim3 grid(g.gx, (hp.lv[l].rows + 63) / 64, nframes);
+        if (g.ry == 16) launch_k(pyr_resize8_tile_kernel<16>, grid, dim3(128), 0, st, m, d_plan, l, frame0, pyr, taps);
+        else if (g.ry == 8) launch_k(pyr_resize8_tile_kernel<8>, grid, dim3(256), 0, st, m, d_plan, l, frame0, pyr, taps);
+        else if (g.ry == 4) launch_k(pyr_resize8_tile_kernel<4>, grid, dim3(512), 0, st, m, d_plan, l, frame0, pyr, taps);
+        else launch_k(pyr_resize8_tile_kernel<2>, grid, dim3(1024), 0, st, m, d_plan, l, frame0, pyr, taps);
     } else if (g.kind == 1) {
         launch_k(pyr_resize8_kernel, dim3(g.gx, g.gy, nframes), dim3(128), 0, st, d_plan, l, g.ry, pyr, taps);
     } else if (g.kind == 3) {
@@ -3212,6 +3324,33 @@ void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nfr
     } else {
         launch_k(pyr_resize_kernel<false>, dim3(g.gx, g.gy, nframes), dim3(128), 0, st, d_plan, l, g.ry, pyr, taps);
     }
+}
+
+// u32 tensor maps {pitch / 4, rows, frames} of the level planes, box = pyr_resize8_tile_kernel's source tile
+int build_pyr_tile_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* out_maps) {
+    static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess || !fn)
+            return -1;
+        encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }
+    FastMaps* fm = reinterpret_cast<FastMaps*>(out_maps);
+    memset(fm, 0, sizeof(FastMaps));
+    for (int l = 0; l < hp.nlevels; ++l) {
+        const OrbxLevel& L = hp.lv[l];
+        cuuint64_t dims[3] = {(cuuint64_t)(L.pitch / 4), (cuuint64_t)L.rows, (cuuint64_t)max_frames};
+        cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)hp.slab_bytes};
+        cuuint32_t box[3] = {PYR_TILE_W / 4, PYR_TILE_H, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&fm->m[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, d_pyr + L.plane_off, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return -(int)r - 100;
+    }
+    return 0;
 }
 
 // dynamic shared memory of fast_cells_kernel (fast_strips_kernel's is static)

@@ -30,8 +30,11 @@
 
 namespace orbx {
 
+// tile_maps: build_pyr_tile_maps' descriptors (launches with full-length strips read their source through TMA tiles), or NULL
 void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nframes, int num_sms, const uint8_t* imgs,
-                      size_t img_pitch, size_t img_frame_stride, uint8_t* pyr, const OrbxTap* taps, cudaStream_t st);
+                      size_t img_pitch, size_t img_frame_stride, uint8_t* pyr, const OrbxTap* taps, cudaStream_t st,
+                      const void* tile_maps = nullptr, int frame0 = 0);
+int build_pyr_tile_maps(const OrbxPlan& hp, uint8_t* d_pyr, int max_frames, void* out_maps);
 // cvtColor(RGB/BGR(A) -> GRAY), src/Tracking.cc:172-255; format = orbx_pixel_format (1..4)
 cudaError_t launch_cvt_gray(const uint8_t* src, size_t src_pitch, size_t src_frame_stride, int w, int h, int nframes, int format,
                             uint8_t* dst, size_t dst_pitch, size_t dst_frame_stride, cudaStream_t st);

@@ -45,6 +45,7 @@ struct OrbxLevel {
     int col8_off, ngroups8;   // pyr_resize8_kernel: this level's OrbxCol8 records (offset in OrbxTap units), groups of 8 plane columns
     int yrow_off;             // per PLANE row row-tap entries (border reflection already applied), OrbxTap units
     int resize8_ok;           // 0: a half-group's source window exceeds 8 bytes (scale factor > 2): 4-pixel kernel instead
+    int resize_tile_ok;       // 1: a CTA's source footprint fits pyr_resize8_tile_kernel's TMA tile (scale factors up to ~1.2)
 };
 
 struct OrbxPlan {

@@ -122,6 +122,29 @@ def test_batch_equals_single_and_is_deterministic():
     gb.close(); g1.close()
 
 
+def test_large_batch_tile_resize_path_equals_single_frames():
+    """A 40 x 1080p batch runs the large pyramid levels through pyr_resize8_tile_kernel (TMA source tiles, full 16-row
+    strips) in sub-batches that start at frame > 0; a single frame takes pyr_resize8_kernel's short strips.  Keypoints,
+    descriptors and every pyramid plane (border included) must be the same bytes."""
+    w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["rgbd_1080p"]
+    base = [fr.cluttered_scene(w, h, 700 + i) for i in range(4)]
+    imgs = [base[i % 4] for i in range(40)]
+    gb = ORBextractor(nf, sf, nl, it, mt, max_batch=len(imgs), download_pyramid=True)
+    g1 = ORBextractor(nf, sf, nl, it, mt, download_pyramid=True)
+    batch = gb.extract_batch(imgs)
+    single = []
+    for im in base:
+        k1, d1 = g1(im)
+        single.append((k1.copy(), d1.copy(), [g1.pyramid(0)[l].copy() for l in range(nl)]))
+    for i in (0, 1, 9, 18, 31, 32, 35, 39):                   # frames of every sub-batch
+        k1, d1, p1 = single[i % 4]
+        assert np.array_equal(batch[i][0].view(np.uint8), k1.view(np.uint8)) and np.array_equal(batch[i][1], d1)
+        pb = gb.pyramid(i)
+        for l in range(nl):
+            assert np.array_equal(pb[l], p1[l]), (i, l)
+    gb.close(); g1.close()
+
+
 def test_stereo_two_handles_two_threads():
     """src/Frame.cc:78-81: left and right extractors run concurrently on two host threads."""
     w, h, nf, sf, nl, it, mt, _ = fr.CONFIGS["stereo_kitti"]
