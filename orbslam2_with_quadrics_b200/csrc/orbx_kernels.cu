@@ -2848,18 +2848,25 @@ init_resolve_kernel(const OrbxPlan* __restrict__ plan, const InitQuery* __restri
     const SpFrame F = sp_frame(plan, P, q.frame, kp, desc, xy_un, cell_start, cell_items, nullptr);
     for (int k = lane; k < kpf; k += 32) { s_dist[k] = INT_MAX; s_owner[k] = -1; }
     if (lane < SP_HISTO) s_hist[lane] = 0;
-    for (int i = lane; i < n1; i += 32) { M12[i] = -1; BIN[i] = 255; }
+    int* PACC = reinterpret_cast<int*>(prev_out + 2 * qb);    // [2 i1]: F2 keypoint (CSR position) i1 had when it was accepted, -1: never
+    for (int i = lane; i < n1; i += 32) { M12[i] = -1; BIN[i] = 255; PACC[2 * i] = -1; }
     __syncwarp();
     int nmatches = 0;
-    int cnt_n = n1 > 0 ? CC[0] : 0;
-    uint32_t e_n = n1 > 0 ? CL[lane] : 0u;
+    // The loop is a chain of short iterations, so what it waits for is memory latency: the candidate counts are fetched 32
+    // keypoints at a time (lane k holds the count of keypoint 32 j + k) and the first list chunk of a keypoint is requested
+    // INIT_AHEAD iterations before it is needed.
+    constexpr int INIT_AHEAD = 4;
+    uint32_t ering[INIT_AHEAD];
+#pragma unroll
+    for (int a = 0; a < INIT_AHEAD; ++a) ering[a] = a < n1 ? CL[(size_t)a * lc + lane] : 0u;
+    int cnt32 = 0;
     for (int i1 = 0; i1 < n1; ++i1) {
-        const int cnt = cnt_n;
-        const uint32_t e0 = e_n;
-        if (i1 + 1 < n1) {                                                // the next keypoint's first chunk: in flight during this decision
-            cnt_n = CC[i1 + 1];
-            e_n = CL[(size_t)(i1 + 1) * lc + lane];
-        }
+        if ((i1 & 31) == 0) cnt32 = i1 + lane < n1 ? CC[i1 + lane] : 0;
+        const int cnt = __shfl_sync(0xffffffffu, cnt32, i1 & 31);
+        const uint32_t e0 = ering[0];
+#pragma unroll
+        for (int a = 0; a + 1 < INIT_AHEAD; ++a) ering[a] = ering[a + 1];
+        ering[INIT_AHEAD - 1] = i1 + INIT_AHEAD < n1 ? CL[(size_t)(i1 + INIT_AHEAD) * lc + lane] : 0u;
         if (cnt == 0) continue;                                           // higher octave or empty window (:424-431)
         unsigned m1, m2;
         if (cnt <= lc) {
@@ -2896,18 +2903,24 @@ init_resolve_kernel(const OrbxPlan* __restrict__ plan, const InitQuery* __restri
                 M12[i1] = p;
                 s_owner[p] = i1;
                 s_dist[p] = d1;
-                if (P.check_ori) {
-                    const int b = sp_rot_bin(angle1[qb + i1], F.K0[(size_t)F.IT[p] * 7 + 3]);      // (:481-490)
-                    s_hist[b] += 1;
-                    BIN[i1] = (uint8_t)b;
-                }
-            }
+                PACC[2 * i1] = p;                                         // what rotHist receives (:481-490) is settled after the loop:
+            }                                                             // its two dependent global loads would sit on this chain
             __syncwarp();                                                 // (nmatches is counted at the end: every steal is -1 + 1)
         }
     }
     __syncwarp();
     __threadfence_block();
     unsigned keep = 0xffffffffu;
+    if (P.check_ori) {                                                    // rotHist: every keypoint that was ever accepted stays in its bin (:481-490)
+        for (int i = lane; i < n1; i += 32) {
+            const int p = PACC[2 * i];
+            if (p < 0) continue;
+            const int b = sp_rot_bin(angle1[qb + i], F.K0[(size_t)F.IT[p] * 7 + 3]);
+            atomicAdd(&s_hist[b], 1);
+            BIN[i] = (uint8_t)b;
+        }
+        __syncwarp();
+    }
     if (P.check_ori) {                                                    // ComputeThreeMaxima (:1601-1642), every lane the same scalars
         int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
         for (int b = 0; b < SP_HISTO; ++b) {
