@@ -90,7 +90,12 @@ ORBX_API int orbx_destroy(orbx_handle* h);
  * stride).  Blocks until the outputs are in host memory. */
 ORBX_API int orbx_extract(orbx_handle* h, const uint8_t* img, int width, int height, size_t stride, orbx_result* result);
 
-/* The same for n <= max_batch frames of identical size in one launch sequence. */
+/* The same for n <= max_batch frames of identical size in one launch sequence.  One (width, height) per call by design: the
+ * plan (level sizes, cell grid, tap tables, tensor maps, HBM layout) is built per geometry and every kernel of the sequence
+ * covers all frames of the batch with it, so a per-frame w[] / h[] (SURVEY.md 8b's sketch) would mean one launch sequence per
+ * distinct size anyway.  Streams of different sizes use one handle per geometry -- in ORB-SLAM2 a camera is one
+ * ORBextractor, so that is the reference's own arrangement (src/Tracking.cc:121-127); a handle that sees a new size rebuilds
+ * its plan (supported, costs a reallocation). */
 ORBX_API int orbx_extract_batch(orbx_handle* h, int n, const uint8_t* const* imgs, int width, int height,
                        const size_t* strides, orbx_result* results);
 
