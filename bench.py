@@ -274,31 +274,54 @@ def measure_config(args, name, B, K, W, rank, world, local, full, sampler):
     stereo_dev = nimg == 2 and args.stereo_match == "device"
     need_pyr = nimg == 2 and not stereo_dev
     mbf, mb = (386.1448, 0.5371657) if name == "stereo_kitti" else (47.90639384423901, 0.11007784)   # KITTI00-02.yaml / EuRoC.yaml
-    ex = ORBextractor(nf, sf, nl, it, mt, device=local, max_batch=nimgs, download_pyramid=False)
-    stream = torch.cuda.ExternalStream(ex.stream, device=torch.device("cuda", local))
+    # Steps alternate over `--handles` extractor handles (default 2: double buffering -- the results of step k stay in HBM
+    # while step k + 1 runs, and the latency-bound tail of one step overlaps the head of the next; each handle then takes
+    # its 64-frame batch as ONE launch sequence: 1.373 -> 1.316 ms per 64 x 1080p).  --handles 1: one handle, two
+    # half-batches on two streams, every step joined before the next one starts.
+    NH = max(1, args.handles)
+    exs = [ORBextractor(nf, sf, nl, it, mt, device=local, max_batch=nimgs, download_pyramid=False,
+                        device_chunks=1 if NH > 1 else 0) for _ in range(NH)]
+    ex = exs[0]
+    tdev = torch.device("cuda", local)
+    streams = [torch.cuda.ExternalStream(e.stream, device=tdev) for e in exs]
+    stream = streams[0]
+    step_no = [0]
 
     def step_device():
-        ex.extract_device(dev.data_ptr(), nimgs, w, h, pitch, h * pitch)
+        exs[step_no[0] % NH].extract_device(dev.data_ptr(), nimgs, w, h, pitch, h * pitch)
+        step_no[0] += 1
 
-    for _ in range(W):
+    def timed_steps(n):
+        """n steps back to back; device time from the first handle's stream at the start to the last stream to finish"""
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(NH)]
+        step_no[0] = 0
+        sharding.barrier(); torch.cuda.synchronize()
+        e0.record(stream)
+        for s in streams[1:]:
+            s.wait_event(e0)
+        for _ in range(n):
+            step_device()
+        for e, s in zip(ends, streams):
+            e.record(s)
+        for e in exs:
+            e.synchronize()
+        torch.cuda.synchronize(); sharding.barrier()
+        return max(e0.elapsed_time(e) for e in ends)
+
+    for _ in range(W * NH):
         step_device()
-    ex.synchronize()
+    for e in exs:
+        e.synchronize()
     res = ex.fetch_results(nimgs)
     kp_counts = [len(k) for k, _ in res]
     cand_per_level, retries_per_level = ex.fast_stats(0)     # FAST corners handed to the quadtree / cells re-run at minThFAST, frame 0
     if min(kp_counts) == 0:
         raise SystemExit("bench: a frame produced no keypoints; refusing to time a degenerate run")
 
-    l0 = ex.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sharding.barrier(); torch.cuda.synchronize()
-    e0.record(stream)
-    for _ in range(K):
-        step_device()
-    e1.record(stream)
-    ex.synchronize(); torch.cuda.synchronize(); sharding.barrier()
-    dev_ms = e0.elapsed_time(e1)
-    launches = ex.launch_count - l0
+    l0 = sum(e.launch_count for e in exs)
+    e0 = torch.cuda.Event(enable_timing=True)
+    dev_ms = timed_steps(K)
+    launches = sum(e.launch_count for e in exs) - l0
     dev_ms_max = sharding.max_over_ranks(dev_ms)
     value = world * B * K / (dev_ms_max / 1e3)
 
@@ -310,13 +333,7 @@ def measure_config(args, name, B, K, W, rank, world, local, full, sampler):
         if s2:
             s2.start()
             time.sleep(0.3)
-        sharding.barrier(); torch.cuda.synchronize()
-        e0.record(stream)
-        for _ in range(Ks):
-            step_device()
-        e1.record(stream)
-        ex.synchronize(); torch.cuda.synchronize(); sharding.barrier()
-        sus_ms = sharding.max_over_ranks(e0.elapsed_time(e1))
+        sus_ms = sharding.max_over_ranks(timed_steps(Ks))
         sustained = {"value": world * B * Ks / (sus_ms / 1e3), "unit": UNIT, "steps": Ks, "seconds": sus_ms / 1e3,
                      "ms_per_step": sus_ms / Ks, "clocks": s2.stop() if s2 else None}
 
@@ -324,10 +341,12 @@ def measure_config(args, name, B, K, W, rank, world, local, full, sampler):
     # FAST / pyramid overlap of the timed pass): the per-kernel durations behind the roofline table
     ex.stage_timing(True)
     for _ in range(K):
-        step_device()
+        ex.extract_device(dev.data_ptr(), nimgs, w, h, pitch, h * pitch)
     ex.synchronize()
     stages = ex.stage_times()
     ex.stage_timing(False)
+    for e in exs[1:]:
+        e.close()
 
     # ---- what the host side of the box can feed: pinned -> device copies of the step's input, no kernels, all ranks at once
     chunks = 4 if B >= 16 else (2 if B >= 4 else 1)
@@ -557,6 +576,9 @@ def own_arm(args):
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_desc(name), "batch_per_gpu": B, "frames_per_step": world * B,
                        "distinct_frames": DISTINCT_FRAMES, "parallelism": "one camera stream per GPU, no collective",
+                       "device_steps": ("steps alternate over %d handles (double buffering: a step's tail overlaps the next step's head); every step is one "
+                                        "orbx_extract_device call on the whole batch" % args.handles) if args.handles > 1 else
+                                       "one handle, two half-batches on two streams, every step joined before the next starts",
                        "l2_policy": "per-step working set (inputs %.0f MB + pyramids %.0f MB per GPU) exceeds the 126 MB L2" % (
                            m["in_mb"], m["pyr_mb"]),
                        "keypoints_per_image": m["n_out"], "fast_candidates_per_level_frame0": m["cand"],
@@ -580,6 +602,7 @@ def main():
     ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
     ap.add_argument("--config", default="rgbd_1080p", choices=list(fr.CONFIGS))
     ap.add_argument("--batch", type=int, default=64, help="frames per step per GPU (1080p: 32 -> 37.2k, 64 -> 39.4k, 128 -> 40.2k, 256 -> 40.7k frames/s)")
+    ap.add_argument("--handles", type=int, default=2, help="extractor handles the device-resident steps alternate over (2 = double buffering; 1 = one handle, every step joined before the next)")
     ap.add_argument("--latency-frames", type=int, default=1000, help="single-frame calls timed for p50/p99 (SURVEY §8d: >= 1000)")
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads (one handle each) in the e2e measurement; 0 = auto: min(4, cores / (2 * ranks))")
     ap.add_argument("--no-numa-bind", dest="numa_bind", action="store_false", help="leave the rank's threads where the scheduler puts them")

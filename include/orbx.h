@@ -60,7 +60,10 @@ typedef struct orbx_config {
                           /*    public mvImagePyramid contract requires (read by src/Frame.cc:563-580); */
                           /* 0: leave it in HBM (monocular / RGB-D callers never read it)               */
     int candidate_divisor;/* per-level candidate capacity = level_pixels / divisor + 1024 (0 -> 8)      */
-    int reserved[7];
+    int device_chunks;    /* orbx_extract_device: sub-batches run on concurrent kernel streams (0 -> 2; 1..4).  */
+                          /* 1 when several handles are driven back to back (double buffering): their launch  */
+                          /* sequences already overlap, and whole batches make the larger launches            */
+    int reserved[6];
 } orbx_config;
 
 /* Same field order and size (28 bytes) as cv::KeyPoint. */

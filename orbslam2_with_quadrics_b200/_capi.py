@@ -40,7 +40,7 @@ class OrbxConfig(C.Structure):
     _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int),
                 ("ini_th_fast", C.c_int), ("min_th_fast", C.c_int), ("device", C.c_int),
                 ("max_batch", C.c_int), ("download_pyramid", C.c_int), ("candidate_divisor", C.c_int),
-                ("reserved", C.c_int * 7)]
+                ("device_chunks", C.c_int), ("reserved", C.c_int * 6)]
 
 
 class OrbxResult(C.Structure):

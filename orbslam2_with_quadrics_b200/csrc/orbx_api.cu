@@ -714,7 +714,7 @@ int enqueue_pipeline(orbx_handle* h, int n, const uint8_t* d_imgs, size_t pitch,
     // descriptors) overlaps the issue-bound head (pyramid, FAST) of the other.  With per-stage timing on, one
     // stream runs everything so each kernel's duration is its own.
     const char* e_ch = getenv("ORBX_DEVICE_CHUNKS");          // tuning override
-    int nchunks = (!h->timing && n >= 8) ? (e_ch ? atoi(e_ch) : 2) : 1;
+    int nchunks = (!h->timing && n >= 8) ? (e_ch ? atoi(e_ch) : h->cfg.device_chunks > 0 ? h->cfg.device_chunks : 2) : 1;
     if (nchunks < 1) nchunks = 1;
     if (nchunks > kMaxChunks) nchunks = kMaxChunks;
     if (nchunks > n) nchunks = n;

@@ -98,44 +98,93 @@ __device__ __forceinline__ const uint8_t* level_px(const uint8_t* slab, const Or
 // row costs ~1.2 row passes; the column pass is two IMAD.HI per pixel.
 // =====================================================================================
 // One work item = 32 x 8 threads' worth of level 0 (32 lanes x 16 bytes wide, 8 plane rows); (tx, ty) = the thread's place in it.
+// A 16-byte vector is "interior" when it is a plain (re-aligned) copy of source bytes; the few vectors per row that touch the
+// reflected border are byte gathers (~200 instructions), and a warp that holds one of them pays for it with all 32 lanes.
+// They are therefore left out here and given to pyr_level0_border_item, where every lane of a warp is such a vector
+// (lane = (row, border vector)): 20.5 M -> 7 M warp instructions per 32 x 1080p.
+struct Lv0Cols { int lo, hiv, nL, cR, nb; };
+__host__ __device__ __forceinline__ Lv0Cols pyr_level0_cols(int w, int aligned16) {
+    Lv0Cols c;
+    c.lo = aligned16 ? 0 : 16;                                     // interior: lo <= dx0 <= hiv (dx0 = source x of byte 0, multiple of 16)
+    c.hiv = aligned16 ? w - 16 : w - 20;
+    c.nL = (ORBX_XO + c.lo) / 16;                                  // border vectors left of the interior
+    c.cR = c.hiv >= c.lo ? ORBX_XO + (c.hiv / 16 + 1) * 16 : ORBX_XO + c.lo;      // first plane column right of it
+    const int ncols16 = (ORBX_XO + w + ORBX_EDGE + 15) / 16;
+    c.nb = c.nL + max(ncols16 - c.cR / 16, 0);
+    return c;
+}
+
+// (a thread copies its vector of PYR_L0_ROWS plane rows, 8 rows apart: all loads are issued before the first store --
+// the copy is bound by bytes in flight, not by instructions)
+#define PYR_L0_ROWS 4
 __device__ __forceinline__ void pyr_level0_item(const OrbxPlan* __restrict__ plan, const uint8_t* __restrict__ imgs, size_t img_pitch,
                                                 size_t img_frame_stride, int aligned16, uint8_t* pyr, int bx, int by, int frame,
                                                 int tx, int ty) {
     const OrbxLevel& L = plan->lv[0];
     const int w = L.w, h = L.h;
     const int c = (bx * 32 + tx) * 16;                             // plane column, multiple of 16 (XO is too)
-    const int row = by * 8 + ty;                                   // plane row
-    if (row >= L.rows || c >= ORBX_XO + w + ORBX_EDGE) return;
-    const int dy = reflect_clamp(row - ORBX_EDGE, h);
-    const uint8_t* src = imgs + (size_t)frame * img_frame_stride + (size_t)dy * img_pitch;
+    const int row0 = by * (8 * PYR_L0_ROWS) + ty;                  // first plane row
     const int dx0 = c - ORBX_XO;
-    uint4 out;
-    if (aligned16 && dx0 >= 0 && dx0 + 15 < w) {
-        out = __ldg(reinterpret_cast<const uint4*>(src + dx0));
-    } else if (dx0 >= 16 && dx0 + 20 <= w) {
+    const Lv0Cols lc = pyr_level0_cols(w, aligned16);
+    if (row0 >= L.rows || dx0 < lc.lo || dx0 > lc.hiv) return;     // border vectors: pyr_level0_border_item
+    const uint8_t* src0 = imgs + (size_t)frame * img_frame_stride + dx0;
+    uint4 out[PYR_L0_ROWS];
+    if (aligned16) {
+#pragma unroll
+        for (int k = 0; k < PYR_L0_ROWS; ++k) {
+            const int dy = reflect_clamp(min(row0 + 8 * k, L.rows - 1) - ORBX_EDGE, h);
+            out[k] = __ldg(reinterpret_cast<const uint4*>(src0 + (size_t)dy * img_pitch));
+        }
+    } else {
         // source rows of arbitrary alignment (e.g. a 1241-byte stride): five aligned words, re-aligned with funnel
         // shifts; the reads stay inside this image row
-        const uint8_t* ps = src + dx0;
-        const int a = (int)(reinterpret_cast<uintptr_t>(ps) & 3);
-        const uint32_t* wp = reinterpret_cast<const uint32_t*>(ps - a);
-        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
-        out = make_uint4(__funnelshift_r(w0, w1, 8 * a), __funnelshift_r(w1, w2, 8 * a), __funnelshift_r(w2, w3, 8 * a),
-                         __funnelshift_r(w3, w4, 8 * a));
-    } else {
-        uint32_t o[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o[i >> 2] |= (uint32_t)__ldg(src + reflect_clamp(dx0 + i, w)) << (8 * (i & 3));
-        out = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int k = 0; k < PYR_L0_ROWS; ++k) {
+            const int dy = reflect_clamp(min(row0 + 8 * k, L.rows - 1) - ORBX_EDGE, h);
+            const uint8_t* ps = src0 + (size_t)dy * img_pitch;
+            const int a = (int)(reinterpret_cast<uintptr_t>(ps) & 3);
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(ps - a);
+            const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
+            out[k] = make_uint4(__funnelshift_r(w0, w1, 8 * a), __funnelshift_r(w1, w2, 8 * a), __funnelshift_r(w2, w3, 8 * a),
+                                __funnelshift_r(w3, w4, 8 * a));
+        }
     }
-    *reinterpret_cast<uint4*>(pyr + (size_t)frame * plan->slab_bytes + L.plane_off + (size_t)row * L.pitch + c) = out;
+    uint8_t* dst = pyr + (size_t)frame * plan->slab_bytes + L.plane_off + (size_t)row0 * L.pitch + c;
+#pragma unroll
+    for (int k = 0; k < PYR_L0_ROWS; ++k)
+        if (row0 + 8 * k < L.rows) *reinterpret_cast<uint4*>(dst + (size_t)(8 * k) * L.pitch) = out[k];
 }
 
+// item = 256 (plane row, border vector) pairs
+__device__ __forceinline__ void pyr_level0_border_item(const OrbxPlan* __restrict__ plan, const uint8_t* __restrict__ imgs, size_t img_pitch,
+                                                       size_t img_frame_stride, int aligned16, uint8_t* pyr, int item, int frame, int tid) {
+    const OrbxLevel& L = plan->lv[0];
+    const int w = L.w, h = L.h;
+    const Lv0Cols lc = pyr_level0_cols(w, aligned16);
+    const int p = item * 256 + tid;
+    const int row = p / lc.nb, j = p - row * lc.nb;
+    if (row >= L.rows) return;
+    const int c = j < lc.nL ? 16 * j : lc.cR + 16 * (j - lc.nL);
+    const int dx0 = c - ORBX_XO;
+    const int dy = reflect_clamp(row - ORBX_EDGE, h);
+    const uint8_t* src = imgs + (size_t)frame * img_frame_stride + (size_t)dy * img_pitch;
+    uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i >> 2] |= (uint32_t)__ldg(src + reflect_clamp(dx0 + i, w)) << (8 * (i & 3));
+    *reinterpret_cast<uint4*>(pyr + (size_t)frame * plan->slab_bytes + L.plane_off + (size_t)row * L.pitch + c) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// grid (gx, gy_main + gy_border, frames): block rows below gy_main copy the interior, the rest take the border vectors
 __global__ void __launch_bounds__(256) pyr_level0_kernel(const OrbxPlan* __restrict__ plan,
                                                          const uint8_t* __restrict__ imgs, size_t img_pitch,
                                                          size_t img_frame_stride, int aligned16,
-                                                         uint8_t* __restrict__ pyr) {
+                                                         uint8_t* __restrict__ pyr, int gy_main) {
     ORBX_PDL_WAIT();
-    pyr_level0_item(plan, imgs, img_pitch, img_frame_stride, aligned16, pyr, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, threadIdx.y);
+    if ((int)blockIdx.y < gy_main)
+        pyr_level0_item(plan, imgs, img_pitch, img_frame_stride, aligned16, pyr, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, threadIdx.y);
+    else
+        pyr_level0_border_item(plan, imgs, img_pitch, img_frame_stride, aligned16, pyr,
+                               ((int)blockIdx.y - gy_main) * (int)gridDim.x + (int)blockIdx.x, blockIdx.z, threadIdx.y * 32 + threadIdx.x);
 }
 
 // =====================================================================================
@@ -993,6 +1042,9 @@ __device__ __forceinline__ uint32_t fast_pretest_word(const uint32_t* __restrict
     // bit 7 of a byte of ((a & 0x7f) + C) | a  <=>  a > t
     const uint32_t s0 = (a0 & 0x7f7f7f7fu) + C, s8 = (a8 & 0x7f7f7f7fu) + C;
     const uint32_t s4 = (a4 & 0x7f7f7f7fu) + C, s12 = (a12 & 0x7f7f7f7fu) + C;
+    // (a third and fourth opposite pair -- the diagonals 2/10 and 6/14, tested as (a | a') > t with the rows reused across
+    // the 8-row group -- drops the survivors of the bench scene from 15.9 % to 11.7 % of the pixels but costs as much as it
+    // saves: FAST 0.774 -> 0.763 ms per 64 x 1080p, the whole step unchanged at 1.372 ms; not kept)
     return ((s0 | a0) | (s8 | a8)) & ((s4 | a4) | (s12 | a12)) & colmask;
 }
 
@@ -3298,7 +3350,7 @@ static PyrGeom pyr_geometry(const OrbxPlan& hp, int l, int nframes, int num_sms)
     PyrGeom g;
     if (l == 0) {
         const int cols16 = (ORBX_XO + L.w + ORBX_EDGE + 15) / 16;          // 16-byte chunks from plane column 0
-        g.gx = (cols16 + 31) / 32; g.gy = (L.rows + 7) / 8; g.ry = 0; g.kind = 0;
+        g.gx = (cols16 + 31) / 32; g.gy = (L.rows + 8 * PYR_L0_ROWS - 1) / (8 * PYR_L0_ROWS); g.ry = 0; g.kind = 0;
     } else if (L.resize8_ok && !force_resize4()) {
         g.gx = (L.ngroups8 + 31) / 32;
         static const int min_ry = getenv("ORBX_PYR_MINRY") ? atoi(getenv("ORBX_PYR_MINRY")) : 2;      // 2: single 640x480 frame 50 -> 38 us
@@ -3324,7 +3376,10 @@ void launch_pyr_level(const OrbxPlan* d_plan, const OrbxPlan& hp, int l, int nfr
     static const int min_tile_ry = getenv("ORBX_PYR_TILE_MINRY") ? atoi(getenv("ORBX_PYR_TILE_MINRY")) : 8;   // strips shorter than this keep pyr_resize8_kernel (measured: 64 x 1080p 1.425 -> 1.378 ms with 8, 1.376 with 4; 64 x 640x480 0.438 / 0.439 / 0.446 ms without / 8 / 4; 2-row strips = 1024-thread CTAs, a single 1080p frame 0.120 vs 0.098 ms)
     if (g.kind == 0) {
         const int aligned16 = ((reinterpret_cast<uintptr_t>(imgs) | img_pitch | img_frame_stride) & 15) == 0;
-        launch_k(pyr_level0_kernel, dim3(g.gx, g.gy, nframes), dim3(32, 8), 0, st, d_plan, imgs, img_pitch, img_frame_stride, aligned16, pyr);
+        const Lv0Cols lc = pyr_level0_cols(hp.lv[0].w, aligned16);
+        const int border_items = (hp.lv[0].rows * lc.nb + 255) / 256;                 // 256 (row, border vector) pairs each
+        const int gy_border = (border_items + g.gx - 1) / g.gx;
+        launch_k(pyr_level0_kernel, dim3(g.gx, g.gy + gy_border, nframes), dim3(32, 8), 0, st, d_plan, imgs, img_pitch, img_frame_stride, aligned16, pyr, g.gy);
     } else if (g.kind == 1 && g.ry >= min_tile_ry && g.ry <= 16 && hp.lv[l].resize_tile_ok && tile_maps && !no_tile) {
         const CUtensorMap& m = reinterpret_cast<const FastMaps*>(tile_maps)->m[l - 1];
         const dim3 grid(g.gx, (hp.lv[l].rows + 63) / 64, nframes);

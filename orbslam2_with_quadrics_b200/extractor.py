@@ -20,11 +20,12 @@ class ORBextractor:
     FAST_SCORE = 1
 
     def __init__(self, nfeatures: int, scaleFactor: float, nlevels: int, iniThFAST: int, minThFAST: int,
-                 device: int = 0, max_batch: int = 1, download_pyramid: bool = True, candidate_divisor: int = 0):
+                 device: int = 0, max_batch: int = 1, download_pyramid: bool = True, candidate_divisor: int = 0,
+                 device_chunks: int = 0):
         self._L = lib()
         self._h = C.c_void_p()
         cfg = OrbxConfig(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device, max_batch,
-                         1 if download_pyramid else 0, candidate_divisor)
+                         1 if download_pyramid else 0, candidate_divisor, device_chunks)
         check(self._L.orbx_create(C.byref(cfg), C.byref(self._h)))
         self.nfeatures, self.nlevels, self.max_batch = nfeatures, nlevels, max_batch
         self.download_pyramid = bool(download_pyramid)
