@@ -226,6 +226,39 @@ ORBX_API int orbx_search_local_points(orbx_handle* h, int nqueries, const orbx_l
 ORBX_API int orbx_search_local_points_device(orbx_handle* h, int nqueries, const orbx_local_points_query* queries, float th,
                                              float nnratio, int use_stereo);
 
+/* ---- Frame::isInFrustum(MapPoint* pMP, float viewingCosLimit) (reference src/Frame.cc:269-325) with MapPoint::PredictScale(dist,
+ * Frame*) and GetMin/MaxDistanceInvariance (src/MapPoint.cc:402-417, :373-383): the loop of Tracking::SearchLocalPoints
+ * (src/Tracking.cc:1165-1178, viewingCosLimit 0.5) that leaves the tracking fields on every local map point, i.e. the producer of
+ * orbx_local_points_query's in_view / proj_xy_xr / scale_level / view_cos -- the result arrays can be handed to
+ * orbx_search_local_points as they are.  A query is one Frame pose and its list of map points; nothing of the handle's extraction
+ * state is read (only its device, stream and nlevels), so the call may precede the frame's extraction.
+ *   consider[i] = 0: the point is not handed to isInFrustum (already seen in this frame, src/Tracking.cc:1169, or isBad(), :1171);
+ *                    its in_view is 0.
+ *   bounds = {mnMinX, mnMaxX, mnMinY, mnMaxY} (orbx_grid_result.bounds), log_scale_factor = Frame::mfLogScaleFactor.
+ * PredictScale goes through the host libm's logf; the library evaluates it with the calling process's own logf (per level, the
+ * smallest ratio that reaches it) and the device only compares, so the levels are the reference's bit for bit.
+ * Result arrays: pinned host memory owned by the handle, valid until its next orbx_is_in_frustum call; fields of points that are
+ * not in view are 0. */
+typedef struct orbx_frustum_query {
+    int n_points;              /* mvpLocalMapPoints.size() */
+    const uint8_t* consider;   /* n: see above; NULL = all */
+    const float* world_pos;    /* n x 3: pMP->GetWorldPos() */
+    const float* normal;       /* n x 3: pMP->GetNormal() */
+    const float* min_dist;     /* n: mfMinDistance (GetMinDistanceInvariance()'s 0.8f is applied by the library) */
+    const float* max_dist;     /* n: mfMaxDistance (likewise 1.2f; PredictScale reads the raw value) */
+    float Tcw[16];             /* Frame::mTcw, row-major 4 x 4 */
+} orbx_frustum_query;
+typedef struct orbx_frustum_result {
+    int n;                     /* = n_points */
+    int n_in_view;             /* nToMatch of Tracking::SearchLocalPoints */
+    const uint8_t* in_view;    /* n: mbTrackInView */
+    const float* proj_xy_xr;   /* n x 3: mTrackProjX, mTrackProjY, mTrackProjXR */
+    const int32_t* scale_level;/* n: mnTrackScaleLevel */
+    const float* view_cos;     /* n: mTrackViewCos */
+} orbx_frustum_result;
+ORBX_API int orbx_is_in_frustum(orbx_handle* h, int nqueries, const orbx_frustum_query* queries, const float* K4, float mbf,
+                                const float* bounds, float log_scale_factor, float viewing_cos_limit, orbx_frustum_result* results);
+
 /* ---- ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist)
  * (reference src/ORBmatcher.cc:1472-1599): the projection matcher of Tracking::Relocalization (src/Tracking.cc:1452 with th 10 /
  * ORBdist 100, :1466 with th 3 / ORBdist 64, ORBmatcher(0.9, true)).  The frame side is the handle's device-resident state

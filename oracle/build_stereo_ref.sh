@@ -2,7 +2,7 @@
 # Builds oracle/_ref/libstereoref.so: the reference's OWN lines of Frame::ComputeStereoMatches,
 # ORBmatcher::DescriptorDistance, the Frame undistort/grid functions, Frame::GetFeaturesInArea and
 # ORBmatcher::SearchByProjection(Frame&, const Frame&) / ComputeThreeMaxima, SearchByProjection(Frame&, vpMapPoints), SearchByBoW(KeyFrame*,
-# Frame&), SearchForInitialization, SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) and MapPoint::PredictScale, taken at build time from where they lie under $REF (never copied into this
+# Frame&), SearchForInitialization, SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist), MapPoint::PredictScale and Frame::isInFrustum, taken at build time from where they lie under $REF (never copied into this
 # repo: the generated translation unit lives in a temporary directory and only the .so is kept), compiled against
 # oracle/shim_stereo/stereo_shim.h.  TEST INFRASTRUCTURE only.
 set -e
@@ -36,6 +36,8 @@ sed -n '1599p' "$M" | grep -q '^}' || { echo "ORBmatcher.cc:1599 is not the end 
 sed -n '373p' "$P" | grep -q 'float MapPoint::GetMinDistanceInvariance' || { echo "MapPoint.cc:373 is not GetMinDistanceInvariance"; exit 1; }
 sed -n '402p' "$P" | grep -q 'int MapPoint::PredictScale(const float &currentDist, Frame\* pF)' || { echo "MapPoint.cc:402 is not PredictScale(dist, Frame*)"; exit 1; }
 sed -n '417p' "$P" | grep -q '^}' || { echo "MapPoint.cc:417 is not the end of PredictScale"; exit 1; }
+sed -n '269p' "$F" | grep -q 'bool Frame::isInFrustum(MapPoint \*pMP, float viewingCosLimit)' || { echo "Frame.cc:269 is not isInFrustum"; exit 1; }
+sed -n '325p' "$F" | grep -q '^}' || { echo "Frame.cc:325 is not the end of isInFrustum"; exit 1; }
 TMP=$(mktemp -d)
 trap 'rm -rf "$TMP"' EXIT
 {
@@ -57,6 +59,7 @@ trap 'rm -rf "$TMP"' EXIT
   sed -n '1472,1599p' "$M"
   sed -n '373,383p' "$P"
   sed -n '402,417p' "$P"
+  sed -n '269,325p' "$F"
   echo '}'
 } > "$TMP/stereo_ref_gen.cpp"
 mkdir -p "$OUT"

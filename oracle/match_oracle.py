@@ -616,3 +616,93 @@ def ref_search_for_initialization(xy_un1, octave1, angle1, desc1, prev_matched, 
                                              p(a[4]), p(a[5]), C.c_int(len(a[5])), C.c_float(nnratio), C.c_int(int(check_orientation)),
                                              C.c_int(int(window)), p(out))
     return int(n), out, prev
+
+
+# ============================================================================= Frame::isInFrustum (the producer of SearchLocalPoints' inputs)
+def predict_scale(max_dist, dist, log_scale_factor, nlevels) -> int:
+    """MapPoint::PredictScale(currentDist, Frame*) (src/MapPoint.cc:402-417): ratio = mfMaxDistance / dist in float,
+    ceil(logf(ratio) / mfLogScaleFactor), clamped to [0, nlevels - 1].  A non-finite quotient (the reference then converts
+    inf / NaN to int, which is undefined; x86 yields INT_MIN -> 0) gives level 0."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = f32(f32(max_dist) / f32(dist))
+        q = f32(_logf(ratio) / f32(log_scale_factor))
+    ns = int(math.ceil(float(q))) if np.isfinite(q) else 0
+    return 0 if ns < 0 else (nlevels - 1 if ns >= nlevels else ns)
+
+
+def is_in_frustum(consider, world, normal, min_dist, max_dist, Tcw, K4, mbf, bounds, log_scale_factor, nlevels, cos_limit=0.5):
+    """Frame::isInFrustum(MapPoint*, viewingCosLimit) (src/Frame.cc:269-325) over a list of map points, with the pose split of
+    Frame::UpdatePoseMatrices (:260-267: mRcw, mtcw, mOw = -mRcw.t() * mtcw).  consider[i] = 0: the point is not handed to
+    isInFrustum at all (Tracking::SearchLocalPoints skips points already seen in the frame and bad points, src/Tracking.cc:1169-1172)
+    and its mbTrackInView stays false.  The matrix products and the norm are the REAL OpenCV (cv2.gemm, cv2.norm); Mat::dot has no
+    Python binding and is restated from OpenCV's published dotProd_32f (modules/core/src/matmul.simd.hpp: for 3 elements no SIMD
+    block is reached and the tail adds the float products, exact in double, to a double accumulator in element order).
+    Returns (in_view uint8[n], proj float32[n, 3] = (mTrackProjX, mTrackProjY, mTrackProjXR), scale_level int32[n], view_cos float32[n])."""
+    import cv2
+    n = len(world)
+    T = np.asarray(Tcw, f32).reshape(4, 4)
+    Rcw, tcw = T[:3, :3], T[:3, 3:4]
+    Ow = _gemm(Rcw, tcw, None, -1.0, cv2.GEMM_1_T)                             # (:266)
+    fx, fy, cx, cy = [f32(v) for v in K4]
+    minx, maxx, miny, maxy = [f32(v) for v in bounds]
+    W = np.asarray(world, f32).reshape(n, 3)
+    Nn = np.asarray(normal, f32).reshape(n, 3)
+    in_view = np.zeros(n, np.uint8)
+    proj = np.zeros((n, 3), f32)
+    level = np.zeros(n, np.int32)
+    vcos = np.zeros(n, f32)
+    for i in range(n):
+        if consider is not None and not consider[i]:
+            continue
+        P = W[i].reshape(3, 1)
+        Pc = _gemm(Rcw, P, tcw)                                                # mRcw*P+mtcw (:277)
+        pcx, pcy, pcz = f32(Pc[0, 0]), f32(Pc[1, 0]), f32(Pc[2, 0])
+        if pcz < f32(0.0):                                                     # (:283)
+            continue
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            invz = f32(f32(1.0) / pcz)                                         # (:287)
+            u = f32(f32(f32(fx * pcx) * invz) + cx)
+            v = f32(f32(f32(fy * pcy) * invz) + cy)
+        if u < minx or u > maxx or v < miny or v > maxy:                       # (:291-294)
+            continue
+        maxd = f32(f32(1.2) * f32(max_dist[i]))                                # GetMaxDistanceInvariance (src/MapPoint.cc:379-383)
+        mind = f32(f32(0.8) * f32(min_dist[i]))
+        PO = (P - Ow).astype(f32)
+        dist = f32(cv2.norm(PO))                                               # (:300)
+        if dist < mind or dist > maxd:
+            continue
+        dot = float(np.float64(PO[0, 0]) * np.float64(Nn[i, 0]))               # Mat::dot: float products accumulated in double
+        dot = float(np.float64(dot) + np.float64(PO[1, 0]) * np.float64(Nn[i, 1]))
+        dot = float(np.float64(dot) + np.float64(PO[2, 0]) * np.float64(Nn[i, 2]))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            vc = f32(np.float64(dot) / np.float64(dist))                       # (:308) double / float -> double -> float
+        if vc < f32(cos_limit):
+            continue
+        level[i] = predict_scale(max_dist[i], dist, log_scale_factor, nlevels)
+        in_view[i] = 1
+        proj[i, 0] = u
+        with np.errstate(over="ignore", invalid="ignore"):
+            proj[i, 2] = f32(u - f32(f32(mbf) * invz))                         # (:319)
+        proj[i, 1] = v
+        vcos[i] = vc
+    return in_view, proj, level, vcos
+
+
+def ref_is_in_frustum(consider, world, normal, min_dist, max_dist, Tcw, K4, mbf, bounds, log_scale_factor, nlevels, cos_limit=0.5):
+    """Same call shape, executed by the reference's own lines of Frame::isInFrustum and MapPoint::PredictScale
+    (oracle/_ref/libstereoref.so)."""
+    r = _load_ref()
+    n = len(world)
+    cons = np.ones(n, np.uint8) if consider is None else np.ascontiguousarray(consider, np.uint8)
+    a = [cons, np.ascontiguousarray(world, f32), np.ascontiguousarray(normal, f32), np.ascontiguousarray(min_dist, f32),
+         np.ascontiguousarray(max_dist, f32), np.ascontiguousarray(Tcw, f32).reshape(16), np.ascontiguousarray(K4, f32),
+         np.ascontiguousarray(bounds, f32)]
+    in_view = np.zeros(n, np.uint8)
+    proj = np.zeros((n, 3), f32)
+    level = np.zeros(n, np.int32)
+    vcos = np.zeros(n, f32)
+    p = lambda x: C.c_void_p(x.ctypes.data)
+    r.matchref_is_in_frustum.restype = C.c_int
+    r.matchref_is_in_frustum(C.c_int(n), *[p(x) for x in a], C.c_float(mbf), C.c_float(log_scale_factor), C.c_int(nlevels),
+                             C.c_float(cos_limit), p(in_view), p(proj), p(level), p(vcos))
+    return in_view, proj, level, vcos

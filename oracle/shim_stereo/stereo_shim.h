@@ -8,7 +8,8 @@
 // (ORBmatcher.cc:1328-1470, :1601-1642) and ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) /
 // RadiusByViewingCos (ORBmatcher.cc:45-129, :131-137), ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (ORBmatcher.cc:159-288),
 // ORBmatcher::SearchForInitialization (ORBmatcher.cc:405-520), ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th,
-// ORBdist) (ORBmatcher.cc:1472-1599) and MapPoint::GetMin/MaxDistanceInvariance / PredictScale(dist, Frame*) (MapPoint.cc:373-383, :402-417),
+// ORBdist) (ORBmatcher.cc:1472-1599), MapPoint::GetMin/MaxDistanceInvariance / PredictScale(dist, Frame*) (MapPoint.cc:373-383, :402-417)
+// and Frame::isInFrustum (Frame.cc:269-325),
 // taken from where they lie at
 // build time, against this header: the handful of cv:: types those lines use (8U / 32F Mat views, convertTo, ones, scalar * Mat,
 // Mat - Mat, norm L1) and the members of Frame / ORBextractor / ORBmatcher they touch.  Written from scratch.
@@ -94,6 +95,14 @@ public:
         dst = out;
     }
     Mat reshape(int cn) const { (void)cn; return *this; }      // N x 2 floats either way (Frame.cc:421-423, :449-451)
+    // Mat::dot of two CV_32F vectors (Frame.cc:308): OpenCV's dotProd_32f accumulates the float products in double (for 3
+    // elements no SIMD block is reached; the float products are exact in double)
+    double dot(const Mat& o) const {
+        double r = 0;
+        for (int i = 0; i < rows; ++i)
+            for (int j = 0; j < cols; ++j) r += (double)at<float>(i, j) * (double)o.at<float>(i, j);
+        return r;
+    }
     static Mat ones(int r, int c, int d) {
         Mat m(r, c, d);
         for (int i = 0; i < r; ++i)
@@ -209,7 +218,7 @@ class Frame;
 class KeyFrame;
 
 struct MapPoint {                     // the accessors and tracking fields ORBmatcher.cc:45-129, :1328-1470, :1472-1599 touch
-    cv::Mat mWorldPos, mDescriptor;
+    cv::Mat mWorldPos, mDescriptor, mNormalVector;
     int nObs;
     bool mbTrackInView, mbBad;        // include/MapPoint.h:92-97
     float mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos;
@@ -218,13 +227,14 @@ struct MapPoint {                     // the accessors and tracking fields ORBma
     std::mutex mMutexPos;
     MapPoint() : nObs(0), mbTrackInView(false), mbBad(false), mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), mTrackViewCos(0),
                  mnTrackScaleLevel(0), mfMinDistance(0), mfMaxDistance(0) {}
-    MapPoint(const MapPoint& o) : mWorldPos(o.mWorldPos), mDescriptor(o.mDescriptor), nObs(o.nObs), mbTrackInView(o.mbTrackInView),
+    MapPoint(const MapPoint& o) : mWorldPos(o.mWorldPos), mDescriptor(o.mDescriptor), mNormalVector(o.mNormalVector), nObs(o.nObs), mbTrackInView(o.mbTrackInView),
                                   mbBad(o.mbBad), mTrackProjX(o.mTrackProjX), mTrackProjY(o.mTrackProjY), mTrackProjXR(o.mTrackProjXR),
                                   mTrackViewCos(o.mTrackViewCos), mnTrackScaleLevel(o.mnTrackScaleLevel),
                                   mfMinDistance(o.mfMinDistance), mfMaxDistance(o.mfMaxDistance) {}
     bool isBad() { return mbBad; }
     cv::Mat GetWorldPos() { return mWorldPos; }
     cv::Mat GetDescriptor() { return mDescriptor; }
+    cv::Mat GetNormal() { return mNormalVector; }
     int Observations() { return nObs; }
     float GetMinDistanceInvariance();                       // the reference's own lines (MapPoint.cc:373-383, :402-417)
     float GetMaxDistanceInvariance();
@@ -262,6 +272,8 @@ public:
     bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
     void UndistortKeyPoints();
     void ComputeImageBounds(const cv::Mat& imLeft);
+    bool isInFrustum(MapPoint* pMP, float viewingCosLimit);                        // include/Frame.h:83
+    cv::Mat mRcw, mtcw, mOw;                                                       // include/Frame.h:199-202 (UpdatePoseMatrices)
     vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1,
                                      const int maxLevel = -1) const;               // include/Frame.h:92
     static float fx, fy, cx, cy;

@@ -364,3 +364,44 @@ extern "C" int matchref_search_for_initialization(int n1, const float* kp1_un, c
     for (int i = 0; i < n1; ++i) { matches12[i] = m12[i]; prev_matched[2 * i] = prev[i].x; prev_matched[2 * i + 1] = prev[i].y; }
     return nmatches;
 }
+
+// Frame::isInFrustum(MapPoint*, viewingCosLimit) (src/Frame.cc:269-325, called per local map point by Tracking::SearchLocalPoints,
+// src/Tracking.cc:1165-1178) with MapPoint::PredictScale, the reference's own lines.  The pose split is Frame::UpdatePoseMatrices'
+// (src/Frame.cc:260-267: mRcw, mtcw, mOw = -mRcw.t() * mtcw).  consider[i] = 0: the point is not handed to isInFrustum.
+// Outputs per point: mbTrackInView, (mTrackProjX, mTrackProjY, mTrackProjXR), mnTrackScaleLevel, mTrackViewCos (0 where not in view).
+extern "C" int matchref_is_in_frustum(int nP, const unsigned char* consider, const float* world, const float* normal,
+                                      const float* min_dist, const float* max_dist, const float* Tcw, const float* K4,
+                                      const float* bounds, float mbf, float log_scale_factor, int nlevels, float cos_limit,
+                                      unsigned char* in_view, float* proj, int* level, float* view_cos) {
+    using namespace ORB_SLAM2;
+    Frame F;
+    F.mTcw = cv::Mat(4, 4, CV_32F);
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) F.mTcw.at<float>(r, c) = Tcw[4 * r + c];
+    F.mRcw = F.mTcw.rowRange(0, 3).colRange(0, 3);
+    F.mtcw = F.mTcw.rowRange(0, 3).col(3);
+    F.mOw = -F.mRcw.t() * F.mtcw;
+    Frame::fx = K4[0]; Frame::fy = K4[1]; Frame::cx = K4[2]; Frame::cy = K4[3];
+    Frame::mnMinX = bounds[0]; Frame::mnMaxX = bounds[1]; Frame::mnMinY = bounds[2]; Frame::mnMaxY = bounds[3];
+    F.mbf = mbf;
+    F.mfLogScaleFactor = log_scale_factor;
+    F.mnScaleLevels = nlevels;
+    int n_in = 0;
+    for (int i = 0; i < nP; ++i) {
+        in_view[i] = 0; level[i] = 0; view_cos[i] = 0.f;
+        proj[3 * i] = proj[3 * i + 1] = proj[3 * i + 2] = 0.f;
+        if (!consider[i]) continue;
+        MapPoint mp;
+        mp.mWorldPos = cv::Mat(3, 1, CV_32F);
+        mp.mNormalVector = cv::Mat(3, 1, CV_32F);
+        for (int k = 0; k < 3; ++k) { mp.mWorldPos.at<float>(k, 0) = world[3 * i + k]; mp.mNormalVector.at<float>(k, 0) = normal[3 * i + k]; }
+        mp.mfMinDistance = min_dist[i];
+        mp.mfMaxDistance = max_dist[i];
+        if (F.isInFrustum(&mp, cos_limit)) {
+            in_view[i] = 1; ++n_in;
+            proj[3 * i] = mp.mTrackProjX; proj[3 * i + 1] = mp.mTrackProjY; proj[3 * i + 2] = mp.mTrackProjXR;
+            level[i] = mp.mnTrackScaleLevel;
+            view_cos[i] = mp.mTrackViewCos;
+        }
+    }
+    return n_in;
+}

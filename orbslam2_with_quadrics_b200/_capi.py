@@ -28,7 +28,7 @@ SYMBOLS = [
     "orbx_search_local_points", "orbx_search_local_points_device",
     "orbx_search_by_projection_kf", "orbx_search_by_projection_kf_device", "orbx_search_for_initialization",
     "orbx_search_by_bow", "orbx_search_by_bow_device", "orbx_vocabulary_create", "orbx_vocabulary_destroy", "orbx_compute_bow", "orbx_compute_bow_device",
-    "orbx_bind_thread_to_device",
+    "orbx_bind_thread_to_device", "orbx_is_in_frustum",
 ]
 GRAY8, BGR8, RGB8, BGRA8, RGBA8 = range(5)
 
@@ -66,6 +66,16 @@ class OrbxLocalPointsQuery(C.Structure):
     _fields_ = [("cur_frame", C.c_int), ("n_points", C.c_int), ("in_view", C.c_void_p), ("proj_xy_xr", C.c_void_p),
                 ("scale_level", C.c_void_p), ("view_cos", C.c_void_p), ("mp_desc", C.c_void_p), ("mp_obs", C.c_void_p),
                 ("cur_obs", C.c_void_p)]
+
+
+class OrbxFrustumQuery(C.Structure):
+    _fields_ = [("n_points", C.c_int), ("consider", C.c_void_p), ("world_pos", C.c_void_p), ("normal", C.c_void_p),
+                ("min_dist", C.c_void_p), ("max_dist", C.c_void_p), ("Tcw", C.c_float * 16)]
+
+
+class OrbxFrustumResult(C.Structure):
+    _fields_ = [("n", C.c_int), ("n_in_view", C.c_int), ("in_view", C.c_void_p), ("proj_xy_xr", C.c_void_p),
+                ("scale_level", C.c_void_p), ("view_cos", C.c_void_p)]
 
 
 class OrbxKeyframeProjectionQuery(C.Structure):
@@ -161,6 +171,8 @@ def lib():
     L.orbx_search_by_projection_fetch.argtypes = [vp, i, C.POINTER(OrbxProjectionQuery), C.POINTER(OrbxProjectionResult)]
     L.orbx_search_local_points.argtypes = [vp, i, C.POINTER(OrbxLocalPointsQuery), f, f, i, C.POINTER(OrbxProjectionResult)]
     L.orbx_search_local_points_device.argtypes = [vp, i, C.POINTER(OrbxLocalPointsQuery), f, f, i]
+    L.orbx_is_in_frustum.argtypes = [vp, i, C.POINTER(OrbxFrustumQuery), C.POINTER(C.c_float), f, C.POINTER(C.c_float), f, f,
+                                     C.POINTER(OrbxFrustumResult)]
     L.orbx_search_by_projection_kf.argtypes = [vp, i, C.POINTER(OrbxKeyframeProjectionQuery), C.POINTER(C.c_float), f, i, i,
                                                C.POINTER(OrbxProjectionResult)]
     L.orbx_search_by_projection_kf_device.argtypes = [vp, i, C.POINTER(OrbxKeyframeProjectionQuery), C.POINTER(C.c_float), f, i, i]

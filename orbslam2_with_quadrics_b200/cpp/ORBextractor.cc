@@ -218,6 +218,35 @@ int ORBextractor::SearchByProjection(const std::vector<float>& lastWorldPos, con
     return r.nmatches;
 }
 
+int ORBextractor::IsInFrustum(const std::vector<unsigned char>& consider, const std::vector<float>& worldPos,
+                              const std::vector<float>& normals, const std::vector<float>& minDistance,
+                              const std::vector<float>& maxDistance, const cv::Mat& Tcw, const cv::Mat& mK, float mbf,
+                              const float bounds[4], float logScaleFactor, float viewingCosLimit, std::vector<unsigned char>& inView,
+                              std::vector<float>& projXYXR, std::vector<int>& scaleLevel, std::vector<float>& viewCos)
+{
+    const size_t n = minDistance.size();
+    if ((!consider.empty() && consider.size() != n) || worldPos.size() != 3 * n || normals.size() != 3 * n || maxDistance.size() != n)
+        throw std::runtime_error("ORBextractor (orbx): IsInFrustum needs one entry per map point in every array");
+    orbx_frustum_query q;
+    q.n_points = (int)n;
+    q.consider = consider.empty() ? 0 : consider.data();
+    q.world_pos = worldPos.data();
+    q.normal = normals.data();
+    q.min_dist = minDistance.data();
+    q.max_dist = maxDistance.data();
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) q.Tcw[4 * r + c] = Tcw.at<float>(r, c);
+    const float K4[4] = {mK.at<float>(0, 0), mK.at<float>(1, 1), mK.at<float>(0, 2), mK.at<float>(1, 2)};
+    orbx_frustum_result r;
+    int rc = orbx_is_in_frustum(handle_, 1, &q, K4, mbf, bounds, logScaleFactor, viewingCosLimit, &r);
+    if (rc != ORBX_OK) orbx_throw(handle_, rc, "orbx_is_in_frustum");
+    inView.assign(r.in_view, r.in_view + n);
+    projXYXR.assign(r.proj_xy_xr, r.proj_xy_xr + 3 * n);
+    scaleLevel.assign(r.scale_level, r.scale_level + n);
+    viewCos.assign(r.view_cos, r.view_cos + n);
+    return r.n_in_view;
+}
+
 int ORBextractor::SearchLocalPoints(const std::vector<unsigned char>& inView, const std::vector<float>& projXYXR,
                                     const std::vector<int>& scaleLevel, const std::vector<float>& viewCos,
                                     const std::vector<unsigned char>& descriptors, const std::vector<int>& observations,

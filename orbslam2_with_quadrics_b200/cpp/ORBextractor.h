@@ -92,6 +92,18 @@ public:
                            const cv::Mat& TcwCurrent, const cv::Mat& TcwLast, const cv::Mat& mK, float mbf, float mb, float th,
                            bool bMono, bool checkOrientation, bool useStereo, std::vector<int>& matchedLast);
 
+    // Frame::isInFrustum(MapPoint*, viewingCosLimit) (reference src/Frame.cc:269-325, with MapPoint::PredictScale) for the whole
+    // local map on the GPU: the loop of Tracking::SearchLocalPoints (src/Tracking.cc:1165-1178).  Per map point: consider = it
+    // is handed to isInFrustum at all (not seen in this frame, !isBad()), world position and mean viewing direction (3 floats
+    // each), mfMinDistance and mfMaxDistance.  Tcw = F.mTcw (4 x 4 CV_32F), K = F.mK, bounds = {mnMinX, mnMaxX, mnMinY, mnMaxY}.
+    // Outputs are SearchLocalPoints' inputs: mbTrackInView, (mTrackProjX, mTrackProjY, mTrackProjXR), mnTrackScaleLevel,
+    // mTrackViewCos.  Returns nToMatch.  Reads nothing of the last operator(): may be called before it.
+    int IsInFrustum(const std::vector<unsigned char>& consider, const std::vector<float>& worldPos, const std::vector<float>& normals,
+                    const std::vector<float>& minDistance, const std::vector<float>& maxDistance, const cv::Mat& Tcw,
+                    const cv::Mat& mK, float mbf, const float bounds[4], float logScaleFactor, float viewingCosLimit,
+                    std::vector<unsigned char>& inView, std::vector<float>& projXYXR, std::vector<int>& scaleLevel,
+                    std::vector<float>& viewCos);
+
     // ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, th) (reference src/ORBmatcher.cc:45-129,
     // the matcher of Tracking::SearchLocalPoints) on the GPU; `this` is F.mpORBextractorLeft as above.  Per map point: the
     // tracking fields Frame::isInFrustum left on it -- inView = mbTrackInView && !isBad(), (mTrackProjX, mTrackProjY,

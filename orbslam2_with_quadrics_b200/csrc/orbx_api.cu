@@ -101,6 +101,9 @@ struct orbx_handle {
     size_t sp_bytes;
     int *d_sp_out, *h_sp_out;  // [match nq * kpf][stats nq * 2]
     size_t sp_out_ints;
+    // Frame::isInFrustum (orbx_is_in_frustum; staging grows on demand, independent of the image geometry)
+    unsigned char *d_fr, *h_fr;
+    size_t fr_bytes;
     // ComputeBoW (orbx_compute_bow; allocated on first use): [leaf B*kpf][nid B*kpf][word ids B*kpf][fv nodes B*kpf]
     // [fv features B*kpf][counts 2B][frames B] as 32-bit words, and the word values as doubles
     unsigned *d_bow, *h_bow;
@@ -871,6 +874,7 @@ int orbx_create(const orbx_config* cfg, orbx_handle** out) {
     h->d_color = h->h_color = 0; h->color_bytes = 0;
     h->d_sp = h->h_sp = 0; h->sp_bytes = 0; h->d_sp_out = h->h_sp_out = 0; h->sp_out_ints = 0;
     h->d_bow = h->h_bow = 0; h->d_bow_val = h->h_bow_val = 0;
+    h->d_fr = h->h_fr = 0; h->fr_bytes = 0;
     h->timing = false; h->ev_created = false; h->ev_head = 0; h->ev_pending = 0;
     memset(h->stage_ms, 0, sizeof h->stage_ms);
     memset(h->stage_launches, 0, sizeof h->stage_launches);
@@ -923,6 +927,7 @@ int orbx_destroy(orbx_handle* h) {
     cudaStreamSynchronize(h->h2d_stream);
     cudaStreamSynchronize(h->d2h_stream);
     free_geometry(h);
+    cudaFree(h->d_fr); cudaFreeHost(h->h_fr);
     if (h->ev_created)
         for (int i = 0; i < kTimingRing; ++i)
             for (int s = 0; s <= ST_COUNT; ++s) cudaEventDestroy(h->ev[i][s]);
@@ -1641,6 +1646,114 @@ struct orbx_vocabulary {
     uint8_t* d_desc;
     double* d_weight;
 };
+
+// Frame::isInFrustum (src/Frame.cc:269-325) + MapPoint::PredictScale (src/MapPoint.cc:402-417) over lists of map points.
+namespace {
+// MapPoint::PredictScale's level for a ratio, evaluated with THIS process's libm -- the one the reference would call
+int frustum_level_host(float ratio, float lsf, int nlevels) {
+    volatile float l = logf(ratio);                    // `log(ratio)` with a float argument under `using namespace std` (:410)
+    volatile float qv = l / lsf;
+    const float c = ceilf(qv);
+    if (!(c == c) || c > 3.0e38f || c < -3.0e38f) return 0;      // NaN / inf -> int is undefined in the reference (x86: INT_MIN -> 0)
+    return c < 0.f ? 0 : (c >= (float)nlevels ? nlevels - 1 : (int)c);
+}
+// T[k] = the smallest positive finite float whose level reaches k (bisection over the bit pattern; levels are monotone in the ratio)
+void frustum_thresholds(float lsf, int nlevels, float* T) {
+    T[0] = 0.f;
+    for (int k = 1; k < nlevels; ++k) {
+        uint32_t lo = 1u, hi = 0x7f7fffffu;            // level(lo) < k <= level(hi) is the invariant
+        float f;
+        memcpy(&f, &hi, 4);
+        if (frustum_level_host(f, lsf, nlevels) < k) { const uint32_t inf = 0x7f800000u; memcpy(&T[k], &inf, 4); continue; }
+        memcpy(&f, &lo, 4);
+        if (frustum_level_host(f, lsf, nlevels) >= k) { memcpy(&T[k], &lo, 4); continue; }
+        while (hi - lo > 1u) {
+            const uint32_t mid = lo + (hi - lo) / 2u;
+            memcpy(&f, &mid, 4);
+            if (frustum_level_host(f, lsf, nlevels) >= k) hi = mid; else lo = mid;
+        }
+        memcpy(&T[k], &hi, 4);
+    }
+}
+}  // namespace
+
+int orbx_is_in_frustum(orbx_handle* h, int nq, const orbx_frustum_query* q, const float* K4, float mbf, const float* bounds,
+                       float log_scale_factor, float viewing_cos_limit, orbx_frustum_result* results) {
+    if (!h || !q || !K4 || !bounds || !results || nq < 1 || nq > 65535 || !(log_scale_factor > 0.f) || !(log_scale_factor < 3.0e38f))
+        return ORBX_ERR_BAD_ARGS;
+    size_t N = 0;
+    int max_n = 0;
+    for (int i = 0; i < nq; ++i) {
+        if (q[i].n_points < 0) return ORBX_ERR_BAD_ARGS;
+        if (q[i].n_points && (!q[i].world_pos || !q[i].normal || !q[i].min_dist || !q[i].max_dist)) return ORBX_ERR_BAD_ARGS;
+        N += (size_t)q[i].n_points;
+        if (q[i].n_points > max_n) max_n = q[i].n_points;
+    }
+    if (N > ((size_t)1 << 30)) return ORBX_ERR_BAD_ARGS;
+    CK(h, cudaSetDevice(h->cfg.device));
+    const size_t qb = (orbx::frustum_query_bytes() + 15) & ~(size_t)15, Np = (N + 15) & ~(size_t)15;
+    // [queries][world N x 3][normal N x 3][min N][max N][consider N] | [proj N x 3][level N][view cos N][in view N]
+    const size_t o_world = (size_t)nq * qb, o_norm = o_world + Np * 12, o_min = o_norm + Np * 12, o_max = o_min + Np * 4,
+                 o_cons = o_max + Np * 4, o_proj = o_cons + Np, o_lvl = o_proj + Np * 12, o_vc = o_lvl + Np * 4, o_in = o_vc + Np * 4,
+                 total = o_in + Np;
+    cudaStream_t st = h->stream;
+    CK(h, cudaStreamSynchronize(st));                                // the staging of a previous call is free
+    if (total > h->fr_bytes) {
+        cudaFree(h->d_fr); cudaFreeHost(h->h_fr); h->d_fr = h->h_fr = 0; h->fr_bytes = 0;
+        CK(h, cudaMalloc(&h->d_fr, total));
+        CK(h, cudaMallocHost(&h->h_fr, total));
+        h->fr_bytes = total;
+    }
+    size_t off = 0;
+    for (int i = 0; i < nq; ++i) {
+        const float* T = q[i].Tcw;
+        const float R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]}, t[3] = {T[3], T[7], T[11]};
+        float Ow[3];                                                 // mOw = -mRcw.t() * mtcw (:266): general gemm path, double products and sum
+        for (int r = 0; r < 3; ++r) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += (double)R[3 * k + r] * (double)t[k];
+            Ow[r] = (float)(s * -1.0);
+        }
+        const size_t n = (size_t)q[i].n_points;
+        orbx::frustum_fill_query(h->h_fr + (size_t)i * qb, R, t, Ow, (int)n, (int)off);
+        if (n) {
+            memcpy(h->h_fr + o_world + off * 12, q[i].world_pos, n * 12);
+            memcpy(h->h_fr + o_norm + off * 12, q[i].normal, n * 12);
+            memcpy(h->h_fr + o_min + off * 4, q[i].min_dist, n * 4);
+            memcpy(h->h_fr + o_max + off * 4, q[i].max_dist, n * 4);
+            if (q[i].consider) memcpy(h->h_fr + o_cons + off, q[i].consider, n);
+            else memset(h->h_fr + o_cons + off, 1, n);
+        }
+        off += n;
+    }
+    float thr[ORBX_MAXL];
+    frustum_thresholds(log_scale_factor, h->cfg.nlevels, thr);
+    if (N) {
+        CK(h, cudaMemcpyAsync(h->d_fr, h->h_fr, o_proj, cudaMemcpyHostToDevice, st));
+        CK(h, orbx::launch_frustum(nq, max_n, h->d_fr, K4, bounds, mbf, viewing_cos_limit, h->cfg.nlevels, thr, h->d_fr + o_cons,
+                                   reinterpret_cast<const float*>(h->d_fr + o_world), reinterpret_cast<const float*>(h->d_fr + o_norm),
+                                   reinterpret_cast<const float*>(h->d_fr + o_min), reinterpret_cast<const float*>(h->d_fr + o_max),
+                                   h->d_fr + o_in, reinterpret_cast<float*>(h->d_fr + o_proj), reinterpret_cast<int*>(h->d_fr + o_lvl),
+                                   reinterpret_cast<float*>(h->d_fr + o_vc), st));
+        ++h->launches;
+        CK(h, cudaMemcpyAsync(h->h_fr + o_proj, h->d_fr + o_proj, total - o_proj, cudaMemcpyDeviceToHost, st));
+        CK(h, cudaStreamSynchronize(st));
+    }
+    off = 0;
+    for (int i = 0; i < nq; ++i) {
+        const size_t n = (size_t)q[i].n_points;
+        results[i].n = (int)n;
+        results[i].in_view = h->h_fr + o_in + off;
+        results[i].proj_xy_xr = reinterpret_cast<const float*>(h->h_fr + o_proj) + off * 3;
+        results[i].scale_level = reinterpret_cast<const int32_t*>(h->h_fr + o_lvl) + off;
+        results[i].view_cos = reinterpret_cast<const float*>(h->h_fr + o_vc) + off;
+        int c = 0;
+        for (size_t k = 0; k < n; ++k) c += results[i].in_view[k];
+        results[i].n_in_view = c;
+        off += n;
+    }
+    return ORBX_OK;
+}
 
 int orbx_vocabulary_create(int device, int n_nodes, int L, const int32_t* child_start, const int32_t* child_items,
                            const uint8_t* node_desc, const double* node_weight, const int32_t* node_word, orbx_vocabulary** out) {

@@ -3531,6 +3531,9 @@ cudaError_t launch_fast(const OrbxPlan* d_plan, const OrbxPlan& hp, const void* 
     // other half-batch's stream to co-run
     static const int env_cap = getenv("ORBX_FAST_CTAS_PER_SM") ? atoi(getenv("ORBX_FAST_CTAS_PER_SM")) : 0;
     if (env_cap > 0 && env_cap < per_sm_eff) per_sm_eff = env_cap;
+    // (several waves of shorter-lived CTAs -- 2 / 4 / 8 x this grid, so that the block scheduler can slip the CTAs of other
+    // streams' kernels in between -- measured 1.309 / 1.318 / 1.348 ms per 64 x 1080p against 1.308 with two handles: the
+    // streams share issue capacity, not residency)
     const long long cap = (long long)num_sms * per_sm_eff;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
@@ -3819,6 +3822,105 @@ cudaError_t launch_stereo(const OrbxPlan* d_plan, const OrbxPlan& hp, int num_sm
     }
     return launch_k(stereo_filter_kernel, dim3((unsigned)npairs), dim3(1024), smem, st, d_plan, countsL, d_pairs, u_right, depth,
                     (const int*)sad);
+}
+
+// =====================================================================================
+// Frame::isInFrustum(MapPoint*, viewingCosLimit) (reference src/Frame.cc:269-325) with MapPoint::PredictScale(dist, Frame*)
+// (src/MapPoint.cc:402-417) and GetMin/MaxDistanceInvariance (:373-383): the producer of the tracking fields that
+// ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th) consumes (Tracking::SearchLocalPoints, src/Tracking.cc:1165-1194).
+// One thread per (query, map point); every float / double operation is the reference's, individually rounded:
+//   Pc = mRcw * P + mtcw        cv::gemm's 3x3 path: float products and sums, the "+ C" in double (as sp_project)
+//   invz = 1.0f / PcZ           float division (the matchers use 1.0 / z in double; this function does not)
+//   dist = cv::norm(P - mOw)    squares and sum in double, sqrt, rounded to float
+//   viewCos = PO.dot(Pn)/dist   Mat::dot: float products accumulated in double; double / float -> double -> float
+//   PredictScale                ratio = mfMaxDistance / dist in float; ceil(logf(ratio) / mfLogScaleFactor) goes through the
+//                               HOST's libm, so the host hands over, per level k, the smallest float ratio T[k] whose quotient
+//                               reaches k (found by bisection over the float's bits with the host's own logf: the function is
+//                               monotone), and the level is the number of thresholds the ratio reaches.  A non-finite or
+//                               non-positive ratio (the reference then converts inf / NaN to int: undefined, INT_MIN -> 0 on
+//                               x86) gives level 0.
+// =====================================================================================
+struct FrustumParams {
+    float fx, fy, cx, cy, min_x, max_x, min_y, max_y, mbf, cos_limit;
+    int nlevels;
+    float T[ORBX_MAXL];                   // T[k], k = 1 .. nlevels - 1
+};
+struct FrustumQuery {
+    float R[9], t[3], Ow[3];
+    int n, off;
+};
+
+__global__ void __launch_bounds__(256)
+frustum_kernel(const FrustumParams P, const FrustumQuery* __restrict__ queries, const uint8_t* __restrict__ consider,
+               const float* __restrict__ world, const float* __restrict__ normal, const float* __restrict__ min_dist,
+               const float* __restrict__ max_dist, uint8_t* __restrict__ in_view, float* __restrict__ proj, int* __restrict__ level,
+               float* __restrict__ view_cos) {
+    const FrustumQuery& q = queries[blockIdx.y];
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= q.n) return;
+    const size_t i = (size_t)q.off + k;
+    in_view[i] = 0;                                                              // pMP->mbTrackInView = false (:271)
+    proj[3 * i] = proj[3 * i + 1] = proj[3 * i + 2] = 0.f;
+    level[i] = 0;
+    view_cos[i] = 0.f;
+    if (!consider[i]) return;
+    const float wx = world[3 * i], wy = world[3 * i + 1], wz = world[3 * i + 2];
+    float c3[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {                                                // (:277)
+        const float t0 = __fadd_rn(__fadd_rn(__fmul_rn(q.R[3 * r], wx), __fmul_rn(q.R[3 * r + 1], wy)), __fmul_rn(q.R[3 * r + 2], wz));
+        c3[r] = __double2float_rn(__dadd_rn((double)t0, (double)q.t[r]));
+    }
+    if (c3[2] < 0.0f) return;                                                    // (:283)
+    const float invz = __fdiv_rn(1.0f, c3[2]);                                   // (:287)
+    const float u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, c3[0]), invz), P.cx);
+    const float v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, c3[1]), invz), P.cy);
+    if (u < P.min_x || u > P.max_x) return;                                      // (:291-294) NaN passes, as in the reference
+    if (v < P.min_y || v > P.max_y) return;
+    const float maxd = __fmul_rn(1.2f, max_dist[i]), mind = __fmul_rn(0.8f, min_dist[i]);      // (src/MapPoint.cc:373-383)
+    const float px = __fsub_rn(wx, q.Ow[0]), py = __fsub_rn(wy, q.Ow[1]), pz = __fsub_rn(wz, q.Ow[2]);     // (:299)
+    const double dx = (double)px, dy = (double)py, dz = (double)pz;
+    const float dist = __double2float_rn(__dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz))));
+    if (dist < mind || dist > maxd) return;                                      // (:302-303)
+    const double dot = __dadd_rn(__dadd_rn(__dmul_rn(dx, (double)normal[3 * i]), __dmul_rn(dy, (double)normal[3 * i + 1])),
+                                 __dmul_rn(dz, (double)normal[3 * i + 2]));
+    const float vc = __double2float_rn(__ddiv_rn(dot, (double)dist));            // (:308)
+    if (vc < P.cos_limit) return;                                                // (:310-311)
+    const float ratio = __fdiv_rn(max_dist[i], dist);                            // (src/MapPoint.cc:407)
+    int lvl = 0;
+    if (ratio > 0.f && ratio <= 3.402823466e38f)                                 // finite and positive
+        for (int j = 1; j < P.nlevels; ++j) lvl += ratio >= P.T[j];
+    in_view[i] = 1;                                                              // (:317-322)
+    proj[3 * i] = u;
+    proj[3 * i + 1] = v;
+    proj[3 * i + 2] = __fsub_rn(u, __fmul_rn(P.mbf, invz));
+    level[i] = lvl;
+    view_cos[i] = vc;
+}
+
+size_t frustum_query_bytes() { return sizeof(FrustumQuery); }
+void frustum_fill_query(void* dst, const float* Rcw, const float* tcw, const float* Ow, int n, int off) {
+    FrustumQuery q;
+    memcpy(q.R, Rcw, sizeof q.R);
+    memcpy(q.t, tcw, sizeof q.t);
+    memcpy(q.Ow, Ow, sizeof q.Ow);
+    q.n = n;
+    q.off = off;
+    memcpy(dst, &q, sizeof q);
+}
+cudaError_t launch_frustum(int nq, int max_n, const void* d_queries, const float* K4, const float* bounds, float mbf, float cos_limit,
+                           int nlevels, const float* thresholds, const uint8_t* consider, const float* world, const float* normal,
+                           const float* min_dist, const float* max_dist, uint8_t* in_view, float* proj, int* level, float* view_cos,
+                           cudaStream_t st) {
+    if (nq < 1 || max_n < 1) return cudaSuccess;
+    FrustumParams P;
+    P.fx = K4[0]; P.fy = K4[1]; P.cx = K4[2]; P.cy = K4[3];
+    P.min_x = bounds[0]; P.max_x = bounds[1]; P.min_y = bounds[2]; P.max_y = bounds[3];
+    P.mbf = mbf; P.cos_limit = cos_limit; P.nlevels = nlevels;
+    for (int k = 0; k < ORBX_MAXL; ++k) P.T[k] = k < nlevels ? thresholds[k] : 0.f;
+    frustum_kernel<<<dim3((unsigned)((max_n + 255) / 256), (unsigned)nq), 256, 0, st>>>(
+        P, reinterpret_cast<const FrustumQuery*>(d_queries), consider, world, normal, min_dist, max_dist, in_view, proj, level, view_cos);
+    return cudaGetLastError();
 }
 
 }  // namespace orbx

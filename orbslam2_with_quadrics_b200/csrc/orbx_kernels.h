@@ -60,6 +60,12 @@ cudaError_t launch_stereo(const OrbxPlan* d_plan, const OrbxPlan& hp, int num_sm
                           const uint8_t* descL, const int* countsL, const uint8_t* pyrR, const float* kpR, const uint8_t* descR,
                           const int* countsR, const int* d_pairs, int npairs, float mbf, float mb, float* u_right, float* depth,
                           int* sad, int* row_start, uint16_t* bucket, cudaStream_t st);
+size_t frustum_query_bytes();
+void frustum_fill_query(void* dst, const float* Rcw, const float* tcw, const float* Ow, int n, int off);
+cudaError_t launch_frustum(int nq, int max_n, const void* d_queries, const float* K4, const float* bounds, float mbf, float cos_limit,
+                           int nlevels, const float* thresholds, const uint8_t* consider, const float* world, const float* normal,
+                           const float* min_dist, const float* max_dist, uint8_t* in_view, float* proj, int* level, float* view_cos,
+                           cudaStream_t st);
 size_t search_projection_query_bytes();
 void search_projection_fill_query(void* dst, const float* Rcw, const float* tcw, int n_last, int frame, int fwd, int bwd);
 cudaError_t launch_search_projection(const OrbxPlan* d_plan, const OrbxPlan& hp, int mode, int nq, const void* d_queries, const float* K4,

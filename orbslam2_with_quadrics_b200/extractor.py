@@ -328,6 +328,42 @@ class ORBextractor:
         del keep
         return out
 
+    # ---------------------------------------------------------------- Frame::isInFrustum over the local map
+    def is_in_frustum(self, queries, K4, mbf: float, bounds, log_scale_factor: float, cos_limit: float = 0.5):
+        """(src/Frame.cc:269-325 with MapPoint::PredictScale, src/MapPoint.cc:402-417; Tracking::SearchLocalPoints) for each query:
+        dicts with consider (uint8 or None), world (n x 3), normal (n x 3), min_dist, max_dist (mfMinDistance / mfMaxDistance), Tcw.
+        Returns [(in_view uint8[n], proj float32[n, 3] = (mTrackProjX, mTrackProjY, mTrackProjXR), scale_level int32[n],
+        view_cos float32[n])] -- the inputs of search_local_points."""
+        qs = (_capi.OrbxFrustumQuery * len(queries))()
+        keep = []
+        for q, d in zip(qs, queries):
+            a = dict(world=np.ascontiguousarray(d["world"], np.float32).reshape(-1, 3), normal=np.ascontiguousarray(d["normal"], np.float32).reshape(-1, 3),
+                     mn=np.ascontiguousarray(d["min_dist"], np.float32), mx=np.ascontiguousarray(d["max_dist"], np.float32))
+            co = None if d.get("consider") is None else np.ascontiguousarray(d["consider"], np.uint8)
+            keep.append((a, co))
+            q.n_points = len(a["mn"])
+            q.consider = None if co is None else co.ctypes.data
+            q.world_pos, q.normal, q.min_dist, q.max_dist = a["world"].ctypes.data, a["normal"].ctypes.data, a["mn"].ctypes.data, a["mx"].ctypes.data
+            q.Tcw = (C.c_float * 16)(*np.asarray(d["Tcw"], np.float32).reshape(16).tolist())
+        res = (_capi.OrbxFrustumResult * len(queries))()
+        k4 = (C.c_float * 4)(*[float(v) for v in K4])
+        bd = (C.c_float * 4)(*[float(v) for v in bounds])
+        check(self._L.orbx_is_in_frustum(self._h, len(queries), qs, k4, mbf, bd, log_scale_factor, cos_limit, res), self._h)
+        out = []
+        for r in res:
+            n = r.n
+            if n == 0:
+                out.append((np.zeros(0, np.uint8), np.zeros((0, 3), np.float32), np.zeros(0, np.int32), np.zeros(0, np.float32)))
+                continue
+            iv = np.ctypeslib.as_array(C.cast(r.in_view, C.POINTER(C.c_uint8)), shape=(n,)).copy()
+            pj = np.ctypeslib.as_array(C.cast(r.proj_xy_xr, C.POINTER(C.c_float)), shape=(n, 3)).copy()
+            lv = np.ctypeslib.as_array(C.cast(r.scale_level, C.POINTER(C.c_int32)), shape=(n,)).copy()
+            vc = np.ctypeslib.as_array(C.cast(r.view_cos, C.POINTER(C.c_float)), shape=(n,)).copy()
+            assert int(iv.sum()) == r.n_in_view
+            out.append((iv, pj, lv, vc))
+        del keep
+        return out
+
     # ---------------------------------------------------------------- ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist)
     def search_by_projection_kf(self, queries, K4, th: float, orb_dist: int, check_orientation: bool = True):
         """(src/ORBmatcher.cc:1472-1599, Tracking::Relocalization) for each query: dicts with cur_frame, search (uint8: good, not yet

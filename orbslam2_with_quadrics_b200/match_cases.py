@@ -203,3 +203,45 @@ def make_initial_frame(rng, xy_un2, octave2, angle2, desc2, n1, flip_bits=10, sh
     angle1[wild] = rng.uniform(0, 360, int(wild.sum())).astype(f32)
     angle1 = np.mod(angle1, f32(360.0)).astype(f32)
     return dict(xy_un1=xy1, octave1=octave1, angle1=angle1, desc1=desc1, prev_matched=xy1.copy())
+
+
+def make_frustum_points(rng, K4, bounds, Tcw, n_points, sf, extreme_frac=0.02):
+    """Local map points for Frame::isInFrustum (src/Frame.cc:269-325, Tracking::SearchLocalPoints): positions spread well beyond
+    the image (so the bounds test rejects some), a few behind the camera, mean viewing directions from head-on to grazing (the
+    0.5 cosine limit cuts through them), scale-invariance ranges placed so that MapPoint::PredictScale lands on every level and
+    the distance test rejects some, plus a few extreme values (ranges of zero width, huge / tiny distances, points already seen)."""
+    fx, fy, cx, cy = [float(v) for v in K4]
+    minx, maxx, miny, maxy = [float(v) for v in bounds]
+    Tc = np.asarray(Tcw, np.float64).reshape(4, 4)
+    Rwc, twc = Tc[:3, :3].T, -Tc[:3, :3].T @ Tc[:3, 3]
+    z = rng.uniform(0.5, 15.0, n_points)
+    px = rng.uniform(minx - 0.15 * (maxx - minx), maxx + 0.15 * (maxx - minx), n_points)
+    py = rng.uniform(miny - 0.15 * (maxy - miny), maxy + 0.15 * (maxy - miny), n_points)
+    Xc = np.stack([(px - cx) / fx * z, (py - cy) / fy * z, z], 1)
+    behind = rng.random(n_points) < 0.04
+    Xc[behind] *= -1.0
+    world = (Xc @ Rwc.T + twc).astype(f32)
+    PO = world.astype(np.float64) - twc
+    dist = np.linalg.norm(PO, axis=1)
+    # mean viewing direction: the ray rotated by a random angle in [0, 80] degrees about a random axis
+    ray = PO / np.maximum(dist, 1e-9)[:, None]
+    axis = rng.normal(0, 1, (n_points, 3))
+    axis -= (axis * ray).sum(1, keepdims=True) * ray
+    axis /= np.maximum(np.linalg.norm(axis, axis=1, keepdims=True), 1e-9)
+    ang = np.deg2rad(rng.uniform(0, 80, n_points))
+    normal = (ray * np.cos(ang)[:, None] + axis * np.sin(ang)[:, None]).astype(f32)
+    # mfMaxDistance = dist * scale^(level + jitter): PredictScale = ceil(log(max / dist) / log(scale)) spreads over all levels (+- 2 beyond)
+    nl = len(sf)
+    lvl = rng.integers(-2, nl + 2, n_points)
+    jitter = rng.uniform(-0.999, 0.0, n_points)
+    s1 = float(sf[1])
+    max_dist = (dist * np.power(s1, lvl + jitter)).astype(f32)
+    min_dist = (max_dist / f32(sf[-1]) * rng.uniform(0.6, 1.1, n_points)).astype(f32)
+    on_boundary = rng.random(n_points) < 0.05                       # ratios that sit exactly on a power of the scale factor
+    max_dist[on_boundary] = (dist[on_boundary].astype(f32) * np.power(f32(s1), rng.integers(0, nl, int(on_boundary.sum())).astype(f32))).astype(f32)
+    ext = rng.random(n_points) < extreme_frac
+    k = int(ext.sum())
+    max_dist[ext] = rng.choice(np.array([0.0, 1e-30, 1e30, 3e38], f32), k)
+    min_dist[ext] = rng.choice(np.array([0.0, 1e-30, 1e-3], f32), k)
+    consider = (rng.random(n_points) >= 0.1).astype(np.uint8)       # 0: already seen in this frame / bad (src/Tracking.cc:1169-1172)
+    return dict(consider=consider, world=world, normal=normal, min_dist=min_dist, max_dist=max_dist)

@@ -180,6 +180,34 @@ def key(case, check):
                                               "bMono" if case[5] else "bStereo", int(check))
 
 
+# Frame::isInFrustum over the local map (Tracking::SearchLocalPoints, src/Tracking.cc:1165-1178, viewingCosLimit 0.5):
+# (seed, mvpLocalMapPoints.size(), viewingCosLimit, mbf)
+FRUSTUM_CASES = [(1, 3000, 0.5, 40.0), (2, 5000, 0.5, 0.0), (3, 800, 0.8, 386.1448), (4, 50, 0.5, 40.0), (5, 6000, 0.2, 47.9)]
+
+
+def frustum_scenario(cf, seed, n_points):
+    rng = np.random.default_rng(5000 + seed)
+    Tc = mc.pose(rng, scale_r=0.3, t=(0.3, -0.2, 0.5))
+    pts = mc.make_frustum_points(rng, K_TUM1, cf["bounds"], Tc, n_points, cf["sf"])
+    return dict(**pts, Tcw=Tc, K4=K_TUM1, bounds=cf["bounds"], log_scale_factor=kf_log_scale(cf), nlevels=cf["nlevels"])
+
+
+def frustum_digest(sc, in_view, proj, level, vcos):
+    ins = hashlib.sha256()
+    for k in ("consider", "world", "normal", "min_dist", "max_dist", "Tcw"):
+        ins.update(np.ascontiguousarray(sc[k]).tobytes())
+    out = hashlib.sha256()
+    out.update(np.ascontiguousarray(in_view, np.uint8).tobytes())
+    out.update(np.ascontiguousarray(proj, np.float32).tobytes())
+    out.update(np.ascontiguousarray(level, np.int32).tobytes())
+    out.update(np.ascontiguousarray(vcos, np.float32).tobytes())
+    return {"in_view": int(np.asarray(in_view).sum()), "inputs_sha256": ins.hexdigest(), "fields_sha256": out.hexdigest()}
+
+
+def frustum_key(case):
+    return "frustum/seed%d/n%d/cos%g/mbf%g" % case
+
+
 if __name__ == "__main__":
     from oracle import stereo_oracle
     stereo_oracle.ref_build()
@@ -213,4 +241,9 @@ if __name__ == "__main__":
         n, m, prev = match_oracle.ref_search_for_initialization(sf=cf["sf"], nnratio=case[2], check_orientation=case[3], window=case[4], **sc)
         out[init_key(case)] = init_digest(sc, n, m, prev)
         print(init_key(case), n)
+    for case in FRUSTUM_CASES:
+        sc = frustum_scenario(cf, *case[:2])
+        r = match_oracle.ref_is_in_frustum(cos_limit=case[2], mbf=case[3], **sc)
+        out[frustum_key(case)] = frustum_digest(sc, *r)
+        print(frustum_key(case), out[frustum_key(case)]["in_view"], sorted(set(r[2][r[0] > 0].tolist())))
     json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "match_golden.json"), "w"), indent=1, sort_keys=True)

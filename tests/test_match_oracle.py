@@ -192,3 +192,21 @@ def test_search_for_initialization_stealing_is_exercised(current_frame):
         if ds and min(ds)[0] <= mo.TH_LOW and min(ds)[1] in owners and owners[min(ds)[1]] > i1:
             stolen += 1
     assert stolen > 0
+
+
+# ----------------------------------------------------------------------------- Frame::isInFrustum (src/Frame.cc:269-325)
+@pytest.mark.parametrize("case", mmg.FRUSTUM_CASES)
+def test_is_in_frustum_restatement_matches_reference_lines_and_golden(case, current_frame):
+    sc = mmg.frustum_scenario(current_frame, *case[:2])
+    r1 = match_oracle.is_in_frustum(cos_limit=case[2], mbf=case[3], **sc)
+    assert mmg.frustum_digest(sc, *r1) == GOLD[mmg.frustum_key(case)]
+    if match_oracle.ref_has("matchref_is_in_frustum"):
+        r2 = match_oracle.ref_is_in_frustum(cos_limit=case[2], mbf=case[3], **sc)
+        for a, b in zip(r1, r2):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8))          # floats by their bits
+    in_view, proj, level, vcos = r1
+    assert not np.any(in_view[sc["consider"] == 0])                              # skipped points are never marked (src/Tracking.cc:1169-1172)
+    if case[1] >= 800:
+        assert 0.1 * case[1] < int(in_view.sum()) < 0.6 * case[1]               # every rejection reason removes something
+        assert set(level[in_view > 0].tolist()) == set(range(current_frame["nlevels"]))
+        assert float(vcos[in_view > 0].min()) < case[2] + 0.05                  # the cosine limit cuts through the scenario
