@@ -623,7 +623,7 @@ def predict_scale(max_dist, dist, log_scale_factor, nlevels) -> int:
     """MapPoint::PredictScale(currentDist, Frame*) (src/MapPoint.cc:402-417): ratio = mfMaxDistance / dist in float,
     ceil(logf(ratio) / mfLogScaleFactor), clamped to [0, nlevels - 1].  A non-finite quotient (the reference then converts
     inf / NaN to int, which is undefined; x86 yields INT_MIN -> 0) gives level 0."""
-    with np.errstate(divide="ignore", invalid="ignore"):
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
         ratio = f32(f32(max_dist) / f32(dist))
         q = f32(_logf(ratio) / f32(log_scale_factor))
     ns = int(math.ceil(float(q))) if np.isfinite(q) else 0
@@ -665,8 +665,9 @@ def is_in_frustum(consider, world, normal, min_dist, max_dist, Tcw, K4, mbf, bou
             v = f32(f32(f32(fy * pcy) * invz) + cy)
         if u < minx or u > maxx or v < miny or v > maxy:                       # (:291-294)
             continue
-        maxd = f32(f32(1.2) * f32(max_dist[i]))                                # GetMaxDistanceInvariance (src/MapPoint.cc:379-383)
-        mind = f32(f32(0.8) * f32(min_dist[i]))
+        with np.errstate(over="ignore", invalid="ignore"):
+            maxd = f32(f32(1.2) * f32(max_dist[i]))                            # GetMaxDistanceInvariance (src/MapPoint.cc:379-383)
+            mind = f32(f32(0.8) * f32(min_dist[i]))
         PO = (P - Ow).astype(f32)
         dist = f32(cv2.norm(PO))                                               # (:300)
         if dist < mind or dist > maxd:

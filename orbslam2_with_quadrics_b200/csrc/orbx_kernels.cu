@@ -3845,10 +3845,11 @@ struct FrustumParams {
     int nlevels;
     float T[ORBX_MAXL];                   // T[k], k = 1 .. nlevels - 1
 };
-struct FrustumQuery {
+struct FrustumQuery {                     // 80 bytes: the staging area holds them back to back at 16-byte granularity
     float R[9], t[3], Ow[3];
-    int n, off;
+    int n, off, pad[3];
 };
+static_assert(sizeof(FrustumQuery) % 16 == 0, "queries are staged as an array");
 
 __global__ void __launch_bounds__(256)
 frustum_kernel(const FrustumParams P, const FrustumQuery* __restrict__ queries, const uint8_t* __restrict__ consider,
@@ -3906,6 +3907,7 @@ void frustum_fill_query(void* dst, const float* Rcw, const float* tcw, const flo
     memcpy(q.Ow, Ow, sizeof q.Ow);
     q.n = n;
     q.off = off;
+    q.pad[0] = q.pad[1] = q.pad[2] = 0;
     memcpy(dst, &q, sizeof q);
 }
 cudaError_t launch_frustum(int nq, int max_n, const void* d_queries, const float* K4, const float* bounds, float mbf, float cos_limit,

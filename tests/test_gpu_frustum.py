@@ -87,17 +87,16 @@ def test_predict_scale_at_the_level_boundaries(sf, nl):
     k = rng.integers(-2, nl + 2, len(z))
     target = (np.float32(sf) ** k.astype(np.float32)).astype(np.float32)              # the ratio aimed at
     ulps = rng.integers(-6, 7, len(z))
-    ratio = (target.view(np.int32) + ulps).view(np.float32)
+    ratio = (target.view(np.int32) + ulps.astype(np.int32)).view(np.float32)
     max_dist = (ratio * z).astype(np.float32)
     wide = rng.random(len(z)) < 0.3
     max_dist[wide] = (z[wide] * np.exp(rng.uniform(-2, 4, int(wide.sum())))).astype(np.float32)
     max_dist[:6] = np.float32([0.0, -1.0, np.inf, np.nan, 3.0e38, 1e-42])
     min_dist = np.zeros_like(z)
-    max_dist_test = np.where(np.isfinite(max_dist) & (max_dist > 0), max_dist, max_dist)
-    q = dict(consider=None, world=world, normal=normal, min_dist=min_dist, max_dist=max_dist_test, Tcw=np.eye(4, dtype=np.float32))
+    q = dict(consider=None, world=world, normal=normal, min_dist=min_dist, max_dist=max_dist, Tcw=np.eye(4, dtype=np.float32))
     K4, bounds = (500.0, 500.0, 320.0, 240.0), (0.0, 640.0, 0.0, 480.0)
     (r,) = gx.is_in_frustum([q], K4, 40.0, bounds, lsf, 0.5)
-    want = match_oracle.is_in_frustum(None, world, normal, min_dist, max_dist_test, q["Tcw"], K4, 40.0, bounds, lsf, nl, 0.5)
+    want = match_oracle.is_in_frustum(None, world, normal, min_dist, max_dist, q["Tcw"], K4, 40.0, bounds, lsf, nl, 0.5)
     assert same_bits(r, want)
     inside = r[0] > 0                                    # dist <= 1.2 * max_dist
     assert inside.sum() > 3000 and set(r[2][inside].tolist()) == set(range(nl))
