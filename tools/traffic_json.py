@@ -17,6 +17,11 @@ def to_bytes(v, u):
     f = float(v.replace(",", ""))
     return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
 per = collections.OrderedDict()
+first = data[0][ki] if data else None
+for n_used, r in enumerate(data):
+    if n_used > 0 and r[ki] == first:            # the capture window ran into the next launch sequence: one sequence only
+        data = data[:n_used]
+        break
 for r in data:
     k = r[ki].split("(")[0].replace("void ", "").replace("orbx::", "")
     per[k] = per.get(k, 0.0) + to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw])
