@@ -311,3 +311,30 @@ def test_graph_replay_is_identical_and_survives_geometry_changes():
             kps, desc = gx(im)
             assert_same(kps, desc, ro)
     gx.close()
+
+
+@pytest.mark.parametrize("offset,pad", [(0, 0), (0, 5), (3, 0), (16, 1)])
+def test_level0_border_split_all_width_residues(offset, pad):
+    """pyr_level0_kernel copies interior 16-byte vectors in one set of CTAs and gives the vectors that touch the reflected
+    border to another (lane = (row, border vector)); which vectors are which depends on width mod 16 and on the alignment of
+    the caller's rows.  Every residue, with aligned (128-bit loads) and unaligned (funnel-shift) source rows, device-resident
+    input: the padded level-0 plane -- border included -- and level 1 made from it are the oracle's bytes."""
+    import torch
+    h = 80
+    for w in range(100, 116):
+        img = fr.cluttered_scene(w, h, 500 + w)
+        pitch = (w + 15) // 16 * 16 + pad
+        buf = torch.zeros(offset + h * pitch + 64, dtype=torch.uint8)
+        flat = buf.numpy()
+        flat[:] = 255                                             # bytes between the rows must never reach the plane
+        rows = flat[offset:offset + h * pitch].reshape(h, pitch)
+        rows[:, :w] = img
+        dev = buf.cuda()
+        gx = ORBextractor(100, 1.2, 2, 20, 7, max_batch=1, download_pyramid=False)
+        gx.extract_device(dev.data_ptr() + offset, 1, w, h, pitch, h * pitch)
+        ro = orb_oracle.ORBextractor(100, 1.2, 2, 20, 7)(img)
+        for l in range(2):
+            assert np.array_equal(gx.stage_dump(0, l, _capi.STAGE_PYRAMID), ro.pyramid[l]), (w, l)
+        (k, d), = gx.fetch_results(1)
+        assert_same(k, d, ro)
+        gx.close()
